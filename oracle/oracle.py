@@ -1,0 +1,90 @@
+"""ctypes binding of the CPU oracle (oracle/liboracle.so) -- TEST INFRASTRUCTURE ONLY.
+
+Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference leg may
+import this module.  The product path (dentist_b200) never does.
+"""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_LIB = None
+
+
+def build(force=False):
+    so = os.path.join(_HERE, "liboracle.so")
+    srcs = [os.path.join(_HERE, f) for f in os.listdir(_HERE) if f.endswith(".c")]
+    if force or not os.path.exists(so) or any(os.path.getmtime(s) > os.path.getmtime(so) for s in srcs):
+        subprocess.check_call(["make", "-C", _HERE, "-s", "-B", "liboracle.so"])
+    return so
+
+
+class OrcParams(C.Structure):
+    _fields_ = [(n, C.c_int32) for n in
+                ("k", "w", "h", "t", "tspace", "minlen", "cdiff", "xdrop", "wmax", "rounds", "self_", "poolmul")]
+
+
+class OrcBlock(C.Structure):
+    _fields_ = [("nreads", C.c_int32), ("off", C.c_void_p), ("bases", C.c_void_p), ("mask", C.c_void_p)]
+
+
+class OrcResult(C.Structure):
+    _fields_ = [("nla", C.c_int64), ("la", C.c_void_p), ("ntrace", C.c_int64), ("trace", C.c_void_p),
+                ("nhits", C.c_int64), ("nseeds", C.c_int64), ("next", C.c_int64)]
+
+
+LA_DTYPE = np.dtype([("tlen", "<i4"), ("diffs", "<i4"), ("abpos", "<i4"), ("bbpos", "<i4"),
+                     ("aepos", "<i4"), ("bepos", "<i4"), ("flags", "<u4"), ("aread", "<i4"),
+                     ("bread", "<i4"), ("toff", "<i4")])
+
+DEFAULTS = dict(k=14, w=6, h=35, t=32, tspace=100, minlen=500, cdiff=20, xdrop=300, wmax=62, rounds=3,
+                self_=0, poolmul=64)
+
+
+def lib():
+    global _LIB
+    if _LIB is None:
+        _LIB = C.CDLL(build())
+        _LIB.orc_align.restype = C.c_int
+        _LIB.orc_align.argtypes = [C.POINTER(OrcBlock), C.POINTER(OrcBlock), C.POINTER(OrcParams),
+                                   C.POINTER(OrcResult)]
+        _LIB.orc_free.argtypes = [C.POINTER(OrcResult)]
+    return _LIB
+
+
+def _block(off, bases, mask):
+    off = np.ascontiguousarray(off, dtype=np.int64)
+    bases = np.ascontiguousarray(bases, dtype=np.uint8)
+    keep = [off, bases]
+    b = OrcBlock(len(off) - 1, off.ctypes.data, bases.ctypes.data, None)
+    if mask is not None:
+        mask = np.ascontiguousarray(mask, dtype=np.uint8)
+        keep.append(mask)
+        b.mask = mask.ctypes.data
+    return b, keep
+
+
+def align(a_off, a_bases, b_off, b_bases, a_mask=None, b_mask=None, **params):
+    """Run the oracle.  Blocks are (offsets[nreads+1], bases uint8 0..3 concatenated).
+    Returns (la structured array, trace uint16 array, stats dict)."""
+    p = dict(DEFAULTS)
+    if "self" in params:
+        params["self_"] = params.pop("self")
+    p.update(params)
+    P = OrcParams(**p)
+    A, ka = _block(a_off, a_bases, a_mask)
+    B, kb = _block(b_off, b_bases, b_mask)
+    R = OrcResult()
+    rc = lib().orc_align(C.byref(A), C.byref(B), C.byref(P), C.byref(R))
+    if rc != 0:
+        raise RuntimeError("oracle failed: %d" % rc)
+    la = np.ctypeslib.as_array(C.cast(R.la, C.POINTER(C.c_uint8)), shape=(R.nla * LA_DTYPE.itemsize,)) \
+        .view(LA_DTYPE).copy() if R.nla else np.zeros(0, LA_DTYPE)
+    tr = np.ctypeslib.as_array(C.cast(R.trace, C.POINTER(C.c_uint16)), shape=(R.ntrace,)).copy() \
+        if R.ntrace else np.zeros(0, np.uint16)
+    stats = dict(nhits=R.nhits, nseeds=R.nseeds, next=R.next)
+    lib().orc_free(C.byref(R))
+    del ka, kb
+    return la, tr, stats

@@ -1,0 +1,62 @@
+#!/usr/bin/env python
+"""Extracts the reference's own golden vectors for the hot path into JSON fixtures.
+
+Run HERE (the only place /root/reference exists):  python tests/golden/make_golden.py
+Reads (never copies code, only literal test data):
+  * source/dentist/dazzler.d:965-1026   LAdump text fed to `dumpLA`
+  * source/dentist/dazzler.d:1045-1166  expected FlatLocalAlignment[]  (ids 1-based, DENTIST flags)
+  * source/dentist/dazzler.d:502-654    expected AlignmentChain[]      (chain packing)
+  * source/dentist/common/alignments/base.d:886-941  real 21-tile daligner trace + 12 assertions
+"""
+import json
+import os
+import re
+
+REF = "/root/reference/source/dentist"
+HERE = os.path.dirname(os.path.abspath(__file__))
+
+
+def lines(path, a, b):
+    with open(path) as f:
+        return f.read().split("\n")[a - 1:b]
+
+
+def main():
+    dz = os.path.join(REF, "dazzler.d")
+    dump = [m.group(1) for ln in lines(dz, 965, 1026) for m in [re.search(r'"(.*)"', ln)] if m]
+    txt = "\n".join(lines(dz, 1045, 1166))
+    flat = []
+    for m in re.finditer(
+            r"FlatLocalAlignment\(\s*(\d+),\s*FlatLocus\((\d+), (\d+), (\d+), (\d+)\),\s*FlatLocus\((\d+), (\d+), (\d+), (\d+)\),"
+            r"\s*AlignmentFlags\((.*?)\),\s*expectedTracePointDistance,\s*\[(.*?)\],\s*\)", txt, re.S):
+        g = m.groups()
+        flags = re.findall(r"AlignmentFlag\.(\w+)", g[9])
+        tps = [[int(a), int(b)] for a, b in re.findall(r"TracePoint\((\d+), (\d+)\)", g[10])]
+        flat.append(dict(id=int(g[0]), contigA=int(g[1]), abpos=int(g[3]), aepos=int(g[4]),
+                         contigB=int(g[5]), bbpos=int(g[7]), bepos=int(g[8]), flags=flags, trace=tps))
+    txt = "\n".join(lines(dz, 502, 654))
+    chains = []
+    for m in re.finditer(r"AlignmentChain\(\s*(\d+),\s*Contig\((\d+), 0\),\s*Contig\((\d+), 0\),\s*AlignmentFlags\((.*?)\),\s*\[(.*?)\],\s*expectedTracePointDistance",
+                         txt, re.S):
+        las = re.findall(r"LocalAlignment\(\s*Locus\((\d+), (\d+)\),\s*Locus\((\d+), (\d+)\),\s*(\d+),", m.group(5))
+        chains.append(dict(id=int(m.group(1)), contigA=int(m.group(2)), contigB=int(m.group(3)),
+                           flags=re.findall(r"AlignmentFlag\.(\w+)", m.group(4)),
+                           las=[[int(x) for x in la] for la in las]))
+    bd = os.path.join(REF, "common/alignments/base.d")
+    txt = "\n".join(lines(bd, 886, 941))
+    tps = [[int(a), int(b)] for a, b in re.findall(r"(?<!Translated)TracePoint\(\s*(\d+),\s*(\d+)\)", txt)]
+    loci = re.findall(r"Locus\((\d+), (\d+)\)", txt)
+    asserts = []
+    for m in re.finditer(r"translateTracePoint\((\d+), RoundingMode\.(\w+)\) == TranslatedTracePoint\((\d+), ([0-9 +]+)\)", txt):
+        asserts.append(dict(pos=int(m.group(1)), mode=m.group(2), a=int(m.group(3)), b=eval(m.group(4))))
+    kat = dict(tspace=100, abpos=int(loci[0][0]), aepos=int(loci[0][1]), bbpos=int(loci[1][0]), bepos=int(loci[1][1]),
+               diffs=292, trace=tps, asserts=asserts, throws=[578, 2585],
+               equal_pairs=[[700, "ceil", 700, "floor"], [699, "ceil", 701, "floor"]])
+    out = dict(source="a-ludi/dentist @ 1aa60e04", tspace=100, ladump=dump, flat=flat, chains=chains, trace_kat=kat)
+    with open(os.path.join(HERE, "las_golden.json"), "w") as f:
+        json.dump(out, f, indent=1)
+    print("flat", len(flat), "chains", len(chains), "dump lines", len(dump), "kat tiles", len(tps), "asserts", len(asserts))
+
+
+if __name__ == "__main__":
+    main()
