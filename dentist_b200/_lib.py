@@ -1,0 +1,89 @@
+"""ctypes loader for libdentist_b200.so (the C ABI declared in include/dentist_b200.h).
+
+Fails loudly when the library is missing: there is no CPU or PyTorch fallback anywhere in this
+package.  PyTorch is only used by bench.py / tests for device selection and torch.distributed.
+"""
+import ctypes as C
+import os
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libdentist_b200.so")
+
+EXPORTS = [
+    "dn_init", "dn_shutdown", "dn_last_error", "dn_version", "dn_launch_count",
+    "dn_align_params_default", "dn_las_free", "dn_block_upload", "dn_block_free", "dn_block_bases",
+    "dn_align_blocks", "dn_align_host", "dn_las_write", "dn_las_read", "dn_dalign", "dn_damap",
+]
+
+
+class DnError(RuntimeError):
+    """Raised for any non-zero return of the C ABI (the D shim raises DazzlerCommandException)."""
+
+
+class LasRecord(C.Structure):
+    _fields_ = [(n, C.c_int32) for n in ("tlen", "diffs", "abpos", "bbpos", "aepos", "bepos")] + \
+               [("flags", C.c_uint32), ("aread", C.c_int32), ("bread", C.c_int32), ("pad_", C.c_int32)]
+
+
+REC_DTYPE = np.dtype([("tlen", "<i4"), ("diffs", "<i4"), ("abpos", "<i4"), ("bbpos", "<i4"),
+                      ("aepos", "<i4"), ("bepos", "<i4"), ("flags", "<u4"), ("aread", "<i4"),
+                      ("bread", "<i4"), ("pad", "<i4")])
+
+
+class BlockDesc(C.Structure):
+    _fields_ = [("nreads", C.c_int32), ("format", C.c_int32), ("rlen", C.c_void_p), ("boff", C.c_void_p),
+                ("data", C.c_void_p), ("data_bytes", C.c_int64), ("mask_anno", C.c_void_p), ("mask_data", C.c_void_p)]
+
+
+class AlignParams(C.Structure):
+    _fields_ = [("k", C.c_int32), ("w", C.c_int32), ("h", C.c_int32), ("t", C.c_int32), ("tspace", C.c_int32),
+                ("minlen", C.c_int32), ("e", C.c_double), ("identity", C.c_int32), ("self_block", C.c_int32),
+                ("rounds", C.c_int32), ("xdrop", C.c_int32), ("wmax", C.c_int32), ("poolmul", C.c_int32)]
+
+
+class AlignStats(C.Structure):
+    _fields_ = [(n, C.c_int64) for n in ("tuples_a", "tuples_b", "hits", "seeds", "extensions", "las",
+                                         "aligned_bases", "trace_points", "algo_bytes_seed", "algo_bytes_extend")] + \
+               [("ms_seed", C.c_float), ("ms_extend", C.c_float), ("ms_total", C.c_float), ("launches", C.c_uint64)]
+
+
+class LasBuf(C.Structure):
+    _fields_ = [("nrec", C.c_int64), ("rec", C.POINTER(LasRecord)), ("toff", C.POINTER(C.c_int64)),
+                ("ntrace", C.c_int64), ("trace", C.POINTER(C.c_uint16)), ("tspace", C.c_int32), ("stats", AlignStats)]
+
+
+_lib = None
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise ImportError("%s is missing: run ./build.sh (or __graft_entry__.build()); dentist_b200 has no "
+                              "CPU fallback" % LIB_PATH)
+        L = C.CDLL(LIB_PATH)
+        L.dn_last_error.restype = C.c_char_p
+        L.dn_version.restype = C.c_char_p
+        L.dn_launch_count.restype = C.c_uint64
+        L.dn_init.argtypes = [C.c_int, C.c_char_p]
+        L.dn_align_params_default.argtypes = [C.POINTER(AlignParams)]
+        L.dn_las_free.argtypes = [C.POINTER(LasBuf)]
+        L.dn_block_upload.argtypes = [C.POINTER(BlockDesc), C.POINTER(C.c_void_p)]
+        L.dn_block_free.argtypes = [C.c_void_p]
+        L.dn_block_bases.argtypes = [C.c_void_p]
+        L.dn_block_bases.restype = C.c_int64
+        L.dn_align_blocks.argtypes = [C.c_void_p, C.c_void_p, C.POINTER(AlignParams), C.POINTER(LasBuf)]
+        L.dn_align_host.argtypes = [C.POINTER(BlockDesc), C.POINTER(BlockDesc), C.POINTER(AlignParams), C.POINTER(LasBuf)]
+        L.dn_las_write.argtypes = [C.c_char_p, C.POINTER(LasBuf)]
+        L.dn_las_read.argtypes = [C.c_char_p, C.POINTER(LasBuf)]
+        L.dn_dalign.argtypes = [C.c_char_p, C.c_char_p, C.POINTER(C.c_char_p), C.c_int, C.c_char_p]
+        L.dn_damap.argtypes = [C.c_char_p, C.c_char_p, C.POINTER(C.c_char_p), C.c_int, C.c_char_p]
+        _lib = L
+    return _lib
+
+
+def check(rc):
+    if rc != 0:
+        raise DnError("dentist_b200 error %d: %s" % (rc, lib().dn_last_error().decode("utf-8", "replace")))

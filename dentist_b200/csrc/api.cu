@@ -1,0 +1,261 @@
+// api.cu -- the C ABI (include/dentist_b200.h): lifecycle, resident blocks, in-memory alignment,
+// LAS serialisation and the file-level drop-ins for dazzler.d's getDalignment / getDamapping.
+#include "engine.cuh"
+#include "dazzdb.hpp"
+#include <mutex>
+#include <string.h>
+#include <stdlib.h>
+#include <string>
+
+using namespace dn;
+
+struct dn_block { DevBlock b; };
+
+namespace {
+thread_local std::string t_err;
+std::mutex g_mu;                 // serialises device work: entry points are re-entrant, the GPU queue is one
+int g_device = -1;
+cudaStream_t g_stream = nullptr;
+
+int fail(int code, const std::string &m) { t_err = m; return code; }
+
+int ensure_device() {
+    if (g_device >= 0) return DN_OK;
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess || n == 0) return fail(DN_ERR_NO_DEVICE, "no CUDA device available (dentist_b200 has no CPU fallback)");
+    if (cudaSetDevice(0) != cudaSuccess) return fail(DN_ERR_NO_DEVICE, "cudaSetDevice(0) failed");
+    g_device = 0;
+    if (!g_stream) cudaStreamCreateWithFlags(&g_stream, cudaStreamNonBlocking);
+    return DN_OK;
+}
+
+template <typename F> int guarded(F &&f) {
+    try { return f(); }
+    catch (const dn::Error &e) { return fail(DN_ERR_CUDA, e.what()); }
+    catch (const std::bad_alloc &) { return fail(DN_ERR_INVALID, "out of host memory"); }
+    catch (const std::exception &e) { return fail(DN_ERR_INVALID, e.what()); }
+}
+
+AlignParams to_internal(const dn_align_params *p) {
+    dn_align_params d; dn_align_params_default(&d);
+    if (p) d = *p;
+    AlignParams q;
+    q.k = d.k; q.w = d.w; q.h = d.h; q.t = d.t; q.tspace = d.tspace; q.minlen = d.minlen;
+    double e = d.e; if (e < 0.7) e = 0.7; if (e > 0.99) e = 0.99;
+    q.cdiff = (int)(6.0 / (1.0 - e) + 0.5);                   // S = 3*(i+j) - C*d drifts to zero at 1-e diffs/column
+    q.xdrop = d.xdrop; q.wmax = d.wmax; q.rounds = d.rounds; q.poolmul = d.poolmul;
+    q.self = (d.self_block && !d.identity) ? 1 : 0;
+    return q;
+}
+
+void to_buf(HostLas &h, int tspace, dn_las_buf *out) {
+    memset(out, 0, sizeof *out);
+    out->nrec = (int64_t)h.rec.size(); out->ntrace = (int64_t)h.trace.size(); out->tspace = tspace; out->stats = h.stats;
+    out->rec = (dn_las_record *)malloc(sizeof(dn_las_record) * (h.rec.size() + 1));
+    out->toff = (int64_t *)malloc(sizeof(int64_t) * (h.rec.size() + 1));
+    out->trace = (uint16_t *)malloc(sizeof(uint16_t) * (h.trace.size() + 1));
+    if (!out->rec || !out->toff || !out->trace) throw std::bad_alloc();
+    if (!h.rec.empty()) { memcpy(out->rec, h.rec.data(), sizeof(dn_las_record) * h.rec.size()); memcpy(out->toff, h.toff.data(), sizeof(int64_t) * h.toff.size()); }
+    if (!h.trace.empty()) memcpy(out->trace, h.trace.data(), sizeof(uint16_t) * h.trace.size());
+}
+}  // namespace
+
+extern "C" {
+
+int dn_init(int device, const char *tmpdir) {
+    (void)tmpdir;
+    std::lock_guard<std::mutex> lk(g_mu);
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess || n == 0) return fail(DN_ERR_NO_DEVICE, "no CUDA device available (dentist_b200 has no CPU fallback)");
+    if (device < 0) device = 0;
+    if (device >= n) return fail(DN_ERR_INVALID, "device index out of range");
+    if (cudaSetDevice(device) != cudaSuccess) return fail(DN_ERR_CUDA, "cudaSetDevice failed");
+    g_device = device;
+    if (!g_stream) cudaStreamCreateWithFlags(&g_stream, cudaStreamNonBlocking);
+    return DN_OK;
+}
+int dn_shutdown(void) {
+    std::lock_guard<std::mutex> lk(g_mu);
+    if (g_stream) { cudaStreamDestroy(g_stream); g_stream = nullptr; }
+    g_device = -1;
+    return DN_OK;
+}
+const char *dn_last_error(void) { return t_err.c_str(); }
+const char *dn_version(void) { return "dentist_b200 0.1.0 (sm_100a)"; }
+uint64_t dn_launch_count(void) { return dn::g_launches.load(); }
+
+void dn_align_params_default(dn_align_params *p) {
+    memset(p, 0, sizeof *p);
+    p->k = 14; p->w = 6; p->h = 35; p->t = 32; p->tspace = 100; p->minlen = 1000; p->e = 0.7;
+    p->identity = 0; p->self_block = 0; p->rounds = 3; p->xdrop = 300; p->wmax = 62; p->poolmul = 64;
+}
+
+void dn_las_free(dn_las_buf *b) {
+    if (!b) return;
+    free(b->rec); free(b->toff); free(b->trace);
+    memset(b, 0, sizeof *b);
+}
+
+int dn_block_upload(const dn_block_desc *desc, dn_block **out) {
+    if (!desc || !out) return fail(DN_ERR_INVALID, "null argument");
+    std::lock_guard<std::mutex> lk(g_mu);
+    if (int rc = ensure_device()) return rc;
+    return guarded([&] {
+        cudaSetDevice(g_device);
+        dn_block *b = new dn_block();
+        try { block_upload(*desc, b->b, g_stream); } catch (...) { delete b; throw; }
+        *out = b; return DN_OK;
+    });
+}
+void dn_block_free(dn_block *blk) {
+    if (!blk) return;
+    std::lock_guard<std::mutex> lk(g_mu);
+    if (g_device >= 0) cudaSetDevice(g_device);
+    delete blk;
+}
+int64_t dn_block_bases(const dn_block *blk) { return blk ? blk->b.total_real : 0; }
+
+int dn_align_blocks(const dn_block *a, const dn_block *b, const dn_align_params *p, dn_las_buf *out) {
+    if (!a || !b || !out) return fail(DN_ERR_INVALID, "null argument");
+    std::lock_guard<std::mutex> lk(g_mu);
+    if (int rc = ensure_device()) return rc;
+    return guarded([&] {
+        cudaSetDevice(g_device);
+        AlignParams q = to_internal(p);
+        HostLas h;
+        align_blocks(a->b, b->b, q, h, g_stream);
+        to_buf(h, q.tspace, out);
+        return DN_OK;
+    });
+}
+
+int dn_align_host(const dn_block_desc *a, const dn_block_desc *b, const dn_align_params *p, dn_las_buf *out) {
+    dn_block *ba = nullptr, *bb = nullptr;
+    int rc = dn_block_upload(a, &ba);
+    if (rc) return rc;
+    const bool same = (a == b);
+    if (!same) { rc = dn_block_upload(b, &bb); if (rc) { dn_block_free(ba); return rc; } }
+    rc = dn_align_blocks(ba, same ? ba : bb, p, out);
+    dn_block_free(ba); if (!same) dn_block_free(bb);
+    return rc;
+}
+
+int dn_las_write(const char *path, const dn_las_buf *buf) {
+    if (!path || !buf) return fail(DN_ERR_INVALID, "null argument");
+    return guarded([&] {
+        FILE *f = fopen(path, "wb");
+        if (!f) return fail(DN_ERR_IO, std::string("cannot open for writing: ") + path);
+        int64_t novl = buf->nrec; int32_t ts = buf->tspace;
+        fwrite(&novl, 8, 1, f); fwrite(&ts, 4, 1, f);
+        const bool large = ts > 125;                     // TRACE_XOVR, dazzler.d:2019-2025
+        std::vector<uint8_t> small;
+        for (int64_t i = 0; i < buf->nrec; i++) {
+            fwrite(&buf->rec[i], 40, 1, f);
+            const uint16_t *t = buf->trace + buf->toff[i]; const int tl = buf->rec[i].tlen;
+            if (large) fwrite(t, 2, tl, f);
+            else { small.resize(tl); for (int x = 0; x < tl; x++) small[x] = (uint8_t)(t[x] > 255 ? 255 : t[x]); fwrite(small.data(), 1, tl, f); }
+        }
+        if (fclose(f) != 0) return fail(DN_ERR_IO, std::string("write failed: ") + path);
+        return DN_OK;
+    });
+}
+
+int dn_las_read(const char *path, dn_las_buf *out) {
+    if (!path || !out) return fail(DN_ERR_INVALID, "null argument");
+    return guarded([&] {
+        FILE *f = fopen(path, "rb");
+        if (!f) return fail(DN_ERR_IO, std::string("cannot open: ") + path);
+        int64_t novl = 0; int32_t ts = 0;
+        if (fread(&novl, 8, 1, f) != 1 || fread(&ts, 4, 1, f) != 1 || novl < 0) { fclose(f); return fail(DN_ERR_IO, "error reading LAS file: unexpected end of file; expected header"); }
+        HostLas h; h.rec.resize(novl); h.toff.resize(novl);
+        const bool large = ts > 125;
+        std::vector<uint8_t> small;
+        for (int64_t i = 0; i < novl; i++) {
+            if (fread(&h.rec[i], 40, 1, f) != 1) { fclose(f); return fail(DN_ERR_IO, "error reading LAS file: unexpected end of file; expected overlapHead"); }
+            const int tl = h.rec[i].tlen;
+            if (tl < 0 || (tl & 1)) { fclose(f); return fail(DN_ERR_IO, "illegal value for tlen: must be multiple of 2"); }
+            h.toff[i] = (int64_t)h.trace.size();
+            size_t o = h.trace.size(); h.trace.resize(o + tl);
+            bool ok;
+            if (large) ok = fread(h.trace.data() + o, 2, tl, f) == (size_t)tl;
+            else { small.resize(tl); ok = fread(small.data(), 1, tl, f) == (size_t)tl; for (int x = 0; x < tl; x++) h.trace[o + x] = small[x]; }
+            if (!ok) { fclose(f); return fail(DN_ERR_IO, "error reading LAS file: unexpected end of file; expected tracePoints"); }
+        }
+        fclose(f);
+        to_buf(h, ts, out);
+        return DN_OK;
+    });
+}
+
+// ---- file-level drop-ins ------------------------------------------------------------------
+
+static int parse_opts(const char *const *opts, int nopts, dn_align_params *p, bool *asym, std::vector<std::string> *masks) {
+    for (int i = 0; i < nopts; i++) {
+        const char *o = opts[i];
+        if (!o || o[0] != '-' || !o[1]) return fail(DN_ERR_INVALID, std::string("bad option: ") + (o ? o : "(null)"));
+        const char *v = o + 2;
+        switch (o[1]) {
+            case 'k': p->k = atoi(v); break;
+            case 'w': p->w = atoi(v); break;
+            case 'h': p->h = atoi(v); break;
+            case 't': p->t = atoi(v); break;
+            case 's': p->tspace = atoi(v); break;
+            case 'l': p->minlen = atoi(v); break;
+            case 'e': p->e = atof(v); break;
+            case 'I': p->identity = 1; break;
+            case 'A': *asym = true; break;
+            case 'm': masks->push_back(v); break;
+            case 'T': case 'M': case 'B': case 'v': case 'b': case 'a': case 'C': case 'N': case 'z': case 'n': case 'P': case 'p': break;   // accepted, no effect on a GPU
+            default: return fail(DN_ERR_INVALID, std::string("unknown option: ") + o);
+        }
+    }
+    if (p->k > 15) p->k = 15;
+    return DN_OK;
+}
+
+static int align_files(const char *dbA, const char *dbB, const char *const *opts, int nopts, const char *outdir, bool mapper) {
+    if (!dbA || !outdir) return fail(DN_ERR_INVALID, "null argument");
+    return guarded([&]() -> int {
+        dn_align_params p; dn_align_params_default(&p);
+        if (mapper) p.minlen = 1000;
+        bool asym = false; std::vector<std::string> masks;
+        if (int rc = parse_opts(opts, nopts, &p, &asym, &masks)) return rc;
+        const bool self = (dbB == nullptr) || std::string(dbA) == std::string(dbB);
+        HostDb A, B;
+        std::string err;
+        if (!read_dazz_db(dbA, masks, A, err)) return fail(DN_ERR_IO, err);
+        if (!self && !read_dazz_db(dbB, masks, B, err)) return fail(DN_ERR_IO, err);
+        HostDb &Bx = self ? A : B;
+        p.self_block = self ? 1 : 0;
+        dn_block_desc da = A.desc(), db = Bx.desc();
+        dn_las_buf ab; memset(&ab, 0, sizeof ab);
+        int rc = dn_align_host(&da, self ? &da : &db, &p, &ab);
+        if (rc) return rc;
+        if (mapper) for (int64_t i = 0; i < ab.nrec; i++) ab.rec[i].flags |= DN_LAS_START | DN_LAS_BEST;
+        std::string pa = std::string(outdir) + "/" + A.name + "." + Bx.name + ".las";
+        rc = dn_las_write(pa.c_str(), &ab);
+        dn_las_free(&ab);
+        if (rc) return rc;
+        if (!self && (!asym || mapper)) {
+            dn_las_buf ba; memset(&ba, 0, sizeof ba);
+            rc = dn_align_host(&db, &da, &p, &ba);
+            if (rc) return rc;
+            if (mapper) for (int64_t i = 0; i < ba.nrec; i++) ba.rec[i].flags |= DN_LAS_START | DN_LAS_BEST;
+            std::string pb = std::string(outdir) + "/" + Bx.name + "." + A.name + ".las";
+            rc = dn_las_write(pb.c_str(), &ba);
+            dn_las_free(&ba);
+            if (rc) return rc;
+        }
+        return DN_OK;
+    });
+}
+
+int dn_dalign(const char *dbA, const char *dbB, const char *const *opts, int nopts, const char *outdir) {
+    return align_files(dbA, dbB, opts, nopts, outdir, false);
+}
+int dn_damap(const char *refDb, const char *queryDb, const char *const *opts, int nopts, const char *outdir) {
+    return align_files(refDb, queryDb, opts, nopts, outdir, true);
+}
+
+}  // extern "C"

@@ -1,0 +1,239 @@
+// engine.cu -- host orchestration of one block-vs-block alignment job on the current device.
+// Everything between "blocks resident in HBM" and "sorted LAS records on the host" happens here;
+// the only host-side arithmetic is the final ordering/serialisation of the (few) surviving records.
+#include "seed.cuh"
+#include <algorithm>
+#include <string.h>
+
+namespace dn {
+
+int ext_warps_per_cta();
+
+namespace {
+
+template <typename T> T d2h_scalar(const T *d, cudaStream_t s) {
+    T v; DN_CUDA(cudaMemcpyAsync(&v, d, sizeof(T), cudaMemcpyDeviceToHost, s)); DN_CUDA(cudaStreamSynchronize(s)); return v;
+}
+int bits_for(uint64_t v) { int b = 0; while (v) { b++; v >>= 1; } return b; }   // bits needed to represent v
+
+struct Timer {
+    cudaEvent_t a, b; cudaStream_t s;
+    Timer(cudaStream_t s_) : s(s_) { cudaEventCreate(&a); cudaEventCreate(&b); }
+    ~Timer() { cudaEventDestroy(a); cudaEventDestroy(b); }
+    void start() { cudaEventRecord(a, s); }
+    float stop() { cudaEventRecord(b, s); cudaEventSynchronize(b); float ms = 0; cudaEventElapsedTime(&ms, a, b); return ms; }
+};
+
+}  // namespace
+
+void align_blocks(const DevBlock &A, const DevBlock &B, const AlignParams &P, HostLas &out, cudaStream_t s) {
+    out.rec.clear(); out.toff.clear(); out.trace.clear(); memset(&out.stats, 0, sizeof out.stats);
+    if (P.k < 4 || P.k > 15) throw Error("k must be in [4,15]");
+    if (P.wmax < 4 || P.wmax > 62) throw Error("wmax must be in [4,62]");
+    if (P.w < 1 || P.w > 12 || P.tspace < 1 || P.tspace > 32767) throw Error("bad w / tspace");
+    if (P.cdiff < 20 || P.xdrop < 1 || P.xdrop > 1000) throw Error("bad cdiff / xdrop");
+    if (P.rounds < 1 || P.poolmul < 1) throw Error("bad rounds / poolmul");
+    const unsigned long long launches0 = g_launches.load();
+    Timer tt(s), ts_(s), te(s);
+    tt.start(); ts_.start();
+    if (A.nreads == 0 || B.nreads == 0) { out.stats.ms_total = tt.stop(); return; }
+    const int k = P.k;
+    const int64_t nA = A.total, nB = B.total;
+
+    // ---- K1 + K2: tuples, radix sort by k-mer -------------------------------------------------
+    DBuf<u64> ta(nA), ta2(nA);
+    emit_tuples(A, false, k, 0u, ta.p, s);
+    u64 *sa = radix_sort_u64(ta.p, ta2.p, nA, 32, 32 + 2 * k + 1, s);
+    if (sa == ta.p) ta2.release(); else ta.release();
+    DBuf<u64> tb(2 * nB), tb2(2 * nB);
+    emit_tuples(B, false, k, 0u, tb.p, s);
+    emit_tuples(B, true, k, (u32)nB, tb.p + nB, s);
+    u64 *sb = radix_sort_u64(tb.p, tb2.p, 2 * nB, 32, 32 + 2 * k + 1, s);
+    if (sb == tb.p) tb2.release(); else tb.release();
+    const int npass_t = (2 * k + 1 + 7) / 8;
+    out.stats.tuples_a = A.total_real; out.stats.tuples_b = 2 * B.total_real;
+    int64_t abytes = (nA + nB) / 4 + (nB / 4)                    // read packed sequence (B twice)
+                     + 8 * (nA + 2 * nB)                          // write tuples
+                     + (int64_t)npass_t * 24 * (nA + 2 * nB);     // 2 reads + 1 write per pass
+
+    // ---- K3: join ------------------------------------------------------------------------------
+    int tbits = bits_for((uint64_t)nA) + 1; if (tbits < 16) tbits = 16; if (tbits > 2 * k) tbits = 2 * k;
+    const int sh = 2 * k - tbits; const u32 nq = 1u << tbits;
+    DBuf<u32> tbl((size_t)nq + 2);
+    DN_LAUNCH(k_prefix_table, (unsigned)((nA + 255) / 256), 256, 0, s, (const u64 *)sa, nA, sh, nq, tbl.p);
+    DBuf<u32> cnt(2 * nB), start(2 * nB);
+    DN_LAUNCH(k_join_count, (unsigned)((2 * nB + 255) / 256), 256, 0, s, (const u64 *)sa, (const u32 *)tbl.p, sh,
+              (const u64 *)sb, 2 * nB, P.t, cnt.p, start.p);
+    DBuf<int64_t> hoff(2 * nB), dtotal(1);
+    exclusive_scan_u32_to_i64(cnt.p, hoff.p, 2 * nB, dtotal.p, s);
+    const int64_t H = d2h_scalar(dtotal.p, s);
+    if (H >= (1ll << 31) - 4096) throw Error("too many seed hits for one block pair (>= 2^31); use smaller blocks or lower -t");
+    out.stats.hits = H;
+    abytes += 8 * nA + 4ll * nq + 2 * 8 * 2 * nB + 16 * 2 * nB + 16 * H;
+
+    // hit-key geometry
+    const int64_t bandw = 1ll << P.w;
+    const int64_t maxlb = ((int64_t)B.maxlen + bandw - 1) / bandw * bandw;
+    std::vector<int64_t> dbase(A.nreads + 1);
+    { int64_t d = 0;
+      for (int r = 0; r < A.nreads; r++) { dbase[r] = d; d = (d + A.h_len[r] + maxlb + bandw - 1) / bandw * bandw + bandw; }
+      dbase[A.nreads] = d; }
+    const int gdbits = bits_for((uint64_t)dbase[A.nreads] + 2 * bandw);
+    const int keybits = gdbits + bits_for((uint64_t)2 * B.nreads);
+    if (keybits > 62) throw Error("hit key does not fit 62 bits");
+    DBuf<int64_t> d_dbase(A.nreads + 1);
+    DN_CUDA(cudaMemcpyAsync(d_dbase.p, dbase.data(), sizeof(int64_t) * (A.nreads + 1), cudaMemcpyHostToDevice, s));
+    JoinGeom JG{A.chunk2read.p, A.off.p, d_dbase.p, B.chunk2read.p, B.off.p, nB, maxlb, gdbits, keybits, P.self};
+    SeedGeom SG{d_dbase.p, A.nreads, gdbits};
+
+    DBuf<ulonglong2> hits((size_t)H + 1), hits2((size_t)H + 1);
+    DBuf<unsigned long long> ninv(1); ninv.zero(s);
+    if (H > 0)
+        DN_LAUNCH(k_join_emit, (unsigned)((2 * nB + 255) / 256), 256, 0, s, (const u64 *)sa, (const u64 *)sb, 2 * nB,
+                  (const u32 *)cnt.p, (const u32 *)start.p, (const int64_t *)hoff.p, JG, hits.p, ninv.p);
+    const int64_t ninvalid = (int64_t)d2h_scalar(ninv.p, s);
+    cnt.release(); start.release(); hoff.release(); ta.release(); ta2.release(); tb.release(); tb2.release(); tbl.release();
+
+    // ---- hit sort: by apos, then stably by (bread, strand, aread, diagonal) -------------------
+    const int aposbits = bits_for((uint64_t)A.maxlen);
+    ulonglong2 *hs = radix_sort_rec16(hits.p, hits2.p, H, 1, 0, aposbits, s);
+    ulonglong2 *ho = hs == hits.p ? hits2.p : hits.p;
+    hs = radix_sort_rec16(hs, ho, H, 0, 0, keybits + 1, s);
+    ho = hs == hits.p ? hits2.p : hits.p;
+    const int npass_h = (aposbits + 7) / 8 + (keybits + 1 + 7) / 8;
+    abytes += (int64_t)npass_h * 48 * H;
+    int64_t n = H - ninvalid;                   // invalid (self) hits sorted to the end
+
+    // ---- rounds of band filter -> seeds -> extension -> retirement ----------------------------
+    ExtGeom EG{A.fwd.p, A.rc.p, B.fwd.p, B.rc.p, A.off.p, B.off.p, A.len.p, B.len.p,
+               P.tspace, P.cdiff, P.xdrop, P.wmax, P.poolmul, (u32)((1ull << 32) / (u32)P.tspace + 1)};
+    {
+        long long span = (long long)B.maxlen + B.maxlen / 2 + 64; if (A.maxlen < span) span = A.maxlen;
+        if ((unsigned long long)span >= (1ull << 32) / (unsigned)P.tspace) throw Error("reads too long for the tile arithmetic");
+    }
+    const int64_t pool_stride = (int64_t)P.poolmul * ([&] { long long sp = (long long)B.maxlen + B.maxlen / 2 + 64;
+                                                           if (A.maxlen < sp) sp = A.maxlen; return sp; }() / P.tspace + 4);
+    std::vector<DBuf<Cand>> round_cands; std::vector<DBuf<uint16_t>> round_traces;
+    std::vector<int32_t> round_beg{0};
+    std::vector<int64_t> round_ntr;
+    float ms_seed = ts_.stop(), ms_ext = 0;
+    int64_t ext_bytes = 0;
+    DBuf<int32_t> dtot32(1);
+
+    for (int round = 0; round < P.rounds && n > 0; round++) {
+        ts_.start();
+        DBuf<int32_t> cov(n), bflag(n), bidx(n), covsum(n);
+        DN_LAUNCH(k_hit_cover, (unsigned)((n + 255) / 256), 256, 0, s, (const ulonglong2 *)hs, n, k, P.w, cov.p, bflag.p);
+        exclusive_scan_i32(bflag.p, bidx.p, n, dtot32.p, s);
+        const int32_t nbands = d2h_scalar(dtot32.p, s);
+        exclusive_scan_i32(cov.p, covsum.p, n, dtot32.p, s);
+        const int32_t total_cov = d2h_scalar(dtot32.p, s);
+        DBuf<int32_t> bfirst((size_t)nbands + 2), cstart(nbands), cidx(nbands);
+        DBuf<u64> bkey((size_t)nbands + 1);
+        DBuf<uint8_t> pass(nbands), hot(nbands);
+        DN_LAUNCH(k_band_table, (unsigned)((n + 255) / 256), 256, 0, s, (const ulonglong2 *)hs, n, P.w, (const int32_t *)bflag.p,
+                  (const int32_t *)bidx.p, bfirst.p, bkey.p, nbands);
+        DN_LAUNCH(k_band_pass, (nbands + 255) / 256, 256, 0, s, (const int32_t *)bfirst.p, (const u64 *)bkey.p,
+                  (const int32_t *)covsum.p, total_cov, n, nbands, P.h, pass.p);
+        DN_LAUNCH(k_band_hot, (nbands + 255) / 256, 256, 0, s, (const u64 *)bkey.p, (const uint8_t *)pass.p, nbands, hot.p, cstart.p);
+        exclusive_scan_i32(cstart.p, cidx.p, nbands, dtot32.p, s);
+        const int32_t nseeds = d2h_scalar(dtot32.p, s);
+        abytes += 16 * n + 8 * n + 3 * 12 * n + 16ll * nbands;
+        if (nseeds == 0) { ms_seed += ts_.stop(); break; }
+        DBuf<Seed> seeds(nseeds); DBuf<uint8_t> consumed(n); consumed.zero(s);
+        DN_LAUNCH(k_seeds, (nbands + 255) / 256, 256, 0, s, (const ulonglong2 *)hs, (const int32_t *)bfirst.p, (const u64 *)bkey.p,
+                  (const uint8_t *)hot.p, (const int32_t *)cstart.p, (const int32_t *)cidx.p, nbands, SG, seeds.p, consumed.p);
+        cov.release(); bflag.release(); bidx.release(); covsum.release();
+        out.stats.seeds += nseeds; out.stats.extensions += 2ll * nseeds;
+        ms_seed += ts_.stop();
+
+        // ---- K5: extension
+        te.start();
+        DBuf<u32> caps(2 * (size_t)nseeds); DBuf<int64_t> tile_off(2 * (size_t)nseeds);
+        launch_task_caps(seeds.p, nseeds, EG, caps.p, s);
+        exclusive_scan_u32_to_i64(caps.p, tile_off.p, 2 * (size_t)nseeds, dtotal.p, s);
+        const int64_t ntile_cap = d2h_scalar(dtotal.p, s);
+        DBuf<int2> tiles((size_t)ntile_cap + 1); DBuf<ExtOut> outs(2 * (size_t)nseeds);
+        const int wpc = ext_warps_per_cta();
+        int ctas = sm_count() * 4;
+        { int64_t need = (2ll * nseeds + wpc - 1) / wpc; if (ctas > need) ctas = (int)need;
+          const int64_t budget = 24ll << 30;   // bytes of HBM for trace-record pools
+          int64_t maxc = budget / (pool_stride * 16 * wpc); if (maxc < 1) maxc = 1;
+          if (ctas > maxc) ctas = (int)maxc; }
+        DBuf<int4> pool((size_t)ctas * wpc * pool_stride);
+        DBuf<int> counter(1); counter.zero(s);
+        launch_extend(seeds.p, nseeds, EG, tile_off.p, tiles.p, outs.p, pool.p, pool_stride, ctas * wpc, counter.p, s);
+        ms_ext += te.stop();
+
+        // ---- K6: candidates, traces, retirement
+        ts_.start();
+        DBuf<Cand> cand_all(nseeds); DBuf<int32_t> valid(nseeds), vidx(nseeds); DBuf<u32> ntl(nseeds); DBuf<int64_t> toff(nseeds);
+        launch_combine(seeds.p, nseeds, EG, P.minlen, tile_off.p, tiles.p, outs.p, cand_all.p, valid.p, ntl.p, s);
+        exclusive_scan_i32(valid.p, vidx.p, nseeds, dtot32.p, s);
+        const int32_t nvalid = d2h_scalar(dtot32.p, s);
+        exclusive_scan_u32_to_i64(ntl.p, toff.p, nseeds, dtotal.p, s);
+        const int64_t ntr = d2h_scalar(dtotal.p, s);
+        DBuf<Cand> rc((size_t)nvalid + 1); DBuf<uint16_t> rtr((size_t)2 * ntr + 2);
+        launch_write_traces(seeds.p, nseeds, EG, tile_off.p, tiles.p, outs.p, cand_all.p, valid.p, vidx.p, toff.p, rc.p, rtr.p, s);
+        DBuf<int32_t> keep(n), kidx(n);
+        launch_retire((const ulonglong2 *)hs, n, consumed.p, rc.p, nvalid, SG, P.w, keep.p, s);
+        exclusive_scan_i32(keep.p, kidx.p, n, dtot32.p, s);
+        const int64_t n_new = d2h_scalar(dtot32.p, s);
+        launch_compact_hits((const ulonglong2 *)hs, n, keep.p, kidx.p, ho, s);
+        DN_CUDA(cudaStreamSynchronize(s));
+        std::swap(hs, ho);
+        abytes += 24 * n + 16 * n_new;
+        n = n_new;
+        round_beg.push_back(round_beg.back() + nvalid);
+        round_ntr.push_back(2 * ntr);
+        round_cands.push_back(std::move(rc)); round_traces.push_back(std::move(rtr));
+        ms_seed += ts_.stop();
+    }
+
+    // ---- duplicate removal over all candidates, download, final ordering -----------------------
+    const int ncand = round_beg.back();
+    const int nrounds = (int)round_cands.size();
+    std::vector<Cand> hc(ncand); std::vector<uint8_t> hdrop(ncand);
+    std::vector<std::vector<uint16_t>> htr(nrounds);
+    if (ncand > 0) {
+        DBuf<Cand> all(ncand); DBuf<int32_t> rb(nrounds + 1); DBuf<uint8_t> drop(ncand);
+        for (int r = 0; r < nrounds; r++)
+            if (round_beg[r + 1] > round_beg[r])
+                DN_CUDA(cudaMemcpyAsync(all.p + round_beg[r], round_cands[r].p, sizeof(Cand) * (round_beg[r + 1] - round_beg[r]),
+                                        cudaMemcpyDeviceToDevice, s));
+        DN_CUDA(cudaMemcpyAsync(rb.p, round_beg.data(), sizeof(int32_t) * (nrounds + 1), cudaMemcpyHostToDevice, s));
+        launch_dedupe(all.p, ncand, rb.p, nrounds, drop.p, s);
+        DN_CUDA(cudaMemcpyAsync(hc.data(), all.p, sizeof(Cand) * ncand, cudaMemcpyDeviceToHost, s));
+        DN_CUDA(cudaMemcpyAsync(hdrop.data(), drop.p, ncand, cudaMemcpyDeviceToHost, s));
+        for (int r = 0; r < nrounds; r++) {
+            htr[r].resize(round_ntr[r]);
+            if (round_ntr[r]) DN_CUDA(cudaMemcpyAsync(htr[r].data(), round_traces[r].p, 2 * round_ntr[r], cudaMemcpyDeviceToHost, s));
+        }
+        DN_CUDA(cudaStreamSynchronize(s));
+    }
+    std::vector<int> order; order.reserve(ncand);
+    for (int j = 0; j < ncand; j++) if (!hdrop[j]) order.push_back(j);
+    auto key = [&](int j) { const Cand &c = hc[j]; return std::make_tuple(c.a, c.bs >> 1, c.bs & 1, c.ab, c.ae, c.bb, c.be, c.diffs); };
+    std::sort(order.begin(), order.end(), [&](int x, int y) { auto kx = key(x), ky = key(y); return kx != ky ? kx < ky : x < y; });
+    out.rec.resize(order.size()); out.toff.resize(order.size());
+    int64_t tot = 0; for (int j : order) tot += 2 * hc[j].nt;
+    out.trace.resize(tot);
+    int64_t to = 0, aligned = 0;
+    for (size_t o = 0; o < order.size(); o++) {
+        const int j = order[o]; const Cand &c = hc[j];
+        int r = (int)(std::upper_bound(round_beg.begin(), round_beg.end(), j) - round_beg.begin()) - 1;
+        dn_las_record &q = out.rec[o];
+        q.tlen = 2 * c.nt; q.diffs = c.diffs; q.abpos = c.ab; q.bbpos = c.bb; q.aepos = c.ae; q.bepos = c.be;
+        q.flags = (c.bs & 1) ? DN_LAS_COMP : 0u; q.aread = c.a; q.bread = c.bs >> 1; q.pad_ = 0;
+        out.toff[o] = to;
+        memcpy(out.trace.data() + to, htr[r].data() + c.toff, sizeof(uint16_t) * 2 * c.nt);
+        to += 2 * c.nt; aligned += c.ae - c.ab;
+        ext_bytes += (c.ae - c.ab) / 4 + (c.be - c.bb) / 4 + 40 + 4 * c.nt;
+    }
+    out.stats.las = (int64_t)order.size(); out.stats.aligned_bases = aligned; out.stats.trace_points = tot / 2;
+    out.stats.algo_bytes_seed = abytes; out.stats.algo_bytes_extend = ext_bytes;
+    out.stats.ms_seed = ms_seed; out.stats.ms_extend = ms_ext; out.stats.ms_total = tt.stop();
+    out.stats.launches = g_launches.load() - launches0;
+}
+
+}  // namespace dn

@@ -1,0 +1,47 @@
+// engine.cuh -- internal interfaces of the alignment engine (device-resident blocks, parameters,
+// stage entry points).  The public boundary is include/dentist_b200.h.
+#pragma once
+#include "common.cuh"
+#include "../../include/dentist_b200.h"
+
+namespace dn {
+
+// A sequence block resident in HBM.
+//  * every read starts at a multiple of 64 bases (16 B of 2-bit data) in one concatenated,
+//    padded coordinate space ("g" coordinates); `off[r]` is that start, off[nreads] the total
+//  * fwd / rc: 2-bit codes, 16 bases per u32, base p of the block in bits 2*(p&15) of word p>>4
+//    (LSB-first so unaligned windows are a funnel shift); rc holds every read reverse-complemented
+//    in place (same offsets) -- as daligner complements a block once instead of per alignment
+//  * chunk2read[g>>10] = read whose padded extent contains g (O(1) position -> read lookup)
+//  * mask / mask_rc: optional bit per g coordinate (1 = masked: no k-mer may touch it)
+struct DevBlock {
+    int nreads = 0;
+    int64_t total = 0;            // padded total bases
+    int64_t total_real = 0;       // sum of read lengths
+    int maxlen = 0;
+    std::vector<int64_t> h_off;
+    std::vector<int32_t> h_len;
+    DBuf<u32> fwd, rc;
+    DBuf<int64_t> off;
+    DBuf<int32_t> len;
+    DBuf<int32_t> chunk2read;
+    DBuf<u32> mask, mask_rc;
+    bool has_mask = false;
+};
+
+struct AlignParams {
+    int k = 14, w = 6, h = 35, t = 32, tspace = 100, minlen = 500, cdiff = 20, xdrop = 300, wmax = 62,
+        rounds = 3, self = 0, poolmul = 64;
+};
+
+struct HostLas {
+    std::vector<dn_las_record> rec;     // sorted in LAsort order
+    std::vector<int64_t> toff;          // trace offset (uint16 units) per record
+    std::vector<uint16_t> trace;        // (diffs, bbases) pairs
+    dn_align_stats stats{};
+};
+
+void block_upload(const dn_block_desc &d, DevBlock &out, cudaStream_t s);
+void align_blocks(const DevBlock &A, const DevBlock &B, const AlignParams &P, HostLas &out, cudaStream_t s);
+
+}  // namespace dn

@@ -1,0 +1,382 @@
+// extend.cu -- O(ND) furthest-reaching wave extension with trace points, one warp per
+// (seed, direction) task; candidate assembly, hit retirement and duplicate removal.
+// Stage K5/K6 of DESIGN.md: the device replacement for daligner's Local_Alignment wave
+// (what `daligner`/`damapper` run behind dazzler.d:6131-6170), emitting daligner-compatible
+// (diffs, bbases) pairs per tspace-tile of A (tile semantics base.d:185-242).
+//
+// Warp layout: the live wave window [lo,hi] (<= 62 diagonals, <= 64 after the +-1 growth) lives in
+// shared memory, two buffers of V (furthest A offset) and T (trace record index) indexed by
+// diagonal mod 64; lane l owns diagonals nlo+l and nlo+32+l of the new wave.  Sequence is read
+// from the 2-bit packed block with 32-bit funnel-shifted windows (16 bases per compare); the whole
+// packed block is L2-resident on B200 (126 MB L2), so slides are L1/L2 hits.
+#include "seed.cuh"
+
+namespace dn {
+
+namespace {
+
+constexpr int EXT_WARPS = 8;                 // warps per CTA
+constexpr int NEGV = -(1 << 29);
+constexpr int NEGS = -(1 << 30);
+
+__device__ __forceinline__ u32 fetch16(const u32 *__restrict__ w, int64_t g) {
+    int64_t wi = g >> 4; int sh = (int)(g & 15) << 1;
+    u32 lo = __ldg(w + wi), hi = __ldg(w + wi + 1);
+    return __funnelshift_r(lo, hi, sh);
+}
+
+__device__ __forceinline__ int slide(const u32 *__restrict__ A, int64_t ga, const u32 *__restrict__ B, int64_t gb, int lim) {
+    int s = 0;
+    while (s < lim) {
+        u32 x = fetch16(A, ga + s) ^ fetch16(B, gb + s);
+        if (x) { s += (__ffs(x) - 1) >> 1; break; }
+        s += 16;
+    }
+    return s < lim ? s : lim;
+}
+
+__host__ __device__ inline int ext_span(int la, int lb) { long long s = (long long)lb + lb / 2 + 64; return la < s ? la : (int)s; }
+
+struct Task {
+    const u32 *A, *B; int64_t ga, gb; int la, lb, firstT;
+};
+
+__device__ __forceinline__ Task make_task(const Seed &sd, int dir, const ExtGeom &G) {
+    Task t;
+    const int br = sd.bs >> 1, st = sd.bs & 1;
+    const int LA = G.a_len[sd.a], LB = G.b_len[br];
+    const int64_t oa = G.a_off[sd.a], ob = G.b_off[br];
+    if (dir == 0) {
+        t.A = G.a_fwd; t.B = st ? G.b_rc : G.b_fwd;
+        t.ga = oa + sd.apos; t.gb = ob + sd.bpos; t.la = LA - sd.apos; t.lb = LB - sd.bpos;
+        t.firstT = (sd.apos / G.ts + 1) * G.ts - sd.apos;
+    } else {
+        t.A = G.a_rc; t.B = st ? G.b_fwd : G.b_rc;
+        t.ga = oa + (LA - sd.apos); t.gb = ob + (LB - sd.bpos); t.la = sd.apos; t.lb = sd.bpos;
+        t.firstT = sd.apos > 0 ? sd.apos - ((sd.apos - 1) / G.ts) * G.ts : G.ts;
+        if (sd.apos == 0 || sd.bpos == 0) { t.la = 0; t.lb = 0; }
+    }
+    return t;
+}
+
+__global__ void __launch_bounds__(256) k_task_caps(const Seed *__restrict__ seeds, int nseeds, ExtGeom G, u32 *__restrict__ caps) {
+    int s = blockIdx.x * blockDim.x + threadIdx.x;
+    if (s >= nseeds) return;
+    Seed sd = seeds[s];
+#pragma unroll
+    for (int dir = 0; dir < 2; dir++) {
+        Task t = make_task(sd, dir, G);
+        caps[2 * s + dir] = (u32)(ext_span(t.la, t.lb) / G.ts + 3);
+    }
+}
+
+__global__ void __launch_bounds__(EXT_WARPS * 32) k_extend(const Seed *__restrict__ seeds, int ntasks, ExtGeom G,
+                                                           const int64_t *__restrict__ tile_off, int2 *__restrict__ tiles,
+                                                           ExtOut *__restrict__ outs, int4 *__restrict__ pool_all,
+                                                           int64_t pool_stride, int *__restrict__ counter) {
+    __shared__ int sV[EXT_WARPS][2][64];
+    __shared__ int sT[EXT_WARPS][2][64];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const u32 FULL = 0xffffffffu;
+    int4 *pool = pool_all + (int64_t)(blockIdx.x * EXT_WARPS + warp) * pool_stride;
+    const int ts = G.ts, C = G.cdiff, X = G.xdrop, WM = G.wmax;
+
+    for (;;) {
+        int task = 0;
+        if (lane == 0) task = atomicAdd(counter, 1);
+        task = __shfl_sync(FULL, task, 0);
+        if (task >= ntasks) break;
+        const Seed sd = seeds[task >> 1];
+        const Task tk = make_task(sd, task & 1, G);
+        const int la = tk.la, lb = tk.lb, firstT = tk.firstT;
+        const int poolcap = G.poolmul * (ext_span(la, lb) / ts + 4);
+        // number of tile boundaries at or below relative A offset i
+        auto NB = [&](int i) -> int { return i >= firstT ? (int)__umulhi((u32)(i - firstT), G.ts_magic) + 1 : 0; };
+
+        int npool = 0;
+        int lo = 0, hi = 0, d = 0;
+        int bS = NEGS, bi = 0, bk = 0, bd = 0, bT = -1;     // lane-local best
+        int gbest;                                            // warp-uniform best S so far
+        int cur = 0;
+        {   // wave 0 (uniform across lanes)
+            int lim = la < lb ? la : lb;
+            int i = slide(tk.A, tk.ga, tk.B, tk.gb, lim);
+            int n = NB(i), T = -1;
+            if (n > poolcap) {
+                if (lane == 0) outs[task] = ExtOut{0, 0, 0, 0};
+                continue;
+            }
+            if (lane == 0) {
+                for (int q = 1; q <= n; q++) { pool[npool] = make_int4(T, firstT + (q - 1) * ts, 0, q); T = npool++; }
+                sV[warp][0][0] = i; sT[warp][0][0] = T;
+                bS = 3 * (2 * i); bi = i; bk = 0; bd = 0; bT = T;
+            }
+            npool = n;
+            gbest = 3 * (2 * i);
+            if (i == la || i == lb) { lo = 1; hi = 0; }
+            __syncwarp();
+        }
+        while (lo <= hi) {
+            d++;
+            const int nlo = lo - 1, nhi = hi + 1;
+            const int *Vo = sV[warp][cur], *To = sT[warp][cur];
+            int *Vn = sV[warp][cur ^ 1], *Tn = sT[warp][cur ^ 1];
+            int ci[2], cpi[2], cT[2];
+            int need_l = 0;
+#pragma unroll
+            for (int sl = 0; sl < 2; sl++) {
+                const int k = nlo + lane + 32 * sl;
+                int i = NEGV, pi = NEGV, pT = -1;
+                if (k <= nhi) {
+                    int vs = (k >= lo && k <= hi) ? Vo[k & 63] : NEGV;
+                    int vd = (k - 1 >= lo && k - 1 <= hi) ? Vo[(k - 1) & 63] : NEGV;
+                    int vi = (k + 1 >= lo && k + 1 <= hi) ? Vo[(k + 1) & 63] : NEGV;
+                    if (vs > NEGV) { i = vs + 1; pi = vs; pT = To[k & 63]; }
+                    if (vd > NEGV && vd + 1 > i) { i = vd + 1; pi = vd; pT = To[(k - 1) & 63]; }
+                    if (vi > NEGV && vi > i) { i = vi; pi = vi; pT = To[(k + 1) & 63]; }
+                    if (i > NEGV) { int j = i - k; if (i > la || j > lb || j < 0) i = NEGV; }
+                    if (i > NEGV) {
+                        int j = i - k;
+                        int lim = min(la - i, lb - j);
+                        i += slide(tk.A, tk.ga + i, tk.B, tk.gb + j, lim);
+                        need_l += NB(i) - NB(pi);
+                    }
+                }
+                ci[sl] = i; cpi[sl] = pi; cT[sl] = pT;
+            }
+            const int need = __reduce_add_sync(FULL, need_l);
+            if (npool + need > poolcap) break;                  // pool exhausted: stop before this wave
+            if (need) {
+                int pre = need_l;                               // inclusive scan across lanes
+#pragma unroll
+                for (int o = 1; o < 32; o <<= 1) { int t = __shfl_up_sync(FULL, pre, o); if (lane >= o) pre += t; }
+                int at = npool + pre - need_l;
+#pragma unroll
+                for (int sl = 0; sl < 2; sl++) {
+                    if (ci[sl] > NEGV) {
+                        const int k = nlo + lane + 32 * sl;
+                        int T = cT[sl];
+                        for (int q = NB(cpi[sl]) + 1, qe = NB(ci[sl]); q <= qe; q++) {
+                            int bnd = firstT + (q - 1) * ts;
+                            pool[at] = make_int4(T, bnd - k, d, q); T = at++;
+                        }
+                        cT[sl] = T;
+                    }
+                }
+                npool += need;
+            }
+            int S[2];
+#pragma unroll
+            for (int sl = 0; sl < 2; sl++) {
+                const int k = nlo + lane + 32 * sl;
+                S[sl] = ci[sl] > NEGV ? 3 * (2 * ci[sl] - k) - C * d : NEGS;
+                if (S[sl] > bS) { bS = S[sl]; bi = ci[sl]; bk = k; bd = d; bT = cT[sl]; }
+            }
+            const int waveS = __reduce_max_sync(FULL, max(S[0], S[1]));
+            gbest = max(gbest, waveS);
+            int kmin = 1 << 30, kmax = -(1 << 30);
+#pragma unroll
+            for (int sl = 0; sl < 2; sl++) {
+                const int k = nlo + lane + 32 * sl;
+                bool alive = ci[sl] > NEGV;
+                if (alive) {
+                    int j = ci[sl] - k;
+                    if (S[sl] < gbest - X || ci[sl] == la || j == lb) alive = false;
+                }
+                if (k <= nhi) { Vn[k & 63] = alive ? ci[sl] : NEGV; Tn[k & 63] = cT[sl]; }
+                if (alive) { kmin = min(kmin, k); kmax = max(kmax, k); }
+            }
+            int alo = __reduce_min_sync(FULL, kmin), ahi = __reduce_max_sync(FULL, kmax);
+            if (alo > ahi) break;
+            if (ahi - alo + 1 > WM) {
+                int wk = 1 << 30;
+                if (S[0] == waveS) wk = nlo + lane;
+                else if (S[1] == waveS) wk = nlo + lane + 32;
+                const int wavek = __reduce_min_sync(FULL, wk);
+                int l2 = wavek - (WM / 2 - 1); if (l2 < alo) l2 = alo;
+                int h2 = l2 + WM - 1; if (h2 > ahi) h2 = ahi;
+                l2 = h2 - WM + 1; if (l2 < alo) l2 = alo;
+                alo = l2; ahi = h2;
+            }
+            lo = alo; hi = ahi; cur ^= 1;
+            __syncwarp();
+        }
+        // winner: max S, then min d, then min k
+        const int mS = __reduce_max_sync(FULL, bS);
+        const int md = __reduce_min_sync(FULL, bS == mS ? bd : (1 << 30));
+        const int mk = __reduce_min_sync(FULL, (bS == mS && bd == md) ? bk : (1 << 30));
+        const u32 win = __ballot_sync(FULL, bS == mS && bd == md && bk == mk);
+        const int wl = __ffs(win) - 1;
+        const int besti = __shfl_sync(FULL, bi, wl), bestk = __shfl_sync(FULL, bk, wl);
+        const int bestd = __shfl_sync(FULL, bd, wl), bestT = __shfl_sync(FULL, bT, wl);
+        __syncwarp();
+        if (lane == 0) {
+            int2 *tl = tiles + tile_off[task];
+            int n = NB(besti);
+            int T = bestT, lastj = 0, lastd = 0;
+            if (T >= 0) { int4 r = pool[T]; lastj = r.y; lastd = r.z; }
+            int4 curr = T >= 0 ? pool[T] : make_int4(-1, 0, 0, 0);
+            for (int q = n; q >= 1; q--) {
+                int pj = 0, pd = 0; int4 pr = make_int4(-1, 0, 0, 0);
+                if (curr.x >= 0) { pr = pool[curr.x]; pj = pr.y; pd = pr.z; }
+                tl[q - 1] = make_int2(curr.y - pj, curr.z - pd);
+                curr = pr;
+            }
+            int lastB = n > 0 ? firstT + (n - 1) * ts : 0;
+            if (besti > lastB) { tl[n] = make_int2((besti - bestk) - lastj, bestd - lastd); n++; }
+            outs[task] = ExtOut{besti, besti - bestk, bestd, n};
+        }
+        __syncwarp();
+    }
+}
+
+// ---------------------------------------------------------------- candidate assembly
+
+__global__ void __launch_bounds__(256) k_combine(const Seed *__restrict__ seeds, int nseeds, ExtGeom G, int minlen,
+                                                 const int64_t *__restrict__ tile_off, const int2 *__restrict__ tiles,
+                                                 const ExtOut *__restrict__ outs, Cand *__restrict__ cand,
+                                                 int32_t *__restrict__ valid, u32 *__restrict__ ntl) {
+    int s = blockIdx.x * blockDim.x + threadIdx.x;
+    if (s >= nseeds) return;
+    const Seed sd = seeds[s];
+    const ExtOut fo = outs[2 * s], ro = outs[2 * s + 1];
+    const int ts = G.ts;
+    const int ab = sd.apos - ro.i_end, bb = sd.bpos - ro.j_end, ae = sd.apos + fo.i_end, be = sd.bpos + fo.j_end;
+    const bool ok = (ae - ab) + (be - bb) >= 2 * minlen;
+    const bool merge = (sd.apos % ts != 0) && ro.ntiles > 0 && fo.ntiles > 0;
+    const int nt = ro.ntiles + fo.ntiles - (merge ? 1 : 0);
+    Cand c;
+    c.a = sd.a; c.bs = sd.bs; c.ab = ab; c.ae = ae; c.bb = bb; c.be = be; c.diffs = fo.d_end + ro.d_end; c.nt = nt; c.toff = 0;
+    int dmin = ab - bb, dmax = dmin;
+    if (ok) {
+        const int2 *ft = tiles + tile_off[2 * s], *rt = tiles + tile_off[2 * s + 1];
+        int apos = ab, bpos = bb, q = 0;
+        auto step = [&](int bbases) {
+            int aend = (q == nt - 1) ? ae : (apos / ts + 1) * ts;
+            bpos += bbases; apos = aend; q++;
+            int dg = apos - bpos; dmin = min(dmin, dg); dmax = max(dmax, dg);
+        };
+        for (int x = ro.ntiles - 1; x >= (merge ? 1 : 0); x--) step(rt[x].x);
+        if (merge) step(rt[0].x + ft[0].x);
+        for (int x = merge ? 1 : 0; x < fo.ntiles; x++) step(ft[x].x);
+    }
+    c.dmin = dmin; c.dmax = dmax;
+    cand[s] = c;
+    valid[s] = ok ? 1 : 0;
+    ntl[s] = ok ? (u32)nt : 0u;
+}
+
+__global__ void __launch_bounds__(256) k_write_traces(const Seed *__restrict__ seeds, int nseeds, ExtGeom G,
+                                                      const int64_t *__restrict__ tile_off, const int2 *__restrict__ tiles,
+                                                      const ExtOut *__restrict__ outs, const Cand *__restrict__ cand,
+                                                      const int32_t *__restrict__ valid, const int32_t *__restrict__ vidx,
+                                                      const int64_t *__restrict__ toff, Cand *__restrict__ cand_out,
+                                                      uint16_t *__restrict__ trace) {
+    int s = blockIdx.x * blockDim.x + threadIdx.x;
+    if (s >= nseeds || !valid[s]) return;
+    const Seed sd = seeds[s];
+    const ExtOut fo = outs[2 * s], ro = outs[2 * s + 1];
+    const bool merge = (sd.apos % G.ts != 0) && ro.ntiles > 0 && fo.ntiles > 0;
+    const int2 *ft = tiles + tile_off[2 * s], *rt = tiles + tile_off[2 * s + 1];
+    Cand c = cand[s];
+    c.toff = 2 * toff[s];
+    uint16_t *o = trace + c.toff;
+    for (int x = ro.ntiles - 1; x >= (merge ? 1 : 0); x--) { *o++ = (uint16_t)rt[x].y; *o++ = (uint16_t)rt[x].x; }
+    if (merge) { *o++ = (uint16_t)(rt[0].y + ft[0].y); *o++ = (uint16_t)(rt[0].x + ft[0].x); }
+    for (int x = merge ? 1 : 0; x < fo.ntiles; x++) { *o++ = (uint16_t)ft[x].y; *o++ = (uint16_t)ft[x].x; }
+    cand_out[vidx[s]] = c;
+}
+
+// ---------------------------------------------------------------- hit retirement
+
+__device__ __forceinline__ u64 gkey(int bs, int a) { return ((u64)(u32)bs << 32) | (u32)a; }
+
+__device__ __forceinline__ int group_lower(const Cand *__restrict__ c, int lo, int hi, u64 key) {
+    while (lo < hi) { int m = (lo + hi) >> 1; if (gkey(c[m].bs, c[m].a) < key) lo = m + 1; else hi = m; }
+    return lo;
+}
+
+__global__ void __launch_bounds__(256) k_retire(const ulonglong2 *__restrict__ hits, int64_t n, const uint8_t *__restrict__ consumed,
+                                                const Cand *__restrict__ rc, int nrc, SeedGeom G, int w, int32_t *__restrict__ keep) {
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    int kp = consumed[i] ? 0 : 1;
+    if (kp && nrc > 0) {
+        ulonglong2 h = hits[i];
+        u64 gd = h.x & ((1ull << G.gdbits) - 1ull);
+        int bs = (int)(h.x >> G.gdbits);
+        int lo = 0, hi = G.na;
+        while (hi - lo > 1) { int mid = (lo + hi) >> 1; if ((u64)G.a_dbase[mid] <= gd) lo = mid; else hi = mid; }
+        const int a = lo, apos = (int)(u32)h.y, bpos = (int)(h.y >> 32), diag = apos - bpos;
+        const u64 key = gkey(bs, a);
+        for (int x = group_lower(rc, 0, nrc, key); x < nrc && gkey(rc[x].bs, rc[x].a) == key; x++) {
+            const Cand c = rc[x];
+            if (apos >= c.ab && apos <= c.ae && diag >= c.dmin - (1 << w) && diag <= c.dmax + (1 << w)) { kp = 0; break; }
+        }
+    }
+    keep[i] = kp;
+}
+
+__global__ void __launch_bounds__(256) k_compact_hits(const ulonglong2 *__restrict__ hits, int64_t n, const int32_t *__restrict__ keep,
+                                                      const int32_t *__restrict__ kidx, ulonglong2 *__restrict__ out) {
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    if (keep[i]) out[kidx[i]] = hits[i];
+}
+
+// drop[j] = some other candidate i of the same (a, bs) contains j in both coordinates (identical: lower index wins)
+__global__ void __launch_bounds__(256) k_dedupe(const Cand *__restrict__ c, int n, const int32_t *__restrict__ rbeg, int nrounds,
+                                                uint8_t *__restrict__ drop) {
+    int j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= n) return;
+    const Cand x = c[j];
+    const u64 key = gkey(x.bs, x.a);
+    int dr = 0;
+    for (int r = 0; r < nrounds && !dr; r++) {
+        const int e = rbeg[r + 1];
+        for (int i = group_lower(c, rbeg[r], e, key); i < e && gkey(c[i].bs, c[i].a) == key; i++) {
+            if (i == j) continue;
+            const Cand y = c[i];
+            if (y.ab <= x.ab && x.ae <= y.ae && y.bb <= x.bb && x.be <= y.be) {
+                bool same = y.ab == x.ab && x.ae == y.ae && y.bb == x.bb && x.be == y.be;
+                if (!same || i < j) { dr = 1; break; }
+            }
+        }
+    }
+    drop[j] = (uint8_t)dr;
+}
+
+}  // namespace
+
+void launch_task_caps(const Seed *seeds, int nseeds, ExtGeom G, u32 *caps, cudaStream_t s) {
+    DN_LAUNCH(k_task_caps, (nseeds + 255) / 256, 256, 0, s, seeds, nseeds, G, caps);
+}
+void launch_extend(const Seed *seeds, int nseeds, ExtGeom G, const int64_t *tile_off, int2 *tiles, ExtOut *outs,
+                   int4 *pool, int64_t pool_stride, int nwarps_total, int *counter, cudaStream_t s) {
+    int ctas = nwarps_total / EXT_WARPS;
+    DN_LAUNCH(k_extend, ctas, EXT_WARPS * 32, 0, s, seeds, 2 * nseeds, G, tile_off, tiles, outs, pool, pool_stride, counter);
+}
+void launch_combine(const Seed *seeds, int nseeds, ExtGeom G, int minlen, const int64_t *tile_off, const int2 *tiles,
+                    const ExtOut *outs, Cand *cand_all, int32_t *valid, u32 *ntl, cudaStream_t s) {
+    DN_LAUNCH(k_combine, (nseeds + 255) / 256, 256, 0, s, seeds, nseeds, G, minlen, tile_off, tiles, outs, cand_all, valid, ntl);
+}
+void launch_write_traces(const Seed *seeds, int nseeds, ExtGeom G, const int64_t *tile_off, const int2 *tiles,
+                         const ExtOut *outs, const Cand *cand_all, const int32_t *valid, const int32_t *vidx,
+                         const int64_t *toff, Cand *cand_out, uint16_t *trace, cudaStream_t s) {
+    DN_LAUNCH(k_write_traces, (nseeds + 255) / 256, 256, 0, s, seeds, nseeds, G, tile_off, tiles, outs, cand_all, valid, vidx,
+              toff, cand_out, trace);
+}
+void launch_retire(const ulonglong2 *hits, int64_t n, const uint8_t *consumed, const Cand *rc, int nrc, SeedGeom G, int w,
+                   int32_t *keep, cudaStream_t s) {
+    DN_LAUNCH(k_retire, (unsigned)((n + 255) / 256), 256, 0, s, hits, n, consumed, rc, nrc, G, w, keep);
+}
+void launch_compact_hits(const ulonglong2 *hits, int64_t n, const int32_t *keep, const int32_t *kidx, ulonglong2 *out, cudaStream_t s) {
+    DN_LAUNCH(k_compact_hits, (unsigned)((n + 255) / 256), 256, 0, s, hits, n, keep, kidx, out);
+}
+void launch_dedupe(const Cand *cands, int ncand, const int32_t *round_beg, int nrounds, uint8_t *drop, cudaStream_t s) {
+    DN_LAUNCH(k_dedupe, (ncand + 255) / 256, 256, 0, s, cands, ncand, round_beg, nrounds, drop);
+}
+
+int ext_warps_per_cta() { return EXT_WARPS; }
+
+}  // namespace dn

@@ -1,0 +1,133 @@
+// radix.cu -- hand-written stable LSD radix sort for the k-mer tuple lists (8-byte keys) and the
+// seed-hit lists (16-byte records), 8-bit digits.  Replaces daligner's threaded byte-radix sort
+// of k-mer tuples (what `daligner`/`damapper` run behind dazzler.d:6131-6170).
+//
+// Per pass: (1) per-CTA digit histogram over a contiguous range, (2) one-CTA exclusive scan of the
+// [digit][cta] table, (3) stable scatter.  Grid = 4 CTAs per SM, each CTA walks its range in tiles.
+// Algorithmic HBM traffic per pass: 2 reads + 1 write of the array.
+#include "common.cuh"
+
+namespace dn {
+namespace {
+
+constexpr int RS_THREADS = 256;
+constexpr int RS_WARPS = RS_THREADS / 32;
+constexpr int RS_ITEMS = 8;                       // per thread per tile
+constexpr int RS_WTILE = 32 * RS_ITEMS;           // items per warp per tile (contiguous)
+constexpr int RS_TILE = RS_WTILE * RS_WARPS;      // 2048
+
+template <typename Item, int FIELD> __device__ __forceinline__ u32 digit_of(const Item &it, int shift);
+template <> __device__ __forceinline__ u32 digit_of<u64, 0>(const u64 &it, int shift) { return (u32)(it >> shift) & 255u; }
+template <> __device__ __forceinline__ u32 digit_of<ulonglong2, 0>(const ulonglong2 &it, int shift) { return (u32)(it.x >> shift) & 255u; }
+template <> __device__ __forceinline__ u32 digit_of<ulonglong2, 1>(const ulonglong2 &it, int shift) { return (u32)((it.y & 0xffffffffull) >> shift) & 255u; }
+
+__host__ __device__ inline size_t cta_range(size_t n, int G) {
+    size_t per = (n + G - 1) / G;
+    return (per + RS_TILE - 1) / RS_TILE * RS_TILE;
+}
+
+template <typename Item, int FIELD>
+__global__ void __launch_bounds__(RS_THREADS) k_radix_hist(const Item *__restrict__ in, size_t n, int shift, u32 *__restrict__ hist /* [256][G] */) {
+    __shared__ u32 h[256];
+    h[threadIdx.x] = 0;
+    __syncthreads();
+    const size_t per = cta_range(n, gridDim.x);
+    size_t beg = per * blockIdx.x, end = beg + per; if (end > n) end = n;
+    for (size_t i = beg + threadIdx.x; i < end; i += RS_THREADS) atomicAdd(&h[digit_of<Item, FIELD>(in[i], shift)], 1u);
+    __syncthreads();
+    hist[(size_t)threadIdx.x * gridDim.x + blockIdx.x] = h[threadIdx.x];
+}
+
+// one CTA, 256 threads: exclusive scan of hist in digit-major order
+__global__ void __launch_bounds__(256) k_radix_scan(u32 *hist, int G) {
+    __shared__ u32 tot[256];
+    u32 *row = hist + (size_t)threadIdx.x * G;
+    u32 s = 0;
+    for (int c = 0; c < G; c++) s += row[c];
+    tot[threadIdx.x] = s;
+    __syncthreads();
+    if (threadIdx.x == 0) { u32 a = 0; for (int d = 0; d < 256; d++) { u32 t = tot[d]; tot[d] = a; a += t; } }
+    __syncthreads();
+    u32 a = tot[threadIdx.x];
+    for (int c = 0; c < G; c++) { u32 t = row[c]; row[c] = a; a += t; }
+}
+
+template <typename Item, int FIELD>
+__global__ void __launch_bounds__(RS_THREADS) k_radix_scatter(const Item *__restrict__ in, Item *__restrict__ out, size_t n, int shift,
+                                                              const u32 *__restrict__ hist) {
+    __shared__ u32 whist[RS_WARPS][256];
+    __shared__ u32 base[256];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    base[threadIdx.x] = hist[(size_t)threadIdx.x * gridDim.x + blockIdx.x];
+    const size_t per = cta_range(n, gridDim.x);
+    size_t beg = per * blockIdx.x, end = beg + per; if (end > n) end = n;
+    for (size_t t0 = beg; t0 < end; t0 += RS_TILE) {
+#pragma unroll
+        for (int w = 0; w < RS_WARPS; w++) whist[w][threadIdx.x] = 0;
+        __syncthreads();
+        Item it[RS_ITEMS]; u32 rk[RS_ITEMS]; u32 dg[RS_ITEMS];
+        const size_t wbase = t0 + (size_t)warp * RS_WTILE;
+#pragma unroll
+        for (int s = 0; s < RS_ITEMS; s++) {
+            size_t idx = wbase + s * 32 + lane;
+            bool valid = idx < end;
+            if (valid) it[s] = in[idx];
+            u32 vmask = __ballot_sync(0xffffffffu, valid);
+            if (valid) {
+                u32 d = digit_of<Item, FIELD>(it[s], shift);
+                dg[s] = d;
+                u32 peers = __match_any_sync(vmask, d);
+                u32 before = whist[warp][d];
+                rk[s] = before + __popc(peers & ((1u << lane) - 1u));
+                __syncwarp(vmask);
+                if ((peers & ((1u << lane) - 1u)) == 0) whist[warp][d] = before + __popc(peers);
+            }
+            __syncwarp();
+        }
+        __syncthreads();
+        {   // exclusive scan over warps for digit = threadIdx.x, advance the CTA base
+            u32 a = base[threadIdx.x];
+#pragma unroll
+            for (int w = 0; w < RS_WARPS; w++) { u32 t = whist[w][threadIdx.x]; whist[w][threadIdx.x] = a; a += t; }
+            base[threadIdx.x] = a;
+        }
+        __syncthreads();
+#pragma unroll
+        for (int s = 0; s < RS_ITEMS; s++) {
+            size_t idx = wbase + s * 32 + lane;
+            if (idx < end) out[whist[warp][dg[s]] + rk[s]] = it[s];
+        }
+        __syncthreads();
+    }
+}
+
+template <typename Item, int FIELD>
+Item *radix_sort_impl(Item *a, Item *b, size_t n, int bit_lo, int bit_hi, cudaStream_t s) {
+    if (n == 0 || bit_hi <= bit_lo) return a;
+    if (n >= (1ull << 32)) throw Error("radix sort: more than 2^32 items");
+    int G = sm_count() * 4;
+    size_t need = (n + RS_TILE - 1) / RS_TILE;
+    if ((size_t)G > need) G = (int)need;
+    DBuf<u32> hist((size_t)256 * G);
+    Item *src = a, *dst = b;
+    for (int shift = bit_lo; shift < bit_hi; shift += 8) {
+        DN_LAUNCH((k_radix_hist<Item, FIELD>), G, RS_THREADS, 0, s, (const Item *)src, n, shift, hist.p);
+        DN_LAUNCH(k_radix_scan, 1, 256, 0, s, hist.p, G);
+        DN_LAUNCH((k_radix_scatter<Item, FIELD>), G, RS_THREADS, 0, s, (const Item *)src, dst, n, shift, (const u32 *)hist.p);
+        Item *t = src; src = dst; dst = t;
+    }
+    DN_CUDA(cudaStreamSynchronize(s));    // hist freed on return
+    return src;
+}
+
+}  // namespace
+
+u64 *radix_sort_u64(u64 *keys, u64 *tmp, size_t n, int bit_lo, int bit_hi, cudaStream_t s) {
+    return radix_sort_impl<u64, 0>(keys, tmp, n, bit_lo, bit_hi, s);
+}
+ulonglong2 *radix_sort_rec16(ulonglong2 *recs, ulonglong2 *tmp, size_t n, int field, int bit_lo, int bit_hi, cudaStream_t s) {
+    if (field == 0) return radix_sort_impl<ulonglong2, 0>(recs, tmp, n, bit_lo, bit_hi, s);
+    return radix_sort_impl<ulonglong2, 1>(recs, tmp, n, bit_lo, bit_hi, s);
+}
+
+}  // namespace dn

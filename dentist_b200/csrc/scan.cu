@@ -1,0 +1,111 @@
+// scan.cu -- hand-written exclusive prefix sums (three-phase: tile reduce, recursive scan of the
+// tile sums, tile scan + offset).  HBM-bound: reads the input twice, writes the output once.
+#include "common.cuh"
+
+namespace dn {
+
+std::atomic<unsigned long long> g_launches{0};
+
+int sm_count() {
+    static int n = 0;
+    if (!n) { int dev; DN_CUDA(cudaGetDevice(&dev)); DN_CUDA(cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev)); }
+    return n;
+}
+
+namespace {
+constexpr int SCAN_THREADS = 256;
+constexpr int SCAN_ITEMS = 16;
+constexpr int SCAN_TILE = SCAN_THREADS * SCAN_ITEMS;
+
+template <typename Tout>
+__device__ __forceinline__ Tout block_exclusive(Tout v, Tout *total, Tout *smem /* 32 */) {
+    // exclusive scan of one value per thread across the block
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    Tout inc = v;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) { Tout t = __shfl_up_sync(0xffffffffu, inc, o); if (lane >= o) inc += t; }
+    if (lane == 31) smem[warp] = inc;
+    __syncthreads();
+    if (warp == 0) {
+        Tout w = lane < (SCAN_THREADS / 32) ? smem[lane] : Tout(0);
+        Tout winc = w;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) { Tout t = __shfl_up_sync(0xffffffffu, winc, o); if (lane >= o) winc += t; }
+        smem[lane] = winc - w;               // exclusive warp offsets
+        if (lane == 31) smem[32] = winc;     // block total
+    }
+    __syncthreads();
+    Tout res = smem[warp] + inc - v;
+    if (total) *total = smem[32];
+    __syncthreads();
+    return res;
+}
+
+template <typename Tin, typename Tout>
+__global__ void __launch_bounds__(SCAN_THREADS) k_scan_reduce(const Tin *__restrict__ in, Tout *__restrict__ sums, size_t n) {
+    __shared__ Tout sm[33];
+    size_t base = (size_t)blockIdx.x * SCAN_TILE;
+    Tout acc = 0;
+#pragma unroll
+    for (int i = 0; i < SCAN_ITEMS; i++) {
+        size_t idx = base + (size_t)i * SCAN_THREADS + threadIdx.x;     // coalesced
+        if (idx < n) acc += (Tout)in[idx];
+    }
+    Tout total;
+    block_exclusive<Tout>(acc, &total, sm);
+    if (threadIdx.x == 0) sums[blockIdx.x] = total;
+}
+
+template <typename Tin, typename Tout>
+__global__ void __launch_bounds__(SCAN_THREADS) k_scan_apply(const Tin *__restrict__ in, Tout *__restrict__ out,
+                                                             const Tout *__restrict__ offs, size_t n, Tout *total_out) {
+    __shared__ Tout sm[33];
+    __shared__ Tout tile[SCAN_TILE];
+    size_t base = (size_t)blockIdx.x * SCAN_TILE;
+#pragma unroll
+    for (int i = 0; i < SCAN_ITEMS; i++) {
+        size_t idx = base + (size_t)i * SCAN_THREADS + threadIdx.x;
+        tile[i * SCAN_THREADS + threadIdx.x] = idx < n ? (Tout)in[idx] : Tout(0);
+    }
+    __syncthreads();
+    Tout v[SCAN_ITEMS]; Tout acc = 0;
+#pragma unroll
+    for (int i = 0; i < SCAN_ITEMS; i++) { v[i] = tile[threadIdx.x * SCAN_ITEMS + i]; acc += v[i]; }
+    Tout total;
+    Tout ex = block_exclusive<Tout>(acc, &total, sm) + (offs ? offs[blockIdx.x] : Tout(0));
+#pragma unroll
+    for (int i = 0; i < SCAN_ITEMS; i++) { tile[threadIdx.x * SCAN_ITEMS + i] = ex; ex += v[i]; }
+    __syncthreads();
+#pragma unroll
+    for (int i = 0; i < SCAN_ITEMS; i++) {
+        size_t idx = base + (size_t)i * SCAN_THREADS + threadIdx.x;
+        if (idx < n) out[idx] = tile[i * SCAN_THREADS + threadIdx.x];
+    }
+    if (total_out && blockIdx.x == gridDim.x - 1 && threadIdx.x == 0)
+        *total_out = (offs ? offs[blockIdx.x] : Tout(0)) + total;
+}
+
+template <typename Tin, typename Tout>
+void scan_rec(const Tin *in, Tout *out, size_t n, Tout *d_total, cudaStream_t s) {
+    if (n == 0) { if (d_total) DN_CUDA(cudaMemsetAsync(d_total, 0, sizeof(Tout), s)); return; }
+    size_t nb = (n + SCAN_TILE - 1) / SCAN_TILE;
+    if (nb == 1) {
+        DN_LAUNCH((k_scan_apply<Tin, Tout>), 1, SCAN_THREADS, 0, s, in, out, (const Tout *)nullptr, n, d_total);
+        return;
+    }
+    DBuf<Tout> sums(nb), offs(nb);
+    DN_LAUNCH((k_scan_reduce<Tin, Tout>), (unsigned)nb, SCAN_THREADS, 0, s, in, sums.p, n);
+    scan_rec<Tout, Tout>(sums.p, offs.p, nb, nullptr, s);
+    DN_LAUNCH((k_scan_apply<Tin, Tout>), (unsigned)nb, SCAN_THREADS, 0, s, in, out, (const Tout *)offs.p, n, d_total);
+    DN_CUDA(cudaStreamSynchronize(s));       // sums/offs are freed on return
+}
+}  // namespace
+
+void exclusive_scan_u32_to_i64(const u32 *in, int64_t *out, size_t n, int64_t *d_total, cudaStream_t s) {
+    scan_rec<u32, long long>(in, (long long *)out, n, (long long *)d_total, s);
+}
+void exclusive_scan_i32(const int32_t *in, int32_t *out, size_t n, int32_t *d_total, cudaStream_t s) {
+    scan_rec<int32_t, int32_t>(in, out, n, d_total, s);
+}
+
+}  // namespace dn

@@ -1,0 +1,318 @@
+// seed.cu -- block upload (2-bit pack + reverse complement), k-mer tuple emit, sorted-list join
+// into seed hits, diagonal-band filter and seed selection.  Stages K0-K4 of DESIGN.md; the
+// device-side replacement for daligner's tuple sort / merge / band filter that DENTIST reaches
+// through dazzler.d:6131-6170.
+#include "engine.cuh"
+#include "seed.cuh"
+
+namespace dn {
+
+// ------------------------------------------------------------------------- K0: upload / pack
+
+__global__ void __launch_bounds__(128) k_pack(const uint8_t *__restrict__ data, const int64_t *__restrict__ boff,
+                                              const int32_t *__restrict__ len, const int64_t *__restrict__ off,
+                                              int format, u32 *__restrict__ fwd, u32 *__restrict__ rc) {
+    const int r = blockIdx.x;
+    const int L = len[r];
+    const uint8_t *src = data + boff[r];
+    const int64_t w0 = off[r] >> 4;
+    const int nw = (int)((off[r + 1] - off[r]) >> 4);
+    for (int w = threadIdx.x; w < nw; w += blockDim.x) {
+        u32 f = 0, c = 0;
+#pragma unroll
+        for (int j = 0; j < 16; j++) {
+            int p = w * 16 + j;
+            if (p < L) {
+                u32 bf, br;
+                int q = L - 1 - p;
+                if (format == DN_SEQ_BYTES) { bf = src[p] & 3u; br = 3u - (src[q] & 3u); }
+                else {
+                    bf = (src[p >> 2] >> (6 - 2 * (p & 3))) & 3u;
+                    br = 3u - ((src[q >> 2] >> (6 - 2 * (q & 3))) & 3u);
+                }
+                f |= bf << (2 * j); c |= br << (2 * j);
+            }
+        }
+        fwd[w0 + w] = f; rc[w0 + w] = c;
+    }
+}
+
+__global__ void k_chunk2read(const int64_t *__restrict__ off, int nreads, int32_t *__restrict__ c2r) {
+    int r = blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= nreads) return;
+    int64_t c0 = (off[r] + 1023) >> 10, c1 = (off[r + 1] + 1023) >> 10;
+    for (int64_t c = c0; c < c1; c++) c2r[c] = r;
+}
+
+// one thread per mask interval: set bits in the forward and the mirrored (rc) bit arrays
+__global__ void k_mask_bits(const int64_t *__restrict__ anno, const int32_t *__restrict__ mdata, int nreads,
+                            const int64_t *__restrict__ off, const int32_t *__restrict__ len,
+                            u32 *__restrict__ mask, u32 *__restrict__ mask_rc) {
+    int r = blockIdx.x;
+    int64_t i0 = anno[r] / 8, i1 = anno[r + 1] / 8;      // (begin,end) int32 pairs
+    const int L = len[r];
+    for (int64_t i = i0 + threadIdx.x; i < i1; i += blockDim.x) {
+        int b = mdata[2 * i], e = mdata[2 * i + 1];
+        if (b < 0) b = 0;
+        if (e > L) e = L;
+        for (int p = b; p < e; p++) {
+            int64_t g = off[r] + p, gr = off[r] + (L - 1 - p);
+            atomicOr(&mask[g >> 5], 1u << (g & 31));
+            atomicOr(&mask_rc[gr >> 5], 1u << (gr & 31));
+        }
+    }
+}
+
+void block_upload(const dn_block_desc &d, DevBlock &B, cudaStream_t s) {
+    if (d.nreads < 0 || (d.nreads > 0 && (!d.rlen || !d.boff || !d.data))) throw Error("dn_block_desc: null field");
+    B.nreads = d.nreads;
+    B.h_len.assign(d.rlen, d.rlen + d.nreads);
+    B.h_off.resize(d.nreads + 1);
+    int64_t g = 0; B.maxlen = 0; B.total_real = 0;
+    for (int r = 0; r < d.nreads; r++) {
+        if (d.rlen[r] < 0) throw Error("negative read length");
+        B.h_off[r] = g; g += ((int64_t)d.rlen[r] + 63) / 64 * 64;
+        if (d.rlen[r] > B.maxlen) B.maxlen = d.rlen[r];
+        B.total_real += d.rlen[r];
+        int64_t need = d.format == DN_SEQ_BPS ? ((int64_t)d.rlen[r] + 3) / 4 : d.rlen[r];
+        if (d.boff[r] < 0 || d.boff[r] + need > d.data_bytes) throw Error("dn_block_desc: read outside data");
+    }
+    B.h_off[d.nreads] = g; B.total = g;
+    if (2 * g >= (1ll << 32) - 1024) throw Error("block too large: 2*padded bases must be < 2^32");
+    size_t nwords = (size_t)(g >> 4) + 8;
+    B.fwd.alloc(nwords); B.rc.alloc(nwords);
+    B.fwd.zero(s); B.rc.zero(s);
+    B.off.alloc(d.nreads + 1); B.len.alloc(d.nreads > 0 ? d.nreads : 1);
+    B.chunk2read.alloc((size_t)(g >> 10) + 2);
+    B.chunk2read.zero(s);
+    DN_CUDA(cudaMemcpyAsync(B.off.p, B.h_off.data(), sizeof(int64_t) * (d.nreads + 1), cudaMemcpyHostToDevice, s));
+    if (d.nreads == 0) { DN_CUDA(cudaStreamSynchronize(s)); return; }
+    DN_CUDA(cudaMemcpyAsync(B.len.p, B.h_len.data(), sizeof(int32_t) * d.nreads, cudaMemcpyHostToDevice, s));
+    DBuf<uint8_t> raw((size_t)d.data_bytes + 16);
+    DBuf<int64_t> boff(d.nreads);
+    DN_CUDA(cudaMemcpyAsync(raw.p, d.data, d.data_bytes, cudaMemcpyHostToDevice, s));
+    DN_CUDA(cudaMemcpyAsync(boff.p, d.boff, sizeof(int64_t) * d.nreads, cudaMemcpyHostToDevice, s));
+    DN_LAUNCH(k_pack, d.nreads, 128, 0, s, (const uint8_t *)raw.p, (const int64_t *)boff.p, (const int32_t *)B.len.p,
+              (const int64_t *)B.off.p, d.format, B.fwd.p, B.rc.p);
+    DN_LAUNCH(k_chunk2read, (d.nreads + 255) / 256, 256, 0, s, (const int64_t *)B.off.p, d.nreads, B.chunk2read.p);
+    B.has_mask = false;
+    if (d.mask_anno && d.mask_data) {
+        int64_t nbytes = d.mask_anno[d.nreads];
+        if (nbytes > 0) {
+            B.has_mask = true;
+            size_t mw = (size_t)(g >> 5) + 4;
+            B.mask.alloc(mw); B.mask_rc.alloc(mw); B.mask.zero(s); B.mask_rc.zero(s);
+            DBuf<int64_t> anno(d.nreads + 1); DBuf<int32_t> md((size_t)nbytes / 4 + 2);
+            DN_CUDA(cudaMemcpyAsync(anno.p, d.mask_anno, sizeof(int64_t) * (d.nreads + 1), cudaMemcpyHostToDevice, s));
+            DN_CUDA(cudaMemcpyAsync(md.p, d.mask_data, nbytes, cudaMemcpyHostToDevice, s));
+            DN_LAUNCH(k_mask_bits, d.nreads, 64, 0, s, (const int64_t *)anno.p, (const int32_t *)md.p, d.nreads,
+                      (const int64_t *)B.off.p, (const int32_t *)B.len.p, B.mask.p, B.mask_rc.p);
+            DN_CUDA(cudaStreamSynchronize(s));
+        }
+    }
+    DN_CUDA(cudaStreamSynchronize(s));
+}
+
+// ------------------------------------------------------------------------- K1: k-mer tuples
+
+// One thread per 16-base word of the padded block: emits 16 tuples (kmer << 32 | payload).
+// Positions that cannot start a k-mer (read end, padding, masked) get kmer 0xffffffff and sort last.
+__global__ void __launch_bounds__(256) k_tuples(const u32 *__restrict__ seq, const u32 *__restrict__ maskbits,
+                                                const int64_t *__restrict__ off, const int32_t *__restrict__ len,
+                                                const int32_t *__restrict__ c2r, int64_t nwords, int k, u32 payload_base,
+                                                u64 *__restrict__ out) {
+    int64_t wi = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (wi >= nwords) return;
+    const int64_t g0 = wi << 4;
+    int r = c2r[g0 >> 10];
+    while (off[r + 1] <= g0) r++;
+    const int p0 = (int)(g0 - off[r]);
+    const int L = len[r];
+    const u64 v = ((u64)seq[wi + 1] << 32) | seq[wi];
+    const u64 kmask = (1ull << (2 * k)) - 1ull;
+    u64 mwin = 0;
+    if (maskbits) {
+        int64_t mw = g0 >> 5;
+        mwin = (((u64)maskbits[mw + 1] << 32) | maskbits[mw]) >> (g0 & 31);
+    }
+    const u64 mk = (1ull << k) - 1ull;
+    ulonglong2 *o2 = reinterpret_cast<ulonglong2 *>(out + g0);
+#pragma unroll
+    for (int j = 0; j < 16; j += 2) {
+        u64 t[2];
+#pragma unroll
+        for (int q = 0; q < 2; q++) {
+            int jj = j + q;
+            bool valid = (p0 + jj + k <= L) && (((mwin >> jj) & mk) == 0);
+            u64 km = valid ? ((v >> (2 * jj)) & kmask) : 0xffffffffull;
+            t[q] = (km << 32) | (u64)(payload_base + (u32)(g0 + jj));
+        }
+        o2[j >> 1] = make_ulonglong2(t[0], t[1]);
+    }
+}
+
+void emit_tuples(const DevBlock &B, bool rc, int k, u32 payload_base, u64 *out, cudaStream_t s) {
+    int64_t nwords = B.total >> 4;
+    if (nwords == 0) return;
+    const u32 *mb = B.has_mask ? (rc ? B.mask_rc.p : B.mask.p) : nullptr;
+    DN_LAUNCH(k_tuples, (unsigned)((nwords + 255) / 256), 256, 0, s, (const u32 *)(rc ? B.rc.p : B.fwd.p), mb,
+              (const int64_t *)B.off.p, (const int32_t *)B.len.p, (const int32_t *)B.chunk2read.p, nwords, k, payload_base, out);
+}
+
+// ------------------------------------------------------------------------- K3: join
+
+// tbl[q] = first index i in the sorted A list with min(kmer_i >> sh, nq) >= q, q in [0, nq]
+__global__ void __launch_bounds__(256) k_prefix_table(const u64 *__restrict__ ta, int64_t na, int sh, u32 nq, u32 *__restrict__ tbl) {
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= na) return;
+    u32 q = (u32)(ta[i] >> 32) >> sh; if (q > nq) q = nq;
+    int64_t qp;
+    if (i == 0) qp = -1;
+    else { u32 t = (u32)(ta[i - 1] >> 32) >> sh; if (t > nq) t = nq; qp = t; }
+    for (int64_t x = qp + 1; x <= (int64_t)q; x++) tbl[x] = (u32)i;
+    if (i == na - 1) for (int64_t x = (int64_t)q + 1; x <= (int64_t)nq; x++) tbl[x] = (u32)na;
+}
+
+__device__ __forceinline__ void a_range(const u64 *__restrict__ ta, const u32 *__restrict__ tbl, int sh, u32 km, u32 &s, u32 &e) {
+    u32 q = km >> sh;
+    u32 lo = tbl[q], hi = tbl[q + 1];
+    // lower bound of km in [lo,hi)
+    u32 a = lo, b = hi;
+    while (a < b) { u32 m = (a + b) >> 1; if ((u32)(ta[m] >> 32) < km) a = m + 1; else b = m; }
+    s = a;
+    b = hi;
+    while (a < b) { u32 m = (a + b) >> 1; if ((u32)(ta[m] >> 32) <= km) a = m + 1; else b = m; }
+    e = a;
+}
+
+__global__ void __launch_bounds__(256) k_join_count(const u64 *__restrict__ ta, const u32 *__restrict__ tbl, int sh,
+                                                    const u64 *__restrict__ tb, int64_t nb, int tcap,
+                                                    u32 *__restrict__ cnt, u32 *__restrict__ start) {
+    int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= nb) return;
+    u32 km = (u32)(tb[j] >> 32);
+    u32 c = 0, s = 0;
+    if (km != 0xffffffffu) {
+        u32 e; a_range(ta, tbl, sh, km, s, e);
+        c = e - s;
+        if (c > (u32)tcap) c = 0;
+    }
+    cnt[j] = c; start[j] = s;
+}
+
+__device__ __forceinline__ int read_of(const int32_t *__restrict__ c2r, const int64_t *__restrict__ off, int64_t g) {
+    int r = c2r[g >> 10];
+    while (off[r + 1] <= g) r++;
+    return r;
+}
+
+// hit record: .x = key = (bs << gdbits) | gd   (invalid: 1 << keybits), .y = apos | bpos << 32
+__global__ void __launch_bounds__(256) k_join_emit(const u64 *__restrict__ ta, const u64 *__restrict__ tb, int64_t nb,
+                                                   const u32 *__restrict__ cnt, const u32 *__restrict__ start,
+                                                   const int64_t *__restrict__ hoff, JoinGeom G,
+                                                   ulonglong2 *__restrict__ hits, unsigned long long *__restrict__ ninvalid) {
+    int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= nb) return;
+    u32 c = cnt[j];
+    if (c == 0) return;
+    u32 pb = (u32)tb[j];
+    int strand = pb >= G.nbp ? 1 : 0;
+    int64_t gb = strand ? (int64_t)pb - G.nbp : (int64_t)pb;
+    int br = read_of(G.b_c2r, G.b_off, gb);
+    int bpos = (int)(gb - G.b_off[br]);
+    u64 bs = (u64)br * 2 + strand;
+    int64_t o = hoff[j];
+    u32 s = start[j];
+    u32 ninv = 0;
+    for (u32 x = 0; x < c; x++) {
+        int64_t ga = (int64_t)(u32)ta[s + x];
+        int ar = read_of(G.a_c2r, G.a_off, ga);
+        int apos = (int)(ga - G.a_off[ar]);
+        u64 key;
+        if (G.self && ar == br) { key = 1ull << G.keybits; ninv++; }
+        else { u64 gd = (u64)(G.a_dbase[ar] + apos - bpos + G.maxlb); key = (bs << G.gdbits) | gd; }
+        hits[o + x] = make_ulonglong2(key, (u64)(u32)apos | ((u64)(u32)bpos << 32));
+    }
+    if (ninv) atomicAdd(ninvalid, (unsigned long long)ninv);
+}
+
+// ------------------------------------------------------------------------- K4: band filter
+
+// per hit: covered-base contribution and band-start flag
+__global__ void __launch_bounds__(256) k_hit_cover(const ulonglong2 *__restrict__ hits, int64_t n, int k, int w,
+                                                   int32_t *__restrict__ cov, int32_t *__restrict__ bflag) {
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    ulonglong2 h = hits[i];
+    int c = k, f = 1;
+    if (i > 0) {
+        ulonglong2 p = hits[i - 1];
+        int da = (int)(u32)h.y - (int)(u32)p.y;
+        if (p.x == h.x && da < k) c = da;
+        f = (p.x >> w) != (h.x >> w);
+    }
+    cov[i] = c; bflag[i] = f;
+}
+
+// band table: for every band start i (bflag), bfirst[bidx] = i, bkey[bidx] = key >> w
+__global__ void __launch_bounds__(256) k_band_table(const ulonglong2 *__restrict__ hits, int64_t n, int w,
+                                                    const int32_t *__restrict__ bflag, const int32_t *__restrict__ bidx,
+                                                    int32_t *__restrict__ bfirst, u64 *__restrict__ bkey, int32_t nbands) {
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    if (bflag[i]) { int b = bidx[i]; bfirst[b] = (int32_t)i; bkey[b] = hits[i].x >> w; }
+    if (i == n - 1) bfirst[nbands] = (int32_t)n;
+}
+
+// per band: pass flag of the pair (q, q+1)
+__global__ void __launch_bounds__(256) k_band_pass(const int32_t *__restrict__ bfirst, const u64 *__restrict__ bkey,
+                                                   const int32_t *__restrict__ covsum, int32_t total_cov, int64_t nhits,
+                                                   int32_t nbands, int h, uint8_t *__restrict__ pass) {
+    int q = blockIdx.x * blockDim.x + threadIdx.x;
+    if (q >= nbands) return;
+    auto cs = [&](int32_t i) { return i >= nhits ? total_cov : covsum[i]; };
+    int sc = cs(bfirst[q + 1]) - cs(bfirst[q]);
+    bool adj = (q + 1 < nbands) && (bkey[q + 1] == bkey[q] + 1);
+    if (adj) sc += cs(bfirst[q + 2]) - cs(bfirst[q + 1]);
+    pass[q] = sc >= h;
+}
+
+// hot[q] = pass[q] || (adjacent(q-1,q) && pass[q-1]); cstart[q] = hot[q] && !(hot[q-1] && adjacent(q-1,q))
+__global__ void __launch_bounds__(256) k_band_hot(const u64 *__restrict__ bkey, const uint8_t *__restrict__ pass, int32_t nbands,
+                                                  uint8_t *__restrict__ hot, int32_t *__restrict__ cstart) {
+    int q = blockIdx.x * blockDim.x + threadIdx.x;
+    if (q >= nbands) return;
+    auto is_hot = [&](int x) -> bool {
+        if (pass[x]) return true;
+        return x > 0 && bkey[x - 1] + 1 == bkey[x] && pass[x - 1];
+    };
+    bool hq = is_hot(q);
+    hot[q] = hq;
+    bool cont = hq && q > 0 && bkey[q - 1] + 1 == bkey[q] && is_hot(q - 1);
+    cstart[q] = hq && !cont;
+}
+
+// one thread per cluster start: walk to the end of the run, pick the median hit as seed
+__global__ void __launch_bounds__(256) k_seeds(const ulonglong2 *__restrict__ hits, const int32_t *__restrict__ bfirst,
+                                               const u64 *__restrict__ bkey, const uint8_t *__restrict__ hot,
+                                               const int32_t *__restrict__ cstart, const int32_t *__restrict__ cidx,
+                                               int32_t nbands, SeedGeom G, Seed *__restrict__ seeds,
+                                               uint8_t *__restrict__ consumed) {
+    int q = blockIdx.x * blockDim.x + threadIdx.x;
+    if (q >= nbands || !cstart[q]) return;
+    int e = q;
+    while (e + 1 < nbands && hot[e + 1] && bkey[e + 1] == bkey[e] + 1) e++;
+    int32_t f = bfirst[q], l = bfirst[e + 1];
+    int32_t m = f + (l - f - 1) / 2;
+    ulonglong2 h = hits[m];
+    u64 gd = h.x & ((1ull << G.gdbits) - 1ull);
+    u32 bs = (u32)(h.x >> G.gdbits);
+    // aread = last r with dbase[r] <= gd
+    int lo = 0, hi = G.na;
+    while (hi - lo > 1) { int mid = (lo + hi) >> 1; if ((u64)G.a_dbase[mid] <= gd) lo = mid; else hi = mid; }
+    Seed s; s.a = lo; s.bs = (int32_t)bs; s.apos = (int32_t)(u32)h.y; s.bpos = (int32_t)(h.y >> 32);
+    seeds[cidx[q]] = s;
+    consumed[m] = 1;
+}
+
+}  // namespace dn

@@ -1,0 +1,62 @@
+// seed.cuh -- shared structs between the seeding and extension stages.
+#pragma once
+#include "engine.cuh"
+
+namespace dn {
+
+struct Seed { int32_t a, bs, apos, bpos; };
+
+// geometry handed to the join: how a (aread, apos, bread, strand, bpos) hit becomes a sort key
+struct JoinGeom {
+    const int32_t *a_c2r; const int64_t *a_off; const int64_t *a_dbase;
+    const int32_t *b_c2r; const int64_t *b_off;
+    int64_t nbp;          // padded bases of B: payloads >= nbp are the complement strand
+    int64_t maxlb;        // max B read length rounded up to the band width
+    int gdbits, keybits, self;
+};
+struct SeedGeom { const int64_t *a_dbase; int na; int gdbits; };
+
+// one candidate local alignment (device + host layout)
+struct Cand {
+    int32_t a, bs, ab, ae, bb, be, diffs, nt, dmin, dmax;
+    int64_t toff;          // offset of its joined trace (uint16 pairs -> 2*nt elements) in the round's trace buffer
+};
+
+struct ExtOut { int32_t i_end, j_end, d_end, ntiles; };
+
+void emit_tuples(const DevBlock &B, bool rc, int k, u32 payload_base, u64 *out, cudaStream_t s);
+
+// kernels defined in seed.cu
+__global__ void k_prefix_table(const u64 *ta, int64_t na, int sh, u32 nq, u32 *tbl);
+__global__ void k_join_count(const u64 *ta, const u32 *tbl, int sh, const u64 *tb, int64_t nb, int tcap, u32 *cnt, u32 *start);
+__global__ void k_join_emit(const u64 *ta, const u64 *tb, int64_t nb, const u32 *cnt, const u32 *start, const int64_t *hoff,
+                            JoinGeom G, ulonglong2 *hits, unsigned long long *ninvalid);
+__global__ void k_hit_cover(const ulonglong2 *hits, int64_t n, int k, int w, int32_t *cov, int32_t *bflag);
+__global__ void k_band_table(const ulonglong2 *hits, int64_t n, int w, const int32_t *bflag, const int32_t *bidx,
+                             int32_t *bfirst, u64 *bkey, int32_t nbands);
+__global__ void k_band_pass(const int32_t *bfirst, const u64 *bkey, const int32_t *covsum, int32_t total_cov, int64_t nhits,
+                            int32_t nbands, int h, uint8_t *pass);
+__global__ void k_band_hot(const u64 *bkey, const uint8_t *pass, int32_t nbands, uint8_t *hot, int32_t *cstart);
+__global__ void k_seeds(const ulonglong2 *hits, const int32_t *bfirst, const u64 *bkey, const uint8_t *hot,
+                        const int32_t *cstart, const int32_t *cidx, int32_t nbands, SeedGeom G, Seed *seeds, uint8_t *consumed);
+
+// extension stage (extend.cu)
+struct ExtGeom {
+    const u32 *a_fwd, *a_rc, *b_fwd, *b_rc;
+    const int64_t *a_off, *b_off; const int32_t *a_len, *b_len;
+    int ts, cdiff, xdrop, wmax, poolmul; u32 ts_magic;
+};
+void launch_task_caps(const Seed *seeds, int nseeds, ExtGeom G, u32 *caps, cudaStream_t s);
+void launch_extend(const Seed *seeds, int nseeds, ExtGeom G, const int64_t *tile_off, int2 *tiles, ExtOut *outs,
+                   int4 *pool, int64_t pool_stride, int nwarps_total, int *counter, cudaStream_t s);
+void launch_combine(const Seed *seeds, int nseeds, ExtGeom G, int minlen, const int64_t *tile_off, const int2 *tiles,
+                    const ExtOut *outs, Cand *cand_all, int32_t *valid, u32 *ntl, cudaStream_t s);
+void launch_write_traces(const Seed *seeds, int nseeds, ExtGeom G, const int64_t *tile_off, const int2 *tiles,
+                         const ExtOut *outs, const Cand *cand_all, const int32_t *valid, const int32_t *vidx,
+                         const int64_t *toff, Cand *cand_out, uint16_t *trace, cudaStream_t s);
+void launch_retire(const ulonglong2 *hits, int64_t n, const uint8_t *consumed, const Cand *rc, int nrc, SeedGeom G, int w,
+                   int32_t *keep, cudaStream_t s);
+void launch_compact_hits(const ulonglong2 *hits, int64_t n, const int32_t *keep, const int32_t *kidx, ulonglong2 *out, cudaStream_t s);
+void launch_dedupe(const Cand *cands, int ncand, const int32_t *round_beg, int nrounds, uint8_t *drop, cudaStream_t s);
+
+}  // namespace dn

@@ -1,0 +1,153 @@
+"""Python mirror of the slice of `source/dentist/dazzler.d` that sits on the hot path, bound to the
+C ABI.  Names and argument meaning follow the reference so the parity tests read like its own:
+
+  getDalignment(dbA[, dbB], opts, outdir) -> las path     dazzler.d:3829-3844
+  getDamapping(refDb, queryDb, opts, outdir) -> las path   dazzler.d:3855-3866
+  getLasFile(dbA, dbB, outdir)                             dazzler.d:4345-4354
+
+plus the in-memory hand-off: `Block` = a DAZZ_DB read block resident in HBM,
+`align_blocks(A, B)` = the records of A.B.las without touching the file system.
+"""
+import ctypes as C
+import os
+
+import numpy as np
+
+from . import _lib
+from ._lib import DnError  # noqa: F401  (re-export)
+
+
+def init(device=0, tmpdir=None):
+    _lib.check(_lib.lib().dn_init(int(device), tmpdir.encode() if tmpdir else None))
+
+
+def launch_count():
+    return int(_lib.lib().dn_launch_count())
+
+
+class Block:
+    """A sequence block resident in HBM (2-bit packed, both strands)."""
+
+    def __init__(self, off, bases=None, bps=None, boff=None, mask=None):
+        """Either `bases` (uint8 codes 0..3 concatenated, read r = bases[off[r]:off[r+1]]) or
+        DAZZ_DB `.bps` bytes with per-read byte offsets `boff` and lengths diff(off)."""
+        off = np.ascontiguousarray(off, dtype=np.int64)
+        rlen = np.ascontiguousarray(np.diff(off), dtype=np.int32)
+        d = _lib.BlockDesc()
+        d.nreads = len(rlen)
+        keep = [rlen]
+        if bps is not None:
+            data = np.ascontiguousarray(bps, dtype=np.uint8)
+            bo = np.ascontiguousarray(boff, dtype=np.int64)
+            d.format = 1
+        else:
+            data = np.ascontiguousarray(bases, dtype=np.uint8)
+            bo = np.ascontiguousarray(off[:-1], dtype=np.int64)
+            d.format = 0
+        keep += [data, bo]
+        d.rlen = rlen.ctypes.data
+        d.boff = bo.ctypes.data
+        d.data = data.ctypes.data
+        d.data_bytes = data.nbytes
+        if mask is not None:   # list of per-read interval lists [(b, e), ...]
+            anno = np.zeros(len(rlen) + 1, np.int64)
+            flat = []
+            for r, iv in enumerate(mask):
+                anno[r] = 4 * len(flat)
+                for b, e in iv:
+                    flat += [b, e]
+            anno[len(rlen)] = 4 * len(flat)
+            md = np.ascontiguousarray(flat if flat else [0, 0], dtype=np.int32)
+            keep += [anno, md]
+            d.mask_anno = anno.ctypes.data
+            d.mask_data = md.ctypes.data
+        self._desc, self._keep = d, keep
+        self._h = C.c_void_p()
+        _lib.check(_lib.lib().dn_block_upload(C.byref(d), C.byref(self._h)))
+        self.nreads = int(d.nreads)
+        self.bases = int(_lib.lib().dn_block_bases(self._h))
+        self.h2d_bytes = int(data.nbytes + rlen.nbytes + bo.nbytes)
+
+    def free(self):
+        if self._h:
+            _lib.lib().dn_block_free(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.free()
+        except Exception:
+            pass
+
+
+def make_params(**kw):
+    p = _lib.AlignParams()
+    _lib.lib().dn_align_params_default(C.byref(p))
+    for k, v in kw.items():
+        if not hasattr(p, k):
+            raise TypeError("unknown alignment parameter %r" % k)
+        setattr(p, k, v)
+    return p
+
+
+def _take(buf):
+    n = int(buf.nrec)
+    if n:
+        rec = np.ctypeslib.as_array(C.cast(buf.rec, C.POINTER(C.c_uint8)), shape=(n * 40,)).view(_lib.REC_DTYPE).copy()
+        toff = np.ctypeslib.as_array(buf.toff, shape=(n,)).copy()
+    else:
+        rec = np.zeros(0, _lib.REC_DTYPE)
+        toff = np.zeros(0, np.int64)
+    tr = np.ctypeslib.as_array(buf.trace, shape=(int(buf.ntrace),)).copy() if buf.ntrace else np.zeros(0, np.uint16)
+    st = {n_: getattr(buf.stats, n_) for n_, _ in _lib.AlignStats._fields_}
+    tspace = int(buf.tspace)
+    _lib.lib().dn_las_free(C.byref(buf))
+    return rec, toff, tr, tspace, st
+
+
+def align_blocks(a, b, **params):
+    """All local alignments of resident block `a` vs `b`: (records, trace offsets, trace, stats)."""
+    p = make_params(**params)
+    buf = _lib.LasBuf()
+    _lib.check(_lib.lib().dn_align_blocks(a._h, b._h, C.byref(p), C.byref(buf)))
+    rec, toff, tr, _, st = _take(buf)
+    return rec, toff, tr, st
+
+
+def read_las(path):
+    buf = _lib.LasBuf()
+    _lib.check(_lib.lib().dn_las_read(path.encode(), C.byref(buf)))
+    rec, toff, tr, tspace, _ = _take(buf)
+    return tspace, rec, toff, tr
+
+
+def _opts(opts):
+    arr = (C.c_char_p * len(opts))(*[o.encode() for o in opts])
+    return arr, len(opts)
+
+
+def _db_name(db):
+    b = os.path.basename(db)
+    for ext in (".db", ".dam"):
+        if b.endswith(ext):
+            b = b[:-len(ext)]
+    return b
+
+
+def getLasFile(dbA, dbB, outdir):
+    """dazzler.d:4345-4354"""
+    return os.path.join(outdir, "%s.%s.las" % (_db_name(dbA), _db_name(dbB if dbB is not None else dbA)))
+
+
+def getDalignment(dbA, dbB=None, opts=(), outdir="."):
+    """dazzler.d:3829-3844 -- `daligner opts dbA dbB` run in outdir; returns the LAS path."""
+    arr, n = _opts(list(opts))
+    _lib.check(_lib.lib().dn_dalign(dbA.encode(), dbB.encode() if dbB else None, arr, n, outdir.encode()))
+    return getLasFile(dbA, dbB, outdir)
+
+
+def getDamapping(refDb, queryDb, opts=(), outdir="."):
+    """dazzler.d:3855-3866 -- `damapper -C opts refDb queryDb`; returns outdir/<ref>.<query>.las."""
+    arr, n = _opts(list(opts))
+    _lib.check(_lib.lib().dn_damap(refDb.encode(), queryDb.encode(), arr, n, outdir.encode()))
+    return getLasFile(refDb, queryDb, outdir)

@@ -1,0 +1,151 @@
+/*
+ * dentist_b200.h -- C ABI of the B200-native alignment + consensus engine that replaces the
+ * external-tool calls in DENTIST's `source/dentist/dazzler.d` (the drop-in boundary).
+ *
+ * Every entry point returns 0 on success and non-zero on error; the message is available from
+ * dn_last_error() (thread-local).  On the D side a non-zero return is turned into the
+ * `DazzlerCommandException` that `executeWrapper` throws today (dazzler.d:6551-6591), which
+ * processPileUps already maps to "skip this pile-up" (processPileUps/package.d:351-373).
+ * Entry points are re-entrant: DENTIST calls them concurrently from std.parallelism workers
+ * (processPileUps/package.d:153).  No torch types, plain pointers and sizes only.
+ *
+ * There is NO CPU fallback: every compute entry point fails with DN_ERR_NO_DEVICE when no CUDA
+ * device is usable.
+ */
+#ifndef DENTIST_B200_H
+#define DENTIST_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define DN_OK 0
+#define DN_ERR_INVALID 1
+#define DN_ERR_NO_DEVICE 2
+#define DN_ERR_CUDA 3
+#define DN_ERR_IO 4
+#define DN_ERR_EMPTY 5     /* e.g. "empty consensus" -- dazzler.d:4232-4235 */
+
+/* ---- lifecycle ------------------------------------------------------------------------- */
+
+/* Select the CUDA device this process uses (one process per GPU).  `tmpdir` may be NULL.
+ * Replaces the start-up tool discovery of `assertExternalToolsAvailable` (commandline.d:339-352). */
+int dn_init(int device, const char *tmpdir);
+int dn_shutdown(void);
+const char *dn_last_error(void);
+const char *dn_version(void);
+/* Number of CUDA kernels this library has launched so far in this process. */
+uint64_t dn_launch_count(void);
+
+/* ---- data model ------------------------------------------------------------------------ */
+
+/* One LAS record, byte-for-byte the 40 bytes DENTIST reads from / writes to a .las file:
+ * DazzlerOverlap[8..48)  (dazzler.d:1717-1725, 1988-2016, 2146-2150).  aread/bread are 0-based
+ * (DENTIST adds 1, dazzler.d:1731-1734).  flags: COMP 0x1, START 0x4, NEXT 0x8, BEST 0x10,
+ * ELIM 0x20 (dazzler.d:1991-1998). */
+typedef struct dn_las_record {
+    int32_t tlen, diffs, abpos, bbpos, aepos, bepos;
+    uint32_t flags;
+    int32_t aread, bread;
+    int32_t pad_;
+} dn_las_record;
+
+#define DN_LAS_COMP 0x1u
+#define DN_LAS_START 0x4u
+#define DN_LAS_NEXT 0x8u
+#define DN_LAS_BEST 0x10u
+#define DN_LAS_ELIM 0x20u
+
+/* Sequence block as it sits in a DAZZ_DB (`.bps` + `.idx`) or in memory.
+ * format DN_SEQ_BYTES: one base per byte, codes a=0 c=1 g=2 t=3 (what DAZZ_DB loads in memory);
+ * format DN_SEQ_BPS:   DAZZ_DB .bps -- 4 bases per byte, first base in the two most significant
+ *                      bits, read r starts at byte boff[r] and spans ceil(rlen[r]/4) bytes.
+ * mask_*: optional mask track in the reference's track layout (dazzler.d:4943-5052):
+ *   mask_anno = nreads+1 int64 BYTE offsets into mask_data, mask_data = int32 (begin,end) pairs. */
+#define DN_SEQ_BYTES 0
+#define DN_SEQ_BPS 1
+typedef struct dn_block_desc {
+    int32_t nreads;
+    int32_t format;
+    const int32_t *rlen;      /* [nreads] */
+    const int64_t *boff;      /* [nreads] byte offset of each read in `data` */
+    const void *data;
+    int64_t data_bytes;
+    const int64_t *mask_anno; /* may be NULL */
+    const int32_t *mask_data; /* may be NULL */
+} dn_block_desc;
+
+/* Parameters of the local aligner; the subset of daligner/damapper flags DENTIST passes
+ * (pileUpAlignmentOptions commandline.d:2886-2902, postConsensusAlignmentOptions :2918-2935,
+ * refVsReadsAlignmentOptions :2943-2955) plus the tool defaults DENTIST leaves alone. */
+typedef struct dn_align_params {
+    int32_t k;          /* -k  k-mer length (<= 15)                    default 14  */
+    int32_t w;          /* -w  log2 of the diagonal band width         default 6   */
+    int32_t h;          /* -h  bases covered by k-mer hits in a band   default 35  */
+    int32_t t;          /* -t  ignore k-mers occurring more often in A default 32  */
+    int32_t tspace;     /* -s  trace point spacing                     default 100 */
+    int32_t minlen;     /* -l  minimum local alignment length          default 1000*/
+    double e;           /* -e  average correlation rate (>= .7)        default .7  */
+    int32_t identity;   /* -I  keep read-vs-itself pairs               default 0   */
+    int32_t self_block; /* A and B are the same block (daligner X X): skip aread == bread unless -I */
+    int32_t rounds;     /* seed/extend rounds                          default 3   */
+    int32_t xdrop;      /* extension x-drop                            default 300 */
+    int32_t wmax;       /* live diagonals per wave (<= 62)             default 62  */
+    int32_t poolmul;    /* trace record pool multiplier                default 64  */
+} dn_align_params;
+void dn_align_params_default(dn_align_params *p);
+
+typedef struct dn_align_stats {
+    int64_t tuples_a, tuples_b, hits, seeds, extensions, las, aligned_bases, trace_points;
+    int64_t algo_bytes_seed;      /* algorithmic HBM bytes of the seeding stages   */
+    int64_t algo_bytes_extend;    /* algorithmic HBM bytes of the wave extension              */
+    float ms_seed, ms_extend, ms_total;   /* CUDA-event times on the engine's stream          */
+    uint64_t launches;
+} dn_align_stats;
+
+typedef struct dn_las_buf {
+    int64_t nrec;
+    dn_las_record *rec;       /* LAsort order = FlatLocalAlignment.opCmp (base.d:1787-1809)   */
+    int64_t *toff;            /* [nrec] offset of each record's trace in `trace` (uint16 units) */
+    int64_t ntrace;
+    uint16_t *trace;          /* (diffs, bbases) pairs, widened to uint16 like dazzler.d:1816-1834 */
+    int32_t tspace;
+    dn_align_stats stats;
+} dn_las_buf;
+void dn_las_free(dn_las_buf *buf);
+
+/* ---- resident blocks + in-memory alignment (no files on the path) -------- */
+
+typedef struct dn_block dn_block;   /* opaque: a sequence block resident in HBM */
+/* H2D copy + on-device 2-bit packing / reverse complement.  Replaces daligner's DB load. */
+int dn_block_upload(const dn_block_desc *desc, dn_block **out);
+void dn_block_free(dn_block *blk);
+int64_t dn_block_bases(const dn_block *blk);
+
+/* All local alignments of block A vs block B (both strands of B).  What `daligner A B` computes
+ * for DENTIST (dazzler.d:6131-6140); result = the records of A.B.las in LAsort order. */
+int dn_align_blocks(const dn_block *a, const dn_block *b, const dn_align_params *p, dn_las_buf *out);
+/* Same, straight from host descriptors (upload + align + download). */
+int dn_align_host(const dn_block_desc *a, const dn_block_desc *b, const dn_align_params *p, dn_las_buf *out);
+
+/* Serialise to the LAS wire format (dazzler.d:1913-2170: int64 novl, int32 tspace, 40-byte records,
+ * uint8 traces iff tspace <= 125). */
+int dn_las_write(const char *path, const dn_las_buf *buf);
+int dn_las_read(const char *path, dn_las_buf *out);
+
+/* ---- file-level drop-ins for dazzler.d ---------------------------------------------------- */
+
+/* getDalignment(dbA[, dbB], opts, outdir)  dazzler.d:3829-3844 / dalign() :6131-6140.
+ * dbB == NULL => self comparison.  Writes outdir/<A>.<B>.las; `opts` are daligner flags
+ * ("-s126", "-l500", "-e0.7", "-k14", "-T8", "-B", "-A", "-I", "-mdust", ...). */
+int dn_dalign(const char *dbA, const char *dbB, const char *const *opts, int nopts, const char *outdir);
+/* getDamapping(refDb, queryDb, opts, outdir)  dazzler.d:3855-3866 / damapper() :6163-6170. */
+int dn_damap(const char *refDb, const char *queryDb, const char *const *opts, int nopts, const char *outdir);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,154 @@
+"""GPU parity: the CUDA path (through the C ABI) must equal the CPU oracle bit for bit on LAS
+records and trace-point integers, on seeded inputs the oracle finishes in seconds."""
+import numpy as np
+import pytest
+
+from dentist_b200 import synth
+
+pytestmark = pytest.mark.gpu
+
+ORC = dict(k=14, w=6, h=35, t=32, cdiff=20, xdrop=300, wmax=62, rounds=3, poolmul=64)
+
+
+def run_both(A, B, tspace, minlen, self_block=0, a_mask=None, b_mask=None, **over):
+    from dentist_b200 import dazzler
+    from oracle import oracle
+    o = dict(ORC); o.update(over)
+    am = bm = None
+    if a_mask is not None:
+        am = np.zeros(A.total, np.uint8)
+        for r, iv in enumerate(a_mask):
+            for b, e in iv:
+                am[A.off[r] + b:A.off[r] + e] = 1
+    if b_mask is not None:
+        bm = np.zeros(B.total, np.uint8)
+        for r, iv in enumerate(b_mask):
+            for b, e in iv:
+                bm[B.off[r] + b:B.off[r] + e] = 1
+    la, tr, st = oracle.align(A.off, A.bases, B.off, B.bases, a_mask=am, b_mask=bm, tspace=tspace, minlen=minlen,
+                              self=self_block, **o)
+    ga = dazzler.Block(A.off, A.bases, mask=a_mask)
+    gb = ga if B is A else dazzler.Block(B.off, B.bases, mask=b_mask)
+    g = {k: v for k, v in o.items() if k not in ("cdiff",)}
+    rec, toff, gtr, gst = dazzler.align_blocks(ga, gb, tspace=tspace, minlen=minlen, self_block=self_block, e=0.7, **g)
+    return (la, tr, st), (rec, toff, gtr, gst)
+
+
+def assert_same(orc, gpu):
+    (la, tr, st), (rec, toff, gtr, gst) = orc, gpu
+    assert gst["hits"] == st["nhits"]
+    assert gst["seeds"] == st["nseeds"]
+    assert len(rec) == len(la)
+    for f in ("aread", "bread", "abpos", "aepos", "bbpos", "bepos", "diffs", "tlen", "flags"):
+        assert np.array_equal(rec[f], la[f]), f
+    assert np.array_equal(toff, la["toff"])
+    assert np.array_equal(gtr, tr)
+
+
+def small_case(seed, cov=4, rl=6000, err=0.13, glen=120000, gaps=2):
+    sc = synth.make_scaffolds(2, glen, seed, n_repeats=1, repeat_copies=4)
+    ref, _ = synth.contigs_from(sc, synth.make_gaps(sc, gaps, seed + 1))
+    reads, _ = synth.simulate_reads(sc, cov, rl, rl // 3, err, seed + 2)
+    return ref, reads
+
+
+@pytest.mark.parametrize("seed,tspace", [(1, 100), (2, 126), (3, 100)])
+def test_ref_vs_reads_matches_oracle(seed, tspace):
+    ref, reads = small_case(seed)
+    orc, gpu = run_both(ref, reads, tspace, 500)
+    assert len(orc[0]) > 50
+    assert_same(orc, gpu)
+
+
+def test_pile_self_alignment_matches_oracle():
+    # processPileUps: daligner -s126 -l500 -e0.7 X X  (commandline.d:2886-2902)
+    sc = synth.make_scaffolds(1, 25000, 21, n_repeats=0)
+    reads, _ = synth.simulate_reads(sc, 12, 7000, 2000, 0.13, 22)
+    orc, gpu = run_both(reads, reads, 126, 500, self_block=1)
+    assert len(orc[0]) > 100
+    assert_same(orc, gpu)
+
+
+def test_ont_like_errors_and_long_reads():
+    sc = synth.make_scaffolds(1, 200000, 31, n_repeats=0)
+    ref, _ = synth.contigs_from(sc, synth.make_gaps(sc, 1, 32))
+    reads, _ = synth.simulate_reads(sc, 3, 20000, 10000, 0.12, 33, mix=(0.25, 0.45, 0.30))
+    orc, gpu = run_both(ref, reads, 100, 1000)
+    assert len(orc[0]) > 10
+    assert_same(orc, gpu)
+
+
+def test_masked_kmers_are_not_seeded():
+    ref, reads = small_case(7, cov=3)
+    amask = [[(0, int(ref.off[r + 1] - ref.off[r]) // 2)] for r in range(ref.nreads)]
+    bmask = [[(100, 400)] for _ in range(reads.nreads)]
+    orc, gpu = run_both(ref, reads, 100, 500, a_mask=amask, b_mask=bmask)
+    assert_same(orc, gpu)
+    orc2, _ = run_both(ref, reads, 100, 500)
+    assert orc[2]["nhits"] < orc2[2]["nhits"]
+
+
+def test_edge_cases_empty_tiny_and_identical():
+    from dentist_b200 import dazzler
+    rng = np.random.default_rng(5)
+    # reads shorter than k, empty read, identical reads (long exact slides crossing many tiles)
+    g = rng.integers(0, 4, 3000, dtype=np.uint8)
+    seqs = [g, g.copy(), g[:10], np.zeros(0, np.uint8), (3 - g)[::-1].copy(), g[500:2500].copy()]
+    off = np.zeros(len(seqs) + 1, np.int64); off[1:] = np.cumsum([len(s) for s in seqs])
+    blk = synth.Block(off, np.concatenate(seqs))
+    orc, gpu = run_both(blk, blk, 126, 500, self_block=1)
+    assert len(orc[0]) >= 6
+    assert_same(orc, gpu)
+    # no hits at all
+    a = synth.Block(np.array([0, 2000]), rng.integers(0, 4, 2000, dtype=np.uint8))
+    b = synth.Block(np.array([0, 2000]), rng.integers(0, 4, 2000, dtype=np.uint8))
+    orc, gpu = run_both(a, b, 100, 500)
+    assert len(gpu[0]) == 0
+    assert_same(orc, gpu)
+    # empty block
+    e = dazzler.Block(np.array([0]), np.zeros(0, np.uint8))
+    rec, _, _, _ = dazzler.align_blocks(e, e, tspace=100)
+    assert len(rec) == 0
+
+
+def test_bps_input_equals_byte_input():
+    from dentist_b200 import dazzler
+    ref, reads = small_case(9, cov=2)
+    bps, boff = [], []
+    o = 0
+    for r in range(reads.nreads):
+        p = synth.pack_2bit_dazz(reads.read(r)); boff.append(o); bps.append(p); o += len(p)
+    gb1 = dazzler.Block(reads.off, reads.bases)
+    gb2 = dazzler.Block(reads.off, bps=np.concatenate(bps), boff=np.array(boff))
+    ga = dazzler.Block(ref.off, ref.bases)
+    r1 = dazzler.align_blocks(ga, gb1, tspace=100, minlen=500)
+    r2 = dazzler.align_blocks(ga, gb2, tspace=100, minlen=500)
+    assert len(r1[0]) > 10
+    assert r1[0].tobytes() == r2[0].tobytes() and np.array_equal(r1[2], r2[2])
+
+
+def test_trace_invariants_at_scale():
+    """Size-independent properties on a larger input (no oracle): tile counts, sums, order."""
+    from dentist_b200 import dazzler
+    from oracle import las
+    sc = synth.make_scaffolds(4, 1000000, 41)
+    ref, _ = synth.contigs_from(sc, synth.make_gaps(sc, 5, 42))
+    reads, truth = synth.simulate_reads(sc, 5, 10000, 3000, 0.13, 43)
+    ga, gb = dazzler.Block(ref.off, ref.bases), dazzler.Block(reads.off, reads.bases)
+    rec, toff, tr, st = dazzler.align_blocks(ga, gb, tspace=100, minlen=1000)
+    assert len(rec) > 1500
+    nt = -(-rec["aepos"] // 100) - rec["abpos"] // 100
+    assert np.array_equal(rec["tlen"], 2 * nt)
+    ends = np.cumsum(rec["tlen"])
+    assert np.array_equal(toff, ends - rec["tlen"])
+    t = tr.reshape(-1, 2).astype(np.int64)
+    idx = np.repeat(np.arange(len(rec)), nt)
+    assert np.array_equal(np.bincount(idx, t[:, 0], len(rec)).astype(np.int64), rec["diffs"])
+    assert np.array_equal(np.bincount(idx, t[:, 1], len(rec)).astype(np.int64), rec["bepos"] - rec["bbpos"])
+    key = np.stack([rec["aread"], rec["bread"], rec["flags"] & 1, rec["abpos"]], 1).tolist()
+    assert key == sorted(key)
+    covered = np.zeros(reads.nreads); np.add.at(covered, rec["bread"], rec["bepos"] - rec["bbpos"])
+    assert (covered / np.diff(reads.off) > 0.8).mean() > 0.9
+    # idempotence: same input, same bytes
+    rec2, _, tr2, _ = dazzler.align_blocks(ga, gb, tspace=100, minlen=1000)
+    assert rec.tobytes() == rec2.tobytes() and np.array_equal(tr, tr2)
