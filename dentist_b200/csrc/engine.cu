@@ -68,7 +68,6 @@ void align_blocks(const DevBlock &A, const DevBlock &B, const AlignParams &P, Ho
     exclusive_scan_u32_to_i64(cnt.p, hoff.p, 2 * nB, dtotal.p, s);
     const int64_t H = d2h_scalar(dtotal.p, s);
     if (H >= (1ll << 31) - 4096) throw Error("too many seed hits for one block pair (>= 2^31); use smaller blocks or lower -t");
-    out.stats.hits = H;
     abytes += 8 * nA + 4ll * nq + 2 * 8 * 2 * nB + 16 * 2 * nB + 16 * H;
 
     // hit-key geometry
@@ -103,6 +102,7 @@ void align_blocks(const DevBlock &A, const DevBlock &B, const AlignParams &P, Ho
     const int npass_h = (aposbits + 7) / 8 + (keybits + 1 + 7) / 8;
     abytes += (int64_t)npass_h * 48 * H;
     int64_t n = H - ninvalid;                   // invalid (self) hits sorted to the end
+    out.stats.hits = n;
 
     // ---- rounds of band filter -> seeds -> extension -> retirement ----------------------------
     ExtGeom EG{A.fwd.p, A.rc.p, B.fwd.p, B.rc.p, A.off.p, B.off.p, A.len.p, B.len.p,
@@ -148,7 +148,7 @@ void align_blocks(const DevBlock &A, const DevBlock &B, const AlignParams &P, Ho
         ms_seed += ts_.stop();
 
         // ---- K5: extension
-        te.start();
+        ts_.start();
         DBuf<u32> caps(2 * (size_t)nseeds); DBuf<int64_t> tile_off(2 * (size_t)nseeds);
         launch_task_caps(seeds.p, nseeds, EG, caps.p, s);
         exclusive_scan_u32_to_i64(caps.p, tile_off.p, 2 * (size_t)nseeds, dtotal.p, s);
@@ -162,6 +162,8 @@ void align_blocks(const DevBlock &A, const DevBlock &B, const AlignParams &P, Ho
           if (ctas > maxc) ctas = (int)maxc; }
         DBuf<int4> pool((size_t)ctas * wpc * pool_stride);
         DBuf<int> counter(1); counter.zero(s);
+        ms_seed += ts_.stop();
+        te.start();                              // brackets exactly the k_extend launch
         launch_extend(seeds.p, nseeds, EG, tile_off.p, tiles.p, outs.p, pool.p, pool_stride, ctas * wpc, counter.p, s);
         ms_ext += te.stop();
 

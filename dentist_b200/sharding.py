@@ -1,0 +1,75 @@
+"""Multi-GPU plumbing: read blocks shard across ranks with no data-path collective (the reference's
+Snakemake per-block fan-out, Snakefile:1143-1170); the per-rank LAS segments are merged by ONE
+all-gatherv at the end (what `LAmerge` does through the file system, Snakefile:1173-1200).
+
+torch.distributed is plumbing only: `nccl` over NVLink on the GPU box, `gloo` in the CPU tests.
+"""
+import numpy as np
+import torch
+import torch.distributed as dist
+
+from ._lib import REC_DTYPE
+
+
+def shard_ranges(n_units, world):
+    """Contiguous, balanced ranges of read indices per rank (block order is preserved so that the
+    concatenation of per-rank `Q.R.las` segments is already sorted by read)."""
+    base, rem = divmod(n_units, world)
+    out, s = [], 0
+    for r in range(world):
+        e = s + base + (1 if r < rem else 0)
+        out.append((s, e))
+        s = e
+    return out
+
+
+def _allgatherv_bytes(buf_u8, device):
+    """all-gather of variable-length byte buffers: sizes first, then one padded all_gather."""
+    world = dist.get_world_size()
+    n = torch.tensor([buf_u8.numel()], dtype=torch.int64, device=device)
+    sizes = [torch.zeros(1, dtype=torch.int64, device=device) for _ in range(world)]
+    dist.all_gather(sizes, n)
+    sizes = [int(s.item()) for s in sizes]
+    m = max(max(sizes), 1)
+    pad = torch.zeros(m, dtype=torch.uint8, device=device)
+    pad[:buf_u8.numel()] = buf_u8.to(device)
+    outs = [torch.empty(m, dtype=torch.uint8, device=device) for _ in range(world)]
+    dist.all_gather(outs, pad)
+    return [o[:s].cpu().numpy() for o, s in zip(outs, sizes)], sizes
+
+
+def gather_las(rec, trace, bread_offset, device="cpu"):
+    """All ranks contribute their LAS segment (records with rank-local `bread`, traces in record
+    order); every rank gets the merged LAS in LAsort order (aread, bread, comp, abpos, ...),
+    with `bread` shifted to the global read numbering.  Returns (records, trace offsets, trace)."""
+    rec = rec.copy()
+    rec["bread"] += bread_offset
+    rb = torch.from_numpy(np.frombuffer(rec.tobytes(), dtype=np.uint8).copy())
+    tb = torch.from_numpy(np.frombuffer(np.ascontiguousarray(trace, dtype=np.uint16).tobytes(), dtype=np.uint8).copy())
+    recs, _ = _allgatherv_bytes(rb, device)
+    trs, _ = _allgatherv_bytes(tb, device)
+    return merge_las([r.view(REC_DTYPE) for r in recs], [t.view(np.uint16) for t in trs])
+
+
+def merge_las(recs, traces):
+    """k-way merge of LAS segments (each in LAsort order) into one (LAmerge semantics)."""
+    toffs = []
+    base = 0
+    for r, t in zip(recs, traces):
+        o = np.cumsum(r["tlen"], dtype=np.int64) - r["tlen"] + base
+        toffs.append(o)
+        base += len(t)
+    rec = np.concatenate(recs) if recs else np.zeros(0, REC_DTYPE)
+    tr = np.concatenate(traces) if traces else np.zeros(0, np.uint16)
+    src = np.concatenate(toffs) if toffs else np.zeros(0, np.int64)
+    if len(rec) == 0:
+        return rec, np.zeros(0, np.int64), tr
+    # base.d:1787-1809 order: (aread, bread, comp, abpos, aepos, bbpos, bepos, diffs); lexsort: last key first
+    order = np.lexsort((rec["diffs"], rec["bepos"], rec["bbpos"], rec["aepos"], rec["abpos"],
+                        rec["flags"] & 1, rec["bread"], rec["aread"]))
+    rec = rec[order]
+    src = src[order]
+    tlen = rec["tlen"].astype(np.int64)
+    dst = np.cumsum(tlen) - tlen
+    idx = np.repeat(src - dst, tlen) + np.arange(int(tlen.sum()))
+    return rec, dst, tr[idx]
