@@ -40,7 +40,8 @@ class BlockDesc(C.Structure):
 class AlignParams(C.Structure):
     _fields_ = [("k", C.c_int32), ("w", C.c_int32), ("h", C.c_int32), ("t", C.c_int32), ("tspace", C.c_int32),
                 ("minlen", C.c_int32), ("e", C.c_double), ("identity", C.c_int32), ("self_block", C.c_int32),
-                ("rounds", C.c_int32), ("xdrop", C.c_int32), ("wmax", C.c_int32), ("poolmul", C.c_int32)]
+                ("rounds", C.c_int32), ("xdrop", C.c_int32), ("wmax", C.c_int32), ("poolmul", C.c_int32),
+                ("join_mode", C.c_int32)]
 
 
 class AlignStats(C.Structure):

@@ -19,6 +19,14 @@ cudaStream_t g_stream = nullptr;
 
 int fail(int code, const std::string &m) { t_err = m; return code; }
 
+void setup_device() {
+    if (!g_stream) cudaStreamCreateWithFlags(&g_stream, cudaStreamNonBlocking);
+    cudaMemPool_t mp;
+    if (cudaDeviceGetDefaultMemPool(&mp, g_device) == cudaSuccess) {     // keep freed blocks cached: no cudaMalloc per step
+        uint64_t thr = ~0ull; cudaMemPoolSetAttribute(mp, cudaMemPoolAttrReleaseThreshold, &thr);
+    }
+}
+
 int ensure_device() {
     if (g_device >= 0) return DN_OK;
     int n = 0;
@@ -26,7 +34,7 @@ int ensure_device() {
     if (e != cudaSuccess || n == 0) return fail(DN_ERR_NO_DEVICE, "no CUDA device available (dentist_b200 has no CPU fallback)");
     if (cudaSetDevice(0) != cudaSuccess) return fail(DN_ERR_NO_DEVICE, "cudaSetDevice(0) failed");
     g_device = 0;
-    if (!g_stream) cudaStreamCreateWithFlags(&g_stream, cudaStreamNonBlocking);
+    setup_device();
     return DN_OK;
 }
 
@@ -46,6 +54,7 @@ AlignParams to_internal(const dn_align_params *p) {
     q.cdiff = (int)(6.0 / (1.0 - e) + 0.5);                   // S = 3*(i+j) - C*d drifts to zero at 1-e diffs/column
     q.xdrop = d.xdrop; q.wmax = d.wmax; q.rounds = d.rounds; q.poolmul = d.poolmul;
     q.self = (d.self_block && !d.identity) ? 1 : 0;
+    q.join_mode = d.join_mode;
     return q;
 }
 
@@ -72,7 +81,7 @@ int dn_init(int device, const char *tmpdir) {
     if (device >= n) return fail(DN_ERR_INVALID, "device index out of range");
     if (cudaSetDevice(device) != cudaSuccess) return fail(DN_ERR_CUDA, "cudaSetDevice failed");
     g_device = device;
-    if (!g_stream) cudaStreamCreateWithFlags(&g_stream, cudaStreamNonBlocking);
+    setup_device();
     return DN_OK;
 }
 int dn_shutdown(void) {
@@ -102,7 +111,7 @@ int dn_block_upload(const dn_block_desc *desc, dn_block **out) {
     std::lock_guard<std::mutex> lk(g_mu);
     if (int rc = ensure_device()) return rc;
     return guarded([&] {
-        cudaSetDevice(g_device);
+        cudaSetDevice(g_device); cur_stream() = g_stream;
         dn_block *b = new dn_block();
         try { block_upload(*desc, b->b, g_stream); } catch (...) { delete b; throw; }
         *out = b; return DN_OK;
@@ -111,7 +120,7 @@ int dn_block_upload(const dn_block_desc *desc, dn_block **out) {
 void dn_block_free(dn_block *blk) {
     if (!blk) return;
     std::lock_guard<std::mutex> lk(g_mu);
-    if (g_device >= 0) cudaSetDevice(g_device);
+    if (g_device >= 0) { cudaSetDevice(g_device); cur_stream() = g_stream; }
     delete blk;
 }
 int64_t dn_block_bases(const dn_block *blk) { return blk ? blk->b.total_real : 0; }
@@ -121,7 +130,7 @@ int dn_align_blocks(const dn_block *a, const dn_block *b, const dn_align_params 
     std::lock_guard<std::mutex> lk(g_mu);
     if (int rc = ensure_device()) return rc;
     return guarded([&] {
-        cudaSetDevice(g_device);
+        cudaSetDevice(g_device); cur_stream() = g_stream;
         AlignParams q = to_internal(p);
         HostLas h;
         align_blocks(a->b, b->b, q, h, g_stream);

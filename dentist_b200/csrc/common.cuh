@@ -25,7 +25,11 @@ extern std::atomic<unsigned long long> g_launches;   // kernels launched by this
     dn::g_launches.fetch_add(1, std::memory_order_relaxed); \
     DN_CUDA(cudaGetLastError()); } while (0)
 
-// Simple RAII device buffer.
+// Stream the engine is currently enqueuing on (thread-local; set by the C-ABI entry points).
+cudaStream_t &cur_stream();
+
+// RAII device buffer on the stream-ordered allocator (cudaMallocAsync): allocations and frees are
+// enqueued on the engine stream and served from a cached pool, so a step does no cudaMalloc/cudaFree.
 template <typename T> struct DBuf {
     T *p = nullptr; size_t n = 0;
     DBuf() {}
@@ -34,8 +38,8 @@ template <typename T> struct DBuf {
     DBuf(DBuf &&o) noexcept : p(o.p), n(o.n) { o.p = nullptr; o.n = 0; }
     DBuf &operator=(DBuf &&o) noexcept { if (this != &o) { release(); p = o.p; n = o.n; o.p = nullptr; o.n = 0; } return *this; }
     ~DBuf() { release(); }
-    void alloc(size_t n_) { release(); n = n_; if (n) DN_CUDA(cudaMalloc((void **)&p, n * sizeof(T))); }
-    void release() { if (p) cudaFree(p); p = nullptr; n = 0; }
+    void alloc(size_t n_) { release(); n = n_; if (n) DN_CUDA(cudaMallocAsync((void **)&p, n * sizeof(T), cur_stream())); }
+    void release() { if (p) cudaFreeAsync(p, cur_stream()); p = nullptr; n = 0; }
     void zero(cudaStream_t s) { if (n) DN_CUDA(cudaMemsetAsync(p, 0, n * sizeof(T), s)); }
     size_t bytes() const { return n * sizeof(T); }
 };

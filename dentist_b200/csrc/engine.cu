@@ -45,30 +45,10 @@ void align_blocks(const DevBlock &A, const DevBlock &B, const AlignParams &P, Ho
     emit_tuples(A, false, k, 0u, ta.p, s);
     u64 *sa = radix_sort_u64(ta.p, ta2.p, nA, 32, 32 + 2 * k + 1, s);
     if (sa == ta.p) ta2.release(); else ta.release();
-    DBuf<u64> tb(2 * nB), tb2(2 * nB);
-    emit_tuples(B, false, k, 0u, tb.p, s);
-    emit_tuples(B, true, k, (u32)nB, tb.p + nB, s);
-    u64 *sb = radix_sort_u64(tb.p, tb2.p, 2 * nB, 32, 32 + 2 * k + 1, s);
-    if (sb == tb.p) tb2.release(); else tb.release();
+    const bool lookup = P.join_mode == 2 || (P.join_mode == 0 && nA * 8 <= (64ll << 20));   // A index is L2-sized
     const int npass_t = (2 * k + 1 + 7) / 8;
     out.stats.tuples_a = A.total_real; out.stats.tuples_b = 2 * B.total_real;
-    int64_t abytes = (nA + nB) / 4 + (nB / 4)                    // read packed sequence (B twice)
-                     + 8 * (nA + 2 * nB)                          // write tuples
-                     + (int64_t)npass_t * 24 * (nA + 2 * nB);     // 2 reads + 1 write per pass
-
-    // ---- K3: join ------------------------------------------------------------------------------
-    int tbits = bits_for((uint64_t)nA) + 1; if (tbits < 16) tbits = 16; if (tbits > 2 * k) tbits = 2 * k;
-    const int sh = 2 * k - tbits; const u32 nq = 1u << tbits;
-    DBuf<u32> tbl((size_t)nq + 2);
-    DN_LAUNCH(k_prefix_table, (unsigned)((nA + 255) / 256), 256, 0, s, (const u64 *)sa, nA, sh, nq, tbl.p);
-    DBuf<u32> cnt(2 * nB), start(2 * nB);
-    DN_LAUNCH(k_join_count, (unsigned)((2 * nB + 255) / 256), 256, 0, s, (const u64 *)sa, (const u32 *)tbl.p, sh,
-              (const u64 *)sb, 2 * nB, P.t, cnt.p, start.p);
-    DBuf<int64_t> hoff(2 * nB), dtotal(1);
-    exclusive_scan_u32_to_i64(cnt.p, hoff.p, 2 * nB, dtotal.p, s);
-    const int64_t H = d2h_scalar(dtotal.p, s);
-    if (H >= (1ll << 31) - 4096) throw Error("too many seed hits for one block pair (>= 2^31); use smaller blocks or lower -t");
-    abytes += 8 * nA + 4ll * nq + 2 * 8 * 2 * nB + 16 * 2 * nB + 16 * H;
+    int64_t abytes = nA / 4 + 8 * nA + (int64_t)npass_t * 24 * nA;      // A: read packed, write tuples, sort passes (2R+1W)
 
     // hit-key geometry
     const int64_t bandw = 1ll << P.w;
@@ -85,13 +65,59 @@ void align_blocks(const DevBlock &A, const DevBlock &B, const AlignParams &P, Ho
     JoinGeom JG{A.chunk2read.p, A.off.p, d_dbase.p, B.chunk2read.p, B.off.p, nB, maxlb, gdbits, keybits, P.self};
     SeedGeom SG{d_dbase.p, A.nreads, gdbits};
 
-    DBuf<ulonglong2> hits((size_t)H + 1), hits2((size_t)H + 1);
+    // ---- K3: join ------------------------------------------------------------------------------
+    int tbits = bits_for((uint64_t)nA) + (lookup ? -1 : 1); if (tbits < 16) tbits = 16; if (tbits > 2 * k) tbits = 2 * k;
+    const int sh = 2 * k - tbits; const u32 nq = 1u << tbits;
+    DBuf<u32> tbl((size_t)nq + 2);
+    DN_LAUNCH(k_prefix_table, (unsigned)((nA + 255) / 256), 256, 0, s, (const u64 *)sa, nA, sh, nq, tbl.p);
+    DBuf<int64_t> dtotal(1);
     DBuf<unsigned long long> ninv(1); ninv.zero(s);
-    if (H > 0)
-        DN_LAUNCH(k_join_emit, (unsigned)((2 * nB + 255) / 256), 256, 0, s, (const u64 *)sa, (const u64 *)sb, 2 * nB,
-                  (const u32 *)cnt.p, (const u32 *)start.p, (const int64_t *)hoff.p, JG, hits.p, ninv.p);
+    DBuf<ulonglong2> hits, hits2;
+    int64_t H = 0;
+    abytes += 8 * nA + 4ll * nq;
+    if (lookup) {
+        // B's tuples are never materialised: count, scan, emit straight from the packed sequence
+        const int64_t nwB = nB >> 4;
+        DBuf<u32> wcnt(2 * nwB); DBuf<int64_t> woff(2 * nwB);
+        for (int st = 0; st < 2; st++) {
+            const u32 *mb = B.has_mask ? (st ? B.mask_rc.p : B.mask.p) : nullptr;
+            DN_LAUNCH(k_lookup_count, (unsigned)((nwB + 255) / 256), 256, 0, s, (const u32 *)(st ? B.rc.p : B.fwd.p), mb,
+                      (const int64_t *)B.off.p, (const int32_t *)B.len.p, (const int32_t *)B.chunk2read.p, nwB, k,
+                      (const u64 *)sa, (const u32 *)tbl.p, sh, P.t, wcnt.p + st * nwB);
+        }
+        exclusive_scan_u32_to_i64(wcnt.p, woff.p, 2 * nwB, dtotal.p, s);
+        H = d2h_scalar(dtotal.p, s);
+        if (H >= (1ll << 31) - 4096) throw Error("too many seed hits for one block pair (>= 2^31); use smaller blocks or lower -t");
+        hits.alloc((size_t)H + 1); hits2.alloc((size_t)H + 1);
+        if (H > 0)
+            for (int st = 0; st < 2; st++) {
+                const u32 *mb = B.has_mask ? (st ? B.mask_rc.p : B.mask.p) : nullptr;
+                DN_LAUNCH(k_lookup_emit, (unsigned)((nwB + 255) / 256), 256, 0, s, (const u32 *)(st ? B.rc.p : B.fwd.p), mb,
+                          (const int64_t *)B.off.p, (const int32_t *)B.len.p, (const int32_t *)B.chunk2read.p, nwB, k,
+                          (const u64 *)sa, (const u32 *)tbl.p, sh, P.t, (const u32 *)(wcnt.p + st * nwB),
+                          (const int64_t *)(woff.p + st * nwB), st, JG, hits.p, ninv.p);
+            }
+        abytes += 2 * (nB / 4) * 2 + 2 * nwB * (4 + 4 + 8 + 8 + 4) + 16 * H;   // packed B read twice per strand, word counts/offsets, hits
+    } else {
+        DBuf<u64> tb(2 * nB), tb2(2 * nB);
+        emit_tuples(B, false, k, 0u, tb.p, s);
+        emit_tuples(B, true, k, (u32)nB, tb.p + nB, s);
+        u64 *sb = radix_sort_u64(tb.p, tb2.p, 2 * nB, 32, 32 + 2 * k + 1, s);
+        DBuf<u32> cnt(2 * nB), start(2 * nB);
+        DN_LAUNCH(k_join_count, (unsigned)((2 * nB + 255) / 256), 256, 0, s, (const u64 *)sa, (const u32 *)tbl.p, sh,
+                  (const u64 *)sb, 2 * nB, P.t, cnt.p, start.p);
+        DBuf<int64_t> hoff(2 * nB);
+        exclusive_scan_u32_to_i64(cnt.p, hoff.p, 2 * nB, dtotal.p, s);
+        H = d2h_scalar(dtotal.p, s);
+        if (H >= (1ll << 31) - 4096) throw Error("too many seed hits for one block pair (>= 2^31); use smaller blocks or lower -t");
+        hits.alloc((size_t)H + 1); hits2.alloc((size_t)H + 1);
+        if (H > 0)
+            DN_LAUNCH(k_join_emit, (unsigned)((2 * nB + 255) / 256), 256, 0, s, (const u64 *)sa, (const u64 *)sb, 2 * nB,
+                      (const u32 *)cnt.p, (const u32 *)start.p, (const int64_t *)hoff.p, JG, hits.p, ninv.p);
+        abytes += 2 * (nB / 4) + 8 * 2 * nB + (int64_t)npass_t * 24 * 2 * nB + 2 * 8 * 2 * nB + 16 * 2 * nB + 16 * H;
+    }
     const int64_t ninvalid = (int64_t)d2h_scalar(ninv.p, s);
-    cnt.release(); start.release(); hoff.release(); ta.release(); ta2.release(); tb.release(); tb2.release(); tbl.release();
+    ta.release(); ta2.release(); tbl.release();
 
     // ---- hit sort: by apos, then stably by (bread, strand, aread, diagonal) -------------------
     const int aposbits = bits_for((uint64_t)A.maxlen);

@@ -116,7 +116,6 @@ Item *radix_sort_impl(Item *a, Item *b, size_t n, int bit_lo, int bit_hi, cudaSt
         DN_LAUNCH((k_radix_scatter<Item, FIELD>), G, RS_THREADS, 0, s, (const Item *)src, dst, n, shift, (const u32 *)hist.p);
         Item *t = src; src = dst; dst = t;
     }
-    DN_CUDA(cudaStreamSynchronize(s));    // hist freed on return
     return src;
 }
 

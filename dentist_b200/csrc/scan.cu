@@ -6,6 +6,8 @@ namespace dn {
 
 std::atomic<unsigned long long> g_launches{0};
 
+cudaStream_t &cur_stream() { static thread_local cudaStream_t s = nullptr; return s; }
+
 int sm_count() {
     static int n = 0;
     if (!n) { int dev; DN_CUDA(cudaGetDevice(&dev)); DN_CUDA(cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev)); }
@@ -97,7 +99,6 @@ void scan_rec(const Tin *in, Tout *out, size_t n, Tout *d_total, cudaStream_t s)
     DN_LAUNCH((k_scan_reduce<Tin, Tout>), (unsigned)nb, SCAN_THREADS, 0, s, in, sums.p, n);
     scan_rec<Tout, Tout>(sums.p, offs.p, nb, nullptr, s);
     DN_LAUNCH((k_scan_apply<Tin, Tout>), (unsigned)nb, SCAN_THREADS, 0, s, in, out, (const Tout *)offs.p, n, d_total);
-    DN_CUDA(cudaStreamSynchronize(s));       // sums/offs are freed on return
 }
 }  // namespace
 

@@ -236,6 +236,87 @@ __global__ void __launch_bounds__(256) k_join_emit(const u64 *__restrict__ ta, c
     if (ninv) atomicAdd(ninvalid, (unsigned long long)ninv);
 }
 
+// ------------------------------------------------------------------------- K3': index lookup join
+// When the A index (sorted tuple list + prefix table) is L2-sized, B's tuples are never
+// materialised or sorted: one thread per 16-base word of B recomputes its 16 k-mers, looks each up
+// in the A index and (pass 1) counts / (pass 2) emits the hits.  Output-identical to the
+// sorted-merge join because the hit list is totally ordered by the sort that follows.
+
+struct WordKmers { u64 v; u64 mwin; int p0, L, r; };
+
+__device__ __forceinline__ WordKmers load_word(const u32 *__restrict__ seq, const u32 *__restrict__ maskbits,
+                                               const int64_t *__restrict__ off, const int32_t *__restrict__ len,
+                                               const int32_t *__restrict__ c2r, int64_t wi) {
+    WordKmers w;
+    const int64_t g0 = wi << 4;
+    int r = c2r[g0 >> 10];
+    while (off[r + 1] <= g0) r++;
+    w.r = r; w.p0 = (int)(g0 - off[r]); w.L = len[r];
+    w.v = ((u64)seq[wi + 1] << 32) | seq[wi];
+    w.mwin = 0;
+    if (maskbits) { int64_t mw = g0 >> 5; w.mwin = (((u64)maskbits[mw + 1] << 32) | maskbits[mw]) >> (g0 & 31); }
+    return w;
+}
+
+__device__ __forceinline__ void a_range_fwd(const u64 *__restrict__ ta, const u32 *__restrict__ tbl, int sh, u32 km, int tcap, u32 &s, u32 &c) {
+    u32 q = km >> sh;
+    u32 a = tbl[q], hi = tbl[q + 1], b = hi;
+    while (a < b) { u32 m = (a + b) >> 1; if ((u32)(ta[m] >> 32) < km) a = m + 1; else b = m; }
+    s = a; c = 0;
+    while (a < hi && (u32)(ta[a] >> 32) == km) { a++; if (++c > (u32)tcap) { c = 0; break; } }
+}
+
+__global__ void __launch_bounds__(256) k_lookup_count(const u32 *__restrict__ seq, const u32 *__restrict__ maskbits,
+                                                      const int64_t *__restrict__ off, const int32_t *__restrict__ len,
+                                                      const int32_t *__restrict__ c2r, int64_t nwords, int k,
+                                                      const u64 *__restrict__ ta, const u32 *__restrict__ tbl, int sh, int tcap,
+                                                      u32 *__restrict__ wcnt) {
+    int64_t wi = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (wi >= nwords) return;
+    const WordKmers w = load_word(seq, maskbits, off, len, c2r, wi);
+    const u64 kmask = (1ull << (2 * k)) - 1ull, mk = (1ull << k) - 1ull;
+    u32 total = 0;
+#pragma unroll 4
+    for (int jj = 0; jj < 16; jj++) {
+        if ((w.p0 + jj + k <= w.L) && (((w.mwin >> jj) & mk) == 0)) {
+            u32 s, c; a_range_fwd(ta, tbl, sh, (u32)((w.v >> (2 * jj)) & kmask), tcap, s, c);
+            total += c;
+        }
+    }
+    wcnt[wi] = total;
+}
+
+__global__ void __launch_bounds__(256) k_lookup_emit(const u32 *__restrict__ seq, const u32 *__restrict__ maskbits,
+                                                     const int64_t *__restrict__ off, const int32_t *__restrict__ len,
+                                                     const int32_t *__restrict__ c2r, int64_t nwords, int k,
+                                                     const u64 *__restrict__ ta, const u32 *__restrict__ tbl, int sh, int tcap,
+                                                     const u32 *__restrict__ wcnt, const int64_t *__restrict__ woff, int strand,
+                                                     JoinGeom G, ulonglong2 *__restrict__ hits, unsigned long long *__restrict__ ninvalid) {
+    int64_t wi = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (wi >= nwords) return;
+    if (wcnt[wi] == 0) return;
+    const WordKmers w = load_word(seq, maskbits, off, len, c2r, wi);
+    const u64 kmask = (1ull << (2 * k)) - 1ull, mk = (1ull << k) - 1ull;
+    const u64 bs = (u64)w.r * 2 + strand;
+    int64_t o = woff[wi];
+    u32 ninv = 0;
+    for (int jj = 0; jj < 16; jj++) {
+        if (!((w.p0 + jj + k <= w.L) && (((w.mwin >> jj) & mk) == 0))) continue;
+        u32 s, c; a_range_fwd(ta, tbl, sh, (u32)((w.v >> (2 * jj)) & kmask), tcap, s, c);
+        const int bpos = w.p0 + jj;
+        for (u32 x = 0; x < c; x++) {
+            int64_t ga = (int64_t)(u32)ta[s + x];
+            int ar = read_of(G.a_c2r, G.a_off, ga);
+            int apos = (int)(ga - G.a_off[ar]);
+            u64 key;
+            if (G.self && ar == w.r) { key = 1ull << G.keybits; ninv++; }
+            else { u64 gd = (u64)(G.a_dbase[ar] + apos - bpos + G.maxlb); key = (bs << G.gdbits) | gd; }
+            hits[o++] = make_ulonglong2(key, (u64)(u32)apos | ((u64)(u32)bpos << 32));
+        }
+    }
+    if (ninv) atomicAdd(ninvalid, (unsigned long long)ninv);
+}
+
 // ------------------------------------------------------------------------- K4: band filter
 
 // per hit: covered-base contribution and band-start flag

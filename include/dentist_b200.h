@@ -95,6 +95,7 @@ typedef struct dn_align_params {
     int32_t xdrop;      /* extension x-drop                            default 300 */
     int32_t wmax;       /* live diagonals per wave (<= 62)             default 62  */
     int32_t poolmul;    /* trace record pool multiplier                default 64  */
+    int32_t join_mode;  /* 0 auto | 1 sort both tuple lists and merge | 2 look B k-mers up in the sorted A index */
 } dn_align_params;
 void dn_align_params_default(dn_align_params *p);
 

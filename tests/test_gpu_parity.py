@@ -13,6 +13,7 @@ ORC = dict(k=14, w=6, h=35, t=32, cdiff=20, xdrop=300, wmax=62, rounds=3, poolmu
 def run_both(A, B, tspace, minlen, self_block=0, a_mask=None, b_mask=None, **over):
     from dentist_b200 import dazzler
     from oracle import oracle
+    gpu_only = {k: over.pop(k) for k in list(over) if k in ("join_mode",)}
     o = dict(ORC); o.update(over)
     am = bm = None
     if a_mask is not None:
@@ -30,6 +31,7 @@ def run_both(A, B, tspace, minlen, self_block=0, a_mask=None, b_mask=None, **ove
     ga = dazzler.Block(A.off, A.bases, mask=a_mask)
     gb = ga if B is A else dazzler.Block(B.off, B.bases, mask=b_mask)
     g = {k: v for k, v in o.items() if k not in ("cdiff",)}
+    g.update(gpu_only)
     rec, toff, gtr, gst = dazzler.align_blocks(ga, gb, tspace=tspace, minlen=minlen, self_block=self_block, e=0.7, **g)
     return (la, tr, st), (rec, toff, gtr, gst)
 
@@ -57,6 +59,18 @@ def test_ref_vs_reads_matches_oracle(seed, tspace):
     ref, reads = small_case(seed)
     orc, gpu = run_both(ref, reads, tspace, 500)
     assert len(orc[0]) > 50
+    assert_same(orc, gpu)
+
+
+@pytest.mark.parametrize("join_mode", [1, 2])
+def test_both_join_strategies_match_oracle(join_mode):
+    """sorted-merge join (both tuple lists radix sorted) and index-lookup join give identical LAS."""
+    ref, reads = small_case(11, cov=3)
+    orc, gpu = run_both(ref, reads, 100, 500, join_mode=join_mode)
+    assert_same(orc, gpu)
+    sc = synth.make_scaffolds(1, 20000, 12, n_repeats=0)
+    pile, _ = synth.simulate_reads(sc, 8, 6000, 1500, 0.13, 13)
+    orc, gpu = run_both(pile, pile, 126, 500, self_block=1, join_mode=join_mode)
     assert_same(orc, gpu)
 
 
