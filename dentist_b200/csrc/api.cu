@@ -21,10 +21,6 @@ int fail(int code, const std::string &m) { t_err = m; return code; }
 
 void setup_device() {
     if (!g_stream) cudaStreamCreateWithFlags(&g_stream, cudaStreamNonBlocking);
-    cudaMemPool_t mp;
-    if (cudaDeviceGetDefaultMemPool(&mp, g_device) == cudaSuccess) {     // keep freed blocks cached: no cudaMalloc per step
-        uint64_t thr = ~0ull; cudaMemPoolSetAttribute(mp, cudaMemPoolAttrReleaseThreshold, &thr);
-    }
 }
 
 int ensure_device() {
@@ -60,13 +56,9 @@ AlignParams to_internal(const dn_align_params *p) {
 
 void to_buf(HostLas &h, int tspace, dn_las_buf *out) {
     memset(out, 0, sizeof *out);
-    out->nrec = (int64_t)h.rec.size(); out->ntrace = (int64_t)h.trace.size(); out->tspace = tspace; out->stats = h.stats;
-    out->rec = (dn_las_record *)malloc(sizeof(dn_las_record) * (h.rec.size() + 1));
-    out->toff = (int64_t *)malloc(sizeof(int64_t) * (h.rec.size() + 1));
-    out->trace = (uint16_t *)malloc(sizeof(uint16_t) * (h.trace.size() + 1));
-    if (!out->rec || !out->toff || !out->trace) throw std::bad_alloc();
-    if (!h.rec.empty()) { memcpy(out->rec, h.rec.data(), sizeof(dn_las_record) * h.rec.size()); memcpy(out->toff, h.toff.data(), sizeof(int64_t) * h.toff.size()); }
-    if (!h.trace.empty()) memcpy(out->trace, h.trace.data(), sizeof(uint16_t) * h.trace.size());
+    out->nrec = h.nrec; out->ntrace = h.ntrace; out->tspace = tspace; out->stats = h.stats;
+    out->rec = h.rec; out->toff = h.toff; out->trace = h.trace;        // ownership moves to the caller (dn_las_free)
+    h.rec = nullptr; h.toff = nullptr; h.trace = nullptr;
 }
 }  // namespace
 
@@ -86,7 +78,8 @@ int dn_init(int device, const char *tmpdir) {
 }
 int dn_shutdown(void) {
     std::lock_guard<std::mutex> lk(g_mu);
-    if (g_stream) { cudaStreamDestroy(g_stream); g_stream = nullptr; }
+    if (g_stream) { cudaStreamSynchronize(g_stream); cudaStreamDestroy(g_stream); g_stream = nullptr; }
+    arena().destroy();
     g_device = -1;
     return DN_OK;
 }
@@ -102,7 +95,7 @@ void dn_align_params_default(dn_align_params *p) {
 
 void dn_las_free(dn_las_buf *b) {
     if (!b) return;
-    free(b->rec); free(b->toff); free(b->trace);
+    hcache_free(b->rec); hcache_free(b->toff); hcache_free(b->trace);
     memset(b, 0, sizeof *b);
 }
 
@@ -111,7 +104,7 @@ int dn_block_upload(const dn_block_desc *desc, dn_block **out) {
     std::lock_guard<std::mutex> lk(g_mu);
     if (int rc = ensure_device()) return rc;
     return guarded([&] {
-        cudaSetDevice(g_device); cur_stream() = g_stream;
+        cudaSetDevice(g_device);
         dn_block *b = new dn_block();
         try { block_upload(*desc, b->b, g_stream); } catch (...) { delete b; throw; }
         *out = b; return DN_OK;
@@ -120,7 +113,7 @@ int dn_block_upload(const dn_block_desc *desc, dn_block **out) {
 void dn_block_free(dn_block *blk) {
     if (!blk) return;
     std::lock_guard<std::mutex> lk(g_mu);
-    if (g_device >= 0) { cudaSetDevice(g_device); cur_stream() = g_stream; }
+    if (g_device >= 0) cudaSetDevice(g_device);
     delete blk;
 }
 int64_t dn_block_bases(const dn_block *blk) { return blk ? blk->b.total_real : 0; }
@@ -130,7 +123,7 @@ int dn_align_blocks(const dn_block *a, const dn_block *b, const dn_align_params 
     std::lock_guard<std::mutex> lk(g_mu);
     if (int rc = ensure_device()) return rc;
     return guarded([&] {
-        cudaSetDevice(g_device); cur_stream() = g_stream;
+        cudaSetDevice(g_device);
         AlignParams q = to_internal(p);
         HostLas h;
         align_blocks(a->b, b->b, q, h, g_stream);
@@ -177,21 +170,27 @@ int dn_las_read(const char *path, dn_las_buf *out) {
         if (!f) return fail(DN_ERR_IO, std::string("cannot open: ") + path);
         int64_t novl = 0; int32_t ts = 0;
         if (fread(&novl, 8, 1, f) != 1 || fread(&ts, 4, 1, f) != 1 || novl < 0) { fclose(f); return fail(DN_ERR_IO, "error reading LAS file: unexpected end of file; expected header"); }
-        HostLas h; h.rec.resize(novl); h.toff.resize(novl);
+        std::vector<dn_las_record> rec(novl); std::vector<int64_t> toff(novl); std::vector<uint16_t> trace;
         const bool large = ts > 125;
         std::vector<uint8_t> small;
         for (int64_t i = 0; i < novl; i++) {
-            if (fread(&h.rec[i], 40, 1, f) != 1) { fclose(f); return fail(DN_ERR_IO, "error reading LAS file: unexpected end of file; expected overlapHead"); }
-            const int tl = h.rec[i].tlen;
+            if (fread(&rec[i], 40, 1, f) != 1) { fclose(f); return fail(DN_ERR_IO, "error reading LAS file: unexpected end of file; expected overlapHead"); }
+            const int tl = rec[i].tlen;
             if (tl < 0 || (tl & 1)) { fclose(f); return fail(DN_ERR_IO, "illegal value for tlen: must be multiple of 2"); }
-            h.toff[i] = (int64_t)h.trace.size();
-            size_t o = h.trace.size(); h.trace.resize(o + tl);
+            toff[i] = (int64_t)trace.size();
+            size_t o = trace.size(); trace.resize(o + tl);
             bool ok;
-            if (large) ok = fread(h.trace.data() + o, 2, tl, f) == (size_t)tl;
-            else { small.resize(tl); ok = fread(small.data(), 1, tl, f) == (size_t)tl; for (int x = 0; x < tl; x++) h.trace[o + x] = small[x]; }
+            if (large) ok = fread(trace.data() + o, 2, tl, f) == (size_t)tl;
+            else { small.resize(tl); ok = fread(small.data(), 1, tl, f) == (size_t)tl; for (int x = 0; x < tl; x++) trace[o + x] = small[x]; }
             if (!ok) { fclose(f); return fail(DN_ERR_IO, "error reading LAS file: unexpected end of file; expected tracePoints"); }
         }
         fclose(f);
+        HostLas h; h.nrec = novl; h.ntrace = (int64_t)trace.size();
+        h.rec = (dn_las_record *)hcache_alloc(sizeof(dn_las_record) * (novl + 1));
+        h.toff = (int64_t *)hcache_alloc(sizeof(int64_t) * (novl + 1));
+        h.trace = (uint16_t *)hcache_alloc(sizeof(uint16_t) * (trace.size() + 1));
+        if (novl) { memcpy(h.rec, rec.data(), sizeof(dn_las_record) * novl); memcpy(h.toff, toff.data(), sizeof(int64_t) * novl); }
+        if (!trace.empty()) memcpy(h.trace, trace.data(), sizeof(uint16_t) * trace.size());
         to_buf(h, ts, out);
         return DN_OK;
     });

@@ -25,23 +25,41 @@ extern std::atomic<unsigned long long> g_launches;   // kernels launched by this
     dn::g_launches.fetch_add(1, std::memory_order_relaxed); \
     DN_CUDA(cudaGetLastError()); } while (0)
 
-// Stream the engine is currently enqueuing on (thread-local; set by the C-ABI entry points).
-cudaStream_t &cur_stream();
+// Workspace arena: one grow-only slab of HBM per process, bump-allocated during a call and reset at
+// the start of the next one, so a steady-state step performs no cudaMalloc / cudaFree at all
+// (driver allocation calls cost milliseconds and serialise the device).
+struct Arena {
+    struct Chunk { char *p; size_t cap, used; };
+    std::vector<Chunk> chunks;
+    size_t high = 0, cur = 0;                 // bytes handed out in this call / high-water mark
+    void *alloc(size_t bytes);
+    void reset();                             // start of a call: reclaim everything, coalesce chunks
+    void destroy();
+};
+Arena &arena();
 
-// RAII device buffer on the stream-ordered allocator (cudaMallocAsync): allocations and frees are
-// enqueued on the engine stream and served from a cached pool, so a step does no cudaMalloc/cudaFree.
+// RAII device buffer.  Default: carved from the arena (freed wholesale at the next reset).
+// persistent(): an owned cudaMalloc allocation that outlives the call (resident blocks).
 template <typename T> struct DBuf {
-    T *p = nullptr; size_t n = 0;
+    T *p = nullptr; size_t n = 0; bool owned = false;
     DBuf() {}
     explicit DBuf(size_t n_) { alloc(n_); }
     DBuf(const DBuf &) = delete; DBuf &operator=(const DBuf &) = delete;
-    DBuf(DBuf &&o) noexcept : p(o.p), n(o.n) { o.p = nullptr; o.n = 0; }
-    DBuf &operator=(DBuf &&o) noexcept { if (this != &o) { release(); p = o.p; n = o.n; o.p = nullptr; o.n = 0; } return *this; }
+    DBuf(DBuf &&o) noexcept : p(o.p), n(o.n), owned(o.owned) { o.p = nullptr; o.n = 0; }
+    DBuf &operator=(DBuf &&o) noexcept { if (this != &o) { release(); p = o.p; n = o.n; owned = o.owned; o.p = nullptr; o.n = 0; } return *this; }
     ~DBuf() { release(); }
-    void alloc(size_t n_) { release(); n = n_; if (n) DN_CUDA(cudaMallocAsync((void **)&p, n * sizeof(T), cur_stream())); }
-    void release() { if (p) cudaFreeAsync(p, cur_stream()); p = nullptr; n = 0; }
+    void alloc(size_t n_) { release(); n = n_; owned = false; if (n) p = (T *)arena().alloc(n * sizeof(T)); }
+    void persistent(size_t n_) { release(); n = n_; owned = true; if (n) DN_CUDA(cudaMalloc((void **)&p, n * sizeof(T))); }
+    void release() { if (p && owned) cudaFree(p); p = nullptr; n = 0; }
     void zero(cudaStream_t s) { if (n) DN_CUDA(cudaMemsetAsync(p, 0, n * sizeof(T), s)); }
     size_t bytes() const { return n * sizeof(T); }
+};
+
+// Pinned host staging buffer (grow-only, reused across calls) for device->host downloads.
+struct PinnedBuf {
+    void *p = nullptr; size_t cap = 0;
+    void *get(size_t bytes);
+    ~PinnedBuf() { if (p) cudaFreeHost(p); }
 };
 
 int sm_count();

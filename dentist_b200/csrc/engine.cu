@@ -4,6 +4,9 @@
 #include "seed.cuh"
 #include <algorithm>
 #include <string.h>
+#include <stdlib.h>
+#include <chrono>
+#include <mutex>
 
 namespace dn {
 
@@ -16,6 +19,19 @@ template <typename T> T d2h_scalar(const T *d, cudaStream_t s) {
 }
 int bits_for(uint64_t v) { int b = 0; while (v) { b++; v >>= 1; } return b; }   // bits needed to represent v
 
+// DN_TRACE=1: print synchronised wall-clock per stage to stderr (diagnostics only; adds syncs)
+struct Trace {
+    bool on; cudaStream_t s; std::chrono::steady_clock::time_point t0;
+    explicit Trace(cudaStream_t s_) : on(getenv("DN_TRACE") != nullptr), s(s_) { if (on) { cudaStreamSynchronize(s); t0 = std::chrono::steady_clock::now(); } }
+    void mark(const char *what) {
+        if (!on) return;
+        cudaStreamSynchronize(s);
+        auto t1 = std::chrono::steady_clock::now();
+        fprintf(stderr, "[dn trace] %-28s %8.3f ms\n", what, std::chrono::duration<double, std::milli>(t1 - t0).count());
+        t0 = t1;
+    }
+};
+
 struct Timer {
     cudaEvent_t a, b; cudaStream_t s;
     Timer(cudaStream_t s_) : s(s_) { cudaEventCreate(&a); cudaEventCreate(&b); }
@@ -26,8 +42,35 @@ struct Timer {
 
 }  // namespace
 
+namespace {
+struct HBlock { size_t cap; size_t pad_[7]; };          // 64-byte header in front of every cached block
+std::mutex g_hmu; std::vector<HBlock *> g_hfree;
+}
+void *hcache_alloc(size_t bytes) {
+    if (bytes < 64) bytes = 64;
+    {
+        std::lock_guard<std::mutex> lk(g_hmu);
+        int best = -1;
+        for (int i = 0; i < (int)g_hfree.size(); i++)
+            if (g_hfree[i]->cap >= bytes && g_hfree[i]->cap <= 4 * bytes + (1 << 20) && (best < 0 || g_hfree[i]->cap < g_hfree[best]->cap)) best = i;
+        if (best >= 0) { HBlock *h = g_hfree[best]; g_hfree.erase(g_hfree.begin() + best); return (void *)(h + 1); }
+    }
+    size_t cap = bytes + (bytes >> 3);
+    HBlock *h = (HBlock *)malloc(sizeof(HBlock) + cap);
+    if (!h) throw std::bad_alloc();
+    h->cap = cap;
+    return (void *)(h + 1);
+}
+void hcache_free(void *p) {
+    if (!p) return;
+    HBlock *h = (HBlock *)p - 1;
+    std::lock_guard<std::mutex> lk(g_hmu);
+    if (g_hfree.size() < 12) g_hfree.push_back(h); else free(h);
+}
+
 void align_blocks(const DevBlock &A, const DevBlock &B, const AlignParams &P, HostLas &out, cudaStream_t s) {
-    out.rec.clear(); out.toff.clear(); out.trace.clear(); memset(&out.stats, 0, sizeof out.stats);
+    out = HostLas();
+    arena().reset();
     if (P.k < 4 || P.k > 15) throw Error("k must be in [4,15]");
     if (P.wmax < 4 || P.wmax > 62) throw Error("wmax must be in [4,62]");
     if (P.w < 1 || P.w > 12 || P.tspace < 1 || P.tspace > 32767) throw Error("bad w / tspace");
@@ -36,16 +79,21 @@ void align_blocks(const DevBlock &A, const DevBlock &B, const AlignParams &P, Ho
     const unsigned long long launches0 = g_launches.load();
     Timer tt(s), ts_(s), te(s);
     tt.start(); ts_.start();
-    if (A.nreads == 0 || B.nreads == 0) { out.stats.ms_total = tt.stop(); return; }
+    if (A.nreads == 0 || B.nreads == 0) {
+        out.rec = (dn_las_record *)hcache_alloc(64); out.toff = (int64_t *)hcache_alloc(64); out.trace = (uint16_t *)hcache_alloc(64);
+        out.stats.ms_total = tt.stop(); return;
+    }
     const int k = P.k;
     const int64_t nA = A.total, nB = B.total;
+    Trace tr(s);
 
     // ---- K1 + K2: tuples, radix sort by k-mer -------------------------------------------------
     DBuf<u64> ta(nA), ta2(nA);
     emit_tuples(A, false, k, 0u, ta.p, s);
     u64 *sa = radix_sort_u64(ta.p, ta2.p, nA, 32, 32 + 2 * k + 1, s);
     if (sa == ta.p) ta2.release(); else ta.release();
-    const bool lookup = P.join_mode == 2 || (P.join_mode == 0 && nA * 8 <= (64ll << 20));   // A index is L2-sized
+    tr.mark("A tuples + sort");
+    const bool lookup = P.join_mode == 2 || (P.join_mode == 0 && nA * 8 <= (2ll << 30));   // auto: index lookup unless the A index is huge
     const int npass_t = (2 * k + 1 + 7) / 8;
     out.stats.tuples_a = A.total_real; out.stats.tuples_b = 2 * B.total_real;
     int64_t abytes = nA / 4 + 8 * nA + (int64_t)npass_t * 24 * nA;      // A: read packed, write tuples, sort passes (2R+1W)
@@ -117,6 +165,7 @@ void align_blocks(const DevBlock &A, const DevBlock &B, const AlignParams &P, Ho
         abytes += 2 * (nB / 4) + 8 * 2 * nB + (int64_t)npass_t * 24 * 2 * nB + 2 * 8 * 2 * nB + 16 * 2 * nB + 16 * H;
     }
     const int64_t ninvalid = (int64_t)d2h_scalar(ninv.p, s);
+    tr.mark("join");
     ta.release(); ta2.release(); tbl.release();
 
     // ---- hit sort: by apos, then stably by (bread, strand, aread, diagonal) -------------------
@@ -128,6 +177,7 @@ void align_blocks(const DevBlock &A, const DevBlock &B, const AlignParams &P, Ho
     const int npass_h = (aposbits + 7) / 8 + (keybits + 1 + 7) / 8;
     abytes += (int64_t)npass_h * 48 * H;
     int64_t n = H - ninvalid;                   // invalid (self) hits sorted to the end
+    tr.mark("hit sort");
     out.stats.hits = n;
 
     // ---- rounds of band filter -> seeds -> extension -> retirement ----------------------------
@@ -165,6 +215,7 @@ void align_blocks(const DevBlock &A, const DevBlock &B, const AlignParams &P, Ho
         exclusive_scan_i32(cstart.p, cidx.p, nbands, dtot32.p, s);
         const int32_t nseeds = d2h_scalar(dtot32.p, s);
         abytes += 16 * n + 8 * n + 3 * 12 * n + 16ll * nbands;
+        tr.mark("band filter");
         if (nseeds == 0) { ms_seed += ts_.stop(); break; }
         DBuf<Seed> seeds(nseeds); DBuf<uint8_t> consumed(n); consumed.zero(s);
         DN_LAUNCH(k_seeds, (nbands + 255) / 256, 256, 0, s, (const ulonglong2 *)hs, (const int32_t *)bfirst.p, (const u64 *)bkey.p,
@@ -189,9 +240,11 @@ void align_blocks(const DevBlock &A, const DevBlock &B, const AlignParams &P, Ho
         DBuf<int4> pool((size_t)ctas * wpc * pool_stride);
         DBuf<int> counter(1); counter.zero(s);
         ms_seed += ts_.stop();
+        tr.mark("seeds + ext setup");
         te.start();                              // brackets exactly the k_extend launch
         launch_extend(seeds.p, nseeds, EG, tile_off.p, tiles.p, outs.p, pool.p, pool_stride, ctas * wpc, counter.p, s);
         ms_ext += te.stop();
+        tr.mark("k_extend");
 
         // ---- K6: candidates, traces, retirement
         ts_.start();
@@ -215,14 +268,19 @@ void align_blocks(const DevBlock &A, const DevBlock &B, const AlignParams &P, Ho
         round_beg.push_back(round_beg.back() + nvalid);
         round_ntr.push_back(2 * ntr);
         round_cands.push_back(std::move(rc)); round_traces.push_back(std::move(rtr));
+        tr.mark("combine + retire");
         ms_seed += ts_.stop();
     }
 
     // ---- duplicate removal over all candidates, download, final ordering -----------------------
     const int ncand = round_beg.back();
     const int nrounds = (int)round_cands.size();
-    std::vector<Cand> hc(ncand); std::vector<uint8_t> hdrop(ncand);
-    std::vector<std::vector<uint16_t>> htr(nrounds);
+    static PinnedBuf pin_c, pin_t;                  // guarded by the API mutex
+    std::vector<int64_t> tr_base(nrounds + 1, 0);
+    for (int r = 0; r < nrounds; r++) tr_base[r + 1] = tr_base[r] + round_ntr[r];
+    Cand *hc = (Cand *)pin_c.get((size_t)ncand * (sizeof(Cand) + 1) + 64);
+    uint8_t *hdrop = (uint8_t *)(hc + ncand);
+    uint16_t *htr = (uint16_t *)pin_t.get((size_t)tr_base[nrounds] * 2 + 64);
     if (ncand > 0) {
         DBuf<Cand> all(ncand); DBuf<int32_t> rb(nrounds + 1); DBuf<uint8_t> drop(ncand);
         for (int r = 0; r < nrounds; r++)
@@ -231,21 +289,36 @@ void align_blocks(const DevBlock &A, const DevBlock &B, const AlignParams &P, Ho
                                         cudaMemcpyDeviceToDevice, s));
         DN_CUDA(cudaMemcpyAsync(rb.p, round_beg.data(), sizeof(int32_t) * (nrounds + 1), cudaMemcpyHostToDevice, s));
         launch_dedupe(all.p, ncand, rb.p, nrounds, drop.p, s);
-        DN_CUDA(cudaMemcpyAsync(hc.data(), all.p, sizeof(Cand) * ncand, cudaMemcpyDeviceToHost, s));
-        DN_CUDA(cudaMemcpyAsync(hdrop.data(), drop.p, ncand, cudaMemcpyDeviceToHost, s));
-        for (int r = 0; r < nrounds; r++) {
-            htr[r].resize(round_ntr[r]);
-            if (round_ntr[r]) DN_CUDA(cudaMemcpyAsync(htr[r].data(), round_traces[r].p, 2 * round_ntr[r], cudaMemcpyDeviceToHost, s));
-        }
+        DN_CUDA(cudaMemcpyAsync(hc, all.p, sizeof(Cand) * ncand, cudaMemcpyDeviceToHost, s));
+        DN_CUDA(cudaMemcpyAsync(hdrop, drop.p, ncand, cudaMemcpyDeviceToHost, s));
+        for (int r = 0; r < nrounds; r++)
+            if (round_ntr[r]) DN_CUDA(cudaMemcpyAsync(htr + tr_base[r], round_traces[r].p, 2 * round_ntr[r], cudaMemcpyDeviceToHost, s));
         DN_CUDA(cudaStreamSynchronize(s));
     }
-    std::vector<int> order; order.reserve(ncand);
-    for (int j = 0; j < ncand; j++) if (!hdrop[j]) order.push_back(j);
-    auto key = [&](int j) { const Cand &c = hc[j]; return std::make_tuple(c.a, c.bs >> 1, c.bs & 1, c.ab, c.ae, c.bb, c.be, c.diffs); };
-    std::sort(order.begin(), order.end(), [&](int x, int y) { auto kx = key(x), ky = key(y); return kx != ky ? kx < ky : x < y; });
-    out.rec.resize(order.size()); out.toff.resize(order.size());
+    tr.mark("dedupe + download");
+    // LAsort order (base.d:1787-1809): (aread, bread, comp, abpos, aepos, bbpos, bepos, diffs); candidate index last
+    struct OKey { uint64_t k1, k2, k3; int j; };
+    std::vector<OKey> okeys; okeys.reserve(ncand);
+    for (int j = 0; j < ncand; j++) if (!hdrop[j]) {
+        const Cand &c = hc[j];
+        okeys.push_back(OKey{((uint64_t)(uint32_t)c.a << 32) | (uint32_t)(c.bs >> 1),
+                             ((uint64_t)(c.bs & 1) << 62) | ((uint64_t)(uint32_t)c.ab << 31) | (uint32_t)c.ae,
+                             ((uint64_t)(uint32_t)c.bb << 32) | (uint32_t)c.be, j});
+    }
+    std::sort(okeys.begin(), okeys.end(), [&](const OKey &x, const OKey &y) {
+        if (x.k1 != y.k1) return x.k1 < y.k1;
+        if (x.k2 != y.k2) return x.k2 < y.k2;
+        if (x.k3 != y.k3) return x.k3 < y.k3;
+        if (hc[x.j].diffs != hc[y.j].diffs) return hc[x.j].diffs < hc[y.j].diffs;
+        return x.j < y.j; });
+    std::vector<int> order(okeys.size());
+    for (size_t o = 0; o < okeys.size(); o++) order[o] = okeys[o].j;
+    out.nrec = (int64_t)order.size();
     int64_t tot = 0; for (int j : order) tot += 2 * hc[j].nt;
-    out.trace.resize(tot);
+    out.ntrace = tot;
+    out.rec = (dn_las_record *)hcache_alloc(sizeof(dn_las_record) * (order.size() + 1));
+    out.toff = (int64_t *)hcache_alloc(sizeof(int64_t) * (order.size() + 1));
+    out.trace = (uint16_t *)hcache_alloc(sizeof(uint16_t) * (tot + 1));
     int64_t to = 0, aligned = 0;
     for (size_t o = 0; o < order.size(); o++) {
         const int j = order[o]; const Cand &c = hc[j];
@@ -254,11 +327,12 @@ void align_blocks(const DevBlock &A, const DevBlock &B, const AlignParams &P, Ho
         q.tlen = 2 * c.nt; q.diffs = c.diffs; q.abpos = c.ab; q.bbpos = c.bb; q.aepos = c.ae; q.bepos = c.be;
         q.flags = (c.bs & 1) ? DN_LAS_COMP : 0u; q.aread = c.a; q.bread = c.bs >> 1; q.pad_ = 0;
         out.toff[o] = to;
-        memcpy(out.trace.data() + to, htr[r].data() + c.toff, sizeof(uint16_t) * 2 * c.nt);
+        memcpy(out.trace + to, htr + tr_base[r] + c.toff, sizeof(uint16_t) * 2 * c.nt);
         to += 2 * c.nt; aligned += c.ae - c.ab;
         ext_bytes += (c.ae - c.ab) / 4 + (c.be - c.bb) / 4 + 40 + 4 * c.nt;
     }
-    out.stats.las = (int64_t)order.size(); out.stats.aligned_bases = aligned; out.stats.trace_points = tot / 2;
+    tr.mark("host order + gather");
+    out.stats.las = out.nrec; out.stats.aligned_bases = aligned; out.stats.trace_points = tot / 2;
     out.stats.algo_bytes_seed = abytes; out.stats.algo_bytes_extend = ext_bytes;
     out.stats.ms_seed = ms_seed; out.stats.ms_extend = ms_ext; out.stats.ms_total = tt.stop();
     out.stats.launches = g_launches.load() - launches0;

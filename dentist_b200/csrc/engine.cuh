@@ -34,12 +34,18 @@ struct AlignParams {
         rounds = 3, self = 0, poolmul = 64, join_mode = 0;   // join_mode: 0 auto, 1 sorted merge, 2 index lookup
 };
 
+// Host result in its final (C ABI) form; arrays come from the recycling host cache (hcache_*).
 struct HostLas {
-    std::vector<dn_las_record> rec;     // sorted in LAsort order
-    std::vector<int64_t> toff;          // trace offset (uint16 units) per record
-    std::vector<uint16_t> trace;        // (diffs, bbases) pairs
+    dn_las_record *rec = nullptr;       // sorted in LAsort order
+    int64_t *toff = nullptr;            // trace offset (uint16 units) per record
+    uint16_t *trace = nullptr;          // (diffs, bbases) pairs
+    int64_t nrec = 0, ntrace = 0;
     dn_align_stats stats{};
 };
+
+// Recycling host allocator for result buffers: fresh multi-MB mallocs page-fault for milliseconds.
+void *hcache_alloc(size_t bytes);
+void hcache_free(void *p);
 
 void block_upload(const dn_block_desc &d, DevBlock &out, cudaStream_t s);
 void align_blocks(const DevBlock &A, const DevBlock &B, const AlignParams &P, HostLas &out, cudaStream_t s);

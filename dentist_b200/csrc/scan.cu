@@ -6,7 +6,45 @@ namespace dn {
 
 std::atomic<unsigned long long> g_launches{0};
 
-cudaStream_t &cur_stream() { static thread_local cudaStream_t s = nullptr; return s; }
+Arena &arena() { static Arena a; return a; }
+
+void *Arena::alloc(size_t bytes) {
+    bytes = (bytes + 511) & ~(size_t)511;
+    cur += bytes; if (cur > high) high = cur;
+    if (!chunks.empty()) {
+        Chunk &c = chunks.back();
+        if (c.used + bytes <= c.cap) { void *r = c.p + c.used; c.used += bytes; return r; }
+    }
+    size_t cap = bytes > (1ull << 30) ? bytes : (1ull << 30);
+    Chunk c{nullptr, cap, bytes};
+    DN_CUDA(cudaMalloc((void **)&c.p, cap));
+    chunks.push_back(c);
+    return c.p;
+}
+
+void Arena::reset() {
+    cur = 0;
+    if (chunks.size() > 1 || (chunks.size() == 1 && chunks[0].cap < high)) {     // coalesce into one slab of the high-water size
+        cudaDeviceSynchronize();
+        for (Chunk &c : chunks) cudaFree(c.p);
+        chunks.clear();
+        size_t cap = high + (high >> 3) + (64ull << 20);
+        Chunk c{nullptr, cap, 0};
+        if (cudaMalloc((void **)&c.p, cap) == cudaSuccess) chunks.push_back(c); else cudaGetLastError();
+    }
+    for (Chunk &c : chunks) c.used = 0;
+}
+
+void Arena::destroy() { for (Chunk &c : chunks) cudaFree(c.p); chunks.clear(); high = cur = 0; }
+
+void *PinnedBuf::get(size_t bytes) {
+    if (bytes > cap) {
+        if (p) cudaFreeHost(p);
+        p = nullptr; cap = bytes + (bytes >> 2) + (1 << 20);
+        DN_CUDA(cudaHostAlloc(&p, cap, cudaHostAllocDefault));
+    }
+    return p;
+}
 
 int sm_count() {
     static int n = 0;

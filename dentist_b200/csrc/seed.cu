@@ -80,16 +80,16 @@ void block_upload(const dn_block_desc &d, DevBlock &B, cudaStream_t s) {
     B.h_off[d.nreads] = g; B.total = g;
     if (2 * g >= (1ll << 32) - 1024) throw Error("block too large: 2*padded bases must be < 2^32");
     size_t nwords = (size_t)(g >> 4) + 8;
-    B.fwd.alloc(nwords); B.rc.alloc(nwords);
+    B.fwd.persistent(nwords); B.rc.persistent(nwords);
     B.fwd.zero(s); B.rc.zero(s);
-    B.off.alloc(d.nreads + 1); B.len.alloc(d.nreads > 0 ? d.nreads : 1);
-    B.chunk2read.alloc((size_t)(g >> 10) + 2);
+    B.off.persistent(d.nreads + 1); B.len.persistent(d.nreads > 0 ? d.nreads : 1);
+    B.chunk2read.persistent((size_t)(g >> 10) + 2);
     B.chunk2read.zero(s);
     DN_CUDA(cudaMemcpyAsync(B.off.p, B.h_off.data(), sizeof(int64_t) * (d.nreads + 1), cudaMemcpyHostToDevice, s));
     if (d.nreads == 0) { DN_CUDA(cudaStreamSynchronize(s)); return; }
     DN_CUDA(cudaMemcpyAsync(B.len.p, B.h_len.data(), sizeof(int32_t) * d.nreads, cudaMemcpyHostToDevice, s));
-    DBuf<uint8_t> raw((size_t)d.data_bytes + 16);
-    DBuf<int64_t> boff(d.nreads);
+    DBuf<uint8_t> raw; raw.persistent((size_t)d.data_bytes + 16);
+    DBuf<int64_t> boff; boff.persistent(d.nreads);
     DN_CUDA(cudaMemcpyAsync(raw.p, d.data, d.data_bytes, cudaMemcpyHostToDevice, s));
     DN_CUDA(cudaMemcpyAsync(boff.p, d.boff, sizeof(int64_t) * d.nreads, cudaMemcpyHostToDevice, s));
     DN_LAUNCH(k_pack, d.nreads, 128, 0, s, (const uint8_t *)raw.p, (const int64_t *)boff.p, (const int32_t *)B.len.p,
@@ -101,8 +101,8 @@ void block_upload(const dn_block_desc &d, DevBlock &B, cudaStream_t s) {
         if (nbytes > 0) {
             B.has_mask = true;
             size_t mw = (size_t)(g >> 5) + 4;
-            B.mask.alloc(mw); B.mask_rc.alloc(mw); B.mask.zero(s); B.mask_rc.zero(s);
-            DBuf<int64_t> anno(d.nreads + 1); DBuf<int32_t> md((size_t)nbytes / 4 + 2);
+            B.mask.persistent(mw); B.mask_rc.persistent(mw); B.mask.zero(s); B.mask_rc.zero(s);
+            DBuf<int64_t> anno; anno.persistent(d.nreads + 1); DBuf<int32_t> md; md.persistent((size_t)nbytes / 4 + 2);
             DN_CUDA(cudaMemcpyAsync(anno.p, d.mask_anno, sizeof(int64_t) * (d.nreads + 1), cudaMemcpyHostToDevice, s));
             DN_CUDA(cudaMemcpyAsync(md.p, d.mask_data, nbytes, cudaMemcpyHostToDevice, s));
             DN_LAUNCH(k_mask_bits, d.nreads, 64, 0, s, (const int64_t *)anno.p, (const int32_t *)md.p, d.nreads,

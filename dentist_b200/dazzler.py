@@ -90,19 +90,40 @@ def make_params(**kw):
     return p
 
 
+class _LasOwner:
+    """Keeps a dn_las_buf alive while numpy views of its arrays exist (zero-copy hand-off)."""
+
+    def __init__(self, buf):
+        self.buf = buf
+
+    def __del__(self):
+        try:
+            _lib.lib().dn_las_free(C.byref(self.buf))
+        except Exception:
+            pass
+
+
+class _View(np.ndarray):
+    _owner = None
+
+
+def _wrap(ptr, nbytes, dtype, owner):
+    if not nbytes:
+        return np.zeros(0, dtype)
+    raw = (C.c_uint8 * nbytes).from_address(C.addressof(ptr.contents))
+    arr = np.frombuffer(raw, dtype=dtype).view(_View)
+    arr._owner = owner
+    return arr
+
+
 def _take(buf):
+    owner = _LasOwner(buf)
     n = int(buf.nrec)
-    if n:
-        rec = np.ctypeslib.as_array(C.cast(buf.rec, C.POINTER(C.c_uint8)), shape=(n * 40,)).view(_lib.REC_DTYPE).copy()
-        toff = np.ctypeslib.as_array(buf.toff, shape=(n,)).copy()
-    else:
-        rec = np.zeros(0, _lib.REC_DTYPE)
-        toff = np.zeros(0, np.int64)
-    tr = np.ctypeslib.as_array(buf.trace, shape=(int(buf.ntrace),)).copy() if buf.ntrace else np.zeros(0, np.uint16)
+    rec = _wrap(buf.rec, n * 40, _lib.REC_DTYPE, owner)
+    toff = _wrap(buf.toff, n * 8, np.int64, owner)
+    tr = _wrap(buf.trace, int(buf.ntrace) * 2, np.uint16, owner)
     st = {n_: getattr(buf.stats, n_) for n_, _ in _lib.AlignStats._fields_}
-    tspace = int(buf.tspace)
-    _lib.lib().dn_las_free(C.byref(buf))
-    return rec, toff, tr, tspace, st
+    return rec, toff, tr, int(buf.tspace), st
 
 
 def align_blocks(a, b, **params):
