@@ -1,0 +1,79 @@
+"""File-level drop-ins: getDalignment / getDamapping read DAZZ_DB files and write LAS files that the
+reference's reader would accept (checked with the pinned oracle codec) and that equal the in-memory result."""
+import numpy as np
+import pytest
+
+from dentist_b200 import synth
+from tests import dbutil
+
+pytestmark = pytest.mark.gpu
+
+
+def _case(seed):
+    sc = synth.make_scaffolds(1, 80000, seed, n_repeats=0)
+    ref, _ = synth.contigs_from(sc, synth.make_gaps(sc, 1, seed + 1))
+    reads, _ = synth.simulate_reads(sc, 4, 6000, 2000, 0.13, seed + 2)
+    return ref, reads
+
+
+def test_getDamapping_writes_both_las_files(tmp_path):
+    from dentist_b200 import dazzler
+    from oracle import las
+    ref, reads = _case(51)
+    dbutil.write_db(str(tmp_path / "ref.dam"), ref)
+    dbutil.write_db(str(tmp_path / "reads.db"), reads)
+    out = dazzler.getDamapping(str(tmp_path / "ref.dam"), str(tmp_path / "reads.db"), ["-C", "-T8", "-e0.7", "-l500"], str(tmp_path))
+    assert out == str(tmp_path / "ref.reads.las")
+    ts, rec, traces = las.decode(open(out, "rb").read())
+    assert ts == 100 and len(rec) > 20
+    ga, gb = dazzler.Block(ref.off, ref.bases), dazzler.Block(reads.off, reads.bases)
+    mrec, mtoff, mtr, _ = dazzler.align_blocks(ga, gb, tspace=100, minlen=500)
+    for f in ("aread", "bread", "abpos", "aepos", "bbpos", "bepos", "diffs", "tlen"):
+        assert np.array_equal(rec[f], mrec[f]), f
+    assert np.concatenate([t.reshape(-1) for t in traces]).tolist() == np.minimum(mtr, 255).tolist()
+    assert all(int(f) & las.START for f in rec["flags"])              # chain flags set -> AlignmentChainPacker accepts it
+    assert len(las.chains(rec)) == len(rec)
+    # transposed file exists, is sorted by read and has uint8 traces
+    ts2, rec2, tr2 = las.decode(open(str(tmp_path / "reads.ref.las"), "rb").read())
+    assert len(rec2) > 20 and rec2["aread"].tolist() == sorted(rec2["aread"].tolist())
+    for r, t in zip(rec2, tr2):
+        assert int(t[:, 1].sum()) == r["bepos"] - r["bbpos"] and len(t) == las.num_tiles(int(r["abpos"]), int(r["aepos"]), 100)
+    # the ABI's own reader agrees with the oracle reader
+    ts3, rec3, toff3, tr3 = dazzler.read_las(out)
+    assert ts3 == 100 and rec3.tobytes() == rec.tobytes()
+
+
+def test_getDalignment_pile_with_dust_mask(tmp_path):
+    """processPileUps: `daligner -T<n> -B -s126 -l500 -e0.7 -mdust X X` (commandline.d:2886-2902)."""
+    from dentist_b200 import dazzler
+    from oracle import las, oracle
+    sc = synth.make_scaffolds(1, 20000, 61, n_repeats=0)
+    pile, _ = synth.simulate_reads(sc, 8, 6000, 1500, 0.13, 62)
+    db = str(tmp_path / "pile.db")
+    dbutil.write_db(db, pile)
+    mask = [[(200, 260), (1000, 1100)] for _ in range(pile.nreads)]
+    dbutil.write_track(db, "dust", mask)
+    out = dazzler.getDalignment(db, None, ["-T8", "-B", "-s126", "-l500", "-e0.7", "-mdust"], str(tmp_path))
+    assert out.endswith("pile.pile.las")
+    ts, rec, traces = las.decode(open(out, "rb").read())
+    assert ts == 126
+    m = np.zeros(pile.total, np.uint8)
+    for r in range(pile.nreads):
+        for b, e in mask[r]:
+            m[pile.off[r] + b:pile.off[r] + e] = 1
+    la, tr, _ = oracle.align(pile.off, pile.bases, pile.off, pile.bases, a_mask=m, b_mask=m, tspace=126, minlen=500, self=1)
+    assert len(la) == len(rec) > 50
+    for f in ("aread", "bread", "abpos", "aepos", "bbpos", "bepos", "diffs", "flags"):
+        assert np.array_equal(rec[f], la[f]), f
+    assert np.concatenate([t.reshape(-1) for t in traces]).tolist() == tr.tolist()
+    assert not np.any(rec["aread"] == rec["bread"])
+
+
+def test_errors_are_reported_not_swallowed(tmp_path):
+    from dentist_b200 import dazzler
+    with pytest.raises(dazzler.DnError, match="cannot find DB stub"):
+        dazzler.getDalignment(str(tmp_path / "nope.db"), None, ["-s126"], str(tmp_path))
+    ref, reads = _case(71)
+    dbutil.write_db(str(tmp_path / "r.db"), reads)
+    with pytest.raises(dazzler.DnError, match="unknown option"):
+        dazzler.getDalignment(str(tmp_path / "r.db"), None, ["-Q3"], str(tmp_path))
