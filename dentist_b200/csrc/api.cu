@@ -1,25 +1,22 @@
 // api.cu -- the C ABI (include/dentist_b200.h): lifecycle, resident blocks, in-memory alignment,
 // LAS serialisation and the file-level drop-ins for dazzler.d's getDalignment / getDamapping.
-#include "engine.cuh"
+#include "api_internal.hpp"
 #include "dazzdb.hpp"
-#include <mutex>
 #include <string.h>
 #include <stdlib.h>
-#include <string>
 
 using namespace dn;
+using namespace dnapi;
 
-struct dn_block { DevBlock b; };
-
-namespace {
+namespace dnapi {
 thread_local std::string t_err;
-std::mutex g_mu;                 // serialises device work: entry points are re-entrant, the GPU queue is one
+std::mutex g_mu;
 int g_device = -1;
 cudaStream_t g_stream = nullptr;
 
 int fail(int code, const std::string &m) { t_err = m; return code; }
 
-void setup_device() {
+static void setup_device() {
     if (!g_stream) cudaStreamCreateWithFlags(&g_stream, cudaStreamNonBlocking);
 }
 
@@ -34,13 +31,9 @@ int ensure_device() {
     return DN_OK;
 }
 
-template <typename F> int guarded(F &&f) {
-    try { return f(); }
-    catch (const dn::Error &e) { return fail(DN_ERR_CUDA, e.what()); }
-    catch (const std::bad_alloc &) { return fail(DN_ERR_INVALID, "out of host memory"); }
-    catch (const std::exception &e) { return fail(DN_ERR_INVALID, e.what()); }
-}
+}  // namespace dnapi
 
+namespace {
 AlignParams to_internal(const dn_align_params *p) {
     dn_align_params d; dn_align_params_default(&d);
     if (p) d = *p;

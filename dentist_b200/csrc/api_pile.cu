@@ -1,0 +1,167 @@
+// api_pile.cu -- C ABI of the per-pile stages: LAS filters, intrinsic QVs, consensus.
+#include "api_internal.hpp"
+#include "pile.cuh"
+#include <string.h>
+#include <stdlib.h>
+#include <algorithm>
+
+using namespace dn;
+using namespace dnapi;
+
+namespace {
+
+struct DevLasIn {               // a host dn_las_buf mirrored in the arena
+    DBuf<dn_las_record> rec; DBuf<int64_t> toff; DBuf<uint16_t> trace;
+    void upload(const dn_las_buf *l, bool with_trace, cudaStream_t s) {
+        rec.alloc(l->nrec + 1); toff.alloc(l->nrec + 1);
+        if (l->nrec) {
+            DN_CUDA(cudaMemcpyAsync(rec.p, l->rec, sizeof(dn_las_record) * l->nrec, cudaMemcpyHostToDevice, s));
+            DN_CUDA(cudaMemcpyAsync(toff.p, l->toff, sizeof(int64_t) * l->nrec, cudaMemcpyHostToDevice, s));
+        }
+        if (with_trace) {
+            trace.alloc(l->ntrace + 2);
+            if (l->ntrace) DN_CUDA(cudaMemcpyAsync(trace.p, l->trace, sizeof(uint16_t) * l->ntrace, cudaMemcpyHostToDevice, s));
+        }
+    }
+};
+
+template <typename T> T *to_device(DBuf<T> &d, const T *h, size_t n, cudaStream_t s) {
+    d.alloc(n + 1);
+    if (n) DN_CUDA(cudaMemcpyAsync(d.p, h, sizeof(T) * n, cudaMemcpyHostToDevice, s));
+    return d.p;
+}
+
+int filter_common(dn_las_buf *las, int mode, double max_err, const int32_t *alen, int32_t na, const int32_t *blen, int32_t nb, int allowance) {
+    if (!las) return fail(DN_ERR_INVALID, "null argument");
+    if (mode == 1) {
+        if (!alen || !blen) return fail(DN_ERR_INVALID, "null read lengths");
+        for (int64_t i = 0; i < las->nrec; i++)
+            if (las->rec[i].aread < 0 || las->rec[i].aread >= na || las->rec[i].bread < 0 || las->rec[i].bread >= nb)
+                return fail(DN_ERR_INVALID, "contig id out of bounds");            // dazzler.d:1765-1778
+    }
+    std::lock_guard<std::mutex> lk(g_mu);
+    if (int rc = ensure_device()) return rc;
+    return guarded([&] {
+        cudaSetDevice(g_device); arena().reset();
+        DevLasIn d; d.upload(las, false, g_stream);
+        DBuf<int32_t> da, db; 
+        if (mode == 1) { to_device(da, alen, na, g_stream); to_device(db, blen, nb, g_stream); }
+        DBuf<dn_las_record> orec(las->nrec + 1); DBuf<int64_t> otoff(las->nrec + 1);
+        int64_t n_out = 0;
+        las_filter_device(d.rec.p, d.toff.p, las->nrec, mode, max_err, da.p, db.p, allowance, orec.p, otoff.p, &n_out, g_stream);
+        if (n_out) {
+            DN_CUDA(cudaMemcpyAsync(las->rec, orec.p, sizeof(dn_las_record) * n_out, cudaMemcpyDeviceToHost, g_stream));
+            DN_CUDA(cudaMemcpyAsync(las->toff, otoff.p, sizeof(int64_t) * n_out, cudaMemcpyDeviceToHost, g_stream));
+        }
+        DN_CUDA(cudaStreamSynchronize(g_stream));
+        las->nrec = n_out;
+        return DN_OK;
+    });
+}
+}  // namespace
+
+extern "C" {
+
+void dn_free(void *p) { hcache_free(p); }
+
+int dn_las_filter_error(dn_las_buf *las, double max_err) { return filter_common(las, 0, max_err, nullptr, 0, nullptr, 0, 0); }
+
+int dn_las_filter_pileup(dn_las_buf *las, const int32_t *alen, int32_t na, const int32_t *blen, int32_t nb, int32_t allowance) {
+    return filter_common(las, 1, 0.0, alen, na, blen, nb, allowance);
+}
+
+int dn_compute_qvs(const int32_t *rlen, int32_t nreads, const dn_las_buf *las, int32_t coverage, uint8_t **qv, int64_t **qoff) {
+    if (!rlen || !las || !qv || !qoff || nreads < 0) return fail(DN_ERR_INVALID, "null argument");
+    if (las->tspace < 1) return fail(DN_ERR_INVALID, "bad trace spacing");
+    for (int64_t i = 0; i < las->nrec; i++) {
+        if (las->rec[i].aread < 0 || las->rec[i].aread >= nreads) return fail(DN_ERR_INVALID, "contig id out of bounds");
+        if (i && las->rec[i].aread < las->rec[i - 1].aread) return fail(DN_ERR_INVALID, "LAS not sorted by A read");
+    }
+    std::lock_guard<std::mutex> lk(g_mu);
+    if (int rc = ensure_device()) return rc;
+    return guarded([&] {
+        cudaSetDevice(g_device); arena().reset();
+        const int ts = las->tspace;
+        int64_t *ho = (int64_t *)hcache_alloc(sizeof(int64_t) * (nreads + 1));
+        ho[0] = 0; for (int r = 0; r < nreads; r++) ho[r + 1] = ho[r] + (rlen[r] + ts - 1) / ts;
+        uint8_t *hq = (uint8_t *)hcache_alloc(ho[nreads] + 1);
+        DevLasIn d; d.upload(las, true, g_stream);
+        DBuf<int32_t> dl; to_device(dl, rlen, nreads, g_stream);
+        DBuf<int64_t> dq; to_device(dq, (const int64_t *)ho, nreads + 1, g_stream);
+        DBuf<uint8_t> q(ho[nreads] + 1);
+        qv_device(dl.p, nreads, d.rec.p, las->nrec, d.toff.p, d.trace.p, ts, coverage, dq.p, q.p, g_stream);
+        if (ho[nreads]) DN_CUDA(cudaMemcpyAsync(hq, q.p, ho[nreads], cudaMemcpyDeviceToHost, g_stream));
+        DN_CUDA(cudaStreamSynchronize(g_stream));
+        *qv = hq; *qoff = ho;
+        return DN_OK;
+    });
+}
+
+void dn_seq_free(dn_seq_buf *b) { if (!b) return; hcache_free(b->off); hcache_free(b->bases); memset(b, 0, sizeof *b); }
+
+int dn_consensus(const dn_block *db, const dn_las_buf *las, const int32_t *reads, int32_t nreads, dn_seq_buf *out) {
+    if (!db || !las || !reads || !out || nreads < 0) return fail(DN_ERR_INVALID, "null argument");
+    const DevBlock &B = db->b;
+    if (las->tspace < 1 || las->tspace > 128) return fail(DN_ERR_INVALID, "consensus needs trace spacing <= 128");
+    for (int i = 0; i < nreads; i++) if (reads[i] < 0 || reads[i] >= B.nreads) return fail(DN_ERR_INVALID, "read id out of bounds");
+    for (int64_t i = 0; i < las->nrec; i++)
+        if (las->rec[i].aread < 0 || las->rec[i].aread >= B.nreads || las->rec[i].bread < 0 || las->rec[i].bread >= B.nreads)
+            return fail(DN_ERR_INVALID, "contig id out of bounds");
+    std::lock_guard<std::mutex> lk(g_mu);
+    if (int rc = ensure_device()) return rc;
+    return guarded([&] {
+        cudaSetDevice(g_device); arena().reset();
+        cudaStream_t s = g_stream;
+        const int ts = las->tspace;
+        // host: which LAs vote, for which target; vote-column and task offsets
+        std::vector<int32_t> target_of(B.nreads, -1);
+        for (int i = 0; i < nreads; i++) target_of[reads[i]] = i;          // a read listed twice: last wins
+        std::vector<int64_t> vote_off(nreads + 1, 0);
+        for (int i = 0; i < nreads; i++) vote_off[i + 1] = vote_off[i] + B.h_len[reads[i]] + 1;
+        const int64_t ncols = vote_off[nreads];
+        std::vector<int32_t> vla, la_target(las->nrec + 1, -1); std::vector<int64_t> task_off;
+        int64_t ntasks = 0;
+        for (int64_t x = 0; x < las->nrec; x++) {
+            int tg = target_of[las->rec[x].aread];
+            if (tg < 0 || reads[tg] != las->rec[x].aread) continue;
+            la_target[x] = tg; vla.push_back((int32_t)x); task_off.push_back(ntasks); ntasks += las->rec[x].tlen / 2;
+        }
+        DevLasIn d; d.upload(las, true, s);
+        DBuf<int32_t> d_vla, d_lat, d_targets; DBuf<int64_t> d_toff, d_voff;
+        to_device(d_vla, vla.data(), vla.size(), s); to_device(d_lat, la_target.data(), la_target.size(), s);
+        to_device(d_targets, reads, nreads, s); to_device(d_toff, task_off.data(), task_off.size(), s);
+        to_device(d_voff, vote_off.data(), vote_off.size(), s);
+        ConsGeom G{B.fwd.p, B.rc.p, B.off.p, B.len.p, d_voff.p};
+        DBuf<int32_t> cnt(ncols * 5 + 1), ins(ncols * 4 + 1), insn(ncols + 1), cov(ncols + 1);
+        cnt.zero(s); ins.zero(s); insn.zero(s); cov.zero(s);
+        if (ntasks > 0) {
+            DBuf<ConsTask> tasks(ntasks);
+            launch_cons_tasks(d.rec.p, d.toff.p, d.trace.p, d_vla.p, (int)vla.size(), d_toff.p, ts, tasks.p, s);
+            DBuf<u32> scratch((size_t)cons_vote_threads() * 2048);
+            launch_cons_vote(tasks.p, ntasks, d.rec.p, d_lat.p, G, scratch.p, cnt.p, ins.p, insn.p, cov.p, s);
+        }
+        DBuf<int32_t> nemit(ncols + 1), eoff(ncols + 1), tot(1); DBuf<uint8_t> sym(2 * ncols + 2);
+        int32_t total = 0;
+        if (ncols > 0) {
+            launch_cons_count(G, d_targets.p, nreads, ncols, cnt.p, ins.p, insn.p, cov.p, nemit.p, sym.p, s);
+            exclusive_scan_i32(nemit.p, eoff.p, ncols, tot.p, s);
+            DN_CUDA(cudaMemcpyAsync(&total, tot.p, 4, cudaMemcpyDeviceToHost, s)); DN_CUDA(cudaStreamSynchronize(s));
+        }
+        DBuf<uint8_t> dout(total + 1);
+        if (ncols > 0) launch_cons_write(ncols, nemit.p, eoff.p, sym.p, dout.p, s);
+        // sequence offsets = eoff at each target's first column
+        std::vector<int32_t> heoff(nreads + 1, total);
+        for (int i = 0; i < nreads; i++)
+            DN_CUDA(cudaMemcpyAsync(&heoff[i], eoff.p + vote_off[i], 4, cudaMemcpyDeviceToHost, s));
+        memset(out, 0, sizeof *out);
+        out->nseq = nreads;
+        out->off = (int64_t *)hcache_alloc(sizeof(int64_t) * (nreads + 1));
+        out->bases = (uint8_t *)hcache_alloc(total + 1);
+        if (total) DN_CUDA(cudaMemcpyAsync(out->bases, dout.p, total, cudaMemcpyDeviceToHost, s));
+        DN_CUDA(cudaStreamSynchronize(s));
+        for (int i = 0; i <= nreads; i++) out->off[i] = heoff[i];
+        return DN_OK;
+    });
+}
+
+}  // extern "C"

@@ -1,0 +1,233 @@
+// pile.cu -- per-pile-up stages of processPileUps on the device:
+//   k_las_filter   averageErrorRate filter (dazzler.d:3885-3899, base.d:1764-1767) and
+//                  isValidPileUpAlignment (dazzler.d:4126-4141)
+//   k_qv           per-tile intrinsic QVs (what DAScover/DASqv and computeintrinsicqv produce behind
+//                  dazzler.d:3782-3792, 6142-6183)
+//   k_cons_*       consensus of a reference read over its pile (what daccord produces behind
+//                  dazzler.d:4213-4255): per-tile global alignment from the trace points, column votes,
+//                  majority emit
+// Specification = oracle/pile_oracle.c (header); everything is integer work except the one fp64 compare
+// of the error-rate filter, which is evaluated with the same IEEE operations as the D source.
+#include "engine.cuh"
+#include "pile.cuh"
+
+namespace dn {
+namespace {
+
+__global__ void __launch_bounds__(256) k_las_filter(const dn_las_record *__restrict__ rec, int64_t n, int mode, double max_err,
+                                                    const int32_t *__restrict__ alen, const int32_t *__restrict__ blen,
+                                                    int allowance, int32_t *__restrict__ keep) {
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const dn_las_record x = rec[i];
+    int k;
+    if (mode == 0) {
+        double rate = (double)x.diffs / (double)(x.aepos - x.abpos);
+        k = rate <= max_err;
+    } else {
+        const int la = alen[x.aread], lb = blen[x.bread];
+        const bool ab = x.abpos <= allowance, bb = x.bbpos <= allowance;
+        const bool ae = x.aepos + allowance >= la, be = x.bepos + allowance >= lb;
+        k = x.aread != x.bread && (((ab && bb) && (ae || be)) || ((ae && be) && (ab || bb)));
+    }
+    keep[i] = k;
+}
+
+__global__ void __launch_bounds__(256) k_las_compact(const dn_las_record *__restrict__ rec, const int64_t *__restrict__ toff, int64_t n,
+                                                     const int32_t *__restrict__ keep, const int32_t *__restrict__ kidx,
+                                                     dn_las_record *__restrict__ orec, int64_t *__restrict__ otoff) {
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n || !keep[i]) return;
+    orec[kidx[i]] = rec[i]; otoff[kidx[i]] = toff[i];          // traces stay where they are
+}
+
+// one CTA per read; records sorted by aread
+__global__ void __launch_bounds__(128) k_qv(const int32_t *__restrict__ rlen, const dn_las_record *__restrict__ rec, int64_t nla,
+                                            const int64_t *__restrict__ toff, const uint16_t *__restrict__ trace, int ts, int cov,
+                                            const int64_t *__restrict__ qoff, uint8_t *__restrict__ qv) {
+    const int r = blockIdx.x;
+    __shared__ int64_t s_lo, s_hi;
+    if (threadIdx.x == 0) {
+        int64_t a = 0, b = nla;
+        while (a < b) { int64_t m = (a + b) >> 1; if (rec[m].aread < r) a = m + 1; else b = m; }
+        s_lo = a; b = nla;
+        while (a < b) { int64_t m = (a + b) >> 1; if (rec[m].aread <= r) a = m + 1; else b = m; }
+        s_hi = a;
+    }
+    __syncthreads();
+    const int L = rlen[r], nt = (L + ts - 1) / ts;
+    for (int t = threadIdx.x; t < nt; t += blockDim.x) {
+        const int t0 = t * ts, t1 = min((t + 1) * ts, L);
+        unsigned char hist[51];
+#pragma unroll
+        for (int i = 0; i < 51; i++) hist[i] = 0;
+        int m = 0;
+        for (int64_t x = s_lo; x < s_hi; x++) {
+            const int ab = rec[x].abpos, ae = rec[x].aepos;
+            if (ab > t0 || ae < t1) continue;
+            const uint16_t *tp = trace + toff[x] + 2 * (t - ab / ts);
+            const int den = (t1 - t0) + tp[1];
+            int v = (200 * (int)tp[0] + den / 2) / den;
+            if (v > 50) v = 50;
+            if (hist[v] < 255) hist[v]++;
+            m++;
+        }
+        int q = 50;
+        if (m * 4 >= cov && m > 0) {
+            int n = cov / 2; if (n < 1) n = 1; if (n > m) n = m;
+            int s = 0, left = n;
+            for (int v = 0; v <= 50 && left > 0; v++) { int c = min((int)hist[v], left); s += c * v; left -= c; }
+            q = (2 * s + n) / (2 * n);
+            if (q > 50) q = 50;
+        }
+        qv[qoff[r] + t] = (uint8_t)q;
+    }
+}
+
+// ------------------------------------------------------------------------------- consensus
+
+__device__ __forceinline__ int base_at(const u32 *__restrict__ w, int64_t g) { return (int)((w[g >> 4] >> ((g & 15) << 1)) & 3u); }
+
+// thread per voting LA: expand its trace into tile tasks
+__global__ void __launch_bounds__(256) k_cons_tasks(const dn_las_record *__restrict__ rec, const int64_t *__restrict__ toff,
+                                                    const uint16_t *__restrict__ trace, const int32_t *__restrict__ vla, int nvla,
+                                                    const int64_t *__restrict__ task_off, int ts, ConsTask *__restrict__ tasks) {
+    int v = blockIdx.x * blockDim.x + threadIdx.x;
+    if (v >= nvla) return;
+    const int x = vla[v];
+    const dn_las_record la = rec[x];
+    int ap = la.abpos, bp = la.bbpos; const int nt = la.tlen / 2;
+    ConsTask *o = tasks + task_off[v];
+    for (int t = 0; t < nt; t++) {
+        const int aend = (t == nt - 1) ? la.aepos : (ap / ts + 1) * ts;
+        const int bb = trace[toff[x] + 2 * t + 1];
+        o[t] = ConsTask{x, ap, aend - ap, bp, bb};
+        ap = aend; bp += bb;
+    }
+}
+
+// thread per tile task: unit-cost global alignment (full DP, directions kept in an interleaved scratch),
+// traceback with priority diagonal > deletion > insertion, atomic column votes
+__global__ void __launch_bounds__(128) k_cons_vote(const ConsTask *__restrict__ tasks, int64_t ntasks,
+                                                   const dn_las_record *__restrict__ rec, const int32_t *__restrict__ la_target,
+                                                   ConsGeom G, u32 *__restrict__ scratch, int32_t *__restrict__ cnt,
+                                                   int32_t *__restrict__ ins, int32_t *__restrict__ insn, int32_t *__restrict__ cov) {
+    const int64_t nthreads = (int64_t)gridDim.x * blockDim.x;
+    const int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    u32 *dirs = scratch + tid;                               // word w of this thread lives at dirs[w * nthreads]
+    for (int64_t task = tid; task < ntasks; task += nthreads) {
+        const ConsTask T = tasks[task];
+        const int n = T.alen, m = T.bb;
+        if (m > 250 || n > 128) continue;
+        const dn_las_record la = rec[T.la];
+        const int tg = la_target[T.la];                       // index of the target (consensus) read
+        const int64_t vbase = G.vote_off[tg];                 // first column of this target in the vote arrays
+        const u32 *Aw = G.fwd, *Bw = (la.flags & DN_LAS_COMP) ? G.rc : G.fwd;
+        const int64_t ga = G.off[la.aread] + T.ap, gb = G.off[la.bread] + T.bp;
+        unsigned char bq[256], row[256];
+        for (int j = 0; j < m; j++) bq[j] = (unsigned char)base_at(Bw, gb + j);
+        for (int j = 0; j <= m; j++) row[j] = (unsigned char)j;
+        const int wpr = (m + 16) >> 4;                        // direction words per row (16 cells per word)
+        for (int i = 1; i <= n; i++) {
+            const int ai = base_at(Aw, ga + i - 1);
+            int diag = row[0]; row[0] = (unsigned char)i;
+            int left = i;
+            u32 word = 0;
+            for (int j = 1; j <= m; j++) {
+                const int up = row[j];
+                const int d = diag + (ai != bq[j - 1]), u = up + 1, l = left + 1;
+                int v = d; if (u < v) v = u; if (l < v) v = l;
+                const u32 dir = (v == d) ? 0u : ((v == u) ? 1u : 2u);
+                word |= dir << ((j & 15) << 1);
+                if ((j & 15) == 15 || j == m) { dirs[(int64_t)((i - 1) * wpr + (j >> 4)) * nthreads] = word; word = 0; }
+                row[j] = (unsigned char)v; diag = up; left = v;
+            }
+        }
+        int i = n, j = m, pend = -1;
+        while (i > 0 || j > 0) {
+            u32 dir;
+            if (i == 0) dir = 2u; else if (j == 0) dir = 1u;
+            else dir = (dirs[(int64_t)((i - 1) * wpr + (j >> 4)) * nthreads] >> ((j & 15) << 1)) & 3u;
+            if (dir != 2u && pend >= 0) { atomicAdd(&ins[(vbase + T.ap + i) * 4 + pend], 1); atomicAdd(&insn[vbase + T.ap + i], 1); pend = -1; }
+            if (dir == 0u) { atomicAdd(&cnt[(vbase + T.ap + i - 1) * 5 + bq[j - 1]], 1); i--; j--; }
+            else if (dir == 1u) { atomicAdd(&cnt[(vbase + T.ap + i - 1) * 5 + 4], 1); i--; }
+            else { pend = bq[j - 1]; j--; }
+        }
+        if (pend >= 0) { atomicAdd(&ins[(vbase + T.ap + i) * 4 + pend], 1); atomicAdd(&insn[vbase + T.ap + i], 1); }
+        for (int x = 0; x < n; x++) atomicAdd(&cov[vbase + T.ap + x], 1);
+    }
+}
+
+// thread per vote column (targets concatenated, L+1 columns each): how many symbols does it emit?
+__global__ void __launch_bounds__(256) k_cons_count(ConsGeom G, const int32_t *__restrict__ targets, int ntargets, int64_t ncols,
+                                                    const int32_t *__restrict__ cnt, const int32_t *__restrict__ ins,
+                                                    const int32_t *__restrict__ insn, const int32_t *__restrict__ cov,
+                                                    int32_t *__restrict__ nemit, uint8_t *__restrict__ sym /* 2 per column */) {
+    int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= ncols) return;
+    int lo = 0, hi = ntargets;                                // target of this column
+    while (hi - lo > 1) { int mid = (lo + hi) >> 1; if (G.vote_off[mid] <= c) lo = mid; else hi = mid; }
+    const int r = targets[lo];
+    const int p = (int)(c - G.vote_off[lo]);
+    const int L = G.len[r];
+    int ne = 0;
+    const int total = (p < L ? cov[c] : (L > 0 ? cov[c - 1] : 0)) + 1;
+    if (2 * insn[c] > total) {
+        int best = 0;
+        for (int s = 1; s < 4; s++) if (ins[c * 4 + s] > ins[c * 4 + best]) best = s;
+        sym[2 * c + ne++] = (uint8_t)best;
+    }
+    if (p < L) {
+        const int own = base_at(G.fwd, G.off[r] + p);
+        int bestsym = own, bestc = cnt[c * 5 + own] + 1;
+        for (int s = 0; s < 5; s++) { int v = cnt[c * 5 + s] + (s == own ? 1 : 0); if (v > bestc) { bestc = v; bestsym = s; } }
+        if (bestsym < 4) sym[2 * c + ne++] = (uint8_t)bestsym;
+    }
+    nemit[c] = ne;
+}
+
+__global__ void __launch_bounds__(256) k_cons_write(int64_t ncols, const int32_t *__restrict__ nemit, const int32_t *__restrict__ eoff,
+                                                    const uint8_t *__restrict__ sym, uint8_t *__restrict__ out) {
+    int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= ncols) return;
+    for (int e = 0; e < nemit[c]; e++) out[eoff[c] + e] = sym[2 * c + e];
+}
+
+}  // namespace
+
+void las_filter_device(const dn_las_record *rec, const int64_t *toff, int64_t n, int mode, double max_err, const int32_t *alen,
+                       const int32_t *blen, int allowance, dn_las_record *orec, int64_t *otoff, int64_t *n_out, cudaStream_t s) {
+    *n_out = 0;
+    if (n == 0) return;
+    DBuf<int32_t> keep(n), kidx(n), tot(1);
+    DN_LAUNCH(k_las_filter, (unsigned)((n + 255) / 256), 256, 0, s, rec, n, mode, max_err, alen, blen, allowance, keep.p);
+    exclusive_scan_i32(keep.p, kidx.p, n, tot.p, s);
+    DN_LAUNCH(k_las_compact, (unsigned)((n + 255) / 256), 256, 0, s, rec, toff, n, (const int32_t *)keep.p, (const int32_t *)kidx.p, orec, otoff);
+    int32_t h; DN_CUDA(cudaMemcpyAsync(&h, tot.p, 4, cudaMemcpyDeviceToHost, s)); DN_CUDA(cudaStreamSynchronize(s));
+    *n_out = h;
+}
+
+void qv_device(const int32_t *rlen, int nreads, const dn_las_record *rec, int64_t nla, const int64_t *toff, const uint16_t *trace,
+               int ts, int cov, const int64_t *qoff, uint8_t *qv, cudaStream_t s) {
+    if (nreads == 0) return;
+    DN_LAUNCH(k_qv, nreads, 128, 0, s, rlen, rec, nla, toff, trace, ts, cov, qoff, qv);
+}
+
+void launch_cons_tasks(const dn_las_record *rec, const int64_t *toff, const uint16_t *trace, const int32_t *vla, int nvla,
+                       const int64_t *task_off, int ts, ConsTask *tasks, cudaStream_t s) {
+    DN_LAUNCH(k_cons_tasks, (nvla + 255) / 256, 256, 0, s, rec, toff, trace, vla, nvla, task_off, ts, tasks);
+}
+int cons_vote_threads() { return sm_count() * 4 * 128; }
+void launch_cons_vote(const ConsTask *tasks, int64_t ntasks, const dn_las_record *rec, const int32_t *la_target, ConsGeom G,
+                      u32 *scratch, int32_t *cnt, int32_t *ins, int32_t *insn, int32_t *cov, cudaStream_t s) {
+    DN_LAUNCH(k_cons_vote, sm_count() * 4, 128, 0, s, tasks, ntasks, rec, la_target, G, scratch, cnt, ins, insn, cov);
+}
+void launch_cons_count(ConsGeom G, const int32_t *targets, int ntargets, int64_t ncols, const int32_t *cnt, const int32_t *ins,
+                       const int32_t *insn, const int32_t *cov, int32_t *nemit, uint8_t *sym, cudaStream_t s) {
+    DN_LAUNCH(k_cons_count, (unsigned)((ncols + 255) / 256), 256, 0, s, G, targets, ntargets, ncols, cnt, ins, insn, cov, nemit, sym);
+}
+void launch_cons_write(int64_t ncols, const int32_t *nemit, const int32_t *eoff, const uint8_t *sym, uint8_t *out, cudaStream_t s) {
+    DN_LAUNCH(k_cons_write, (unsigned)((ncols + 255) / 256), 256, 0, s, ncols, nemit, eoff, sym, out);
+}
+
+}  // namespace dn

@@ -172,3 +172,85 @@ def getDamapping(refDb, queryDb, opts=(), outdir="."):
     arr, n = _opts(list(opts))
     _lib.check(_lib.lib().dn_damap(refDb.encode(), queryDb.encode(), arr, n, outdir.encode()))
     return getLasFile(refDb, queryDb, outdir)
+
+
+# ---------------------------------------------------------------------------------------------
+# per-pile stages (processPileUps/package.d:474-619) on in-memory LAS buffers
+
+
+class Las:
+    """An in-memory LAS (owner of a dn_las_buf).  `rec`, `toff`, `trace` are zero-copy views."""
+
+    def __init__(self, buf):
+        self._buf = buf
+        self._owner = _LasOwner(buf)
+        self.stats = {n_: getattr(buf.stats, n_) for n_, _ in _lib.AlignStats._fields_}
+        self._refresh()
+
+    def _refresh(self):
+        b = self._buf
+        n = int(b.nrec)
+        self.rec = _wrap(b.rec, n * 40, _lib.REC_DTYPE, self._owner)
+        self.toff = _wrap(b.toff, n * 8, np.int64, self._owner)
+        self.trace = _wrap(b.trace, int(b.ntrace) * 2, np.uint16, self._owner)
+        self.tspace = int(b.tspace)
+
+    def __len__(self):
+        return int(self._buf.nrec)
+
+    def traces(self):
+        return [self.trace[o:o + t].reshape(-1, 2) for o, t in zip(self.toff, self.rec["tlen"])]
+
+    def filterLocalAlignments(self, max_err):
+        """dazzler.d:3885-3899 with pred = averageErrorRate <= max_err (package.d:483-485)."""
+        _lib.check(_lib.lib().dn_las_filter_error(C.byref(self._buf), C.c_double(max_err)))
+        self._refresh()
+        return self
+
+    def filterPileUpAlignments(self, alen, blen, allowance):
+        """dazzler.d:4043-4094 (forceFlat; records are already flat and sorted)."""
+        alen = np.ascontiguousarray(alen, np.int32); blen = np.ascontiguousarray(blen, np.int32)
+        _lib.check(_lib.lib().dn_las_filter_pileup(C.byref(self._buf), alen.ctypes.data_as(C.c_void_p), len(alen),
+                                                    blen.ctypes.data_as(C.c_void_p), len(blen), int(allowance)))
+        self._refresh()
+        return self
+
+    def write(self, path):
+        _lib.check(_lib.lib().dn_las_write(path.encode(), C.byref(self._buf)))
+
+
+def align(a, b, **params):
+    p = make_params(**params)
+    buf = _lib.LasBuf()
+    _lib.check(_lib.lib().dn_align_blocks(a._h, b._h, C.byref(p), C.byref(buf)))
+    return Las(buf)
+
+
+def computeQVs(rlen, las, coverage):
+    """dazzler.d:3782-3792: returns (qv bytes, qoff[nreads+1])."""
+    L = _lib.lib()
+    rlen = np.ascontiguousarray(rlen, np.int32)
+    qv = C.POINTER(C.c_uint8)(); qoff = C.POINTER(C.c_int64)()
+    _lib.check(L.dn_compute_qvs(rlen.ctypes.data_as(C.c_void_p), len(rlen), C.byref(las._buf), int(coverage),
+                                C.byref(qv), C.byref(qoff)))
+    o = np.ctypeslib.as_array(qoff, shape=(len(rlen) + 1,)).copy()
+    q = np.ctypeslib.as_array(qv, shape=(max(int(o[-1]), 1),))[:int(o[-1])].copy()
+    L.dn_free(qv); L.dn_free(qoff)
+    return q, o
+
+
+class _SeqBuf(C.Structure):
+    _fields_ = [("nseq", C.c_int32), ("off", C.POINTER(C.c_int64)), ("bases", C.POINTER(C.c_uint8))]
+
+
+def getConsensus(block, las, reads):
+    """dazzler.d:4213-4255 for each 0-based read id in `reads`; returns a list of base-code arrays."""
+    L = _lib.lib()
+    reads = np.ascontiguousarray(reads, np.int32)
+    out = _SeqBuf()
+    _lib.check(L.dn_consensus(block._h, C.byref(las._buf), reads.ctypes.data_as(C.c_void_p), len(reads), C.byref(out)))
+    off = np.ctypeslib.as_array(out.off, shape=(len(reads) + 1,)).copy()
+    tot = int(off[-1])
+    bases = np.ctypeslib.as_array(out.bases, shape=(max(tot, 1),))[:tot].copy()
+    L.dn_seq_free(C.byref(out))
+    return [bases[off[i]:off[i + 1]] for i in range(len(reads))]

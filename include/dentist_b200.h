@@ -137,6 +137,29 @@ int dn_align_host(const dn_block_desc *a, const dn_block_desc *b, const dn_align
 int dn_las_write(const char *path, const dn_las_buf *buf);
 int dn_las_read(const char *path, dn_las_buf *out);
 
+/* ---- per-pile stages of processPileUps (commands/processPileUps/package.d:474-619) -------------- */
+
+/* filterLocalAlignments!(la => la.averageErrorRate <= maxAlignmentError)  dazzler.d:3885-3899,
+ * package.d:483-485: keeps records with diffs/(aepos-abpos) <= max_err (fp64 compare). In place,
+ * order preserving; trace storage is left untouched (toff still points into it). */
+int dn_las_filter_error(dn_las_buf *las, double max_err);
+/* filterPileUpAlignments(..., Yes.forceFlat) / isValidPileUpAlignment  dazzler.d:4084-4141: keeps
+ * aread != bread and (left-anchored and right-proper) or (right-anchored and left-proper) within
+ * `allowance` (= trace spacing, commandline.d:2325-2332).  alen/blen = read lengths of the A/B DB. */
+int dn_las_filter_pileup(dn_las_buf *las, const int32_t *alen, int32_t na, const int32_t *blen, int32_t nb, int32_t allowance);
+/* computeQVs(db, las, coverage)  dazzler.d:3782-3792 (`DAScover`, `DASqv -c`) and
+ * computeIntrinsicQV  dazzler.d:4303-4308 (`computeintrinsicqv -d`): one QV byte in [0,50] per
+ * trace-spacing tile of every read; *qv has qoff[nreads] bytes, read r owns [qoff[r], qoff[r+1]).
+ * `las` must be sorted by A read.  Free both arrays with dn_free. */
+int dn_compute_qvs(const int32_t *rlen, int32_t nreads, const dn_las_buf *las, int32_t coverage, uint8_t **qv, int64_t **qoff);
+void dn_free(void *p);
+/* getConsensus(db, las, readId, opts)  dazzler.d:4213-4255 (`daccord -f -I<i>,<i>`): full-length
+ * consensus of each listed read (0-based) over the local alignments in `las` that have it as A read.
+ * Several reads = several piles in one launch.  Sequences come back as base codes 0..3. */
+typedef struct dn_seq_buf { int32_t nseq; int64_t *off; uint8_t *bases; } dn_seq_buf;
+int dn_consensus(const dn_block *db, const dn_las_buf *las, const int32_t *reads, int32_t nreads, dn_seq_buf *out);
+void dn_seq_free(dn_seq_buf *buf);
+
 /* ---- file-level drop-ins for dazzler.d ---------------------------------------------------- */
 
 /* getDalignment(dbA[, dbB], opts, outdir)  dazzler.d:3829-3844 / dalign() :6131-6140.

@@ -88,3 +88,60 @@ def align(a_off, a_bases, b_off, b_bases, a_mask=None, b_mask=None, **params):
     lib().orc_free(C.byref(R))
     del ka, kb
     return la, tr, stats
+
+
+# ---------------------------------------------------------------------------------------------
+# per-pile stages (oracle/pile_oracle.c)
+
+LAS40 = np.dtype([("tlen", "<i4"), ("diffs", "<i4"), ("abpos", "<i4"), ("bbpos", "<i4"), ("aepos", "<i4"),
+                  ("bepos", "<i4"), ("flags", "<u4"), ("aread", "<i4"), ("bread", "<i4"), ("pad", "<i4")])
+
+
+def _las40(rec):
+    out = np.zeros(len(rec), LAS40)
+    for f in ("tlen", "diffs", "abpos", "bbpos", "aepos", "bepos", "flags", "aread", "bread"):
+        out[f] = rec[f]
+    return out
+
+
+def _p(a):
+    return a.ctypes.data_as(C.c_void_p)
+
+
+def filter_error(rec, max_err):
+    r = _las40(rec); keep = np.zeros(len(r), np.uint8)
+    f = lib().orc_filter_error; f.argtypes = [C.c_void_p, C.c_int64, C.c_double, C.c_void_p]
+    f(_p(r), len(r), float(max_err), _p(keep))
+    return keep.astype(bool)
+
+
+def filter_pileup(rec, alen, blen, allowance):
+    r = _las40(rec); keep = np.zeros(len(r), np.uint8)
+    alen = np.ascontiguousarray(alen, np.int32); blen = np.ascontiguousarray(blen, np.int32)
+    f = lib().orc_filter_pileup; f.argtypes = [C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p]
+    f(_p(r), len(r), _p(alen), _p(blen), int(allowance), _p(keep))
+    return keep.astype(bool)
+
+
+def qv(rlen, rec, toff, trace, tspace, cov):
+    """rec sorted by aread.  Returns (qv bytes, qv_off[nreads+1])."""
+    rlen = np.ascontiguousarray(rlen, np.int32)
+    r = _las40(rec); toff = np.ascontiguousarray(toff, np.int64); trace = np.ascontiguousarray(trace, np.uint16)
+    nt = (rlen.astype(np.int64) + tspace - 1) // tspace
+    qoff = np.zeros(len(rlen) + 1, np.int64); qoff[1:] = np.cumsum(nt)
+    out = np.zeros(int(qoff[-1]), np.uint8)
+    f = lib().orc_qv
+    f.argtypes = [C.c_void_p, C.c_int32, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p]
+    f(_p(rlen), len(rlen), _p(r), len(r), _p(toff), _p(trace), int(tspace), int(cov), _p(qoff), _p(out))
+    return out, qoff
+
+
+def consensus(off, bases, rec, toff, trace, tspace, read):
+    off = np.ascontiguousarray(off, np.int64); bases = np.ascontiguousarray(bases, np.uint8)
+    r = _las40(rec); toff = np.ascontiguousarray(toff, np.int64); trace = np.ascontiguousarray(trace, np.uint16)
+    L = int(off[read + 1] - off[read])
+    out = np.zeros(2 * L + 16, np.uint8); n = C.c_int32(0)
+    f = lib().orc_consensus
+    f.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_void_p, C.POINTER(C.c_int32)]
+    f(_p(off), _p(bases), _p(r), len(r), _p(toff), _p(trace), int(tspace), int(read), _p(out), C.byref(n))
+    return out[:n.value].copy()

@@ -1,0 +1,184 @@
+/*
+ * pile_oracle.c -- CPU ORACLE (test infrastructure, NOT product code) for the per-pile-up stages of
+ * processPileUps (commands/processPileUps/package.d:474-619):
+ *
+ *   orc_filter_error     filterLocalAlignments!(la => la.averageErrorRate <= maxAlignmentError)
+ *                        dazzler.d:3885-3899, call package.d:483-485, rate base.d:1764-1767
+ *   orc_filter_pileup    filterPileUpAlignments / isValidPileUpAlignment  dazzler.d:4084-4141
+ *                        (FlatLocus.beginsWithin / endsWithin base.d:1713-1724)
+ *   orc_qv               computeQVs -> `DAScover`, `DASqv -c<cov>`  dazzler.d:3782-3792, 6142-6156
+ *                        and `computeintrinsicqv -d<depth>` dazzler.d:6172-6183 (same rule, other track)
+ *   orc_consensus        getConsensus -> `daccord -f -I<i>,<i>`  dazzler.d:4213-4255, 6187-6220
+ *
+ * PARITY STATUS.  The two filters restate D source that IS in /root/reference and are exact.
+ * orc_qv and orc_consensus are "parity unpinned": DASCRUBBER @ a53dbe87 and daccord 0.0.18 are absent
+ * (no source, no binaries), and the reference holds no QV vectors.  They follow north_star's definition
+ * ("per-gap pile-up consensus as a ... majority/intrinsic-QV vote over the aligned read pile") and the
+ * DASqv rule recorded in SURVEY Appendix A.2; the one reference vector that exists for this stage, the
+ * consensus KAT dazzler.d:4257-4299 (3 reads, two single-base errors => consensus == read 3), is
+ * reproduced in tests/test_pile_oracle.py.
+ *
+ * Specification
+ *  QV: for read a and tile t (A bases [t*ts, min((t+1)*ts, len))) every LA with aread == a whose trace
+ *      has a FULL tile t (tile lies inside [abpos, aepos]) contributes
+ *      v = min(50, (200*diffs + (alen+bb)/2) / (alen+bb)), alen = tile length, bb = its B bases.
+ *      m = #contributions; if m*4 < cov the tile is uncovered: QV = 50.  Otherwise sort ascending and
+ *      QV = round-half-up mean of the first n = clamp(cov/2, 1, m) values.
+ *  Consensus of read r: every LA with aread == r votes.  Per tile, the A tile and the B tile are aligned
+ *      globally with unit costs; traceback from the end prefers diagonal, then "A base unmatched"
+ *      (deletion in B), then "B base inserted".  Each aligned column adds a vote {a,c,g,t} or {deleted}
+ *      to its A position; the first base of an insertion run between A positions p-1 and p votes for an
+ *      insertion in front of p.  Tiles with more than 250 B bases do not vote.  Read r itself votes its own
+ *      base once.  Position p emits the winning symbol (ties: r's own base first, then lowest code;
+ *      a winning "deleted" emits nothing); an insertion in front of p is emitted when more than half of
+ *      (covering LAs + 1) vote for one.  Uncovered positions keep r's base (daccord -f).
+ */
+#include <stdint.h>
+#include <stdlib.h>
+#include <string.h>
+
+typedef struct {
+    int32_t tlen, diffs, abpos, bbpos, aepos, bepos;
+    uint32_t flags;
+    int32_t aread, bread;
+    int32_t pad;
+} las_rec;                                  /* the 40-byte LAS record */
+
+void orc_filter_error(const las_rec *la, int64_t n, double max_err, uint8_t *keep) {
+    for (int64_t i = 0; i < n; i++) {
+        double rate = (double)la[i].diffs / (double)(la[i].aepos - la[i].abpos);
+        keep[i] = rate <= max_err;
+    }
+}
+
+void orc_filter_pileup(const las_rec *la, int64_t n, const int32_t *alen, const int32_t *blen, int32_t allowance, uint8_t *keep) {
+    for (int64_t i = 0; i < n; i++) {
+        const las_rec *x = &la[i];
+        int la_ = alen[x->aread], lb_ = blen[x->bread];
+        int ab = x->abpos <= allowance, bb = x->bbpos <= allowance;
+        int ae = x->aepos + allowance >= la_, be = x->bepos + allowance >= lb_;
+        int left_anch = ab && bb, left_prop = ab || bb, right_anch = ae && be, right_prop = ae || be;
+        keep[i] = x->aread != x->bread && ((left_anch && right_prop) || (right_anch && left_prop));
+    }
+}
+
+static int cmp_int(const void *a, const void *b) { return *(const int *)a - *(const int *)b; }
+
+/* qv_off[r] = first tile byte of read r (prefix sum of ceil(len/ts)); la sorted by aread */
+void orc_qv(const int32_t *rlen, int32_t nreads, const las_rec *la, int64_t nla, const int64_t *toff,
+            const uint16_t *trace, int32_t ts, int32_t cov, const int64_t *qv_off, uint8_t *qv)
+{
+    int *vals = malloc(sizeof(int) * (nla + 1));
+    int64_t lo = 0;
+    for (int r = 0; r < nreads; r++) {
+        while (lo < nla && la[lo].aread < r) lo++;
+        int64_t hi = lo;
+        while (hi < nla && la[hi].aread == r) hi++;
+        int nt = (rlen[r] + ts - 1) / ts;
+        for (int t = 0; t < nt; t++) {
+            int t0 = t * ts, t1 = (t + 1) * ts < rlen[r] ? (t + 1) * ts : rlen[r];
+            int m = 0;
+            for (int64_t x = lo; x < hi; x++) {
+                if (la[x].abpos > t0 || la[x].aepos < t1) continue;
+                int idx = t - la[x].abpos / ts;
+                const uint16_t *tp = trace + toff[x] + 2 * idx;
+                int alen = t1 - t0, den = alen + tp[1];
+                int v = (200 * tp[0] + den / 2) / den;
+                vals[m++] = v > 50 ? 50 : v;
+            }
+            int q = 50;
+            if (m * 4 >= cov && m > 0) {
+                qsort(vals, m, sizeof(int), cmp_int);
+                int n = cov / 2; if (n < 1) n = 1; if (n > m) n = m;
+                int s = 0; for (int i = 0; i < n; i++) s += vals[i];
+                q = (2 * s + n) / (2 * n);
+                if (q > 50) q = 50;
+            }
+            qv[qv_off[r] + t] = (uint8_t)q;
+        }
+        lo = hi;
+    }
+    free(vals);
+}
+
+/* votes: cnt[p*5 + sym] (sym 0..3 base, 4 deleted), ins[p*4 + base], insn[p], cov[p] */
+static void vote_tile(const uint8_t *a, int n, const uint8_t *b, int m, int p0,
+                      int32_t *cnt, int32_t *ins, int32_t *insn, int32_t *cov)
+{
+    if (m > 250) return;
+    static uint8_t D[128 + 1][256];
+    for (int j = 0; j <= m; j++) D[0][j] = (uint8_t)j;
+    for (int i = 1; i <= n; i++) {
+        D[i][0] = (uint8_t)i;
+        for (int j = 1; j <= m; j++) {
+            int d = D[i - 1][j - 1] + (a[i - 1] != b[j - 1]);
+            int u = D[i - 1][j] + 1, l = D[i][j - 1] + 1;
+            int v = d; if (u < v) v = u; if (l < v) v = l;
+            D[i][j] = (uint8_t)v;
+        }
+    }
+    int i = n, j = m;
+    int pend = -1;                              /* first base (lowest j) of the insertion run being walked */
+    while (i > 0 || j > 0) {
+        if (i > 0 && j > 0 && D[i][j] == D[i - 1][j - 1] + (a[i - 1] != b[j - 1])) {
+            if (pend >= 0) { ins[(p0 + i) * 4 + pend]++; insn[p0 + i]++; pend = -1; }
+            cnt[(p0 + i - 1) * 5 + b[j - 1]]++; i--; j--;
+        } else if (i > 0 && D[i][j] == D[i - 1][j] + 1) {
+            if (pend >= 0) { ins[(p0 + i) * 4 + pend]++; insn[p0 + i]++; pend = -1; }
+            cnt[(p0 + i - 1) * 5 + 4]++; i--;
+        } else {
+            pend = b[j - 1]; j--;               /* b[j-1] is inserted in front of A position p0+i */
+        }
+    }
+    if (pend >= 0) { ins[(p0 + i) * 4 + pend]++; insn[p0 + i]++; }
+    for (int x = 0; x < n; x++) cov[p0 + x]++;
+}
+
+/* bases/off: the DB block (codes 0..3); returns consensus length in *outlen (out must hold 2*len+16) */
+int orc_consensus(const int64_t *off, const uint8_t *bases, const las_rec *la, int64_t nla, const int64_t *toff,
+                  const uint16_t *trace, int32_t ts, int32_t r, uint8_t *out, int32_t *outlen)
+{
+    const int L = (int)(off[r + 1] - off[r]);
+    const uint8_t *A = bases + off[r];
+    int32_t *cnt = calloc((size_t)(L + 1) * 5, 4), *ins = calloc((size_t)(L + 2) * 4, 4);
+    int32_t *insn = calloc(L + 2, 4), *cov = calloc(L + 2, 4);
+    uint8_t *brc = NULL; int brc_cap = 0;
+    for (int64_t x = 0; x < nla; x++) {
+        if (la[x].aread != r) continue;
+        const int b = la[x].bread, LB = (int)(off[b + 1] - off[b]);
+        const uint8_t *B = bases + off[b];
+        if (la[x].flags & 1u) {
+            if (LB > brc_cap) { brc = realloc(brc, LB + 1); brc_cap = LB; }
+            for (int i = 0; i < LB; i++) brc[i] = 3 - B[LB - 1 - i];
+            B = brc;
+        }
+        int ap = la[x].abpos, bp = la[x].bbpos, nt = la[x].tlen / 2;
+        for (int t = 0; t < nt; t++) {
+            int aend = (t == nt - 1) ? la[x].aepos : (ap / ts + 1) * ts;
+            int bb = trace[toff[x] + 2 * t + 1];
+            vote_tile(A + ap, aend - ap, B + bp, bb, ap, cnt, ins, insn, cov);
+            ap = aend; bp += bb;
+        }
+    }
+    int o = 0;
+    for (int p = 0; p <= L; p++) {
+        /* insertion in front of p (p == L: after the last base) */
+        int total = (p < L ? cov[p] : (L > 0 ? cov[L - 1] : 0)) + 1;
+        if (2 * insn[p] > total) {
+            int best = 0;
+            for (int s = 1; s < 4; s++) if (ins[p * 4 + s] > ins[p * 4 + best]) best = s;
+            out[o++] = (uint8_t)best;
+        }
+        if (p == L) break;
+        int own = A[p];
+        int bestsym = own, bestc = cnt[p * 5 + own] + 1;
+        for (int s = 0; s < 5; s++) {
+            int c = cnt[p * 5 + s] + (s == own ? 1 : 0);
+            if (c > bestc) { bestc = c; bestsym = s; }
+        }
+        if (bestsym < 4) out[o++] = (uint8_t)bestsym;
+    }
+    *outlen = o;
+    free(cnt); free(ins); free(insn); free(cov); free(brc);
+    return 0;
+}

@@ -52,6 +52,12 @@ def main():
     kat = dict(tspace=100, abpos=int(loci[0][0]), aepos=int(loci[0][1]), bbpos=int(loci[1][0]), bepos=int(loci[1][1]),
                diffs=292, trace=tps, asserts=asserts, throws=[578, 2585],
                equal_pairs=[[700, "ceil", 700, "floor"], [699, "ceil", 701, "floor"]])
+    # consensus KAT dazzler.d:4257-4299: three 1050-bp reads, reads 1 and 2 carry one substitution each
+    # (capital letter), `daligner -l15` + filterPileUpAlignments(allowance 100) + daccord => consensus == read 3
+    fa = [m.group(1) for ln in lines(dz, 4262, 4266) for m in [re.search(r'"(>.*)"', ln)] if m]
+    cons = dict(reads=["".join(r.split("\\n")[1:]) for r in fa], minlen=15, allowance=100, expected_read=2)
+    with open(os.path.join(HERE, "consensus_kat.json"), "w") as f:
+        json.dump(cons, f, indent=1)
     out = dict(source="a-ludi/dentist @ 1aa60e04", tspace=100, ladump=dump, flat=flat, chains=chains, trace_kat=kat)
     with open(os.path.join(HERE, "las_golden.json"), "w") as f:
         json.dump(out, f, indent=1)

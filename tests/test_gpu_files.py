@@ -71,7 +71,7 @@ def test_getDalignment_pile_with_dust_mask(tmp_path):
 
 def test_errors_are_reported_not_swallowed(tmp_path):
     from dentist_b200 import dazzler
-    with pytest.raises(dazzler.DnError, match="cannot find DB stub"):
+    with pytest.raises(dazzler.DnError, match="cannot (find|open)"):
         dazzler.getDalignment(str(tmp_path / "nope.db"), None, ["-s126"], str(tmp_path))
     ref, reads = _case(71)
     dbutil.write_db(str(tmp_path / "r.db"), reads)

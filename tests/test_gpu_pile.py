@@ -1,0 +1,85 @@
+"""GPU parity of the per-pile stages (filters, intrinsic QVs, consensus) against oracle/pile_oracle.c,
+including the reference's own consensus KAT (dazzler.d:4257-4299)."""
+import numpy as np
+import pytest
+
+from dentist_b200 import synth
+from tests.test_pile_oracle import kat_block
+
+pytestmark = pytest.mark.gpu
+
+
+def _pile(seed, cov=10, glen=20000, rl=6000, err=0.13):
+    sc = synth.make_scaffolds(1, glen, seed, n_repeats=0)
+    reads, _ = synth.simulate_reads(sc, cov, rl, rl // 4, err, seed + 1)
+    return reads
+
+
+def _gpu_las(blk, tspace, minlen):
+    from dentist_b200 import dazzler
+    g = dazzler.Block(blk.off, blk.bases)
+    return g, dazzler.align(g, g, tspace=tspace, minlen=minlen, self_block=1)
+
+
+def test_filters_match_oracle_and_reference_definition():
+    from oracle import oracle
+    blk = _pile(81)
+    g, las = _gpu_las(blk, 126, 500)
+    lens = np.diff(blk.off)
+    rec0 = las.rec.copy(); toff0 = las.toff.copy()
+    ke = oracle.filter_error(rec0, 0.22)
+    assert 0 < ke.sum() < len(rec0)
+    las.filterLocalAlignments(0.22)
+    assert np.array_equal(las.rec, rec0[ke]) and np.array_equal(las.toff, toff0[ke])
+    rec1 = las.rec.copy()
+    kp = oracle.filter_pileup(rec1, lens, lens, 126)
+    assert 0 < kp.sum() < len(rec1)
+    las.filterPileUpAlignments(lens, lens, 126)
+    assert np.array_equal(las.rec, rec1[kp])
+    # traces still reachable through toff
+    for r, t in zip(las.rec[:20], las.traces()[:20]):
+        assert int(t[:, 0].sum()) == r["diffs"]
+
+
+def test_qvs_match_oracle():
+    from dentist_b200 import dazzler
+    from oracle import oracle
+    blk = _pile(91, cov=14)
+    g, las = _gpu_las(blk, 126, 500)
+    lens = np.diff(blk.off)
+    las.filterLocalAlignments(0.3)
+    for cov in (4, blk.nreads):
+        q, qoff = dazzler.computeQVs(lens, las, cov)
+        oq, ooff = oracle.qv(lens, las.rec, las.toff, las.trace, 126, cov)
+        assert np.array_equal(qoff, ooff) and np.array_equal(q, oq)
+        assert q.min() < 30 and q.max() == 50
+
+
+def test_reference_consensus_kat_on_gpu():
+    from dentist_b200 import dazzler
+    k, blk = kat_block()
+    g, las = _gpu_las(blk, 100, k["minlen"])
+    lens = np.diff(blk.off)
+    las.filterPileUpAlignments(lens, lens, k["allowance"])
+    assert len(las) == 6
+    cons = dazzler.getConsensus(g, las, [0, 1, 2])
+    for c in cons:
+        assert np.array_equal(c, blk.read(k["expected_read"]))
+
+
+def test_consensus_matches_oracle_on_noisy_piles():
+    from dentist_b200 import dazzler
+    from oracle import oracle
+    blk = _pile(95, cov=12, glen=15000, rl=7000)
+    g, las = _gpu_las(blk, 126, 500)
+    lens = np.diff(blk.off)
+    las.filterLocalAlignments(0.3).filterPileUpAlignments(lens, lens, 126)
+    targets = [0, 3, blk.nreads - 1, 5]
+    cons = dazzler.getConsensus(g, las, targets)
+    for r, c in zip(targets, cons):
+        oc = oracle.consensus(blk.off, blk.bases, las.rec, las.toff, las.trace, 126, r)
+        assert np.array_equal(c, oc), r
+        assert abs(len(c) - lens[r]) < 0.1 * lens[r]
+    # a read without any alignment keeps its own sequence (daccord -f)
+    empty = dazzler.getConsensus(g, dazzler.align(g, g, tspace=126, minlen=10 ** 6, self_block=1), [2])
+    assert np.array_equal(empty[0], blk.read(2))
