@@ -71,6 +71,11 @@ int dn_las_filter_pileup(dn_las_buf *las, const int32_t *alen, int32_t na, const
 }
 
 int dn_compute_qvs(const int32_t *rlen, int32_t nreads, const dn_las_buf *las, int32_t coverage, uint8_t **qv, int64_t **qoff) {
+    return dn_compute_qvs_v(rlen, nreads, las, coverage, nullptr, qv, qoff);
+}
+
+int dn_compute_qvs_v(const int32_t *rlen, int32_t nreads, const dn_las_buf *las, int32_t coverage, const int32_t *cov_per_read,
+                     uint8_t **qv, int64_t **qoff) {
     if (!rlen || !las || !qv || !qoff || nreads < 0) return fail(DN_ERR_INVALID, "null argument");
     if (las->tspace < 1) return fail(DN_ERR_INVALID, "bad trace spacing");
     for (int64_t i = 0; i < las->nrec; i++) {
@@ -89,7 +94,8 @@ int dn_compute_qvs(const int32_t *rlen, int32_t nreads, const dn_las_buf *las, i
         DBuf<int32_t> dl; to_device(dl, rlen, nreads, g_stream);
         DBuf<int64_t> dq; to_device(dq, (const int64_t *)ho, nreads + 1, g_stream);
         DBuf<uint8_t> q(ho[nreads] + 1);
-        qv_device(dl.p, nreads, d.rec.p, las->nrec, d.toff.p, d.trace.p, ts, coverage, dq.p, q.p, g_stream);
+        DBuf<int32_t> dcv; if (cov_per_read) to_device(dcv, cov_per_read, nreads, g_stream);
+        qv_device(dl.p, nreads, d.rec.p, las->nrec, d.toff.p, d.trace.p, ts, coverage, cov_per_read ? dcv.p : nullptr, dq.p, q.p, g_stream);
         if (ho[nreads]) DN_CUDA(cudaMemcpyAsync(hq, q.p, ho[nreads], cudaMemcpyDeviceToHost, g_stream));
         DN_CUDA(cudaStreamSynchronize(g_stream));
         *qv = hq; *qoff = ho;

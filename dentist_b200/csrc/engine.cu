@@ -110,7 +110,9 @@ void align_blocks(const DevBlock &A, const DevBlock &B, const AlignParams &P, Ho
     if (keybits > 62) throw Error("hit key does not fit 62 bits");
     DBuf<int64_t> d_dbase(A.nreads + 1);
     DN_CUDA(cudaMemcpyAsync(d_dbase.p, dbase.data(), sizeof(int64_t) * (A.nreads + 1), cudaMemcpyHostToDevice, s));
-    JoinGeom JG{A.chunk2read.p, A.off.p, d_dbase.p, B.chunk2read.p, B.off.p, nB, maxlb, gdbits, keybits, P.self};
+    const bool grouped = A.has_group && B.has_group;
+    JoinGeom JG{A.chunk2read.p, A.off.p, d_dbase.p, B.chunk2read.p, B.off.p, nB, maxlb, gdbits, keybits, P.self,
+                grouped ? A.group.p : nullptr, grouped ? B.group.p : nullptr};
     SeedGeom SG{d_dbase.p, A.nreads, gdbits};
 
     // ---- K3: join ------------------------------------------------------------------------------

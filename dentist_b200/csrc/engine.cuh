@@ -27,6 +27,8 @@ struct DevBlock {
     DBuf<int32_t> chunk2read;
     DBuf<u32> mask, mask_rc;
     bool has_mask = false;
+    DBuf<int32_t> group;          // optional pile id per read
+    bool has_group = false;
 };
 
 struct AlignParams {

@@ -43,9 +43,11 @@ __global__ void __launch_bounds__(256) k_las_compact(const dn_las_record *__rest
 
 // one CTA per read; records sorted by aread
 __global__ void __launch_bounds__(128) k_qv(const int32_t *__restrict__ rlen, const dn_las_record *__restrict__ rec, int64_t nla,
-                                            const int64_t *__restrict__ toff, const uint16_t *__restrict__ trace, int ts, int cov,
+                                            const int64_t *__restrict__ toff, const uint16_t *__restrict__ trace, int ts, int cov_all,
+                                            const int32_t *__restrict__ cov_per_read,
                                             const int64_t *__restrict__ qoff, uint8_t *__restrict__ qv) {
     const int r = blockIdx.x;
+    const int cov = cov_per_read ? cov_per_read[r] : cov_all;
     __shared__ int64_t s_lo, s_hi;
     if (threadIdx.x == 0) {
         int64_t a = 0, b = nla;
@@ -208,9 +210,9 @@ void las_filter_device(const dn_las_record *rec, const int64_t *toff, int64_t n,
 }
 
 void qv_device(const int32_t *rlen, int nreads, const dn_las_record *rec, int64_t nla, const int64_t *toff, const uint16_t *trace,
-               int ts, int cov, const int64_t *qoff, uint8_t *qv, cudaStream_t s) {
+               int ts, int cov, const int32_t *cov_per_read, const int64_t *qoff, uint8_t *qv, cudaStream_t s) {
     if (nreads == 0) return;
-    DN_LAUNCH(k_qv, nreads, 128, 0, s, rlen, rec, nla, toff, trace, ts, cov, qoff, qv);
+    DN_LAUNCH(k_qv, nreads, 128, 0, s, rlen, rec, nla, toff, trace, ts, cov, cov_per_read, qoff, qv);
 }
 
 void launch_cons_tasks(const dn_las_record *rec, const int64_t *toff, const uint16_t *trace, const int32_t *vla, int nvla,

@@ -95,6 +95,11 @@ void block_upload(const dn_block_desc &d, DevBlock &B, cudaStream_t s) {
     DN_LAUNCH(k_pack, d.nreads, 128, 0, s, (const uint8_t *)raw.p, (const int64_t *)boff.p, (const int32_t *)B.len.p,
               (const int64_t *)B.off.p, d.format, B.fwd.p, B.rc.p);
     DN_LAUNCH(k_chunk2read, (d.nreads + 255) / 256, 256, 0, s, (const int64_t *)B.off.p, d.nreads, B.chunk2read.p);
+    B.has_group = d.group != nullptr;
+    if (d.group) {
+        B.group.persistent(d.nreads);
+        DN_CUDA(cudaMemcpyAsync(B.group.p, d.group, sizeof(int32_t) * d.nreads, cudaMemcpyHostToDevice, s));
+    }
     B.has_mask = false;
     if (d.mask_anno && d.mask_data) {
         int64_t nbytes = d.mask_anno[d.nreads];
@@ -229,7 +234,7 @@ __global__ void __launch_bounds__(256) k_join_emit(const u64 *__restrict__ ta, c
         int ar = read_of(G.a_c2r, G.a_off, ga);
         int apos = (int)(ga - G.a_off[ar]);
         u64 key;
-        if (G.self && ar == br) { key = 1ull << G.keybits; ninv++; }
+        if ((G.self && ar == br) || (G.a_group && G.a_group[ar] != G.b_group[br])) { key = 1ull << G.keybits; ninv++; }
         else { u64 gd = (u64)(G.a_dbase[ar] + apos - bpos + G.maxlb); key = (bs << G.gdbits) | gd; }
         hits[o + x] = make_ulonglong2(key, (u64)(u32)apos | ((u64)(u32)bpos << 32));
     }
@@ -309,7 +314,7 @@ __global__ void __launch_bounds__(256) k_lookup_emit(const u32 *__restrict__ seq
             int ar = read_of(G.a_c2r, G.a_off, ga);
             int apos = (int)(ga - G.a_off[ar]);
             u64 key;
-            if (G.self && ar == w.r) { key = 1ull << G.keybits; ninv++; }
+            if ((G.self && ar == w.r) || (G.a_group && G.a_group[ar] != G.b_group[w.r])) { key = 1ull << G.keybits; ninv++; }
             else { u64 gd = (u64)(G.a_dbase[ar] + apos - bpos + G.maxlb); key = (bs << G.gdbits) | gd; }
             hits[o++] = make_ulonglong2(key, (u64)(u32)apos | ((u64)(u32)bpos << 32));
         }

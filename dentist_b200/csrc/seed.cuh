@@ -13,6 +13,7 @@ struct JoinGeom {
     int64_t nbp;          // padded bases of B: payloads >= nbp are the complement strand
     int64_t maxlb;        // max B read length rounded up to the band width
     int gdbits, keybits, self;
+    const int32_t *a_group, *b_group;   // optional: pairs with different group ids are dropped
 };
 struct SeedGeom { const int64_t *a_dbase; int na; int gdbits; };
 

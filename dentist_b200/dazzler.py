@@ -28,7 +28,7 @@ def launch_count():
 class Block:
     """A sequence block resident in HBM (2-bit packed, both strands)."""
 
-    def __init__(self, off, bases=None, bps=None, boff=None, mask=None):
+    def __init__(self, off, bases=None, bps=None, boff=None, mask=None, group=None):
         """Either `bases` (uint8 codes 0..3 concatenated, read r = bases[off[r]:off[r+1]]) or
         DAZZ_DB `.bps` bytes with per-read byte offsets `boff` and lengths diff(off)."""
         off = np.ascontiguousarray(off, dtype=np.int64)
@@ -61,6 +61,11 @@ class Block:
             keep += [anno, md]
             d.mask_anno = anno.ctypes.data
             d.mask_data = md.ctypes.data
+        if group is not None:  # pile id per read: only reads of the same pile are compared
+            grp = np.ascontiguousarray(group, dtype=np.int32)
+            assert len(grp) == len(rlen)
+            keep.append(grp)
+            d.group = grp.ctypes.data
         self._desc, self._keep = d, keep
         self._h = C.c_void_p()
         _lib.check(_lib.lib().dn_block_upload(C.byref(d), C.byref(self._h)))
@@ -231,8 +236,14 @@ def computeQVs(rlen, las, coverage):
     L = _lib.lib()
     rlen = np.ascontiguousarray(rlen, np.int32)
     qv = C.POINTER(C.c_uint8)(); qoff = C.POINTER(C.c_int64)()
-    _lib.check(L.dn_compute_qvs(rlen.ctypes.data_as(C.c_void_p), len(rlen), C.byref(las._buf), int(coverage),
-                                C.byref(qv), C.byref(qoff)))
+    if np.ndim(coverage) == 0:
+        _lib.check(L.dn_compute_qvs(rlen.ctypes.data_as(C.c_void_p), len(rlen), C.byref(las._buf), int(coverage),
+                                    C.byref(qv), C.byref(qoff)))
+    else:   # one coverage per read (batched pile-ups)
+        cv = np.ascontiguousarray(coverage, np.int32)
+        assert len(cv) == len(rlen)
+        _lib.check(L.dn_compute_qvs_v(rlen.ctypes.data_as(C.c_void_p), len(rlen), C.byref(las._buf), 0,
+                                      cv.ctypes.data_as(C.c_void_p), C.byref(qv), C.byref(qoff)))
     o = np.ctypeslib.as_array(qoff, shape=(len(rlen) + 1,)).copy()
     q = np.ctypeslib.as_array(qv, shape=(max(int(o[-1]), 1),))[:int(o[-1])].copy()
     L.dn_free(qv); L.dn_free(qoff)

@@ -1,0 +1,71 @@
+"""Host-side mirror of `PileUpProcessor.processPileUp` (commands/processPileUps/package.d:283-374) for a
+whole BATCH of pile-ups at once: the reference runs the steps below per pile-up, forking a tool at
+each one (>= 12 fork/execs per pile-up); here every step is one call on a block that
+holds the cropped reads of all pile-ups (pile id per read = `group`).
+
+  computeQVs                   package.d:474-516   A1 + A5 + A9 + A13
+  findReferenceReadCandidates  package.d:518-568   A10 (host logic, mirrored here in numpy)
+  computeConsensus             package.d:600-619   A11
+  alignConsensusToFlankingContigs  package.d:621-697   A12
+(chainLocalAlignments, package.d:492, is not built yet -- DESIGN.md §7.)
+"""
+import numpy as np
+
+from . import dazzler
+
+MAX_QV = 50            # DbRecord.maxQV, dazzler.d:2873
+MIN_QV_COVERAGE = 4    # dazzler.d:3771
+BAD_FRACTION = 0.08    # commandline.d:1101
+TSPACE = 126           # forceLargeTracePointType, dazzler.d:154
+MIN_ANCHOR = 500       # commandline.d:2036, 2894
+
+
+def find_reference_read_candidates(qv, qoff, reads):
+    """package.d:518-568 for one pile: reads ranked by (numBadQVs, meanQV, readId); returns read ids."""
+    hist = np.zeros(MAX_QV, np.int64)
+    per = [qv[qoff[r]:qoff[r + 1]] for r in reads]
+    for q in per:
+        hist += np.bincount(q[q < MAX_QV], minlength=MAX_QV)[:MAX_QV]
+    bad_thres = int(BAD_FRACTION * int(hist.sum()))
+    cum = np.cumsum(hist[::-1])
+    idx = int(np.argmax(cum >= bad_thres)) if (cum >= bad_thres).any() else -1
+    bad_qv = MAX_QV - 1 - idx
+    scored = sorted((int((q >= bad_qv).sum()), float(q.mean()) if len(q) else 0.0, int(r)) for q, r in zip(per, reads))
+    return [r for _, _, r in scored]
+
+
+def process_pileups(reads, group, max_alignment_error=0.3, flanks=None):
+    """reads: synth.Block-like (off, bases) of all cropped reads; group: pile id per read.
+    Returns dict(consensus=[codes per pile], reference_read=[read id per pile], las=Las, flank_las=Las|None)."""
+    group = np.ascontiguousarray(group, np.int32)
+    lens = np.diff(reads.off).astype(np.int32)
+    npiles = int(group.max()) + 1 if len(group) else 0
+    g = dazzler.Block(reads.off, reads.bases, group=group)
+    # daligner -T<n> -B -s126 -l500 -e0.7 -mdust X X   (pileUpAlignmentOptions, commandline.d:2886-2902)
+    las = dazzler.align(g, g, tspace=TSPACE, minlen=MIN_ANCHOR, e=0.7, self_block=1)
+    las.filterLocalAlignments(max_alignment_error)                      # package.d:483-485
+    if len(las) == 0:
+        raise dazzler.DnError("empty pileup alignment")                  # package.d:487-490
+    # coverage = |allowedReferenceReadIds| (all reads of the pile here), raised to 4 for piles of >= 4 reads
+    psize = np.bincount(group, minlength=npiles)
+    cov_pile = np.where((psize < MIN_QV_COVERAGE), psize, np.maximum(psize, MIN_QV_COVERAGE))
+    qv, qoff = dazzler.computeQVs(lens, las, cov_pile[group])            # package.d:498-503
+    las.filterPileUpAlignments(lens, lens, TSPACE)                       # package.d:505-510
+    if len(las) == 0:
+        raise dazzler.DnError("empty pileup alignment after filtering")
+    order = np.argsort(group, kind="stable")
+    bounds = np.searchsorted(group[order], np.arange(npiles + 1))
+    ref_reads = []
+    for p in range(npiles):
+        members = order[bounds[p]:bounds[p + 1]]
+        ref_reads.append(find_reference_read_candidates(qv, qoff, members)[0])
+    cons = dazzler.getConsensus(g, las, ref_reads)                       # package.d:600-619
+    out = dict(consensus=cons, reference_read=ref_reads, las=las, qv=qv, qoff=qoff, flank_las=None)
+    if flanks is not None:
+        # daligner -A -B -s126 -l126 -e0.7 F C   (postConsensusAlignmentOptions, commandline.d:2918-2935)
+        coff = np.zeros(len(cons) + 1, np.int64); coff[1:] = np.cumsum([len(c) for c in cons])
+        cb = dazzler.Block(coff, np.concatenate(cons) if cons else np.zeros(0, np.uint8))
+        fb = flanks if isinstance(flanks, dazzler.Block) else dazzler.Block(flanks.off, flanks.bases)
+        out["flank_las"] = dazzler.align(fb, cb, tspace=TSPACE, minlen=TSPACE, e=0.7)
+    g.free()
+    return out

@@ -131,3 +131,24 @@ def pack_2bit_dazz(bases):
     pad = (-n) % 4
     b = np.concatenate([bases, np.zeros(pad, np.uint8)]).reshape(-1, 4)
     return ((b[:, 0] << 6) | (b[:, 1] << 4) | (b[:, 2] << 2) | b[:, 3]).astype(np.uint8)
+
+
+def make_pile_batch(scaffolds, gaps, seed, depth=18, anchor=1500, err=0.13, mix=(0.73, 0.20, 0.07)):
+    """Cropped pile-ups as `processPileUps` sees them after `crop` (package.d:409, cropper.d:113): for
+    every gap, `depth` noisy full-length copies (random strand) of the region gap +- anchor.
+    Returns (Block of all cropped reads, pile id per read, list of (scaffold, begin, end) regions)."""
+    rng = np.random.default_rng(seed)
+    seqs, group, regions = [], [], []
+    pid = 0
+    for si, gl in enumerate(gaps):
+        for (b, e) in gl:
+            rb, re_ = max(0, b - anchor), min(len(scaffolds[si]), e + anchor)
+            region = scaffolds[si][rb:re_]
+            n = int(rng.integers(max(4, depth - 6), depth + 7))
+            blk, _ = simulate_reads([region], n, len(region), 1, err, int(rng.integers(1 << 30)), mix=mix,
+                                    min_len=len(region), lognormal=False)
+            for r in range(blk.nreads):
+                seqs.append(blk.read(r)); group.append(pid)
+            regions.append((si, rb, re_)); pid += 1
+    off = np.zeros(len(seqs) + 1, np.int64); off[1:] = np.cumsum([len(s) for s in seqs])
+    return Block(off, np.concatenate(seqs)), np.array(group, np.int32), regions

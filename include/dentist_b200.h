@@ -76,6 +76,8 @@ typedef struct dn_block_desc {
     int64_t data_bytes;
     const int64_t *mask_anno; /* may be NULL */
     const int32_t *mask_data; /* may be NULL */
+    const int32_t *group;     /* may be NULL; [nreads] pile id: only reads of equal group are compared (a whole
+                                 batch of pile-ups = one block = one launch; package.d:153 runs them one by one) */
 } dn_block_desc;
 
 /* Parameters of the local aligner; the subset of daligner/damapper flags DENTIST passes
@@ -152,6 +154,9 @@ int dn_las_filter_pileup(dn_las_buf *las, const int32_t *alen, int32_t na, const
  * trace-spacing tile of every read; *qv has qoff[nreads] bytes, read r owns [qoff[r], qoff[r+1]).
  * `las` must be sorted by A read.  Free both arrays with dn_free. */
 int dn_compute_qvs(const int32_t *rlen, int32_t nreads, const dn_las_buf *las, int32_t coverage, uint8_t **qv, int64_t **qoff);
+/* same with one coverage per read (a batch of pile-ups in one block: package.d:498-501 per pile) */
+int dn_compute_qvs_v(const int32_t *rlen, int32_t nreads, const dn_las_buf *las, int32_t coverage, const int32_t *cov_per_read,
+                     uint8_t **qv, int64_t **qoff);
 void dn_free(void *p);
 /* getConsensus(db, las, readId, opts)  dazzler.d:4213-4255 (`daccord -f -I<i>,<i>`): full-length
  * consensus of each listed read (0-based) over the local alignments in `las` that have it as A read.

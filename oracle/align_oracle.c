@@ -69,6 +69,7 @@ typedef struct {
     const int64_t *off;     /* nreads+1, base offsets into bases[] */
     const uint8_t *bases;   /* 0..3 */
     const uint8_t *mask;    /* per base 0/1 or NULL */
+    const int32_t *group;   /* per read pile id or NULL: hits between different groups are dropped */
 } orc_block;
 
 typedef struct {
@@ -313,6 +314,7 @@ int orc_align(const orc_block *A, const orc_block *B, const orc_params *P, orc_r
         if (ea - ia <= P->t) {
             for (int64_t x = ia; x < ea; x++) for (int64_t y = ib; y < eb; y++) {
                 if (P->self && TA[x].read == TB[y].read) continue;
+                if (A->group && B->group && A->group[TA[x].read] != B->group[TB[y].read]) continue;
                 if (nh == caph) { caph *= 2; H = realloc(H, sizeof(hit_t) * caph); }
                 hit_t *q = &H[nh++];
                 q->a = TA[x].read; q->bs = TB[y].read * 2 + TB[y].strand;

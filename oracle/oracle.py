@@ -27,7 +27,8 @@ class OrcParams(C.Structure):
 
 
 class OrcBlock(C.Structure):
-    _fields_ = [("nreads", C.c_int32), ("off", C.c_void_p), ("bases", C.c_void_p), ("mask", C.c_void_p)]
+    _fields_ = [("nreads", C.c_int32), ("off", C.c_void_p), ("bases", C.c_void_p), ("mask", C.c_void_p),
+                ("group", C.c_void_p)]
 
 
 class OrcResult(C.Structure):
@@ -54,11 +55,15 @@ def lib():
     return _LIB
 
 
-def _block(off, bases, mask):
+def _block(off, bases, mask, group=None):
     off = np.ascontiguousarray(off, dtype=np.int64)
     bases = np.ascontiguousarray(bases, dtype=np.uint8)
     keep = [off, bases]
-    b = OrcBlock(len(off) - 1, off.ctypes.data, bases.ctypes.data, None)
+    b = OrcBlock(len(off) - 1, off.ctypes.data, bases.ctypes.data, None, None)
+    if group is not None:
+        group = np.ascontiguousarray(group, dtype=np.int32)
+        keep.append(group)
+        b.group = group.ctypes.data
     if mask is not None:
         mask = np.ascontiguousarray(mask, dtype=np.uint8)
         keep.append(mask)
@@ -66,7 +71,7 @@ def _block(off, bases, mask):
     return b, keep
 
 
-def align(a_off, a_bases, b_off, b_bases, a_mask=None, b_mask=None, **params):
+def align(a_off, a_bases, b_off, b_bases, a_mask=None, b_mask=None, a_group=None, b_group=None, **params):
     """Run the oracle.  Blocks are (offsets[nreads+1], bases uint8 0..3 concatenated).
     Returns (la structured array, trace uint16 array, stats dict)."""
     p = dict(DEFAULTS)
@@ -74,8 +79,8 @@ def align(a_off, a_bases, b_off, b_bases, a_mask=None, b_mask=None, **params):
         params["self_"] = params.pop("self")
     p.update(params)
     P = OrcParams(**p)
-    A, ka = _block(a_off, a_bases, a_mask)
-    B, kb = _block(b_off, b_bases, b_mask)
+    A, ka = _block(a_off, a_bases, a_mask, a_group)
+    B, kb = _block(b_off, b_bases, b_mask, b_group)
     R = OrcResult()
     rc = lib().orc_align(C.byref(A), C.byref(B), C.byref(P), C.byref(R))
     if rc != 0:

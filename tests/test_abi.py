@@ -46,7 +46,7 @@ def test_no_cpu_fallback_without_device():
         pytest.skip("a GPU is present")
     L = _lib.lib()
     rlen = np.array([8], np.int32); boff = np.array([0], np.int64); data = np.zeros(8, np.uint8)
-    d = _lib.BlockDesc(1, 0, rlen.ctypes.data, boff.ctypes.data, data.ctypes.data, 8, None, None)
+    d = _lib.BlockDesc(1, 0, rlen.ctypes.data, boff.ctypes.data, data.ctypes.data, 8, None, None, None)
     h = C.c_void_p()
     rc = L.dn_block_upload(C.byref(d), C.byref(h))
     assert rc == 2 and b"no CUDA device" in L.dn_last_error()

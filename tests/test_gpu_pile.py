@@ -83,3 +83,55 @@ def test_consensus_matches_oracle_on_noisy_piles():
     # a read without any alignment keeps its own sequence (daccord -f)
     empty = dazzler.getConsensus(g, dazzler.align(g, g, tspace=126, minlen=10 ** 6, self_block=1), [2])
     assert np.array_equal(empty[0], blk.read(2))
+
+
+def test_batched_pileups_equal_per_pile_processing():
+    """All pile-ups of a batch in ONE block (pile id per read) give exactly what the reference's
+    one-pile-at-a-time loop (package.d:153) gives: per-pile oracle runs, concatenated."""
+    from dentist_b200 import pileups
+    from oracle import oracle
+    sc = synth.make_scaffolds(1, 120000, 301, n_repeats=0)
+    gaps = synth.make_gaps(sc, 4, 302, min_len=200, max_len=1500)
+    reads, group, regions = synth.make_pile_batch(sc, gaps, 303, depth=9, anchor=1200)
+    ref, _ = synth.contigs_from(sc, gaps)
+    res = pileups.process_pileups(reads, group, flanks=ref)
+    lens = np.diff(reads.off)
+    assert len(res["consensus"]) == 4
+    for p in range(4):
+        members = np.flatnonzero(group == p)
+        lo, hi = members[0], members[-1] + 1
+        off = reads.off[lo:hi + 1] - reads.off[lo]
+        bases = reads.bases[reads.off[lo]:reads.off[hi]]
+        la, tr, _ = oracle.align(off, bases, off, bases, tspace=126, minlen=500, self=1)
+        toff = la["toff"].astype(np.int64)
+        keep = oracle.filter_error(la, 0.3)
+        la, toff = la[keep], toff[keep]
+        q, qoff = oracle.qv(lens[lo:hi], la, toff, tr, 126, max(len(members), 4) if len(members) >= 4 else len(members))
+        assert np.array_equal(q, res["qv"][res["qoff"][lo]:res["qoff"][hi]])
+        kp = oracle.filter_pileup(la, lens[lo:hi], lens[lo:hi], 126)
+        la, toff = la[kp], toff[kp]
+        sel = (res["las"].rec["aread"] >= lo) & (res["las"].rec["aread"] < hi)
+        grec = res["las"].rec[sel]
+        assert len(grec) == len(la)
+        assert np.array_equal(grec["aread"] - lo, la["aread"]) and np.array_equal(grec["bread"] - lo, la["bread"])
+        for f in ("abpos", "aepos", "bbpos", "bepos", "diffs", "flags"):
+            assert np.array_equal(grec[f], la[f]), f
+        cand = pileups.find_reference_read_candidates(q, qoff, np.arange(len(members)))
+        assert cand[0] + lo == res["reference_read"][p]
+        oc = oracle.consensus(off, bases, la, toff, tr, 126, cand[0])
+        assert np.array_equal(oc, res["consensus"][p])
+        # the consensus is closer to the truth than the raw reference read: compare 12-mers with the region
+        si, rb, re_ = regions[p]
+        t = sc[si][rb:re_]
+        def kmers(s, k=12):
+            v = np.zeros(len(s) - k + 1, np.int64)
+            for i in range(k):
+                v = v * 4 + s[i:len(s) - k + 1 + i]
+            return set(v.tolist())
+        kt = kmers(t) | kmers((3 - t)[::-1])
+        raw = reads.read(res["reference_read"][p])
+        assert np.mean([x in kt for x in kmers(oc)]) > np.mean([x in kt for x in kmers(raw)]) + 0.2
+    # every consensus aligns to its two flanking contigs (package.d:699-769 needs one proper overlap per flank)
+    fl = res["flank_las"].rec
+    for p in range(4):
+        assert len(set(fl["aread"][fl["bread"] == p].tolist())) >= 2
