@@ -43,19 +43,36 @@ def make_workload(scale, rank):
 
 
 def clocks_sampler(stop, out, gpu_index):
-    q = "clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown," \
-        "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+    """Samples SM clock / throttle reasons every 200 ms DURING the timed region.  Uses NVML in-process
+    (same counters as the recipe's `nvidia-smi --query-gpu=clocks.sm,...,clocks_event_reasons.* -lms 200`
+    line) because forking nvidia-smi 5x/s takes the driver lock for milliseconds and perturbs a 40 ms step."""
     try:
-        p = subprocess.Popen(["nvidia-smi", "-i", str(gpu_index), "--query-gpu=" + q, "--format=csv,noheader,nounits", "-lms", "200"],
-                             stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
-    except Exception:
-        return
-    def rd():
-        for ln in p.stdout:
-            out.append(ln.strip())
-    t = threading.Thread(target=rd, daemon=True); t.start()
-    stop.wait()
-    p.terminate()
+        import pynvml as nv
+        nv.nvmlInit()
+        h = nv.nvmlDeviceGetHandleByIndex(gpu_index)
+        mx = nv.nvmlDeviceGetMaxClockInfo(h, nv.NVML_CLOCK_SM)
+        names = [("hw_slowdown", nv.nvmlClocksThrottleReasonHwSlowdown), ("hw_thermal_slowdown", nv.nvmlClocksThrottleReasonHwThermalSlowdown),
+                 ("sw_thermal_slowdown", nv.nvmlClocksThrottleReasonSwThermalSlowdown), ("sw_power_cap", nv.nvmlClocksThrottleReasonSwPowerCap)]
+        while not stop.is_set():
+            sm = nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM)
+            pw = nv.nvmlDeviceGetPowerUsage(h) / 1000.0
+            r = nv.nvmlDeviceGetCurrentClocksThrottleReasons(h)
+            out.append("%d, %d, %.1f, 0x%x, %s" % (sm, mx, pw, r, ", ".join("Active" if r & bit else "Not Active" for _, bit in names)))
+            stop.wait(0.2)
+    except Exception as e:   # NVML unavailable: fall back to the recipe's nvidia-smi line
+        q = "clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown," \
+            "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+        try:
+            p = subprocess.Popen(["nvidia-smi", "-i", str(gpu_index), "--query-gpu=" + q, "--format=csv,noheader,nounits", "-lms", "200"],
+                                 stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+        except Exception:
+            return
+        def rd():
+            for ln in p.stdout:
+                out.append(ln.strip())
+        t = threading.Thread(target=rd, daemon=True); t.start()
+        stop.wait()
+        p.terminate()
 
 
 def summarize_clocks(lines):
@@ -215,6 +232,8 @@ def main():
         rec, toff, tr, st = dazzler.align_blocks(ga, gb, **PARAMS)
         dev_ms += st["ms_total"]; ext_ms += st["ms_extend"]; seed_ms += st["ms_seed"]
         aligned += st["aligned_bases"]; ext_bytes += st["algo_bytes_extend"]; seed_bytes += st["algo_bytes_seed"]; nla = len(rec)
+        if os.environ.get("BENCH_DEBUG"):
+            print("[bench] step ms_total %.2f seed %.2f extend %.2f" % (st["ms_total"], st["ms_seed"], st["ms_extend"]), file=sys.stderr)
     barrier()
     wall = time.perf_counter() - t0
     launches = dazzler.launch_count() - l0

@@ -43,9 +43,11 @@ struct Timer {
 }  // namespace
 
 namespace {
-struct HBlock { size_t cap; size_t pad_[7]; };          // 64-byte header in front of every cached block
+struct HBlock { size_t cap; size_t pinned; size_t pad_[6]; };   // 64-byte header in front of every cached block
 std::mutex g_hmu; std::vector<HBlock *> g_hfree;
 }
+// Result buffers are page-locked (D2H lands in them directly at PCIe speed) and recycled: both a fresh
+// multi-MB malloc (page faults) and a cudaHostAlloc cost milliseconds.
 void *hcache_alloc(size_t bytes) {
     if (bytes < 64) bytes = 64;
     {
@@ -56,16 +58,23 @@ void *hcache_alloc(size_t bytes) {
         if (best >= 0) { HBlock *h = g_hfree[best]; g_hfree.erase(g_hfree.begin() + best); return (void *)(h + 1); }
     }
     size_t cap = bytes + (bytes >> 3);
-    HBlock *h = (HBlock *)malloc(sizeof(HBlock) + cap);
+    HBlock *h = nullptr; size_t pinned = 0;
+    if (bytes >= (256 << 10)) {
+        void *p = nullptr;
+        if (cudaHostAlloc(&p, sizeof(HBlock) + cap, cudaHostAllocDefault) == cudaSuccess) { h = (HBlock *)p; pinned = 1; }
+        else cudaGetLastError();
+    }
+    if (!h) h = (HBlock *)malloc(sizeof(HBlock) + cap);
     if (!h) throw std::bad_alloc();
-    h->cap = cap;
+    h->cap = cap; h->pinned = pinned;
     return (void *)(h + 1);
 }
 void hcache_free(void *p) {
     if (!p) return;
     HBlock *h = (HBlock *)p - 1;
     std::lock_guard<std::mutex> lk(g_hmu);
-    if (g_hfree.size() < 12) g_hfree.push_back(h); else free(h);
+    if (g_hfree.size() < 16) { g_hfree.push_back(h); return; }
+    if (h->pinned) cudaFreeHost(h); else free(h);
 }
 
 void align_blocks(const DevBlock &A, const DevBlock &B, const AlignParams &P, HostLas &out, cudaStream_t s) {
@@ -274,15 +283,11 @@ void align_blocks(const DevBlock &A, const DevBlock &B, const AlignParams &P, Ho
         ms_seed += ts_.stop();
     }
 
-    // ---- duplicate removal over all candidates, download, final ordering -----------------------
+    // ---- duplicate removal, LAsort ordering and trace gather on the device; one download ---------
     const int ncand = round_beg.back();
     const int nrounds = (int)round_cands.size();
-    static PinnedBuf pin_c, pin_t;                  // guarded by the API mutex
-    std::vector<int64_t> tr_base(nrounds + 1, 0);
-    for (int r = 0; r < nrounds; r++) tr_base[r + 1] = tr_base[r] + round_ntr[r];
-    Cand *hc = (Cand *)pin_c.get((size_t)ncand * (sizeof(Cand) + 1) + 64);
-    uint8_t *hdrop = (uint8_t *)(hc + ncand);
-    uint16_t *htr = (uint16_t *)pin_t.get((size_t)tr_base[nrounds] * 2 + 64);
+    if (nrounds > 16) throw Error("more than 16 rounds");
+    int64_t aligned = 0, tot = 0;
     if (ncand > 0) {
         DBuf<Cand> all(ncand); DBuf<int32_t> rb(nrounds + 1); DBuf<uint8_t> drop(ncand);
         for (int r = 0; r < nrounds; r++)
@@ -291,49 +296,49 @@ void align_blocks(const DevBlock &A, const DevBlock &B, const AlignParams &P, Ho
                                         cudaMemcpyDeviceToDevice, s));
         DN_CUDA(cudaMemcpyAsync(rb.p, round_beg.data(), sizeof(int32_t) * (nrounds + 1), cudaMemcpyHostToDevice, s));
         launch_dedupe(all.p, ncand, rb.p, nrounds, drop.p, s);
-        DN_CUDA(cudaMemcpyAsync(hc, all.p, sizeof(Cand) * ncand, cudaMemcpyDeviceToHost, s));
-        DN_CUDA(cudaMemcpyAsync(hdrop, drop.p, ncand, cudaMemcpyDeviceToHost, s));
-        for (int r = 0; r < nrounds; r++)
-            if (round_ntr[r]) DN_CUDA(cudaMemcpyAsync(htr + tr_base[r], round_traces[r].p, 2 * round_ntr[r], cudaMemcpyDeviceToHost, s));
-        DN_CUDA(cudaStreamSynchronize(s));
+        // LAsort order (base.d:1787-1809): (aread, bread, comp, abpos, aepos, bbpos, bepos, diffs), candidate index last
+        FinalBits fb{bits_for((uint64_t)A.maxlen), bits_for((uint64_t)B.maxlen), bits_for((uint64_t)A.nreads), bits_for((uint64_t)B.nreads)};
+        DBuf<ulonglong2> it1(ncand), it2(ncand); DBuf<unsigned long long> ctr(3); ctr.zero(s);
+        ulonglong2 *cur = it1.p, *oth = it2.p;
+        const int fbits[4] = {bits_for((uint64_t)A.maxlen + B.maxlen), 2 * fb.nb, 2 * fb.na + 1, fb.nra + fb.nrb + 1};
+        for (int f = 0; f < 4; f++) {
+            launch_final_setkey(all.p, drop.p, cur, ncand, f, fb, ctr.p, s);
+            ulonglong2 *res = radix_sort_rec16(cur, oth, ncand, 0, 0, fbits[f], s);
+            if (res != cur) { oth = cur; cur = res; }
+        }
+        unsigned long long hctr[3];
+        DN_CUDA(cudaMemcpyAsync(hctr, ctr.p, sizeof hctr, cudaMemcpyDeviceToHost, s)); DN_CUDA(cudaStreamSynchronize(s));
+        const int nkeep = ncand - (int)hctr[0];
+        tr.mark("dedupe + final sort");
+        out.nrec = nkeep;
+        out.rec = (dn_las_record *)hcache_alloc(sizeof(dn_las_record) * ((size_t)nkeep + 1));
+        out.toff = (int64_t *)hcache_alloc(sizeof(int64_t) * ((size_t)nkeep + 1));
+        if (nkeep > 0) {
+            DBuf<dn_las_record> drec(nkeep); DBuf<u32> tl(nkeep); DBuf<int64_t> dtoff(nkeep);
+            launch_final_records(all.p, cur, nkeep, drec.p, tl.p, ctr.p + 1, s);
+            exclusive_scan_u32_to_i64(tl.p, dtoff.p, nkeep, dtotal.p, s);
+            tot = d2h_scalar(dtotal.p, s);
+            FinalGeom FG; memset(&FG, 0, sizeof FG); FG.nrounds = nrounds;
+            for (int r = 0; r < nrounds; r++) { FG.round_trace[r] = round_traces[r].p; FG.round_beg[r] = round_beg[r]; }
+            FG.round_beg[nrounds] = round_beg[nrounds];
+            DBuf<uint16_t> dtr((size_t)tot + 1);
+            launch_final_traces(all.p, cur, nkeep, dtoff.p, FG, dtr.p, s);
+            tr.mark("final records + traces");
+            out.trace = (uint16_t *)hcache_alloc(sizeof(uint16_t) * ((size_t)tot + 1));
+            tr.mark("host buffer alloc");
+            DN_CUDA(cudaMemcpyAsync(out.rec, drec.p, sizeof(dn_las_record) * nkeep, cudaMemcpyDeviceToHost, s));
+            DN_CUDA(cudaMemcpyAsync(out.toff, dtoff.p, sizeof(int64_t) * nkeep, cudaMemcpyDeviceToHost, s));
+            if (tot) DN_CUDA(cudaMemcpyAsync(out.trace, dtr.p, sizeof(uint16_t) * tot, cudaMemcpyDeviceToHost, s));
+            DN_CUDA(cudaMemcpyAsync(hctr, ctr.p, sizeof hctr, cudaMemcpyDeviceToHost, s));
+            DN_CUDA(cudaStreamSynchronize(s));
+            aligned = (int64_t)hctr[1]; ext_bytes = (int64_t)hctr[2];
+        }
     }
-    tr.mark("dedupe + download");
-    // LAsort order (base.d:1787-1809): (aread, bread, comp, abpos, aepos, bbpos, bepos, diffs); candidate index last
-    struct OKey { uint64_t k1, k2, k3; int j; };
-    std::vector<OKey> okeys; okeys.reserve(ncand);
-    for (int j = 0; j < ncand; j++) if (!hdrop[j]) {
-        const Cand &c = hc[j];
-        okeys.push_back(OKey{((uint64_t)(uint32_t)c.a << 32) | (uint32_t)(c.bs >> 1),
-                             ((uint64_t)(c.bs & 1) << 62) | ((uint64_t)(uint32_t)c.ab << 31) | (uint32_t)c.ae,
-                             ((uint64_t)(uint32_t)c.bb << 32) | (uint32_t)c.be, j});
-    }
-    std::sort(okeys.begin(), okeys.end(), [&](const OKey &x, const OKey &y) {
-        if (x.k1 != y.k1) return x.k1 < y.k1;
-        if (x.k2 != y.k2) return x.k2 < y.k2;
-        if (x.k3 != y.k3) return x.k3 < y.k3;
-        if (hc[x.j].diffs != hc[y.j].diffs) return hc[x.j].diffs < hc[y.j].diffs;
-        return x.j < y.j; });
-    std::vector<int> order(okeys.size());
-    for (size_t o = 0; o < okeys.size(); o++) order[o] = okeys[o].j;
-    out.nrec = (int64_t)order.size();
-    int64_t tot = 0; for (int j : order) tot += 2 * hc[j].nt;
+    if (!out.rec) out.rec = (dn_las_record *)hcache_alloc(64);
+    if (!out.toff) out.toff = (int64_t *)hcache_alloc(64);
+    if (!out.trace) out.trace = (uint16_t *)hcache_alloc(64);
     out.ntrace = tot;
-    out.rec = (dn_las_record *)hcache_alloc(sizeof(dn_las_record) * (order.size() + 1));
-    out.toff = (int64_t *)hcache_alloc(sizeof(int64_t) * (order.size() + 1));
-    out.trace = (uint16_t *)hcache_alloc(sizeof(uint16_t) * (tot + 1));
-    int64_t to = 0, aligned = 0;
-    for (size_t o = 0; o < order.size(); o++) {
-        const int j = order[o]; const Cand &c = hc[j];
-        int r = (int)(std::upper_bound(round_beg.begin(), round_beg.end(), j) - round_beg.begin()) - 1;
-        dn_las_record &q = out.rec[o];
-        q.tlen = 2 * c.nt; q.diffs = c.diffs; q.abpos = c.ab; q.bbpos = c.bb; q.aepos = c.ae; q.bepos = c.be;
-        q.flags = (c.bs & 1) ? DN_LAS_COMP : 0u; q.aread = c.a; q.bread = c.bs >> 1; q.pad_ = 0;
-        out.toff[o] = to;
-        memcpy(out.trace + to, htr + tr_base[r] + c.toff, sizeof(uint16_t) * 2 * c.nt);
-        to += 2 * c.nt; aligned += c.ae - c.ab;
-        ext_bytes += (c.ae - c.ab) / 4 + (c.be - c.bb) / 4 + 40 + 4 * c.nt;
-    }
-    tr.mark("host order + gather");
+    tr.mark("dedupe + order + download");
     out.stats.las = out.nrec; out.stats.aligned_bases = aligned; out.stats.trace_points = tot / 2;
     out.stats.algo_bytes_seed = abytes; out.stats.algo_bytes_extend = ext_bytes;
     out.stats.ms_seed = ms_seed; out.stats.ms_extend = ms_ext; out.stats.ms_total = tt.stop();

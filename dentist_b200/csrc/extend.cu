@@ -74,8 +74,9 @@ __global__ void __launch_bounds__(EXT_WARPS * 32) k_extend(const Seed *__restric
                                                            const int64_t *__restrict__ tile_off, int2 *__restrict__ tiles,
                                                            ExtOut *__restrict__ outs, int4 *__restrict__ pool_all,
                                                            int64_t pool_stride, int *__restrict__ counter) {
-    __shared__ int sV[EXT_WARPS][2][64];
-    __shared__ int sT[EXT_WARPS][2][64];
+    __shared__ int sV[EXT_WARPS][2][64];      // furthest A offset per diagonal (two wave buffers)
+    __shared__ int sT[EXT_WARPS][2][64];      // trace record index per diagonal
+    __shared__ int sR[EXT_WARPS][2][64];      // next tile boundary (relative A offset) above the cell
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const u32 FULL = 0xffffffffu;
     int4 *pool = pool_all + (int64_t)(blockIdx.x * EXT_WARPS + warp) * pool_stride;
@@ -108,7 +109,7 @@ __global__ void __launch_bounds__(EXT_WARPS * 32) k_extend(const Seed *__restric
             }
             if (lane == 0) {
                 for (int q = 1; q <= n; q++) { pool[npool] = make_int4(T, firstT + (q - 1) * ts, 0, q); T = npool++; }
-                sV[warp][0][0] = i; sT[warp][0][0] = T;
+                sV[warp][0][0] = i; sT[warp][0][0] = T; sR[warp][0][0] = firstT + n * ts;
                 bS = 3 * (2 * i); bi = i; bk = 0; bd = 0; bT = T;
             }
             npool = n;
@@ -119,49 +120,48 @@ __global__ void __launch_bounds__(EXT_WARPS * 32) k_extend(const Seed *__restric
         while (lo <= hi) {
             d++;
             const int nlo = lo - 1, nhi = hi + 1;
-            const int *Vo = sV[warp][cur], *To = sT[warp][cur];
-            int *Vn = sV[warp][cur ^ 1], *Tn = sT[warp][cur ^ 1];
-            int ci[2], cpi[2], cT[2];
-            int need_l = 0;
-#pragma unroll
-            for (int sl = 0; sl < 2; sl++) {
+            const bool two = nhi - nlo >= 32;                   // warp-uniform: second slot in use
+            const int *Vo = sV[warp][cur], *To = sT[warp][cur], *Ro = sR[warp][cur];
+            int *Vn = sV[warp][cur ^ 1], *Tn = sT[warp][cur ^ 1], *Rn = sR[warp][cur ^ 1];
+            int ci[2] = {NEGV, NEGV}, cT[2] = {-1, -1}, cR[2] = {0, 0}, cn[2] = {0, 0};
+            // one cell of the new wave: best of the three predecessors, slide, count crossed boundaries
+            auto cell = [&](const int sl) {
                 const int k = nlo + lane + 32 * sl;
-                int i = NEGV, pi = NEGV, pT = -1;
-                if (k <= nhi) {
-                    int vs = (k >= lo && k <= hi) ? Vo[k & 63] : NEGV;
-                    int vd = (k - 1 >= lo && k - 1 <= hi) ? Vo[(k - 1) & 63] : NEGV;
-                    int vi = (k + 1 >= lo && k + 1 <= hi) ? Vo[(k + 1) & 63] : NEGV;
-                    if (vs > NEGV) { i = vs + 1; pi = vs; pT = To[k & 63]; }
-                    if (vd > NEGV && vd + 1 > i) { i = vd + 1; pi = vd; pT = To[(k - 1) & 63]; }
-                    if (vi > NEGV && vi > i) { i = vi; pi = vi; pT = To[(k + 1) & 63]; }
-                    if (i > NEGV) { int j = i - k; if (i > la || j > lb || j < 0) i = NEGV; }
-                    if (i > NEGV) {
-                        int j = i - k;
-                        int lim = min(la - i, lb - j);
-                        i += slide(tk.A, tk.ga + i, tk.B, tk.gb + j, lim);
-                        need_l += NB(i) - NB(pi);
-                    }
-                }
-                ci[sl] = i; cpi[sl] = pi; cT[sl] = pT;
-            }
-            const int need = __reduce_add_sync(FULL, need_l);
-            if (npool + need > poolcap) break;                  // pool exhausted: stop before this wave
-            if (need) {
+                if (k > nhi) return;
+                int i = NEGV, ps = k;
+                const int vs = (k >= lo && k <= hi) ? Vo[k & 63] : NEGV;
+                const int vd = (k - 1 >= lo) ? Vo[(k - 1) & 63] : NEGV;          // k-1 <= hi always holds
+                const int vi = (k + 1 <= hi) ? Vo[(k + 1) & 63] : NEGV;          // k+1 >= lo always holds
+                if (vs > NEGV) { i = vs + 1; }
+                if (vd > NEGV && vd + 1 > i) { i = vd + 1; ps = k - 1; }
+                if (vi > NEGV && vi > i) { i = vi; ps = k + 1; }
+                if (i == NEGV) return;
+                int j = i - k;
+                if (i > la || j > lb || j < 0) return;
+                i += slide(tk.A, tk.ga + i, tk.B, tk.gb + j, min(la - i, lb - j));
+                int R = Ro[ps & 63], n = 0;
+                while (i >= R) { n++; R += ts; }
+                ci[sl] = i; cT[sl] = To[ps & 63]; cR[sl] = R; cn[sl] = n;
+            };
+            cell(0);
+            if (two) cell(1);
+            const int need_l = cn[0] + cn[1];
+            if (__any_sync(FULL, need_l != 0)) {
+                const int need = __reduce_add_sync(FULL, need_l);
+                if (npool + need > poolcap) break;              // pool exhausted: stop before this wave
                 int pre = need_l;                               // inclusive scan across lanes
 #pragma unroll
                 for (int o = 1; o < 32; o <<= 1) { int t = __shfl_up_sync(FULL, pre, o); if (lane >= o) pre += t; }
                 int at = npool + pre - need_l;
 #pragma unroll
                 for (int sl = 0; sl < 2; sl++) {
-                    if (ci[sl] > NEGV) {
-                        const int k = nlo + lane + 32 * sl;
-                        int T = cT[sl];
-                        for (int q = NB(cpi[sl]) + 1, qe = NB(ci[sl]); q <= qe; q++) {
-                            int bnd = firstT + (q - 1) * ts;
-                            pool[at] = make_int4(T, bnd - k, d, q); T = at++;
-                        }
-                        cT[sl] = T;
+                    const int k = nlo + lane + 32 * sl;
+                    int T = cT[sl];
+                    for (int q = cn[sl]; q >= 1; q--) {
+                        const int bnd = cR[sl] - q * ts;        // boundaries crossed, in increasing order
+                        pool[at] = make_int4(T, bnd - k, d, 0); T = at++;
                     }
+                    cT[sl] = T;
                 }
                 npool += need;
             }
@@ -174,20 +174,17 @@ __global__ void __launch_bounds__(EXT_WARPS * 32) k_extend(const Seed *__restric
             }
             const int waveS = __reduce_max_sync(FULL, max(S[0], S[1]));
             gbest = max(gbest, waveS);
-            int kmin = 1 << 30, kmax = -(1 << 30);
+            bool alive[2];
 #pragma unroll
             for (int sl = 0; sl < 2; sl++) {
                 const int k = nlo + lane + 32 * sl;
-                bool alive = ci[sl] > NEGV;
-                if (alive) {
-                    int j = ci[sl] - k;
-                    if (S[sl] < gbest - X || ci[sl] == la || j == lb) alive = false;
-                }
-                if (k <= nhi) { Vn[k & 63] = alive ? ci[sl] : NEGV; Tn[k & 63] = cT[sl]; }
-                if (alive) { kmin = min(kmin, k); kmax = max(kmax, k); }
+                alive[sl] = ci[sl] > NEGV && !(S[sl] < gbest - X || ci[sl] == la || ci[sl] - k == lb);
+                if (k <= nhi) { Vn[k & 63] = alive[sl] ? ci[sl] : NEGV; Tn[k & 63] = cT[sl]; Rn[k & 63] = cR[sl]; }
             }
-            int alo = __reduce_min_sync(FULL, kmin), ahi = __reduce_max_sync(FULL, kmax);
-            if (alo > ahi) break;
+            const u32 m0 = __ballot_sync(FULL, alive[0]), m1 = two ? __ballot_sync(FULL, alive[1]) : 0u;
+            if ((m0 | m1) == 0u) break;
+            int alo = nlo + (m0 ? __ffs(m0) - 1 : 32 + __ffs(m1) - 1);
+            int ahi = nlo + (m1 ? 63 - __clz(m1) : 31 - __clz(m0));
             if (ahi - alo + 1 > WM) {
                 int wk = 1 << 30;
                 if (S[0] == waveS) wk = nlo + lane;
@@ -346,7 +343,68 @@ __global__ void __launch_bounds__(256) k_dedupe(const Cand *__restrict__ c, int 
     drop[j] = (uint8_t)dr;
 }
 
+// ---------------------------------------------------------------- final ordering on the device
+
+// LAsort order (base.d:1787-1809) by four stable LSD sorts over (key, candidate index) items
+__global__ void __launch_bounds__(256) k_final_setkey(const Cand *__restrict__ c, const uint8_t *__restrict__ drop,
+                                                      ulonglong2 *__restrict__ items, int n, int field, FinalBits fb,
+                                                      unsigned long long *__restrict__ ndrop) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const u64 idx = field == 0 ? (u64)i : items[i].y;
+    const Cand x = c[idx];
+    u64 key;
+    if (field == 0) key = (u64)(u32)x.diffs;
+    else if (field == 1) key = ((u64)(u32)x.bb << fb.nb) | (u32)x.be;
+    else if (field == 2) key = ((u64)(x.bs & 1) << (2 * fb.na)) | ((u64)(u32)x.ab << fb.na) | (u32)x.ae;
+    else {
+        const u64 d = drop[idx] ? 1ull : 0ull;
+        key = (d << (fb.nra + fb.nrb)) | ((u64)(u32)x.a << fb.nrb) | (u32)(x.bs >> 1);
+        if (d) atomicAdd(ndrop, 1ull);
+    }
+    items[i] = make_ulonglong2(key, idx);
+}
+
+__global__ void __launch_bounds__(256) k_final_records(const Cand *__restrict__ c, const ulonglong2 *__restrict__ items, int nkeep,
+                                                       dn_las_record *__restrict__ rec, u32 *__restrict__ tl,
+                                                       unsigned long long *__restrict__ acc /* [0] aligned bases, [1] ext bytes */) {
+    int o = blockIdx.x * blockDim.x + threadIdx.x;
+    if (o >= nkeep) return;
+    const Cand x = c[items[o].y];
+    dn_las_record q;
+    q.tlen = 2 * x.nt; q.diffs = x.diffs; q.abpos = x.ab; q.bbpos = x.bb; q.aepos = x.ae; q.bepos = x.be;
+    q.flags = (x.bs & 1) ? DN_LAS_COMP : 0u; q.aread = x.a; q.bread = x.bs >> 1; q.pad_ = 0;
+    rec[o] = q; tl[o] = (u32)(2 * x.nt);
+    atomicAdd(&acc[0], (unsigned long long)(x.ae - x.ab));
+    atomicAdd(&acc[1], (unsigned long long)((x.ae - x.ab) / 4 + (x.be - x.bb) / 4 + 40 + 4 * x.nt));
+}
+
+// one warp per record: copy its (diffs, bbases) pairs from the round buffer to the output position
+__global__ void __launch_bounds__(256) k_final_traces(const Cand *__restrict__ c, const ulonglong2 *__restrict__ items, int nkeep,
+                                                      const int64_t *__restrict__ toff, FinalGeom G, uint16_t *__restrict__ out) {
+    const int o = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+    if (o >= nkeep) return;
+    const int j = (int)items[o].y;
+    const Cand x = c[j];
+    int r = 0;
+    while (r + 1 < G.nrounds && j >= G.round_beg[r + 1]) r++;
+    const uint16_t *src = G.round_trace[r] + x.toff;
+    uint16_t *dst = out + toff[o];
+    for (int q = lane; q < 2 * x.nt; q += 32) dst[q] = src[q];
+}
+
 }  // namespace
+
+void launch_final_setkey(const Cand *c, const uint8_t *drop, ulonglong2 *items, int n, int field, FinalBits fb,
+                         unsigned long long *ndrop, cudaStream_t s) {
+    DN_LAUNCH(k_final_setkey, (n + 255) / 256, 256, 0, s, c, drop, items, n, field, fb, ndrop);
+}
+void launch_final_records(const Cand *c, const ulonglong2 *items, int nkeep, dn_las_record *rec, u32 *tl, unsigned long long *acc, cudaStream_t s) {
+    DN_LAUNCH(k_final_records, (nkeep + 255) / 256, 256, 0, s, c, items, nkeep, rec, tl, acc);
+}
+void launch_final_traces(const Cand *c, const ulonglong2 *items, int nkeep, const int64_t *toff, FinalGeom G, uint16_t *out, cudaStream_t s) {
+    DN_LAUNCH(k_final_traces, (nkeep * 32 + 255) / 256, 256, 0, s, c, items, nkeep, toff, G, out);
+}
 
 void launch_task_caps(const Seed *seeds, int nseeds, ExtGeom G, u32 *caps, cudaStream_t s) {
     DN_LAUNCH(k_task_caps, (nseeds + 255) / 256, 256, 0, s, seeds, nseeds, G, caps);

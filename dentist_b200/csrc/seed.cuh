@@ -63,6 +63,12 @@ void launch_write_traces(const Seed *seeds, int nseeds, ExtGeom G, const int64_t
 void launch_retire(const ulonglong2 *hits, int64_t n, const uint8_t *consumed, const Cand *rc, int nrc, SeedGeom G, int w,
                    int32_t *keep, cudaStream_t s);
 void launch_compact_hits(const ulonglong2 *hits, int64_t n, const int32_t *keep, const int32_t *kidx, ulonglong2 *out, cudaStream_t s);
+struct FinalBits { int na, nb, nra, nrb; };       // bits of: A coordinate, B coordinate, A read id, B read id
+struct FinalGeom { const uint16_t *round_trace[16]; int32_t round_beg[17]; int nrounds; };
+void launch_final_setkey(const Cand *c, const uint8_t *drop, ulonglong2 *items, int n, int field, FinalBits fb,
+                         unsigned long long *ndrop, cudaStream_t s);
+void launch_final_records(const Cand *c, const ulonglong2 *items, int nkeep, dn_las_record *rec, u32 *tl, unsigned long long *acc, cudaStream_t s);
+void launch_final_traces(const Cand *c, const ulonglong2 *items, int nkeep, const int64_t *toff, FinalGeom G, uint16_t *out, cudaStream_t s);
 void launch_dedupe(const Cand *cands, int ncand, const int32_t *round_beg, int nrounds, uint8_t *drop, cudaStream_t s);
 
 }  // namespace dn
