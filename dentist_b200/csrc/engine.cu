@@ -121,9 +121,11 @@ void align_blocks(const DevBlock &A, const DevBlock &B, const AlignParams &P, Ho
     DN_CUDA(cudaMemcpyAsync(d_dbase.p, dbase.data(), sizeof(int64_t) * (A.nreads + 1), cudaMemcpyHostToDevice, s));
     const bool grouped = A.has_group && B.has_group;
     JoinGeom JG{A.chunk2read.p, A.off.p, d_dbase.p, B.chunk2read.p, B.off.p, nB, maxlb, gdbits, keybits, P.self,
-                grouped ? A.group.p : nullptr, grouped ? B.group.p : nullptr};
+                grouped ? A.group.p : nullptr, grouped ? B.group.p : nullptr, B.nreads};
     SeedGeom SG{d_dbase.p, A.nreads, gdbits};
 
+    const int aposbits = bits_for((uint64_t)A.maxlen);
+    bool segsorted = false;
     // ---- K3: join ------------------------------------------------------------------------------
     int tbits = bits_for((uint64_t)nA) + (lookup ? -1 : 1); if (tbits < 16) tbits = 16; if (tbits > 2 * k) tbits = 2 * k;
     const int sh = 2 * k - tbits; const u32 nq = 1u << tbits;
@@ -142,7 +144,7 @@ void align_blocks(const DevBlock &A, const DevBlock &B, const AlignParams &P, Ho
             const u32 *mb = B.has_mask ? (st ? B.mask_rc.p : B.mask.p) : nullptr;
             DN_LAUNCH(k_lookup_count, (unsigned)((nwB + 255) / 256), 256, 0, s, (const u32 *)(st ? B.rc.p : B.fwd.p), mb,
                       (const int64_t *)B.off.p, (const int32_t *)B.len.p, (const int32_t *)B.chunk2read.p, nwB, k,
-                      (const u64 *)sa, (const u32 *)tbl.p, sh, P.t, wcnt.p + st * nwB);
+                      (const u64 *)sa, (const u32 *)tbl.p, sh, P.t, JG, wcnt.p + st * nwB);
         }
         exclusive_scan_u32_to_i64(wcnt.p, woff.p, 2 * nwB, dtotal.p, s);
         H = d2h_scalar(dtotal.p, s);
@@ -154,9 +156,61 @@ void align_blocks(const DevBlock &A, const DevBlock &B, const AlignParams &P, Ho
                 DN_LAUNCH(k_lookup_emit, (unsigned)((nwB + 255) / 256), 256, 0, s, (const u32 *)(st ? B.rc.p : B.fwd.p), mb,
                           (const int64_t *)B.off.p, (const int32_t *)B.len.p, (const int32_t *)B.chunk2read.p, nwB, k,
                           (const u64 *)sa, (const u32 *)tbl.p, sh, P.t, (const u32 *)(wcnt.p + st * nwB),
-                          (const int64_t *)(woff.p + st * nwB), st, JG, hits.p, ninv.p);
+                          (const int64_t *)(woff.p + st * nwB), st, JG, hits.p);
             }
         abytes += 2 * (nB / 4) * 2 + 2 * nwB * (4 + 4 + 8 + 8 + 4) + 16 * H;   // packed B read twice per strand, word counts/offsets, hits
+        // hits were emitted grouped by (strand, read) in ascending order: sort inside the segments only
+        if (H > 0 && gdbits + aposbits <= 63 && !getenv("DN_NO_SEGSORT")) {
+            const int nseg = 2 * B.nreads;
+            DBuf<int64_t> seg_off((size_t)nseg + 1);
+            launch_seg_offsets(woff.p, B.off.p, B.nreads, nwB, H, seg_off.p, s);
+            std::vector<int64_t> hso((size_t)nseg + 1);
+            DN_CUDA(cudaMemcpyAsync(hso.data(), seg_off.p, sizeof(int64_t) * (nseg + 1), cudaMemcpyDeviceToHost, s));
+            DN_CUDA(cudaStreamSynchronize(s));
+            std::vector<int32_t> cls[3]; const int caps[3] = {2048, 8192, 16384};
+            std::vector<int> big;                       // segments too large for shared memory
+            int64_t nbig = 0;
+            for (int i = 0; i < nseg; i++) {
+                const int64_t len = hso[i + 1] - hso[i];
+                if (len < 2) continue;
+                int c = 0; while (c < 3 && len > caps[c]) c++;
+                if (c == 3) { big.push_back(i); nbig += len; } else cls[c].push_back(i);
+            }
+            const bool fits = big.size() <= 256;
+            if (getenv("DN_TRACE")) {
+                int64_t mx = 0; for (int i = 0; i < nseg; i++) mx = std::max(mx, hso[i + 1] - hso[i]);
+                fprintf(stderr, "[dn trace] segments %d, largest %lld hits, classes %zu/%zu/%zu, fits %d\n", nseg, (long long)mx,
+                        cls[0].size(), cls[1].size(), cls[2].size(), (int)fits);
+                fprintf(stderr, "[dn trace] oversized segments %zu (%lld hits)\n", big.size(), (long long)nbig);
+            }
+            if (fits) {
+                for (int c = 0; c < 3; c++) {
+                    if (cls[c].empty()) continue;
+                    DBuf<int32_t> lst(cls[c].size());
+                    DN_CUDA(cudaMemcpyAsync(lst.p, cls[c].data(), sizeof(int32_t) * cls[c].size(), cudaMemcpyHostToDevice, s));
+                    launch_segsort(hits.p, seg_off.p, lst.p, (int)cls[c].size(), caps[c], gdbits, aposbits, s);
+                }
+                if (!big.empty()) {
+                    // the few oversized segments: gather, radix sort by (bs, gd, apos), copy back range by range
+                    DBuf<ulonglong2> t1(nbig), t2(nbig);
+                    int64_t o = 0;
+                    for (int i : big) {
+                        const int64_t len = hso[i + 1] - hso[i];
+                        DN_CUDA(cudaMemcpyAsync(t1.p + o, hits.p + hso[i], 16 * len, cudaMemcpyDeviceToDevice, s)); o += len;
+                    }
+                    ulonglong2 *r = radix_sort_rec16(t1.p, t2.p, nbig, 1, 0, aposbits, s);
+                    r = radix_sort_rec16(r, r == t1.p ? t2.p : t1.p, nbig, 0, 0, keybits, s);
+                    o = 0;
+                    for (int i : big) {
+                        const int64_t len = hso[i + 1] - hso[i];
+                        DN_CUDA(cudaMemcpyAsync(hits.p + hso[i], r + o, 16 * len, cudaMemcpyDeviceToDevice, s)); o += len;
+                    }
+                }
+                DN_CUDA(cudaStreamSynchronize(s));      // cls[] vectors are read by the async copies above
+                segsorted = true;
+                abytes += 32 * H + 8ll * nseg;
+            }
+        }
     } else {
         DBuf<u64> tb(2 * nB), tb2(2 * nB);
         emit_tuples(B, false, k, 0u, tb.p, s);
@@ -180,20 +234,22 @@ void align_blocks(const DevBlock &A, const DevBlock &B, const AlignParams &P, Ho
     ta.release(); ta2.release(); tbl.release();
 
     // ---- hit sort: by apos, then stably by (bread, strand, aread, diagonal) -------------------
-    const int aposbits = bits_for((uint64_t)A.maxlen);
-    ulonglong2 *hs = radix_sort_rec16(hits.p, hits2.p, H, 1, 0, aposbits, s);
-    ulonglong2 *ho = hs == hits.p ? hits2.p : hits.p;
-    hs = radix_sort_rec16(hs, ho, H, 0, 0, keybits + 1, s);
-    ho = hs == hits.p ? hits2.p : hits.p;
-    const int npass_h = (aposbits + 7) / 8 + (keybits + 1 + 7) / 8;
-    abytes += (int64_t)npass_h * 48 * H;
+    ulonglong2 *hs = hits.p, *ho = hits2.p;
+    if (!segsorted) {
+        hs = radix_sort_rec16(hits.p, hits2.p, H, 1, 0, aposbits, s);
+        ho = hs == hits.p ? hits2.p : hits.p;
+        hs = radix_sort_rec16(hs, ho, H, 0, 0, keybits + 1, s);
+        ho = hs == hits.p ? hits2.p : hits.p;
+        const int npass_h = (aposbits + 7) / 8 + (keybits + 1 + 7) / 8;
+        abytes += (int64_t)npass_h * 48 * H;
+    }
     int64_t n = H - ninvalid;                   // invalid (self) hits sorted to the end
     tr.mark("hit sort");
     out.stats.hits = n;
 
     // ---- rounds of band filter -> seeds -> extension -> retirement ----------------------------
     ExtGeom EG{A.fwd.p, A.rc.p, B.fwd.p, B.rc.p, A.off.p, B.off.p, A.len.p, B.len.p,
-               P.tspace, P.cdiff, P.xdrop, P.wmax, P.poolmul, (u32)((1ull << 32) / (u32)P.tspace + 1)};
+               P.tspace, P.cdiff, P.xdrop, P.wmax, P.poolmul, (u32)((1ull << 32) / (u32)P.tspace + 1), B.nreads};
     {
         long long span = (long long)B.maxlen + B.maxlen / 2 + 64; if (A.maxlen < span) span = A.maxlen;
         if ((unsigned long long)span >= (1ull << 32) / (unsigned)P.tspace) throw Error("reads too long for the tile arithmetic");
@@ -297,7 +353,7 @@ void align_blocks(const DevBlock &A, const DevBlock &B, const AlignParams &P, Ho
         DN_CUDA(cudaMemcpyAsync(rb.p, round_beg.data(), sizeof(int32_t) * (nrounds + 1), cudaMemcpyHostToDevice, s));
         launch_dedupe(all.p, ncand, rb.p, nrounds, drop.p, s);
         // LAsort order (base.d:1787-1809): (aread, bread, comp, abpos, aepos, bbpos, bepos, diffs), candidate index last
-        FinalBits fb{bits_for((uint64_t)A.maxlen), bits_for((uint64_t)B.maxlen), bits_for((uint64_t)A.nreads), bits_for((uint64_t)B.nreads)};
+        FinalBits fb{bits_for((uint64_t)A.maxlen), bits_for((uint64_t)B.maxlen), bits_for((uint64_t)A.nreads), bits_for((uint64_t)B.nreads), B.nreads};
         DBuf<ulonglong2> it1(ncand), it2(ncand); DBuf<unsigned long long> ctr(3); ctr.zero(s);
         ulonglong2 *cur = it1.p, *oth = it2.p;
         const int fbits[4] = {bits_for((uint64_t)A.maxlen + B.maxlen), 2 * fb.nb, 2 * fb.na + 1, fb.nra + fb.nrb + 1};
@@ -315,7 +371,7 @@ void align_blocks(const DevBlock &A, const DevBlock &B, const AlignParams &P, Ho
         out.toff = (int64_t *)hcache_alloc(sizeof(int64_t) * ((size_t)nkeep + 1));
         if (nkeep > 0) {
             DBuf<dn_las_record> drec(nkeep); DBuf<u32> tl(nkeep); DBuf<int64_t> dtoff(nkeep);
-            launch_final_records(all.p, cur, nkeep, drec.p, tl.p, ctr.p + 1, s);
+            launch_final_records(all.p, cur, nkeep, B.nreads, drec.p, tl.p, ctr.p + 1, s);
             exclusive_scan_u32_to_i64(tl.p, dtoff.p, nkeep, dtotal.p, s);
             tot = d2h_scalar(dtotal.p, s);
             FinalGeom FG; memset(&FG, 0, sizeof FG); FG.nrounds = nrounds;

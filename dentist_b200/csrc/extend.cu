@@ -43,7 +43,7 @@ struct Task {
 
 __device__ __forceinline__ Task make_task(const Seed &sd, int dir, const ExtGeom &G) {
     Task t;
-    const int br = sd.bs >> 1, st = sd.bs & 1;
+    const int st = sd.bs >= G.nb_reads ? 1 : 0, br = sd.bs - st * G.nb_reads;
     const int LA = G.a_len[sd.a], LB = G.b_len[br];
     const int64_t oa = G.a_off[sd.a], ob = G.b_off[br];
     if (dir == 0) {
@@ -356,24 +356,25 @@ __global__ void __launch_bounds__(256) k_final_setkey(const Cand *__restrict__ c
     u64 key;
     if (field == 0) key = (u64)(u32)x.diffs;
     else if (field == 1) key = ((u64)(u32)x.bb << fb.nb) | (u32)x.be;
-    else if (field == 2) key = ((u64)(x.bs & 1) << (2 * fb.na)) | ((u64)(u32)x.ab << fb.na) | (u32)x.ae;
+    else if (field == 2) key = ((u64)(x.bs >= fb.nb_reads ? 1 : 0) << (2 * fb.na)) | ((u64)(u32)x.ab << fb.na) | (u32)x.ae;
     else {
         const u64 d = drop[idx] ? 1ull : 0ull;
-        key = (d << (fb.nra + fb.nrb)) | ((u64)(u32)x.a << fb.nrb) | (u32)(x.bs >> 1);
+        key = (d << (fb.nra + fb.nrb)) | ((u64)(u32)x.a << fb.nrb) | (u32)(x.bs >= fb.nb_reads ? x.bs - fb.nb_reads : x.bs);
         if (d) atomicAdd(ndrop, 1ull);
     }
     items[i] = make_ulonglong2(key, idx);
 }
 
 __global__ void __launch_bounds__(256) k_final_records(const Cand *__restrict__ c, const ulonglong2 *__restrict__ items, int nkeep,
-                                                       dn_las_record *__restrict__ rec, u32 *__restrict__ tl,
+                                                       int nb_reads, dn_las_record *__restrict__ rec, u32 *__restrict__ tl,
                                                        unsigned long long *__restrict__ acc /* [0] aligned bases, [1] ext bytes */) {
     int o = blockIdx.x * blockDim.x + threadIdx.x;
     if (o >= nkeep) return;
     const Cand x = c[items[o].y];
     dn_las_record q;
     q.tlen = 2 * x.nt; q.diffs = x.diffs; q.abpos = x.ab; q.bbpos = x.bb; q.aepos = x.ae; q.bepos = x.be;
-    q.flags = (x.bs & 1) ? DN_LAS_COMP : 0u; q.aread = x.a; q.bread = x.bs >> 1; q.pad_ = 0;
+    const int comp = x.bs >= nb_reads ? 1 : 0;
+    q.flags = comp ? DN_LAS_COMP : 0u; q.aread = x.a; q.bread = x.bs - comp * nb_reads; q.pad_ = 0;
     rec[o] = q; tl[o] = (u32)(2 * x.nt);
     atomicAdd(&acc[0], (unsigned long long)(x.ae - x.ab));
     atomicAdd(&acc[1], (unsigned long long)((x.ae - x.ab) / 4 + (x.be - x.bb) / 4 + 40 + 4 * x.nt));
@@ -399,8 +400,8 @@ void launch_final_setkey(const Cand *c, const uint8_t *drop, ulonglong2 *items, 
                          unsigned long long *ndrop, cudaStream_t s) {
     DN_LAUNCH(k_final_setkey, (n + 255) / 256, 256, 0, s, c, drop, items, n, field, fb, ndrop);
 }
-void launch_final_records(const Cand *c, const ulonglong2 *items, int nkeep, dn_las_record *rec, u32 *tl, unsigned long long *acc, cudaStream_t s) {
-    DN_LAUNCH(k_final_records, (nkeep + 255) / 256, 256, 0, s, c, items, nkeep, rec, tl, acc);
+void launch_final_records(const Cand *c, const ulonglong2 *items, int nkeep, int nb_reads, dn_las_record *rec, u32 *tl, unsigned long long *acc, cudaStream_t s) {
+    DN_LAUNCH(k_final_records, (nkeep + 255) / 256, 256, 0, s, c, items, nkeep, nb_reads, rec, tl, acc);
 }
 void launch_final_traces(const Cand *c, const ulonglong2 *items, int nkeep, const int64_t *toff, FinalGeom G, uint16_t *out, cudaStream_t s) {
     DN_LAUNCH(k_final_traces, (nkeep * 32 + 255) / 256, 256, 0, s, c, items, nkeep, toff, G, out);

@@ -211,6 +211,10 @@ __device__ __forceinline__ int read_of(const int32_t *__restrict__ c2r, const in
     return r;
 }
 
+__device__ __forceinline__ bool pair_ok(const JoinGeom &G, int ar, int br) {
+    return !((G.self && ar == br) || (G.a_group && G.a_group[ar] != G.b_group[br]));
+}
+
 // hit record: .x = key = (bs << gdbits) | gd   (invalid: 1 << keybits), .y = apos | bpos << 32
 __global__ void __launch_bounds__(256) k_join_emit(const u64 *__restrict__ ta, const u64 *__restrict__ tb, int64_t nb,
                                                    const u32 *__restrict__ cnt, const u32 *__restrict__ start,
@@ -225,7 +229,7 @@ __global__ void __launch_bounds__(256) k_join_emit(const u64 *__restrict__ ta, c
     int64_t gb = strand ? (int64_t)pb - G.nbp : (int64_t)pb;
     int br = read_of(G.b_c2r, G.b_off, gb);
     int bpos = (int)(gb - G.b_off[br]);
-    u64 bs = (u64)br * 2 + strand;
+    u64 bs = (u64)strand * G.nb_reads + br;
     int64_t o = hoff[j];
     u32 s = start[j];
     u32 ninv = 0;
@@ -275,17 +279,23 @@ __global__ void __launch_bounds__(256) k_lookup_count(const u32 *__restrict__ se
                                                       const int64_t *__restrict__ off, const int32_t *__restrict__ len,
                                                       const int32_t *__restrict__ c2r, int64_t nwords, int k,
                                                       const u64 *__restrict__ ta, const u32 *__restrict__ tbl, int sh, int tcap,
-                                                      u32 *__restrict__ wcnt) {
+                                                      JoinGeom G, u32 *__restrict__ wcnt) {
     int64_t wi = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (wi >= nwords) return;
     const WordKmers w = load_word(seq, maskbits, off, len, c2r, wi);
     const u64 kmask = (1ull << (2 * k)) - 1ull, mk = (1ull << k) - 1ull;
+    const bool restricted = G.self || G.a_group;
     u32 total = 0;
 #pragma unroll 4
     for (int jj = 0; jj < 16; jj++) {
         if ((w.p0 + jj + k <= w.L) && (((w.mwin >> jj) & mk) == 0)) {
             u32 s, c; a_range_fwd(ta, tbl, sh, (u32)((w.v >> (2 * jj)) & kmask), tcap, s, c);
-            total += c;
+            if (restricted) {                     // self pairs / pairs across pile-ups are never emitted
+                for (u32 x = 0; x < c; x++) {
+                    const int ar = read_of(G.a_c2r, G.a_off, (int64_t)(u32)ta[s + x]);
+                    total += pair_ok(G, ar, w.r) ? 1u : 0u;
+                }
+            } else total += c;
         }
     }
     wcnt[wi] = total;
@@ -296,15 +306,14 @@ __global__ void __launch_bounds__(256) k_lookup_emit(const u32 *__restrict__ seq
                                                      const int32_t *__restrict__ c2r, int64_t nwords, int k,
                                                      const u64 *__restrict__ ta, const u32 *__restrict__ tbl, int sh, int tcap,
                                                      const u32 *__restrict__ wcnt, const int64_t *__restrict__ woff, int strand,
-                                                     JoinGeom G, ulonglong2 *__restrict__ hits, unsigned long long *__restrict__ ninvalid) {
+                                                     JoinGeom G, ulonglong2 *__restrict__ hits) {
     int64_t wi = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (wi >= nwords) return;
     if (wcnt[wi] == 0) return;
     const WordKmers w = load_word(seq, maskbits, off, len, c2r, wi);
     const u64 kmask = (1ull << (2 * k)) - 1ull, mk = (1ull << k) - 1ull;
-    const u64 bs = (u64)w.r * 2 + strand;
+    const u64 bs = (u64)strand * G.nb_reads + w.r;
     int64_t o = woff[wi];
-    u32 ninv = 0;
     for (int jj = 0; jj < 16; jj++) {
         if (!((w.p0 + jj + k <= w.L) && (((w.mwin >> jj) & mk) == 0))) continue;
         u32 s, c; a_range_fwd(ta, tbl, sh, (u32)((w.v >> (2 * jj)) & kmask), tcap, s, c);
@@ -313,13 +322,11 @@ __global__ void __launch_bounds__(256) k_lookup_emit(const u32 *__restrict__ seq
             int64_t ga = (int64_t)(u32)ta[s + x];
             int ar = read_of(G.a_c2r, G.a_off, ga);
             int apos = (int)(ga - G.a_off[ar]);
-            u64 key;
-            if ((G.self && ar == w.r) || (G.a_group && G.a_group[ar] != G.b_group[w.r])) { key = 1ull << G.keybits; ninv++; }
-            else { u64 gd = (u64)(G.a_dbase[ar] + apos - bpos + G.maxlb); key = (bs << G.gdbits) | gd; }
-            hits[o++] = make_ulonglong2(key, (u64)(u32)apos | ((u64)(u32)bpos << 32));
+            if (!pair_ok(G, ar, w.r)) continue;
+            const u64 gd = (u64)(G.a_dbase[ar] + apos - bpos + G.maxlb);
+            hits[o++] = make_ulonglong2((bs << G.gdbits) | gd, (u64)(u32)apos | ((u64)(u32)bpos << 32));
         }
     }
-    if (ninv) atomicAdd(ninvalid, (unsigned long long)ninv);
 }
 
 // ------------------------------------------------------------------------- K4: band filter

@@ -14,6 +14,7 @@ struct JoinGeom {
     int64_t maxlb;        // max B read length rounded up to the band width
     int gdbits, keybits, self;
     const int32_t *a_group, *b_group;   // optional: pairs with different group ids are dropped
+    int nb_reads;                       // hit/seed/candidate `bs` = strand * nb_reads + bread (strand-major)
 };
 struct SeedGeom { const int64_t *a_dbase; int na; int gdbits; };
 
@@ -33,10 +34,10 @@ __global__ void k_join_count(const u64 *ta, const u32 *tbl, int sh, const u64 *t
 __global__ void k_join_emit(const u64 *ta, const u64 *tb, int64_t nb, const u32 *cnt, const u32 *start, const int64_t *hoff,
                             JoinGeom G, ulonglong2 *hits, unsigned long long *ninvalid);
 __global__ void k_lookup_count(const u32 *seq, const u32 *maskbits, const int64_t *off, const int32_t *len, const int32_t *c2r,
-                               int64_t nwords, int k, const u64 *ta, const u32 *tbl, int sh, int tcap, u32 *wcnt);
+                               int64_t nwords, int k, const u64 *ta, const u32 *tbl, int sh, int tcap, JoinGeom G, u32 *wcnt);
 __global__ void k_lookup_emit(const u32 *seq, const u32 *maskbits, const int64_t *off, const int32_t *len, const int32_t *c2r,
                               int64_t nwords, int k, const u64 *ta, const u32 *tbl, int sh, int tcap, const u32 *wcnt,
-                              const int64_t *woff, int strand, JoinGeom G, ulonglong2 *hits, unsigned long long *ninvalid);
+                              const int64_t *woff, int strand, JoinGeom G, ulonglong2 *hits);
 __global__ void k_hit_cover(const ulonglong2 *hits, int64_t n, int k, int w, int32_t *cov, int32_t *bflag);
 __global__ void k_band_table(const ulonglong2 *hits, int64_t n, int w, const int32_t *bflag, const int32_t *bidx,
                              int32_t *bfirst, u64 *bkey, int32_t nbands);
@@ -46,11 +47,17 @@ __global__ void k_band_hot(const u64 *bkey, const uint8_t *pass, int32_t nbands,
 __global__ void k_seeds(const ulonglong2 *hits, const int32_t *bfirst, const u64 *bkey, const uint8_t *hot,
                         const int32_t *cstart, const int32_t *cidx, int32_t nbands, SeedGeom G, Seed *seeds, uint8_t *consumed);
 
+// segmented hit sort (segsort.cu)
+void launch_seg_offsets(const int64_t *woff, const int64_t *b_off, int nr, int64_t nwB, int64_t H, int64_t *seg_off, cudaStream_t s);
+void launch_segsort(ulonglong2 *hits, const int64_t *seg_off, const int32_t *seglist, int nseg, int cap, int gdbits, int aposbits,
+                    cudaStream_t s);
+
 // extension stage (extend.cu)
 struct ExtGeom {
     const u32 *a_fwd, *a_rc, *b_fwd, *b_rc;
     const int64_t *a_off, *b_off; const int32_t *a_len, *b_len;
     int ts, cdiff, xdrop, wmax, poolmul; u32 ts_magic;
+    int nb_reads;
 };
 void launch_task_caps(const Seed *seeds, int nseeds, ExtGeom G, u32 *caps, cudaStream_t s);
 void launch_extend(const Seed *seeds, int nseeds, ExtGeom G, const int64_t *tile_off, int2 *tiles, ExtOut *outs,
@@ -63,11 +70,11 @@ void launch_write_traces(const Seed *seeds, int nseeds, ExtGeom G, const int64_t
 void launch_retire(const ulonglong2 *hits, int64_t n, const uint8_t *consumed, const Cand *rc, int nrc, SeedGeom G, int w,
                    int32_t *keep, cudaStream_t s);
 void launch_compact_hits(const ulonglong2 *hits, int64_t n, const int32_t *keep, const int32_t *kidx, ulonglong2 *out, cudaStream_t s);
-struct FinalBits { int na, nb, nra, nrb; };       // bits of: A coordinate, B coordinate, A read id, B read id
+struct FinalBits { int na, nb, nra, nrb, nb_reads; };       // bits of: A coordinate, B coordinate, A read id, B read id
 struct FinalGeom { const uint16_t *round_trace[16]; int32_t round_beg[17]; int nrounds; };
 void launch_final_setkey(const Cand *c, const uint8_t *drop, ulonglong2 *items, int n, int field, FinalBits fb,
                          unsigned long long *ndrop, cudaStream_t s);
-void launch_final_records(const Cand *c, const ulonglong2 *items, int nkeep, dn_las_record *rec, u32 *tl, unsigned long long *acc, cudaStream_t s);
+void launch_final_records(const Cand *c, const ulonglong2 *items, int nkeep, int nb_reads, dn_las_record *rec, u32 *tl, unsigned long long *acc, cudaStream_t s);
 void launch_final_traces(const Cand *c, const ulonglong2 *items, int nkeep, const int64_t *toff, FinalGeom G, uint16_t *out, cudaStream_t s);
 void launch_dedupe(const Cand *cands, int ncand, const int32_t *round_beg, int nrounds, uint8_t *drop, cudaStream_t s);
 
