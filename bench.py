@@ -228,6 +228,7 @@ def main():
     held = None
     for _ in range(args.warmup):     # hold the previous result like the timed loop does (both result-buffer sets get warm)
         held = dazzler.align_blocks(ga, gb, **PARAMS)
+    held = None
     stop = threading.Event(); clk = []
     th = threading.Thread(target=clocks_sampler, args=(stop, clk, local_rank), daemon=True); th.start()
     barrier()
