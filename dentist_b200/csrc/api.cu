@@ -252,6 +252,33 @@ static int align_files(const char *dbA, const char *dbB, const char *const *opts
     });
 }
 
+int dn_dbdust(const char *db, const char *const *opts, int nopts) {
+    if (!db) return fail(DN_ERR_INVALID, "null argument");
+    return guarded([&]() -> int {
+        int window = 64, minlen = 10; double thr = 2.0;                 // DBdust defaults (dazzler.d:3796-3806)
+        for (int i = 0; i < nopts; i++) {
+            const char *o = opts[i];
+            if (!o || o[0] != '-' || !o[1]) return fail(DN_ERR_INVALID, "bad option");
+            if (o[1] == 'w') window = atoi(o + 2); else if (o[1] == 't') thr = atof(o + 2); else if (o[1] == 'm') minlen = atoi(o + 2);
+            else if (o[1] == 'b') continue; else return fail(DN_ERR_INVALID, std::string("unknown option: ") + o);
+        }
+        HostDb D; std::string err;
+        if (!read_dazz_db(db, {}, D, err)) return fail(DN_ERR_IO, err);
+        dn_block_desc d = D.desc();
+        dn_block *blk = nullptr;
+        if (int rc = dn_block_upload(&d, &blk)) return rc;
+        int64_t *anno = nullptr; int32_t *data = nullptr;
+        int rc = dn_dust_block(blk, window, thr, minlen, &anno, &data);
+        dn_block_free(blk);
+        if (rc) return rc;
+        std::vector<std::vector<int32_t>> iv(D.rlen.size());
+        for (size_t r = 0; r < iv.size(); r++) iv[r].assign(data + anno[r] / 4, data + anno[r + 1] / 4);
+        hcache_free(anno); hcache_free(data);
+        if (!write_mask_track(db, "dust", iv, err)) return fail(DN_ERR_IO, err);
+        return DN_OK;
+    });
+}
+
 int dn_dalign(const char *dbA, const char *dbB, const char *const *opts, int nopts, const char *outdir) {
     return align_files(dbA, dbB, opts, nopts, outdir, false);
 }

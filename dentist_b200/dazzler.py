@@ -265,3 +265,21 @@ def getConsensus(block, las, reads):
     bases = np.ctypeslib.as_array(out.bases, shape=(max(tot, 1),))[:tot].copy()
     L.dn_seq_free(C.byref(out))
     return [bases[off[i]:off[i + 1]] for i in range(len(reads))]
+
+
+def dbdust(block, window=64, threshold=2.0, minlen=10):
+    """dazzler.d:3815-3818 on a resident block: per-read list of masked (begin, end) intervals."""
+    L = _lib.lib()
+    anno = C.POINTER(C.c_int64)(); data = C.POINTER(C.c_int32)()
+    _lib.check(L.dn_dust_block(block._h, int(window), C.c_double(threshold), int(minlen), C.byref(anno), C.byref(data)))
+    a = np.ctypeslib.as_array(anno, shape=(block.nreads + 1,)).copy()
+    n = int(a[-1]) // 4
+    d = np.ctypeslib.as_array(data, shape=(max(n, 1),))[:n].copy()
+    L.dn_free(anno); L.dn_free(data)
+    return [[(int(d[i]), int(d[i + 1])) for i in range(int(a[r]) // 4, int(a[r + 1]) // 4, 2)] for r in range(block.nreads)]
+
+
+def dbdustFile(dbFile, opts=()):
+    """dazzler.d:3815-3818 on a DB file: writes the `dust` track next to it."""
+    arr, n = _opts(list(opts))
+    _lib.check(_lib.lib().dn_dbdust(dbFile.encode(), arr, n))

@@ -165,12 +165,20 @@ typedef struct dn_seq_buf { int32_t nseq; int64_t *off; uint8_t *bases; } dn_seq
 int dn_consensus(const dn_block *db, const dn_las_buf *las, const int32_t *reads, int32_t nreads, dn_seq_buf *out);
 void dn_seq_free(dn_seq_buf *buf);
 
+/* dbdust(db, opts)  dazzler.d:3815-3818 (`DBdust -w -t -m`): low-complexity intervals of every read of a
+ * resident block in the reference's mask-track layout (dazzler.d:4943-5052): *anno = nreads+1 int64
+ * byte offsets into *data, *data = int32 (begin,end) pairs.  Free both with dn_free.  Feed them to
+ * dn_block_desc.mask_* (what `-mdust` does). */
+int dn_dust_block(const dn_block *blk, int32_t window, double threshold, int32_t minlen, int64_t **anno, int32_t **data);
+
 /* ---- file-level drop-ins for dazzler.d ---------------------------------------------------- */
 
 /* getDalignment(dbA[, dbB], opts, outdir)  dazzler.d:3829-3844 / dalign() :6131-6140.
  * dbB == NULL => self comparison.  Writes outdir/<A>.<B>.las; `opts` are daligner flags
  * ("-s126", "-l500", "-e0.7", "-k14", "-T8", "-B", "-A", "-I", "-mdust", ...). */
 int dn_dalign(const char *dbA, const char *dbB, const char *const *opts, int nopts, const char *outdir);
+/* dbdust(dbFile, dbdustOptions)  dazzler.d:3815-3818: writes the `dust` track (.<db>.dust.anno/.data). */
+int dn_dbdust(const char *db, const char *const *opts, int nopts);
 /* getDamapping(refDb, queryDb, opts, outdir)  dazzler.d:3855-3866 / damapper() :6163-6170. */
 int dn_damap(const char *refDb, const char *queryDb, const char *const *opts, int nopts, const char *outdir);
 

@@ -77,3 +77,27 @@ def test_errors_are_reported_not_swallowed(tmp_path):
     dbutil.write_db(str(tmp_path / "r.db"), reads)
     with pytest.raises(dazzler.DnError, match="unknown option"):
         dazzler.getDalignment(str(tmp_path / "r.db"), None, ["-Q3"], str(tmp_path))
+
+
+def test_dbdust_writes_a_track_that_mdust_reads(tmp_path):
+    from dentist_b200 import dazzler
+    from oracle import dust
+    import struct
+    rng = np.random.default_rng(3)
+    seqs = [rng.integers(0, 4, 2000, dtype=np.uint8) for _ in range(4)]
+    seqs[1][300:420] = 3
+    off = np.zeros(5, np.int64); off[1:] = np.cumsum([len(s) for s in seqs])
+    blk = synth.Block(off, np.concatenate(seqs))
+    db = str(tmp_path / "x.db")
+    dbutil.write_db(db, blk)
+    dazzler.dbdustFile(db, ["-w64", "-t2.0", "-m10"])
+    anno = open(str(tmp_path / ".x.dust.anno"), "rb").read()
+    data = open(str(tmp_path / ".x.dust.data"), "rb").read()
+    n, size = struct.unpack_from("<ii", anno, 0)
+    assert (n, size) == (4, 0)                                     # mask track header, dazzler.d:4943-4975
+    offs = struct.unpack_from("<5q", anno, 8)
+    got = [[struct.unpack_from("<ii", data, o) for o in range(offs[r], offs[r + 1], 8)] for r in range(4)]
+    assert got == dust.dust_block(blk.off, blk.bases) and got[1] and not got[0]
+    # -mdust now changes the seeds
+    out = dazzler.getDalignment(db, None, ["-s126", "-l500", "-mdust"], str(tmp_path))
+    assert out.endswith("x.x.las")

@@ -135,3 +135,32 @@ def test_batched_pileups_equal_per_pile_processing():
     fl = res["flank_las"].rec
     for p in range(4):
         assert len(set(fl["aread"][fl["bread"] == p].tolist())) >= 2
+
+
+def test_dust_mask_matches_oracle():
+    from dentist_b200 import dazzler
+    from oracle import dust
+    rng = np.random.default_rng(17)
+    seqs = []
+    for i in range(12):
+        s = rng.integers(0, 4, int(rng.integers(300, 3000)), dtype=np.uint8)
+        if i % 3 == 0:                       # plant a homopolymer run, a dinucleotide repeat and a short tandem
+            s[100:190] = 0
+            s[250:290] = np.tile([1, 2], 20)
+        if i % 4 == 1 and len(s) > 900:
+            s[700:820] = np.tile([0, 3, 3], 40)
+        seqs.append(s)
+    seqs.append(np.zeros(20, np.uint8)); seqs.append(np.zeros(0, np.uint8)); seqs.append(np.full(700, 2, np.uint8))
+    off = np.zeros(len(seqs) + 1, np.int64); off[1:] = np.cumsum([len(s) for s in seqs])
+    blk = synth.Block(off, np.concatenate(seqs))
+    g = dazzler.Block(blk.off, blk.bases)
+    for kw in (dict(), dict(window=32, threshold=1.5, minlen=40)):
+        got = dazzler.dbdust(g, **kw)
+        okw = dict(w=kw.get("window", 64), threshold=kw.get("threshold", 2.0), minlen=kw.get("minlen", 10))
+        exp = dust.dust_block(blk.off, blk.bases, **okw)
+        assert got == exp
+    d = dazzler.dbdust(g)
+    assert any(b <= 100 and e >= 190 for b, e in d[0]) and d[-1] == [(0, 700)] and d[-2] == [] and d[1] == []
+    # the mask plugs into the aligner exactly like `-mdust`
+    g2 = dazzler.Block(blk.off, blk.bases, mask=d)
+    assert g2.nreads == g.nreads
