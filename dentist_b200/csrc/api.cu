@@ -233,7 +233,7 @@ static int align_files(const char *dbA, const char *dbB, const char *const *opts
         dn_las_buf ab; memset(&ab, 0, sizeof ab);
         int rc = dn_align_host(&da, self ? &da : &db, &p, &ab);
         if (rc) return rc;
-        if (mapper) for (int64_t i = 0; i < ab.nrec; i++) ab.rec[i].flags |= DN_LAS_START | DN_LAS_BEST;
+        if (mapper) { rc = dn_las_chain_mapper(&ab, (int32_t)Bx.rlen.size(), 1000, 10000); if (rc) { dn_las_free(&ab); return rc; } }
         std::string pa = std::string(outdir) + "/" + A.name + "." + Bx.name + ".las";
         rc = dn_las_write(pa.c_str(), &ab);
         dn_las_free(&ab);
@@ -242,7 +242,7 @@ static int align_files(const char *dbA, const char *dbB, const char *const *opts
             dn_las_buf ba; memset(&ba, 0, sizeof ba);
             rc = dn_align_host(&db, &da, &p, &ba);
             if (rc) return rc;
-            if (mapper) for (int64_t i = 0; i < ba.nrec; i++) ba.rec[i].flags |= DN_LAS_START | DN_LAS_BEST;
+            if (mapper) { rc = dn_las_chain_mapper(&ba, (int32_t)A.rlen.size(), 1000, 10000); if (rc) { dn_las_free(&ba); return rc; } }
             std::string pb = std::string(outdir) + "/" + Bx.name + "." + A.name + ".las";
             rc = dn_las_write(pb.c_str(), &ba);
             dn_las_free(&ba);

@@ -103,6 +103,25 @@ int dn_compute_qvs_v(const int32_t *rlen, int32_t nreads, const dn_las_buf *las,
     });
 }
 
+int dn_las_chain_mapper(dn_las_buf *las, int32_t nb_reads, int32_t max_indel, int32_t max_gap) {
+    if (!las || nb_reads < 0) return fail(DN_ERR_INVALID, "null argument");
+    for (int64_t i = 0; i < las->nrec; i++)
+        if (las->rec[i].bread < 0 || las->rec[i].bread >= nb_reads) return fail(DN_ERR_INVALID, "contig id out of bounds");
+    std::lock_guard<std::mutex> lk(g_mu);
+    if (int rc = ensure_device()) return rc;
+    return guarded([&] {
+        cudaSetDevice(g_device); arena().reset();
+        DBuf<dn_las_record> d(las->nrec + 1);
+        if (las->nrec) {
+            DN_CUDA(cudaMemcpyAsync(d.p, las->rec, sizeof(dn_las_record) * las->nrec, cudaMemcpyHostToDevice, g_stream));
+            mapper_chain_device(d.p, las->nrec, nb_reads, max_indel, max_gap, g_stream);
+            DN_CUDA(cudaMemcpyAsync(las->rec, d.p, sizeof(dn_las_record) * las->nrec, cudaMemcpyDeviceToHost, g_stream));
+            DN_CUDA(cudaStreamSynchronize(g_stream));
+        }
+        return DN_OK;
+    });
+}
+
 void dn_seq_free(dn_seq_buf *b) { if (!b) return; hcache_free(b->off); hcache_free(b->bases); memset(b, 0, sizeof *b); }
 
 int dn_consensus(const dn_block *db, const dn_las_buf *las, const int32_t *reads, int32_t nreads, dn_seq_buf *out) {

@@ -233,3 +233,62 @@ void launch_cons_write(int64_t ncols, const int32_t *nemit, const int32_t *eoff,
 }
 
 }  // namespace dn
+
+// ------------------------------------------------------------------------------- mapper chains
+// damapper reports, per read, chains of local alignments (START / NEXT flags, BEST on the top chain;
+// decoded by DENTIST at dazzler.d:1738-1755 and packed into AlignmentChains at :708-743).
+// Specification (oracle/chain_oracle.py; DAMAPPER is absent -> parity unpinned): records are in LAsort
+// order; record i+1 CONTINUES the chain of record i when both have the same (aread, bread, comp), both
+// coordinates advance (abpos, aepos, bbpos, bepos all strictly larger), the gap difference
+// |(ab'-ae) - (bb'-be)| <= max_indel and max(|ab'-ae|, |bb'-be|) <= max_gap.  A chain's score is the sum
+// of its (aepos-abpos); per B read the chain with the highest score (ties: first in file order) is BEST.
+namespace dn {
+namespace {
+
+__device__ __forceinline__ bool continues(const dn_las_record &x, const dn_las_record &y, int max_indel, int max_gap) {
+    if (x.aread != y.aread || x.bread != y.bread || ((x.flags ^ y.flags) & DN_LAS_COMP)) return false;
+    if (!(y.abpos > x.abpos && y.aepos > x.aepos && y.bbpos > x.bbpos && y.bepos > x.bepos)) return false;
+    const int ga = y.abpos - x.aepos, gb = y.bbpos - x.bepos;
+    const int indel = ga > gb ? ga - gb : gb - ga;
+    const int mg = max(ga < 0 ? -ga : ga, gb < 0 ? -gb : gb);
+    return indel <= max_indel && mg <= max_gap;
+}
+
+// pass 1: chain starts; one thread per chain start walks its chain, scores it, competes for its read
+__global__ void __launch_bounds__(256) k_chain_score(const dn_las_record *__restrict__ rec, int64_t n, int max_indel, int max_gap,
+                                                     unsigned long long *__restrict__ best /* per B read */) {
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    if (i > 0 && continues(rec[i - 1], rec[i], max_indel, max_gap)) return;         // not a chain start
+    long long score = 0; int64_t j = i;
+    for (;;) { score += rec[j].aepos - rec[j].abpos; if (j + 1 < n && continues(rec[j], rec[j + 1], max_indel, max_gap)) j++; else break; }
+    // highest score wins, ties: lowest start index  ->  pack (score, ~index)
+    const unsigned long long packed = ((unsigned long long)score << 32) | (unsigned long long)(0xffffffffu - (unsigned)i);
+    atomicMax(&best[rec[i].bread], packed);
+}
+
+__global__ void __launch_bounds__(256) k_chain_flags(dn_las_record *__restrict__ rec, int64_t n, int max_indel, int max_gap,
+                                                     const unsigned long long *__restrict__ best) {
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const bool cont = i > 0 && continues(rec[i - 1], rec[i], max_indel, max_gap);
+    unsigned f = rec[i].flags & ~(DN_LAS_START | DN_LAS_NEXT | DN_LAS_BEST);
+    if (cont) f |= DN_LAS_NEXT;
+    else {
+        f |= DN_LAS_START;
+        const unsigned long long b = best[rec[i].bread];
+        if ((unsigned)(0xffffffffu - (unsigned)(b & 0xffffffffu)) == (unsigned)i) f |= DN_LAS_BEST;
+    }
+    rec[i].flags = f;
+}
+
+}  // namespace
+
+void mapper_chain_device(dn_las_record *rec, int64_t n, int nb_reads, int max_indel, int max_gap, cudaStream_t s) {
+    if (n == 0) return;
+    DBuf<unsigned long long> best(nb_reads + 1); best.zero(s);
+    DN_LAUNCH(k_chain_score, (unsigned)((n + 255) / 256), 256, 0, s, (const dn_las_record *)rec, n, max_indel, max_gap, best.p);
+    DN_LAUNCH(k_chain_flags, (unsigned)((n + 255) / 256), 256, 0, s, rec, n, max_indel, max_gap, (const unsigned long long *)best.p);
+}
+
+}  // namespace dn

@@ -15,6 +15,8 @@ void las_filter_device(const dn_las_record *rec, const int64_t *toff, int64_t n,
                        const int32_t *blen, int allowance, dn_las_record *orec, int64_t *otoff, int64_t *n_out, cudaStream_t s);
 void qv_device(const int32_t *rlen, int nreads, const dn_las_record *rec, int64_t nla, const int64_t *toff, const uint16_t *trace,
                int ts, int cov, const int32_t *cov_per_read, const int64_t *qoff, uint8_t *qv, cudaStream_t s);
+// damapper-style chain flags (START/NEXT/BEST) on records in LAsort order
+void mapper_chain_device(dn_las_record *rec, int64_t n, int nb_reads, int max_indel, int max_gap, cudaStream_t s);
 void launch_cons_tasks(const dn_las_record *rec, const int64_t *toff, const uint16_t *trace, const int32_t *vla, int nvla,
                        const int64_t *task_off, int ts, ConsTask *tasks, cudaStream_t s);
 int cons_vote_threads();

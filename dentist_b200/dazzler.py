@@ -220,6 +220,12 @@ class Las:
         self._refresh()
         return self
 
+    def chainMapper(self, nb_reads, max_indel=1000, max_gap=10000):
+        """damapper-style START/NEXT/BEST flags (decoded at dazzler.d:1738-1755)."""
+        _lib.check(_lib.lib().dn_las_chain_mapper(C.byref(self._buf), int(nb_reads), int(max_indel), int(max_gap)))
+        self._refresh()
+        return self
+
     def write(self, path):
         _lib.check(_lib.lib().dn_las_write(path.encode(), C.byref(self._buf)))
 

@@ -165,6 +165,11 @@ typedef struct dn_seq_buf { int32_t nseq; int64_t *off; uint8_t *bases; } dn_seq
 int dn_consensus(const dn_block *db, const dn_las_buf *las, const int32_t *reads, int32_t nreads, dn_seq_buf *out);
 void dn_seq_free(dn_seq_buf *buf);
 
+/* damapper-style chain flags: START on the first record of a chain, NEXT on continuations, BEST on the
+ * top-scoring chain of every B read -- the flags DENTIST decodes at dazzler.d:1738-1755 and packs into
+ * AlignmentChains at :708-743.  `las` must be in LAsort order (as dn_align_blocks returns it). */
+int dn_las_chain_mapper(dn_las_buf *las, int32_t nb_reads, int32_t max_indel, int32_t max_gap);
+
 /* dbdust(db, opts)  dazzler.d:3815-3818 (`DBdust -w -t -m`): low-complexity intervals of every read of a
  * resident block in the reference's mask-track layout (dazzler.d:4943-5052): *anno = nreads+1 int64
  * byte offsets into *data, *data = int32 (begin,end) pairs.  Free both with dn_free.  Feed them to

@@ -31,7 +31,7 @@ def test_getDamapping_writes_both_las_files(tmp_path):
     for f in ("aread", "bread", "abpos", "aepos", "bbpos", "bepos", "diffs", "tlen"):
         assert np.array_equal(rec[f], mrec[f]), f
     assert np.concatenate([t.reshape(-1) for t in traces]).tolist() == np.minimum(mtr, 255).tolist()
-    assert all(int(f) & las.START for f in rec["flags"])              # chain flags set -> AlignmentChainPacker accepts it
+    assert all(int(f) & (las.START | las.NEXT) for f in rec["flags"])              # chain flags set -> AlignmentChainPacker accepts it
     assert len(las.chains(rec)) == len(rec)
     # transposed file exists, is sorted by read and has uint8 traces
     ts2, rec2, tr2 = las.decode(open(str(tmp_path / "reads.ref.las"), "rb").read())

@@ -164,3 +164,33 @@ def test_dust_mask_matches_oracle():
     # the mask plugs into the aligner exactly like `-mdust`
     g2 = dazzler.Block(blk.off, blk.bases, mask=d)
     assert g2.nreads == g.nreads
+
+
+def test_mapper_chain_flags_match_oracle_and_pack_into_chains():
+    from dentist_b200 import dazzler
+    from oracle import chain_oracle, las as olas
+    # reads with a large insertion in the middle align as two colinear local alignments -> one chain
+    sc = synth.make_scaffolds(1, 150000, 401, n_repeats=1, repeat_copies=3)
+    ref, _ = synth.contigs_from(sc, synth.make_gaps(sc, 1, 402))
+    reads, _ = synth.simulate_reads(sc, 3, 9000, 2500, 0.12, 403)
+    rng = np.random.default_rng(5)
+    seqs = []
+    for r in range(reads.nreads):
+        s = reads.read(r)
+        if r % 3 == 0 and len(s) > 5000:           # splice 300 random bases into the middle
+            m = len(s) // 2
+            s = np.concatenate([s[:m], rng.integers(0, 4, 300, dtype=np.uint8), s[m:]])
+        seqs.append(s)
+    off = np.zeros(len(seqs) + 1, np.int64); off[1:] = np.cumsum([len(s) for s in seqs])
+    rd = synth.Block(off, np.concatenate(seqs))
+    ga, gb = dazzler.Block(ref.off, ref.bases), dazzler.Block(rd.off, rd.bases)
+    las = dazzler.align(ga, gb, tspace=100, minlen=500)
+    before = las.rec.copy()
+    las.chainMapper(rd.nreads)
+    exp = chain_oracle.mapper_chain_flags(before)
+    assert np.array_equal(las.rec["flags"], exp)
+    groups = olas.chains(las.rec)                      # AlignmentChainPacker accepts it (dazzler.d:708-743)
+    assert sum(len(g) for g in groups) == len(las) and any(len(g) > 1 for g in groups)
+    # exactly one BEST chain per mapped read
+    starts = las.rec[(las.rec["flags"] & olas.BEST) != 0]
+    assert sorted(starts["bread"].tolist()) == sorted(set(las.rec["bread"].tolist()))
