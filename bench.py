@@ -28,7 +28,7 @@ from dentist_b200 import synth  # noqa: E402
 
 WORKLOAD = "synthetic 10 Mbp assembly, 100 gaps, 20x PacBio-like 10 kb reads (BASELINE.json configs[1])"
 PARAMS = dict(tspace=100, minlen=1000, e=0.7)          # damapper -C -e0.7, default -s100 (commandline.d:2943-2955)
-ORC = dict(k=14, w=6, h=35, t=32, cdiff=20, xdrop=300, wmax=62, rounds=3, poolmul=64)
+ORC = dict(k=14, w=6, h=35, t=32, cdiff=20, xdrop=300, wmax=30, rounds=3, poolmul=64)
 
 
 def make_workload(scale, rank):

@@ -83,7 +83,7 @@ uint64_t dn_launch_count(void) { return dn::g_launches.load(); }
 void dn_align_params_default(dn_align_params *p) {
     memset(p, 0, sizeof *p);
     p->k = 14; p->w = 6; p->h = 35; p->t = 32; p->tspace = 100; p->minlen = 1000; p->e = 0.7;
-    p->identity = 0; p->self_block = 0; p->rounds = 3; p->xdrop = 300; p->wmax = 62; p->poolmul = 64;
+    p->identity = 0; p->self_block = 0; p->rounds = 3; p->xdrop = 300; p->wmax = 30; p->poolmul = 64;
 }
 
 void dn_las_free(dn_las_buf *b) {

@@ -32,7 +32,7 @@ struct DevBlock {
 };
 
 struct AlignParams {
-    int k = 14, w = 6, h = 35, t = 32, tspace = 100, minlen = 500, cdiff = 20, xdrop = 300, wmax = 62,
+    int k = 14, w = 6, h = 35, t = 32, tspace = 100, minlen = 500, cdiff = 20, xdrop = 300, wmax = 30,
         rounds = 3, self = 0, poolmul = 64, join_mode = 0;   // join_mode: 0 auto, 1 sorted merge, 2 index lookup
 };
 

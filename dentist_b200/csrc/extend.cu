@@ -227,6 +227,136 @@ __global__ void __launch_bounds__(EXT_WARPS * 32) k_extend(const Seed *__restric
     }
 }
 
+// Register-resident variant for wmax <= 30 (the default): the window never exceeds 32 diagonals, lane l
+// owns the diagonal congruent to l mod 32, and V / T / R live in registers; neighbours are one shuffle
+// away.  No shared memory, no modular addressing, one slot per lane.  Same specification, same results.
+__global__ void __launch_bounds__(EXT_WARPS * 32) k_extend32(const Seed *__restrict__ seeds, int ntasks, ExtGeom G,
+                                                             const int64_t *__restrict__ tile_off, int2 *__restrict__ tiles,
+                                                             ExtOut *__restrict__ outs, int4 *__restrict__ pool_all,
+                                                             int64_t pool_stride, int *__restrict__ counter) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const u32 FULL = 0xffffffffu;
+    int4 *pool = pool_all + (int64_t)(blockIdx.x * EXT_WARPS + warp) * pool_stride;
+    const int ts = G.ts, C = G.cdiff, X = G.xdrop, WM = G.wmax;
+    const int lane_l = (lane + 31) & 31, lane_r = (lane + 1) & 31;
+
+    for (;;) {
+        int task = 0;
+        if (lane == 0) task = atomicAdd(counter, 1);
+        task = __shfl_sync(FULL, task, 0);
+        if (task >= ntasks) break;
+        const Seed sd = seeds[task >> 1];
+        const Task tk = make_task(sd, task & 1, G);
+        const int la = tk.la, lb = tk.lb, firstT = tk.firstT;
+        const int poolcap = G.poolmul * (ext_span(la, lb) / ts + 4);
+        auto NB = [&](int i) -> int { return i >= firstT ? (int)__umulhi((u32)(i - firstT), G.ts_magic) + 1 : 0; };
+
+        int npool = 0, lo = 0, hi = 0, d = 0;
+        int V = NEGV, T = -1, R = 0;                          // this lane's diagonal
+        int bS = NEGS, bi = 0, bk = 0, bd = 0, bT = -1;     // lane-local best
+        int gbest;
+        {   // wave 0 (uniform): diagonal 0 lives in lane 0
+            const int i = slide(tk.A, tk.ga, tk.B, tk.gb, la < lb ? la : lb);
+            const int n = NB(i);
+            if (n > poolcap) {
+                if (lane == 0) outs[task] = ExtOut{0, 0, 0, 0};
+                continue;
+            }
+            if (lane == 0) {
+                int t = -1;
+                for (int q = 1; q <= n; q++) { pool[npool] = make_int4(t, firstT + (q - 1) * ts, 0, q); t = npool++; }
+                V = i; T = t; R = firstT + n * ts;
+                bS = 3 * (2 * i); bi = i; bk = 0; bd = 0; bT = t;
+            }
+            npool = n;
+            gbest = 3 * (2 * i);
+            if (i == la || i == lb) { lo = 1; hi = 0; }
+            __syncwarp();
+        }
+        while (lo <= hi) {
+            d++;
+            const int nlo = lo - 1, nhi = hi + 1;
+            const int k = nlo + ((lane - nlo) & 31);            // the diagonal = lane (mod 32) inside the new window
+            const int Vl = __shfl_sync(FULL, V, lane_l), Vr = __shfl_sync(FULL, V, lane_r);
+            int i = NEGV, src = lane;
+            if (k <= nhi) {
+                const int vs = (k >= lo && k <= hi) ? V : NEGV;
+                const int vd = (k - 1 >= lo) ? Vl : NEGV;
+                const int vi = (k + 1 <= hi) ? Vr : NEGV;
+                if (vs > NEGV) i = vs + 1;
+                if (vd > NEGV && vd + 1 > i) { i = vd + 1; src = lane_l; }
+                if (vi > NEGV && vi > i) { i = vi; src = lane_r; }
+            }
+            int cT = __shfl_sync(FULL, T, src), cR = __shfl_sync(FULL, R, src);
+            int cn = 0;
+            if (i > NEGV) {
+                const int j = i - k;
+                if (i > la || j > lb || j < 0) i = NEGV;
+                else {
+                    i += slide(tk.A, tk.ga + i, tk.B, tk.gb + j, min(la - i, lb - j));
+                    while (i >= cR) { cn++; cR += ts; }
+                }
+            }
+            if (__any_sync(FULL, cn != 0)) {
+                const int need = __reduce_add_sync(FULL, cn);
+                if (npool + need > poolcap) break;              // pool exhausted: stop before this wave
+                int pre = cn;
+#pragma unroll
+                for (int o = 1; o < 32; o <<= 1) { int t = __shfl_up_sync(FULL, pre, o); if (lane >= o) pre += t; }
+                int at = npool + pre - cn;
+                for (int q = cn; q >= 1; q--) { pool[at] = make_int4(cT, cR - q * ts - k, d, 0); cT = at++; }
+                npool += need;
+            }
+            const int S = i > NEGV ? 3 * (2 * i - k) - C * d : NEGS;
+            if (S > bS) { bS = S; bi = i; bk = k; bd = d; bT = cT; }
+            const int waveS = __reduce_max_sync(FULL, S);
+            gbest = max(gbest, waveS);
+            const bool alive = i > NEGV && !(S < gbest - X || i == la || i - k == lb);
+            if (k <= nhi) { V = alive ? i : NEGV; T = cT; R = cR; }
+            const u32 m = __ballot_sync(FULL, alive);
+            if (m == 0u) break;
+            const u32 rot = __funnelshift_r(m, m, nlo & 31);    // bit j <-> diagonal nlo + j
+            int alo = nlo + __ffs(rot) - 1, ahi = nlo + 31 - __clz(rot);
+            if (ahi - alo + 1 > WM) {
+                const u32 mb = __ballot_sync(FULL, S == waveS);
+                const u32 rb = __funnelshift_r(mb, mb, nlo & 31);
+                const int wavek = nlo + __ffs(rb) - 1;
+                int l2 = wavek - (WM / 2 - 1); if (l2 < alo) l2 = alo;
+                int h2 = l2 + WM - 1; if (h2 > ahi) h2 = ahi;
+                l2 = h2 - WM + 1; if (l2 < alo) l2 = alo;
+                alo = l2; ahi = h2;
+            }
+            lo = alo; hi = ahi;
+        }
+        // winner: max S, then min d, then min k
+        const int mS = __reduce_max_sync(FULL, bS);
+        const int md = __reduce_min_sync(FULL, bS == mS ? bd : (1 << 30));
+        const int mk = __reduce_min_sync(FULL, (bS == mS && bd == md) ? bk : (1 << 30));
+        const u32 win = __ballot_sync(FULL, bS == mS && bd == md && bk == mk);
+        const int wl = __ffs(win) - 1;
+        const int besti = __shfl_sync(FULL, bi, wl), bestk = __shfl_sync(FULL, bk, wl);
+        const int bestd = __shfl_sync(FULL, bd, wl), bestT = __shfl_sync(FULL, bT, wl);
+        __syncwarp();
+        if (lane == 0) {
+            int2 *tl = tiles + tile_off[task];
+            int n = NB(besti);
+            int lastj = 0, lastd = 0;
+            int4 curr = bestT >= 0 ? pool[bestT] : make_int4(-1, 0, 0, 0);
+            if (bestT >= 0) { lastj = curr.y; lastd = curr.z; }
+            for (int q = n; q >= 1; q--) {
+                int pj = 0, pd = 0; int4 pr = make_int4(-1, 0, 0, 0);
+                if (curr.x >= 0) { pr = pool[curr.x]; pj = pr.y; pd = pr.z; }
+                tl[q - 1] = make_int2(curr.y - pj, curr.z - pd);
+                curr = pr;
+            }
+            const int lastB = n > 0 ? firstT + (n - 1) * ts : 0;
+            if (besti > lastB) { tl[n] = make_int2((besti - bestk) - lastj, bestd - lastd); n++; }
+            outs[task] = ExtOut{besti, besti - bestk, bestd, n};
+        }
+        __syncwarp();
+    }
+}
+
 // ---------------------------------------------------------------- candidate assembly
 
 __global__ void __launch_bounds__(256) k_combine(const Seed *__restrict__ seeds, int nseeds, ExtGeom G, int minlen,
@@ -413,7 +543,8 @@ void launch_task_caps(const Seed *seeds, int nseeds, ExtGeom G, u32 *caps, cudaS
 void launch_extend(const Seed *seeds, int nseeds, ExtGeom G, const int64_t *tile_off, int2 *tiles, ExtOut *outs,
                    int4 *pool, int64_t pool_stride, int nwarps_total, int *counter, cudaStream_t s) {
     int ctas = nwarps_total / EXT_WARPS;
-    DN_LAUNCH(k_extend, ctas, EXT_WARPS * 32, 0, s, seeds, 2 * nseeds, G, tile_off, tiles, outs, pool, pool_stride, counter);
+    if (G.wmax <= 30) DN_LAUNCH(k_extend32, ctas, EXT_WARPS * 32, 0, s, seeds, 2 * nseeds, G, tile_off, tiles, outs, pool, pool_stride, counter);
+    else DN_LAUNCH(k_extend, ctas, EXT_WARPS * 32, 0, s, seeds, 2 * nseeds, G, tile_off, tiles, outs, pool, pool_stride, counter);
 }
 void launch_combine(const Seed *seeds, int nseeds, ExtGeom G, int minlen, const int64_t *tile_off, const int2 *tiles,
                     const ExtOut *outs, Cand *cand_all, int32_t *valid, u32 *ntl, cudaStream_t s) {

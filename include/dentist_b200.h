@@ -95,7 +95,7 @@ typedef struct dn_align_params {
     int32_t self_block; /* A and B are the same block (daligner X X): skip aread == bread unless -I */
     int32_t rounds;     /* seed/extend rounds                          default 3   */
     int32_t xdrop;      /* extension x-drop                            default 300 */
-    int32_t wmax;       /* live diagonals per wave (<= 62)             default 62  */
+    int32_t wmax;       /* live diagonals per wave (<= 62)             default 30  */
     int32_t poolmul;    /* trace record pool multiplier                default 64  */
     int32_t join_mode;  /* 0 auto | 1 sort both tuple lists and merge | 2 look B k-mers up in the sorted A index */
 } dn_align_params;

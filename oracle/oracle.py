@@ -40,7 +40,7 @@ LA_DTYPE = np.dtype([("tlen", "<i4"), ("diffs", "<i4"), ("abpos", "<i4"), ("bbpo
                      ("aepos", "<i4"), ("bepos", "<i4"), ("flags", "<u4"), ("aread", "<i4"),
                      ("bread", "<i4"), ("toff", "<i4")])
 
-DEFAULTS = dict(k=14, w=6, h=35, t=32, tspace=100, minlen=500, cdiff=20, xdrop=300, wmax=62, rounds=3,
+DEFAULTS = dict(k=14, w=6, h=35, t=32, tspace=100, minlen=500, cdiff=20, xdrop=300, wmax=30, rounds=3,
                 self_=0, poolmul=64)
 
 

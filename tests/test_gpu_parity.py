@@ -7,7 +7,7 @@ from dentist_b200 import synth
 
 pytestmark = pytest.mark.gpu
 
-ORC = dict(k=14, w=6, h=35, t=32, cdiff=20, xdrop=300, wmax=62, rounds=3, poolmul=64)
+ORC = dict(k=14, w=6, h=35, t=32, cdiff=20, xdrop=300, wmax=30, rounds=3, poolmul=64)
 
 
 def run_both(A, B, tspace, minlen, self_block=0, a_mask=None, b_mask=None, **over):
@@ -71,6 +71,16 @@ def test_both_join_strategies_match_oracle(join_mode):
     sc = synth.make_scaffolds(1, 20000, 12, n_repeats=0)
     pile, _ = synth.simulate_reads(sc, 8, 6000, 1500, 0.13, 13)
     orc, gpu = run_both(pile, pile, 126, 500, self_block=1, join_mode=join_mode)
+    assert_same(orc, gpu)
+
+
+@pytest.mark.parametrize("wmax,xdrop", [(62, 300), (40, 600), (12, 300), (30, 900)])
+def test_window_cap_variants_match_oracle(wmax, xdrop):
+    """wmax > 30 runs the shared-memory two-slot kernel, wmax <= 30 the register-resident one; tight caps and
+    wide x-drops exercise the window clamp."""
+    ref, reads = small_case(17, cov=3)
+    orc, gpu = run_both(ref, reads, 100, 500, wmax=wmax, xdrop=xdrop)
+    assert len(orc[0]) > 30
     assert_same(orc, gpu)
 
 
