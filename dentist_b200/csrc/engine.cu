@@ -140,11 +140,13 @@ void align_blocks(const DevBlock &A, const DevBlock &B, const AlignParams &P, Ho
         // B's tuples are never materialised: count, scan, emit straight from the packed sequence
         const int64_t nwB = nB >> 4;
         DBuf<u32> wcnt(2 * nwB); DBuf<int64_t> woff(2 * nwB);
+        DBuf<u32> kbits((1u << 28) / 32); kbits.zero(s);
+        DN_LAUNCH(k_kmer_bitmap, (unsigned)((nA + 255) / 256), 256, 0, s, (const u64 *)sa, nA, kbits.p);
         for (int st = 0; st < 2; st++) {
             const u32 *mb = B.has_mask ? (st ? B.mask_rc.p : B.mask.p) : nullptr;
             DN_LAUNCH(k_lookup_count, (unsigned)((nwB + 255) / 256), 256, 0, s, (const u32 *)(st ? B.rc.p : B.fwd.p), mb,
                       (const int64_t *)B.off.p, (const int32_t *)B.len.p, (const int32_t *)B.chunk2read.p, nwB, k,
-                      (const u64 *)sa, (const u32 *)tbl.p, sh, P.t, JG, wcnt.p + st * nwB);
+                      (const u64 *)sa, (const u32 *)tbl.p, sh, P.t, (const u32 *)kbits.p, JG, wcnt.p + st * nwB);
         }
         exclusive_scan_u32_to_i64(wcnt.p, woff.p, 2 * nwB, dtotal.p, s);
         H = d2h_scalar(dtotal.p, s);
@@ -155,7 +157,7 @@ void align_blocks(const DevBlock &A, const DevBlock &B, const AlignParams &P, Ho
                 const u32 *mb = B.has_mask ? (st ? B.mask_rc.p : B.mask.p) : nullptr;
                 DN_LAUNCH(k_lookup_emit, (unsigned)((nwB + 255) / 256), 256, 0, s, (const u32 *)(st ? B.rc.p : B.fwd.p), mb,
                           (const int64_t *)B.off.p, (const int32_t *)B.len.p, (const int32_t *)B.chunk2read.p, nwB, k,
-                          (const u64 *)sa, (const u32 *)tbl.p, sh, P.t, (const u32 *)(wcnt.p + st * nwB),
+                          (const u64 *)sa, (const u32 *)tbl.p, sh, P.t, (const u32 *)kbits.p, (const u32 *)(wcnt.p + st * nwB),
                           (const int64_t *)(woff.p + st * nwB), st, JG, hits.p);
             }
         abytes += 2 * (nB / 4) * 2 + 2 * nwB * (4 + 4 + 8 + 8 + 4) + 16 * H;   // packed B read twice per strand, word counts/offsets, hits

@@ -251,6 +251,23 @@ __global__ void __launch_bounds__(256) k_join_emit(const u64 *__restrict__ ta, c
 // in the A index and (pass 1) counts / (pass 2) emits the hits.  Output-identical to the
 // sorted-merge join because the hit list is totally ordered by the sort that follows.
 
+// Presence bitmap over k-mers (bit = kmer mod 2^28; exact for k <= 14): 32 MB, L2-resident.  Four out of
+// five read k-mers carry a sequencing error and occur nowhere in A; the bitmap rejects them with ONE
+// sector read instead of the table + list walk.
+__global__ void __launch_bounds__(256) k_kmer_bitmap(const u64 *__restrict__ ta, int64_t na, u32 *__restrict__ bits) {
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= na) return;
+    const u32 km = (u32)(ta[i] >> 32);
+    if (km == 0xffffffffu) return;
+    if (i > 0 && (u32)(ta[i - 1] >> 32) == km) return;          // one atomic per distinct k-mer
+    const u32 b = km & 0x0fffffffu;
+    atomicOr(&bits[b >> 5], 1u << (b & 31));
+}
+__device__ __forceinline__ bool kmer_present(const u32 *__restrict__ bits, u32 km) {
+    const u32 b = km & 0x0fffffffu;
+    return (bits[b >> 5] >> (b & 31)) & 1u;
+}
+
 struct WordKmers { u64 v; u64 mwin; int p0, L, r; };
 
 __device__ __forceinline__ WordKmers load_word(const u32 *__restrict__ seq, const u32 *__restrict__ maskbits,
@@ -279,17 +296,23 @@ __global__ void __launch_bounds__(256) k_lookup_count(const u32 *__restrict__ se
                                                       const int64_t *__restrict__ off, const int32_t *__restrict__ len,
                                                       const int32_t *__restrict__ c2r, int64_t nwords, int k,
                                                       const u64 *__restrict__ ta, const u32 *__restrict__ tbl, int sh, int tcap,
-                                                      JoinGeom G, u32 *__restrict__ wcnt) {
+                                                      const u32 *__restrict__ kbits, JoinGeom G, u32 *__restrict__ wcnt) {
     int64_t wi = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (wi >= nwords) return;
     const WordKmers w = load_word(seq, maskbits, off, len, c2r, wi);
     const u64 kmask = (1ull << (2 * k)) - 1ull, mk = (1ull << k) - 1ull;
     const bool restricted = G.self || G.a_group;
     u32 total = 0;
-#pragma unroll 4
-    for (int jj = 0; jj < 16; jj++) {
-        if ((w.p0 + jj + k <= w.L) && (((w.mwin >> jj) & mk) == 0)) {
-            u32 s, c; a_range_fwd(ta, tbl, sh, (u32)((w.v >> (2 * jj)) & kmask), tcap, s, c);
+    u32 present = 0;                                  // 16 independent bitmap probes first (memory-level parallelism)
+#pragma unroll
+    for (int jj = 0; jj < 16; jj++)
+        if ((w.p0 + jj + k <= w.L) && (((w.mwin >> jj) & mk) == 0) && kmer_present(kbits, (u32)((w.v >> (2 * jj)) & kmask)))
+            present |= 1u << jj;
+    while (present) {
+        const int jj = __ffs(present) - 1; present &= present - 1;
+        {
+            const u32 km = (u32)((w.v >> (2 * jj)) & kmask);
+            u32 s, c; a_range_fwd(ta, tbl, sh, km, tcap, s, c);
             if (restricted) {                     // self pairs / pairs across pile-ups are never emitted
                 for (u32 x = 0; x < c; x++) {
                     const int ar = read_of(G.a_c2r, G.a_off, (int64_t)(u32)ta[s + x]);
@@ -305,7 +328,8 @@ __global__ void __launch_bounds__(256) k_lookup_emit(const u32 *__restrict__ seq
                                                      const int64_t *__restrict__ off, const int32_t *__restrict__ len,
                                                      const int32_t *__restrict__ c2r, int64_t nwords, int k,
                                                      const u64 *__restrict__ ta, const u32 *__restrict__ tbl, int sh, int tcap,
-                                                     const u32 *__restrict__ wcnt, const int64_t *__restrict__ woff, int strand,
+                                                     const u32 *__restrict__ kbits, const u32 *__restrict__ wcnt,
+                                                     const int64_t *__restrict__ woff, int strand,
                                                      JoinGeom G, ulonglong2 *__restrict__ hits) {
     int64_t wi = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (wi >= nwords) return;
@@ -314,9 +338,15 @@ __global__ void __launch_bounds__(256) k_lookup_emit(const u32 *__restrict__ seq
     const u64 kmask = (1ull << (2 * k)) - 1ull, mk = (1ull << k) - 1ull;
     const u64 bs = (u64)strand * G.nb_reads + w.r;
     int64_t o = woff[wi];
-    for (int jj = 0; jj < 16; jj++) {
-        if (!((w.p0 + jj + k <= w.L) && (((w.mwin >> jj) & mk) == 0))) continue;
-        u32 s, c; a_range_fwd(ta, tbl, sh, (u32)((w.v >> (2 * jj)) & kmask), tcap, s, c);
+    u32 present = 0;
+#pragma unroll
+    for (int jj = 0; jj < 16; jj++)
+        if ((w.p0 + jj + k <= w.L) && (((w.mwin >> jj) & mk) == 0) && kmer_present(kbits, (u32)((w.v >> (2 * jj)) & kmask)))
+            present |= 1u << jj;
+    while (present) {                                 // ascending jj: hits of a word stay ordered by bpos
+        const int jj = __ffs(present) - 1; present &= present - 1;
+        const u32 km = (u32)((w.v >> (2 * jj)) & kmask);
+        u32 s, c; a_range_fwd(ta, tbl, sh, km, tcap, s, c);
         const int bpos = w.p0 + jj;
         for (u32 x = 0; x < c; x++) {
             int64_t ga = (int64_t)(u32)ta[s + x];
