@@ -125,7 +125,7 @@ void align_blocks(const DevBlock &A, const DevBlock &B, const AlignParams &P, Ho
     SeedGeom SG{d_dbase.p, A.nreads, gdbits};
 
     const int aposbits = bits_for((uint64_t)A.maxlen);
-    bool segsorted = false;
+    bool segsorted = false, seg_in_hits2 = false;
     // ---- K3: join ------------------------------------------------------------------------------
     int tbits = bits_for((uint64_t)nA) + (lookup ? -1 : 1); if (tbits < 16) tbits = 16; if (tbits > 2 * k) tbits = 2 * k;
     const int sh = 2 * k - tbits; const u32 nq = 1u << tbits;
@@ -170,11 +170,12 @@ void align_blocks(const DevBlock &A, const DevBlock &B, const AlignParams &P, Ho
             DN_CUDA(cudaMemcpyAsync(hso.data(), seg_off.p, sizeof(int64_t) * (nseg + 1), cudaMemcpyDeviceToHost, s));
             DN_CUDA(cudaStreamSynchronize(s));
             std::vector<int32_t> cls[3]; const int caps[3] = {2048, 8192, 16384};
+            const bool radix = gdbits <= 32 && !getenv("DN_BITONIC");     // stable radix by gd: hits -> hits2
             std::vector<int> big;                       // segments too large for shared memory
             int64_t nbig = 0;
             for (int i = 0; i < nseg; i++) {
                 const int64_t len = hso[i + 1] - hso[i];
-                if (len < 2) continue;
+                if (len < (radix ? 1 : 2)) continue;              // the radix variant writes to the other buffer: copy singletons too
                 int c = 0; while (c < 3 && len > caps[c]) c++;
                 if (c == 3) { big.push_back(i); nbig += len; } else cls[c].push_back(i);
             }
@@ -190,8 +191,11 @@ void align_blocks(const DevBlock &A, const DevBlock &B, const AlignParams &P, Ho
                     if (cls[c].empty()) continue;
                     DBuf<int32_t> lst(cls[c].size());
                     DN_CUDA(cudaMemcpyAsync(lst.p, cls[c].data(), sizeof(int32_t) * cls[c].size(), cudaMemcpyHostToDevice, s));
-                    launch_segsort(hits.p, seg_off.p, lst.p, (int)cls[c].size(), caps[c], gdbits, aposbits, s);
+                    if (radix) launch_segsort_radix(hits.p, hits2.p, seg_off.p, lst.p, (int)cls[c].size(), caps[c], gdbits, s);
+                    else launch_segsort(hits.p, seg_off.p, lst.p, (int)cls[c].size(), caps[c], gdbits, aposbits, s);
                 }
+                ulonglong2 *sorted = radix ? hits2.p : hits.p;
+
                 if (!big.empty()) {
                     // the few oversized segments: gather, radix sort by (bs, gd, apos), copy back range by range
                     DBuf<ulonglong2> t1(nbig), t2(nbig);
@@ -205,11 +209,11 @@ void align_blocks(const DevBlock &A, const DevBlock &B, const AlignParams &P, Ho
                     o = 0;
                     for (int i : big) {
                         const int64_t len = hso[i + 1] - hso[i];
-                        DN_CUDA(cudaMemcpyAsync(hits.p + hso[i], r + o, 16 * len, cudaMemcpyDeviceToDevice, s)); o += len;
+                        DN_CUDA(cudaMemcpyAsync(sorted + hso[i], r + o, 16 * len, cudaMemcpyDeviceToDevice, s)); o += len;
                     }
                 }
                 DN_CUDA(cudaStreamSynchronize(s));      // cls[] vectors are read by the async copies above
-                segsorted = true;
+                segsorted = true; seg_in_hits2 = radix;
                 abytes += 32 * H + 8ll * nseg;
             }
         }
@@ -236,7 +240,7 @@ void align_blocks(const DevBlock &A, const DevBlock &B, const AlignParams &P, Ho
     ta.release(); ta2.release(); tbl.release();
 
     // ---- hit sort: by apos, then stably by (bread, strand, aread, diagonal) -------------------
-    ulonglong2 *hs = hits.p, *ho = hits2.p;
+    ulonglong2 *hs = seg_in_hits2 ? hits2.p : hits.p, *ho = seg_in_hits2 ? hits.p : hits2.p;
     if (!segsorted) {
         hs = radix_sort_rec16(hits.p, hits2.p, H, 1, 0, aposbits, s);
         ho = hs == hits.p ? hits2.p : hits.p;

@@ -54,6 +54,9 @@ void launch_seg_offsets(const int64_t *woff, const int64_t *b_off, int nr, int64
 void launch_segsort(ulonglong2 *hits, const int64_t *seg_off, const int32_t *seglist, int nseg, int cap, int gdbits, int aposbits,
                     cudaStream_t s);
 
+void launch_segsort_radix(const ulonglong2 *in, ulonglong2 *out, const int64_t *seg_off, const int32_t *seglist, int nseg, int cap,
+                          int gdbits, cudaStream_t s);
+
 // extension stage (extend.cu)
 struct ExtGeom {
     const u32 *a_fwd, *a_rc, *b_fwd, *b_rc;

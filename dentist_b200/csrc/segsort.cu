@@ -62,6 +62,87 @@ __global__ void __launch_bounds__(1024) k_segsort(ulonglong2 *__restrict__ hits,
     }
 }
 
+// Stable in-CTA LSD radix sort of one segment by diagonal coordinate gd (<= 32 bits), 8-bit digits.
+// Hits of one (strand, read) segment are emitted in ascending bpos, so on a fixed diagonal they are
+// already in ascending apos: a STABLE sort by gd alone yields the (gd, apos) order -- half the key bits
+// of the bitonic kernel and O(n) work per pass.  Keys (u32 gd) and original indices (u16) ping-pong in
+// shared memory; the 16-byte records are gathered once at the end into the output buffer.
+template <int WARPS>
+__global__ void __launch_bounds__(WARPS * 32) k_segsort_radix(const ulonglong2 *__restrict__ in, ulonglong2 *__restrict__ out,
+                                                              const int64_t *__restrict__ seg_off, const int32_t *__restrict__ seglist,
+                                                              int cap, int gdbits) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    u32 *key0 = reinterpret_cast<u32 *>(smem_raw), *key1 = key0 + cap;
+    unsigned short *idx0 = reinterpret_cast<unsigned short *>(key1 + cap), *idx1 = idx0 + cap;
+    u32 *whist = reinterpret_cast<u32 *>(idx1 + cap);          // [WARPS][256]
+    u32 *dtot = whist + WARPS * 256;                            // [256] digit totals / bases
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int seg = seglist[blockIdx.x];
+    const int64_t beg = seg_off[seg];
+    const int n = (int)(seg_off[seg + 1] - beg);
+    const u64 gdmask = (1ull << gdbits) - 1ull;
+    for (int i = threadIdx.x; i < n; i += WARPS * 32) { key0[i] = (u32)(in[beg + i].x & gdmask); idx0[i] = (unsigned short)i; }
+    const int per = ((n + WARPS - 1) / WARPS + 31) & ~31;       // contiguous, 32-aligned sub-range per warp
+    const int wb = min(n, warp * per), we = min(n, wb + per);
+    __syncthreads();
+    u32 *kin = key0, *kout = key1; unsigned short *iin = idx0, *iout = idx1;
+    for (int shift = 0; shift < gdbits; shift += 8) {
+        for (int t = threadIdx.x; t < WARPS * 256; t += WARPS * 32) whist[t] = 0;
+        __syncthreads();
+        u32 *wh = whist + warp * 256;
+        for (int i0 = wb; i0 < we; i0 += 32) {                  // per-warp digit histogram
+            const int i = i0 + lane; const bool v = i < we;
+            const u32 vm = __ballot_sync(0xffffffffu, v);
+            if (v) {
+                const u32 dg = (kin[i] >> shift) & 255u;
+                const u32 peers = __match_any_sync(vm, dg);
+                if ((peers & ((1u << lane) - 1u)) == 0) wh[dg] += __popc(peers);
+            }
+            __syncwarp();
+        }
+        __syncthreads();
+        if (threadIdx.x < 256) {                                // digit totals, per-warp exclusive offsets
+            u32 a = 0;
+#pragma unroll
+            for (int w = 0; w < WARPS; w++) { u32 t = whist[w * 256 + threadIdx.x]; whist[w * 256 + threadIdx.x] = a; a += t; }
+            dtot[threadIdx.x] = a;
+        }
+        __syncthreads();
+        if (warp == 0) {                                        // exclusive scan of the 256 digit totals
+            u32 v[8], s = 0;
+#pragma unroll
+            for (int q = 0; q < 8; q++) { v[q] = dtot[lane * 8 + q]; s += v[q]; }
+            u32 inc = s;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) { u32 t = __shfl_up_sync(0xffffffffu, inc, o); if (lane >= o) inc += t; }
+            u32 ex = inc - s;
+#pragma unroll
+            for (int q = 0; q < 8; q++) { dtot[lane * 8 + q] = ex; ex += v[q]; }
+        }
+        __syncthreads();
+        for (int i0 = wb; i0 < we; i0 += 32) {                  // stable scatter
+            const int i = i0 + lane; const bool v = i < we;
+            const u32 vm = __ballot_sync(0xffffffffu, v);
+            if (v) {
+                const u32 kk = kin[i];
+                const u32 dg = (kk >> shift) & 255u;
+                const u32 peers = __match_any_sync(vm, dg);
+                const u32 before = wh[dg];
+                const u32 pos = dtot[dg] + before + __popc(peers & ((1u << lane) - 1u));
+                kout[pos] = kk; iout[pos] = iin[i];
+                __syncwarp(vm);
+                if ((peers & ((1u << lane) - 1u)) == 0) wh[dg] = before + __popc(peers);
+            }
+            __syncwarp();
+        }
+        __syncthreads();
+        { u32 *t = kin; kin = kout; kout = t; unsigned short *u = iin; iin = iout; iout = u; }
+    }
+    const u64 hi = n > 0 ? (in[beg].x & ~gdmask) : 0ull;
+    for (int i = threadIdx.x; i < n; i += WARPS * 32)
+        out[beg + i] = make_ulonglong2(hi | kin[i], in[beg + iin[i]].y);
+}
+
 }  // namespace
 
 void launch_seg_offsets(const int64_t *woff, const int64_t *b_off, int nr, int64_t nwB, int64_t H, int64_t *seg_off, cudaStream_t s) {
@@ -80,6 +161,24 @@ void launch_segsort(ulonglong2 *hits, const int64_t *seg_off, const int32_t *seg
     }
     // big segments need many warps to hide shared-memory latency: 1024 threads for the 8k/16k classes
     DN_LAUNCH(k_segsort, nseg, cap > 2048 ? 1024 : 256, smem, s, hits, seg_off, seglist, gdbits, aposbits);
+}
+
+// radix variant (gdbits <= 32): reads `in`, writes `out`; segments not listed must be copied by the caller
+void launch_segsort_radix(const ulonglong2 *in, ulonglong2 *out, const int64_t *seg_off, const int32_t *seglist, int nseg, int cap,
+                          int gdbits, cudaStream_t s) {
+    if (nseg == 0) return;
+    if (cap <= 2048) {
+        const size_t smem = (size_t)cap * 12 + 8 * 256 * 4 + 1024;
+        DN_LAUNCH((k_segsort_radix<8>), nseg, 256, smem, s, in, out, seg_off, seglist, cap, gdbits);
+    } else {
+        const size_t smem = (size_t)cap * 12 + 16 * 256 * 4 + 1024;
+        static size_t attr_set = 0;
+        if (smem > attr_set) {
+            DN_CUDA(cudaFuncSetAttribute(k_segsort_radix<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            attr_set = smem;
+        }
+        DN_LAUNCH((k_segsort_radix<16>), nseg, 512, smem, s, in, out, seg_off, seglist, cap, gdbits);
+    }
 }
 
 }  // namespace dn
