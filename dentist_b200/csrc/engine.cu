@@ -142,6 +142,16 @@ void align_blocks(const DevBlock &A, const DevBlock &B, const AlignParams &P, Ho
         DBuf<u32> wcnt(2 * nwB); DBuf<int64_t> woff(2 * nwB);
         DBuf<u32> kbits((1u << 28) / 32); kbits.zero(s);
         DN_LAUNCH(k_kmer_bitmap, (unsigned)((nA + 255) / 256), 256, 0, s, (const u64 *)sa, nA, kbits.p);
+        // pin the 32 MB bitmap in the persisting part of L2 while the streaming lookups run
+        {
+            static bool limit_set = false;
+            if (!limit_set) { cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, 48u << 20); cudaGetLastError(); limit_set = true; }
+            cudaStreamAttrValue av; memset(&av, 0, sizeof av);
+            av.accessPolicyWindow.base_ptr = kbits.p; av.accessPolicyWindow.num_bytes = (size_t)(1u << 28) / 8;
+            av.accessPolicyWindow.hitRatio = 1.0f; av.accessPolicyWindow.hitProp = cudaAccessPropertyPersisting;
+            av.accessPolicyWindow.missProp = cudaAccessPropertyStreaming;
+            cudaStreamSetAttribute(s, cudaStreamAttributeAccessPolicyWindow, &av); cudaGetLastError();
+        }
         for (int st = 0; st < 2; st++) {
             const u32 *mb = B.has_mask ? (st ? B.mask_rc.p : B.mask.p) : nullptr;
             DN_LAUNCH(k_lookup_count, (unsigned)((nwB + 255) / 256), 256, 0, s, (const u32 *)(st ? B.rc.p : B.fwd.p), mb,
@@ -161,6 +171,11 @@ void align_blocks(const DevBlock &A, const DevBlock &B, const AlignParams &P, Ho
                           (const int64_t *)(woff.p + st * nwB), st, JG, hits.p);
             }
         abytes += 2 * (nB / 4) * 2 + 2 * nwB * (4 + 4 + 8 + 8 + 4) + 16 * H;   // packed B read twice per strand, word counts/offsets, hits
+        {
+            cudaStreamAttrValue av; memset(&av, 0, sizeof av);            // release the L2 set-aside
+            cudaStreamSetAttribute(s, cudaStreamAttributeAccessPolicyWindow, &av); cudaGetLastError();
+            cudaCtxResetPersistingL2Cache(); cudaGetLastError();
+        }
         // hits were emitted grouped by (strand, read) in ascending order: sort inside the segments only
         if (H > 0 && gdbits + aposbits <= 63 && !getenv("DN_NO_SEGSORT")) {
             const int nseg = 2 * B.nreads;

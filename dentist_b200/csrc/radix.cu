@@ -27,7 +27,7 @@ __host__ __device__ inline size_t cta_range(size_t n, int G) {
 }
 
 template <typename Item, int FIELD>
-__global__ void __launch_bounds__(RS_THREADS) k_radix_hist(const Item *__restrict__ in, size_t n, int shift, u32 *__restrict__ hist /* [256][G] */) {
+__global__ void __launch_bounds__(RS_THREADS) k_radix_hist(const Item *__restrict__ in, size_t n, int shift, u32 *__restrict__ hist /* [G][256] */) {
     __shared__ u32 h[256];
     h[threadIdx.x] = 0;
     __syncthreads();
@@ -35,21 +35,33 @@ __global__ void __launch_bounds__(RS_THREADS) k_radix_hist(const Item *__restric
     size_t beg = per * blockIdx.x, end = beg + per; if (end > n) end = n;
     for (size_t i = beg + threadIdx.x; i < end; i += RS_THREADS) atomicAdd(&h[digit_of<Item, FIELD>(in[i], shift)], 1u);
     __syncthreads();
-    hist[(size_t)threadIdx.x * gridDim.x + blockIdx.x] = h[threadIdx.x];
+    hist[(size_t)blockIdx.x * 256 + threadIdx.x] = h[threadIdx.x];        // [cta][digit]: coalesced here and in the scan
 }
 
 // one CTA, 256 threads: exclusive scan of hist in digit-major order
 __global__ void __launch_bounds__(256) k_radix_scan(u32 *hist, int G) {
     __shared__ u32 tot[256];
-    u32 *row = hist + (size_t)threadIdx.x * G;
+    u32 *col = hist + threadIdx.x;                       // thread = digit; consecutive threads read consecutive words
     u32 s = 0;
-    for (int c = 0; c < G; c++) s += row[c];
+#pragma unroll 8
+    for (int c = 0; c < G; c++) s += col[(size_t)c * 256];
     tot[threadIdx.x] = s;
     __syncthreads();
-    if (threadIdx.x == 0) { u32 a = 0; for (int d = 0; d < 256; d++) { u32 t = tot[d]; tot[d] = a; a += t; } }
+    if (threadIdx.x < 32) {                              // exclusive scan of the 256 digit totals by one warp
+        u32 v[8], t = 0;
+#pragma unroll
+        for (int q = 0; q < 8; q++) { v[q] = tot[threadIdx.x * 8 + q]; t += v[q]; }
+        u32 inc = t;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) { u32 x = __shfl_up_sync(0xffffffffu, inc, o); if ((int)threadIdx.x >= o) inc += x; }
+        u32 ex = inc - t;
+#pragma unroll
+        for (int q = 0; q < 8; q++) { tot[threadIdx.x * 8 + q] = ex; ex += v[q]; }
+    }
     __syncthreads();
     u32 a = tot[threadIdx.x];
-    for (int c = 0; c < G; c++) { u32 t = row[c]; row[c] = a; a += t; }
+#pragma unroll 8
+    for (int c = 0; c < G; c++) { u32 t = col[(size_t)c * 256]; col[(size_t)c * 256] = a; a += t; }
 }
 
 template <typename Item, int FIELD>
@@ -58,7 +70,7 @@ __global__ void __launch_bounds__(RS_THREADS) k_radix_scatter(const Item *__rest
     __shared__ u32 whist[RS_WARPS][256];
     __shared__ u32 base[256];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    base[threadIdx.x] = hist[(size_t)threadIdx.x * gridDim.x + blockIdx.x];
+    base[threadIdx.x] = hist[(size_t)blockIdx.x * 256 + threadIdx.x];
     const size_t per = cta_range(n, gridDim.x);
     size_t beg = per * blockIdx.x, end = beg + per; if (end > n) end = n;
     for (size_t t0 = beg; t0 < end; t0 += RS_TILE) {

@@ -321,7 +321,7 @@ __global__ void __launch_bounds__(256) k_lookup_count(const u32 *__restrict__ se
             } else total += c;
         }
     }
-    wcnt[wi] = total;
+    __stcs(wcnt + wi, total);
 }
 
 __global__ void __launch_bounds__(256) k_lookup_emit(const u32 *__restrict__ seq, const u32 *__restrict__ maskbits,
@@ -333,11 +333,11 @@ __global__ void __launch_bounds__(256) k_lookup_emit(const u32 *__restrict__ seq
                                                      JoinGeom G, ulonglong2 *__restrict__ hits) {
     int64_t wi = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (wi >= nwords) return;
-    if (wcnt[wi] == 0) return;
+    if (__ldcs(wcnt + wi) == 0) return;                  // streamed once: keep it out of the way of the A index in L2
     const WordKmers w = load_word(seq, maskbits, off, len, c2r, wi);
     const u64 kmask = (1ull << (2 * k)) - 1ull, mk = (1ull << k) - 1ull;
     const u64 bs = (u64)strand * G.nb_reads + w.r;
-    int64_t o = woff[wi];
+    int64_t o = __ldcs((const long long *)woff + wi);
     u32 present = 0;
 #pragma unroll
     for (int jj = 0; jj < 16; jj++)
@@ -354,7 +354,8 @@ __global__ void __launch_bounds__(256) k_lookup_emit(const u32 *__restrict__ seq
             int apos = (int)(ga - G.a_off[ar]);
             if (!pair_ok(G, ar, w.r)) continue;
             const u64 gd = (u64)(G.a_dbase[ar] + apos - bpos + G.maxlb);
-            hits[o++] = make_ulonglong2((bs << G.gdbits) | gd, (u64)(u32)apos | ((u64)(u32)bpos << 32));
+            __stcs(reinterpret_cast<ulonglong2 *>(hits + o), make_ulonglong2((bs << G.gdbits) | gd, (u64)(u32)apos | ((u64)(u32)bpos << 32)));
+            o++;
         }
     }
 }
