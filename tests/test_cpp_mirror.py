@@ -1,0 +1,74 @@
+"""The C++ mirror of dazzler.d (include/dentist_b200.hpp) compiles against the C ABI; without a GPU every
+compute call raises DazzlerCommandException (no CPU fallback); on a GPU it gives what the Python path gives."""
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+M = (1 << 64) - 1
+
+
+def build(tmp_path):
+    exe = str(tmp_path / "replay")
+    subprocess.check_call(["g++", "-std=c++17", "-O1", "-I", os.path.join(ROOT, "include"), os.path.join(ROOT, "tests", "cpp", "replay.cpp"),
+                           "-L", os.path.join(ROOT, "dentist_b200"), "-ldentist_b200", "-Wl,-rpath," + os.path.join(ROOT, "dentist_b200"),
+                           "-o", exe])
+    return exe
+
+
+def test_cpp_mirror_builds_and_fails_loudly_without_gpu(tmp_path):
+    import torch
+    exe = build(tmp_path)
+    if torch.cuda.is_available():
+        pytest.skip("a GPU is present")
+    r = subprocess.run([exe, "7"], capture_output=True, text=True)
+    assert r.returncode == 3 and "DazzlerCommandException" in r.stdout and "no CUDA device" in r.stdout
+
+
+def _pile(seed):
+    s = seed
+    def lcg():
+        nonlocal s
+        s = (s * 6364136223846793005 + 1442695040888963407) & M
+        return s >> 33
+    L, N = 3000, 8
+    truth = [lcg() & 3 for _ in range(L)]
+    reads = []
+    for _ in range(N):
+        out = []
+        for i in range(L):
+            u = lcg() % 100
+            if u < 3:
+                continue
+            if u < 6:
+                out.append(lcg() & 3)
+            out.append((truth[i] + 1 + lcg() % 3) & 3 if u < 8 else truth[i])
+        reads.append(np.array(out, np.uint8))
+    return reads
+
+
+@pytest.mark.gpu
+def test_cpp_mirror_equals_python_path(tmp_path):
+    from dentist_b200 import dazzler
+    exe = build(tmp_path)
+    r = subprocess.run([exe, "7"], capture_output=True, text=True)
+    assert r.returncode == 0, r.stdout + r.stderr
+    got = dict(ln.split(" ", 1) for ln in r.stdout.strip().split("\n"))
+    reads = _pile(7)
+    off = np.zeros(len(reads) + 1, np.int64); off[1:] = np.cumsum([len(x) for x in reads])
+    g = dazzler.Block(off, np.concatenate(reads))
+    lens = np.diff(off)
+    las = dazzler.align(g, g, tspace=126, minlen=500, self_block=1)
+    assert int(got["raw"]) == len(las) > 20
+    las.filterLocalAlignments(0.3)
+    q, _ = dazzler.computeQVs(lens, las, 4)
+    las.filterPileUpAlignments(lens, lens, 126)
+    assert int(got["filtered"]) == len(las)
+    assert int(got["qvsum"]) == int(q.astype(np.int64).sum())
+    cons = dazzler.getConsensus(g, las, [0])[0]
+    h = 1469598103934665603
+    for b in cons.tolist():
+        h = ((h ^ b) * 1099511628211) & M
+    assert got["consensus"] == "%d %d" % (len(cons), h)
