@@ -131,6 +131,9 @@ def oracle_pile(reads, group, p):
     la, tr, _ = oracle.align(off, bases, off, bases, tspace=126, minlen=500, self=1, **ORC)
     toff = la["toff"].astype(np.int64)
     keep = oracle.filter_error(la, 0.3); la, toff = la[keep], toff[keep]
+    from oracle import chaining
+    src, fl = chaining.chain_local_alignments(la, chaining.ChainingOptions(min_score=126))
+    la, toff = la[src].copy(), toff[src]; la["flags"] = fl
     q, qoff = oracle.qv(lens, la, toff, tr, 126, max(len(members), 4) if len(members) >= 4 else len(members))
     kp = oracle.filter_pileup(la, lens, lens, 126); la, toff = la[kp], toff[kp]
     cand = pileups.find_reference_read_candidates(q, qoff, np.arange(len(members)))
@@ -266,6 +269,8 @@ def main():
         barrier()
         dt = time.perf_counter() - t1
         a2.free(); b2.free()
+        if os.environ.get("BENCH_DEBUG"):
+            print("[bench] e2e iter %d %.2f ms (align ms_total %.2f)" % (it, dt * 1e3, st["ms_total"]), file=sys.stderr)
         if it >= 1:
             e2e_t += dt; e2e_units += st["aligned_bases"]
             h2d = a2.h2d_bytes + b2.h2d_bytes; d2h = rec.nbytes + tr.nbytes
@@ -287,6 +292,8 @@ def main():
             barrier(); t1 = time.perf_counter()
             res = pileups.process_pileups(preads, pgroup, flanks=ga)
             barrier(); dt = time.perf_counter() - t1
+            if os.environ.get("BENCH_DEBUG"):
+                print("[bench] consensus iter %d %.2f ms" % (it, dt * 1e3), file=sys.stderr)
             if it >= 1:
                 ct += dt; cb += sum(len(c) for c in res["consensus"])
         t3 = torch.tensor([ct], dtype=torch.float64, device=dev); u3 = torch.tensor([float(cb)], dtype=torch.float64, device=dev)

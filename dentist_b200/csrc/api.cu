@@ -72,7 +72,7 @@ int dn_init(int device, const char *tmpdir) {
 int dn_shutdown(void) {
     std::lock_guard<std::mutex> lk(g_mu);
     if (g_stream) { cudaStreamSynchronize(g_stream); cudaStreamDestroy(g_stream); g_stream = nullptr; }
-    arena().destroy();
+    arena().destroy(); dcache_destroy();
     g_device = -1;
     return DN_OK;
 }

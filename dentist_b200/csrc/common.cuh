@@ -38,6 +38,12 @@ struct Arena {
 };
 Arena &arena();
 
+// Recycling allocator for buffers that outlive a call (resident blocks): cudaMalloc / cudaFree cost
+// milliseconds and synchronise the device, so freed buffers are kept and handed out again.
+void *dcache_alloc(size_t bytes);
+void dcache_free(void *p);
+void dcache_destroy();
+
 // RAII device buffer.  Default: carved from the arena (freed wholesale at the next reset).
 // persistent(): an owned cudaMalloc allocation that outlives the call (resident blocks).
 template <typename T> struct DBuf {
@@ -49,8 +55,8 @@ template <typename T> struct DBuf {
     DBuf &operator=(DBuf &&o) noexcept { if (this != &o) { release(); p = o.p; n = o.n; owned = o.owned; o.p = nullptr; o.n = 0; } return *this; }
     ~DBuf() { release(); }
     void alloc(size_t n_) { release(); n = n_; owned = false; if (n) p = (T *)arena().alloc(n * sizeof(T)); }
-    void persistent(size_t n_) { release(); n = n_; owned = true; if (n) DN_CUDA(cudaMalloc((void **)&p, n * sizeof(T))); }
-    void release() { if (p && owned) cudaFree(p); p = nullptr; n = 0; }
+    void persistent(size_t n_) { release(); n = n_; owned = true; if (n) p = (T *)dcache_alloc(n * sizeof(T)); }
+    void release() { if (p && owned) dcache_free(p); p = nullptr; n = 0; }
     void zero(cudaStream_t s) { if (n) DN_CUDA(cudaMemsetAsync(p, 0, n * sizeof(T), s)); }
     size_t bytes() const { return n * sizeof(T); }
 };

@@ -1,6 +1,7 @@
 // scan.cu -- hand-written exclusive prefix sums (three-phase: tile reduce, recursive scan of the
 // tile sums, tile scan + offset).  HBM-bound: reads the input twice, writes the output once.
 #include "common.cuh"
+#include <mutex>
 
 namespace dn {
 
@@ -36,6 +37,40 @@ void Arena::reset() {
 }
 
 void Arena::destroy() { for (Chunk &c : chunks) cudaFree(c.p); chunks.clear(); high = cur = 0; }
+
+namespace {
+struct DBlock { void *p; size_t cap; };
+std::mutex g_dmu; std::vector<DBlock> g_dfree; std::vector<DBlock> g_dlive; size_t g_dfree_bytes = 0;
+}
+void *dcache_alloc(size_t bytes) {
+    bytes = (bytes + 511) & ~(size_t)511;
+    std::lock_guard<std::mutex> lk(g_dmu);
+    int best = -1;
+    for (int i = 0; i < (int)g_dfree.size(); i++)
+        if (g_dfree[i].cap >= bytes && g_dfree[i].cap <= bytes + (bytes >> 1) + (1 << 20) && (best < 0 || g_dfree[i].cap < g_dfree[best].cap)) best = i;
+    DBlock b;
+    if (best >= 0) { b = g_dfree[best]; g_dfree.erase(g_dfree.begin() + best); g_dfree_bytes -= b.cap; }
+    else { b.cap = bytes; DN_CUDA(cudaMalloc(&b.p, bytes)); }
+    g_dlive.push_back(b);
+    return b.p;
+}
+void dcache_free(void *p) {
+    if (!p) return;
+    std::lock_guard<std::mutex> lk(g_dmu);
+    for (size_t i = 0; i < g_dlive.size(); i++)
+        if (g_dlive[i].p == p) {
+            DBlock b = g_dlive[i]; g_dlive.erase(g_dlive.begin() + i);
+            if (g_dfree.size() < 64 && g_dfree_bytes + b.cap <= (8ull << 30)) { g_dfree.push_back(b); g_dfree_bytes += b.cap; }
+            else cudaFree(b.p);
+            return;
+        }
+    cudaFree(p);
+}
+void dcache_destroy() {
+    std::lock_guard<std::mutex> lk(g_dmu);
+    for (auto &b : g_dfree) cudaFree(b.p);
+    g_dfree.clear(); g_dfree_bytes = 0;
+}
 
 void *PinnedBuf::get(size_t bytes) {
     if (bytes > cap) {

@@ -220,6 +220,27 @@ class Las:
         self._refresh()
         return self
 
+    def chainLocalAlignments(self, max_indel=1000, max_chain_gap=10000, max_rel_overlap=0.3, min_rel_score=1.0, min_score=None):
+        """dazzler.d:3995-4018 / chaining.d:122-334 with ChainingOptions (commandline.d:2820-2830)."""
+        ms = self.tspace if min_score is None else min_score
+        _lib.check(_lib.lib().dn_las_chain(C.byref(self._buf), int(max_indel), int(max_chain_gap), C.c_double(max_rel_overlap),
+                                           C.c_double(min_rel_score), int(ms)))
+        self._refresh()
+        return self
+
+    def forceFlat(self):
+        """filterPileUpAlignments(..., Yes.forceFlat) (dazzler.d:4084-4093): drop the chain flags and sort the
+        records in FlatLocalAlignment order (base.d:1787-1809).  Host glue on the (few) records of a pile."""
+        n = len(self)
+        if n == 0:
+            return self
+        rec = self.rec
+        rec["flags"] &= np.uint32(0x1 | 0x20)
+        order = np.lexsort((rec["diffs"], rec["bepos"], rec["bbpos"], rec["aepos"], rec["abpos"], rec["flags"] & 1, rec["bread"], rec["aread"]))
+        r2 = rec[order].copy(); t2 = self.toff[order].copy()
+        rec[:] = r2; self.toff[:] = t2
+        return self
+
     def chainMapper(self, nb_reads, max_indel=1000, max_gap=10000):
         """damapper-style START/NEXT/BEST flags (decoded at dazzler.d:1738-1755)."""
         _lib.check(_lib.lib().dn_las_chain_mapper(C.byref(self._buf), int(nb_reads), int(max_indel), int(max_gap)))

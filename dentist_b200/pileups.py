@@ -7,7 +7,7 @@ holds the cropped reads of all pile-ups (pile id per read = `group`).
   findReferenceReadCandidates  package.d:518-568   A10 (host logic, mirrored here in numpy)
   computeConsensus             package.d:600-619   A11
   alignConsensusToFlankingContigs  package.d:621-697   A12
-(chainLocalAlignments, package.d:492, is not built yet -- DESIGN.md §7.)
+  chainLocalAlignments         package.d:492       A6 (chaining.d restated on the device)
 """
 import numpy as np
 
@@ -46,11 +46,13 @@ def process_pileups(reads, group, max_alignment_error=0.3, flanks=None):
     las.filterLocalAlignments(max_alignment_error)                      # package.d:483-485
     if len(las) == 0:
         raise dazzler.DnError("empty pileup alignment")                  # package.d:487-490
+    las.chainLocalAlignments(min_score=TSPACE)                           # package.d:492-496, chainingOptions commandline.d:2820-2830
     # coverage = |allowedReferenceReadIds| (all reads of the pile here), raised to 4 for piles of >= 4 reads
     psize = np.bincount(group, minlength=npiles)
     cov_pile = np.where((psize < MIN_QV_COVERAGE), psize, np.maximum(psize, MIN_QV_COVERAGE))
     qv, qoff = dazzler.computeQVs(lens, las, cov_pile[group])            # package.d:498-503
-    las.filterPileUpAlignments(lens, lens, TSPACE)                       # package.d:505-510
+    las.filterPileUpAlignments(lens, lens, TSPACE)                       # package.d:505-510 (Yes.forceFlat)
+    las.forceFlat()
     if len(las) == 0:
         raise dazzler.DnError("empty pileup alignment after filtering")
     order = np.argsort(group, kind="stable")

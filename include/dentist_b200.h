@@ -165,6 +165,14 @@ typedef struct dn_seq_buf { int32_t nseq; int64_t *off; uint8_t *bases; } dn_seq
 int dn_consensus(const dn_block *db, const dn_las_buf *las, const int32_t *reads, int32_t nreads, dn_seq_buf *out);
 void dn_seq_free(dn_seq_buf *buf);
 
+/* chainLocalAlignments(db, las, chainingOptions)  dazzler.d:3995-4018 -> common/alignments/chaining.d:122-334:
+ * per (A,B) pair the best chain(s) of local alignments; the records are rewritten chain by chain with
+ * START(+BEST)/NEXT flags as writeAlignmentChain does (dazzler.d:2037-2083); ELIM records are dropped.
+ * Options = ChainingOptions (commandline.d:2820-2830; defaults 1000, 10000, 0.3, 1.0, tspace).
+ * `las` must be ordered by (aread, bread). */
+int dn_las_chain(dn_las_buf *las, int32_t max_indel, int32_t max_chain_gap, double max_rel_overlap, double min_rel_score,
+                 int32_t min_score);
+
 /* damapper-style chain flags: START on the first record of a chain, NEXT on continuations, BEST on the
  * top-scoring chain of every B read -- the flags DENTIST decodes at dazzler.d:1738-1755 and packs into
  * AlignmentChains at :708-743.  `las` must be in LAsort order (as dn_align_blocks returns it). */

@@ -89,7 +89,7 @@ def test_batched_pileups_equal_per_pile_processing():
     """All pile-ups of a batch in ONE block (pile id per read) give exactly what the reference's
     one-pile-at-a-time loop (package.d:153) gives: per-pile oracle runs, concatenated."""
     from dentist_b200 import pileups
-    from oracle import oracle
+    from oracle import chaining, oracle
     sc = synth.make_scaffolds(1, 120000, 301, n_repeats=0)
     gaps = synth.make_gaps(sc, 4, 302, min_len=200, max_len=1500)
     reads, group, regions = synth.make_pile_batch(sc, gaps, 303, depth=9, anchor=1200)
@@ -106,10 +106,16 @@ def test_batched_pileups_equal_per_pile_processing():
         toff = la["toff"].astype(np.int64)
         keep = oracle.filter_error(la, 0.3)
         la, toff = la[keep], toff[keep]
+        src, fl = chaining.chain_local_alignments(la, chaining.ChainingOptions(min_score=126))
+        la, toff = la[src].copy(), toff[src]
+        la["flags"] = fl
         q, qoff = oracle.qv(lens[lo:hi], la, toff, tr, 126, max(len(members), 4) if len(members) >= 4 else len(members))
         assert np.array_equal(q, res["qv"][res["qoff"][lo]:res["qoff"][hi]])
         kp = oracle.filter_pileup(la, lens[lo:hi], lens[lo:hi], 126)
         la, toff = la[kp], toff[kp]
+        la["flags"] &= 0x21                                              # Yes.forceFlat: unchained + FlatLocalAlignment order
+        o = np.lexsort((la["diffs"], la["bepos"], la["bbpos"], la["aepos"], la["abpos"], la["flags"] & 1, la["bread"], la["aread"]))
+        la, toff = la[o], toff[o]
         sel = (res["las"].rec["aread"] >= lo) & (res["las"].rec["aread"] < hi)
         grec = res["las"].rec[sel]
         assert len(grec) == len(la)
@@ -194,3 +200,47 @@ def test_mapper_chain_flags_match_oracle_and_pack_into_chains():
     # exactly one BEST chain per mapped read
     starts = las.rec[(las.rec["flags"] & olas.BEST) != 0]
     assert sorted(starts["bread"].tolist()) == sorted(set(las.rec["bread"].tolist()))
+
+
+def test_chain_local_alignments_matches_oracle():
+    """chaining.d restated on the device == oracle/chaining.py (exact restatement of the D source)."""
+    from dentist_b200 import dazzler
+    from oracle import chaining, las as olas
+    sc = synth.make_scaffolds(1, 20000, 21, n_repeats=1, repeat_len=800, repeat_copies=3)
+    reads, _ = synth.simulate_reads(sc, 10, 7000, 2000, 0.13, 22)
+    rng = np.random.default_rng(1)
+    seqs = []
+    for r in range(reads.nreads):
+        s = reads.read(r)
+        if r % 2 == 0 and len(s) > 4000:                  # junk in the middle breaks alignments into chainable pieces
+            m = len(s) // 2
+            s = np.concatenate([s[:m], rng.integers(0, 4, 200, dtype=np.uint8), s[m:]])
+        seqs.append(s)
+    off = np.zeros(len(seqs) + 1, np.int64); off[1:] = np.cumsum([len(s) for s in seqs])
+    g = dazzler.Block(off, np.concatenate(seqs))
+    for opts in (dict(), dict(min_rel_score=0.5, max_rel_overlap=0.1), dict(max_indel=50, max_chain_gap=300, min_rel_score=0.2)):
+        las = dazzler.align(g, g, tspace=126, minlen=500, self_block=1)
+        before, toff0 = las.rec.copy(), las.toff.copy()
+        assert len(before) > 500
+        las.chainLocalAlignments(**opts)
+        o = chaining.ChainingOptions(max_indel=opts.get("max_indel", 1000), max_chain_gap=opts.get("max_chain_gap", 10000),
+                                     max_rel_overlap=opts.get("max_rel_overlap", 0.3), min_rel_score=opts.get("min_rel_score", 1.0), min_score=126)
+        src, fl = chaining.chain_local_alignments(before, o)
+        assert len(las) == len(src)
+        assert np.array_equal(las.rec["flags"], fl)
+        for f in ("aread", "bread", "abpos", "aepos", "bbpos", "bepos", "diffs", "tlen"):
+            assert np.array_equal(las.rec[f], before[src][f]), f
+        assert np.array_equal(las.toff, toff0[src])
+        chains = olas.chains(las.rec)                       # what AlignmentChainPacker (dazzler.d:708-743) builds from it
+        assert sum(len(c) for c in chains) == len(las) and any(len(c) > 1 for c in chains)
+    # disabled records are ignored, unordered input is rejected like chaining.d:131-140
+    las = dazzler.align(g, g, tspace=126, minlen=500, self_block=1)
+    las.rec["flags"][::3] |= 0x20
+    b2 = las.rec.copy()
+    las.chainLocalAlignments()
+    src, fl = chaining.chain_local_alignments(b2, chaining.ChainingOptions(min_score=126))
+    assert np.array_equal(las.rec["flags"], fl) and len(las) == len(src)
+    las = dazzler.align(g, g, tspace=126, minlen=500, self_block=1)
+    las.rec[:] = las.rec[::-1].copy()
+    with pytest.raises(dazzler.DnError, match="not ordered properly"):
+        las.chainLocalAlignments()
