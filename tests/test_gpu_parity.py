@@ -176,3 +176,34 @@ def test_trace_invariants_at_scale():
     # idempotence: same input, same bytes
     rec2, _, tr2, _ = dazzler.align_blocks(ga, gb, tspace=100, minlen=1000)
     assert rec.tobytes() == rec2.tobytes() and np.array_equal(tr, tr2)
+
+
+def test_long_ont_like_reads_at_scale():
+    """configs[2]-like reads (20 kb +- 10 kb, 12 % ONT-like error, some > 50 kb): segments beyond the shared-memory
+    classes, long traces and the record pool are exercised; checked through size-independent invariants."""
+    from dentist_b200 import dazzler
+    sc = synth.make_scaffolds(3, 1500000, 51)
+    ref, meta = synth.contigs_from(sc, synth.make_gaps(sc, 3, 52))
+    reads, truth = synth.simulate_reads(sc, 4, 20000, 10000, 0.12, 53, mix=(0.25, 0.45, 0.30))
+    long_reads, _ = synth.simulate_reads(sc, 0.15, 90000, 5000, 0.12, 54, mix=(0.25, 0.45, 0.30))
+    seqs = [reads.read(r) for r in range(reads.nreads)] + [long_reads.read(r) for r in range(long_reads.nreads)]
+    off = np.zeros(len(seqs) + 1, np.int64); off[1:] = np.cumsum([len(s) for s in seqs])
+    allr = synth.Block(off, np.concatenate(seqs))
+    assert np.diff(off).max() > 80000
+    ga, gb = dazzler.Block(ref.off, ref.bases), dazzler.Block(allr.off, allr.bases)
+    rec, toff, tr, st = dazzler.align_blocks(ga, gb, tspace=100, minlen=1000)
+    nt = -(-rec["aepos"] // 100) - rec["abpos"] // 100
+    assert np.array_equal(rec["tlen"], 2 * nt)
+    t = tr.reshape(-1, 2).astype(np.int64)
+    idx = np.repeat(np.arange(len(rec)), nt)
+    assert np.array_equal(np.bincount(idx, t[:, 0], len(rec)).astype(np.int64), rec["diffs"])
+    assert np.array_equal(np.bincount(idx, t[:, 1], len(rec)).astype(np.int64), rec["bepos"] - rec["bbpos"])
+    lens = np.diff(off)
+    assert (rec["bepos"] <= lens[rec["bread"]]).all() and (rec["aepos"] <= np.diff(ref.off)[rec["aread"]]).all()
+    covered = np.zeros(allr.nreads); np.add.at(covered, rec["bread"], rec["bepos"] - rec["bbpos"])
+    assert (covered / lens > 0.8).mean() > 0.9
+    err = rec["diffs"].sum() / (rec["aepos"] - rec["abpos"]).sum()
+    assert 0.08 < err < 0.16
+    # the same job through the sorted-merge join gives the same bytes
+    rec2, _, tr2, _ = dazzler.align_blocks(ga, gb, tspace=100, minlen=1000, join_mode=1)
+    assert rec.tobytes() == rec2.tobytes() and np.array_equal(tr, tr2)

@@ -1,0 +1,51 @@
+#!/usr/bin/env python
+"""BASELINE.json configs[4]: align-only throughput sweep -- read length 1k..100k x error 5..15 %, one block pair
+per cell, device-resident blocks, vs the CPU oracle port on a bounded sample.  Writes JSON lines.
+  python tools/sweep_align.py [--ref-mbp 50] [--reads-mbp 50] [--out profiles/r01_sweep_align.jsonl]"""
+import argparse, json, os, sys, time
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import numpy as np
+from dentist_b200 import dazzler, synth
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--ref-mbp", type=float, default=50); ap.add_argument("--reads-mbp", type=float, default=50)
+    ap.add_argument("--out", default="gpurun_out/sweep_align.jsonl"); ap.add_argument("--cpu", action="store_true")
+    a = ap.parse_args()
+    dazzler.init(0)
+    n_sc = max(1, int(a.ref_mbp))
+    sc = synth.make_scaffolds(n_sc, 1000000, 4001, n_repeats=0)
+    ref, _ = synth.contigs_from(sc, [[] for _ in sc])
+    ga = dazzler.Block(ref.off, ref.bases)
+    out = open(a.out, "w")
+    for L in (1000, 2000, 5000, 10000, 20000, 50000, 100000):
+        for ei, e in enumerate((0.05, 0.10, 0.15)):
+            reads, _ = synth.simulate_reads(sc, a.reads_mbp / a.ref_mbp, L, 1, e, 4002 + ei + L, min_len=L, lognormal=False)
+            gb = dazzler.Block(reads.off, reads.bases)
+            minlen = min(1000, L // 2)
+            for _ in range(2):
+                dazzler.align_blocks(ga, gb, tspace=100, minlen=minlen)
+            ms, al = 0.0, 0
+            for _ in range(3):
+                rec, _, _, st = dazzler.align_blocks(ga, gb, tspace=100, minlen=minlen)
+                ms += st["ms_total"]; al += st["aligned_bases"]
+            row = dict(read_len=L, error=e, ref_bp=int(ref.total), reads_bp=int(reads.total), reads=int(reads.nreads), las=int(len(rec)),
+                       ms_per_step=ms / 3, gbp_aligned_per_s=al / 1e9 / (ms / 1e3), input_gbp_per_s=3 * reads.total / 1e9 / (ms / 1e3),
+                       hits=int(st["hits"]), seeds=int(st["seeds"]))
+            if a.cpu:
+                from oracle import oracle
+                nr = max(1, int(np.searchsorted(reads.off, 300000)))
+                sub = synth.Block(sc and np.array([0, len(sc[0])], np.int64), sc[0])
+                t0 = time.perf_counter()
+                la, _, _ = oracle.align(sub.off, sub.bases, reads.off[:nr + 1], reads.bases[:reads.off[nr]], tspace=100, minlen=minlen)
+                dt = time.perf_counter() - t0
+                row["cpu_port_gbp_aligned_per_s_1core"] = float((la["aepos"] - la["abpos"]).sum()) / 1e9 / dt
+                row["cpu_sample"] = "first %d reads vs scaffold 0 (1 Mbp)" % nr
+            out.write(json.dumps(row) + "\n"); out.flush()
+            print(row, flush=True)
+            gb.free()
+
+
+if __name__ == "__main__":
+    main()
