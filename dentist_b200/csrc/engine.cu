@@ -140,14 +140,14 @@ void align_blocks(const DevBlock &A, const DevBlock &B, const AlignParams &P, Ho
         // B's tuples are never materialised: count, scan, emit straight from the packed sequence
         const int64_t nwB = nB >> 4;
         DBuf<u32> wcnt(2 * nwB); DBuf<int64_t> woff(2 * nwB);
-        DBuf<u32> kbits((1u << 28) / 32); kbits.zero(s);
+        DBuf<u32> kbits((1u << KBITS_LOG2) / 32); kbits.zero(s);
         DN_LAUNCH(k_kmer_bitmap, (unsigned)((nA + 255) / 256), 256, 0, s, (const u64 *)sa, nA, kbits.p);
         // pin the 32 MB bitmap in the persisting part of L2 while the streaming lookups run
         {
             static bool limit_set = false;
             if (!limit_set) { cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, 48u << 20); cudaGetLastError(); limit_set = true; }
             cudaStreamAttrValue av; memset(&av, 0, sizeof av);
-            av.accessPolicyWindow.base_ptr = kbits.p; av.accessPolicyWindow.num_bytes = (size_t)(1u << 28) / 8;
+            av.accessPolicyWindow.base_ptr = kbits.p; av.accessPolicyWindow.num_bytes = (size_t)(1u << KBITS_LOG2) / 8;
             av.accessPolicyWindow.hitRatio = 1.0f; av.accessPolicyWindow.hitProp = cudaAccessPropertyPersisting;
             av.accessPolicyWindow.missProp = cudaAccessPropertyStreaming;
             cudaStreamSetAttribute(s, cudaStreamAttributeAccessPolicyWindow, &av); cudaGetLastError();

@@ -254,17 +254,19 @@ __global__ void __launch_bounds__(256) k_join_emit(const u64 *__restrict__ ta, c
 // Presence bitmap over k-mers (bit = kmer mod 2^28; exact for k <= 14): 32 MB, L2-resident.  Four out of
 // five read k-mers carry a sequencing error and occur nowhere in A; the bitmap rejects them with ONE
 // sector read instead of the table + list walk.
+__device__ __forceinline__ u32 kbit_index(u32 km) { return (km * 0x9E3779B1u) >> (32 - KBITS_LOG2); }   // multiplicative hash
+
 __global__ void __launch_bounds__(256) k_kmer_bitmap(const u64 *__restrict__ ta, int64_t na, u32 *__restrict__ bits) {
     int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= na) return;
     const u32 km = (u32)(ta[i] >> 32);
     if (km == 0xffffffffu) return;
     if (i > 0 && (u32)(ta[i - 1] >> 32) == km) return;          // one atomic per distinct k-mer
-    const u32 b = km & 0x0fffffffu;
+    const u32 b = kbit_index(km);
     atomicOr(&bits[b >> 5], 1u << (b & 31));
 }
 __device__ __forceinline__ bool kmer_present(const u32 *__restrict__ bits, u32 km) {
-    const u32 b = km & 0x0fffffffu;
+    const u32 b = kbit_index(km);
     return (bits[b >> 5] >> (b & 31)) & 1u;
 }
 

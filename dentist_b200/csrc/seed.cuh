@@ -4,6 +4,8 @@
 
 namespace dn {
 
+constexpr int KBITS_LOG2 = 28;      // k-mer presence filter: 2^28 bits = 32 MB (hashed; false positives only cost a lookup; 2^26 measured slower)
+
 struct Seed { int32_t a, bs, apos, bpos; };
 
 // geometry handed to the join: how a (aread, apos, bread, strand, bpos) hit becomes a sort key
