@@ -41,13 +41,10 @@ def test_reference_consensus_kat():
 def test_consensus_corrects_noisy_pile():
     sc = synth.make_scaffolds(1, 12000, 5, n_repeats=0)
     truth_seq = sc[0][1000:9000]
-    rng = np.random.default_rng(9)
-    # 14 forward-strand reads over the same 8 kb window, 10 % error
+    # 14 reads (either strand) over the same 8 kb window, 10 % error
     seqs = []
     for i in range(14):
-        sub = [truth_seq.copy()]
-        r, _ = synth.simulate_reads(sub, 1.0, 8000, 1, 0.10, 100 + i, min_len=8000, lognormal=False)
-        # simulate_reads may flip the strand; recover forward orientation by regenerating until forward
+        r, _ = synth.simulate_reads([truth_seq.copy()], 1.0, 8000, 1, 0.10, 100 + i, min_len=8000, lognormal=False)
         seqs.append(r)
     reads = []
     for i, r in enumerate(seqs):
@@ -58,23 +55,9 @@ def test_consensus_corrects_noisy_pile():
     sel = np.flatnonzero(keep & oracle.filter_error(la, 0.3))
     assert (la[sel]["aread"] == 0).sum() >= 8
     cons = oracle.consensus(blk.off, blk.bases, la[sel], toff[sel], tr, 126, 0)
-    # error of raw read vs consensus against the truth (either strand), by edit distance on a window
-    def ed(a, b):
-        prev = np.arange(len(b) + 1)
-        for i in range(1, len(a) + 1):
-            cur = np.empty(len(b) + 1, np.int64); cur[0] = i
-            sub = prev[:-1] + (a[i - 1] != b)
-            dele = prev[1:] + 1
-            best = np.minimum(sub, dele)
-            for j in range(1, len(b) + 1):
-                cur[j] = min(best[j - 1], cur[j - 1] + 1)
-            prev = cur
-        return int(prev[-1])
     t = truth_seq
     rc = lambda s: (3 - s)[::-1]
     raw = blk.read(0)
-    w = 600
-    e_raw = min(ed(raw[1000:1000 + w], t[1000 - 150:1000 + w + 150][150:150 + w]), ed(raw[1000:1000 + w], rc(t)[1000:1000 + w]))
     # compare identities with a cheap proxy instead: k-mer containment against truth
     def kmers(s, k=12):
         v = np.zeros(len(s) - k + 1, np.int64)
@@ -84,7 +67,7 @@ def test_consensus_corrects_noisy_pile():
     kt = kmers(t) | kmers(rc(t))
     f_raw = np.mean([x in kt for x in kmers(raw)])
     f_cons = np.mean([x in kt for x in kmers(cons)])
-    assert f_raw < 0.45 and f_cons > 0.80, (f_raw, f_cons, e_raw)
+    assert f_raw < 0.45 and f_cons > 0.80, (f_raw, f_cons)
 
 
 def test_filters_match_definitions():
