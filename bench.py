@@ -214,11 +214,14 @@ def main():
     ref_bps, ref_boff = bps_of(ref)
     reads_bps, reads_boff = bps_of(reads)
 
-    bread_offset = 0
+    bread_offset = 0; gather_bounds = None
     if world > 1:
         cnts = [torch.zeros(1, dtype=torch.int64, device=dev) for _ in range(world)]
         dist.all_gather(cnts, torch.tensor([reads.nreads], dtype=torch.int64, device=dev))
         bread_offset = int(sum(int(c.item()) for c in cnts[:rank]))
+        mx = torch.tensor([int(np.diff(reads.off).max())], dtype=torch.int64, device=dev)
+        dist.all_reduce(mx, op=dist.ReduceOp.MAX)
+        gather_bounds = (int(np.diff(ref.off).max()), int(mx.item()), ref.nreads, int(sum(int(c.item()) for c in cnts)))
 
     def barrier():
         if world > 1:
@@ -265,7 +268,7 @@ def main():
         b2 = dazzler.Block(reads.off, bps=reads_bps, boff=reads_boff)
         rec, toff, tr, st = dazzler.align_blocks(a2, b2, **PARAMS)
         if world > 1:
-            rec, toff, tr = sharding.gather_las(rec, tr, bread_offset, device=dev)
+            rec, toff, tr = sharding.gather_las(rec, tr, bread_offset, device=dev, tspace=PARAMS["tspace"], bounds=gather_bounds)
         barrier()
         dt = time.perf_counter() - t1
         a2.free(); b2.free()

@@ -136,6 +136,21 @@ int dn_align_host(const dn_block_desc *a, const dn_block_desc *b, const dn_align
     return rc;
 }
 
+int dn_las_merge_device(const void *d_rec, int64_t nrec, const void *d_trace, int64_t ntrace, int32_t tspace, int64_t max_alen,
+                        int64_t max_blen, int64_t na_reads, int64_t nb_reads, dn_las_buf *out) {
+    if (!out || nrec < 0 || ntrace < 0 || (nrec && !d_rec) || (ntrace && !d_trace)) return fail(DN_ERR_INVALID, "null argument");
+    std::lock_guard<std::mutex> lk(g_mu);
+    if (int rc = ensure_device()) return rc;
+    return guarded([&] {
+        cudaSetDevice(g_device);
+        cudaDeviceSynchronize();                         // the inputs come from another stream (e.g. NCCL via torch)
+        HostLas h;
+        merge_las_device((const dn_las_record *)d_rec, nrec, (const uint16_t *)d_trace, ntrace, max_alen, max_blen, na_reads, nb_reads, h, g_stream);
+        to_buf(h, tspace, out);
+        return DN_OK;
+    });
+}
+
 int dn_las_write(const char *path, const dn_las_buf *buf) {
     if (!path || !buf) return fail(DN_ERR_INVALID, "null argument");
     return guarded([&] {

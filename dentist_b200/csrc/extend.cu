@@ -570,3 +570,81 @@ void launch_dedupe(const Cand *cands, int ncand, const int32_t *round_beg, int n
 int ext_warps_per_cta() { return EXT_WARPS; }
 
 }  // namespace dn
+
+// ---------------------------------------------------------------- LAS merge (what LAmerge does, Snakefile:1173-1200)
+// Device-resident concatenation of LAS segments (e.g. the result of the NCCL all-gatherv) -> one LAS in
+// LAsort order (base.d:1787-1809) with its traces gathered: four stable LSD sorts of (key, index) items.
+namespace dn {
+namespace {
+
+__global__ void __launch_bounds__(256) k_merge_tlen(const dn_las_record *__restrict__ rec, int64_t n, u32 *__restrict__ tl) {
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) tl[i] = (u32)rec[i].tlen;
+}
+__global__ void __launch_bounds__(256) k_merge_setkey(const dn_las_record *__restrict__ rec, ulonglong2 *__restrict__ items, int64_t n,
+                                                      int field, FinalBits fb) {
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const u64 idx = field == 0 ? (u64)i : items[i].y;
+    const dn_las_record x = rec[idx];
+    u64 key;
+    if (field == 0) key = (u64)(u32)x.diffs;
+    else if (field == 1) key = ((u64)(u32)x.bbpos << fb.nb) | (u32)x.bepos;
+    else if (field == 2) key = ((u64)(x.flags & DN_LAS_COMP) << (2 * fb.na)) | ((u64)(u32)x.abpos << fb.na) | (u32)x.aepos;
+    else key = ((u64)(u32)x.aread << fb.nrb) | (u32)x.bread;
+    items[i] = make_ulonglong2(key, idx);
+}
+__global__ void __launch_bounds__(256) k_merge_records(const dn_las_record *__restrict__ rec, const ulonglong2 *__restrict__ items, int64_t n,
+                                                       dn_las_record *__restrict__ out, u32 *__restrict__ tl) {
+    int64_t o = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (o >= n) return;
+    const dn_las_record x = rec[items[o].y];
+    out[o] = x; tl[o] = (u32)x.tlen;
+}
+__global__ void __launch_bounds__(256) k_merge_traces(const ulonglong2 *__restrict__ items, int64_t n, const int64_t *__restrict__ src_toff,
+                                                      const int64_t *__restrict__ dst_toff, const dn_las_record *__restrict__ out_rec,
+                                                      const uint16_t *__restrict__ src, uint16_t *__restrict__ dst) {
+    const int64_t o = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5; const int lane = threadIdx.x & 31;
+    if (o >= n) return;
+    const uint16_t *s = src + src_toff[items[o].y];
+    uint16_t *d = dst + dst_toff[o];
+    for (int q = lane; q < out_rec[o].tlen; q += 32) d[q] = s[q];
+}
+int bits_of(uint64_t v) { int b = 0; while (v) { b++; v >>= 1; } return b; }
+
+}  // namespace
+
+void merge_las_device(const dn_las_record *d_rec, int64_t n, const uint16_t *d_trace, int64_t ntrace, int64_t max_alen, int64_t max_blen,
+                      int64_t na_reads, int64_t nb_reads, HostLas &out, cudaStream_t s) {
+    out = HostLas();
+    arena().reset();
+    out.rec = (dn_las_record *)hcache_alloc(sizeof(dn_las_record) * (size_t)(n + 1));
+    out.toff = (int64_t *)hcache_alloc(sizeof(int64_t) * (size_t)(n + 1));
+    out.trace = (uint16_t *)hcache_alloc(sizeof(uint16_t) * (size_t)(ntrace + 1));
+    out.nrec = n; out.ntrace = ntrace;
+    if (n == 0) return;
+    if (n >= (1ll << 31)) throw Error("too many records to merge");
+    DBuf<u32> tl(n); DBuf<int64_t> stoff(n), dtoff(n), tot(1);
+    DN_LAUNCH(k_merge_tlen, (unsigned)((n + 255) / 256), 256, 0, s, d_rec, n, tl.p);
+    exclusive_scan_u32_to_i64(tl.p, stoff.p, n, tot.p, s);
+    FinalBits fb{bits_of((uint64_t)max_alen), bits_of((uint64_t)max_blen), bits_of((uint64_t)na_reads), bits_of((uint64_t)nb_reads), 0};
+    const int fbits[4] = {bits_of((uint64_t)max_alen + max_blen), 2 * fb.nb, 2 * fb.na + 1, fb.nra + fb.nrb};
+    DBuf<ulonglong2> it1(n), it2(n);
+    ulonglong2 *cur = it1.p, *oth = it2.p;
+    for (int f = 0; f < 4; f++) {
+        DN_LAUNCH(k_merge_setkey, (unsigned)((n + 255) / 256), 256, 0, s, d_rec, cur, n, f, fb);
+        ulonglong2 *res = radix_sort_rec16(cur, oth, n, 0, 0, fbits[f], s);
+        if (res != cur) { oth = cur; cur = res; }
+    }
+    DBuf<dn_las_record> orec(n); DBuf<uint16_t> otr((size_t)ntrace + 1);
+    DN_LAUNCH(k_merge_records, (unsigned)((n + 255) / 256), 256, 0, s, d_rec, (const ulonglong2 *)cur, n, orec.p, tl.p);
+    exclusive_scan_u32_to_i64(tl.p, dtoff.p, n, tot.p, s);
+    DN_LAUNCH(k_merge_traces, (unsigned)((n * 32 + 255) / 256), 256, 0, s, (const ulonglong2 *)cur, n, (const int64_t *)stoff.p,
+              (const int64_t *)dtoff.p, (const dn_las_record *)orec.p, d_trace, otr.p);
+    DN_CUDA(cudaMemcpyAsync(out.rec, orec.p, sizeof(dn_las_record) * n, cudaMemcpyDeviceToHost, s));
+    DN_CUDA(cudaMemcpyAsync(out.toff, dtoff.p, sizeof(int64_t) * n, cudaMemcpyDeviceToHost, s));
+    if (ntrace) DN_CUDA(cudaMemcpyAsync(out.trace, otr.p, sizeof(uint16_t) * ntrace, cudaMemcpyDeviceToHost, s));
+    DN_CUDA(cudaStreamSynchronize(s));
+}
+
+}  // namespace dn

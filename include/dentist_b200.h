@@ -134,6 +134,12 @@ int dn_align_blocks(const dn_block *a, const dn_block *b, const dn_align_params 
 /* Same, straight from host descriptors (upload + align + download). */
 int dn_align_host(const dn_block_desc *a, const dn_block_desc *b, const dn_align_params *p, dn_las_buf *out);
 
+/* LAmerge (Snakefile:863-873, 1173-1200) for device-resident segments: `d_rec` = nrec concatenated 40-byte records,
+ * `d_trace` = their uint16 traces concatenated in the same order (both DEVICE pointers, e.g. the receive
+ * buffer of the all-gatherv); returns one LAS in LAsort order.  max_*len / n*_reads bound the key widths. */
+int dn_las_merge_device(const void *d_rec, int64_t nrec, const void *d_trace, int64_t ntrace, int32_t tspace, int64_t max_alen,
+                        int64_t max_blen, int64_t na_reads, int64_t nb_reads, dn_las_buf *out);
+
 /* Serialise to the LAS wire format (dazzler.d:1913-2170: int64 novl, int32 tspace, 40-byte records,
  * uint8 traces iff tspace <= 125). */
 int dn_las_write(const char *path, const dn_las_buf *buf);

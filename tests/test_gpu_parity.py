@@ -207,3 +207,32 @@ def test_long_ont_like_reads_at_scale():
     # the same job through the sorted-merge join gives the same bytes
     rec2, _, tr2, _ = dazzler.align_blocks(ga, gb, tspace=100, minlen=1000, join_mode=1)
     assert rec.tobytes() == rec2.tobytes() and np.array_equal(tr, tr2)
+
+
+def test_device_las_merge_equals_lasort_order():
+    """dn_las_merge_device (what replaces LAmerge after the all-gatherv): segments split by read range and
+    concatenated on the device merge back into exactly the single-GPU LAS."""
+    import ctypes as C
+    import torch
+    from dentist_b200 import dazzler, _lib
+    ref, reads = small_case(23, cov=4)
+    ga, gb = dazzler.Block(ref.off, ref.bases), dazzler.Block(reads.off, reads.bases)
+    las = dazzler.align(ga, gb, tspace=100, minlen=500)
+    rec, toff, tr = las.rec, las.toff, las.trace
+    cuts = [0, reads.nreads // 3, 2 * reads.nreads // 3, reads.nreads]
+    parts_r, parts_t = [], []
+    for lo, hi in zip(cuts[:-1][::-1], cuts[1:][::-1]):              # segments in a different order than the reads
+        sel = np.flatnonzero((rec["bread"] >= lo) & (rec["bread"] < hi))
+        parts_r.append(rec[sel]); parts_t.append(np.concatenate([tr[toff[i]:toff[i] + rec[i]["tlen"]] for i in sel]))
+    drec = torch.from_numpy(np.frombuffer(np.concatenate(parts_r).tobytes(), np.uint8).copy()).cuda()
+    dtr = torch.from_numpy(np.concatenate(parts_t).view(np.uint8).copy()).cuda()
+    torch.cuda.synchronize()
+    buf = _lib.LasBuf()
+    _lib.check(_lib.lib().dn_las_merge_device(C.c_void_p(drec.data_ptr()), len(rec), C.c_void_p(dtr.data_ptr()), len(tr), 100,
+                                              int(np.diff(ref.off).max()), int(np.diff(reads.off).max()), ref.nreads, reads.nreads, C.byref(buf)))
+    m = dazzler.Las(buf)
+    assert m.rec.tobytes() == rec.tobytes() and np.array_equal(m.toff, toff) and np.array_equal(m.trace, tr)
+    # and the numpy merge used by the gloo tests agrees
+    from dentist_b200 import sharding
+    r2, o2, t2 = sharding.merge_las(parts_r, parts_t)
+    assert r2.tobytes() == rec.tobytes() and np.array_equal(t2, tr)

@@ -9,4 +9,4 @@ for i in range(8):
     t=time.perf_counter()
     rec, toff, tr, st = dazzler.align_blocks(ga, gb, **bench.PARAMS)
     dt=time.perf_counter()-t
-    print("call %d wall %.2f ms_total %.2f seed %.2f ext %.2f nla %d"%(i, dt*1e3, st["ms_total"], st["ms_seed"], st["ms_extend"], len(rec)), flush=True)
+    print("call %d wall %.2f ms_total %.2f seed %.2f ext %.2f nla %d hits %d seeds %d" % (i, dt*1e3, st["ms_total"], st["ms_seed"], st["ms_extend"], len(rec), st["hits"], st["seeds"]), flush=True)
