@@ -308,7 +308,6 @@ void align_blocks(const DevBlock &A, const DevBlock &B, const AlignParams &P, Ho
         DBuf<Seed> seeds(nseeds); DBuf<uint8_t> consumed(n); consumed.zero(s);
         DN_LAUNCH(k_seeds, (nbands + 255) / 256, 256, 0, s, (const ulonglong2 *)hs, (const int32_t *)bfirst.p, (const u64 *)bkey.p,
                   (const uint8_t *)hot.p, (const int32_t *)cstart.p, (const int32_t *)cidx.p, nbands, SG, seeds.p, consumed.p);
-        cov.release(); bflag.release(); bidx.release(); covsum.release();
         out.stats.seeds += nseeds; out.stats.extensions += 2ll * nseeds;
         ms_seed += ts_.stop();
 
@@ -345,13 +344,14 @@ void align_blocks(const DevBlock &A, const DevBlock &B, const AlignParams &P, Ho
         DBuf<Cand> rc((size_t)nvalid + 1); DBuf<uint16_t> rtr((size_t)2 * ntr + 2);
         launch_write_traces(seeds.p, nseeds, EG, tile_off.p, tiles.p, outs.p, cand_all.p, valid.p, vidx.p, toff.p, rc.p, rtr.p, s);
         DBuf<int32_t> keep(n), kidx(n);
-        launch_retire((const ulonglong2 *)hs, n, consumed.p, rc.p, nvalid, SG, P.w, keep.p, s);
+        launch_retire((const ulonglong2 *)hs, n, consumed.p, rc.p, nvalid, SG, P.w, bflag.p, bidx.p, hot.p, keep.p, s);
         exclusive_scan_i32(keep.p, kidx.p, n, dtot32.p, s);
         const int64_t n_new = d2h_scalar(dtot32.p, s);
         launch_compact_hits((const ulonglong2 *)hs, n, keep.p, kidx.p, ho, s);
         DN_CUDA(cudaStreamSynchronize(s));
         std::swap(hs, ho);
         abytes += 24 * n + 16 * n_new;
+        if (getenv("DN_TRACE")) fprintf(stderr, "[dn trace] round %d: %lld hits, %d bands, %d seeds, %d candidates >= minlen, %lld hits left\n", round, (long long)(n), nbands, nseeds, nvalid, (long long)n_new);
         n = n_new;
         round_beg.push_back(round_beg.back() + nvalid);
         round_ntr.push_back(2 * ntr);
@@ -386,6 +386,7 @@ void align_blocks(const DevBlock &A, const DevBlock &B, const AlignParams &P, Ho
         unsigned long long hctr[3];
         DN_CUDA(cudaMemcpyAsync(hctr, ctr.p, sizeof hctr, cudaMemcpyDeviceToHost, s)); DN_CUDA(cudaStreamSynchronize(s));
         const int nkeep = ncand - (int)hctr[0];
+        if (getenv("DN_TRACE")) fprintf(stderr, "[dn trace] candidates %d, kept after duplicate removal %d\n", ncand, nkeep);
         tr.mark("dedupe + final sort");
         out.nrec = nkeep;
         out.rec = (dn_las_record *)hcache_alloc(sizeof(dn_las_record) * ((size_t)nkeep + 1));

@@ -424,10 +424,15 @@ __device__ __forceinline__ int group_lower(const Cand *__restrict__ c, int lo, i
 }
 
 __global__ void __launch_bounds__(256) k_retire(const ulonglong2 *__restrict__ hits, int64_t n, const uint8_t *__restrict__ consumed,
-                                                const Cand *__restrict__ rc, int nrc, SeedGeom G, int w, int32_t *__restrict__ keep) {
+                                                const Cand *__restrict__ rc, int nrc, SeedGeom G, int w,
+                                                const int32_t *__restrict__ bflag, const int32_t *__restrict__ bidx,
+                                                const uint8_t *__restrict__ hot, int32_t *__restrict__ keep) {
     int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     int kp = consumed[i] ? 0 : 1;
+    // a hit in a cold band can never become part of a hot band later (scores only shrink): drop it for good.
+    // Pure optimisation -- the later rounds see exactly the clusters they would have seen anyway.
+    if (kp && !hot[bflag[i] ? bidx[i] : bidx[i] - 1]) kp = 0;
     if (kp && nrc > 0) {
         ulonglong2 h = hits[i];
         u64 gd = h.x & ((1ull << G.gdbits) - 1ull);
@@ -557,8 +562,8 @@ void launch_write_traces(const Seed *seeds, int nseeds, ExtGeom G, const int64_t
               toff, cand_out, trace);
 }
 void launch_retire(const ulonglong2 *hits, int64_t n, const uint8_t *consumed, const Cand *rc, int nrc, SeedGeom G, int w,
-                   int32_t *keep, cudaStream_t s) {
-    DN_LAUNCH(k_retire, (unsigned)((n + 255) / 256), 256, 0, s, hits, n, consumed, rc, nrc, G, w, keep);
+                   const int32_t *bflag, const int32_t *bidx, const uint8_t *hot, int32_t *keep, cudaStream_t s) {
+    DN_LAUNCH(k_retire, (unsigned)((n + 255) / 256), 256, 0, s, hits, n, consumed, rc, nrc, G, w, bflag, bidx, hot, keep);
 }
 void launch_compact_hits(const ulonglong2 *hits, int64_t n, const int32_t *keep, const int32_t *kidx, ulonglong2 *out, cudaStream_t s) {
     DN_LAUNCH(k_compact_hits, (unsigned)((n + 255) / 256), 256, 0, s, hits, n, keep, kidx, out);
