@@ -319,7 +319,7 @@ void align_blocks(const DevBlock &A, const DevBlock &B, const AlignParams &P, Ho
         const int64_t ntile_cap = d2h_scalar(dtotal.p, s);
         DBuf<int2> tiles((size_t)ntile_cap + 1); DBuf<ExtOut> outs(2 * (size_t)nseeds);
         const int wpc = ext_warps_per_cta();
-        int ctas = sm_count() * 4;
+        int ctas = sm_count() * 4;      // 63 registers: 4 CTAs x 8 warps per SM (5 CTAs at 48 registers measured slower)
         { int64_t need = (2ll * nseeds + wpc - 1) / wpc; if (ctas > need) ctas = (int)need;
           const int64_t budget = 24ll << 30;   // bytes of HBM for trace-record pools
           int64_t maxc = budget / (pool_stride * 16 * wpc); if (maxc < 1) maxc = 1;

@@ -254,7 +254,13 @@ __global__ void __launch_bounds__(256) k_join_emit(const u64 *__restrict__ ta, c
 // Presence bitmap over k-mers (bit = kmer mod 2^28; exact for k <= 14): 32 MB, L2-resident.  Four out of
 // five read k-mers carry a sequencing error and occur nowhere in A; the bitmap rejects them with ONE
 // sector read instead of the table + list walk.
-__device__ __forceinline__ u32 kbit_index(u32 km) { return (km * 0x9E3779B1u) >> (32 - KBITS_LOG2); }   // multiplicative hash
+// blocked Bloom filter: one 32-bit word per k-mer (multiplicative hash), three bits inside it (second hash):
+// a probe touches ONE sector; 2^27 bits = 16 MB for ~1 % false positives at 10 M distinct k-mers
+__device__ __forceinline__ void kbit_slot(u32 km, u32 &word, u32 &mask) {
+    word = (km * 0x9E3779B1u) >> (32 - (KBITS_LOG2 - 5));
+    const u32 h = km * 0x85EBCA6Bu;
+    mask = (1u << (h >> 27)) | (1u << ((h >> 22) & 31u)) | (1u << ((h >> 17) & 31u));
+}
 
 __global__ void __launch_bounds__(256) k_kmer_bitmap(const u64 *__restrict__ ta, int64_t na, u32 *__restrict__ bits) {
     int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -262,12 +268,12 @@ __global__ void __launch_bounds__(256) k_kmer_bitmap(const u64 *__restrict__ ta,
     const u32 km = (u32)(ta[i] >> 32);
     if (km == 0xffffffffu) return;
     if (i > 0 && (u32)(ta[i - 1] >> 32) == km) return;          // one atomic per distinct k-mer
-    const u32 b = kbit_index(km);
-    atomicOr(&bits[b >> 5], 1u << (b & 31));
+    u32 word, mask; kbit_slot(km, word, mask);
+    atomicOr(&bits[word], mask);
 }
 __device__ __forceinline__ bool kmer_present(const u32 *__restrict__ bits, u32 km) {
-    const u32 b = kbit_index(km);
-    return (bits[b >> 5] >> (b & 31)) & 1u;
+    u32 word, mask; kbit_slot(km, word, mask);
+    return (bits[word] & mask) == mask;
 }
 
 struct WordKmers { u64 v; u64 mwin; int p0, L, r; };

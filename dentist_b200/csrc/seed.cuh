@@ -4,7 +4,7 @@
 
 namespace dn {
 
-constexpr int KBITS_LOG2 = 28;      // k-mer presence filter: 2^28 bits = 32 MB (hashed; false positives only cost a lookup; 2^26 measured slower)
+constexpr int KBITS_LOG2 = 27;      // k-mer presence filter (blocked Bloom, 3 bits per k-mer): 2^27 bits = 16 MB
 
 struct Seed { int32_t a, bs, apos, bpos; };
 
