@@ -31,6 +31,7 @@ extern std::atomic<unsigned long long> g_launches;   // kernels launched by this
 struct Arena {
     struct Chunk { char *p; size_t cap, used; };
     std::vector<Chunk> chunks;
+    std::vector<void *> loose;                // DN_NO_ARENA=1: one cudaMalloc per buffer so compute-sanitizer sees every bound
     size_t high = 0, cur = 0;                 // bytes handed out in this call / high-water mark
     void *alloc(size_t bytes);
     void reset();                             // start of a call: reclaim everything, coalesce chunks

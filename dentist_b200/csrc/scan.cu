@@ -2,6 +2,7 @@
 // tile sums, tile scan + offset).  HBM-bound: reads the input twice, writes the output once.
 #include "common.cuh"
 #include <mutex>
+#include <stdlib.h>
 
 namespace dn {
 
@@ -10,6 +11,8 @@ std::atomic<unsigned long long> g_launches{0};
 Arena &arena() { static Arena a; return a; }
 
 void *Arena::alloc(size_t bytes) {
+    static const bool no_arena = getenv("DN_NO_ARENA") != nullptr;
+    if (no_arena) { void *p = nullptr; DN_CUDA(cudaMalloc(&p, bytes ? bytes : 1)); loose.push_back(p); return p; }
     bytes = (bytes + 511) & ~(size_t)511;
     cur += bytes; if (cur > high) high = cur;
     if (!chunks.empty()) {
@@ -24,6 +27,7 @@ void *Arena::alloc(size_t bytes) {
 }
 
 void Arena::reset() {
+    if (!loose.empty()) { cudaDeviceSynchronize(); for (void *p : loose) cudaFree(p); loose.clear(); }
     cur = 0;
     if (chunks.size() > 1 || (chunks.size() == 1 && chunks[0].cap < high)) {     // coalesce into one slab of the high-water size
         cudaDeviceSynchronize();
