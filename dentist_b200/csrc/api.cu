@@ -103,6 +103,18 @@ int dn_block_upload(const dn_block_desc *desc, dn_block **out) {
         *out = b; return DN_OK;
     });
 }
+int dn_block_crop(const dn_block *src, int32_t n, const int32_t *read, const int32_t *begin, const int32_t *end, const int32_t *group,
+                  dn_block **out) {
+    if (!src || !out || n < 0 || (n && (!read || !begin || !end))) return fail(DN_ERR_INVALID, "null argument");
+    std::lock_guard<std::mutex> lk(g_mu);
+    if (int rc = ensure_device()) return rc;
+    return guarded([&] {
+        cudaSetDevice(g_device);
+        dn_block *b = new dn_block();
+        try { block_crop(src->b, n, read, begin, end, group, b->b, g_stream); } catch (...) { delete b; throw; }
+        *out = b; return DN_OK;
+    });
+}
 void dn_block_free(dn_block *blk) {
     if (!blk) return;
     std::lock_guard<std::mutex> lk(g_mu);

@@ -118,6 +118,63 @@ void block_upload(const dn_block_desc &d, DevBlock &B, cudaStream_t s) {
     DN_CUDA(cudaStreamSynchronize(s));
 }
 
+// ------------------------------------------------------------------------- crop
+// Cropped pile-up reads straight from the resident read block (cropper.d:383-421 builds a FASTA and a
+// fresh DB instead): output read i = bases [begin, end) of source read `read[i]`.  Both strands are
+// shifted copies: fwd_out = fwd_src + begin, rc_out = rc_src + (L - end).  One thread per output word.
+__global__ void __launch_bounds__(128) k_crop(const u32 *__restrict__ sfwd, const u32 *__restrict__ src_rc,
+                                              const int64_t *__restrict__ soff, const int32_t *__restrict__ slen,
+                                              const int32_t *__restrict__ read, const int32_t *__restrict__ begin,
+                                              const int32_t *__restrict__ len, const int64_t *__restrict__ off,
+                                              u32 *__restrict__ fwd, u32 *__restrict__ rc) {
+    const int r = blockIdx.x;
+    const int L = len[r], s = read[r];
+    const int64_t gf = soff[s] + begin[r], gr = soff[s] + (slen[s] - (begin[r] + L));
+    const int64_t w0 = off[r] >> 4;
+    const int nw = (int)((off[r + 1] - off[r]) >> 4);
+    for (int w = threadIdx.x; w < nw; w += blockDim.x) {
+        const int p = w * 16, n = min(16, L - p);
+        u32 f = 0, c = 0;
+        if (n > 0) {
+            const int64_t a = gf + p, b = gr + p;
+            f = __funnelshift_r(sfwd[a >> 4], sfwd[(a >> 4) + 1], (int)(a & 15) << 1);
+            c = __funnelshift_r(src_rc[b >> 4], src_rc[(b >> 4) + 1], (int)(b & 15) << 1);
+            if (n < 16) { const u32 m = (1u << (2 * n)) - 1u; f &= m; c &= m; }
+        }
+        fwd[w0 + w] = f; rc[w0 + w] = c;
+    }
+}
+
+void block_crop(const DevBlock &S, int n, const int32_t *read, const int32_t *begin, const int32_t *end, const int32_t *group,
+                DevBlock &B, cudaStream_t s) {
+    B.nreads = n; B.h_len.resize(n); B.h_off.resize(n + 1);
+    int64_t g = 0; B.maxlen = 0; B.total_real = 0;
+    for (int r = 0; r < n; r++) {
+        if (read[r] < 0 || read[r] >= S.nreads) throw Error("crop: read id out of bounds");
+        if (begin[r] < 0 || end[r] < begin[r] || end[r] > S.h_len[read[r]]) throw Error("crop: slice outside the read");
+        const int L = end[r] - begin[r];
+        B.h_len[r] = L; B.h_off[r] = g; g += ((int64_t)L + 63) / 64 * 64;
+        if (L > B.maxlen) B.maxlen = L;
+        B.total_real += L;
+    }
+    B.h_off[n] = g; B.total = g;
+    const size_t nwords = (size_t)(g >> 4) + 8;
+    B.fwd.persistent(nwords); B.rc.persistent(nwords); B.fwd.zero(s); B.rc.zero(s);
+    B.off.persistent(n + 1); B.len.persistent(n > 0 ? n : 1); B.chunk2read.persistent((size_t)(g >> 10) + 2); B.chunk2read.zero(s);
+    DN_CUDA(cudaMemcpyAsync(B.off.p, B.h_off.data(), sizeof(int64_t) * (n + 1), cudaMemcpyHostToDevice, s));
+    B.has_mask = false; B.has_group = group != nullptr;
+    if (n == 0) { DN_CUDA(cudaStreamSynchronize(s)); return; }
+    DN_CUDA(cudaMemcpyAsync(B.len.p, B.h_len.data(), sizeof(int32_t) * n, cudaMemcpyHostToDevice, s));
+    DBuf<int32_t> dread, dbeg; dread.persistent(n); dbeg.persistent(n);
+    DN_CUDA(cudaMemcpyAsync(dread.p, read, sizeof(int32_t) * n, cudaMemcpyHostToDevice, s));
+    DN_CUDA(cudaMemcpyAsync(dbeg.p, begin, sizeof(int32_t) * n, cudaMemcpyHostToDevice, s));
+    if (group) { B.group.persistent(n); DN_CUDA(cudaMemcpyAsync(B.group.p, group, sizeof(int32_t) * n, cudaMemcpyHostToDevice, s)); }
+    DN_LAUNCH(k_crop, n, 128, 0, s, (const u32 *)S.fwd.p, (const u32 *)S.rc.p, (const int64_t *)S.off.p, (const int32_t *)S.len.p,
+              (const int32_t *)dread.p, (const int32_t *)dbeg.p, (const int32_t *)B.len.p, (const int64_t *)B.off.p, B.fwd.p, B.rc.p);
+    DN_LAUNCH(k_chunk2read, (n + 255) / 256, 256, 0, s, (const int64_t *)B.off.p, n, B.chunk2read.p);
+    DN_CUDA(cudaStreamSynchronize(s));
+}
+
 // ------------------------------------------------------------------------- K1: k-mer tuples
 
 // One thread per 16-base word of the padded block: emits 16 tuples (kmer << 32 | payload).

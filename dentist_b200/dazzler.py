@@ -73,6 +73,22 @@ class Block:
         self.bases = int(_lib.lib().dn_block_bases(self._h))
         self.h2d_bytes = int(data.nbytes + rlen.nbytes + bo.nbytes)
 
+    @classmethod
+    def crop(cls, src, read, begin, end, group=None):
+        """Cropped reads of `src` as a new resident block (cropper.d:383-421 without FASTA / DB files)."""
+        read = np.ascontiguousarray(read, np.int32); begin = np.ascontiguousarray(begin, np.int32); end = np.ascontiguousarray(end, np.int32)
+        grp = None if group is None else np.ascontiguousarray(group, np.int32)
+        self = cls.__new__(cls)
+        self._keep = []; self._desc = None
+        self._h = C.c_void_p()
+        _lib.check(_lib.lib().dn_block_crop(src._h, len(read), read.ctypes.data_as(C.c_void_p), begin.ctypes.data_as(C.c_void_p),
+                                            end.ctypes.data_as(C.c_void_p), None if grp is None else grp.ctypes.data_as(C.c_void_p),
+                                            C.byref(self._h)))
+        self.nreads = len(read)
+        self.bases = int(_lib.lib().dn_block_bases(self._h))
+        self.h2d_bytes = int(read.nbytes * 3)
+        return self
+
     def free(self):
         if self._h:
             _lib.lib().dn_block_free(self._h)

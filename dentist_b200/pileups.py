@@ -20,6 +20,36 @@ TSPACE = 126           # forceLargeTracePointType, dazzler.d:154
 MIN_ANCHOR = 500       # commandline.d:2036, 2894
 
 
+def translate_trace_point(abpos, aepos, bbpos, tspace, trace, pos):
+    """Trace.translateTracePoint!\"contigA\"(pos, RoundingMode.floor) (base.d:185-229): the read coordinate that the
+    trace points map the last tile boundary at or below `pos` to.  Returns (contigA pos, contigB pos)."""
+    if not (abpos <= pos <= aepos):
+        raise ValueError("position outside the alignment")
+    second = (abpos // tspace) * tspace + tspace
+    if pos < second:
+        idx = 0
+    elif pos < aepos:
+        idx = 1 + (pos - second) // tspace
+    else:
+        idx = len(trace)
+    b = bbpos + int(sum(int(t[1]) for t in trace[:idx]))
+    a = abpos if idx == 0 else ((abpos // tspace) * tspace + idx * tspace if idx < len(trace) else aepos)
+    return a, b
+
+
+def get_cropping_slice(abpos, aepos, bbpos, tspace, trace, complement, seed, read_len, crop_ref_pos):
+    """getCroppingSlice (cropper.d:503-550): the part of the read that is kept when the pile-up is cropped at
+    reference position `crop_ref_pos`; seed = 'front' | 'back' (AlignmentLocationSeed).  Forward read coordinates."""
+    _, cpos = translate_trace_point(abpos, aepos, bbpos, tspace, trace, crop_ref_pos)
+    if seed == "front":
+        b, e = 0, cpos
+    else:
+        b, e = cpos, read_len
+    if complement:
+        b, e = read_len - e, read_len - b
+    return b, e
+
+
 def find_reference_read_candidates(qv, qoff, reads):
     """package.d:518-568 for one pile: reads ranked by (numBadQVs, meanQV, readId); returns read ids."""
     hist = np.zeros(MAX_QV, np.int64)

@@ -125,6 +125,11 @@ void dn_las_free(dn_las_buf *buf);
 typedef struct dn_block dn_block;   /* opaque: a sequence block resident in HBM */
 /* H2D copy + on-device 2-bit packing / reverse complement.  Replaces daligner's DB load. */
 int dn_block_upload(const dn_block_desc *desc, dn_block **out);
+/* Cropped pile-up reads without leaving HBM (replaces getCroppedReadAsFasta + buildDbFile, cropper.d:171, 383-421):
+ * output read i = bases [begin[i], end[i]) of read[i] of `src` (forward coordinates, as getCroppingSlice
+ * cropper.d:503-550 returns them); `group` (optional) = pile-up id per output read. */
+int dn_block_crop(const dn_block *src, int32_t n, const int32_t *read, const int32_t *begin, const int32_t *end, const int32_t *group,
+                  dn_block **out);
 void dn_block_free(dn_block *blk);
 int64_t dn_block_bases(const dn_block *blk);
 

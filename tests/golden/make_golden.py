@@ -58,10 +58,27 @@ def main():
     cons = dict(reads=["".join(r.split("\\n")[1:]) for r in fa], minlen=15, allowance=100, expected_read=2)
     with open(os.path.join(HERE, "consensus_kat.json"), "w") as f:
         json.dump(cons, f, indent=1)
+    # getCroppingSlice KATs  commands/processPileUps/cropper.d:552-647
+    cp = os.path.join(REF, "commands/processPileUps/cropper.d")
+    txt = "\n".join(lines(cp, 552, 647))
+    cases = []
+    for blk in txt.split("enum alignment = SeededAlignment(")[1:]:
+        contigs = re.findall(r"Contig\((\d+), (\d+)\)", blk)
+        loci = re.findall(r"Locus\((\d+), (\d+)\)", blk)
+        tps = [[int(a), int(b)] for a, b in re.findall(r"TracePoint\(\s*(\d+),\s*(\d+)\)", blk)]
+        comp = "AlignmentFlags(complement)" in blk
+        seed = re.search(r"AlignmentLocationSeed\.(\w+)", blk).group(1)
+        asserts = [[int(p), int(b), int(e)] for p, b, e in
+                   re.findall(r"ReferencePoint\(1, (\d+)\)\]\) ==\s*ReadInterval\(\d+, (\d+), (\d+)\)", blk)]
+        cases.append(dict(read_len=int(contigs[1][1]), abpos=int(loci[0][0]), aepos=int(loci[0][1]), bbpos=int(loci[1][0]),
+                          bepos=int(loci[1][1]), trace=tps, complement=comp, seed=seed, tspace=100, asserts=asserts))
+    with open(os.path.join(HERE, "cropper_kat.json"), "w") as f:
+        json.dump(cases, f, indent=1)
     out = dict(source="a-ludi/dentist @ 1aa60e04", tspace=100, ladump=dump, flat=flat, chains=chains, trace_kat=kat)
     with open(os.path.join(HERE, "las_golden.json"), "w") as f:
         json.dump(out, f, indent=1)
-    print("flat", len(flat), "chains", len(chains), "dump lines", len(dump), "kat tiles", len(tps), "asserts", len(asserts))
+    print("flat", len(flat), "chains", len(chains), "dump lines", len(dump), "kat tiles", len(kat["trace"]), "asserts", len(kat["asserts"]),
+          "cropper cases", len(cases), "consensus reads", len(cons["reads"]))
 
 
 if __name__ == "__main__":
