@@ -154,8 +154,8 @@ def oracle_piles_threads(reads, group, piles, nthreads):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=5)
-    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="b200")
     ap.add_argument("--scale", type=float, default=1.0, help="shrink the workload (tests only; 1.0 = configs[1])")
     ap.add_argument("--cpu-sample-mbp", type=float, default=16.0)
@@ -178,8 +178,11 @@ def main():
         ref, reads = make_workload(args.scale, 0)
         times, aligned = [], 0
         sample = ""
+        # bounded sample per step: the whole --steps K --warmup W run stays within ~2 minutes of CPU time
+        # (the port maps ~0.07 Mbp of reads per second and thread against this assembly)
+        per_step_mbp = max(1.0, min(args.cpu_sample_mbp, 0.07 * cores * 100.0 / (args.steps + 0.25 * args.warmup)))
         for it in range(args.warmup + args.steps):
-            a, dt, sample = oracle_threads(ref, reads, cores, args.cpu_sample_mbp * 1e6 * (1 if it >= args.warmup else 0.25))
+            a, dt, sample = oracle_threads(ref, reads, cores, per_step_mbp * 1e6 * (1 if it >= args.warmup else 0.25))
             if it >= args.warmup:
                 times.append(dt); aligned += a
         v = aligned / 1e9 / sum(times)

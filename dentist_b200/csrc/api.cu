@@ -306,6 +306,41 @@ int dn_dbdust(const char *db, const char *const *opts, int nopts) {
     });
 }
 
+int dn_consensus_db(const char *db, const char *las, uint32_t read_id_1based, const char *const *opts, int nopts, char *out_db, size_t cap) {
+    (void)opts; (void)nopts;                                   // daccord options (-t, -w, -a, -k ...) have no effect here
+    if (!db || !las || !out_db || read_id_1based == 0) return fail(DN_ERR_INVALID, "null argument");
+    return guarded([&]() -> int {
+        HostDb D; std::string err;
+        if (!read_dazz_db(db, {}, D, err)) return fail(DN_ERR_IO, err);
+        if (read_id_1based > D.rlen.size()) return fail(DN_ERR_INVALID, "read id out of bounds");
+        dn_las_buf L; memset(&L, 0, sizeof L);
+        if (int rc = dn_las_read(las, &L)) return rc;
+        if (L.nrec == 0) { dn_las_free(&L); return fail(DN_ERR_EMPTY, "empty pre-consensus alignment"); }   // dazzler.d:4246-4249
+        dn_block_desc d = D.desc();
+        dn_block *blk = nullptr;
+        int rc = dn_block_upload(&d, &blk);
+        if (rc) { dn_las_free(&L); return rc; }
+        const int32_t r = (int32_t)read_id_1based - 1;                       // daccord -I<i>,<i> is 0-based, dazzler.d:4225-4227
+        dn_seq_buf s; memset(&s, 0, sizeof s);
+        rc = dn_consensus(blk, &L, &r, 1, &s);
+        dn_block_free(blk); dn_las_free(&L);
+        if (rc) return rc;
+        const int64_t n = s.off[1] - s.off[0];
+        if (n <= 0) { dn_seq_free(&s); return fail(DN_ERR_EMPTY, "empty consensus"); }                     // dazzler.d:4232-4235
+        // <db dir>/<db root>-daccord-I<i>-<i>.dam  (dazzler.d:6187-6220)
+        std::string p(db);
+        size_t sl = p.find_last_of('/'); std::string dir = sl == std::string::npos ? "." : p.substr(0, sl);
+        std::string out = dir + "/" + D.name + "-daccord-I" + std::to_string(r) + "-" + std::to_string(r) + ".dam";
+        std::vector<std::vector<uint8_t>> reads(1);
+        reads[0].assign(s.bases + s.off[0], s.bases + s.off[1]);
+        dn_seq_free(&s);
+        if (!write_dazz_db(out, reads, err)) return fail(DN_ERR_IO, err);
+        if (out.size() + 1 > cap) return fail(DN_ERR_INVALID, "output path buffer too small");
+        memcpy(out_db, out.c_str(), out.size() + 1);
+        return DN_OK;
+    });
+}
+
 int dn_dalign(const char *dbA, const char *dbB, const char *const *opts, int nopts, const char *outdir) {
     return align_files(dbA, dbB, opts, nopts, outdir, false);
 }

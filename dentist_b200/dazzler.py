@@ -326,3 +326,11 @@ def dbdustFile(dbFile, opts=()):
     """dazzler.d:3815-3818 on a DB file: writes the `dust` track next to it."""
     arr, n = _opts(list(opts))
     _lib.check(_lib.lib().dn_dbdust(dbFile.encode(), arr, n))
+
+
+def getConsensusDb(dbFile, filteredLasFile, readId, opts=()):
+    """dazzler.d:4213-4238 (file form): returns the path of the consensus .dam; raises "empty consensus"."""
+    arr, n = _opts(list(opts))
+    out = C.create_string_buffer(4096)
+    _lib.check(_lib.lib().dn_consensus_db(dbFile.encode(), filteredLasFile.encode(), int(readId), arr, n, out, 4096))
+    return out.value.decode()

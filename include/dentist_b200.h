@@ -203,6 +203,11 @@ int dn_dust_block(const dn_block *blk, int32_t window, double threshold, int32_t
 int dn_dalign(const char *dbA, const char *dbB, const char *const *opts, int nopts, const char *outdir);
 /* dbdust(dbFile, dbdustOptions)  dazzler.d:3815-3818: writes the `dust` track (.<db>.dust.anno/.data). */
 int dn_dbdust(const char *db, const char *const *opts, int nopts);
+/* getConsensus(dbFile, filteredLasFile, readId, options)  dazzler.d:4213-4255: consensus of read `read_id_1based`
+ * (DENTIST ids are 1-based; daccord's -I is 0-based, :4225-4227) over the alignments in `las`; writes
+ * <dir>/<db>-daccord-I<i>-<i>.dam (+ hidden .idx/.bps/.hdr) holding exactly one read and returns its path in
+ * out_db.  DN_ERR_EMPTY ("empty consensus", :4232-4235) when nothing comes back. */
+int dn_consensus_db(const char *db, const char *las, uint32_t read_id_1based, const char *const *opts, int nopts, char *out_db, size_t cap);
 /* getDamapping(refDb, queryDb, opts, outdir)  dazzler.d:3855-3866 / damapper() :6163-6170. */
 int dn_damap(const char *refDb, const char *queryDb, const char *const *opts, int nopts, const char *outdir);
 

@@ -101,3 +101,28 @@ def test_dbdust_writes_a_track_that_mdust_reads(tmp_path):
     # -mdust now changes the seeds
     out = dazzler.getDalignment(db, None, ["-s126", "-l500", "-mdust"], str(tmp_path))
     assert out.endswith("x.x.las")
+
+
+def test_getConsensus_file_form_on_the_reference_kat(tmp_path):
+    """dazzler.d:4257-4299 through files: buildDamFile -> daligner -l15 -> filterPileUpAlignments -> getConsensus
+    -> the consensus .dam holds exactly one read, equal to read 3."""
+    import struct
+    from dentist_b200 import dazzler
+    from tests.test_pile_oracle import kat_block
+    k, blk = kat_block()
+    db = str(tmp_path / "kat.dam")
+    dbutil.write_db(db, blk)
+    las_path = dazzler.getDalignment(db, None, ["-l%d" % k["minlen"], "-s100"], str(tmp_path))
+    ts, rec, toff, tr = dazzler.read_las(las_path)
+    assert len(rec) == 6
+    out = dazzler.getConsensusDb(db, las_path, 1)
+    assert out == str(tmp_path / "kat-daccord-I0-0.dam")
+    idx = open(str(tmp_path / ".kat-daccord-I0-0.idx"), "rb").read()
+    bps = open(str(tmp_path / ".kat-daccord-I0-0.bps"), "rb").read()
+    ureads, = struct.unpack_from("<i", idx, 0)
+    rlen, = struct.unpack_from("<i", idx, 112 + 4)
+    assert ureads == 1 and rlen == 1050
+    codes = np.array([(b >> s) & 3 for b in bps for s in (6, 4, 2, 0)], np.uint8)[:rlen]
+    assert np.array_equal(codes, blk.read(k["expected_read"]))
+    with pytest.raises(dazzler.DnError, match="out of bounds"):
+        dazzler.getConsensusDb(db, las_path, 9)
