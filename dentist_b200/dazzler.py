@@ -334,3 +334,31 @@ def getConsensusDb(dbFile, filteredLasFile, readId, opts=()):
     out = C.create_string_buffer(4096)
     _lib.check(_lib.lib().dn_consensus_db(dbFile.encode(), filteredLasFile.encode(), int(readId), arr, n, out, 4096))
     return out.value.decode()
+
+
+def collectFilter(las, alen, blen, repeat_mask=None, max_alignment_error=0.3, proper_alignment_allowance=100, min_anchor_length=500):
+    """collectPileUps' filterAlignments (collectPileUps/package.d:129-160, filter.d:122-356) on a chained LAS.
+    repeat_mask: per A contig a sorted list of disjoint (begin, end).  Returns (first record of each chain,
+    status per chain, sorted list of B reads the filters consumed)."""
+    L = _lib.lib()
+    alen = np.ascontiguousarray(alen, np.int32); blen = np.ascontiguousarray(blen, np.int32)
+    anno = data = None
+    if repeat_mask is not None:
+        anno = np.zeros(len(alen) + 1, np.int64); flat = []
+        for r in range(len(alen)):
+            anno[r] = 4 * len(flat)
+            for b, e in repeat_mask[r] if r < len(repeat_mask) else []:
+                flat += [b, e]
+        anno[len(alen)] = 4 * len(flat)
+        data = np.ascontiguousarray(flat if flat else [0, 0], np.int32)
+    n = C.c_int64(0); first = C.POINTER(C.c_int32)(); st = C.POINTER(C.c_uint8)(); used = C.POINTER(C.c_uint8)()
+    _lib.check(L.dn_collect_filter(C.byref(las._buf), alen.ctypes.data_as(C.c_void_p), len(alen), blen.ctypes.data_as(C.c_void_p), len(blen),
+                                   None if anno is None else anno.ctypes.data_as(C.c_void_p), None if data is None else data.ctypes.data_as(C.c_void_p),
+                                   C.c_double(max_alignment_error), int(proper_alignment_allowance), int(min_anchor_length),
+                                   C.byref(n), C.byref(first), C.byref(st), C.byref(used)))
+    nc = int(n.value)
+    f = np.ctypeslib.as_array(first, shape=(max(nc, 1),))[:nc].copy()
+    s_ = np.ctypeslib.as_array(st, shape=(max(nc, 1),))[:nc].copy()
+    u = np.ctypeslib.as_array(used, shape=(max(len(blen), 1),))[:len(blen)].copy()
+    L.dn_free(first); L.dn_free(st); L.dn_free(used)
+    return f, s_, np.flatnonzero(u).tolist()

@@ -189,6 +189,16 @@ int dn_las_chain(dn_las_buf *las, int32_t max_indel, int32_t max_chain_gap, doub
  * AlignmentChains at :708-743.  `las` must be in LAsort order (as dn_align_blocks returns it). */
 int dn_las_chain_mapper(dn_las_buf *las, int32_t nb_reads, int32_t max_indel, int32_t max_gap);
 
+/* The alignment filters of collectPileUps (commands/collectPileUps/filter.d:122-356, order of package.d:129-141:
+ * LQ, Improper, WeaklyAnchored, Contained, Ambiguous, Redundant) over the AlignmentChains of a chained
+ * ref-vs-reads LAS (`las` in LAsort order with START/NEXT flags).  mask_* = repeat mask on the A contigs in
+ * the track layout (may be NULL).  Returns per chain the index of its first record and a status byte
+ * (0 kept, 1 LQ, 2 improper, 3 weakly anchored, 4 contained, 5 ambiguous read, 6 redundant read, 7 disabled on
+ * input) and per B read whether the filters consumed it (removed from `unusedReads`).  Free with dn_free. */
+int dn_collect_filter(const dn_las_buf *las, const int32_t *alen, int32_t na, const int32_t *blen, int32_t nb,
+                      const int64_t *mask_anno, const int32_t *mask_data, double max_err, int32_t allowance, int32_t min_anchor,
+                      int64_t *nchains, int32_t **chain_first, uint8_t **chain_status, uint8_t **read_used);
+
 /* dbdust(db, opts)  dazzler.d:3815-3818 (`DBdust -w -t -m`): low-complexity intervals of every read of a
  * resident block in the reference's mask-track layout (dazzler.d:4943-5052): *anno = nreads+1 int64
  * byte offsets into *data, *data = int32 (begin,end) pairs.  Free both with dn_free.  Feed them to
