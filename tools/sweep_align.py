@@ -12,6 +12,8 @@ def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--ref-mbp", type=float, default=50); ap.add_argument("--reads-mbp", type=float, default=50)
     ap.add_argument("--out", default="gpurun_out/sweep_align.jsonl"); ap.add_argument("--cpu", action="store_true")
+    ap.add_argument("--lens", default="1000,2000,5000,10000,20000,50000,100000"); ap.add_argument("--errors", default="0.05,0.10,0.15")
+    ap.add_argument("--ont", action="store_true", help="ONT-like error mix and a log-normal length spread (configs[2] reads)")
     a = ap.parse_args()
     dazzler.init(0)
     n_sc = max(1, int(a.ref_mbp))
@@ -19,9 +21,12 @@ def main():
     ref, _ = synth.contigs_from(sc, [[] for _ in sc])
     ga = dazzler.Block(ref.off, ref.bases)
     out = open(a.out, "w")
-    for L in (1000, 2000, 5000, 10000, 20000, 50000, 100000):
-        for ei, e in enumerate((0.05, 0.10, 0.15)):
-            reads, _ = synth.simulate_reads(sc, a.reads_mbp / a.ref_mbp, L, 1, e, 4002 + ei + L, min_len=L, lognormal=False)
+    for L in [int(x) for x in a.lens.split(",")]:
+        for ei, e in enumerate([float(x) for x in a.errors.split(",")]):
+            if a.ont:
+                reads, _ = synth.simulate_reads(sc, a.reads_mbp / a.ref_mbp, L, L // 2, e, 2003, mix=(0.25, 0.45, 0.30))
+            else:
+                reads, _ = synth.simulate_reads(sc, a.reads_mbp / a.ref_mbp, L, 1, e, 4002 + ei + L, min_len=L, lognormal=False)
             gb = dazzler.Block(reads.off, reads.bases)
             minlen = min(1000, L // 2)
             for _ in range(2):
