@@ -137,12 +137,12 @@ void align_blocks(const DevBlock &A, const DevBlock &B, const AlignParams &P, Ho
     int64_t H = 0;
     abytes += 8 * nA + 4ll * nq;
     if (lookup) {
-        // B's tuples are never materialised: count, scan, emit straight from the packed sequence
+        // B's tuples are never materialised: hits come straight from the packed sequence
         const int64_t nwB = nB >> 4;
-        DBuf<u32> wcnt(2 * nwB); DBuf<int64_t> woff(2 * nwB);
+        const int nseg = 2 * B.nreads;
         DBuf<u32> kbits((1u << KBITS_LOG2) / 32); kbits.zero(s);
         DN_LAUNCH(k_kmer_bitmap, (unsigned)((nA + 255) / 256), 256, 0, s, (const u64 *)sa, nA, kbits.p);
-        // pin the 32 MB bitmap in the persisting part of L2 while the streaming lookups run
+        // pin the k-mer filter in the persisting part of L2 while the streaming lookups run
         {
             static bool limit_set = false;
             if (!limit_set) { cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, 48u << 20); cudaGetLastError(); limit_set = true; }
@@ -152,84 +152,82 @@ void align_blocks(const DevBlock &A, const DevBlock &B, const AlignParams &P, Ho
             av.accessPolicyWindow.missProp = cudaAccessPropertyStreaming;
             cudaStreamSetAttribute(s, cudaStreamAttributeAccessPolicyWindow, &av); cudaGetLastError();
         }
-        for (int st = 0; st < 2; st++) {
-            const u32 *mb = B.has_mask ? (st ? B.mask_rc.p : B.mask.p) : nullptr;
-            DN_LAUNCH(k_lookup_count, (unsigned)((nwB + 255) / 256), 256, 0, s, (const u32 *)(st ? B.rc.p : B.fwd.p), mb,
-                      (const int64_t *)B.off.p, (const int32_t *)B.len.p, (const int32_t *)B.chunk2read.p, nwB, k,
-                      (const u64 *)sa, (const u32 *)tbl.p, sh, P.t, (const u32 *)kbits.p, JG, wcnt.p + st * nwB);
-        }
-        exclusive_scan_u32_to_i64(wcnt.p, woff.p, 2 * nwB, dtotal.p, s);
-        H = d2h_scalar(dtotal.p, s);
-        if (H >= (1ll << 31) - 4096) throw Error("too many seed hits for one block pair (>= 2^31); use smaller blocks or lower -t");
-        hits.alloc((size_t)H + 1); hits2.alloc((size_t)H + 1);
-        if (H > 0)
+        DBuf<int64_t> seg_beg((size_t)nseg + 1); DBuf<int32_t> seg_len((size_t)nseg + 1);
+        // (a fused one-CTA-per-read count+reserve+emit kernel was measured at 2x the time of these two passes:
+        //  the lookups are latency-bound and want full occupancy, which the per-read shared-memory state prevents)
+        {
+            DBuf<u32> wcnt(2 * nwB); DBuf<int64_t> woff(2 * nwB);
             for (int st = 0; st < 2; st++) {
                 const u32 *mb = B.has_mask ? (st ? B.mask_rc.p : B.mask.p) : nullptr;
-                DN_LAUNCH(k_lookup_emit, (unsigned)((nwB + 255) / 256), 256, 0, s, (const u32 *)(st ? B.rc.p : B.fwd.p), mb,
+                DN_LAUNCH(k_lookup_count, (unsigned)((nwB + 255) / 256), 256, 0, s, (const u32 *)(st ? B.rc.p : B.fwd.p), mb,
                           (const int64_t *)B.off.p, (const int32_t *)B.len.p, (const int32_t *)B.chunk2read.p, nwB, k,
-                          (const u64 *)sa, (const u32 *)tbl.p, sh, P.t, (const u32 *)kbits.p, (const u32 *)(wcnt.p + st * nwB),
-                          (const int64_t *)(woff.p + st * nwB), st, JG, hits.p);
+                          (const u64 *)sa, (const u32 *)tbl.p, sh, P.t, (const u32 *)kbits.p, JG, wcnt.p + st * nwB);
             }
-        abytes += 2 * (nB / 4) * 2 + 2 * nwB * (4 + 4 + 8 + 8 + 4) + 16 * H;   // packed B read twice per strand, word counts/offsets, hits
+            exclusive_scan_u32_to_i64(wcnt.p, woff.p, 2 * nwB, dtotal.p, s);
+            H = d2h_scalar(dtotal.p, s);
+            if (H >= (1ll << 31) - 4096) throw Error("too many seed hits for one block pair (>= 2^31); use smaller blocks or lower -t");
+            hits.alloc((size_t)H + 1); hits2.alloc((size_t)H + 1);
+            if (H > 0)
+                for (int st = 0; st < 2; st++) {
+                    const u32 *mb = B.has_mask ? (st ? B.mask_rc.p : B.mask.p) : nullptr;
+                    DN_LAUNCH(k_lookup_emit, (unsigned)((nwB + 255) / 256), 256, 0, s, (const u32 *)(st ? B.rc.p : B.fwd.p), mb,
+                              (const int64_t *)B.off.p, (const int32_t *)B.len.p, (const int32_t *)B.chunk2read.p, nwB, k,
+                              (const u64 *)sa, (const u32 *)tbl.p, sh, P.t, (const u32 *)kbits.p, (const u32 *)(wcnt.p + st * nwB),
+                              (const int64_t *)(woff.p + st * nwB), st, JG, hits.p);
+                }
+            launch_seg_offsets(woff.p, B.off.p, B.nreads, nwB, H, seg_beg.p, seg_len.p, s);
+            abytes += 2 * (nB / 4) * 2 + 2 * nwB * (4 + 4 + 8 + 8 + 4) + 16 * H;   // packed B read twice per strand, word counts/offsets, hits
+        }
+        if (H >= (1ll << 31) - 4096) throw Error("too many seed hits for one block pair (>= 2^31); use smaller blocks or lower -t");
         {
             cudaStreamAttrValue av; memset(&av, 0, sizeof av);            // release the L2 set-aside
             cudaStreamSetAttribute(s, cudaStreamAttributeAccessPolicyWindow, &av); cudaGetLastError();
             cudaCtxResetPersistingL2Cache(); cudaGetLastError();
         }
-        // hits were emitted grouped by (strand, read) in ascending order: sort inside the segments only
+        // every (strand, read) segment is contiguous and, per diagonal, already in apos order: sort inside the segments only
         if (H > 0 && gdbits + aposbits <= 63 && !getenv("DN_NO_SEGSORT")) {
-            const int nseg = 2 * B.nreads;
-            DBuf<int64_t> seg_off((size_t)nseg + 1);
-            launch_seg_offsets(woff.p, B.off.p, B.nreads, nwB, H, seg_off.p, s);
-            std::vector<int64_t> hso((size_t)nseg + 1);
-            DN_CUDA(cudaMemcpyAsync(hso.data(), seg_off.p, sizeof(int64_t) * (nseg + 1), cudaMemcpyDeviceToHost, s));
+            std::vector<int64_t> hbeg(nseg); std::vector<int32_t> hlen(nseg);
+            DN_CUDA(cudaMemcpyAsync(hbeg.data(), seg_beg.p, sizeof(int64_t) * nseg, cudaMemcpyDeviceToHost, s));
+            DN_CUDA(cudaMemcpyAsync(hlen.data(), seg_len.p, sizeof(int32_t) * nseg, cudaMemcpyDeviceToHost, s));
             DN_CUDA(cudaStreamSynchronize(s));
             std::vector<int32_t> cls[3]; const int caps[3] = {2048, 8192, 16384};
             const bool radix = gdbits <= 32 && !getenv("DN_BITONIC");     // stable radix by gd: hits -> hits2
             std::vector<int> big;                       // segments too large for shared memory
             int64_t nbig = 0;
             for (int i = 0; i < nseg; i++) {
-                const int64_t len = hso[i + 1] - hso[i];
+                const int64_t len = hlen[i];
                 if (len < (radix ? 1 : 2)) continue;              // the radix variant writes to the other buffer: copy singletons too
                 int c = 0; while (c < 3 && len > caps[c]) c++;
                 if (c == 3) { big.push_back(i); nbig += len; } else cls[c].push_back(i);
             }
             const bool fits = big.size() <= 256;
             if (getenv("DN_TRACE")) {
-                int64_t mx = 0; for (int i = 0; i < nseg; i++) mx = std::max(mx, hso[i + 1] - hso[i]);
-                fprintf(stderr, "[dn trace] segments %d, largest %lld hits, classes %zu/%zu/%zu, fits %d\n", nseg, (long long)mx,
-                        cls[0].size(), cls[1].size(), cls[2].size(), (int)fits);
-                fprintf(stderr, "[dn trace] oversized segments %zu (%lld hits)\n", big.size(), (long long)nbig);
+                int64_t mx = 0; for (int i = 0; i < nseg; i++) mx = std::max<int64_t>(mx, hlen[i]);
+                fprintf(stderr, "[dn trace] %s join, segments %d, largest %lld hits, classes %zu/%zu/%zu, oversized %zu (%lld hits), fits %d\n",
+                        "two-pass", nseg, (long long)mx, cls[0].size(), cls[1].size(), cls[2].size(), big.size(), (long long)nbig, (int)fits);
             }
             if (fits) {
                 for (int c = 0; c < 3; c++) {
                     if (cls[c].empty()) continue;
                     DBuf<int32_t> lst(cls[c].size());
                     DN_CUDA(cudaMemcpyAsync(lst.p, cls[c].data(), sizeof(int32_t) * cls[c].size(), cudaMemcpyHostToDevice, s));
-                    if (radix) launch_segsort_radix(hits.p, hits2.p, seg_off.p, lst.p, (int)cls[c].size(), caps[c], gdbits, s);
-                    else launch_segsort(hits.p, seg_off.p, lst.p, (int)cls[c].size(), caps[c], gdbits, aposbits, s);
+                    if (radix) launch_segsort_radix(hits.p, hits2.p, seg_beg.p, seg_len.p, lst.p, (int)cls[c].size(), caps[c], gdbits, s);
+                    else launch_segsort(hits.p, seg_beg.p, seg_len.p, lst.p, (int)cls[c].size(), caps[c], gdbits, aposbits, s);
                 }
                 ulonglong2 *sorted = radix ? hits2.p : hits.p;
-
                 if (!big.empty()) {
-                    // the few oversized segments: gather, radix sort by (bs, gd, apos), copy back range by range
+                    // the few oversized segments: gather, radix sort by (bs, gd, apos), copy back segment by segment (ascending bs)
                     DBuf<ulonglong2> t1(nbig), t2(nbig);
                     int64_t o = 0;
-                    for (int i : big) {
-                        const int64_t len = hso[i + 1] - hso[i];
-                        DN_CUDA(cudaMemcpyAsync(t1.p + o, hits.p + hso[i], 16 * len, cudaMemcpyDeviceToDevice, s)); o += len;
-                    }
+                    for (int i : big) { DN_CUDA(cudaMemcpyAsync(t1.p + o, hits.p + hbeg[i], 16 * (int64_t)hlen[i], cudaMemcpyDeviceToDevice, s)); o += hlen[i]; }
                     ulonglong2 *r = radix_sort_rec16(t1.p, t2.p, nbig, 1, 0, aposbits, s);
                     r = radix_sort_rec16(r, r == t1.p ? t2.p : t1.p, nbig, 0, 0, keybits, s);
                     o = 0;
-                    for (int i : big) {
-                        const int64_t len = hso[i + 1] - hso[i];
-                        DN_CUDA(cudaMemcpyAsync(sorted + hso[i], r + o, 16 * len, cudaMemcpyDeviceToDevice, s)); o += len;
-                    }
+                    for (int i : big) { DN_CUDA(cudaMemcpyAsync(sorted + hbeg[i], r + o, 16 * (int64_t)hlen[i], cudaMemcpyDeviceToDevice, s)); o += hlen[i]; }
                 }
                 DN_CUDA(cudaStreamSynchronize(s));      // cls[] vectors are read by the async copies above
                 segsorted = true; seg_in_hits2 = radix;
-                abytes += 32 * H + 8ll * nseg;
+                abytes += 32 * H + 12ll * nseg;
             }
         }
     } else {

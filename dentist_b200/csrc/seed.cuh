@@ -52,12 +52,13 @@ __global__ void k_seeds(const ulonglong2 *hits, const int32_t *bfirst, const u64
                         const int32_t *cstart, const int32_t *cidx, int32_t nbands, SeedGeom G, Seed *seeds, uint8_t *consumed);
 
 // segmented hit sort (segsort.cu)
-void launch_seg_offsets(const int64_t *woff, const int64_t *b_off, int nr, int64_t nwB, int64_t H, int64_t *seg_off, cudaStream_t s);
-void launch_segsort(ulonglong2 *hits, const int64_t *seg_off, const int32_t *seglist, int nseg, int cap, int gdbits, int aposbits,
-                    cudaStream_t s);
+void launch_seg_offsets(const int64_t *woff, const int64_t *b_off, int nr, int64_t nwB, int64_t H, int64_t *seg_beg, int32_t *seg_len,
+                        cudaStream_t s);
+void launch_segsort(ulonglong2 *hits, const int64_t *seg_beg, const int32_t *seg_len, const int32_t *seglist, int nseg, int cap, int gdbits,
+                    int aposbits, cudaStream_t s);
 
-void launch_segsort_radix(const ulonglong2 *in, ulonglong2 *out, const int64_t *seg_off, const int32_t *seglist, int nseg, int cap,
-                          int gdbits, cudaStream_t s);
+void launch_segsort_radix(const ulonglong2 *in, ulonglong2 *out, const int64_t *seg_beg, const int32_t *seg_len, const int32_t *seglist,
+                          int nseg, int cap, int gdbits, cudaStream_t s);
 
 // extension stage (extend.cu)
 struct ExtGeom {

@@ -9,20 +9,21 @@ namespace dn {
 namespace {
 
 __global__ void __launch_bounds__(256) k_seg_offsets(const int64_t *__restrict__ woff, const int64_t *__restrict__ b_off, int nr,
-                                                     int64_t nwB, int64_t H, int64_t *__restrict__ seg_off) {
+                                                     int64_t nwB, int64_t H, int64_t *__restrict__ seg_beg, int32_t *__restrict__ seg_len) {
     int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i > 2 * nr) return;
-    if (i == 2 * nr) { seg_off[i] = H; return; }
-    const int st = i >= nr, r = i - st * nr;
-    seg_off[i] = woff[st * nwB + (b_off[r] >> 4)];
+    if (i >= 2 * nr) return;
+    auto at = [&](int q) -> int64_t { if (q == 2 * nr) return H; const int st = q >= nr, r = q - st * nr; return woff[st * nwB + (b_off[r] >> 4)]; };
+    const int64_t b = at(i);
+    seg_beg[i] = b; seg_len[i] = (int32_t)(at(i + 1) - b);
 }
 
-__global__ void __launch_bounds__(1024) k_segsort(ulonglong2 *__restrict__ hits, const int64_t *__restrict__ seg_off,
+__global__ void __launch_bounds__(1024) k_segsort(ulonglong2 *__restrict__ hits, const int64_t *__restrict__ seg_beg,
+                                                 const int32_t *__restrict__ seg_len,
                                                  const int32_t *__restrict__ seglist, int gdbits, int aposbits) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int seg = seglist[blockIdx.x];
-    const int64_t beg = seg_off[seg];
-    const int n = (int)(seg_off[seg + 1] - beg);
+    const int64_t beg = seg_beg[seg];
+    const int n = seg_len[seg];
     int Np = 2; while (Np < n) Np <<= 1;
     u64 *key = reinterpret_cast<u64 *>(smem_raw);
     u32 *val = reinterpret_cast<u32 *>(key + Np);
@@ -69,8 +70,8 @@ __global__ void __launch_bounds__(1024) k_segsort(ulonglong2 *__restrict__ hits,
 // shared memory; the 16-byte records are gathered once at the end into the output buffer.
 template <int WARPS>
 __global__ void __launch_bounds__(WARPS * 32) k_segsort_radix(const ulonglong2 *__restrict__ in, ulonglong2 *__restrict__ out,
-                                                              const int64_t *__restrict__ seg_off, const int32_t *__restrict__ seglist,
-                                                              int cap, int gdbits) {
+                                                              const int64_t *__restrict__ seg_beg, const int32_t *__restrict__ seg_len,
+                                                              const int32_t *__restrict__ seglist, int cap, int gdbits) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     u32 *key0 = reinterpret_cast<u32 *>(smem_raw), *key1 = key0 + cap;
     unsigned short *idx0 = reinterpret_cast<unsigned short *>(key1 + cap), *idx1 = idx0 + cap;
@@ -78,8 +79,8 @@ __global__ void __launch_bounds__(WARPS * 32) k_segsort_radix(const ulonglong2 *
     u32 *dtot = whist + WARPS * 256;                            // [256] digit totals / bases
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int seg = seglist[blockIdx.x];
-    const int64_t beg = seg_off[seg];
-    const int n = (int)(seg_off[seg + 1] - beg);
+    const int64_t beg = seg_beg[seg];
+    const int n = seg_len[seg];
     const u64 gdmask = (1ull << gdbits) - 1ull;
     for (int i = threadIdx.x; i < n; i += WARPS * 32) { key0[i] = (u32)(in[beg + i].x & gdmask); idx0[i] = (unsigned short)i; }
     const int per = ((n + WARPS - 1) / WARPS + 31) & ~31;       // contiguous, 32-aligned sub-range per warp
@@ -145,12 +146,13 @@ __global__ void __launch_bounds__(WARPS * 32) k_segsort_radix(const ulonglong2 *
 
 }  // namespace
 
-void launch_seg_offsets(const int64_t *woff, const int64_t *b_off, int nr, int64_t nwB, int64_t H, int64_t *seg_off, cudaStream_t s) {
-    DN_LAUNCH(k_seg_offsets, (2 * nr + 1 + 255) / 256, 256, 0, s, woff, b_off, nr, nwB, H, seg_off);
+void launch_seg_offsets(const int64_t *woff, const int64_t *b_off, int nr, int64_t nwB, int64_t H, int64_t *seg_beg, int32_t *seg_len,
+                        cudaStream_t s) {
+    DN_LAUNCH(k_seg_offsets, (2 * nr + 255) / 256, 256, 0, s, woff, b_off, nr, nwB, H, seg_beg, seg_len);
 }
 
 // cap = per-segment capacity class (power of two); segments in `seglist` have at most cap hits
-void launch_segsort(ulonglong2 *hits, const int64_t *seg_off, const int32_t *seglist, int nseg, int cap, int gdbits, int aposbits,
+void launch_segsort(ulonglong2 *hits, const int64_t *seg_beg, const int32_t *seg_len, const int32_t *seglist, int nseg, int cap, int gdbits, int aposbits,
                     cudaStream_t s) {
     if (nseg == 0) return;
     const size_t smem = (size_t)cap * 12;
@@ -160,16 +162,16 @@ void launch_segsort(ulonglong2 *hits, const int64_t *seg_off, const int32_t *seg
         attr_set = smem;
     }
     // big segments need many warps to hide shared-memory latency: 1024 threads for the 8k/16k classes
-    DN_LAUNCH(k_segsort, nseg, cap > 2048 ? 1024 : 256, smem, s, hits, seg_off, seglist, gdbits, aposbits);
+    DN_LAUNCH(k_segsort, nseg, cap > 2048 ? 1024 : 256, smem, s, hits, seg_beg, seg_len, seglist, gdbits, aposbits);
 }
 
 // radix variant (gdbits <= 32): reads `in`, writes `out`; segments not listed must be copied by the caller
-void launch_segsort_radix(const ulonglong2 *in, ulonglong2 *out, const int64_t *seg_off, const int32_t *seglist, int nseg, int cap,
+void launch_segsort_radix(const ulonglong2 *in, ulonglong2 *out, const int64_t *seg_beg, const int32_t *seg_len, const int32_t *seglist, int nseg, int cap,
                           int gdbits, cudaStream_t s) {
     if (nseg == 0) return;
     if (cap <= 2048) {
         const size_t smem = (size_t)cap * 12 + 8 * 256 * 4 + 1024;
-        DN_LAUNCH((k_segsort_radix<8>), nseg, 256, smem, s, in, out, seg_off, seglist, cap, gdbits);
+        DN_LAUNCH((k_segsort_radix<8>), nseg, 256, smem, s, in, out, seg_beg, seg_len, seglist, cap, gdbits);
     } else {
         const size_t smem = (size_t)cap * 12 + 16 * 256 * 4 + 1024;
         static size_t attr_set = 0;
@@ -177,7 +179,7 @@ void launch_segsort_radix(const ulonglong2 *in, ulonglong2 *out, const int64_t *
             DN_CUDA(cudaFuncSetAttribute(k_segsort_radix<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
             attr_set = smem;
         }
-        DN_LAUNCH((k_segsort_radix<16>), nseg, 512, smem, s, in, out, seg_off, seglist, cap, gdbits);
+        DN_LAUNCH((k_segsort_radix<16>), nseg, 512, smem, s, in, out, seg_beg, seg_len, seglist, cap, gdbits);
     }
 }
 
