@@ -361,7 +361,8 @@ __global__ void __launch_bounds__(256) k_lookup_count(const u32 *__restrict__ se
                                                       const int64_t *__restrict__ off, const int32_t *__restrict__ len,
                                                       const int32_t *__restrict__ c2r, int64_t nwords, int k,
                                                       const u64 *__restrict__ ta, const u32 *__restrict__ tbl, int sh, int tcap,
-                                                      const u32 *__restrict__ kbits, JoinGeom G, u32 *__restrict__ wcnt) {
+                                                      const u32 *__restrict__ kbits, JoinGeom G, u32 *__restrict__ wcnt,
+                                                      unsigned short *__restrict__ hitmask) {
     int64_t wi = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (wi >= nwords) return;
     const WordKmers w = load_word(seq, maskbits, off, len, c2r, wi);
@@ -373,27 +374,33 @@ __global__ void __launch_bounds__(256) k_lookup_count(const u32 *__restrict__ se
     for (int jj = 0; jj < 16; jj++)
         if ((w.p0 + jj + k <= w.L) && (((w.mwin >> jj) & mk) == 0) && kmer_present(kbits, (u32)((w.v >> (2 * jj)) & kmask)))
             present |= 1u << jj;
+    u32 hm = 0;                                       // positions that really produce hits: the emit pass skips the filter
     while (present) {
         const int jj = __ffs(present) - 1; present &= present - 1;
         {
             const u32 km = (u32)((w.v >> (2 * jj)) & kmask);
             u32 s, c; a_range_fwd(ta, tbl, sh, km, tcap, s, c);
+            u32 add = c;
             if (restricted) {                     // self pairs / pairs across pile-ups are never emitted
+                add = 0;
                 for (u32 x = 0; x < c; x++) {
                     const int ar = read_of(G.a_c2r, G.a_off, (int64_t)(u32)ta[s + x]);
-                    total += pair_ok(G, ar, w.r) ? 1u : 0u;
+                    add += pair_ok(G, ar, w.r) ? 1u : 0u;
                 }
-            } else total += c;
+            }
+            total += add;
+            if (add) hm |= 1u << jj;
         }
     }
     __stcs(wcnt + wi, total);
+    hitmask[wi] = (unsigned short)hm;
 }
 
 __global__ void __launch_bounds__(256) k_lookup_emit(const u32 *__restrict__ seq, const u32 *__restrict__ maskbits,
                                                      const int64_t *__restrict__ off, const int32_t *__restrict__ len,
                                                      const int32_t *__restrict__ c2r, int64_t nwords, int k,
                                                      const u64 *__restrict__ ta, const u32 *__restrict__ tbl, int sh, int tcap,
-                                                     const u32 *__restrict__ kbits, const u32 *__restrict__ wcnt,
+                                                     const unsigned short *__restrict__ hitmask, const u32 *__restrict__ wcnt,
                                                      const int64_t *__restrict__ woff, int strand,
                                                      JoinGeom G, ulonglong2 *__restrict__ hits) {
     int64_t wi = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -403,11 +410,8 @@ __global__ void __launch_bounds__(256) k_lookup_emit(const u32 *__restrict__ seq
     const u64 kmask = (1ull << (2 * k)) - 1ull, mk = (1ull << k) - 1ull;
     const u64 bs = (u64)strand * G.nb_reads + w.r;
     int64_t o = __ldcs((const long long *)woff + wi);
-    u32 present = 0;
-#pragma unroll
-    for (int jj = 0; jj < 16; jj++)
-        if ((w.p0 + jj + k <= w.L) && (((w.mwin >> jj) & mk) == 0) && kmer_present(kbits, (u32)((w.v >> (2 * jj)) & kmask)))
-            present |= 1u << jj;
+    u32 present = hitmask[wi];                        // from the count pass: no filter probes, no fruitless lookups
+    (void)mk;
     while (present) {                                 // ascending jj: hits of a word stay ordered by bpos
         const int jj = __ffs(present) - 1; present &= present - 1;
         const u32 km = (u32)((w.v >> (2 * jj)) & kmask);
