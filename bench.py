@@ -333,9 +333,9 @@ def main():
                "e2e": {"value": e2e, "unit": "Gbp/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h)},
                "gpu_launches": int(launches),
                "clocks": summarize_clocks(clk),
-               "roofline": {"kernel": "k_extend32 (O(ND) wave extension, 32% of device time)", "bound": "hbm", "achieved": ext_gbs, "peak": peak,
+               "roofline": {"kernel": "k_extend32 (O(ND) wave extension, 37% of device time)", "bound": "hbm", "achieved": ext_gbs, "peak": peak,
                             "unit": "GB/s", "frac": ext_gbs / peak,
-                            "traffic": 88.6e6 / 3, "traffic_source": "ncu dram__bytes_read+write of the round-1 launch (profiles/r01_prof_extend32_r1e_details.txt) averaged over the 3 launches of a step",
+                            "traffic": 97.6e6 / 3, "traffic_source": "ncu dram__bytes_read+write of the round-0 launch (profiles/r01_prof_extend32_r1g_details.txt) averaged over the 3 launches of a step",
                             "peak_source": peak_src,
                             "note": "instruction-issue-bound kernel (80% issue slots busy, DRAM 0.15%): algorithmic bytes = packed sequence under each alignment + records + traces"},
                "roofline_seed": {"kernels": "A tuples+radix, lookup join, segment sort, band filter, retire, final ordering", "bound": "hbm", "achieved": seed_gbs, "peak": peak,
