@@ -122,6 +122,47 @@ int dn_las_chain_mapper(dn_las_buf *las, int32_t nb_reads, int32_t max_indel, in
     });
 }
 
+int dn_las_force_flat(dn_las_buf *las) {
+    if (!las) return fail(DN_ERR_INVALID, "null argument");
+    std::lock_guard<std::mutex> lk(g_mu);
+    if (int rc = ensure_device()) return rc;
+    return guarded([&] { cudaSetDevice(g_device); force_flat_device(las->rec, las->toff, las->nrec, g_stream); return DN_OK; });
+}
+
+// findReferenceReadCandidates (processPileUps/package.d:518-568) for a batch of pile-ups: host logic on the
+// QV bytes (stays on the host in DENTIST too).  rank[pile_off[p] .. pile_off[p+1]) = reads of pile p ordered by
+// (numBadQVs, meanQV, readId).
+int dn_reference_read_candidates(const uint8_t *qv, const int64_t *qoff, const int32_t *group, int32_t nreads, int32_t npiles,
+                                 double bad_fraction, int32_t *rank, int64_t *pile_off) {
+    if (!qv || !qoff || !group || !rank || !pile_off || nreads < 0 || npiles < 0) return fail(DN_ERR_INVALID, "null argument");
+    return guarded([&]() -> int {
+        const int MAXQV = 50;                                         // DbRecord.maxQV, dazzler.d:2873
+        std::vector<std::vector<int32_t>> members(npiles);
+        for (int r = 0; r < nreads; r++) { if (group[r] < 0 || group[r] >= npiles) return fail(DN_ERR_INVALID, "pile id out of bounds"); members[group[r]].push_back(r); }
+        int64_t o = 0;
+        for (int p = 0; p < npiles; p++) {
+            pile_off[p] = o;
+            long long hist[50] = {0}, total = 0;
+            for (int r : members[p]) for (int64_t q = qoff[r]; q < qoff[r + 1]; q++) if (qv[q] < MAXQV) { hist[qv[q]]++; total++; }
+            const size_t bad_thres = (size_t)(bad_fraction * (double)total);
+            long long cum = 0; int idx = -1;
+            for (int v = MAXQV - 1; v >= 0; v--) { cum += hist[v]; if ((size_t)cum >= bad_thres) { idx = MAXQV - 1 - v; break; } }
+            const int bad_qv = MAXQV - 1 - idx;                       // package.d:536-540
+            struct S { long long nbad; double mean; int32_t id; };
+            std::vector<S> sc;
+            for (int r : members[p]) {
+                long long nb = 0, sum = 0; const int64_t n = qoff[r + 1] - qoff[r];
+                for (int64_t q = qoff[r]; q < qoff[r + 1]; q++) { nb += qv[q] >= bad_qv; sum += qv[q]; }
+                sc.push_back(S{nb, n ? (double)sum / (double)n : 0.0, r});
+            }
+            std::sort(sc.begin(), sc.end(), [](const S &a, const S &b) { if (a.nbad != b.nbad) return a.nbad < b.nbad; if (a.mean != b.mean) return a.mean < b.mean; return a.id < b.id; });
+            for (const S &x : sc) rank[o++] = x.id;
+        }
+        pile_off[npiles] = o;
+        return DN_OK;
+    });
+}
+
 void dn_seq_free(dn_seq_buf *b) { if (!b) return; hcache_free(b->off); hcache_free(b->bases); memset(b, 0, sizeof *b); }
 
 int dn_consensus(const dn_block *db, const dn_las_buf *las, const int32_t *reads, int32_t nreads, dn_seq_buf *out) {

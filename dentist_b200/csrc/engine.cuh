@@ -52,6 +52,7 @@ void hcache_free(void *p);
 void block_upload(const dn_block_desc &d, DevBlock &out, cudaStream_t s);
 void block_crop(const DevBlock &src, int n, const int32_t *read, const int32_t *begin, const int32_t *end, const int32_t *group,
                 DevBlock &out, cudaStream_t s);
+void force_flat_device(dn_las_record *h_rec, int64_t *h_toff, int64_t n, cudaStream_t s);
 void merge_las_device(const dn_las_record *d_rec, int64_t n, const uint16_t *d_trace, int64_t ntrace, int64_t max_alen, int64_t max_blen,
                       int64_t na_reads, int64_t nb_reads, HostLas &out, cudaStream_t s);
 void align_blocks(const DevBlock &A, const DevBlock &B, const AlignParams &P, HostLas &out, cudaStream_t s);

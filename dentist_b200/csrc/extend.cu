@@ -619,6 +619,46 @@ int bits_of(uint64_t v) { int b = 0; while (v) { b++; v >>= 1; } return b; }
 
 }  // namespace
 
+
+// forceFlat (dazzler.d:4084-4093): clear the chain flags and put the records into FlatLocalAlignment order;
+// the traces stay where they are (toff is permuted with the records).
+namespace { __global__ void __launch_bounds__(256) k_flat_gather(const dn_las_record *__restrict__ rec, const int64_t *__restrict__ toff,
+                                                                  const ulonglong2 *__restrict__ items, int64_t n,
+                                                                  dn_las_record *__restrict__ orec, int64_t *__restrict__ otoff) {
+    int64_t o = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (o >= n) return;
+    const u64 i = items[o].y;
+    dn_las_record x = rec[i];
+    x.flags &= (DN_LAS_COMP | DN_LAS_ELIM);
+    orec[o] = x; otoff[o] = toff[i];
+} }
+
+void force_flat_device(dn_las_record *h_rec, int64_t *h_toff, int64_t n, cudaStream_t s) {
+    arena().reset();
+    if (n == 0) return;
+    int64_t mxa = 1, mxb = 1, na = 1, nb = 1;
+    for (int64_t i = 0; i < n; i++) {
+        mxa = std::max<int64_t>(mxa, h_rec[i].aepos); mxb = std::max<int64_t>(mxb, h_rec[i].bepos);
+        na = std::max<int64_t>(na, (int64_t)h_rec[i].aread + 1); nb = std::max<int64_t>(nb, (int64_t)h_rec[i].bread + 1);
+    }
+    DBuf<dn_las_record> drec(n), orec(n); DBuf<int64_t> dtoff(n), otoff(n); DBuf<ulonglong2> it1(n), it2(n);
+    DN_CUDA(cudaMemcpyAsync(drec.p, h_rec, sizeof(dn_las_record) * n, cudaMemcpyHostToDevice, s));
+    DN_CUDA(cudaMemcpyAsync(dtoff.p, h_toff, sizeof(int64_t) * n, cudaMemcpyHostToDevice, s));
+    FinalBits fb{bits_of((uint64_t)mxa), bits_of((uint64_t)mxb), bits_of((uint64_t)na), bits_of((uint64_t)nb), 0};
+    const int fbits[4] = {bits_of((uint64_t)mxa + mxb), 2 * fb.nb, 2 * fb.na + 1, fb.nra + fb.nrb};
+    ulonglong2 *cur = it1.p, *oth = it2.p;
+    for (int f = 0; f < 4; f++) {
+        DN_LAUNCH(k_merge_setkey, (unsigned)((n + 255) / 256), 256, 0, s, (const dn_las_record *)drec.p, cur, n, f, fb);
+        ulonglong2 *res = radix_sort_rec16(cur, oth, n, 0, 0, fbits[f], s);
+        if (res != cur) { oth = cur; cur = res; }
+    }
+    DN_LAUNCH(k_flat_gather, (unsigned)((n + 255) / 256), 256, 0, s, (const dn_las_record *)drec.p, (const int64_t *)dtoff.p,
+              (const ulonglong2 *)cur, n, orec.p, otoff.p);
+    DN_CUDA(cudaMemcpyAsync(h_rec, orec.p, sizeof(dn_las_record) * n, cudaMemcpyDeviceToHost, s));
+    DN_CUDA(cudaMemcpyAsync(h_toff, otoff.p, sizeof(int64_t) * n, cudaMemcpyDeviceToHost, s));
+    DN_CUDA(cudaStreamSynchronize(s));
+}
+
 void merge_las_device(const dn_las_record *d_rec, int64_t n, const uint16_t *d_trace, int64_t ntrace, int64_t max_alen, int64_t max_blen,
                       int64_t na_reads, int64_t nb_reads, HostLas &out, cudaStream_t s) {
     out = HostLas();

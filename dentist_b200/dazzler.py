@@ -246,15 +246,9 @@ class Las:
 
     def forceFlat(self):
         """filterPileUpAlignments(..., Yes.forceFlat) (dazzler.d:4084-4093): drop the chain flags and sort the
-        records in FlatLocalAlignment order (base.d:1787-1809).  Host glue on the (few) records of a pile."""
-        n = len(self)
-        if n == 0:
-            return self
-        rec = self.rec
-        rec["flags"] &= np.uint32(0x1 | 0x20)
-        order = np.lexsort((rec["diffs"], rec["bepos"], rec["bbpos"], rec["aepos"], rec["abpos"], rec["flags"] & 1, rec["bread"], rec["aread"]))
-        r2 = rec[order].copy(); t2 = self.toff[order].copy()
-        rec[:] = r2; self.toff[:] = t2
+        records in FlatLocalAlignment order (base.d:1787-1809)."""
+        _lib.check(_lib.lib().dn_las_force_flat(C.byref(self._buf)))
+        self._refresh()
         return self
 
     def chainMapper(self, nb_reads, max_indel=1000, max_gap=10000):
@@ -362,3 +356,13 @@ def collectFilter(las, alen, blen, repeat_mask=None, max_alignment_error=0.3, pr
     u = np.ctypeslib.as_array(used, shape=(max(len(blen), 1),))[:len(blen)].copy()
     L.dn_free(first); L.dn_free(st); L.dn_free(used)
     return f, s_, np.flatnonzero(u).tolist()
+
+
+def findReferenceReadCandidates(qv, qoff, group, npiles, bad_fraction=0.08):
+    """processPileUps/package.d:518-568 for a batch: list (per pile) of read ids ranked by (numBadQVs, meanQV, readId)."""
+    qv = np.ascontiguousarray(qv, np.uint8); qoff = np.ascontiguousarray(qoff, np.int64); group = np.ascontiguousarray(group, np.int32)
+    rank = np.zeros(len(group), np.int32); poff = np.zeros(npiles + 1, np.int64)
+    _lib.check(_lib.lib().dn_reference_read_candidates(qv.ctypes.data_as(C.c_void_p), qoff.ctypes.data_as(C.c_void_p),
+                                                       group.ctypes.data_as(C.c_void_p), len(group), int(npiles), C.c_double(bad_fraction),
+                                                       rank.ctypes.data_as(C.c_void_p), poff.ctypes.data_as(C.c_void_p)))
+    return [rank[poff[p]:poff[p + 1]] for p in range(npiles)]

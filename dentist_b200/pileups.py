@@ -85,12 +85,7 @@ def process_pileups(reads, group, max_alignment_error=0.3, flanks=None):
     las.forceFlat()
     if len(las) == 0:
         raise dazzler.DnError("empty pileup alignment after filtering")
-    order = np.argsort(group, kind="stable")
-    bounds = np.searchsorted(group[order], np.arange(npiles + 1))
-    ref_reads = []
-    for p in range(npiles):
-        members = order[bounds[p]:bounds[p + 1]]
-        ref_reads.append(find_reference_read_candidates(qv, qoff, members)[0])
+    ref_reads = [int(c[0]) for c in dazzler.findReferenceReadCandidates(qv, qoff, group, npiles, BAD_FRACTION)]   # package.d:518-568
     cons = dazzler.getConsensus(g, las, ref_reads)                       # package.d:600-619
     out = dict(consensus=cons, reference_read=ref_reads, las=las, qv=qv, qoff=qoff, flank_las=None)
     if flanks is not None:

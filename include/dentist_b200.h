@@ -184,6 +184,14 @@ void dn_seq_free(dn_seq_buf *buf);
 int dn_las_chain(dn_las_buf *las, int32_t max_indel, int32_t max_chain_gap, double max_rel_overlap, double min_rel_score,
                  int32_t min_score);
 
+/* filterPileUpAlignments(..., Yes.forceFlat) tail (dazzler.d:4084-4093): clear the chain flags and sort the
+ * records in FlatLocalAlignment order (base.d:1787-1809). */
+int dn_las_force_flat(dn_las_buf *las);
+/* findReferenceReadCandidates (processPileUps/package.d:518-568) for a batch of pile-ups (host logic):
+ * rank[pile_off[p] .. pile_off[p+1]) = reads of pile p ordered by (numBadQVs, meanQV, readId). */
+int dn_reference_read_candidates(const uint8_t *qv, const int64_t *qoff, const int32_t *group, int32_t nreads, int32_t npiles,
+                                 double bad_fraction, int32_t *rank, int64_t *pile_off);
+
 /* damapper-style chain flags: START on the first record of a chain, NEXT on continuations, BEST on the
  * top-scoring chain of every B read -- the flags DENTIST decodes at dazzler.d:1738-1755 and packs into
  * AlignmentChains at :708-743.  `las` must be in LAsort order (as dn_align_blocks returns it). */

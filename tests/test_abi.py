@@ -79,3 +79,21 @@ def test_las_file_roundtrip_through_the_abi(tmp_path):
     with pytest.raises(dazzler.DnError):
         open(str(tmp_path / "bad.las"), "wb").write(open(p, "rb").read()[:-3])
         dazzler.read_las(str(tmp_path / "bad.las"))
+
+
+def test_reference_read_candidates_matches_python_mirror():
+    """dn_reference_read_candidates (host logic, processPileUps/package.d:518-568) == the numpy mirror in pileups.py."""
+    from dentist_b200 import dazzler, pileups
+    rng = np.random.default_rng(8)
+    nreads, npiles = 60, 7
+    group = np.sort(rng.integers(0, npiles, nreads)).astype(np.int32)
+    ntiles = rng.integers(5, 40, nreads)
+    qoff = np.zeros(nreads + 1, np.int64); qoff[1:] = np.cumsum(ntiles)
+    qv = rng.integers(0, 51, int(qoff[-1])).astype(np.uint8)
+    got = dazzler.findReferenceReadCandidates(qv, qoff, group, npiles)
+    for p in range(npiles):
+        members = np.flatnonzero(group == p)
+        if len(members) == 0:
+            assert len(got[p]) == 0
+            continue
+        assert got[p].tolist() == pileups.find_reference_read_candidates(qv, qoff, members)
