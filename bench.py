@@ -271,7 +271,9 @@ def main():
         b2 = dazzler.Block(reads.off, bps=reads_bps, boff=reads_boff)
         rec, toff, tr, st = dazzler.align_blocks(a2, b2, **PARAMS)
         if world > 1:
-            rec, toff, tr = sharding.gather_las(rec, tr, bread_offset, device=dev, tspace=PARAMS["tspace"], bounds=gather_bounds)
+            merged = sharding.gather_las(rec, tr, bread_offset, device=dev, tspace=PARAMS["tspace"], bounds=gather_bounds, root=0)
+            if merged is not None:
+                rec, toff, tr = merged
         barrier()
         dt = time.perf_counter() - t1
         a2.free(); b2.free()
@@ -307,7 +309,7 @@ def main():
             dist.all_reduce(t3, op=dist.ReduceOp.MAX); dist.all_reduce(u3, op=dist.ReduceOp.SUM)
         cons = {"value": float(u3[0]) / float(t3[0]), "unit": "consensus bases/s", "pile_ups_per_gpu": int(pgroup.max()) + 1,
                 "cropped_reads_per_gpu": int(preads.nreads), "cropped_bp_per_gpu": int(preads.total),
-                "stages": "pile alignment (daligner -s126 -l500) + error filter + QVs + pile filter + reference read + consensus + flank alignment"}
+                "stages": "pile alignment (daligner -s126 -l500) + error filter + chaining + QVs + pile filter + reference read + consensus + flank alignment"}
         if rank == 0:
             piles = list(range(min(int(pgroup.max()) + 1, 2 * cores)))
             nb, dt = oracle_piles_threads(preads, pgroup, piles, cores)

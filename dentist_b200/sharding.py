@@ -40,13 +40,14 @@ def _allgatherv_bytes(buf_u8, device, keep_on_device=False):
     return [o[:s].cpu().numpy() for o, s in zip(outs, sizes)], sizes
 
 
-def gather_las(rec, trace, bread_offset, device="cpu", tspace=100, bounds=None):
+def gather_las(rec, trace, bread_offset, device="cpu", tspace=100, bounds=None, root=None):
     """All ranks contribute their LAS segment (records with rank-local `bread`, traces in record order); every
     rank gets the merged LAS in LAsort order (aread, bread, comp, abpos, ...), with `bread` shifted to the global
     read numbering.  Returns (records, trace offsets, trace).
     On CUDA the gathered bytes never leave the device before they are merged (dn_las_merge_device);
     `bounds` = (max_alen, max_blen, na_reads, nb_reads_total) sizes the sort keys.  On CPU (gloo tests) the
-    merge is the numpy `merge_las`."""
+    merge is the numpy `merge_las`.  root=None: every rank merges (all ranks hold R.Q.las); root=r: all ranks take part
+    in the all-gatherv but only rank r merges and downloads (the others return None) -- one merged file, as LAmerge writes."""
     rec = rec.copy()
     rec["bread"] += bread_offset
     rb = torch.from_numpy(np.frombuffer(rec.tobytes(), dtype=np.uint8).copy())
@@ -54,6 +55,14 @@ def gather_las(rec, trace, bread_offset, device="cpu", tspace=100, bounds=None):
     is_cuda = torch.device(device).type == "cuda"
     recs, rsz = _allgatherv_bytes(rb, device, keep_on_device=is_cuda)
     trs, tsz = _allgatherv_bytes(tb, device, keep_on_device=is_cuda)
+    is_cuda_ = is_cuda
+    if bounds is None and is_cuda_:      # key widths from the data: max over ranks of the coordinates / ids present
+        loc = [int(rec[f].max()) + 1 if len(rec) else 1 for f in ("aepos", "bepos", "aread", "bread")]
+        mx = torch.tensor(loc, dtype=torch.int64, device=device)
+        dist.all_reduce(mx, op=dist.ReduceOp.MAX)
+        bounds = tuple(int(v) for v in mx.tolist())
+    if root is not None and dist.get_rank() != root:
+        return None
     if not is_cuda:
         return merge_las([r.view(REC_DTYPE) for r in recs], [t.view(np.uint16) for t in trs])
     import ctypes as C
@@ -61,11 +70,6 @@ def gather_las(rec, trace, bread_offset, device="cpu", tspace=100, bounds=None):
     drec = torch.cat(recs) if recs else torch.zeros(0, dtype=torch.uint8, device=device)
     dtr = torch.cat(trs) if trs else torch.zeros(0, dtype=torch.uint8, device=device)
     torch.cuda.synchronize()
-    if bounds is None:      # key widths from the data: max over ranks of the coordinates / ids present
-        loc = [int(rec[f].max()) + 1 if len(rec) else 1 for f in ("aepos", "bepos", "aread", "bread")]
-        mx = torch.tensor(loc, dtype=torch.int64, device=device)
-        dist.all_reduce(mx, op=dist.ReduceOp.MAX)
-        bounds = tuple(int(v) for v in mx.tolist())
     buf = _lib.LasBuf()
     _lib.check(_lib.lib().dn_las_merge_device(C.c_void_p(drec.data_ptr()), sum(rsz) // 40, C.c_void_p(dtr.data_ptr()), sum(tsz) // 2,
                                               int(tspace), int(bounds[0]), int(bounds[1]), int(bounds[2]), int(bounds[3]), C.byref(buf)))
