@@ -96,3 +96,36 @@ def process_pileups(reads, group, max_alignment_error=0.3, flanks=None):
         out["flank_las"] = dazzler.align(fb, cb, tspace=TSPACE, minlen=TSPACE, e=0.7)
     g.free()
     return out
+
+
+def _subtract(intervals, mask):
+    out = []
+    for b, e in intervals:
+        cur = b
+        for mb, me in mask:
+            if me <= cur or mb >= e:
+                continue
+            if mb > cur:
+                out.append((cur, mb))
+            cur = max(cur, me)
+        if cur < e:
+            out.append((cur, e))
+    return out
+
+
+def common_trace_point(intervals, seed, tspace, contig_len, repeat_mask=()):
+    """getCommonTracePoint (cropper.d:446-500): a trace point (multiple of `tspace`, or the contig end) that lies in
+    the A interval of every alignment and -- if possible -- outside `repeat_mask`; the last one for seed 'front',
+    the first one for seed 'back'; -1 if there is none.  intervals = [(abpos, aepos), ...] on one contig."""
+    b = max(i[0] for i in intervals); e = min(i[1] for i in intervals)
+    common = [(b, e)] if b < e else []
+    for region in (_subtract(common, sorted(repeat_mask)), common):
+        if not region:
+            continue
+        lo = -(-region[0][0] // tspace) * tspace
+        sup = -(-region[-1][1] // tspace) * tspace
+        cands = list(range(lo, sup, tspace)) + ([contig_len] if sup > contig_len else [])
+        ok = [c for c in cands if any(rb <= c < re_ for rb, re_ in region) or c == region[-1][1]]
+        if ok:
+            return ok[-1] if seed == "front" else ok[0]
+    return -1
