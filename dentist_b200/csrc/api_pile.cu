@@ -138,7 +138,11 @@ int dn_reference_read_candidates(const uint8_t *qv, const int64_t *qoff, const i
     return guarded([&]() -> int {
         const int MAXQV = 50;                                         // DbRecord.maxQV, dazzler.d:2873
         std::vector<std::vector<int32_t>> members(npiles);
-        for (int r = 0; r < nreads; r++) { if (group[r] < 0 || group[r] >= npiles) return fail(DN_ERR_INVALID, "pile id out of bounds"); members[group[r]].push_back(r); }
+        for (int r = 0; r < nreads; r++) {
+            if (group[r] < 0) continue;                               // not in allowedReferenceReadIds (package.d:456-468, 520-523)
+            if (group[r] >= npiles) return fail(DN_ERR_INVALID, "pile id out of bounds");
+            members[group[r]].push_back(r);
+        }
         int64_t o = 0;
         for (int p = 0; p < npiles; p++) {
             pile_off[p] = o;

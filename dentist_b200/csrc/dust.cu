@@ -43,49 +43,80 @@ __global__ void __launch_bounds__(256) k_dust_windows(const u32 *__restrict__ se
 using namespace dn;
 using namespace dnapi;
 
+// Device window flags -> merged (begin, end) intervals per read in the track layout of dazzler.d:4943-5052.
+// Caller holds g_mu and has reset the arena.
+static void dust_intervals(const DevBlock &B, int window, double threshold, int minlen, std::vector<int64_t> &anno, std::vector<int32_t> &iv) {
+    const int stride = window / 2, t10 = (int)(threshold * 10.0 + 0.5);
+    std::vector<int64_t> woff(B.nreads + 1, 0);
+    for (int r = 0; r < B.nreads; r++) woff[r + 1] = woff[r] + (B.h_len[r] > 0 ? (B.h_len[r] + stride - 1) / stride : 0);
+    const int64_t nw = woff[B.nreads];
+    std::vector<uint8_t> flags(nw + 1);
+    if (nw > 0) {
+        DBuf<int64_t> dw(B.nreads + 1); DBuf<uint8_t> df(nw);
+        DN_CUDA(cudaMemcpyAsync(dw.p, woff.data(), sizeof(int64_t) * (B.nreads + 1), cudaMemcpyHostToDevice, g_stream));
+        DN_LAUNCH(k_dust_windows, B.nreads, 256, 0, g_stream, (const u32 *)B.fwd.p, (const int64_t *)B.off.p, (const int32_t *)B.len.p,
+                  (const int64_t *)dw.p, B.nreads, window, t10, df.p);
+        DN_CUDA(cudaMemcpyAsync(flags.data(), df.p, nw, cudaMemcpyDeviceToHost, g_stream));
+        DN_CUDA(cudaStreamSynchronize(g_stream));
+    }
+    anno.assign(B.nreads + 1, 0); iv.clear();
+    for (int r = 0; r < B.nreads; r++) {
+        anno[r] = 4 * (int64_t)iv.size();
+        const int64_t n = woff[r + 1] - woff[r]; const int L = B.h_len[r];
+        int64_t q = 0;
+        while (q < n) {
+            if (!flags[woff[r] + q]) { q++; continue; }
+            int64_t e = q;
+            while (e + 1 < n && flags[woff[r] + e + 1]) e++;
+            int b0 = (int)(q * stride), e0 = (int)std::min<int64_t>(e * stride + window, L);
+            if (e0 - b0 >= minlen) { iv.push_back(b0); iv.push_back(e0); }
+            q = e + 1;
+        }
+    }
+    anno[B.nreads] = 4 * (int64_t)iv.size();
+}
+
+static int check_dust_args(int32_t window) {
+    if (window < 16 || window > 64 || (window & 1)) return fail(DN_ERR_INVALID, "DUST window must be even and in [16,64]");
+    return DN_OK;
+}
+
 extern "C" {
 
 int dn_dust_block(const dn_block *blk, int32_t window, double threshold, int32_t minlen, int64_t **anno, int32_t **data) {
     if (!blk || !anno || !data) return fail(DN_ERR_INVALID, "null argument");
-    if (window < 16 || window > 64 || (window & 1)) return fail(DN_ERR_INVALID, "DUST window must be even and in [16,64]");
+    if (int rc = check_dust_args(window)) return rc;
     std::lock_guard<std::mutex> lk(g_mu);
     if (int rc = ensure_device()) return rc;
     return guarded([&] {
         cudaSetDevice(g_device); arena().reset();
         const DevBlock &B = blk->b;
-        const int stride = window / 2, t10 = (int)(threshold * 10.0 + 0.5);
-        std::vector<int64_t> woff(B.nreads + 1, 0);
-        for (int r = 0; r < B.nreads; r++) woff[r + 1] = woff[r] + (B.h_len[r] > 0 ? (B.h_len[r] + stride - 1) / stride : 0);
-        const int64_t nw = woff[B.nreads];
-        std::vector<uint8_t> flags(nw + 1);
-        if (nw > 0) {
-            DBuf<int64_t> dw(B.nreads + 1); DBuf<uint8_t> df(nw);
-            DN_CUDA(cudaMemcpyAsync(dw.p, woff.data(), sizeof(int64_t) * (B.nreads + 1), cudaMemcpyHostToDevice, g_stream));
-            DN_LAUNCH(k_dust_windows, B.nreads, 256, 0, g_stream, (const u32 *)B.fwd.p, (const int64_t *)B.off.p, (const int32_t *)B.len.p,
-                      (const int64_t *)dw.p, B.nreads, window, t10, df.p);
-            DN_CUDA(cudaMemcpyAsync(flags.data(), df.p, nw, cudaMemcpyDeviceToHost, g_stream));
-            DN_CUDA(cudaStreamSynchronize(g_stream));
-        }
-        // host glue: runs of flagged windows -> (begin, end) pairs in the track layout of dazzler.d:4943-5052
-        std::vector<int32_t> iv;
+        std::vector<int64_t> a; std::vector<int32_t> iv;
+        dust_intervals(B, window, threshold, minlen, a, iv);
         int64_t *ha = (int64_t *)hcache_alloc(sizeof(int64_t) * (B.nreads + 1));
-        for (int r = 0; r < B.nreads; r++) {
-            ha[r] = 4 * (int64_t)iv.size();
-            const int64_t n = woff[r + 1] - woff[r]; const int L = B.h_len[r];
-            int64_t q = 0;
-            while (q < n) {
-                if (!flags[woff[r] + q]) { q++; continue; }
-                int64_t e = q;
-                while (e + 1 < n && flags[woff[r] + e + 1]) e++;
-                int b0 = (int)(q * stride), e0 = (int)std::min<int64_t>(e * stride + window, L);
-                if (e0 - b0 >= minlen) { iv.push_back(b0); iv.push_back(e0); }
-                q = e + 1;
-            }
-        }
-        ha[B.nreads] = 4 * (int64_t)iv.size();
+        memcpy(ha, a.data(), sizeof(int64_t) * (B.nreads + 1));
         int32_t *hd = (int32_t *)hcache_alloc(sizeof(int32_t) * (iv.size() + 2));
         if (!iv.empty()) memcpy(hd, iv.data(), sizeof(int32_t) * iv.size());
         *anno = ha; *data = hd;
+        return DN_OK;
+    });
+}
+
+int dn_block_mask_dust(dn_block *blk, int32_t window, double threshold, int32_t minlen, int64_t *masked_bases) {
+    if (!blk) return fail(DN_ERR_INVALID, "null argument");
+    if (int rc = check_dust_args(window)) return rc;
+    std::lock_guard<std::mutex> lk(g_mu);
+    if (int rc = ensure_device()) return rc;
+    return guarded([&] {
+        cudaSetDevice(g_device); arena().reset();
+        DevBlock &B = blk->b;
+        std::vector<int64_t> a; std::vector<int32_t> iv;
+        dust_intervals(B, window, threshold, minlen, a, iv);
+        int64_t m = 0;
+        for (size_t i = 0; i + 1 < iv.size(); i += 2) m += iv[i + 1] - iv[i];
+        if (masked_bases) *masked_bases = m;
+        iv.push_back(0); iv.push_back(0);                                   // keeps data() valid for an empty track
+        block_add_mask(B, a.data(), iv.data(), g_stream);
         return DN_OK;
     });
 }

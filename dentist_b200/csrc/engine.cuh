@@ -50,6 +50,7 @@ void *hcache_alloc(size_t bytes);
 void hcache_free(void *p);
 
 void block_upload(const dn_block_desc &d, DevBlock &out, cudaStream_t s);
+void block_add_mask(DevBlock &B, const int64_t *anno_h, const int32_t *data_h, cudaStream_t s);
 void block_crop(const DevBlock &src, int n, const int32_t *read, const int32_t *begin, const int32_t *end, const int32_t *group,
                 DevBlock &out, cudaStream_t s);
 void force_flat_device(dn_las_record *h_rec, int64_t *h_toff, int64_t n, cudaStream_t s);

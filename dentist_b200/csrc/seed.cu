@@ -63,6 +63,24 @@ __global__ void k_mask_bits(const int64_t *__restrict__ anno, const int32_t *__r
     }
 }
 
+// ORs the intervals of a mask track (anno = byte offsets into int32 (begin, end) pairs, dazzler.d:4943-5052) into the
+// block's seed-exclusion bits; several tracks (-mdust -mrep) accumulate.
+void block_add_mask(DevBlock &B, const int64_t *anno_h, const int32_t *data_h, cudaStream_t s) {
+    const int64_t nbytes = anno_h[B.nreads];
+    if (nbytes <= 0) return;
+    if (!B.has_mask) {
+        const size_t mw = (size_t)(B.total >> 5) + 4;
+        B.mask.persistent(mw); B.mask_rc.persistent(mw); B.mask.zero(s); B.mask_rc.zero(s);
+        B.has_mask = true;
+    }
+    DBuf<int64_t> anno; anno.persistent(B.nreads + 1); DBuf<int32_t> md; md.persistent((size_t)nbytes / 4 + 2);
+    DN_CUDA(cudaMemcpyAsync(anno.p, anno_h, sizeof(int64_t) * (B.nreads + 1), cudaMemcpyHostToDevice, s));
+    DN_CUDA(cudaMemcpyAsync(md.p, data_h, nbytes, cudaMemcpyHostToDevice, s));
+    DN_LAUNCH(k_mask_bits, B.nreads, 64, 0, s, (const int64_t *)anno.p, (const int32_t *)md.p, B.nreads,
+              (const int64_t *)B.off.p, (const int32_t *)B.len.p, B.mask.p, B.mask_rc.p);
+    DN_CUDA(cudaStreamSynchronize(s));
+}
+
 void block_upload(const dn_block_desc &d, DevBlock &B, cudaStream_t s) {
     if (d.nreads < 0 || (d.nreads > 0 && (!d.rlen || !d.boff || !d.data))) throw Error("dn_block_desc: null field");
     B.nreads = d.nreads;
@@ -101,20 +119,7 @@ void block_upload(const dn_block_desc &d, DevBlock &B, cudaStream_t s) {
         DN_CUDA(cudaMemcpyAsync(B.group.p, d.group, sizeof(int32_t) * d.nreads, cudaMemcpyHostToDevice, s));
     }
     B.has_mask = false;
-    if (d.mask_anno && d.mask_data) {
-        int64_t nbytes = d.mask_anno[d.nreads];
-        if (nbytes > 0) {
-            B.has_mask = true;
-            size_t mw = (size_t)(g >> 5) + 4;
-            B.mask.persistent(mw); B.mask_rc.persistent(mw); B.mask.zero(s); B.mask_rc.zero(s);
-            DBuf<int64_t> anno; anno.persistent(d.nreads + 1); DBuf<int32_t> md; md.persistent((size_t)nbytes / 4 + 2);
-            DN_CUDA(cudaMemcpyAsync(anno.p, d.mask_anno, sizeof(int64_t) * (d.nreads + 1), cudaMemcpyHostToDevice, s));
-            DN_CUDA(cudaMemcpyAsync(md.p, d.mask_data, nbytes, cudaMemcpyHostToDevice, s));
-            DN_LAUNCH(k_mask_bits, d.nreads, 64, 0, s, (const int64_t *)anno.p, (const int32_t *)md.p, d.nreads,
-                      (const int64_t *)B.off.p, (const int32_t *)B.len.p, B.mask.p, B.mask_rc.p);
-            DN_CUDA(cudaStreamSynchronize(s));
-        }
-    }
+    if (d.mask_anno && d.mask_data) block_add_mask(B, d.mask_anno, d.mask_data, s);
     DN_CUDA(cudaStreamSynchronize(s));
 }
 

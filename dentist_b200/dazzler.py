@@ -72,6 +72,7 @@ class Block:
         self.nreads = int(d.nreads)
         self.bases = int(_lib.lib().dn_block_bases(self._h))
         self.h2d_bytes = int(data.nbytes + rlen.nbytes + bo.nbytes)
+        self.has_group = group is not None
 
     @classmethod
     def crop(cls, src, read, begin, end, group=None):
@@ -87,7 +88,15 @@ class Block:
         self.nreads = len(read)
         self.bases = int(_lib.lib().dn_block_bases(self._h))
         self.h2d_bytes = int(read.nbytes * 3)
+        self.has_group = group is not None
         return self
+
+    def maskDust(self, window=64, threshold=2.0, minlen=10):
+        """dbdust(db) followed by `-mdust` (package.d:476-481): DUST intervals join the block's own seed mask on the
+        device.  Returns the number of masked bases."""
+        m = C.c_int64(0)
+        _lib.check(_lib.lib().dn_block_mask_dust(self._h, int(window), C.c_double(threshold), int(minlen), C.byref(m)))
+        return int(m.value)
 
     def free(self):
         if self._h:

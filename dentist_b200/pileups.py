@@ -64,34 +64,58 @@ def find_reference_read_candidates(qv, qoff, reads):
     return [r for _, _, r in scored]
 
 
-def process_pileups(reads, group, max_alignment_error=0.3, flanks=None):
+def process_pileups(reads, group, max_alignment_error=0.3, flanks=None, allowed=None, dust=False, candidates=False):
     """reads: synth.Block-like (off, bases) of all cropped reads; group: pile id per read.
+    allowed: bool per read = member of allowedReferenceReadIds (package.d:456-468; default all); dust: DUST-mask the
+    cropped reads first (package.d:476); candidates: also return the ranked reference read candidates of every pile.
     Returns dict(consensus=[codes per pile], reference_read=[read id per pile], las=Las, flank_las=Las|None)."""
     group = np.ascontiguousarray(group, np.int32)
     lens = np.diff(reads.off).astype(np.int32)
     npiles = int(group.max()) + 1 if len(group) else 0
     g = dazzler.Block(reads.off, reads.bases, group=group)
+    if dust:
+        g.maskDust()                                                     # dbdust(croppedDb) + -mdust, package.d:476-481
     # daligner -T<n> -B -s126 -l500 -e0.7 -mdust X X   (pileUpAlignmentOptions, commandline.d:2886-2902)
     las = dazzler.align(g, g, tspace=TSPACE, minlen=MIN_ANCHOR, e=0.7, self_block=1)
     las.filterLocalAlignments(max_alignment_error)                      # package.d:483-485
     if len(las) == 0:
         raise dazzler.DnError("empty pileup alignment")                  # package.d:487-490
     las.chainLocalAlignments(min_score=TSPACE)                           # package.d:492-496, chainingOptions commandline.d:2820-2830
-    # coverage = |allowedReferenceReadIds| (all reads of the pile here), raised to 4 for piles of >= 4 reads
+    # coverage = |allowedReferenceReadIds|, raised to minQVCoverage for piles of >= 4 reads (package.d:498-501)
     psize = np.bincount(group, minlength=npiles)
-    cov_pile = np.where((psize < MIN_QV_COVERAGE), psize, np.maximum(psize, MIN_QV_COVERAGE))
+    ok = np.ones(len(group), bool) if allowed is None else np.ascontiguousarray(allowed, bool)
+    nallowed = np.bincount(group[ok], minlength=npiles)
+    cov_pile = np.where((nallowed < MIN_QV_COVERAGE) & (psize >= MIN_QV_COVERAGE), MIN_QV_COVERAGE, nallowed)
     qv, qoff = dazzler.computeQVs(lens, las, cov_pile[group])            # package.d:498-503
     las.filterPileUpAlignments(lens, lens, TSPACE)                       # package.d:505-510 (Yes.forceFlat)
     las.forceFlat()
     if len(las) == 0:
         raise dazzler.DnError("empty pileup alignment after filtering")
-    ref_reads = [int(c[0]) for c in dazzler.findReferenceReadCandidates(qv, qoff, group, npiles, BAD_FRACTION)]   # package.d:518-568
-    cons = dazzler.getConsensus(g, las, ref_reads)                       # package.d:600-619
+    ranked = dazzler.findReferenceReadCandidates(qv, qoff, np.where(ok, group, -1), npiles, BAD_FRACTION)   # package.d:518-568
+    # selectReferenceRead / computeConsensus with retry on the next candidate (package.d:307-329)
+    ref_reads = [int(c[0]) if len(c) else -1 for c in ranked]
+    cons = [np.zeros(0, np.uint8)] * npiles
+    pending = [p for p in range(npiles) if ref_reads[p] >= 0]
+    attempt = 0
+    while pending:
+        got = dazzler.getConsensus(g, las, [ref_reads[p] for p in pending])   # package.d:600-619
+        nxt = []
+        for p, c in zip(pending, got):
+            if len(c):
+                cons[p] = c
+            elif attempt + 1 < len(ranked[p]):
+                ref_reads[p] = int(ranked[p][attempt + 1]); nxt.append(p)
+            else:
+                ref_reads[p] = -1                                            # "no valid reference read found"
+        pending = nxt; attempt += 1
     out = dict(consensus=cons, reference_read=ref_reads, las=las, qv=qv, qoff=qoff, flank_las=None)
+    if candidates:
+        out["candidates"] = ranked
     if flanks is not None:
         # daligner -A -B -s126 -l126 -e0.7 F C   (postConsensusAlignmentOptions, commandline.d:2918-2935)
         coff = np.zeros(len(cons) + 1, np.int64); coff[1:] = np.cumsum([len(c) for c in cons])
-        cb = dazzler.Block(coff, np.concatenate(cons) if cons else np.zeros(0, np.uint8))
+        cb = dazzler.Block(coff, np.concatenate(cons) if cons else np.zeros(0, np.uint8),
+                           group=None if not getattr(flanks, "has_group", False) else np.arange(npiles, dtype=np.int32))
         fb = flanks if isinstance(flanks, dazzler.Block) else dazzler.Block(flanks.off, flanks.bases)
         out["flank_las"] = dazzler.align(fb, cb, tspace=TSPACE, minlen=TSPACE, e=0.7)
     g.free()
@@ -113,13 +137,41 @@ def _subtract(intervals, mask):
     return out
 
 
-def common_trace_point(intervals, seed, tspace, contig_len, repeat_mask=()):
+def _normalise(intervals):
+    """Region semantics (util/region.d): sorted, overlapping or touching intervals merged, empty ones dropped."""
+    out = []
+    for b, e in sorted((int(b), int(e)) for b, e in intervals if e > b):
+        if out and b <= out[-1][1]:
+            out[-1] = (out[-1][0], max(out[-1][1], e))
+        else:
+            out.append((b, e))
+    return out
+
+
+def _intersect(x, y):
+    out, i, j = [], 0, 0
+    while i < len(x) and j < len(y):
+        b, e = max(x[i][0], y[j][0]), min(x[i][1], y[j][1])
+        if b < e:
+            out.append((b, e))
+        if x[i][1] < y[j][1]:
+            i += 1
+        else:
+            j += 1
+    return out
+
+
+def common_trace_point(regions, seed, tspace, contig_len, repeat_mask=()):
     """getCommonTracePoint (cropper.d:446-500): a trace point (multiple of `tspace`, or the contig end) that lies in
-    the A interval of every alignment and -- if possible -- outside `repeat_mask`; the last one for seed 'front',
-    the first one for seed 'back'; -1 if there is none.  intervals = [(abpos, aepos), ...] on one contig."""
-    b = max(i[0] for i in intervals); e = min(i[1] for i in intervals)
-    common = [(b, e)] if b < e else []
-    for region in (_subtract(common, sorted(repeat_mask)), common):
+    the contig-A region of every alignment chain and -- if possible -- outside `repeat_mask`; the last one for seed
+    'front', the first one for seed 'back'; -1 if there is none.
+    regions: per chain either one (abpos, aepos) or the list of its local alignments' (abpos, aepos)."""
+    common = None
+    for r in regions:
+        r = _normalise([r] if isinstance(r[0], (int, np.integer)) else r)
+        common = r if common is None else _intersect(common, r)
+    common = common or []
+    for region in (_subtract(common, _normalise(repeat_mask)), common):
         if not region:
             continue
         lo = -(-region[0][0] // tspace) * tspace

@@ -188,7 +188,8 @@ int dn_las_chain(dn_las_buf *las, int32_t max_indel, int32_t max_chain_gap, doub
  * records in FlatLocalAlignment order (base.d:1787-1809). */
 int dn_las_force_flat(dn_las_buf *las);
 /* findReferenceReadCandidates (processPileUps/package.d:518-568) for a batch of pile-ups (host logic):
- * rank[pile_off[p] .. pile_off[p+1]) = reads of pile p ordered by (numBadQVs, meanQV, readId). */
+ * rank[pile_off[p] .. pile_off[p+1]) = reads of pile p ordered by (numBadQVs, meanQV, readId).  group[r] < 0 = read r is
+ * not in allowedReferenceReadIds (package.d:456-468): it neither enters the QV histogram nor the ranking. */
 int dn_reference_read_candidates(const uint8_t *qv, const int64_t *qoff, const int32_t *group, int32_t nreads, int32_t npiles,
                                  double bad_fraction, int32_t *rank, int64_t *pile_off);
 
@@ -212,6 +213,10 @@ int dn_collect_filter(const dn_las_buf *las, const int32_t *alen, int32_t na, co
  * byte offsets into *data, *data = int32 (begin,end) pairs.  Free both with dn_free.  Feed them to
  * dn_block_desc.mask_* (what `-mdust` does). */
 int dn_dust_block(const dn_block *blk, int32_t window, double threshold, int32_t minlen, int64_t **anno, int32_t **data);
+
+/* dbdust + `-mdust` in one step (processPileUps/package.d:476-481, 655-665): DUST intervals of the resident block are
+ * OR-ed into its own seed-exclusion mask; nothing returns to the host except the number of masked bases (may be NULL). */
+int dn_block_mask_dust(dn_block *blk, int32_t window, double threshold, int32_t minlen, int64_t *masked_bases);
 
 /* ---- file-level drop-ins for dazzler.d ---------------------------------------------------- */
 

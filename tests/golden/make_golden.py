@@ -74,6 +74,26 @@ def main():
                           bepos=int(loci[1][1]), trace=tps, complement=comp, seed=seed, tspace=100, asserts=asserts))
     with open(os.path.join(HERE, "cropper_kat.json"), "w") as f:
         json.dump(cases, f, indent=1)
+    # PileUpDb / InsertionDb test data  common/binio/_testdata/{pileupdb,insertiondb}.d (literal data only) with the
+    # element counts the reference's size tests use (pileupdb.d:430-464, insertiondb.d:470-511)
+    binio = {}
+    for name in ("pileupdb", "insertiondb"):
+        src = open(os.path.join(REF, "common/binio/_testdata/%s.d" % name)).read()
+        counts = {m.group(1): int(m.group(2)) for m in re.finditer(r"enum (num\w+) = (\d+);", src)}
+        body = src[src.index("return [", src.index("TestData()")) + len("return "):]
+        body = body[:body.rindex("];") + 1]
+        body = body.replace("CompressedSequence.from(", "Seq(").replace("AlignmentLocationSeed.", "")
+        ns = dict(__builtins__={}, complement=1, front="front", back="back", begin="begin", end="end", pre="pre", post="post",
+                  Contig=lambda a, b: [a, b], Locus=lambda a, b: [a, b], TracePoint=lambda a, b: [a, b], Seq=lambda x: x, id_t=lambda x: x,
+                  AlignmentFlags=lambda *f: sum(f), ContigNode=lambda a, b: [a, b],
+                  LocalAlignment=lambda a, b, d, t: dict(ab=a[0], ae=a[1], bb=b[0], be=b[1], diffs=d, trace=t),
+                  AlignmentChain=lambda i, a, b, f, l, tpd=0: dict(id=i, contigA=a, contigB=b, flags=f, las=l, tpd=tpd),
+                  SeededAlignment=lambda c, s: dict(c, seed=s), ReadAlignment=lambda *s: list(s),
+                  InsertionInfo=lambda seq, cl, ov, rid: dict(sequence=seq, contig_length=cl, overlaps=ov, read_ids=rid),
+                  Insertion=lambda s, e, info: dict(info, start=s, end=e))
+        binio[name] = dict(counts=counts, data=eval(body, ns))
+    with open(os.path.join(HERE, "binio_kat.json"), "w") as f:
+        json.dump(binio, f, separators=(",", ":"))
     out = dict(source="a-ludi/dentist @ 1aa60e04", tspace=100, ladump=dump, flat=flat, chains=chains, trace_kat=kat)
     with open(os.path.join(HERE, "las_golden.json"), "w") as f:
         json.dump(out, f, indent=1)
