@@ -1,0 +1,111 @@
+"""Host logic of the batched `dentist process` driver (dentist_b200/process.py) on the reference's own pile-up and
+insertion test data (common/binio/_testdata/*.d) -- no GPU."""
+import json
+import os
+
+import numpy as np
+import pytest
+
+from dentist_b200 import pileups, process
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+KAT = json.load(open(os.path.join(HERE, "golden", "binio_kat.json")))
+
+
+def _seeded(d):
+    return dict(id=d["id"], contigA=tuple(d["contigA"]), contigB=tuple(d["contigB"]), flags=d["flags"], tpd=d["tpd"] or 100, seed=d["seed"],
+                las=[dict(ab=l["ab"], ae=l["ae"], bb=l["bb"], be=l["be"], diffs=l["diffs"], trace=np.array(l["trace"], np.uint16).reshape(-1, 2))
+                     for l in d["las"]])
+
+
+class _Seqs:
+    """random sequences of given lengths, 1-based ids -> read(i) 0-based"""
+
+    def __init__(self, lengths, seed):
+        rng = np.random.default_rng(seed)
+        self.seq = {i: rng.integers(0, 4, n).astype(np.uint8) for i, n in lengths.items()}
+
+    def read(self, i):
+        return self.seq[i + 1]
+
+
+def test_common_trace_point_rules():
+    ctp = pileups.common_trace_point
+    assert ctp([(250, 1000), (130, 1000)], "back", 100, 1000) == 300            # first grid point inside every alignment
+    assert ctp([(0, 730), (0, 655)], "front", 100, 5000) == 600                 # last grid point for a front seed
+    assert ctp([(0, 730), (0, 655)], "front", 100, 5000, repeat_mask=[(550, 700)]) == 500     # avoids the repeat mask ...
+    assert ctp([(0, 730), (0, 655)], "front", 100, 5000, repeat_mask=[(0, 5000)]) == 600      # ... unless nothing is left
+    assert ctp([[(0, 210), (390, 900)], (0, 900)], "back", 100, 900) == 0        # chain with a hole: region = its local alignments
+    assert ctp([[(10, 210), (390, 900)], (380, 900)], "back", 100, 900) == 400
+    assert ctp([(0, 300), (400, 900)], "back", 100, 900) == -1                   # no common region
+    assert ctp([(850, 955)], "back", 100, 955) == 900
+    assert ctp([(910, 955)], "back", 100, 955) == 955                            # only the contig end is left as a candidate
+
+
+def test_crop_reference_pileups():
+    piles = [[[_seeded(s) for s in ra] for ra in p] for p in KAT["pileupdb"]["data"]]
+    contigs = {sa["contigA"][0]: sa["contigA"][1] for p in piles for ra in p for sa in ra}
+    rlens = {sa["contigB"][0]: sa["contigB"][1] for p in piles for ra in p for sa in ra}
+    ref, reads = _Seqs(contigs, 1), _Seqs(rlens, 2)
+    for pile in piles:
+        crop = process.crop_pileup(pile, ref, reads, {}, 500)
+        assert [c for c, _ in crop["ref_positions"]] == sorted({sa["contigA"][0] for ra in pile for sa in ra})
+        for (cid, pos), seed in zip(crop["ref_positions"], crop["seeds"]):
+            assert pos % 100 == 0 or pos == contigs[cid]
+            for ra in pile:
+                for sa in ra:
+                    if sa["contigA"][0] == cid:
+                        assert sa["seed"] == seed and any(la["ab"] <= pos <= la["ae"] for la in sa["las"])
+        for ra, seq, ok in zip(pile, crop["sequences"], crop["allowed"]):
+            assert 0 < len(seq) <= ra[0]["contigB"][1] + 2 * 500
+            assert ok == (len(ra) == len(crop["ref_positions"]))
+    # second pile-up: a gap between contigs 1 and 2; the spanning read keeps exactly what lies between both crop points
+    pile = piles[1]
+    crop = process.crop_pileup(pile, ref, reads, {}, 500)
+    span = [i for i, ra in enumerate(pile) if len(ra) == 2][0]
+    sa_l, sa_r = pile[span]
+    b0, e0 = process.chain_cropping_slice(sa_l, dict(crop["ref_positions"])[1])
+    b1, e1 = process.chain_cropping_slice(sa_r, dict(crop["ref_positions"])[2])
+    assert len(crop["sequences"][span]) == min(e0, e1) - max(b0, b1)
+    with pytest.raises(process.PileUpSkipped):
+        process.crop_pileup([[dict(pile[0][0], las=[dict(pile[0][0]["las"][0], ab=8290, ae=8300)])], pile[1]], ref, reads, {}, 500)
+
+
+def test_support_patches_extend_short_anchors():
+    ref, reads = _Seqs({1: 3000}, 3), _Seqs({1: 4000, 2: 4000}, 4)
+    tr = np.array([[0, 100]] * 3, np.uint16)
+    mk = lambda rid, comp: dict(id=rid, contigA=(1, 3000), contigB=(rid, 4000), flags=1 if comp else 0, tpd=100, seed="front",
+                                las=[dict(ab=0, ae=300, bb=3700, be=4000, diffs=0, trace=tr)])
+    crop = process.crop_pileup([[mk(1, False)], [mk(2, True)]], ref, reads, {}, 500)
+    assert crop["ref_positions"] == [(1, 200)] and crop["seeds"] == ["front"]
+    patch = ref.read(0)[200:500]                                                     # contig[pos .. minAnchorLength)
+    fwd, rev = crop["sequences"]
+    assert np.array_equal(fwd, np.concatenate([reads.read(0)[:3900], patch]))         # read kept up to the crop point + patch behind it
+    assert np.array_equal(rev, np.concatenate([(3 - patch)[::-1], reads.read(1)[100:]]))   # complement: mirrored slice, patch in front
+
+
+def test_adjust_repeat_mask():
+    mask = {1: [(0, 900)], 2: [(0, 100)]}
+    out = process.adjust_repeat_mask(mask, {1: 5000, 2: 5000}, [(1, 1200), (2, 4000)], ["front", "back"], 500)
+    assert 1 not in out and out[2] == [(0, 100)]                                     # 300 unmasked anchor bases < 500 -> mask dropped
+
+
+def test_insertion_alignment_on_reference_insertions():
+    n = 0
+    for ins in KAT["insertiondb"]["data"]:
+        ov = [_seeded(s) for s in ins["overlaps"]]
+        if not ov:
+            continue
+        ref_read = [dict(contigA=o["contigA"], contigB=(7, 1), flags=o["flags"], seed=o["seed"]) for o in ov]
+        positions = [(o["contigA"][0], 0) for o in ov]
+        chains = [dict(o, seed="front", flags=o["flags"]) for o in ov]
+        got = process.insertion_alignment(chains, ref_read, positions, 100)
+        assert [(g["contigA"], g["seed"], g["las"][0]["ab"]) for g in got] == [(o["contigA"], o["seed"], o["las"][0]["ab"]) for o in ov]
+        start, end = process.make_join(ref_read)
+        assert (list(start), list(end)) == (ins["start"], ins["end"])
+        # a consensus that maps to the other strand than the reference read did is rejected
+        with pytest.raises(process.PileUpSkipped):
+            shifted = dict(chains[0], flags=chains[0]["flags"] ^ 1)
+            process.insertion_alignment([shifted] + [dict(c) for c in chains[1:]], ref_read, positions, 100)
+        n += 1
+    assert n >= 10
