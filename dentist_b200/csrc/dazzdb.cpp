@@ -168,7 +168,8 @@ bool write_dazz_db(const std::string &path, const std::vector<std::vector<uint8_
     f = fopen((dir + "/." + root + ".idx").c_str(), "wb"); if (!f) { err = "cannot write .idx"; return false; }
     fwrite(&h, sizeof h, 1, f); if (!rd.empty()) fwrite(rd.data(), sizeof(IdxRead), rd.size(), f); fclose(f);
     f = fopen((dir + "/." + root + ".bps").c_str(), "wb"); if (!f) { err = "cannot write .bps"; return false; }
-    if (!bps.empty()) fwrite(bps.data(), 1, bps.size(), f); fclose(f);
+    if (!bps.empty()) fwrite(bps.data(), 1, bps.size(), f);
+    fclose(f);
     if (dam) { f = fopen((dir + "/." + root + ".hdr").c_str(), "wb"); if (f) { fprintf(f, ">%s\n", root.c_str()); fclose(f); } }
     return true;
 }

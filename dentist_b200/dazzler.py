@@ -172,6 +172,18 @@ def read_las(path):
     return tspace, rec, toff, tr
 
 
+def write_las(path, tspace, rec, toff, trace):
+    """Write caller-owned arrays as a LAS file (writer side of dazzler.d:1913-2170): rec = REC_DTYPE records,
+    toff = trace offset (uint16 units) per record, trace = uint16 (diffs, bases) pairs."""
+    rec = np.ascontiguousarray(rec, _lib.REC_DTYPE); toff = np.ascontiguousarray(toff, np.int64); trace = np.ascontiguousarray(trace, np.uint16)
+    buf = _lib.LasBuf()
+    buf.nrec = len(rec); buf.ntrace = len(trace); buf.tspace = int(tspace)
+    buf.rec = C.cast(rec.ctypes.data, C.POINTER(_lib.LasRecord))
+    buf.toff = C.cast(toff.ctypes.data, C.POINTER(C.c_int64))
+    buf.trace = C.cast(trace.ctypes.data, C.POINTER(C.c_uint16))
+    _lib.check(_lib.lib().dn_las_write(path.encode(), C.byref(buf)))
+
+
 def _opts(opts):
     arr = (C.c_char_p * len(opts))(*[o.encode() for o in opts])
     return arr, len(opts)

@@ -97,3 +97,12 @@ def test_reference_read_candidates_matches_python_mirror():
             assert len(got[p]) == 0
             continue
         assert got[p].tolist() == pileups.find_reference_read_candidates(qv, qoff, members)
+
+
+def test_cli_stand_ins_exist_and_print_usage():
+    """dn-damapper / dn-daligner / dn-dbdust keep the argv contract of the tools the workflow calls (Snakefile:1143-1169)."""
+    import subprocess
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    for tool, args in (("dn-damapper", ["only-one.db"]), ("dn-daligner", []), ("dn-dbdust", ["a.db", "b.db"])):
+        r = subprocess.run([os.path.join(root, "bin", tool)] + args, capture_output=True, text=True)
+        assert r.returncode == 1 and r.stderr.startswith("Usage: " + tool), (tool, r.stderr)

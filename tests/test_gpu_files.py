@@ -126,3 +126,25 @@ def test_getConsensus_file_form_on_the_reference_kat(tmp_path):
     assert np.array_equal(codes, blk.read(k["expected_read"]))
     with pytest.raises(dazzler.DnError, match="out of bounds"):
         dazzler.getConsensusDb(db, las_path, 9)
+
+
+def test_cli_damapper_equals_the_library_call(tmp_path):
+    """`dn-damapper -C -e0.7 R Q` run in a directory leaves the same R.Q.las / Q.R.las there as getDamapping."""
+    import os
+    import subprocess
+    from dentist_b200 import dazzler
+    ref, reads = _case(57)
+    (tmp_path / "cli").mkdir(); (tmp_path / "api").mkdir()
+    dbutil.write_db(str(tmp_path / "ref.dam"), ref)
+    dbutil.write_db(str(tmp_path / "reads.db"), reads)
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    r = subprocess.run([os.path.join(root, "bin", "dn-damapper"), "-C", "-T4", "-e0.7", str(tmp_path / "ref.dam"), str(tmp_path / "reads.db")],
+                       cwd=str(tmp_path / "cli"), capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    dazzler.getDamapping(str(tmp_path / "ref.dam"), str(tmp_path / "reads.db"), ["-C", "-T4", "-e0.7"], str(tmp_path / "api"))
+    for name in ("ref.reads.las", "reads.ref.las"):
+        a = open(str(tmp_path / "cli" / name), "rb").read(); b = open(str(tmp_path / "api" / name), "rb").read()
+        assert len(a) > 1000 and a == b, name
+    r = subprocess.run([os.path.join(root, "bin", "dn-damapper"), "-C", str(tmp_path / "missing.dam"), str(tmp_path / "reads.db")],
+                       cwd=str(tmp_path / "cli"), capture_output=True, text=True)
+    assert r.returncode == 1 and "missing" in r.stderr
