@@ -379,6 +379,40 @@ def collectFilter(las, alen, blen, repeat_mask=None, max_alignment_error=0.3, pr
     return f, s_, np.flatnonzero(u).tolist()
 
 
+def _track(anno_p, data_p, n):
+    L = _lib.lib()
+    a = np.ctypeslib.as_array(anno_p, shape=(n + 1,)).copy()
+    m = int(a[-1]) // 4
+    d = np.ctypeslib.as_array(data_p, shape=(max(m, 1),))[:m].copy()
+    L.dn_free(anno_p); L.dn_free(data_p)
+    return [[(int(d[i]), int(d[i + 1])) for i in range(int(a[r]) // 4, int(a[r + 1]) // 4, 2)] for r in range(n)]
+
+
+def maskRepetitiveRegions(las, alen, blen, coverage_bounds, improper_coverage_bounds=None, proper_alignment_allowance=100):
+    """`dentist mask-repetitive-regions` (commands/maskRepetitiveRegions.d:135-232) on an in-memory LAS: per A contig the
+    intervals whose chain coverage leaves coverage_bounds, united (reads alignments only) with those whose coverage by
+    IMPROPER chains leaves improper_coverage_bounds."""
+    L = _lib.lib()
+    alen = np.ascontiguousarray(alen, np.int32); blen = np.ascontiguousarray(blen, np.int32)
+    passes = [(coverage_bounds, 0)] + ([(improper_coverage_bounds, 1)] if improper_coverage_bounds is not None else [])
+    masks = []
+    for (lo, hi), improper in passes:
+        anno = C.POINTER(C.c_int64)(); data = C.POINTER(C.c_int32)()
+        _lib.check(L.dn_mask_coverage(C.byref(las._buf), alen.ctypes.data_as(C.c_void_p), len(alen), blen.ctypes.data_as(C.c_void_p), len(blen),
+                                      C.c_double(lo), C.c_double(hi), improper, int(proper_alignment_allowance), C.byref(anno), C.byref(data)))
+        masks.append(_track(anno, data, len(alen)))
+    out = []
+    for c in range(len(alen)):                                    # repetitiveRegions | repetitiveRegionsImproper (:209)
+        merged = []
+        for b, e in sorted(iv for m in masks for iv in m[c]):
+            if merged and b <= merged[-1][1]:
+                merged[-1] = (merged[-1][0], max(merged[-1][1], e))
+            else:
+                merged.append((b, e))
+        out.append(merged)
+    return out
+
+
 def findReferenceReadCandidates(qv, qoff, group, npiles, bad_fraction=0.08):
     """processPileUps/package.d:518-568 for a batch: list (per pile) of read ids ranked by (numBadQVs, meanQV, readId)."""
     qv = np.ascontiguousarray(qv, np.uint8); qoff = np.ascontiguousarray(qoff, np.int64); group = np.ascontiguousarray(group, np.int32)

@@ -208,6 +208,14 @@ int dn_collect_filter(const dn_las_buf *las, const int32_t *alen, int32_t na, co
                       const int64_t *mask_anno, const int32_t *mask_data, double max_err, int32_t allowance, int32_t min_anchor,
                       int64_t *nchains, int32_t **chain_first, uint8_t **chain_status, uint8_t **read_used);
 
+/* BadAlignmentCoverageAssessor (commands/maskRepetitiveRegions.d:258-420) over the chains of a ref-vs-reads or self
+ * LAS (`alignmentIntervals`, :186-205): the parts of every A contig whose alignment coverage is < lower or > upper,
+ * in the mask-track layout (*anno = na+1 int64 byte offsets, *data = int32 (begin, end) pairs; free with dn_free).
+ * improper_only != 0 counts only chains that are not isProper(allowance) (the second pass of assessRepeatStructure,
+ * :160-176).  An empty LAS gives an empty mask (:349-350). */
+int dn_mask_coverage(const dn_las_buf *las, const int32_t *alen, int32_t na, const int32_t *blen, int32_t nb,
+                     double lower, double upper, int32_t improper_only, int32_t allowance, int64_t **anno, int32_t **data);
+
 /* dbdust(db, opts)  dazzler.d:3815-3818 (`DBdust -w -t -m`): low-complexity intervals of every read of a
  * resident block in the reference's mask-track layout (dazzler.d:4943-5052): *anno = nreads+1 int64
  * byte offsets into *data, *data = int32 (begin,end) pairs.  Free both with dn_free.  Feed them to

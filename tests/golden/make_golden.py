@@ -94,11 +94,19 @@ def main():
         binio[name] = dict(counts=counts, data=eval(body, ns))
     with open(os.path.join(HERE, "binio_kat.json"), "w") as f:
         json.dump(binio, f, separators=(",", ":"))
+    # BadAlignmentCoverageAssessor KATs  commands/maskRepetitiveRegions.d:302-340 (inputs), :395-411 (mask), :582-617 (changes)
+    mp = os.path.join(REF, "commands/maskRepetitiveRegions.d")
+    iv = lambda a, b: [[int(x) for x in m] for m in re.findall(r"ReferenceInterval\((\d+),\s*(\d+),\s*(\d+)\)", "\n".join(lines(mp, a, b)))]
+    txt = "\n".join(lines(mp, 575, 650))
+    maskcov = dict(alignments=iv(296, 331), contigs=iv(333, 341), bounds=[3, 5], mask=iv(402, 411),
+                   changes=[[int(x) for x in m] for m in re.findall(r"CoverageChange\((\d+),\s*(\d+),\s*(\d+),\s*(\d+)\)", txt)])
+    with open(os.path.join(HERE, "maskcov_kat.json"), "w") as f:
+        json.dump(maskcov, f)
     out = dict(source="a-ludi/dentist @ 1aa60e04", tspace=100, ladump=dump, flat=flat, chains=chains, trace_kat=kat)
     with open(os.path.join(HERE, "las_golden.json"), "w") as f:
         json.dump(out, f, indent=1)
     print("flat", len(flat), "chains", len(chains), "dump lines", len(dump), "kat tiles", len(kat["trace"]), "asserts", len(kat["asserts"]),
-          "cropper cases", len(cases), "consensus reads", len(cons["reads"]))
+          "cropper cases", len(cases), "consensus reads", len(cons["reads"]), "maskcov", len(maskcov["alignments"]), len(maskcov["contigs"]), len(maskcov["mask"]), len(maskcov["changes"]))
 
 
 if __name__ == "__main__":
