@@ -413,6 +413,29 @@ def maskRepetitiveRegions(las, alen, blen, coverage_bounds, improper_coverage_bo
     return out
 
 
+def _track_arrays(mask, n):
+    """per-sequence interval lists -> (anno, data) of the mask-track layout (dazzler.d:4943-5052)"""
+    anno = np.zeros(n + 1, np.int64); flat = []
+    for r in range(n):
+        anno[r] = 4 * len(flat)
+        for b, e in (mask[r] if r < len(mask) else []):
+            flat += [b, e]
+    anno[n] = 4 * len(flat)
+    return anno, np.ascontiguousarray(flat if flat else [0, 0], np.int32)
+
+
+def propagateMask(las, mask, na, blen):
+    """`dentist propagate-mask` (commands/propagateMask.d:109-300) on an in-memory LAS with trace points: mask = per A
+    contig a sorted list of disjoint (begin, end); returns the propagated mask per B read."""
+    L = _lib.lib()
+    blen = np.ascontiguousarray(blen, np.int32)
+    manno, mdata = _track_arrays(mask, na)
+    anno = C.POINTER(C.c_int64)(); data = C.POINTER(C.c_int32)()
+    _lib.check(L.dn_propagate_mask(C.byref(las._buf), int(na), manno.ctypes.data_as(C.c_void_p), mdata.ctypes.data_as(C.c_void_p),
+                                   blen.ctypes.data_as(C.c_void_p), len(blen), C.byref(anno), C.byref(data)))
+    return _track(anno, data, len(blen))
+
+
 def findReferenceReadCandidates(qv, qoff, group, npiles, bad_fraction=0.08):
     """processPileUps/package.d:518-568 for a batch: list (per pile) of read ids ranked by (numBadQVs, meanQV, readId)."""
     qv = np.ascontiguousarray(qv, np.uint8); qoff = np.ascontiguousarray(qoff, np.int64); group = np.ascontiguousarray(group, np.int32)

@@ -216,6 +216,13 @@ int dn_collect_filter(const dn_las_buf *las, const int32_t *alen, int32_t na, co
 int dn_mask_coverage(const dn_las_buf *las, const int32_t *alen, int32_t na, const int32_t *blen, int32_t nb,
                      double lower, double upper, int32_t improper_only, int32_t allowance, int64_t **anno, int32_t **data);
 
+/* `dentist propagate-mask` (commands/propagateMask.d:109-300): every local alignment of `las` (trace points required)
+ * carries the parts of its A contig's mask (mask_anno / mask_data: track layout, sorted disjoint intervals) over to its
+ * B read -- begin rounded down, end rounded up to a trace point (base.d:185-242), mirrored for complement alignments;
+ * the union per B read returns in the track layout (*anno = nb+1 offsets, *data = pairs; free with dn_free). */
+int dn_propagate_mask(const dn_las_buf *las, int32_t na, const int64_t *mask_anno, const int32_t *mask_data,
+                      const int32_t *blen, int32_t nb, int64_t **anno, int32_t **data);
+
 /* dbdust(db, opts)  dazzler.d:3815-3818 (`DBdust -w -t -m`): low-complexity intervals of every read of a
  * resident block in the reference's mask-track layout (dazzler.d:4943-5052): *anno = nreads+1 int64
  * byte offsets into *data, *data = int32 (begin,end) pairs.  Free both with dn_free.  Feed them to

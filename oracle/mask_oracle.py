@@ -85,3 +85,39 @@ def mask_repetitive_regions(rec, alen, blen, bounds, improper_bounds=None, allow
         else:
             out.append((c, b, e))
     return out
+
+
+def propagate_mask(rec, traces, tspace, mask_by_contig, blen):
+    """MaskPropagator (commands/propagateMask.d:109-300): every local alignment carries the parts of the A-contig mask
+    it overlaps over to its B read -- interval begin translated with RoundingMode.floor, end with ceil
+    (Trace.translateTracePoint, base.d:185-242, pinned by the 21-tile KAT in tests/golden/las_golden.json), mirrored for
+    complement alignments -- and the per-read union is the output mask.  No unit test in the reference for the
+    sweep itself: pinned through the translate KAT and the D source only.
+    mask_by_contig: per A contig a sorted list of disjoint (begin, end); returns the same for the B reads."""
+    from oracle import las as _las
+    out = [[] for _ in blen]
+    for i in range(len(rec)):
+        r = rec[i]
+        a, b = int(r["aread"]), int(r["bread"])
+        ab, ae, bb = int(r["abpos"]), int(r["aepos"]), int(r["bbpos"])
+        hit = [(mb, me) for mb, me in mask_by_contig[a] if me > ab and mb < ae]      # getIntersectingIntervals :216-231
+        for k, (mb, me) in enumerate(hit):
+            if k == 0:
+                mb = max(mb, ab)
+            if k == len(hit) - 1:
+                me = min(me, ae)
+            pb = _las.translate_trace_point(ab, ae, bb, tspace, traces[i], mb, "floor")[1]
+            pe = _las.translate_trace_point(ab, ae, bb, tspace, traces[i], me, "ceil")[1]
+            if int(r["flags"]) & COMP:
+                pb, pe = int(blen[b]) - pe, int(blen[b]) - pb
+            out[b].append((pb, pe))
+    res = []
+    for iv in out:                                                                    # QueryRegion normalisation (mergeMasks :296-300)
+        m = []
+        for s, e in sorted(x for x in iv if x[1] > x[0]):
+            if m and s <= m[-1][1]:
+                m[-1] = (m[-1][0], max(m[-1][1], e))
+            else:
+                m.append((s, e))
+        res.append(m)
+    return res
