@@ -9,6 +9,7 @@
 #include <cstdint>
 #include <stdexcept>
 #include <string>
+#include <utility>
 #include <vector>
 
 namespace dentist {
@@ -90,6 +91,11 @@ class Las {
     void filterPileUpAlignments(const std::vector<int32_t> &aLengths, const std::vector<int32_t> &bLengths, int32_t allowance) {
         enforce(dn_las_filter_pileup(&buf_, aLengths.data(), (int32_t)aLengths.size(), bLengths.data(), (int32_t)bLengths.size(), allowance));
     }
+    /// chainLocalAlignments(db, las, chainingOptions)  dazzler.d:3995-4018, defaults commandline.d:2820-2830
+    void chainLocalAlignments(int32_t maxIndel = 1000, int32_t maxChainGap = 10000, double maxRelOverlap = 0.3, double minRelScore = 1.0,
+                              int32_t minScore = -1) {
+        enforce(dn_las_chain(&buf_, maxIndel, maxChainGap, maxRelOverlap, minRelScore, minScore < 0 ? buf_.tspace : minScore));
+    }
     void writeAlignments(const std::string &lasFile) const { enforce(dn_las_write(lasFile.c_str(), &buf_)); }   // dazzler.d:1913-1960
 
   private:
@@ -104,6 +110,12 @@ class Block {
     Block &operator=(const Block &) = delete;
     ~Block() { dn_block_free(h_); }
     const dn_block *raw() const { return h_; }
+    /// dbdust(db) + `-mdust` (processPileUps/package.d:476-481): returns the number of masked bases.
+    int64_t maskDust(int32_t window = 64, double threshold = 2.0, int32_t minLength = 10) {
+        int64_t m = 0;
+        enforce(dn_block_mask_dust(h_, window, threshold, minLength, &m));
+        return m;
+    }
 
   private:
     dn_block *h_ = nullptr;
@@ -124,6 +136,43 @@ inline std::vector<std::vector<uint8_t>> computeQVs(const std::vector<int32_t> &
     for (size_t r = 0; r < out.size(); r++) out[r].assign(qv + off[r], qv + off[r + 1]);
     dn_free(qv); dn_free(off);
     return out;
+}
+
+/// A mask as DENTIST's ReferenceRegion restricted to one DB: per contig a sorted list of disjoint [begin, end).
+using Mask = std::vector<std::vector<std::pair<int32_t, int32_t>>>;
+
+namespace detail {
+inline Mask takeTrack(int64_t *anno, int32_t *data, size_t n) {
+    Mask out(n);
+    for (size_t r = 0; r < n; r++)
+        for (int64_t i = anno[r] / 4; i < anno[r + 1] / 4; i += 2) out[r].emplace_back(data[i], data[i + 1]);
+    dn_free(anno); dn_free(data);
+    return out;
+}
+}  // namespace detail
+
+/// BadAlignmentCoverageAssessor(lower, upper)(alignmentIntervals(improperOnly), contigIntervals)
+/// commands/maskRepetitiveRegions.d:135-232, 258-420
+inline Mask maskCoverage(const Las &las, const std::vector<int32_t> &aLengths, const std::vector<int32_t> &bLengths, double lowerLimit,
+                         double upperLimit, bool improperOnly = false, int32_t properAlignmentAllowance = 0) {
+    int64_t *anno = nullptr; int32_t *data = nullptr;
+    enforce(dn_mask_coverage(las.raw(), aLengths.data(), (int32_t)aLengths.size(), bLengths.data(), (int32_t)bLengths.size(), lowerLimit,
+                             upperLimit, improperOnly ? 1 : 0, properAlignmentAllowance, &anno, &data));
+    return detail::takeTrack(anno, data, aLengths.size());
+}
+
+/// MaskPropagator  commands/propagateMask.d:109-300: the A-contig mask carried over to the B reads through the trace points.
+inline Mask propagateMask(const Las &las, const Mask &inputMask, const std::vector<int32_t> &bLengths) {
+    std::vector<int64_t> manno(inputMask.size() + 1, 0); std::vector<int32_t> mdata;
+    for (size_t c = 0; c < inputMask.size(); c++) {
+        manno[c] = 4 * (int64_t)mdata.size();
+        for (auto &iv : inputMask[c]) { mdata.push_back(iv.first); mdata.push_back(iv.second); }
+    }
+    manno[inputMask.size()] = 4 * (int64_t)mdata.size();
+    mdata.push_back(0); mdata.push_back(0);
+    int64_t *anno = nullptr; int32_t *data = nullptr;
+    enforce(dn_propagate_mask(las.raw(), (int32_t)inputMask.size(), manno.data(), mdata.data(), bLengths.data(), (int32_t)bLengths.size(), &anno, &data));
+    return detail::takeTrack(anno, data, bLengths.size());
 }
 
 /// getConsensus(db, las, readId, opts)  dazzler.d:4213-4238; readId is 1-based like in DENTIST.

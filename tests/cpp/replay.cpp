@@ -31,16 +31,26 @@ int main(int argc, char **argv) {
         dn_block_desc d{}; d.nreads = N; d.format = DN_SEQ_BYTES; d.rlen = rlen.data(); d.boff = boff.data();
         d.data = bases.data(); d.data_bytes = (int64_t)bases.size();
         Block db(d);
+        printf("dust %lld\n", (long long)db.maskDust());
         dn_align_params p; dn_align_params_default(&p);
         p.tspace = 126; p.minlen = 500; p.self_block = 1;                      // daligner -s126 -l500 -e0.7 X X
         Las las = align(db, db, p);
         printf("raw %lld\n", (long long)las.size());
         las.filterLocalAlignments(0.3);
+        las.chainLocalAlignments();
+        printf("chained %lld\n", (long long)las.size());
         auto qv = computeQVs(rlen, las, 4);
         las.filterPileUpAlignments(rlen, rlen, 126);
         printf("filtered %lld\n", (long long)las.size());
         long long qsum = 0; for (auto &q : qv) for (auto x : q) qsum += x;
         printf("qvsum %lld\n", qsum);
+        auto cov = maskCoverage(las, rlen, rlen, 0, 5);
+        long long covered = 0; for (auto &c : cov) for (auto &iv : c) covered += iv.second - iv.first;
+        printf("overcovered %lld\n", covered);
+        Mask in(N); in[0].emplace_back(500, 900);
+        auto prop = propagateMask(las, in, rlen);
+        long long pb = 0; for (auto &c : prop) for (auto &iv : c) pb += iv.second - iv.first;
+        printf("propagated %lld\n", pb);
         auto cons = getConsensus(db, las, 1);
         unsigned long long h = 1469598103934665603ull; int same = 0;
         for (size_t i = 0; i < cons.size(); i++) { h = (h ^ cons[i]) * 1099511628211ull; }

@@ -59,14 +59,21 @@ def test_cpp_mirror_equals_python_path(tmp_path):
     reads = _pile(7)
     off = np.zeros(len(reads) + 1, np.int64); off[1:] = np.cumsum([len(x) for x in reads])
     g = dazzler.Block(off, np.concatenate(reads))
+    assert int(got["dust"]) == g.maskDust()
     lens = np.diff(off)
     las = dazzler.align(g, g, tspace=126, minlen=500, self_block=1)
     assert int(got["raw"]) == len(las) > 20
     las.filterLocalAlignments(0.3)
+    las.chainLocalAlignments()
+    assert int(got["chained"]) == len(las)
     q, _ = dazzler.computeQVs(lens, las, 4)
     las.filterPileUpAlignments(lens, lens, 126)
     assert int(got["filtered"]) == len(las)
     assert int(got["qvsum"]) == int(q.astype(np.int64).sum())
+    cov = dazzler.maskRepetitiveRegions(las, lens, lens, (0, 5))
+    assert int(got["overcovered"]) == sum(e - b for c in cov for b, e in c) > 0
+    prop = dazzler.propagateMask(las, [[(500, 900)]] + [[] for _ in reads[1:]], len(reads), lens)
+    assert int(got["propagated"]) == sum(e - b for c in prop for b, e in c) > 0
     cons = dazzler.getConsensus(g, las, [0])[0]
     h = 1469598103934665603
     for b in cons.tolist():
