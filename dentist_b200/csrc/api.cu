@@ -238,7 +238,7 @@ static int parse_opts(const char *const *opts, int nopts, dn_align_params *p, bo
             default: return fail(DN_ERR_INVALID, std::string("unknown option: ") + o);
         }
     }
-    if (p->k > 15) p->k = 15;
+    if (p->k > 31) p->k = 31;                      /* damapper's default k = 20 is honoured (16-byte tuples) */
     return DN_OK;
 }
 
@@ -246,7 +246,7 @@ static int align_files(const char *dbA, const char *dbB, const char *const *opts
     if (!dbA || !outdir) return fail(DN_ERR_INVALID, "null argument");
     return guarded([&]() -> int {
         dn_align_params p; dn_align_params_default(&p);
-        if (mapper) p.minlen = 1000;
+        if (mapper) { p.minlen = 1000; p.k = 20; }       /* damapper's own defaults (DENTIST passes neither -k nor -l, commandline.d:2943-2955) */
         bool asym = false; std::vector<std::string> masks;
         if (int rc = parse_opts(opts, nopts, &p, &asym, &masks)) return rc;
         const bool self = (dbB == nullptr) || std::string(dbA) == std::string(dbB);

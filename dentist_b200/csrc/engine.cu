@@ -80,7 +80,7 @@ void hcache_free(void *p) {
 void align_blocks(const DevBlock &A, const DevBlock &B, const AlignParams &P, HostLas &out, cudaStream_t s) {
     out = HostLas();
     arena().reset();
-    if (P.k < 4 || P.k > 15) throw Error("k must be in [4,15]");
+    if (P.k < 4 || P.k > 31) throw Error("k must be in [4,31]");
     if (P.wmax < 4 || P.wmax > 62) throw Error("wmax must be in [4,62]");
     if (P.w < 1 || P.w > 12 || P.tspace < 1 || P.tspace > 32767) throw Error("bad w / tspace");
     if (P.cdiff < 20 || P.xdrop < 1 || P.xdrop > 1000) throw Error("bad cdiff / xdrop");
@@ -97,15 +97,27 @@ void align_blocks(const DevBlock &A, const DevBlock &B, const AlignParams &P, Ho
     Trace tr(s);
 
     // ---- K1 + K2: tuples, radix sort by k-mer -------------------------------------------------
-    DBuf<u64> ta(nA), ta2(nA);
-    emit_tuples(A, false, k, 0u, ta.p, s);
-    u64 *sa = radix_sort_u64(ta.p, ta2.p, nA, 32, 32 + 2 * k + 1, s);
-    if (sa == ta.p) ta2.release(); else ta.release();
+    // k <= 15: 8-byte tuples (kmer << 32 | position); k = 16..31: 16-byte {kmer, position} tuples, index lookup join only
+    const bool wide = k > 15;
+    if (wide && P.join_mode == 1) throw Error("the sorted-merge join (join_mode 1) supports k <= 15 only");
+    DBuf<u64> ta, ta2; DBuf<ulonglong2> tw, tw2;
+    u64 *sa = nullptr; ulonglong2 *sw = nullptr;
+    if (!wide) {
+        ta.alloc(nA); ta2.alloc(nA);
+        emit_tuples(A, false, k, 0u, ta.p, s);
+        sa = radix_sort_u64(ta.p, ta2.p, nA, 32, 32 + 2 * k + 1, s);
+        if (sa == ta.p) ta2.release(); else ta.release();
+    } else {
+        tw.alloc(nA); tw2.alloc(nA);
+        emit_tuples_wide(A, k, tw.p, s);
+        sw = radix_sort_rec16(tw.p, tw2.p, nA, 0, 0, 2 * k + 1, s);
+        if (sw == tw.p) tw2.release(); else tw.release();
+    }
     tr.mark("A tuples + sort");
-    const bool lookup = P.join_mode == 2 || (P.join_mode == 0 && nA * 8 <= (2ll << 30));   // auto: index lookup unless the A index is huge
+    const bool lookup = wide || P.join_mode == 2 || (P.join_mode == 0 && nA * 8 <= (2ll << 30));   // auto: index lookup unless the A index is huge
     const int npass_t = (2 * k + 1 + 7) / 8;
     out.stats.tuples_a = A.total_real; out.stats.tuples_b = 2 * B.total_real;
-    int64_t abytes = nA / 4 + 8 * nA + (int64_t)npass_t * 24 * nA;      // A: read packed, write tuples, sort passes (2R+1W)
+    int64_t abytes = nA / 4 + (wide ? 16 : 8) * nA + (int64_t)npass_t * (wide ? 48 : 24) * nA;      // A: read packed, write tuples, sort passes (2R+1W)
 
     // hit-key geometry
     const int64_t bandw = 1ll << P.w;
@@ -130,7 +142,8 @@ void align_blocks(const DevBlock &A, const DevBlock &B, const AlignParams &P, Ho
     int tbits = bits_for((uint64_t)nA) + (lookup ? -1 : 1); if (tbits < 16) tbits = 16; if (tbits > 2 * k) tbits = 2 * k;
     const int sh = 2 * k - tbits; const u32 nq = 1u << tbits;
     DBuf<u32> tbl((size_t)nq + 2);
-    DN_LAUNCH(k_prefix_table, (unsigned)((nA + 255) / 256), 256, 0, s, (const u64 *)sa, nA, sh, nq, tbl.p);
+    if (!wide) DN_LAUNCH(k_prefix_table, (unsigned)((nA + 255) / 256), 256, 0, s, (const u64 *)sa, nA, sh, nq, tbl.p);
+    else DN_LAUNCH(k_prefix_table_w, (unsigned)((nA + 255) / 256), 256, 0, s, (const ulonglong2 *)sw, nA, sh, nq, tbl.p);
     DBuf<int64_t> dtotal(1);
     DBuf<unsigned long long> ninv(1); ninv.zero(s);
     DBuf<ulonglong2> hits, hits2;
@@ -141,7 +154,8 @@ void align_blocks(const DevBlock &A, const DevBlock &B, const AlignParams &P, Ho
         const int64_t nwB = nB >> 4;
         const int nseg = 2 * B.nreads;
         DBuf<u32> kbits((1u << KBITS_LOG2) / 32); kbits.zero(s);
-        DN_LAUNCH(k_kmer_bitmap, (unsigned)((nA + 255) / 256), 256, 0, s, (const u64 *)sa, nA, kbits.p);
+        if (!wide) DN_LAUNCH(k_kmer_bitmap, (unsigned)((nA + 255) / 256), 256, 0, s, (const u64 *)sa, nA, kbits.p);
+        else DN_LAUNCH(k_kmer_bitmap_w, (unsigned)((nA + 255) / 256), 256, 0, s, (const ulonglong2 *)sw, nA, kbits.p);
         // pin the k-mer filter in the persisting part of L2 while the streaming lookups run
         {
             static bool limit_set = false;
@@ -159,9 +173,14 @@ void align_blocks(const DevBlock &A, const DevBlock &B, const AlignParams &P, Ho
             DBuf<u32> wcnt(2 * nwB); DBuf<int64_t> woff(2 * nwB); DBuf<unsigned short> hitmask(2 * nwB);
             for (int st = 0; st < 2; st++) {
                 const u32 *mb = B.has_mask ? (st ? B.mask_rc.p : B.mask.p) : nullptr;
-                DN_LAUNCH(k_lookup_count, (unsigned)((nwB + 255) / 256), 256, 0, s, (const u32 *)(st ? B.rc.p : B.fwd.p), mb,
-                          (const int64_t *)B.off.p, (const int32_t *)B.len.p, (const int32_t *)B.chunk2read.p, nwB, k,
-                          (const u64 *)sa, (const u32 *)tbl.p, sh, P.t, (const u32 *)kbits.p, JG, wcnt.p + st * nwB, hitmask.p + st * nwB);
+                if (!wide)
+                    DN_LAUNCH(k_lookup_count, (unsigned)((nwB + 255) / 256), 256, 0, s, (const u32 *)(st ? B.rc.p : B.fwd.p), mb,
+                              (const int64_t *)B.off.p, (const int32_t *)B.len.p, (const int32_t *)B.chunk2read.p, nwB, k,
+                              (const u64 *)sa, (const u32 *)tbl.p, sh, P.t, (const u32 *)kbits.p, JG, wcnt.p + st * nwB, hitmask.p + st * nwB);
+                else
+                    DN_LAUNCH(k_lookup_count_w, (unsigned)((nwB + 255) / 256), 256, 0, s, (const u32 *)(st ? B.rc.p : B.fwd.p), mb,
+                              (const int64_t *)B.off.p, (const int32_t *)B.len.p, (const int32_t *)B.chunk2read.p, nwB, k,
+                              (const ulonglong2 *)sw, (const u32 *)tbl.p, sh, P.t, (const u32 *)kbits.p, JG, wcnt.p + st * nwB, hitmask.p + st * nwB);
             }
             exclusive_scan_u32_to_i64(wcnt.p, woff.p, 2 * nwB, dtotal.p, s);
             H = d2h_scalar(dtotal.p, s);
@@ -170,10 +189,16 @@ void align_blocks(const DevBlock &A, const DevBlock &B, const AlignParams &P, Ho
             if (H > 0)
                 for (int st = 0; st < 2; st++) {
                     const u32 *mb = B.has_mask ? (st ? B.mask_rc.p : B.mask.p) : nullptr;
-                    DN_LAUNCH(k_lookup_emit, (unsigned)((nwB + 255) / 256), 256, 0, s, (const u32 *)(st ? B.rc.p : B.fwd.p), mb,
-                              (const int64_t *)B.off.p, (const int32_t *)B.len.p, (const int32_t *)B.chunk2read.p, nwB, k,
-                              (const u64 *)sa, (const u32 *)tbl.p, sh, P.t, (const unsigned short *)(hitmask.p + st * nwB), (const u32 *)(wcnt.p + st * nwB),
-                              (const int64_t *)(woff.p + st * nwB), st, JG, hits.p);
+                    if (!wide)
+                        DN_LAUNCH(k_lookup_emit, (unsigned)((nwB + 255) / 256), 256, 0, s, (const u32 *)(st ? B.rc.p : B.fwd.p), mb,
+                                  (const int64_t *)B.off.p, (const int32_t *)B.len.p, (const int32_t *)B.chunk2read.p, nwB, k,
+                                  (const u64 *)sa, (const u32 *)tbl.p, sh, P.t, (const unsigned short *)(hitmask.p + st * nwB), (const u32 *)(wcnt.p + st * nwB),
+                                  (const int64_t *)(woff.p + st * nwB), st, JG, hits.p);
+                    else
+                        DN_LAUNCH(k_lookup_emit_w, (unsigned)((nwB + 255) / 256), 256, 0, s, (const u32 *)(st ? B.rc.p : B.fwd.p), mb,
+                                  (const int64_t *)B.off.p, (const int32_t *)B.len.p, (const int32_t *)B.chunk2read.p, nwB, k,
+                                  (const ulonglong2 *)sw, (const u32 *)tbl.p, sh, P.t, (const unsigned short *)(hitmask.p + st * nwB), (const u32 *)(wcnt.p + st * nwB),
+                                  (const int64_t *)(woff.p + st * nwB), st, JG, hits.p);
                 }
             launch_seg_offsets(woff.p, B.off.p, B.nreads, nwB, H, seg_beg.p, seg_len.p, s);
             abytes += 2 * (nB / 4) * 2 + 2 * nwB * (4 + 4 + 8 + 8 + 4) + 16 * H;   // packed B read twice per strand, word counts/offsets, hits

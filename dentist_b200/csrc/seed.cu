@@ -226,18 +226,83 @@ void emit_tuples(const DevBlock &B, bool rc, int k, u32 payload_base, u64 *out, 
               (const int64_t *)B.off.p, (const int32_t *)B.len.p, (const int32_t *)B.chunk2read.p, nwords, k, payload_base, out);
 }
 
+// k = 16..31: the k-mer needs up to 62 bits, so an A tuple is 16 bytes {kmer, global position}; invalid positions get
+// kmer ~0 and sort last.  A k-mer starting at base jj <= 15 of the word ends before base 46: three packed words.
+__device__ __forceinline__ u64 wide_kmer(u64 v, u32 w2, int jj, u64 kmask) {
+    const u64 x = jj ? ((v >> (2 * jj)) | ((u64)w2 << (64 - 2 * jj))) : v;
+    return x & kmask;
+}
+
+__global__ void __launch_bounds__(256) k_tuples_wide(const u32 *__restrict__ seq, const u32 *__restrict__ maskbits,
+                                                     const int64_t *__restrict__ off, const int32_t *__restrict__ len,
+                                                     const int32_t *__restrict__ c2r, int64_t nwords, int k,
+                                                     ulonglong2 *__restrict__ out) {
+    int64_t wi = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (wi >= nwords) return;
+    const int64_t g0 = wi << 4;
+    int r = c2r[g0 >> 10];
+    while (off[r + 1] <= g0) r++;
+    const int p0 = (int)(g0 - off[r]);
+    const int L = len[r];
+    const u64 v = ((u64)seq[wi + 1] << 32) | seq[wi];
+    const u32 w2 = seq[wi + 2];
+    const u64 kmask = (1ull << (2 * k)) - 1ull, mk = (1ull << k) - 1ull;
+    u64 mwin = 0;
+    if (maskbits) { int64_t mw = g0 >> 5; mwin = (((u64)maskbits[mw + 1] << 32) | maskbits[mw]) >> (g0 & 31); }
+#pragma unroll
+    for (int jj = 0; jj < 16; jj++) {
+        const bool valid = (p0 + jj + k <= L) && (((mwin >> jj) & mk) == 0);
+        out[g0 + jj] = make_ulonglong2(valid ? wide_kmer(v, w2, jj, kmask) : ~0ull, (u64)(u32)(g0 + jj));
+    }
+}
+
+void emit_tuples_wide(const DevBlock &B, int k, ulonglong2 *out, cudaStream_t s) {
+    int64_t nwords = B.total >> 4;
+    if (nwords == 0) return;
+    DN_LAUNCH(k_tuples_wide, (unsigned)((nwords + 255) / 256), 256, 0, s, (const u32 *)B.fwd.p, B.has_mask ? (const u32 *)B.mask.p : nullptr,
+              (const int64_t *)B.off.p, (const int32_t *)B.len.p, (const int32_t *)B.chunk2read.p, nwords, k, out);
+}
+
 // ------------------------------------------------------------------------- K3: join
 
+// The sorted A index behind one interface: 8-byte tuples (kmer << 32 | position) for k <= 15, 16-byte tuples
+// {kmer, position} for k = 16..31.
+struct Idx32 {
+    const u64 *t;
+    typedef u32 key_t;
+    static constexpr bool wide = false;
+    __device__ __forceinline__ u32 key(int64_t i) const { return (u32)(t[i] >> 32); }
+    __device__ __forceinline__ u32 pos(int64_t i) const { return (u32)t[i]; }
+    __device__ __forceinline__ static bool invalid(u32 km) { return km == 0xffffffffu; }
+    __device__ __forceinline__ static u32 fold(u32 km) { return km; }
+};
+struct Idx64 {
+    const ulonglong2 *t;
+    typedef u64 key_t;
+    static constexpr bool wide = true;
+    __device__ __forceinline__ u64 key(int64_t i) const { return t[i].x; }
+    __device__ __forceinline__ u32 pos(int64_t i) const { return (u32)t[i].y; }
+    __device__ __forceinline__ static bool invalid(u64 km) { return km == ~0ull; }
+    __device__ __forceinline__ static u32 fold(u64 km) { return (u32)(km ^ (km >> 31)); }
+};
+
 // tbl[q] = first index i in the sorted A list with min(kmer_i >> sh, nq) >= q, q in [0, nq]
-__global__ void __launch_bounds__(256) k_prefix_table(const u64 *__restrict__ ta, int64_t na, int sh, u32 nq, u32 *__restrict__ tbl) {
+template <class IDX>
+__device__ __forceinline__ void prefix_table_body(IDX ta, int64_t na, int sh, u32 nq, u32 *__restrict__ tbl) {
     int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= na) return;
-    u32 q = (u32)(ta[i] >> 32) >> sh; if (q > nq) q = nq;
+    u64 q = (u64)ta.key(i) >> sh; if (q > nq) q = nq;
     int64_t qp;
     if (i == 0) qp = -1;
-    else { u32 t = (u32)(ta[i - 1] >> 32) >> sh; if (t > nq) t = nq; qp = t; }
+    else { u64 t = (u64)ta.key(i - 1) >> sh; if (t > nq) t = nq; qp = (int64_t)t; }
     for (int64_t x = qp + 1; x <= (int64_t)q; x++) tbl[x] = (u32)i;
     if (i == na - 1) for (int64_t x = (int64_t)q + 1; x <= (int64_t)nq; x++) tbl[x] = (u32)na;
+}
+__global__ void __launch_bounds__(256) k_prefix_table(const u64 *__restrict__ ta, int64_t na, int sh, u32 nq, u32 *__restrict__ tbl) {
+    prefix_table_body(Idx32{ta}, na, sh, nq, tbl);
+}
+__global__ void __launch_bounds__(256) k_prefix_table_w(const ulonglong2 *__restrict__ ta, int64_t na, int sh, u32 nq, u32 *__restrict__ tbl) {
+    prefix_table_body(Idx64{ta}, na, sh, nq, tbl);
 }
 
 __device__ __forceinline__ void a_range(const u64 *__restrict__ ta, const u32 *__restrict__ tbl, int sh, u32 km, u32 &s, u32 &e) {
@@ -324,22 +389,30 @@ __device__ __forceinline__ void kbit_slot(u32 km, u32 &word, u32 &mask) {
     mask = (1u << (h >> 27)) | (1u << ((h >> 22) & 31u)) | (1u << ((h >> 17) & 31u));
 }
 
-__global__ void __launch_bounds__(256) k_kmer_bitmap(const u64 *__restrict__ ta, int64_t na, u32 *__restrict__ bits) {
+template <class IDX>
+__device__ __forceinline__ void kmer_bitmap_body(IDX ta, int64_t na, u32 *__restrict__ bits) {
     int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= na) return;
-    const u32 km = (u32)(ta[i] >> 32);
-    if (km == 0xffffffffu) return;
-    if (i > 0 && (u32)(ta[i - 1] >> 32) == km) return;          // one atomic per distinct k-mer
-    u32 word, mask; kbit_slot(km, word, mask);
+    const typename IDX::key_t km = ta.key(i);
+    if (IDX::invalid(km)) return;
+    if (i > 0 && ta.key(i - 1) == km) return;                    // one atomic per distinct k-mer
+    u32 word, mask; kbit_slot(IDX::fold(km), word, mask);
     atomicOr(&bits[word], mask);
+}
+__global__ void __launch_bounds__(256) k_kmer_bitmap(const u64 *__restrict__ ta, int64_t na, u32 *__restrict__ bits) {
+    kmer_bitmap_body(Idx32{ta}, na, bits);
+}
+__global__ void __launch_bounds__(256) k_kmer_bitmap_w(const ulonglong2 *__restrict__ ta, int64_t na, u32 *__restrict__ bits) {
+    kmer_bitmap_body(Idx64{ta}, na, bits);
 }
 __device__ __forceinline__ bool kmer_present(const u32 *__restrict__ bits, u32 km) {
     u32 word, mask; kbit_slot(km, word, mask);
     return (bits[word] & mask) == mask;
 }
 
-struct WordKmers { u64 v; u64 mwin; int p0, L, r; };
+struct WordKmers { u64 v; u64 mwin; u32 w2; int p0, L, r; };
 
+template <bool WIDE>
 __device__ __forceinline__ WordKmers load_word(const u32 *__restrict__ seq, const u32 *__restrict__ maskbits,
                                                const int64_t *__restrict__ off, const int32_t *__restrict__ len,
                                                const int32_t *__restrict__ c2r, int64_t wi) {
@@ -349,47 +422,56 @@ __device__ __forceinline__ WordKmers load_word(const u32 *__restrict__ seq, cons
     while (off[r + 1] <= g0) r++;
     w.r = r; w.p0 = (int)(g0 - off[r]); w.L = len[r];
     w.v = ((u64)seq[wi + 1] << 32) | seq[wi];
+    w.w2 = WIDE ? seq[wi + 2] : 0u;
     w.mwin = 0;
     if (maskbits) { int64_t mw = g0 >> 5; w.mwin = (((u64)maskbits[mw + 1] << 32) | maskbits[mw]) >> (g0 & 31); }
     return w;
 }
 
-__device__ __forceinline__ void a_range_fwd(const u64 *__restrict__ ta, const u32 *__restrict__ tbl, int sh, u32 km, int tcap, u32 &s, u32 &c) {
-    u32 q = km >> sh;
-    u32 a = tbl[q], hi = tbl[q + 1], b = hi;
-    while (a < b) { u32 m = (a + b) >> 1; if ((u32)(ta[m] >> 32) < km) a = m + 1; else b = m; }
-    s = a; c = 0;
-    while (a < hi && (u32)(ta[a] >> 32) == km) { a++; if (++c > (u32)tcap) { c = 0; break; } }
+template <class IDX>
+__device__ __forceinline__ typename IDX::key_t kmer_at(const WordKmers &w, int jj, u64 kmask) {
+    if (IDX::wide) return (typename IDX::key_t)wide_kmer(w.v, w.w2, jj, kmask);
+    return (typename IDX::key_t)((w.v >> (2 * jj)) & kmask);
 }
 
-__global__ void __launch_bounds__(256) k_lookup_count(const u32 *__restrict__ seq, const u32 *__restrict__ maskbits,
-                                                      const int64_t *__restrict__ off, const int32_t *__restrict__ len,
-                                                      const int32_t *__restrict__ c2r, int64_t nwords, int k,
-                                                      const u64 *__restrict__ ta, const u32 *__restrict__ tbl, int sh, int tcap,
-                                                      const u32 *__restrict__ kbits, JoinGeom G, u32 *__restrict__ wcnt,
-                                                      unsigned short *__restrict__ hitmask) {
+template <class IDX>
+__device__ __forceinline__ void a_range_fwd(IDX ta, const u32 *__restrict__ tbl, int sh, typename IDX::key_t km, int tcap, u32 &s, u32 &c) {
+    const u32 q = (u32)((u64)km >> sh);
+    u32 a = tbl[q], hi = tbl[q + 1], b = hi;
+    while (a < b) { u32 m = (a + b) >> 1; if (ta.key(m) < km) a = m + 1; else b = m; }
+    s = a; c = 0;
+    while (a < hi && ta.key(a) == km) { a++; if (++c > (u32)tcap) { c = 0; break; } }
+}
+
+template <class IDX>
+__device__ __forceinline__ void lookup_count_body(const u32 *__restrict__ seq, const u32 *__restrict__ maskbits,
+                                                  const int64_t *__restrict__ off, const int32_t *__restrict__ len,
+                                                  const int32_t *__restrict__ c2r, int64_t nwords, int k,
+                                                  IDX ta, const u32 *__restrict__ tbl, int sh, int tcap,
+                                                  const u32 *__restrict__ kbits, const JoinGeom &G, u32 *__restrict__ wcnt,
+                                                  unsigned short *__restrict__ hitmask) {
     int64_t wi = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (wi >= nwords) return;
-    const WordKmers w = load_word(seq, maskbits, off, len, c2r, wi);
+    const WordKmers w = load_word<IDX::wide>(seq, maskbits, off, len, c2r, wi);
     const u64 kmask = (1ull << (2 * k)) - 1ull, mk = (1ull << k) - 1ull;
     const bool restricted = G.self || G.a_group;
     u32 total = 0;
     u32 present = 0;                                  // 16 independent bitmap probes first (memory-level parallelism)
 #pragma unroll
     for (int jj = 0; jj < 16; jj++)
-        if ((w.p0 + jj + k <= w.L) && (((w.mwin >> jj) & mk) == 0) && kmer_present(kbits, (u32)((w.v >> (2 * jj)) & kmask)))
+        if ((w.p0 + jj + k <= w.L) && (((w.mwin >> jj) & mk) == 0) && kmer_present(kbits, IDX::fold(kmer_at<IDX>(w, jj, kmask))))
             present |= 1u << jj;
     u32 hm = 0;                                       // positions that really produce hits: the emit pass skips the filter
     while (present) {
         const int jj = __ffs(present) - 1; present &= present - 1;
         {
-            const u32 km = (u32)((w.v >> (2 * jj)) & kmask);
+            const typename IDX::key_t km = kmer_at<IDX>(w, jj, kmask);
             u32 s, c; a_range_fwd(ta, tbl, sh, km, tcap, s, c);
             u32 add = c;
             if (restricted) {                     // self pairs / pairs across pile-ups are never emitted
                 add = 0;
                 for (u32 x = 0; x < c; x++) {
-                    const int ar = read_of(G.a_c2r, G.a_off, (int64_t)(u32)ta[s + x]);
+                    const int ar = read_of(G.a_c2r, G.a_off, (int64_t)ta.pos(s + x));
                     add += pair_ok(G, ar, w.r) ? 1u : 0u;
                 }
             }
@@ -401,29 +483,46 @@ __global__ void __launch_bounds__(256) k_lookup_count(const u32 *__restrict__ se
     hitmask[wi] = (unsigned short)hm;
 }
 
-__global__ void __launch_bounds__(256) k_lookup_emit(const u32 *__restrict__ seq, const u32 *__restrict__ maskbits,
-                                                     const int64_t *__restrict__ off, const int32_t *__restrict__ len,
-                                                     const int32_t *__restrict__ c2r, int64_t nwords, int k,
-                                                     const u64 *__restrict__ ta, const u32 *__restrict__ tbl, int sh, int tcap,
-                                                     const unsigned short *__restrict__ hitmask, const u32 *__restrict__ wcnt,
-                                                     const int64_t *__restrict__ woff, int strand,
-                                                     JoinGeom G, ulonglong2 *__restrict__ hits) {
+__global__ void __launch_bounds__(256) k_lookup_count(const u32 *__restrict__ seq, const u32 *__restrict__ maskbits,
+                                                      const int64_t *__restrict__ off, const int32_t *__restrict__ len,
+                                                      const int32_t *__restrict__ c2r, int64_t nwords, int k,
+                                                      const u64 *__restrict__ ta, const u32 *__restrict__ tbl, int sh, int tcap,
+                                                      const u32 *__restrict__ kbits, JoinGeom G, u32 *__restrict__ wcnt,
+                                                      unsigned short *__restrict__ hitmask) {
+    lookup_count_body(seq, maskbits, off, len, c2r, nwords, k, Idx32{ta}, tbl, sh, tcap, kbits, G, wcnt, hitmask);
+}
+__global__ void __launch_bounds__(256) k_lookup_count_w(const u32 *__restrict__ seq, const u32 *__restrict__ maskbits,
+                                                        const int64_t *__restrict__ off, const int32_t *__restrict__ len,
+                                                        const int32_t *__restrict__ c2r, int64_t nwords, int k,
+                                                        const ulonglong2 *__restrict__ ta, const u32 *__restrict__ tbl, int sh, int tcap,
+                                                        const u32 *__restrict__ kbits, JoinGeom G, u32 *__restrict__ wcnt,
+                                                        unsigned short *__restrict__ hitmask) {
+    lookup_count_body(seq, maskbits, off, len, c2r, nwords, k, Idx64{ta}, tbl, sh, tcap, kbits, G, wcnt, hitmask);
+}
+
+template <class IDX>
+__device__ __forceinline__ void lookup_emit_body(const u32 *__restrict__ seq, const u32 *__restrict__ maskbits,
+                                                 const int64_t *__restrict__ off, const int32_t *__restrict__ len,
+                                                 const int32_t *__restrict__ c2r, int64_t nwords, int k,
+                                                 IDX ta, const u32 *__restrict__ tbl, int sh, int tcap,
+                                                 const unsigned short *__restrict__ hitmask, const u32 *__restrict__ wcnt,
+                                                 const int64_t *__restrict__ woff, int strand,
+                                                 const JoinGeom &G, ulonglong2 *__restrict__ hits) {
     int64_t wi = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (wi >= nwords) return;
     if (__ldcs(wcnt + wi) == 0) return;                  // streamed once: keep it out of the way of the A index in L2
-    const WordKmers w = load_word(seq, maskbits, off, len, c2r, wi);
-    const u64 kmask = (1ull << (2 * k)) - 1ull, mk = (1ull << k) - 1ull;
+    const WordKmers w = load_word<IDX::wide>(seq, maskbits, off, len, c2r, wi);
+    const u64 kmask = (1ull << (2 * k)) - 1ull;
     const u64 bs = (u64)strand * G.nb_reads + w.r;
     int64_t o = __ldcs((const long long *)woff + wi);
     u32 present = hitmask[wi];                        // from the count pass: no filter probes, no fruitless lookups
-    (void)mk;
     while (present) {                                 // ascending jj: hits of a word stay ordered by bpos
         const int jj = __ffs(present) - 1; present &= present - 1;
-        const u32 km = (u32)((w.v >> (2 * jj)) & kmask);
+        const typename IDX::key_t km = kmer_at<IDX>(w, jj, kmask);
         u32 s, c; a_range_fwd(ta, tbl, sh, km, tcap, s, c);
         const int bpos = w.p0 + jj;
         for (u32 x = 0; x < c; x++) {
-            int64_t ga = (int64_t)(u32)ta[s + x];
+            int64_t ga = (int64_t)ta.pos(s + x);
             int ar = read_of(G.a_c2r, G.a_off, ga);
             int apos = (int)(ga - G.a_off[ar]);
             if (!pair_ok(G, ar, w.r)) continue;
@@ -432,6 +531,25 @@ __global__ void __launch_bounds__(256) k_lookup_emit(const u32 *__restrict__ seq
             o++;
         }
     }
+}
+
+__global__ void __launch_bounds__(256) k_lookup_emit(const u32 *__restrict__ seq, const u32 *__restrict__ maskbits,
+                                                     const int64_t *__restrict__ off, const int32_t *__restrict__ len,
+                                                     const int32_t *__restrict__ c2r, int64_t nwords, int k,
+                                                     const u64 *__restrict__ ta, const u32 *__restrict__ tbl, int sh, int tcap,
+                                                     const unsigned short *__restrict__ hitmask, const u32 *__restrict__ wcnt,
+                                                     const int64_t *__restrict__ woff, int strand,
+                                                     JoinGeom G, ulonglong2 *__restrict__ hits) {
+    lookup_emit_body(seq, maskbits, off, len, c2r, nwords, k, Idx32{ta}, tbl, sh, tcap, hitmask, wcnt, woff, strand, G, hits);
+}
+__global__ void __launch_bounds__(256) k_lookup_emit_w(const u32 *__restrict__ seq, const u32 *__restrict__ maskbits,
+                                                       const int64_t *__restrict__ off, const int32_t *__restrict__ len,
+                                                       const int32_t *__restrict__ c2r, int64_t nwords, int k,
+                                                       const ulonglong2 *__restrict__ ta, const u32 *__restrict__ tbl, int sh, int tcap,
+                                                       const unsigned short *__restrict__ hitmask, const u32 *__restrict__ wcnt,
+                                                       const int64_t *__restrict__ woff, int strand,
+                                                       JoinGeom G, ulonglong2 *__restrict__ hits) {
+    lookup_emit_body(seq, maskbits, off, len, c2r, nwords, k, Idx64{ta}, tbl, sh, tcap, hitmask, wcnt, woff, strand, G, hits);
 }
 
 // ------------------------------------------------------------------------- K4: band filter

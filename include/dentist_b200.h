@@ -84,7 +84,7 @@ typedef struct dn_block_desc {
  * (pileUpAlignmentOptions commandline.d:2886-2902, postConsensusAlignmentOptions :2918-2935,
  * refVsReadsAlignmentOptions :2943-2955) plus the tool defaults DENTIST leaves alone. */
 typedef struct dn_align_params {
-    int32_t k;          /* -k  k-mer length (<= 15)                    default 14  */
+    int32_t k;          /* -k  k-mer length (4..31; > 15 uses 16-byte tuples) default 14  */
     int32_t w;          /* -w  log2 of the diagonal band width         default 6   */
     int32_t h;          /* -h  bases covered by k-mer hits in a band   default 35  */
     int32_t t;          /* -t  ignore k-mers occurring more often in A default 32  */

@@ -50,7 +50,7 @@
 #include <stdio.h>
 
 typedef struct {
-    int32_t k;        /* k-mer length (<= 16)                       */
+    int32_t k;        /* k-mer length (<= 31)                       */
     int32_t w;        /* log2 band width                             */
     int32_t h;        /* min covered bases in a band pair            */
     int32_t t;        /* max k-mer multiplicity in A                 */
@@ -89,7 +89,7 @@ typedef struct {
 
 /* ---------------------------------------------------------------- helpers */
 
-typedef struct { uint32_t kmer; int32_t read; int32_t pos; int32_t strand; } tup_t;
+typedef struct { uint64_t kmer; int32_t read; int32_t pos; int32_t strand; } tup_t;
 typedef struct { int32_t bs; int32_t a; int32_t diag; int32_t apos; int32_t bpos; int32_t free_; } hit_t;
 
 static int cmp_tup(const void *x, const void *y) {
@@ -131,7 +131,7 @@ static int64_t emit_tuples(const orc_block *B, const uint8_t *seq, int strand, i
     for (int r = 0; r < B->nreads; r++) {
         int64_t o = B->off[r]; int len = (int)(B->off[r + 1] - o);
         for (int p = 0; p + k <= len; p++) {
-            uint32_t km = 0; int ok = 1;
+            uint64_t km = 0; int ok = 1;
             for (int i = 0; i < k; i++) {
                 km = (km << 2) | seq[o + p + i];
                 if (B->mask) {
@@ -308,7 +308,7 @@ int orc_align(const orc_block *A, const orc_block *B, const orc_params *P, orc_r
     for (int64_t ia = 0, ib = 0; ia < nta && ib < ntb;) {
         if (TA[ia].kmer < TB[ib].kmer) { ia++; continue; }
         if (TA[ia].kmer > TB[ib].kmer) { ib++; continue; }
-        int64_t ea = ia, eb = ib; uint32_t km = TA[ia].kmer;
+        int64_t ea = ia, eb = ib; uint64_t km = TA[ia].kmer;
         while (ea < nta && TA[ea].kmer == km) ea++;
         while (eb < ntb && TB[eb].kmer == km) eb++;
         if (ea - ia <= P->t) {

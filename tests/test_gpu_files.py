@@ -27,7 +27,7 @@ def test_getDamapping_writes_both_las_files(tmp_path):
     ts, rec, traces = las.decode(open(out, "rb").read())
     assert ts == 100 and len(rec) > 20
     ga, gb = dazzler.Block(ref.off, ref.bases), dazzler.Block(reads.off, reads.bases)
-    mrec, mtoff, mtr, _ = dazzler.align_blocks(ga, gb, tspace=100, minlen=500)
+    mrec, mtoff, mtr, _ = dazzler.align_blocks(ga, gb, tspace=100, minlen=500, k=20)     # damapper's default k
     for f in ("aread", "bread", "abpos", "aepos", "bbpos", "bepos", "diffs", "tlen"):
         assert np.array_equal(rec[f], mrec[f]), f
     assert np.concatenate([t.reshape(-1) for t in traces]).tolist() == np.minimum(mtr, 255).tolist()

@@ -84,6 +84,25 @@ def test_window_cap_variants_match_oracle(wmax, xdrop):
     assert_same(orc, gpu)
 
 
+@pytest.mark.parametrize("k", [16, 20, 31])
+def test_long_kmers_use_the_wide_index_and_match_oracle(k):
+    """k > 15 (damapper's default is 20): 16-byte {kmer, position} tuples, 3-word k-mer extraction, same results as the
+    oracle -- with and without seed masks, for a reference mapping and for a pile self-alignment."""
+    ref, reads = small_case(41 + k, cov=4, err=0.08)
+    orc, gpu = run_both(ref, reads, 100, 500, k=k)
+    assert len(orc[0]) > (5 if k == 31 else 40)
+    assert_same(orc, gpu)
+    amask = [[(0, int(ref.off[r + 1] - ref.off[r]) // 3)] for r in range(ref.nreads)]
+    bmask = [[(37, 911)] for _ in range(reads.nreads)]
+    orc_m, gpu_m = run_both(ref, reads, 100, 500, a_mask=amask, b_mask=bmask, k=k)
+    assert_same(orc_m, gpu_m)
+    assert orc_m[2]["nhits"] < orc[2]["nhits"]
+    sc = synth.make_scaffolds(1, 20000, 43, n_repeats=0)
+    pile, _ = synth.simulate_reads(sc, 8, 6000, 1500, 0.08, 44)
+    orc, gpu = run_both(pile, pile, 126, 500, self_block=1, k=k)
+    assert_same(orc, gpu)
+
+
 def test_pile_self_alignment_matches_oracle():
     # processPileUps: daligner -s126 -l500 -e0.7 X X  (commandline.d:2886-2902)
     sc = synth.make_scaffolds(1, 25000, 21, n_repeats=0)

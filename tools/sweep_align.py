@@ -13,6 +13,7 @@ def main():
     ap.add_argument("--ref-mbp", type=float, default=50); ap.add_argument("--reads-mbp", type=float, default=50)
     ap.add_argument("--out", default="gpurun_out/sweep_align.jsonl"); ap.add_argument("--cpu", action="store_true")
     ap.add_argument("--lens", default="1000,2000,5000,10000,20000,50000,100000"); ap.add_argument("--errors", default="0.05,0.10,0.15")
+    ap.add_argument("--k", type=int, default=20, help="k-mer length (damapper default 20)")
     ap.add_argument("--ont", action="store_true", help="ONT-like error mix and a log-normal length spread (configs[2] reads)")
     a = ap.parse_args()
     dazzler.init(0)
@@ -30,12 +31,12 @@ def main():
             gb = dazzler.Block(reads.off, reads.bases)
             minlen = min(1000, L // 2)
             for _ in range(2):
-                dazzler.align_blocks(ga, gb, tspace=100, minlen=minlen)
+                dazzler.align_blocks(ga, gb, tspace=100, minlen=minlen, k=a.k)
             ms, al = 0.0, 0
             for _ in range(3):
-                rec, _, _, st = dazzler.align_blocks(ga, gb, tspace=100, minlen=minlen)
+                rec, _, _, st = dazzler.align_blocks(ga, gb, tspace=100, minlen=minlen, k=a.k)
                 ms += st["ms_total"]; al += st["aligned_bases"]
-            row = dict(read_len=L, error=e, ref_bp=int(ref.total), reads_bp=int(reads.total), reads=int(reads.nreads), las=int(len(rec)),
+            row = dict(k=a.k, read_len=L, error=e, ref_bp=int(ref.total), reads_bp=int(reads.total), reads=int(reads.nreads), las=int(len(rec)),
                        ms_per_step=ms / 3, gbp_aligned_per_s=al / 1e9 / (ms / 1e3), input_gbp_per_s=3 * reads.total / 1e9 / (ms / 1e3),
                        hits=int(st["hits"]), seeds=int(st["seeds"]))
             if a.cpu:
@@ -43,7 +44,7 @@ def main():
                 nr = max(1, int(np.searchsorted(reads.off, 300000)))
                 sub = synth.Block(sc and np.array([0, len(sc[0])], np.int64), sc[0])
                 t0 = time.perf_counter()
-                la, _, _ = oracle.align(sub.off, sub.bases, reads.off[:nr + 1], reads.bases[:reads.off[nr]], tspace=100, minlen=minlen)
+                la, _, _ = oracle.align(sub.off, sub.bases, reads.off[:nr + 1], reads.bases[:reads.off[nr]], tspace=100, minlen=minlen, k=a.k)
                 dt = time.perf_counter() - t0
                 row["cpu_port_gbp_aligned_per_s_1core"] = float((la["aepos"] - la["abpos"]).sum()) / 1e9 / dt
                 row["cpu_sample"] = "first %d reads vs scaffold 0 (1 Mbp)" % nr
