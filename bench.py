@@ -306,6 +306,23 @@ def main():
     dev_ms_max, wall_ms_max = float(tmax[0]), float(tmax[1])
     value = float(units[0]) / 1e9 / (dev_ms_max / 1e3)
 
+    # ---- extra (not the headline): the reference index kept resident across read blocks (dn_block_index), as a
+    # multi-block job would run it -- the per-step A-side tuple build + sort + table + filter leave the step
+    resident = None
+    if not args.profile:
+        ga.index(PARAMS["k"])
+        rms = 0.0; ral = 0
+        for it in range(2 + args.steps):
+            _, _, _, st = dazzler.align_blocks(ga, gb, **PARAMS)
+            if it >= 2:
+                rms += st["ms_total"]; ral += st["aligned_bases"]
+        ga.index(0)
+        rt = torch.tensor([rms], dtype=torch.float64, device=dev); ru = torch.tensor([float(ral)], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(rt, op=dist.ReduceOp.MAX); dist.all_reduce(ru, op=dist.ReduceOp.SUM)
+        resident = {"value": float(ru[0]) / 1e9 / (float(rt[0]) / 1e3), "unit": "Gbp/s", "ms_per_step": float(rt[0]) / args.steps,
+                    "note": "same steps with the assembly's k-mer index built once (dn_block_index) instead of per step; identical output"}
+
     # ---- end-to-end arm (`e2e`): host buffers in, host LAS out, merged across ranks -------------
     e2e_t = 0.0; e2e_units = 0; h2d = d2h = 0
     for it in range(0 if args.profile else 1 + args.steps):
@@ -392,6 +409,8 @@ def main():
         out["cpu_baseline"] = {"value": a / 1e9 / dt, "unit": "Gbp/s", "cores": cores, "kind": kind, "sample": sample}
         if cons is not None:
             out["consensus"] = cons
+        if resident is not None:
+            out["resident_reference_index"] = resident
         emit(out)
     if world > 1:
         dist.barrier(); dist.destroy_process_group()

@@ -15,7 +15,7 @@ EXPORTS = [
     "dn_init", "dn_shutdown", "dn_last_error", "dn_version", "dn_launch_count",
     "dn_align_params_default", "dn_las_free", "dn_block_upload", "dn_block_free", "dn_block_bases",
     "dn_align_blocks", "dn_align_host", "dn_las_write", "dn_las_read", "dn_dalign", "dn_damap",
-    "dn_las_filter_error", "dn_las_filter_pileup", "dn_compute_qvs", "dn_compute_qvs_v", "dn_dust_block", "dn_block_mask_dust", "dn_mask_coverage", "dn_propagate_mask", "dn_dbdust", "dn_las_chain_mapper", "dn_las_chain", "dn_las_merge_device", "dn_block_crop", "dn_consensus_db", "dn_collect_filter", "dn_las_force_flat", "dn_reference_read_candidates", "dn_free", "dn_consensus", "dn_seq_free",
+    "dn_las_filter_error", "dn_las_filter_pileup", "dn_compute_qvs", "dn_compute_qvs_v", "dn_dust_block", "dn_block_mask_dust", "dn_block_index", "dn_mask_coverage", "dn_propagate_mask", "dn_dbdust", "dn_las_chain_mapper", "dn_las_chain", "dn_las_merge_device", "dn_block_crop", "dn_consensus_db", "dn_collect_filter", "dn_las_force_flat", "dn_reference_read_candidates", "dn_free", "dn_consensus", "dn_seq_free",
 ]
 
 
@@ -101,6 +101,7 @@ def lib():
         L.dn_dust_block.argtypes = [C.c_void_p, C.c_int32, C.c_double, C.c_int32, C.c_void_p, C.c_void_p]
         L.dn_mask_coverage.argtypes = [C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p, C.c_int32, C.c_double, C.c_double, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p]
         L.dn_propagate_mask.argtypes = [C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p]
+        L.dn_block_index.argtypes = [C.c_void_p, C.c_int32]
         L.dn_block_mask_dust.argtypes = [C.c_void_p, C.c_int32, C.c_double, C.c_int32, C.c_void_p]
         L.dn_free.argtypes = [C.c_void_p]
         L.dn_consensus.argtypes = [C.c_void_p, C.POINTER(LasBuf), C.c_void_p, C.c_int32, C.c_void_p]

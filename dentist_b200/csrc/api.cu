@@ -123,6 +123,18 @@ void dn_block_free(dn_block *blk) {
 }
 int64_t dn_block_bases(const dn_block *blk) { return blk ? blk->b.total_real : 0; }
 
+int dn_block_index(dn_block *blk, int32_t k) {
+    if (!blk) return fail(DN_ERR_INVALID, "null argument");
+    std::lock_guard<std::mutex> lk(g_mu);
+    if (int rc = ensure_device()) return rc;
+    return guarded([&] {
+        cudaSetDevice(g_device); arena().reset();
+        if (k <= 0) blk->b.index.drop();
+        else block_build_index(blk->b, k, g_stream);
+        return DN_OK;
+    });
+}
+
 int dn_align_blocks(const dn_block *a, const dn_block *b, const dn_align_params *p, dn_las_buf *out) {
     if (!a || !b || !out) return fail(DN_ERR_INVALID, "null argument");
     std::lock_guard<std::mutex> lk(g_mu);

@@ -77,6 +77,50 @@ void hcache_free(void *p) {
     if (h->pinned) cudaFreeHost(h); else free(h);
 }
 
+static int index_tbits(int64_t nA, int k, bool lookup) {
+    int tbits = bits_for((uint64_t)nA) + (lookup ? -1 : 1);
+    if (tbits < 16) tbits = 16;
+    if (tbits > 2 * k) tbits = 2 * k;
+    return tbits;
+}
+
+// dn_block_index: the A-side index of align_blocks (sorted k-mer tuples, prefix table, k-mer filter) built once and kept
+// with the block -- a reference block is aligned against many read blocks (Snakefile:1143-1170 fan-out).
+void block_build_index(DevBlock &A, int k, cudaStream_t s) {
+    if (k < 4 || k > 31) throw Error("k must be in [4,31]");
+    A.index.drop();
+    const int64_t nA = A.total;
+    if (nA == 0) return;
+    const bool wide = k > 15;
+    DevBlock::Index &X = A.index;
+    if (!wide) {
+        DBuf<u64> ta(nA), ta2(nA);
+        emit_tuples(A, false, k, 0u, ta.p, s);
+        u64 *sa = radix_sort_u64(ta.p, ta2.p, nA, 32, 32 + 2 * k + 1, s);
+        X.ta.persistent(nA);
+        DN_CUDA(cudaMemcpyAsync(X.ta.p, sa, sizeof(u64) * nA, cudaMemcpyDeviceToDevice, s));
+    } else {
+        DBuf<ulonglong2> tw(nA), tw2(nA);
+        emit_tuples_wide(A, k, tw.p, s);
+        ulonglong2 *sw = radix_sort_rec16(tw.p, tw2.p, nA, 0, 0, 2 * k + 1, s);
+        X.tw.persistent(nA);
+        DN_CUDA(cudaMemcpyAsync(X.tw.p, sw, sizeof(ulonglong2) * nA, cudaMemcpyDeviceToDevice, s));
+    }
+    X.tbits = index_tbits(nA, k, true);
+    const int sh = 2 * k - X.tbits; const u32 nq = 1u << X.tbits;
+    X.tbl.persistent((size_t)nq + 2);
+    X.kbits.persistent((1u << KBITS_LOG2) / 32); X.kbits.zero(s);
+    if (!wide) {
+        DN_LAUNCH(k_prefix_table, (unsigned)((nA + 255) / 256), 256, 0, s, (const u64 *)X.ta.p, nA, sh, nq, X.tbl.p);
+        DN_LAUNCH(k_kmer_bitmap, (unsigned)((nA + 255) / 256), 256, 0, s, (const u64 *)X.ta.p, nA, X.kbits.p);
+    } else {
+        DN_LAUNCH(k_prefix_table_w, (unsigned)((nA + 255) / 256), 256, 0, s, (const ulonglong2 *)X.tw.p, nA, sh, nq, X.tbl.p);
+        DN_LAUNCH(k_kmer_bitmap_w, (unsigned)((nA + 255) / 256), 256, 0, s, (const ulonglong2 *)X.tw.p, nA, X.kbits.p);
+    }
+    DN_CUDA(cudaStreamSynchronize(s));
+    X.k = k; X.valid = true;
+}
+
 void align_blocks(const DevBlock &A, const DevBlock &B, const AlignParams &P, HostLas &out, cudaStream_t s) {
     out = HostLas();
     arena().reset();
@@ -102,7 +146,9 @@ void align_blocks(const DevBlock &A, const DevBlock &B, const AlignParams &P, Ho
     if (wide && P.join_mode == 1) throw Error("the sorted-merge join (join_mode 1) supports k <= 15 only");
     DBuf<u64> ta, ta2; DBuf<ulonglong2> tw, tw2;
     u64 *sa = nullptr; ulonglong2 *sw = nullptr;
-    if (!wide) {
+    const DevBlock::Index *cached = (A.index.valid && A.index.k == k && P.join_mode != 1) ? &A.index : nullptr;
+    if (cached) { sa = cached->ta.p; sw = cached->tw.p; }
+    else if (!wide) {
         ta.alloc(nA); ta2.alloc(nA);
         emit_tuples(A, false, k, 0u, ta.p, s);
         sa = radix_sort_u64(ta.p, ta2.p, nA, 32, 32 + 2 * k + 1, s);
@@ -114,7 +160,7 @@ void align_blocks(const DevBlock &A, const DevBlock &B, const AlignParams &P, Ho
         if (sw == tw.p) tw2.release(); else tw.release();
     }
     tr.mark("A tuples + sort");
-    const bool lookup = wide || P.join_mode == 2 || (P.join_mode == 0 && nA * 8 <= (2ll << 30));   // auto: index lookup unless the A index is huge
+    const bool lookup = cached || wide || P.join_mode == 2 || (P.join_mode == 0 && nA * 8 <= (2ll << 30));   // auto: index lookup unless the A index is huge
     const int npass_t = (2 * k + 1 + 7) / 8;
     out.stats.tuples_a = A.total_real; out.stats.tuples_b = 2 * B.total_real;
     int64_t abytes = nA / 4 + (wide ? 16 : 8) * nA + (int64_t)npass_t * (wide ? 48 : 24) * nA;      // A: read packed, write tuples, sort passes (2R+1W)
@@ -139,11 +185,17 @@ void align_blocks(const DevBlock &A, const DevBlock &B, const AlignParams &P, Ho
     const int aposbits = bits_for((uint64_t)A.maxlen);
     bool segsorted = false, seg_in_hits2 = false;
     // ---- K3: join ------------------------------------------------------------------------------
-    int tbits = bits_for((uint64_t)nA) + (lookup ? -1 : 1); if (tbits < 16) tbits = 16; if (tbits > 2 * k) tbits = 2 * k;
+    int tbits = index_tbits(nA, k, lookup);
+    if (cached) tbits = cached->tbits;
     const int sh = 2 * k - tbits; const u32 nq = 1u << tbits;
-    DBuf<u32> tbl((size_t)nq + 2);
-    if (!wide) DN_LAUNCH(k_prefix_table, (unsigned)((nA + 255) / 256), 256, 0, s, (const u64 *)sa, nA, sh, nq, tbl.p);
-    else DN_LAUNCH(k_prefix_table_w, (unsigned)((nA + 255) / 256), 256, 0, s, (const ulonglong2 *)sw, nA, sh, nq, tbl.p);
+    DBuf<u32> tbl_own; const u32 *tblp;
+    if (cached) tblp = cached->tbl.p;
+    else {
+        tbl_own.alloc((size_t)nq + 2); tblp = tbl_own.p;
+        if (!wide) DN_LAUNCH(k_prefix_table, (unsigned)((nA + 255) / 256), 256, 0, s, (const u64 *)sa, nA, sh, nq, tbl_own.p);
+        else DN_LAUNCH(k_prefix_table_w, (unsigned)((nA + 255) / 256), 256, 0, s, (const ulonglong2 *)sw, nA, sh, nq, tbl_own.p);
+    }
+    struct { const u32 *p; } tbl{tblp};
     DBuf<int64_t> dtotal(1);
     DBuf<unsigned long long> ninv(1); ninv.zero(s);
     DBuf<ulonglong2> hits, hits2;
@@ -153,15 +205,18 @@ void align_blocks(const DevBlock &A, const DevBlock &B, const AlignParams &P, Ho
         // B's tuples are never materialised: hits come straight from the packed sequence
         const int64_t nwB = nB >> 4;
         const int nseg = 2 * B.nreads;
-        DBuf<u32> kbits((1u << KBITS_LOG2) / 32); kbits.zero(s);
-        if (!wide) DN_LAUNCH(k_kmer_bitmap, (unsigned)((nA + 255) / 256), 256, 0, s, (const u64 *)sa, nA, kbits.p);
-        else DN_LAUNCH(k_kmer_bitmap_w, (unsigned)((nA + 255) / 256), 256, 0, s, (const ulonglong2 *)sw, nA, kbits.p);
+        DBuf<u32> kbits_own; struct { const u32 *p; } kbits{cached ? cached->kbits.p : nullptr};
+        if (!cached) {
+            kbits_own.alloc((1u << KBITS_LOG2) / 32); kbits_own.zero(s); kbits.p = kbits_own.p;
+            if (!wide) DN_LAUNCH(k_kmer_bitmap, (unsigned)((nA + 255) / 256), 256, 0, s, (const u64 *)sa, nA, kbits_own.p);
+            else DN_LAUNCH(k_kmer_bitmap_w, (unsigned)((nA + 255) / 256), 256, 0, s, (const ulonglong2 *)sw, nA, kbits_own.p);
+        }
         // pin the k-mer filter in the persisting part of L2 while the streaming lookups run
         {
             static bool limit_set = false;
             if (!limit_set) { cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, 48u << 20); cudaGetLastError(); limit_set = true; }
             cudaStreamAttrValue av; memset(&av, 0, sizeof av);
-            av.accessPolicyWindow.base_ptr = kbits.p; av.accessPolicyWindow.num_bytes = (size_t)(1u << KBITS_LOG2) / 8;
+            av.accessPolicyWindow.base_ptr = (void *)kbits.p; av.accessPolicyWindow.num_bytes = (size_t)(1u << KBITS_LOG2) / 8;
             av.accessPolicyWindow.hitRatio = 1.0f; av.accessPolicyWindow.hitProp = cudaAccessPropertyPersisting;
             av.accessPolicyWindow.missProp = cudaAccessPropertyStreaming;
             cudaStreamSetAttribute(s, cudaStreamAttributeAccessPolicyWindow, &av); cudaGetLastError();
@@ -275,7 +330,7 @@ void align_blocks(const DevBlock &A, const DevBlock &B, const AlignParams &P, Ho
     }
     const int64_t ninvalid = (int64_t)d2h_scalar(ninv.p, s);
     tr.mark("join");
-    ta.release(); ta2.release(); tbl.release();
+    ta.release(); ta2.release(); tw.release(); tw2.release(); tbl_own.release();
 
     // ---- hit sort: by apos, then stably by (bread, strand, aread, diagonal) -------------------
     ulonglong2 *hs = seg_in_hits2 ? hits2.p : hits.p, *ho = seg_in_hits2 ? hits.p : hits2.p;

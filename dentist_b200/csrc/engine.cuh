@@ -29,7 +29,16 @@ struct DevBlock {
     bool has_mask = false;
     DBuf<int32_t> group;          // optional pile id per read
     bool has_group = false;
+    // optional resident k-mer index (dn_block_index): the sorted tuple list, prefix table and k-mer filter that
+    // align_blocks otherwise rebuilds for the A block on every call.  Invalidated when the seed mask changes.
+    struct Index {
+        int k = 0, tbits = 0;
+        DBuf<u64> ta; DBuf<ulonglong2> tw; DBuf<u32> tbl, kbits;
+        bool valid = false;
+        void drop() { ta.release(); tw.release(); tbl.release(); kbits.release(); valid = false; k = 0; }
+    } index;
 };
+void block_build_index(DevBlock &A, int k, cudaStream_t s);
 
 struct AlignParams {
     int k = 14, w = 6, h = 35, t = 32, tspace = 100, minlen = 500, cdiff = 20, xdrop = 300, wmax = 30,

@@ -68,6 +68,7 @@ __global__ void k_mask_bits(const int64_t *__restrict__ anno, const int32_t *__r
 void block_add_mask(DevBlock &B, const int64_t *anno_h, const int32_t *data_h, cudaStream_t s) {
     const int64_t nbytes = anno_h[B.nreads];
     if (nbytes <= 0) return;
+    B.index.drop();                                        // masked k-mers leave the index: rebuild on demand
     if (!B.has_mask) {
         const size_t mw = (size_t)(B.total >> 5) + 4;
         B.mask.persistent(mw); B.mask_rc.persistent(mw); B.mask.zero(s); B.mask_rc.zero(s);

@@ -91,6 +91,11 @@ class Block:
         self.has_group = group is not None
         return self
 
+    def index(self, k):
+        """Build and keep the k-mer index of this block (dn_block_index): later alignments with this block as A and
+        the same k skip the index build.  k <= 0 drops it."""
+        _lib.check(_lib.lib().dn_block_index(self._h, int(k)))
+
     def maskDust(self, window=64, threshold=2.0, minlen=10):
         """dbdust(db) followed by `-mdust` (package.d:476-481): DUST intervals join the block's own seed mask on the
         device.  Returns the number of masked bases."""

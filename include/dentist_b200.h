@@ -132,6 +132,11 @@ int dn_block_crop(const dn_block *src, int32_t n, const int32_t *read, const int
                   dn_block **out);
 void dn_block_free(dn_block *blk);
 int64_t dn_block_bases(const dn_block *blk);
+/* Optional: build the k-mer index of a block once (sorted tuples, prefix table, k-mer filter) and keep it with the
+ * block; every later dn_align_blocks(blk, B, p) with p->k == k then skips the A-side index build -- one reference
+ * block is aligned against many read blocks (Snakefile:1143-1170).  Results are identical with and without it.
+ * k <= 0 drops the index; changing the block's seed mask (dn_block_mask_dust) drops it too. */
+int dn_block_index(dn_block *blk, int32_t k);
 
 /* All local alignments of block A vs block B (both strands of B).  What `daligner A B` computes
  * for DENTIST (dazzler.d:6131-6140); result = the records of A.B.las in LAsort order. */

@@ -103,6 +103,30 @@ def test_long_kmers_use_the_wide_index_and_match_oracle(k):
     assert_same(orc, gpu)
 
 
+@pytest.mark.parametrize("k", [14, 20])
+def test_resident_reference_index_gives_identical_results(k):
+    """dn_block_index: the A-side index built once and reused over several read blocks; dropped by a mask change."""
+    from dentist_b200 import dazzler
+    ref, reads = small_case(61, cov=4)
+    ga = dazzler.Block(ref.off, ref.bases)
+    half = reads.nreads // 2
+    blocks = [dazzler.Block(reads.off[:half + 1], reads.bases[:reads.off[half]]),
+              dazzler.Block(reads.off[half:] - reads.off[half], reads.bases[reads.off[half]:])]
+    plain = [dazzler.align_blocks(ga, gb, tspace=100, minlen=500, k=k) for gb in blocks]
+    ga.index(k)
+    for gb, want in zip(blocks, plain):
+        for _ in range(2):
+            got = dazzler.align_blocks(ga, gb, tspace=100, minlen=500, k=k)
+            assert got[0].tobytes() == want[0].tobytes() and got[2].tobytes() == want[2].tobytes() and len(got[0]) > 20
+    other = dazzler.align_blocks(ga, blocks[0], tspace=100, minlen=500, k=k + 1)         # another k: the index is ignored
+    assert len(other[0]) > 20
+    assert ga.maskDust(threshold=0.5) > 0                                                # a new mask drops the index
+    masked = dazzler.align_blocks(ga, blocks[0], tspace=100, minlen=500, k=k)
+    gm = dazzler.Block(ref.off, ref.bases); gm.maskDust(threshold=0.5)
+    want = dazzler.align_blocks(gm, blocks[0], tspace=100, minlen=500, k=k)
+    assert masked[0].tobytes() == want[0].tobytes() and masked[3]["hits"] < plain[0][3]["hits"]
+
+
 def test_pile_self_alignment_matches_oracle():
     # processPileUps: daligner -s126 -l500 -e0.7 X X  (commandline.d:2886-2902)
     sc = synth.make_scaffolds(1, 25000, 21, n_repeats=0)
