@@ -450,10 +450,11 @@ __device__ __forceinline__ void lookup_count_body(const u32 *__restrict__ seq, c
                                                   const int32_t *__restrict__ c2r, int64_t nwords, int k,
                                                   IDX ta, const u32 *__restrict__ tbl, int sh, int tcap,
                                                   const u32 *__restrict__ kbits, const JoinGeom &G, u32 *__restrict__ wcnt,
-                                                  unsigned short *__restrict__ hitmask) {
+                                                  unsigned short *__restrict__ hitmask, u32 *__restrict__ wstart) {
     int64_t wi = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (wi >= nwords) return;
     const WordKmers w = load_word<IDX::wide>(seq, maskbits, off, len, c2r, wi);
+    u32 s0 = 0;                                       // index range start of the first position with hits: the emit pass starts there
     const u64 kmask = (1ull << (2 * k)) - 1ull, mk = (1ull << k) - 1ull;
     const bool restricted = G.self || G.a_group;
     u32 total = 0;
@@ -477,11 +478,12 @@ __device__ __forceinline__ void lookup_count_body(const u32 *__restrict__ seq, c
                 }
             }
             total += add;
-            if (add) hm |= 1u << jj;
+            if (add) { if (!hm) s0 = s; hm |= 1u << jj; }
         }
     }
     __stcs(wcnt + wi, total);
     hitmask[wi] = (unsigned short)hm;
+    if (hm) __stcs(wstart + wi, s0);
 }
 
 __global__ void __launch_bounds__(256) k_lookup_count(const u32 *__restrict__ seq, const u32 *__restrict__ maskbits,
@@ -489,16 +491,16 @@ __global__ void __launch_bounds__(256) k_lookup_count(const u32 *__restrict__ se
                                                       const int32_t *__restrict__ c2r, int64_t nwords, int k,
                                                       const u64 *__restrict__ ta, const u32 *__restrict__ tbl, int sh, int tcap,
                                                       const u32 *__restrict__ kbits, JoinGeom G, u32 *__restrict__ wcnt,
-                                                      unsigned short *__restrict__ hitmask) {
-    lookup_count_body(seq, maskbits, off, len, c2r, nwords, k, Idx32{ta}, tbl, sh, tcap, kbits, G, wcnt, hitmask);
+                                                      unsigned short *__restrict__ hitmask, u32 *__restrict__ wstart) {
+    lookup_count_body(seq, maskbits, off, len, c2r, nwords, k, Idx32{ta}, tbl, sh, tcap, kbits, G, wcnt, hitmask, wstart);
 }
 __global__ void __launch_bounds__(256) k_lookup_count_w(const u32 *__restrict__ seq, const u32 *__restrict__ maskbits,
                                                         const int64_t *__restrict__ off, const int32_t *__restrict__ len,
                                                         const int32_t *__restrict__ c2r, int64_t nwords, int k,
                                                         const ulonglong2 *__restrict__ ta, const u32 *__restrict__ tbl, int sh, int tcap,
                                                         const u32 *__restrict__ kbits, JoinGeom G, u32 *__restrict__ wcnt,
-                                                        unsigned short *__restrict__ hitmask) {
-    lookup_count_body(seq, maskbits, off, len, c2r, nwords, k, Idx64{ta}, tbl, sh, tcap, kbits, G, wcnt, hitmask);
+                                                        unsigned short *__restrict__ hitmask, u32 *__restrict__ wstart) {
+    lookup_count_body(seq, maskbits, off, len, c2r, nwords, k, Idx64{ta}, tbl, sh, tcap, kbits, G, wcnt, hitmask, wstart);
 }
 
 template <class IDX>
@@ -507,7 +509,7 @@ __device__ __forceinline__ void lookup_emit_body(const u32 *__restrict__ seq, co
                                                  const int32_t *__restrict__ c2r, int64_t nwords, int k,
                                                  IDX ta, const u32 *__restrict__ tbl, int sh, int tcap,
                                                  const unsigned short *__restrict__ hitmask, const u32 *__restrict__ wcnt,
-                                                 const int64_t *__restrict__ woff, int strand,
+                                                 const int64_t *__restrict__ woff, const u32 *__restrict__ wstart, u32 na, int strand,
                                                  const JoinGeom &G, ulonglong2 *__restrict__ hits) {
     int64_t wi = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (wi >= nwords) return;
@@ -517,10 +519,15 @@ __device__ __forceinline__ void lookup_emit_body(const u32 *__restrict__ seq, co
     const u64 bs = (u64)strand * G.nb_reads + w.r;
     int64_t o = __ldcs((const long long *)woff + wi);
     u32 present = hitmask[wi];                        // from the count pass: no filter probes, no fruitless lookups
+    bool first = true;
     while (present) {                                 // ascending jj: hits of a word stay ordered by bpos
         const int jj = __ffs(present) - 1; present &= present - 1;
         const typename IDX::key_t km = kmer_at<IDX>(w, jj, kmask);
-        u32 s, c; a_range_fwd(ta, tbl, sh, km, tcap, s, c);
+        u32 s, c;
+        if (first) {                                  // the count pass left this position's range start: no table, no search
+            s = __ldcs(wstart + wi); c = 0; first = false;
+            for (u32 a = s; a < na && ta.key(a) == km; a++) c++;      // <= tcap entries (a longer run was dropped by the count pass)
+        } else a_range_fwd(ta, tbl, sh, km, tcap, s, c);
         const int bpos = w.p0 + jj;
         for (u32 x = 0; x < c; x++) {
             int64_t ga = (int64_t)ta.pos(s + x);
@@ -539,18 +546,18 @@ __global__ void __launch_bounds__(256) k_lookup_emit(const u32 *__restrict__ seq
                                                      const int32_t *__restrict__ c2r, int64_t nwords, int k,
                                                      const u64 *__restrict__ ta, const u32 *__restrict__ tbl, int sh, int tcap,
                                                      const unsigned short *__restrict__ hitmask, const u32 *__restrict__ wcnt,
-                                                     const int64_t *__restrict__ woff, int strand,
+                                                     const int64_t *__restrict__ woff, const u32 *__restrict__ wstart, u32 na, int strand,
                                                      JoinGeom G, ulonglong2 *__restrict__ hits) {
-    lookup_emit_body(seq, maskbits, off, len, c2r, nwords, k, Idx32{ta}, tbl, sh, tcap, hitmask, wcnt, woff, strand, G, hits);
+    lookup_emit_body(seq, maskbits, off, len, c2r, nwords, k, Idx32{ta}, tbl, sh, tcap, hitmask, wcnt, woff, wstart, na, strand, G, hits);
 }
 __global__ void __launch_bounds__(256) k_lookup_emit_w(const u32 *__restrict__ seq, const u32 *__restrict__ maskbits,
                                                        const int64_t *__restrict__ off, const int32_t *__restrict__ len,
                                                        const int32_t *__restrict__ c2r, int64_t nwords, int k,
                                                        const ulonglong2 *__restrict__ ta, const u32 *__restrict__ tbl, int sh, int tcap,
                                                        const unsigned short *__restrict__ hitmask, const u32 *__restrict__ wcnt,
-                                                       const int64_t *__restrict__ woff, int strand,
+                                                       const int64_t *__restrict__ woff, const u32 *__restrict__ wstart, u32 na, int strand,
                                                        JoinGeom G, ulonglong2 *__restrict__ hits) {
-    lookup_emit_body(seq, maskbits, off, len, c2r, nwords, k, Idx64{ta}, tbl, sh, tcap, hitmask, wcnt, woff, strand, G, hits);
+    lookup_emit_body(seq, maskbits, off, len, c2r, nwords, k, Idx64{ta}, tbl, sh, tcap, hitmask, wcnt, woff, wstart, na, strand, G, hits);
 }
 
 // ------------------------------------------------------------------------- K4: band filter
