@@ -279,3 +279,36 @@ def test_device_las_merge_equals_lasort_order():
     from dentist_b200 import sharding
     r2, o2, t2 = sharding.merge_las(parts_r, parts_t)
     assert r2.tobytes() == rec.tobytes() and np.array_equal(t2, tr)
+
+
+def test_concurrent_callers_get_the_serial_results():
+    """DENTIST calls the boundary from std.parallelism worker threads (processPileUps/package.d:153): four host threads
+    hammer the same library (align, filters, QVs, consensus) and must each see exactly what a serial run returns."""
+    import threading
+    from dentist_b200 import dazzler
+    cases = []
+    for t in range(4):
+        sc = synth.make_scaffolds(1, 20000, 300 + t, n_repeats=0)
+        pile, _ = synth.simulate_reads(sc, 8, 6000, 1500, 0.13, 400 + t)
+        cases.append(pile)
+
+    def work(pile):
+        g = dazzler.Block(pile.off, pile.bases)
+        lens = np.diff(pile.off)
+        las = dazzler.align(g, g, tspace=126, minlen=500, self_block=1)
+        raw = las.rec.tobytes()
+        las.filterLocalAlignments(0.3)
+        las.chainLocalAlignments()
+        q, _ = dazzler.computeQVs(lens, las, 4)
+        las.filterPileUpAlignments(lens, lens, 126)
+        las.forceFlat()
+        cons = dazzler.getConsensus(g, las, [0, 1])
+        g.free()
+        return raw, q.tobytes(), las.rec.tobytes(), [c.tobytes() for c in cons]
+
+    serial = [work(p) for p in cases]
+    for _ in range(3):
+        out = [None] * 4
+        th = [threading.Thread(target=lambda i=i: out.__setitem__(i, work(cases[i]))) for i in range(4)]
+        [t.start() for t in th]; [t.join() for t in th]
+        assert out == serial
