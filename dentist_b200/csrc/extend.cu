@@ -277,16 +277,13 @@ __global__ void __launch_bounds__(EXT_WARPS * 32) k_extend32(const Seed *__restr
             d++;
             const int nlo = lo - 1, nhi = hi + 1;
             const int k = nlo + ((lane - nlo) & 31);            // the diagonal = lane (mod 32) inside the new window
+            // invariant: V == NEGV in every lane whose diagonal is outside [lo, hi] (kept at the end of each wave), so the
+            // three predecessors need no range checks and lanes beyond nhi fall out by themselves
             const int Vl = __shfl_sync(FULL, V, lane_l), Vr = __shfl_sync(FULL, V, lane_r);
-            int i = NEGV, src = lane;
-            if (k <= nhi) {
-                const int vs = (k >= lo && k <= hi) ? V : NEGV;
-                const int vd = (k - 1 >= lo) ? Vl : NEGV;
-                const int vi = (k + 1 <= hi) ? Vr : NEGV;
-                if (vs > NEGV) i = vs + 1;
-                if (vd > NEGV && vd + 1 > i) { i = vd + 1; src = lane_l; }
-                if (vi > NEGV && vi > i) { i = vi; src = lane_r; }
-            }
+            int i = V + 1, src = lane;
+            if (Vl + 1 > i) { i = Vl + 1; src = lane_l; }
+            if (Vr > i) { i = Vr; src = lane_r; }
+            if (i <= NEGV + 1) i = NEGV;
             int cT = __shfl_sync(FULL, T, src), cR = __shfl_sync(FULL, R, src);
             int cn = 0;
             if (i > NEGV) {
@@ -312,7 +309,7 @@ __global__ void __launch_bounds__(EXT_WARPS * 32) k_extend32(const Seed *__restr
             const int waveS = __reduce_max_sync(FULL, S);
             gbest = max(gbest, waveS);
             const bool alive = i > NEGV && !(S < gbest - X || i == la || i - k == lb);
-            if (k <= nhi) { V = alive ? i : NEGV; T = cT; R = cR; }
+            V = alive ? i : NEGV; T = cT; R = cR;
             const u32 m = __ballot_sync(FULL, alive);
             if (m == 0u) break;
             const u32 rot = __funnelshift_r(m, m, nlo & 31);    // bit j <-> diagonal nlo + j
@@ -325,6 +322,7 @@ __global__ void __launch_bounds__(EXT_WARPS * 32) k_extend32(const Seed *__restr
                 int h2 = l2 + WM - 1; if (h2 > ahi) h2 = ahi;
                 l2 = h2 - WM + 1; if (l2 < alo) l2 = alo;
                 alo = l2; ahi = h2;
+                if (k < alo || k > ahi) V = NEGV;              // trimmed off the window
             }
             lo = alo; hi = ahi;
         }
