@@ -19,13 +19,14 @@ constexpr int EXT_WARPS = 8;                 // warps per CTA
 constexpr int NEGV = -(1 << 29);
 constexpr int NEGS = -(1 << 30);
 
-__device__ __forceinline__ u32 fetch16(const u32 *__restrict__ w, int64_t g) {
-    int64_t wi = g >> 4; int sh = (int)(g & 15) << 1;
+// base offsets fit 32 bits: a block holds < 2^31 padded bases (block_upload checks 2 * total < 2^32)
+__device__ __forceinline__ u32 fetch16(const u32 *__restrict__ w, u32 g) {
+    const u32 wi = g >> 4; const int sh = (int)(g & 15u) << 1;
     u32 lo = __ldg(w + wi), hi = __ldg(w + wi + 1);
     return __funnelshift_r(lo, hi, sh);
 }
 
-__device__ __forceinline__ int slide(const u32 *__restrict__ A, int64_t ga, const u32 *__restrict__ B, int64_t gb, int lim) {
+__device__ __forceinline__ int slide(const u32 *__restrict__ A, u32 ga, const u32 *__restrict__ B, u32 gb, int lim) {
     int s = 0;
     while (s < lim) {
         u32 x = fetch16(A, ga + s) ^ fetch16(B, gb + s);
@@ -38,7 +39,7 @@ __device__ __forceinline__ int slide(const u32 *__restrict__ A, int64_t ga, cons
 __host__ __device__ inline int ext_span(int la, int lb) { long long s = (long long)lb + lb / 2 + 64; return la < s ? la : (int)s; }
 
 struct Task {
-    const u32 *A, *B; int64_t ga, gb; int la, lb, firstT;
+    const u32 *A, *B; u32 ga, gb; int la, lb, firstT;
 };
 
 __device__ __forceinline__ Task make_task(const Seed &sd, int dir, const ExtGeom &G) {
@@ -48,11 +49,11 @@ __device__ __forceinline__ Task make_task(const Seed &sd, int dir, const ExtGeom
     const int64_t oa = G.a_off[sd.a], ob = G.b_off[br];
     if (dir == 0) {
         t.A = G.a_fwd; t.B = st ? G.b_rc : G.b_fwd;
-        t.ga = oa + sd.apos; t.gb = ob + sd.bpos; t.la = LA - sd.apos; t.lb = LB - sd.bpos;
+        t.ga = (u32)(oa + sd.apos); t.gb = (u32)(ob + sd.bpos); t.la = LA - sd.apos; t.lb = LB - sd.bpos;
         t.firstT = (sd.apos / G.ts + 1) * G.ts - sd.apos;
     } else {
         t.A = G.a_rc; t.B = st ? G.b_fwd : G.b_rc;
-        t.ga = oa + (LA - sd.apos); t.gb = ob + (LB - sd.bpos); t.la = sd.apos; t.lb = sd.bpos;
+        t.ga = (u32)(oa + (LA - sd.apos)); t.gb = (u32)(ob + (LB - sd.bpos)); t.la = sd.apos; t.lb = sd.bpos;
         t.firstT = sd.apos > 0 ? sd.apos - ((sd.apos - 1) / G.ts) * G.ts : G.ts;
         if (sd.apos == 0 || sd.bpos == 0) { t.la = 0; t.lb = 0; }
     }
