@@ -139,26 +139,29 @@ template <typename Tin, typename Tout>
 __global__ void __launch_bounds__(SCAN_THREADS) k_scan_apply(const Tin *__restrict__ in, Tout *__restrict__ out,
                                                              const Tout *__restrict__ offs, size_t n, Tout *total_out) {
     __shared__ Tout sm[33];
-    __shared__ Tout tile[SCAN_TILE];
+    // one pad slot per 32 elements: the transposed accesses (thread t owns slots 16t .. 16t+15) would otherwise hit the
+    // same bank from every second thread (16-way conflicts)
+    __shared__ Tout tile[SCAN_TILE + SCAN_TILE / 32];
+    auto at = [](int x) { return x + (x >> 5); };
     size_t base = (size_t)blockIdx.x * SCAN_TILE;
 #pragma unroll
     for (int i = 0; i < SCAN_ITEMS; i++) {
         size_t idx = base + (size_t)i * SCAN_THREADS + threadIdx.x;
-        tile[i * SCAN_THREADS + threadIdx.x] = idx < n ? (Tout)in[idx] : Tout(0);
+        tile[at(i * SCAN_THREADS + threadIdx.x)] = idx < n ? (Tout)in[idx] : Tout(0);
     }
     __syncthreads();
     Tout v[SCAN_ITEMS]; Tout acc = 0;
 #pragma unroll
-    for (int i = 0; i < SCAN_ITEMS; i++) { v[i] = tile[threadIdx.x * SCAN_ITEMS + i]; acc += v[i]; }
+    for (int i = 0; i < SCAN_ITEMS; i++) { v[i] = tile[at(threadIdx.x * SCAN_ITEMS + i)]; acc += v[i]; }
     Tout total;
     Tout ex = block_exclusive<Tout>(acc, &total, sm) + (offs ? offs[blockIdx.x] : Tout(0));
 #pragma unroll
-    for (int i = 0; i < SCAN_ITEMS; i++) { tile[threadIdx.x * SCAN_ITEMS + i] = ex; ex += v[i]; }
+    for (int i = 0; i < SCAN_ITEMS; i++) { tile[at(threadIdx.x * SCAN_ITEMS + i)] = ex; ex += v[i]; }
     __syncthreads();
 #pragma unroll
     for (int i = 0; i < SCAN_ITEMS; i++) {
         size_t idx = base + (size_t)i * SCAN_THREADS + threadIdx.x;
-        if (idx < n) out[idx] = tile[i * SCAN_THREADS + threadIdx.x];
+        if (idx < n) out[idx] = tile[at(i * SCAN_THREADS + threadIdx.x)];
     }
     if (total_out && blockIdx.x == gridDim.x - 1 && threadIdx.x == 0)
         *total_out = (offs ? offs[blockIdx.x] : Tout(0)) + total;
