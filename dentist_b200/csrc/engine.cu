@@ -401,7 +401,8 @@ void align_blocks(const DevBlock &A, const DevBlock &B, const AlignParams &P, Ho
         const int64_t ntile_cap = d2h_scalar(dtotal.p, s);
         DBuf<int2> tiles((size_t)ntile_cap + 1); DBuf<ExtOut> outs(2 * (size_t)nseeds);
         const int wpc = ext_warps_per_cta();
-        int ctas = sm_count() * 4;      // 63 registers: 4 CTAs x 8 warps per SM (5 CTAs at 48 registers measured slower)
+        static const int ext_ctas_per_sm = getenv("DN_EXT_CTAS") ? atoi(getenv("DN_EXT_CTAS")) : 5;
+        int ctas = sm_count() * ext_ctas_per_sm;      // 47 registers: up to 5 CTAs x 8 warps per SM
         { int64_t need = (2ll * nseeds + wpc - 1) / wpc; if (ctas > need) ctas = (int)need;
           const int64_t budget = 24ll << 30;   // bytes of HBM for trace-record pools
           int64_t maxc = budget / (pool_stride * 16 * wpc); if (maxc < 1) maxc = 1;
