@@ -402,9 +402,9 @@ def main():
                "clocks": summarize_clocks(clk),
                "roofline": {"kernel": "k_extend32 (O(ND) wave extension, 45% of device time)", "bound": "hbm", "achieved": ext_gbs, "peak": peak,
                             "unit": "GB/s", "frac": ext_gbs / peak,
-                            "traffic": 97.6e6 / 3, "traffic_source": "ncu dram__bytes_read+write of the round-0 launch (profiles/r01_prof_extend32_r1g_details.txt) averaged over the 3 launches of a step",
+                            "traffic": 98.5e6 / 3, "traffic_source": "ncu dram__bytes_read+write of the round-0 launch (72.1 + 26.5 MB, profiles/r01_prof_extend32_r1i_details.txt) averaged over the 3 launches of a step",
                             "peak_source": peak_src,
-                            "note": "instruction-issue-bound kernel (80% issue slots busy, DRAM 0.15%): algorithmic bytes = packed sequence under each alignment + records + traces"},
+                            "note": "instruction-issue-bound kernel (79% issue slots busy, IPC 3.1, DRAM 0.2%): algorithmic bytes = packed sequence under each alignment + records + traces"},
                "roofline_seed": {"kernels": "A tuples+radix, lookup join, segment sort, band filter, retire, final ordering", "bound": "hbm", "achieved": seed_gbs, "peak": peak,
                                  "unit": "GB/s", "frac": seed_gbs / peak},
                "stage_ms_per_step": {"seed": seed_ms / args.steps, "extend": ext_ms / args.steps}}
