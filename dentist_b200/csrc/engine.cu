@@ -225,18 +225,18 @@ void align_blocks(const DevBlock &A, const DevBlock &B, const AlignParams &P, Ho
         // (a fused one-CTA-per-read count+reserve+emit kernel was measured at 2x the time of these two passes:
         //  the lookups are latency-bound and want full occupancy, which the per-read shared-memory state prevents)
         {
-            DBuf<u32> wcnt(2 * nwB), wstart(2 * nwB), wlist(2 * nwB), nlist(2); DBuf<int64_t> woff(2 * nwB);
+            DBuf<u32> wcnt(2 * nwB), wlist(2 * nwB), nlist(2); DBuf<int64_t> woff(2 * nwB);
             nlist.zero(s); DBuf<unsigned short> hitmask(2 * nwB);
             for (int st = 0; st < 2; st++) {
                 const u32 *mb = B.has_mask ? (st ? B.mask_rc.p : B.mask.p) : nullptr;
                 if (!wide)
                     DN_LAUNCH(k_lookup_count, (unsigned)((nwB + 255) / 256), 256, 0, s, (const u32 *)(st ? B.rc.p : B.fwd.p), mb,
                               (const int64_t *)B.off.p, (const int32_t *)B.len.p, (const int32_t *)B.chunk2read.p, nwB, k,
-                              (const u64 *)sa, (const u32 *)tbl.p, sh, P.t, (const u32 *)kbits.p, JG, wcnt.p + st * nwB, hitmask.p + st * nwB, wstart.p + st * nwB, wlist.p + st * nwB, nlist.p + st);
+                              (const u64 *)sa, (const u32 *)tbl.p, sh, P.t, (const u32 *)kbits.p, JG, wcnt.p + st * nwB, hitmask.p + st * nwB, wlist.p + st * nwB, nlist.p + st);
                 else
                     DN_LAUNCH(k_lookup_count_w, (unsigned)((nwB + 255) / 256), 256, 0, s, (const u32 *)(st ? B.rc.p : B.fwd.p), mb,
                               (const int64_t *)B.off.p, (const int32_t *)B.len.p, (const int32_t *)B.chunk2read.p, nwB, k,
-                              (const ulonglong2 *)sw, (const u32 *)tbl.p, sh, P.t, (const u32 *)kbits.p, JG, wcnt.p + st * nwB, hitmask.p + st * nwB, wstart.p + st * nwB, wlist.p + st * nwB, nlist.p + st);
+                              (const ulonglong2 *)sw, (const u32 *)tbl.p, sh, P.t, (const u32 *)kbits.p, JG, wcnt.p + st * nwB, hitmask.p + st * nwB, wlist.p + st * nwB, nlist.p + st);
             }
             exclusive_scan_u32_to_i64(wcnt.p, woff.p, 2 * nwB, dtotal.p, s);
             H = d2h_scalar(dtotal.p, s);
@@ -252,12 +252,12 @@ void align_blocks(const DevBlock &A, const DevBlock &B, const AlignParams &P, Ho
                         DN_LAUNCH(k_lookup_emit, (unsigned)((nl[st] + 255) / 256), 256, 0, s, (const u32 *)(st ? B.rc.p : B.fwd.p), mb,
                                   (const int64_t *)B.off.p, (const int32_t *)B.len.p, (const int32_t *)B.chunk2read.p, (int64_t)nl[st], k,
                                   (const u64 *)sa, (const u32 *)tbl.p, sh, P.t, (const unsigned short *)(hitmask.p + st * nwB), (const u32 *)(wcnt.p + st * nwB),
-                                  (const int64_t *)(woff.p + st * nwB), (const u32 *)(wstart.p + st * nwB), (u32)nA, st, JG, hits.p, (const u32 *)(wlist.p + st * nwB));
+                                  (const int64_t *)(woff.p + st * nwB), st, JG, hits.p, (const u32 *)(wlist.p + st * nwB));
                     else
                         DN_LAUNCH(k_lookup_emit_w, (unsigned)((nl[st] + 255) / 256), 256, 0, s, (const u32 *)(st ? B.rc.p : B.fwd.p), mb,
                                   (const int64_t *)B.off.p, (const int32_t *)B.len.p, (const int32_t *)B.chunk2read.p, (int64_t)nl[st], k,
                                   (const ulonglong2 *)sw, (const u32 *)tbl.p, sh, P.t, (const unsigned short *)(hitmask.p + st * nwB), (const u32 *)(wcnt.p + st * nwB),
-                                  (const int64_t *)(woff.p + st * nwB), (const u32 *)(wstart.p + st * nwB), (u32)nA, st, JG, hits.p, (const u32 *)(wlist.p + st * nwB));
+                                  (const int64_t *)(woff.p + st * nwB), st, JG, hits.p, (const u32 *)(wlist.p + st * nwB));
                 }
             launch_seg_offsets(woff.p, B.off.p, B.nreads, nwB, H, seg_beg.p, seg_len.p, s);
             abytes += 2 * (nB / 4) * 2 + 2 * nwB * (4 + 4 + 8 + 8 + 4) + 16 * H;   // packed B read twice per strand, word counts/offsets, hits

@@ -38,20 +38,20 @@ __global__ void k_join_emit(const u64 *ta, const u64 *tb, int64_t nb, const u32 
                             JoinGeom G, ulonglong2 *hits, unsigned long long *ninvalid);
 __global__ void k_lookup_count(const u32 *seq, const u32 *maskbits, const int64_t *off, const int32_t *len, const int32_t *c2r,
                                int64_t nwords, int k, const u64 *ta, const u32 *tbl, int sh, int tcap, const u32 *kbits, JoinGeom G,
-                               u32 *wcnt, unsigned short *hitmask, u32 *wstart, u32 *wlist, u32 *nlist);
+                               u32 *wcnt, unsigned short *hitmask, u32 *wlist, u32 *nlist);
 __global__ void k_kmer_bitmap(const u64 *ta, int64_t na, u32 *bits);
 __global__ void k_lookup_emit(const u32 *seq, const u32 *maskbits, const int64_t *off, const int32_t *len, const int32_t *c2r,
                               int64_t nwords, int k, const u64 *ta, const u32 *tbl, int sh, int tcap, const unsigned short *hitmask,
-                              const u32 *wcnt, const int64_t *woff, const u32 *wstart, u32 na, int strand, JoinGeom G, ulonglong2 *hits, const u32 *wlist);
+                              const u32 *wcnt, const int64_t *woff, int strand, JoinGeom G, ulonglong2 *hits, const u32 *wlist);
 // k = 16..31 variants over 16-byte {kmer, position} index entries
 __global__ void k_prefix_table_w(const ulonglong2 *ta, int64_t na, int sh, u32 nq, u32 *tbl);
 __global__ void k_kmer_bitmap_w(const ulonglong2 *ta, int64_t na, u32 *bits);
 __global__ void k_lookup_count_w(const u32 *seq, const u32 *maskbits, const int64_t *off, const int32_t *len, const int32_t *c2r,
                                  int64_t nwords, int k, const ulonglong2 *ta, const u32 *tbl, int sh, int tcap, const u32 *kbits, JoinGeom G,
-                                 u32 *wcnt, unsigned short *hitmask, u32 *wstart, u32 *wlist, u32 *nlist);
+                                 u32 *wcnt, unsigned short *hitmask, u32 *wlist, u32 *nlist);
 __global__ void k_lookup_emit_w(const u32 *seq, const u32 *maskbits, const int64_t *off, const int32_t *len, const int32_t *c2r,
                                 int64_t nwords, int k, const ulonglong2 *ta, const u32 *tbl, int sh, int tcap, const unsigned short *hitmask,
-                                const u32 *wcnt, const int64_t *woff, const u32 *wstart, u32 na, int strand, JoinGeom G, ulonglong2 *hits, const u32 *wlist);
+                                const u32 *wcnt, const int64_t *woff, int strand, JoinGeom G, ulonglong2 *hits, const u32 *wlist);
 __global__ void k_hit_cover(const ulonglong2 *hits, int64_t n, int k, int w, int32_t *cov, int32_t *bflag);
 __global__ void k_band_table(const ulonglong2 *hits, int64_t n, int w, const int32_t *bflag, const int32_t *bidx,
                              int32_t *bfirst, u64 *bkey, int32_t nbands);
