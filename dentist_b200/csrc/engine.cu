@@ -130,8 +130,8 @@ void align_blocks(const DevBlock &A, const DevBlock &B, const AlignParams &P, Ho
     if (P.cdiff < 20 || P.xdrop < 1 || P.xdrop > 1000) throw Error("bad cdiff / xdrop");
     if (P.rounds < 1 || P.poolmul < 1) throw Error("bad rounds / poolmul");
     const unsigned long long launches0 = g_launches.load();
-    Timer tt(s), ts_(s), te(s);
-    tt.start(); ts_.start();
+    Timer tt(s);
+    tt.start();
     if (A.nreads == 0 || B.nreads == 0) {
         out.rec = (dn_las_record *)hcache_alloc(64); out.toff = (int64_t *)hcache_alloc(64); out.trace = (uint16_t *)hcache_alloc(64);
         out.stats.ms_total = tt.stop(); return;
@@ -362,18 +362,19 @@ void align_blocks(const DevBlock &A, const DevBlock &B, const AlignParams &P, Ho
     std::vector<DBuf<Cand>> round_cands; std::vector<DBuf<uint16_t>> round_traces;
     std::vector<int32_t> round_beg{0};
     std::vector<int64_t> round_ntr;
-    float ms_seed = ts_.stop(), ms_ext = 0;
+    float ms_ext = 0;
+    std::vector<std::pair<cudaEvent_t, cudaEvent_t>> ext_ev;      // brackets of the k_extend launches, read after the last sync
     int64_t ext_bytes = 0;
-    DBuf<int32_t> dtot32(1);
+    DBuf<int32_t> dtot32(2);
 
     for (int round = 0; round < P.rounds && n > 0; round++) {
-        ts_.start();
         DBuf<int32_t> cov(n), bflag(n), bidx(n), covsum(n);
         DN_LAUNCH(k_hit_cover, (unsigned)((n + 255) / 256), 256, 0, s, (const ulonglong2 *)hs, n, k, P.w, cov.p, bflag.p);
         exclusive_scan_i32(bflag.p, bidx.p, n, dtot32.p, s);
-        const int32_t nbands = d2h_scalar(dtot32.p, s);
-        exclusive_scan_i32(cov.p, covsum.p, n, dtot32.p, s);
-        const int32_t total_cov = d2h_scalar(dtot32.p, s);
+        exclusive_scan_i32(cov.p, covsum.p, n, dtot32.p + 1, s);
+        int32_t two[2];
+        DN_CUDA(cudaMemcpyAsync(two, dtot32.p, 8, cudaMemcpyDeviceToHost, s)); DN_CUDA(cudaStreamSynchronize(s));
+        const int32_t nbands = two[0], total_cov = two[1];
         DBuf<int32_t> bfirst((size_t)nbands + 2), cstart(nbands), cidx(nbands);
         DBuf<u64> bkey((size_t)nbands + 1);
         DBuf<uint8_t> pass(nbands), hot(nbands);
@@ -386,15 +387,13 @@ void align_blocks(const DevBlock &A, const DevBlock &B, const AlignParams &P, Ho
         const int32_t nseeds = d2h_scalar(dtot32.p, s);
         abytes += 16 * n + 8 * n + 3 * 12 * n + 16ll * nbands;
         tr.mark("band filter");
-        if (nseeds == 0) { ms_seed += ts_.stop(); break; }
+        if (nseeds == 0) break;
         DBuf<Seed> seeds(nseeds); DBuf<uint8_t> consumed(n); consumed.zero(s);
         DN_LAUNCH(k_seeds, (nbands + 255) / 256, 256, 0, s, (const ulonglong2 *)hs, (const int32_t *)bfirst.p, (const u64 *)bkey.p,
                   (const uint8_t *)hot.p, (const int32_t *)cstart.p, (const int32_t *)cidx.p, nbands, SG, seeds.p, consumed.p);
         out.stats.seeds += nseeds; out.stats.extensions += 2ll * nseeds;
-        ms_seed += ts_.stop();
 
         // ---- K5: extension
-        ts_.start();
         DBuf<u32> caps(2 * (size_t)nseeds); DBuf<int64_t> tile_off(2 * (size_t)nseeds);
         launch_task_caps(seeds.p, nseeds, EG, caps.p, s);
         exclusive_scan_u32_to_i64(caps.p, tile_off.p, 2 * (size_t)nseeds, dtotal.p, s);
@@ -409,20 +408,22 @@ void align_blocks(const DevBlock &A, const DevBlock &B, const AlignParams &P, Ho
           if (ctas > maxc) ctas = (int)maxc; }
         DBuf<int4> pool((size_t)ctas * wpc * pool_stride);
         DBuf<int> counter(1); counter.zero(s);
-        ms_seed += ts_.stop();
         tr.mark("seeds + ext setup");
-        te.start();                              // brackets exactly the k_extend launch
-        launch_extend(seeds.p, nseeds, EG, tile_off.p, tiles.p, outs.p, pool.p, pool_stride, ctas * wpc, counter.p, s);
-        ms_ext += te.stop();
+        {   // events bracket exactly the k_extend launch; no host sync here
+            cudaEvent_t ea, eb; cudaEventCreate(&ea); cudaEventCreate(&eb);
+            cudaEventRecord(ea, s);
+            launch_extend(seeds.p, nseeds, EG, tile_off.p, tiles.p, outs.p, pool.p, pool_stride, ctas * wpc, counter.p, s);
+            cudaEventRecord(eb, s);
+            ext_ev.emplace_back(ea, eb);
+        }
         tr.mark("k_extend");
 
         // ---- K6: candidates, traces, retirement
-        ts_.start();
         DBuf<Cand> cand_all(nseeds); DBuf<int32_t> valid(nseeds), vidx(nseeds); DBuf<u32> ntl(nseeds); DBuf<int64_t> toff(nseeds);
         launch_combine(seeds.p, nseeds, EG, P.minlen, tile_off.p, tiles.p, outs.p, cand_all.p, valid.p, ntl.p, s);
         exclusive_scan_i32(valid.p, vidx.p, nseeds, dtot32.p, s);
-        const int32_t nvalid = d2h_scalar(dtot32.p, s);
         exclusive_scan_u32_to_i64(ntl.p, toff.p, nseeds, dtotal.p, s);
+        const int32_t nvalid = d2h_scalar(dtot32.p, s);              // both scans are queued: one drain serves the two reads
         const int64_t ntr = d2h_scalar(dtotal.p, s);
         DBuf<Cand> rc((size_t)nvalid + 1); DBuf<uint16_t> rtr((size_t)2 * ntr + 2);
         launch_write_traces(seeds.p, nseeds, EG, tile_off.p, tiles.p, outs.p, cand_all.p, valid.p, vidx.p, toff.p, rc.p, rtr.p, s);
@@ -440,7 +441,6 @@ void align_blocks(const DevBlock &A, const DevBlock &B, const AlignParams &P, Ho
         round_ntr.push_back(2 * ntr);
         round_cands.push_back(std::move(rc)); round_traces.push_back(std::move(rtr));
         tr.mark("combine + retire");
-        ms_seed += ts_.stop();
     }
 
     // ---- duplicate removal, LAsort ordering and trace gather on the device; one download ---------
@@ -502,7 +502,9 @@ void align_blocks(const DevBlock &A, const DevBlock &B, const AlignParams &P, Ho
     tr.mark("dedupe + order + download");
     out.stats.las = out.nrec; out.stats.aligned_bases = aligned; out.stats.trace_points = tot / 2;
     out.stats.algo_bytes_seed = abytes; out.stats.algo_bytes_extend = ext_bytes;
-    out.stats.ms_seed = ms_seed; out.stats.ms_extend = ms_ext; out.stats.ms_total = tt.stop();
+    out.stats.ms_total = tt.stop();                          // syncs the stream: the extension brackets are complete
+    for (auto &e : ext_ev) { float ms = 0; cudaEventElapsedTime(&ms, e.first, e.second); ms_ext += ms; cudaEventDestroy(e.first); cudaEventDestroy(e.second); }
+    out.stats.ms_extend = ms_ext; out.stats.ms_seed = out.stats.ms_total - ms_ext;      // seed = everything but the k_extend launches
     out.stats.launches = g_launches.load() - launches0;
 }
 
