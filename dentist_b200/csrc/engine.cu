@@ -431,8 +431,7 @@ void align_blocks(const DevBlock &A, const DevBlock &B, const AlignParams &P, Ho
         launch_retire((const ulonglong2 *)hs, n, consumed.p, rc.p, nvalid, SG, P.w, bflag.p, bidx.p, hot.p, keep.p, s);
         exclusive_scan_i32(keep.p, kidx.p, n, dtot32.p, s);
         const int64_t n_new = d2h_scalar(dtot32.p, s);
-        launch_compact_hits((const ulonglong2 *)hs, n, keep.p, kidx.p, ho, s);
-        DN_CUDA(cudaStreamSynchronize(s));
+        launch_compact_hits((const ulonglong2 *)hs, n, keep.p, kidx.p, ho, s);      // same stream: the next round is ordered behind it
         std::swap(hs, ho);
         abytes += 24 * n + 16 * n_new;
         if (getenv("DN_TRACE")) fprintf(stderr, "[dn trace] round %d: %lld hits, %d bands, %d seeds, %d candidates >= minlen, %lld hits left\n", round, (long long)(n), nbands, nseeds, nvalid, (long long)n_new);
