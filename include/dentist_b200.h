@@ -105,7 +105,7 @@ typedef struct dn_align_stats {
     int64_t tuples_a, tuples_b, hits, seeds, extensions, las, aligned_bases, trace_points;
     int64_t algo_bytes_seed;      /* algorithmic HBM bytes of the seeding stages   */
     int64_t algo_bytes_extend;    /* algorithmic HBM bytes of the wave extension              */
-    float ms_seed, ms_extend, ms_total;   /* CUDA-event times on the engine's stream          */
+    float ms_seed, ms_extend, ms_total;   /* CUDA-event times on the engine's stream: total, the k_extend launches, and seed = total - extend */
     uint64_t launches;
 } dn_align_stats;
 
