@@ -109,13 +109,15 @@ void block_build_index(DevBlock &A, int k, cudaStream_t s) {
     X.tbits = index_tbits(nA, k, true);
     const int sh = 2 * k - X.tbits; const u32 nq = 1u << X.tbits;
     X.tbl.persistent((size_t)nq + 2);
-    X.kbits.persistent((1u << KBITS_LOG2) / 32); X.kbits.zero(s);
+    X.kbits_log2 = kbits_log2_for(nA);
+    const int kshift = 32 - (X.kbits_log2 - 5);
+    X.kbits.persistent((size_t)1 << (X.kbits_log2 - 5)); X.kbits.zero(s);
     if (!wide) {
         DN_LAUNCH(k_prefix_table, (unsigned)((nA + 255) / 256), 256, 0, s, (const u64 *)X.ta.p, nA, sh, nq, X.tbl.p);
-        DN_LAUNCH(k_kmer_bitmap, (unsigned)((nA + 255) / 256), 256, 0, s, (const u64 *)X.ta.p, nA, X.kbits.p);
+        DN_LAUNCH(k_kmer_bitmap, (unsigned)((nA + 255) / 256), 256, 0, s, (const u64 *)X.ta.p, nA, kshift, X.kbits.p);
     } else {
         DN_LAUNCH(k_prefix_table_w, (unsigned)((nA + 255) / 256), 256, 0, s, (const ulonglong2 *)X.tw.p, nA, sh, nq, X.tbl.p);
-        DN_LAUNCH(k_kmer_bitmap_w, (unsigned)((nA + 255) / 256), 256, 0, s, (const ulonglong2 *)X.tw.p, nA, X.kbits.p);
+        DN_LAUNCH(k_kmer_bitmap_w, (unsigned)((nA + 255) / 256), 256, 0, s, (const ulonglong2 *)X.tw.p, nA, kshift, X.kbits.p);
     }
     DN_CUDA(cudaStreamSynchronize(s));
     X.k = k; X.valid = true;
@@ -206,17 +208,18 @@ void align_blocks(const DevBlock &A, const DevBlock &B, const AlignParams &P, Ho
         const int64_t nwB = nB >> 4;
         const int nseg = 2 * B.nreads;
         DBuf<u32> kbits_own; struct { const u32 *p; } kbits{cached ? cached->kbits.p : nullptr};
+        const int kblog = cached ? cached->kbits_log2 : kbits_log2_for(nA), kshift = 32 - (kblog - 5);
         if (!cached) {
-            kbits_own.alloc((1u << KBITS_LOG2) / 32); kbits_own.zero(s); kbits.p = kbits_own.p;
-            if (!wide) DN_LAUNCH(k_kmer_bitmap, (unsigned)((nA + 255) / 256), 256, 0, s, (const u64 *)sa, nA, kbits_own.p);
-            else DN_LAUNCH(k_kmer_bitmap_w, (unsigned)((nA + 255) / 256), 256, 0, s, (const ulonglong2 *)sw, nA, kbits_own.p);
+            kbits_own.alloc((size_t)1 << (kblog - 5)); kbits_own.zero(s); kbits.p = kbits_own.p;
+            if (!wide) DN_LAUNCH(k_kmer_bitmap, (unsigned)((nA + 255) / 256), 256, 0, s, (const u64 *)sa, nA, kshift, kbits_own.p);
+            else DN_LAUNCH(k_kmer_bitmap_w, (unsigned)((nA + 255) / 256), 256, 0, s, (const ulonglong2 *)sw, nA, kshift, kbits_own.p);
         }
         // pin the k-mer filter in the persisting part of L2 while the streaming lookups run
         {
             static bool limit_set = false;
             if (!limit_set) { cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, 48u << 20); cudaGetLastError(); limit_set = true; }
             cudaStreamAttrValue av; memset(&av, 0, sizeof av);
-            av.accessPolicyWindow.base_ptr = (void *)kbits.p; av.accessPolicyWindow.num_bytes = (size_t)(1u << KBITS_LOG2) / 8;
+            av.accessPolicyWindow.base_ptr = (void *)kbits.p; av.accessPolicyWindow.num_bytes = kblog <= 28 ? ((size_t)1 << (kblog - 3)) : 0;   // only an L2-sized filter is pinned
             av.accessPolicyWindow.hitRatio = 1.0f; av.accessPolicyWindow.hitProp = cudaAccessPropertyPersisting;
             av.accessPolicyWindow.missProp = cudaAccessPropertyStreaming;
             cudaStreamSetAttribute(s, cudaStreamAttributeAccessPolicyWindow, &av); cudaGetLastError();
@@ -232,11 +235,11 @@ void align_blocks(const DevBlock &A, const DevBlock &B, const AlignParams &P, Ho
                 if (!wide)
                     DN_LAUNCH(k_lookup_count, (unsigned)((nwB + 255) / 256), 256, 0, s, (const u32 *)(st ? B.rc.p : B.fwd.p), mb,
                               (const int64_t *)B.off.p, (const int32_t *)B.len.p, (const int32_t *)B.chunk2read.p, nwB, k,
-                              (const u64 *)sa, (const u32 *)tbl.p, sh, P.t, (const u32 *)kbits.p, JG, wcnt.p + st * nwB, hitmask.p + st * nwB, wlist.p + st * nwB, nlist.p + st);
+                              (const u64 *)sa, (const u32 *)tbl.p, sh, P.t, (const u32 *)kbits.p, kshift, JG, wcnt.p + st * nwB, hitmask.p + st * nwB, wlist.p + st * nwB, nlist.p + st);
                 else
                     DN_LAUNCH(k_lookup_count_w, (unsigned)((nwB + 255) / 256), 256, 0, s, (const u32 *)(st ? B.rc.p : B.fwd.p), mb,
                               (const int64_t *)B.off.p, (const int32_t *)B.len.p, (const int32_t *)B.chunk2read.p, nwB, k,
-                              (const ulonglong2 *)sw, (const u32 *)tbl.p, sh, P.t, (const u32 *)kbits.p, JG, wcnt.p + st * nwB, hitmask.p + st * nwB, wlist.p + st * nwB, nlist.p + st);
+                              (const ulonglong2 *)sw, (const u32 *)tbl.p, sh, P.t, (const u32 *)kbits.p, kshift, JG, wcnt.p + st * nwB, hitmask.p + st * nwB, wlist.p + st * nwB, nlist.p + st);
             }
             exclusive_scan_u32_to_i64(wcnt.p, woff.p, 2 * nwB, dtotal.p, s);
             H = d2h_scalar(dtotal.p, s);

@@ -32,7 +32,7 @@ struct DevBlock {
     // optional resident k-mer index (dn_block_index): the sorted tuple list, prefix table and k-mer filter that
     // align_blocks otherwise rebuilds for the A block on every call.  Invalidated when the seed mask changes.
     struct Index {
-        int k = 0, tbits = 0;
+        int k = 0, tbits = 0, kbits_log2 = 27;
         DBuf<u64> ta; DBuf<ulonglong2> tw; DBuf<u32> tbl, kbits;
         bool valid = false;
         void drop() { ta.release(); tw.release(); tbl.release(); kbits.release(); valid = false; k = 0; }

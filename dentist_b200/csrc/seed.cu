@@ -384,30 +384,30 @@ __global__ void __launch_bounds__(256) k_join_emit(const u64 *__restrict__ ta, c
 // sector read instead of the table + list walk.
 // blocked Bloom filter: one 32-bit word per k-mer (multiplicative hash), three bits inside it (second hash):
 // a probe touches ONE sector; 2^27 bits = 16 MB for ~1 % false positives at 10 M distinct k-mers
-__device__ __forceinline__ void kbit_slot(u32 km, u32 &word, u32 &mask) {
-    word = (km * 0x9E3779B1u) >> (32 - (KBITS_LOG2 - 5));
+__device__ __forceinline__ void kbit_slot(u32 km, int kshift, u32 &word, u32 &mask) {      // kshift = 32 - (log2(filter bits) - 5)
+    word = (km * 0x9E3779B1u) >> kshift;
     const u32 h = km * 0x85EBCA6Bu;
     mask = (1u << (h >> 27)) | (1u << ((h >> 22) & 31u)) | (1u << ((h >> 17) & 31u));
 }
 
 template <class IDX>
-__device__ __forceinline__ void kmer_bitmap_body(IDX ta, int64_t na, u32 *__restrict__ bits) {
+__device__ __forceinline__ void kmer_bitmap_body(IDX ta, int64_t na, int kshift, u32 *__restrict__ bits) {
     int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= na) return;
     const typename IDX::key_t km = ta.key(i);
     if (IDX::invalid(km)) return;
     if (i > 0 && ta.key(i - 1) == km) return;                    // one atomic per distinct k-mer
-    u32 word, mask; kbit_slot(IDX::fold(km), word, mask);
+    u32 word, mask; kbit_slot(IDX::fold(km), kshift, word, mask);
     atomicOr(&bits[word], mask);
 }
-__global__ void __launch_bounds__(256) k_kmer_bitmap(const u64 *__restrict__ ta, int64_t na, u32 *__restrict__ bits) {
-    kmer_bitmap_body(Idx32{ta}, na, bits);
+__global__ void __launch_bounds__(256) k_kmer_bitmap(const u64 *__restrict__ ta, int64_t na, int kshift, u32 *__restrict__ bits) {
+    kmer_bitmap_body(Idx32{ta}, na, kshift, bits);
 }
-__global__ void __launch_bounds__(256) k_kmer_bitmap_w(const ulonglong2 *__restrict__ ta, int64_t na, u32 *__restrict__ bits) {
-    kmer_bitmap_body(Idx64{ta}, na, bits);
+__global__ void __launch_bounds__(256) k_kmer_bitmap_w(const ulonglong2 *__restrict__ ta, int64_t na, int kshift, u32 *__restrict__ bits) {
+    kmer_bitmap_body(Idx64{ta}, na, kshift, bits);
 }
-__device__ __forceinline__ bool kmer_present(const u32 *__restrict__ bits, u32 km) {
-    u32 word, mask; kbit_slot(km, word, mask);
+__device__ __forceinline__ bool kmer_present(const u32 *__restrict__ bits, int kshift, u32 km) {
+    u32 word, mask; kbit_slot(km, kshift, word, mask);
     return (bits[word] & mask) == mask;
 }
 
@@ -453,7 +453,7 @@ __device__ __forceinline__ void lookup_count_body(const u32 *__restrict__ seq, c
                                                   const int64_t *__restrict__ off, const int32_t *__restrict__ len,
                                                   const int32_t *__restrict__ c2r, int64_t nwords, int k,
                                                   IDX ta, const u32 *__restrict__ tbl, int sh, int tcap,
-                                                  const u32 *__restrict__ kbits, const JoinGeom &G, u32 *__restrict__ wcnt,
+                                                  const u32 *__restrict__ kbits, int kshift, const JoinGeom &G, u32 *__restrict__ wcnt,
                                                   unsigned short *__restrict__ hitmask,
                                                   u32 *__restrict__ wlist, u32 *__restrict__ nlist) {
     __shared__ u32 s_total[8][32], s_hm[8][32];
@@ -469,7 +469,7 @@ __device__ __forceinline__ void lookup_count_body(const u32 *__restrict__ seq, c
         w = load_word<IDX::wide>(seq, maskbits, off, len, c2r, wi);
 #pragma unroll
         for (int jj = 0; jj < 16; jj++)
-            if ((w.p0 + jj + k <= w.L) && (((w.mwin >> jj) & mk) == 0) && kmer_present(kbits, IDX::fold(kmer_at<IDX>(w, jj, kmask))))
+            if ((w.p0 + jj + k <= w.L) && (((w.mwin >> jj) & mk) == 0) && kmer_present(kbits, kshift, IDX::fold(kmer_at<IDX>(w, jj, kmask))))
                 present |= 1u << jj;
     }
     s_total[warp][lane] = 0; s_hm[warp][lane] = 0;
@@ -528,19 +528,19 @@ __global__ void __launch_bounds__(256) k_lookup_count(const u32 *__restrict__ se
                                                       const int64_t *__restrict__ off, const int32_t *__restrict__ len,
                                                       const int32_t *__restrict__ c2r, int64_t nwords, int k,
                                                       const u64 *__restrict__ ta, const u32 *__restrict__ tbl, int sh, int tcap,
-                                                      const u32 *__restrict__ kbits, JoinGeom G, u32 *__restrict__ wcnt,
+                                                      const u32 *__restrict__ kbits, int kshift, JoinGeom G, u32 *__restrict__ wcnt,
                                                       unsigned short *__restrict__ hitmask,
                                                       u32 *__restrict__ wlist, u32 *__restrict__ nlist) {
-    lookup_count_body(seq, maskbits, off, len, c2r, nwords, k, Idx32{ta}, tbl, sh, tcap, kbits, G, wcnt, hitmask, wlist, nlist);
+    lookup_count_body(seq, maskbits, off, len, c2r, nwords, k, Idx32{ta}, tbl, sh, tcap, kbits, kshift, G, wcnt, hitmask, wlist, nlist);
 }
 __global__ void __launch_bounds__(256) k_lookup_count_w(const u32 *__restrict__ seq, const u32 *__restrict__ maskbits,
                                                         const int64_t *__restrict__ off, const int32_t *__restrict__ len,
                                                         const int32_t *__restrict__ c2r, int64_t nwords, int k,
                                                         const ulonglong2 *__restrict__ ta, const u32 *__restrict__ tbl, int sh, int tcap,
-                                                        const u32 *__restrict__ kbits, JoinGeom G, u32 *__restrict__ wcnt,
+                                                        const u32 *__restrict__ kbits, int kshift, JoinGeom G, u32 *__restrict__ wcnt,
                                                         unsigned short *__restrict__ hitmask,
                                                         u32 *__restrict__ wlist, u32 *__restrict__ nlist) {
-    lookup_count_body(seq, maskbits, off, len, c2r, nwords, k, Idx64{ta}, tbl, sh, tcap, kbits, G, wcnt, hitmask, wlist, nlist);
+    lookup_count_body(seq, maskbits, off, len, c2r, nwords, k, Idx64{ta}, tbl, sh, tcap, kbits, kshift, G, wcnt, hitmask, wlist, nlist);
 }
 
 template <class IDX>

@@ -4,7 +4,9 @@
 
 namespace dn {
 
-constexpr int KBITS_LOG2 = 27;      // k-mer presence filter (blocked Bloom, 3 bits per k-mer): 2^27 bits = 16 MB
+// k-mer presence filter (blocked Bloom, 3 bits per k-mer): >= 12 bits per indexed position, 2^27 bits (16 MB, pinned in
+// L2) at least, 2^32 at most (a 100 Mbp reference block gets 2^31 bits = 256 MB; a 16 MB filter would be ~90 % full there)
+inline int kbits_log2_for(int64_t n_index) { int b = 27; while (b < 32 && (1ll << b) < 12 * n_index) b++; return b; }
 
 struct Seed { int32_t a, bs, apos, bpos; };
 
@@ -37,17 +39,17 @@ __global__ void k_join_count(const u64 *ta, const u32 *tbl, int sh, const u64 *t
 __global__ void k_join_emit(const u64 *ta, const u64 *tb, int64_t nb, const u32 *cnt, const u32 *start, const int64_t *hoff,
                             JoinGeom G, ulonglong2 *hits, unsigned long long *ninvalid);
 __global__ void k_lookup_count(const u32 *seq, const u32 *maskbits, const int64_t *off, const int32_t *len, const int32_t *c2r,
-                               int64_t nwords, int k, const u64 *ta, const u32 *tbl, int sh, int tcap, const u32 *kbits, JoinGeom G,
+                               int64_t nwords, int k, const u64 *ta, const u32 *tbl, int sh, int tcap, const u32 *kbits, int kshift, JoinGeom G,
                                u32 *wcnt, unsigned short *hitmask, u32 *wlist, u32 *nlist);
-__global__ void k_kmer_bitmap(const u64 *ta, int64_t na, u32 *bits);
+__global__ void k_kmer_bitmap(const u64 *ta, int64_t na, int kshift, u32 *bits);
 __global__ void k_lookup_emit(const u32 *seq, const u32 *maskbits, const int64_t *off, const int32_t *len, const int32_t *c2r,
                               int64_t nwords, int k, const u64 *ta, const u32 *tbl, int sh, int tcap, const unsigned short *hitmask,
                               const u32 *wcnt, const int64_t *woff, int strand, JoinGeom G, ulonglong2 *hits, const u32 *wlist);
 // k = 16..31 variants over 16-byte {kmer, position} index entries
 __global__ void k_prefix_table_w(const ulonglong2 *ta, int64_t na, int sh, u32 nq, u32 *tbl);
-__global__ void k_kmer_bitmap_w(const ulonglong2 *ta, int64_t na, u32 *bits);
+__global__ void k_kmer_bitmap_w(const ulonglong2 *ta, int64_t na, int kshift, u32 *bits);
 __global__ void k_lookup_count_w(const u32 *seq, const u32 *maskbits, const int64_t *off, const int32_t *len, const int32_t *c2r,
-                                 int64_t nwords, int k, const ulonglong2 *ta, const u32 *tbl, int sh, int tcap, const u32 *kbits, JoinGeom G,
+                                 int64_t nwords, int k, const ulonglong2 *ta, const u32 *tbl, int sh, int tcap, const u32 *kbits, int kshift, JoinGeom G,
                                  u32 *wcnt, unsigned short *hitmask, u32 *wlist, u32 *nlist);
 __global__ void k_lookup_emit_w(const u32 *seq, const u32 *maskbits, const int64_t *off, const int32_t *len, const int32_t *c2r,
                                 int64_t nwords, int k, const ulonglong2 *ta, const u32 *tbl, int sh, int tcap, const unsigned short *hitmask,
