@@ -43,7 +43,7 @@ def make_workload(scale, rank):
 
 
 def clocks_sampler(stop, out, gpu_index):
-    """Samples SM clock / throttle reasons every 200 ms DURING the timed region.  Uses NVML in-process
+    """Samples SM clock / throttle reasons every 50 ms DURING the timed region (the default run times about 0.3 s).  Uses NVML in-process
     (same counters as the recipe's `nvidia-smi --query-gpu=clocks.sm,...,clocks_event_reasons.* -lms 200`
     line) because forking nvidia-smi 5x/s takes the driver lock for milliseconds and perturbs a 40 ms step."""
     try:
@@ -58,7 +58,7 @@ def clocks_sampler(stop, out, gpu_index):
             pw = nv.nvmlDeviceGetPowerUsage(h) / 1000.0
             r = nv.nvmlDeviceGetCurrentClocksThrottleReasons(h)
             out.append("%d, %d, %.1f, 0x%x, %s" % (sm, mx, pw, r, ", ".join("Active" if r & bit else "Not Active" for _, bit in names)))
-            stop.wait(0.2)
+            stop.wait(0.05)
     except Exception as e:   # NVML unavailable: fall back to the recipe's nvidia-smi line
         q = "clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown," \
             "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
