@@ -295,13 +295,19 @@ __global__ void __launch_bounds__(EXT_WARPS * 32) k_extend32(const Seed *__restr
                     while (i >= cR) { cn++; cR += ts; }
                 }
             }
-            if (__any_sync(FULL, cn != 0)) {
-                const int need = __reduce_add_sync(FULL, cn);
-                if (npool + need > poolcap) break;              // pool exhausted: stop before this wave
-                int pre = cn;
+            const u32 cm = __ballot_sync(FULL, cn != 0);
+            if (cm) {
+                int need, at;
+                if (!__any_sync(FULL, cn > 1)) {                // the usual case: at most one tile boundary per cell
+                    need = __popc(cm); at = npool + __popc(cm & ((1u << lane) - 1u));
+                } else {
+                    need = __reduce_add_sync(FULL, cn);
+                    int pre = cn;
 #pragma unroll
-                for (int o = 1; o < 32; o <<= 1) { int t = __shfl_up_sync(FULL, pre, o); if (lane >= o) pre += t; }
-                int at = npool + pre - cn;
+                    for (int o = 1; o < 32; o <<= 1) { int t = __shfl_up_sync(FULL, pre, o); if (lane >= o) pre += t; }
+                    at = npool + pre - cn;
+                }
+                if (npool + need > poolcap) break;              // pool exhausted: stop before this wave
                 for (int q = cn; q >= 1; q--) { pool[at] = make_int4(cT, cR - q * ts - k, d, 0); cT = at++; }
                 npool += need;
             }
