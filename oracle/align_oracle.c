@@ -40,7 +40,8 @@
  *      coordinate) it records (B offset, diffs so far); tiles are differences of records.
  *   7. an alignment is kept when (aepos-abpos)+(bepos-bbpos) >= 2*minlen; contained
  *      duplicates are dropped; hits covered by a kept alignment are retired and the whole
- *      select/extend step repeats on the remaining hits for up to `rounds` rounds.
+ *      select/extend step repeats on the remaining hits for up to `rounds` rounds; a round that
+ *      keeps no alignment ends the loop (its clusters would only be retried one hit poorer).
  *   8. output order = LAsort order (aread, bread, comp, abpos, aepos, bbpos, bepos, diffs)
  *      = FlatLocalAlignment.opCmp, base.d:1787-1809.
  */
@@ -446,6 +447,7 @@ int orc_align(const orc_block *A, const orc_block *B, const orc_params *P, orc_r
             }
             nh = o;
         }
+        if (ncand == nnew0) break;                     /* nothing kept this round: stop */
     }
 
     /* 7a. drop contained duplicates among ALL candidates of the same (a, b, strand):
