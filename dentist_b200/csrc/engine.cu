@@ -93,6 +93,7 @@ void block_build_index(DevBlock &A, int k, cudaStream_t s) {
     if (nA == 0) return;
     const bool wide = k > 15;
     DevBlock::Index &X = A.index;
+    int64_t nI = nA;
     if (!wide) {
         DBuf<u64> ta(nA), ta2(nA);
         emit_tuples(A, false, k, 0u, ta.p, s);
@@ -101,23 +102,25 @@ void block_build_index(DevBlock &A, int k, cudaStream_t s) {
         DN_CUDA(cudaMemcpyAsync(X.ta.p, sa, sizeof(u64) * nA, cudaMemcpyDeviceToDevice, s));
     } else {
         DBuf<ulonglong2> tw(nA), tw2(nA);
-        emit_tuples_wide(A, k, tw.p, s);
-        ulonglong2 *sw = radix_sort_rec16(tw.p, tw2.p, nA, 0, 0, 2 * k + 1, s);
-        X.tw.persistent(nA);
-        DN_CUDA(cudaMemcpyAsync(X.tw.p, sw, sizeof(ulonglong2) * nA, cudaMemcpyDeviceToDevice, s));
+        nI = emit_tuples_wide(A, k, tw.p, s);
+        ulonglong2 *sw = radix_sort_rec16(tw.p, tw2.p, nI, 0, 0, 2 * k, s);
+        X.tw.persistent(nI + 1);
+        if (nI) DN_CUDA(cudaMemcpyAsync(X.tw.p, sw, sizeof(ulonglong2) * nI, cudaMemcpyDeviceToDevice, s));
     }
-    X.tbits = index_tbits(nA, k, true);
+    X.n = nI;
+    X.tbits = index_tbits(nI, k, true);
     const int sh = 2 * k - X.tbits; const u32 nq = 1u << X.tbits;
     X.tbl.persistent((size_t)nq + 2);
-    X.kbits_log2 = kbits_log2_for(nA);
+    X.kbits_log2 = kbits_log2_for(nI);
     const int kshift = 32 - (X.kbits_log2 - 5);
     X.kbits.persistent((size_t)1 << (X.kbits_log2 - 5)); X.kbits.zero(s);
+    X.tbl.zero(s);                                           // an index without entries: every range is empty
     if (!wide) {
-        DN_LAUNCH(k_prefix_table, (unsigned)((nA + 255) / 256), 256, 0, s, (const u64 *)X.ta.p, nA, sh, nq, X.tbl.p);
-        DN_LAUNCH(k_kmer_bitmap, (unsigned)((nA + 255) / 256), 256, 0, s, (const u64 *)X.ta.p, nA, kshift, X.kbits.p);
-    } else {
-        DN_LAUNCH(k_prefix_table_w, (unsigned)((nA + 255) / 256), 256, 0, s, (const ulonglong2 *)X.tw.p, nA, sh, nq, X.tbl.p);
-        DN_LAUNCH(k_kmer_bitmap_w, (unsigned)((nA + 255) / 256), 256, 0, s, (const ulonglong2 *)X.tw.p, nA, kshift, X.kbits.p);
+        DN_LAUNCH(k_prefix_table, (unsigned)((nI + 255) / 256), 256, 0, s, (const u64 *)X.ta.p, nI, sh, nq, X.tbl.p);
+        DN_LAUNCH(k_kmer_bitmap, (unsigned)((nI + 255) / 256), 256, 0, s, (const u64 *)X.ta.p, nI, kshift, X.kbits.p);
+    } else if (nI > 0) {
+        DN_LAUNCH(k_prefix_table_w, (unsigned)((nI + 255) / 256), 256, 0, s, (const ulonglong2 *)X.tw.p, nI, sh, nq, X.tbl.p);
+        DN_LAUNCH(k_kmer_bitmap_w, (unsigned)((nI + 255) / 256), 256, 0, s, (const ulonglong2 *)X.tw.p, nI, kshift, X.kbits.p);
     }
     DN_CUDA(cudaStreamSynchronize(s));
     X.k = k; X.valid = true;
@@ -149,7 +152,8 @@ void align_blocks(const DevBlock &A, const DevBlock &B, const AlignParams &P, Ho
     DBuf<u64> ta, ta2; DBuf<ulonglong2> tw, tw2;
     u64 *sa = nullptr; ulonglong2 *sw = nullptr;
     const DevBlock::Index *cached = (A.index.valid && A.index.k == k && P.join_mode != 1) ? &A.index : nullptr;
-    if (cached) { sa = cached->ta.p; sw = cached->tw.p; }
+    int64_t nI = nA;                                       // index entries: k > 15 keeps the valid positions only
+    if (cached) { sa = cached->ta.p; sw = cached->tw.p; nI = cached->n; }
     else if (!wide) {
         ta.alloc(nA); ta2.alloc(nA);
         emit_tuples(A, false, k, 0u, ta.p, s);
@@ -157,13 +161,13 @@ void align_blocks(const DevBlock &A, const DevBlock &B, const AlignParams &P, Ho
         if (sa == ta.p) ta2.release(); else ta.release();
     } else {
         tw.alloc(nA); tw2.alloc(nA);
-        emit_tuples_wide(A, k, tw.p, s);
-        sw = radix_sort_rec16(tw.p, tw2.p, nA, 0, 0, 2 * k + 1, s);
+        nI = emit_tuples_wide(A, k, tw.p, s);
+        sw = radix_sort_rec16(tw.p, tw2.p, nI, 0, 0, 2 * k, s);
         if (sw == tw.p) tw2.release(); else tw.release();
     }
     tr.mark("A tuples + sort");
     const bool lookup = cached || wide || P.join_mode == 2 || (P.join_mode == 0 && nA * 8 <= (2ll << 30));   // auto: index lookup unless the A index is huge
-    const int npass_t = (2 * k + 1 + 7) / 8;
+    const int npass_t = (2 * k + (wide ? 0 : 1) + 7) / 8;
     out.stats.tuples_a = A.total_real; out.stats.tuples_b = 2 * B.total_real;
     int64_t abytes = nA / 4 + (wide ? 16 : 8) * nA + (int64_t)npass_t * (wide ? 48 : 24) * nA;      // A: read packed, write tuples, sort passes (2R+1W)
 
@@ -187,7 +191,7 @@ void align_blocks(const DevBlock &A, const DevBlock &B, const AlignParams &P, Ho
     const int aposbits = bits_for((uint64_t)A.maxlen);
     bool segsorted = false, seg_in_hits2 = false;
     // ---- K3: join ------------------------------------------------------------------------------
-    int tbits = index_tbits(nA, k, lookup);
+    int tbits = index_tbits(nI, k, lookup);
     if (cached) tbits = cached->tbits;
     const int sh = 2 * k - tbits; const u32 nq = 1u << tbits;
     DBuf<u32> tbl_own; const u32 *tblp;
@@ -195,7 +199,8 @@ void align_blocks(const DevBlock &A, const DevBlock &B, const AlignParams &P, Ho
     else {
         tbl_own.alloc((size_t)nq + 2); tblp = tbl_own.p;
         if (!wide) DN_LAUNCH(k_prefix_table, (unsigned)((nA + 255) / 256), 256, 0, s, (const u64 *)sa, nA, sh, nq, tbl_own.p);
-        else DN_LAUNCH(k_prefix_table_w, (unsigned)((nA + 255) / 256), 256, 0, s, (const ulonglong2 *)sw, nA, sh, nq, tbl_own.p);
+        else if (nI > 0) DN_LAUNCH(k_prefix_table_w, (unsigned)((nI + 255) / 256), 256, 0, s, (const ulonglong2 *)sw, nI, sh, nq, tbl_own.p);
+        else tbl_own.zero(s);                                // no valid k-mer in A: every range is empty
     }
     struct { const u32 *p; } tbl{tblp};
     DBuf<int64_t> dtotal(1);
@@ -208,11 +213,11 @@ void align_blocks(const DevBlock &A, const DevBlock &B, const AlignParams &P, Ho
         const int64_t nwB = nB >> 4;
         const int nseg = 2 * B.nreads;
         DBuf<u32> kbits_own; struct { const u32 *p; } kbits{cached ? cached->kbits.p : nullptr};
-        const int kblog = cached ? cached->kbits_log2 : kbits_log2_for(nA), kshift = 32 - (kblog - 5);
+        const int kblog = cached ? cached->kbits_log2 : kbits_log2_for(nI), kshift = 32 - (kblog - 5);
         if (!cached) {
             kbits_own.alloc((size_t)1 << (kblog - 5)); kbits_own.zero(s); kbits.p = kbits_own.p;
             if (!wide) DN_LAUNCH(k_kmer_bitmap, (unsigned)((nA + 255) / 256), 256, 0, s, (const u64 *)sa, nA, kshift, kbits_own.p);
-            else DN_LAUNCH(k_kmer_bitmap_w, (unsigned)((nA + 255) / 256), 256, 0, s, (const ulonglong2 *)sw, nA, kshift, kbits_own.p);
+            else if (nI > 0) DN_LAUNCH(k_kmer_bitmap_w, (unsigned)((nI + 255) / 256), 256, 0, s, (const ulonglong2 *)sw, nI, kshift, kbits_own.p);
         }
         // pin the k-mer filter in the persisting part of L2 while the streaming lookups run
         {

@@ -33,6 +33,7 @@ struct DevBlock {
     // align_blocks otherwise rebuilds for the A block on every call.  Invalidated when the seed mask changes.
     struct Index {
         int k = 0, tbits = 0, kbits_log2 = 27;
+        int64_t n = 0;                 // index entries (k > 15: valid positions only)
         DBuf<u64> ta; DBuf<ulonglong2> tw; DBuf<u32> tbl, kbits;
         bool valid = false;
         void drop() { ta.release(); tw.release(); tbl.release(); kbits.release(); valid = false; k = 0; }

@@ -234,34 +234,66 @@ __device__ __forceinline__ u64 wide_kmer(u64 v, u32 w2, int jj, u64 kmask) {
     return x & kmask;
 }
 
-__global__ void __launch_bounds__(256) k_tuples_wide(const u32 *__restrict__ seq, const u32 *__restrict__ maskbits,
-                                                     const int64_t *__restrict__ off, const int32_t *__restrict__ len,
-                                                     const int32_t *__restrict__ c2r, int64_t nwords, int k,
-                                                     ulonglong2 *__restrict__ out) {
-    int64_t wi = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (wi >= nwords) return;
+// Only positions that can start a k-mer become tuples (no sentinel entries to sort): pass 1 counts them per word,
+// pass 2 writes them behind the scanned offsets.  The sort key is then exactly the 2k k-mer bits.
+__device__ __forceinline__ u32 wide_valid_mask(const u32 *__restrict__ maskbits, const int64_t *__restrict__ off,
+                                               const int32_t *__restrict__ len, const int32_t *__restrict__ c2r, int64_t wi, int k) {
     const int64_t g0 = wi << 4;
     int r = c2r[g0 >> 10];
     while (off[r + 1] <= g0) r++;
     const int p0 = (int)(g0 - off[r]);
     const int L = len[r];
-    const u64 v = ((u64)seq[wi + 1] << 32) | seq[wi];
-    const u32 w2 = seq[wi + 2];
-    const u64 kmask = (1ull << (2 * k)) - 1ull, mk = (1ull << k) - 1ull;
+    const u64 mk = (1ull << k) - 1ull;
     u64 mwin = 0;
     if (maskbits) { int64_t mw = g0 >> 5; mwin = (((u64)maskbits[mw + 1] << 32) | maskbits[mw]) >> (g0 & 31); }
+    u32 valid = 0;
 #pragma unroll
-    for (int jj = 0; jj < 16; jj++) {
-        const bool valid = (p0 + jj + k <= L) && (((mwin >> jj) & mk) == 0);
-        out[g0 + jj] = make_ulonglong2(valid ? wide_kmer(v, w2, jj, kmask) : ~0ull, (u64)(u32)(g0 + jj));
+    for (int jj = 0; jj < 16; jj++)
+        if ((p0 + jj + k <= L) && (((mwin >> jj) & mk) == 0)) valid |= 1u << jj;
+    return valid;
+}
+
+__global__ void __launch_bounds__(256) k_tuples_wide_count(const u32 *__restrict__ maskbits, const int64_t *__restrict__ off,
+                                                           const int32_t *__restrict__ len, const int32_t *__restrict__ c2r,
+                                                           int64_t nwords, int k, u32 *__restrict__ cnt) {
+    int64_t wi = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (wi >= nwords) return;
+    cnt[wi] = (u32)__popc(wide_valid_mask(maskbits, off, len, c2r, wi, k));
+}
+
+__global__ void __launch_bounds__(256) k_tuples_wide(const u32 *__restrict__ seq, const u32 *__restrict__ maskbits,
+                                                     const int64_t *__restrict__ off, const int32_t *__restrict__ len,
+                                                     const int32_t *__restrict__ c2r, int64_t nwords, int k,
+                                                     const int64_t *__restrict__ woff, ulonglong2 *__restrict__ out) {
+    int64_t wi = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (wi >= nwords) return;
+    u32 valid = wide_valid_mask(maskbits, off, len, c2r, wi, k);
+    if (!valid) return;
+    const int64_t g0 = wi << 4;
+    const u64 v = ((u64)seq[wi + 1] << 32) | seq[wi];
+    const u32 w2 = seq[wi + 2];
+    const u64 kmask = (1ull << (2 * k)) - 1ull;
+    int64_t o = woff[wi];
+    while (valid) {
+        const int jj = __ffs(valid) - 1; valid &= valid - 1;
+        out[o++] = make_ulonglong2(wide_kmer(v, w2, jj, kmask), (u64)(u32)(g0 + jj));
     }
 }
 
-void emit_tuples_wide(const DevBlock &B, int k, ulonglong2 *out, cudaStream_t s) {
+// returns the number of tuples written (a host sync: the caller sizes the sort and the index with it)
+int64_t emit_tuples_wide(const DevBlock &B, int k, ulonglong2 *out, cudaStream_t s) {
     int64_t nwords = B.total >> 4;
-    if (nwords == 0) return;
-    DN_LAUNCH(k_tuples_wide, (unsigned)((nwords + 255) / 256), 256, 0, s, (const u32 *)B.fwd.p, B.has_mask ? (const u32 *)B.mask.p : nullptr,
-              (const int64_t *)B.off.p, (const int32_t *)B.len.p, (const int32_t *)B.chunk2read.p, nwords, k, out);
+    if (nwords == 0) return 0;
+    const u32 *mb = B.has_mask ? (const u32 *)B.mask.p : nullptr;
+    DBuf<u32> cnt(nwords); DBuf<int64_t> woff(nwords), tot(1);
+    DN_LAUNCH(k_tuples_wide_count, (unsigned)((nwords + 255) / 256), 256, 0, s, mb, (const int64_t *)B.off.p, (const int32_t *)B.len.p,
+              (const int32_t *)B.chunk2read.p, nwords, k, cnt.p);
+    exclusive_scan_u32_to_i64(cnt.p, woff.p, nwords, tot.p, s);
+    DN_LAUNCH(k_tuples_wide, (unsigned)((nwords + 255) / 256), 256, 0, s, (const u32 *)B.fwd.p, mb,
+              (const int64_t *)B.off.p, (const int32_t *)B.len.p, (const int32_t *)B.chunk2read.p, nwords, k, (const int64_t *)woff.p, out);
+    int64_t n = 0;
+    DN_CUDA(cudaMemcpyAsync(&n, tot.p, sizeof n, cudaMemcpyDeviceToHost, s)); DN_CUDA(cudaStreamSynchronize(s));
+    return n;
 }
 
 // ------------------------------------------------------------------------- K3: join

@@ -31,7 +31,7 @@ struct Cand {
 struct ExtOut { int32_t i_end, j_end, d_end, ntiles; };
 
 void emit_tuples(const DevBlock &B, bool rc, int k, u32 payload_base, u64 *out, cudaStream_t s);
-void emit_tuples_wide(const DevBlock &B, int k, ulonglong2 *out, cudaStream_t s);      // k = 16..31: {kmer, position} tuples of the forward strand
+int64_t emit_tuples_wide(const DevBlock &B, int k, ulonglong2 *out, cudaStream_t s);   // k = 16..31: {kmer, position} tuples of the valid forward positions; returns their number
 
 // kernels defined in seed.cu
 __global__ void k_prefix_table(const u64 *ta, int64_t na, int sh, u32 nq, u32 *tbl);

@@ -101,6 +101,11 @@ def test_long_kmers_use_the_wide_index_and_match_oracle(k):
     pile, _ = synth.simulate_reads(sc, 8, 6000, 1500, 0.08, 44)
     orc, gpu = run_both(pile, pile, 126, 500, self_block=1, k=k)
     assert_same(orc, gpu)
+    # an A block without a single valid k-mer (reads shorter than k): an empty index, no alignments, no crash
+    tiny = synth.Block(np.arange(0, 60, 15, dtype=np.int64), np.random.default_rng(3).integers(0, 4, 45).astype(np.uint8))
+    orc, gpu = run_both(tiny, reads, 100, 500, k=k)
+    assert len(orc[0]) == 0
+    assert_same(orc, gpu)
 
 
 @pytest.mark.parametrize("k", [14, 20])
