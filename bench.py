@@ -329,9 +329,10 @@ def main():
     for it in range(0 if args.profile else E2E_WARM + args.steps):
         barrier()
         t1 = time.perf_counter()
-        a2 = dazzler.Block(ref.off, bps=ref_bps, boff=ref_boff)
-        b2 = dazzler.Block(reads.off, bps=reads_bps, boff=reads_boff)
-        rec, toff, tr, st = dazzler.align_blocks(a2, b2, **PARAMS)
+        # dn_align_host: pinned host .bps in, host LAS out, one call (the reads' upload overlaps the assembly's indexing)
+        a2 = dazzler.HostBlock(ref.off, bps=ref_bps, boff=ref_boff)
+        b2 = dazzler.HostBlock(reads.off, bps=reads_bps, boff=reads_boff)
+        rec, toff, tr, st = dazzler.align_host(a2, b2, **PARAMS)
         if world > 1:
             tg = time.perf_counter()
             merged = sharding.gather_las(rec, tr, bread_offset, device=dev, tspace=PARAMS["tspace"], bounds=gather_bounds, root=0)
@@ -341,7 +342,6 @@ def main():
                 print("[bench] rank %d gather+merge %.2f ms" % (rank, (time.perf_counter() - tg) * 1e3), file=sys.stderr)
         barrier()
         dt = time.perf_counter() - t1
-        a2.free(); b2.free()
         if os.environ.get("BENCH_DEBUG"):
             print("[bench] e2e iter %d %.2f ms (align ms_total %.2f)" % (it, dt * 1e3, st["ms_total"]), file=sys.stderr)
         if it >= E2E_WARM:

@@ -3,6 +3,7 @@
 #include "api_internal.hpp"
 #include "dazzdb.hpp"
 #include <string.h>
+#include <memory>
 #include <stdlib.h>
 
 using namespace dn;
@@ -150,14 +151,27 @@ int dn_align_blocks(const dn_block *a, const dn_block *b, const dn_align_params 
 }
 
 int dn_align_host(const dn_block_desc *a, const dn_block_desc *b, const dn_align_params *p, dn_las_buf *out) {
-    dn_block *ba = nullptr, *bb = nullptr;
-    int rc = dn_block_upload(a, &ba);
-    if (rc) return rc;
-    const bool same = (a == b);
-    if (!same) { rc = dn_block_upload(b, &bb); if (rc) { dn_block_free(ba); return rc; } }
-    rc = dn_align_blocks(ba, same ? ba : bb, p, out);
-    dn_block_free(ba); if (!same) dn_block_free(bb);
-    return rc;
+    if (!a || !b || !out) return fail(DN_ERR_INVALID, "null argument");
+    std::lock_guard<std::mutex> lk(g_mu);
+    if (int rc = ensure_device()) return rc;
+    return guarded([&] {
+        cudaSetDevice(g_device);
+        static cudaStream_t copy_stream = nullptr;
+        if (!copy_stream) DN_CUDA(cudaStreamCreateWithFlags(&copy_stream, cudaStreamNonBlocking));
+        const bool same = (a == b);
+        std::unique_ptr<dn_block> ba(new dn_block()), bb(same ? nullptr : new dn_block());
+        // B's (large) host->device copy and packing run on the copy stream while A is uploaded and indexed on the
+        // engine's stream; align_blocks waits for B right before the join
+        if (!same) block_upload(*b, bb->b, copy_stream, true);
+        block_upload(*a, ba->b, g_stream);
+        AlignParams q = to_internal(p);
+        HostLas h;
+        try { align_blocks(ba->b, same ? ba->b : bb->b, q, h, g_stream); }
+        catch (...) { cudaStreamSynchronize(copy_stream); throw; }
+        cudaStreamSynchronize(copy_stream);
+        to_buf(h, q.tspace, out);
+        return DN_OK;
+    });
 }
 
 int dn_las_merge_device(const void *d_rec, int64_t nrec, const void *d_trace, int64_t ntrace, int32_t tspace, int64_t max_alen,

@@ -141,6 +141,7 @@ void align_blocks(const DevBlock &A, const DevBlock &B, const AlignParams &P, Ho
         out.rec = (dn_las_record *)hcache_alloc(64); out.toff = (int64_t *)hcache_alloc(64); out.trace = (uint16_t *)hcache_alloc(64);
         out.stats.ms_total = tt.stop(); return;
     }
+    if (A.ready) DN_CUDA(cudaStreamWaitEvent(s, A.ready, 0));
     const int k = P.k;
     const int64_t nA = A.total, nB = B.total;
     Trace tr(s);
@@ -190,6 +191,7 @@ void align_blocks(const DevBlock &A, const DevBlock &B, const AlignParams &P, Ho
 
     const int aposbits = bits_for((uint64_t)A.maxlen);
     bool segsorted = false, seg_in_hits2 = false;
+    if (B.ready) DN_CUDA(cudaStreamWaitEvent(s, B.ready, 0));       // B may still be uploading on the copy stream (dn_align_host)
     // ---- K3: join ------------------------------------------------------------------------------
     int tbits = index_tbits(nI, k, lookup);
     if (cached) tbits = cached->tbits;

@@ -82,7 +82,9 @@ void block_add_mask(DevBlock &B, const int64_t *anno_h, const int32_t *data_h, c
     DN_CUDA(cudaStreamSynchronize(s));
 }
 
-void block_upload(const dn_block_desc &d, DevBlock &B, cudaStream_t s) {
+// async = true: no host sync at the end; `B.ready` is recorded on `s` and the staging buffers stay with the block
+// (the caller keeps the host arrays alive and untouched until the block was consumed -- dn_align_host does)
+void block_upload(const dn_block_desc &d, DevBlock &B, cudaStream_t s, bool async) {
     if (d.nreads < 0 || (d.nreads > 0 && (!d.rlen || !d.boff || !d.data))) throw Error("dn_block_desc: null field");
     B.nreads = d.nreads;
     B.h_len.assign(d.rlen, d.rlen + d.nreads);
@@ -107,8 +109,8 @@ void block_upload(const dn_block_desc &d, DevBlock &B, cudaStream_t s) {
     DN_CUDA(cudaMemcpyAsync(B.off.p, B.h_off.data(), sizeof(int64_t) * (d.nreads + 1), cudaMemcpyHostToDevice, s));
     if (d.nreads == 0) { DN_CUDA(cudaStreamSynchronize(s)); return; }
     DN_CUDA(cudaMemcpyAsync(B.len.p, B.h_len.data(), sizeof(int32_t) * d.nreads, cudaMemcpyHostToDevice, s));
-    DBuf<uint8_t> raw; raw.persistent((size_t)d.data_bytes + 16);
-    DBuf<int64_t> boff; boff.persistent(d.nreads);
+    DBuf<uint8_t> &raw = B.up_raw; raw.persistent((size_t)d.data_bytes + 16);
+    DBuf<int64_t> &boff = B.up_boff; boff.persistent(d.nreads);
     DN_CUDA(cudaMemcpyAsync(raw.p, d.data, d.data_bytes, cudaMemcpyHostToDevice, s));
     DN_CUDA(cudaMemcpyAsync(boff.p, d.boff, sizeof(int64_t) * d.nreads, cudaMemcpyHostToDevice, s));
     DN_LAUNCH(k_pack, d.nreads, 128, 0, s, (const uint8_t *)raw.p, (const int64_t *)boff.p, (const int32_t *)B.len.p,
@@ -121,7 +123,13 @@ void block_upload(const dn_block_desc &d, DevBlock &B, cudaStream_t s) {
     }
     B.has_mask = false;
     if (d.mask_anno && d.mask_data) block_add_mask(B, d.mask_anno, d.mask_data, s);
+    if (async) {
+        if (!B.ready) DN_CUDA(cudaEventCreateWithFlags(&B.ready, cudaEventDisableTiming));
+        DN_CUDA(cudaEventRecord(B.ready, s));
+        return;
+    }
     DN_CUDA(cudaStreamSynchronize(s));
+    raw.release(); boff.release();
 }
 
 // ------------------------------------------------------------------------- crop

@@ -25,53 +25,67 @@ def launch_count():
     return int(_lib.lib().dn_launch_count())
 
 
+def _block_desc(off, bases=None, bps=None, boff=None, mask=None, group=None):
+    """dn_block_desc over caller-owned numpy arrays; returns (desc, arrays to keep alive, payload bytes)."""
+    off = np.ascontiguousarray(off, dtype=np.int64)
+    rlen = np.ascontiguousarray(np.diff(off), dtype=np.int32)
+    d = _lib.BlockDesc()
+    d.nreads = len(rlen)
+    keep = [rlen]
+    if bps is not None:
+        data = np.ascontiguousarray(bps, dtype=np.uint8)
+        bo = np.ascontiguousarray(boff, dtype=np.int64)
+        d.format = 1
+    else:
+        data = np.ascontiguousarray(bases, dtype=np.uint8)
+        bo = np.ascontiguousarray(off[:-1], dtype=np.int64)
+        d.format = 0
+    keep += [data, bo]
+    d.rlen = rlen.ctypes.data
+    d.boff = bo.ctypes.data
+    d.data = data.ctypes.data
+    d.data_bytes = data.nbytes
+    if mask is not None:   # list of per-read interval lists [(b, e), ...]
+        anno = np.zeros(len(rlen) + 1, np.int64)
+        flat = []
+        for r, iv in enumerate(mask):
+            anno[r] = 4 * len(flat)
+            for b, e in iv:
+                flat += [b, e]
+        anno[len(rlen)] = 4 * len(flat)
+        md = np.ascontiguousarray(flat if flat else [0, 0], dtype=np.int32)
+        keep += [anno, md]
+        d.mask_anno = anno.ctypes.data
+        d.mask_data = md.ctypes.data
+    if group is not None:  # pile id per read: only reads of the same pile are compared
+        grp = np.ascontiguousarray(group, dtype=np.int32)
+        assert len(grp) == len(rlen)
+        keep.append(grp)
+        d.group = grp.ctypes.data
+    return d, keep, int(data.nbytes + rlen.nbytes + bo.nbytes)
+
+
+class HostBlock:
+    """A sequence block still on the host (pinned or pageable numpy arrays): the input of `align_host`."""
+
+    def __init__(self, off, bases=None, bps=None, boff=None, mask=None, group=None):
+        self._desc, self._keep, self.h2d_bytes = _block_desc(off, bases, bps, boff, mask, group)
+        self.nreads = int(self._desc.nreads)
+
+
 class Block:
     """A sequence block resident in HBM (2-bit packed, both strands)."""
 
     def __init__(self, off, bases=None, bps=None, boff=None, mask=None, group=None):
         """Either `bases` (uint8 codes 0..3 concatenated, read r = bases[off[r]:off[r+1]]) or
         DAZZ_DB `.bps` bytes with per-read byte offsets `boff` and lengths diff(off)."""
-        off = np.ascontiguousarray(off, dtype=np.int64)
-        rlen = np.ascontiguousarray(np.diff(off), dtype=np.int32)
-        d = _lib.BlockDesc()
-        d.nreads = len(rlen)
-        keep = [rlen]
-        if bps is not None:
-            data = np.ascontiguousarray(bps, dtype=np.uint8)
-            bo = np.ascontiguousarray(boff, dtype=np.int64)
-            d.format = 1
-        else:
-            data = np.ascontiguousarray(bases, dtype=np.uint8)
-            bo = np.ascontiguousarray(off[:-1], dtype=np.int64)
-            d.format = 0
-        keep += [data, bo]
-        d.rlen = rlen.ctypes.data
-        d.boff = bo.ctypes.data
-        d.data = data.ctypes.data
-        d.data_bytes = data.nbytes
-        if mask is not None:   # list of per-read interval lists [(b, e), ...]
-            anno = np.zeros(len(rlen) + 1, np.int64)
-            flat = []
-            for r, iv in enumerate(mask):
-                anno[r] = 4 * len(flat)
-                for b, e in iv:
-                    flat += [b, e]
-            anno[len(rlen)] = 4 * len(flat)
-            md = np.ascontiguousarray(flat if flat else [0, 0], dtype=np.int32)
-            keep += [anno, md]
-            d.mask_anno = anno.ctypes.data
-            d.mask_data = md.ctypes.data
-        if group is not None:  # pile id per read: only reads of the same pile are compared
-            grp = np.ascontiguousarray(group, dtype=np.int32)
-            assert len(grp) == len(rlen)
-            keep.append(grp)
-            d.group = grp.ctypes.data
+        d, keep, nbytes = _block_desc(off, bases, bps, boff, mask, group)
         self._desc, self._keep = d, keep
         self._h = C.c_void_p()
         _lib.check(_lib.lib().dn_block_upload(C.byref(d), C.byref(self._h)))
         self.nreads = int(d.nreads)
         self.bases = int(_lib.lib().dn_block_bases(self._h))
-        self.h2d_bytes = int(data.nbytes + rlen.nbytes + bo.nbytes)
+        self.h2d_bytes = nbytes
         self.has_group = group is not None
 
     @classmethod
@@ -159,6 +173,16 @@ def _take(buf):
     tr = _wrap(buf.trace, int(buf.ntrace) * 2, np.uint16, owner)
     st = {n_: getattr(buf.stats, n_) for n_, _ in _lib.AlignStats._fields_}
     return rec, toff, tr, int(buf.tspace), st
+
+
+def align_host(a, b, **params):
+    """dn_align_host: host blocks in, host LAS out -- upload, alignment and download in ONE call; the upload of `b`
+    overlaps the upload and indexing of `a`.  Returns (records, trace offsets, trace, stats) like align_blocks."""
+    p = make_params(**params)
+    buf = _lib.LasBuf()
+    _lib.check(_lib.lib().dn_align_host(C.byref(a._desc), C.byref(b._desc), C.byref(p), C.byref(buf)))
+    rec, toff, tr, _, st = _take(buf)
+    return rec, toff, tr, st
 
 
 def align_blocks(a, b, **params):

@@ -286,6 +286,31 @@ def test_device_las_merge_equals_lasort_order():
     assert r2.tobytes() == rec.tobytes() and np.array_equal(t2, tr)
 
 
+def test_align_host_equals_resident_blocks():
+    """dn_align_host (overlapped upload of B on a copy stream) returns what upload + dn_align_blocks returns: byte and
+    .bps input, with masks, several calls in a row (recycled staging buffers)."""
+    from dentist_b200 import dazzler
+    ref, reads = small_case(71, cov=4)
+    want = dazzler.align_blocks(dazzler.Block(ref.off, ref.bases), dazzler.Block(reads.off, reads.bases), tspace=100, minlen=500, k=20)
+    assert len(want[0]) > 30
+    parts, boff, o = [], [], 0
+    for r in range(reads.nreads):
+        q = synth.pack_2bit_dazz(reads.read(r)); boff.append(o); parts.append(q); o += len(q)
+    bps, boff = np.concatenate(parts), np.array(boff, np.int64)
+    for _ in range(3):
+        got = dazzler.align_host(dazzler.HostBlock(ref.off, ref.bases), dazzler.HostBlock(reads.off, bps=bps, boff=boff), tspace=100, minlen=500, k=20)
+        assert got[0].tobytes() == want[0].tobytes() and got[2].tobytes() == want[2].tobytes()
+    amask = [[(0, 500)] for _ in range(ref.nreads)]; bmask = [[(100, 400)] for _ in range(reads.nreads)]
+    want = dazzler.align_blocks(dazzler.Block(ref.off, ref.bases, mask=amask), dazzler.Block(reads.off, reads.bases, mask=bmask), tspace=100, minlen=500)
+    got = dazzler.align_host(dazzler.HostBlock(ref.off, ref.bases, mask=amask), dazzler.HostBlock(reads.off, reads.bases, mask=bmask), tspace=100, minlen=500)
+    assert got[0].tobytes() == want[0].tobytes() and got[2].tobytes() == want[2].tobytes()
+    same = dazzler.HostBlock(reads.off, reads.bases)
+    self_host = dazzler.align_host(same, same, tspace=126, minlen=500, self_block=1)
+    g = dazzler.Block(reads.off, reads.bases)
+    self_dev = dazzler.align_blocks(g, g, tspace=126, minlen=500, self_block=1)
+    assert self_host[0].tobytes() == self_dev[0].tobytes()
+
+
 def test_concurrent_callers_get_the_serial_results():
     """DENTIST calls the boundary from std.parallelism worker threads (processPileUps/package.d:153): four host threads
     hammer the same library (align, filters, QVs, consensus) and must each see exactly what a serial run returns."""
