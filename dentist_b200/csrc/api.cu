@@ -4,6 +4,7 @@
 #include "dazzdb.hpp"
 #include <string.h>
 #include <memory>
+#include <chrono>
 #include <stdlib.h>
 
 using namespace dn;
@@ -160,16 +161,26 @@ int dn_align_host(const dn_block_desc *a, const dn_block_desc *b, const dn_align
         if (!copy_stream) DN_CUDA(cudaStreamCreateWithFlags(&copy_stream, cudaStreamNonBlocking));
         const bool same = (a == b);
         std::unique_ptr<dn_block> ba(new dn_block()), bb(same ? nullptr : new dn_block());
-        // B's (large) host->device copy and packing run on the copy stream while A is uploaded and indexed on the
-        // engine's stream; align_blocks waits for B right before the join
-        if (!same) block_upload(*b, bb->b, copy_stream, true);
+        // B's (large) host->device copy and packing run on the copy stream while A is indexed on the engine's stream;
+        // align_blocks waits for B right before the join
+        const bool trace = getenv("DN_TRACE") != nullptr;
+        auto now = [] { return std::chrono::steady_clock::now(); };
+        auto ms = [](std::chrono::steady_clock::time_point a, std::chrono::steady_clock::time_point b) { return std::chrono::duration<double, std::milli>(b - a).count(); };
+        // A first: both uploads share the host->device copy engine, and A's small copy must not queue behind B's
+        const auto t0 = now();
         block_upload(*a, ba->b, g_stream);
+        const auto t1 = now();
+        if (!same) block_upload(*b, bb->b, copy_stream, true);
+        const auto t2 = now();
         AlignParams q = to_internal(p);
         HostLas h;
         try { align_blocks(ba->b, same ? ba->b : bb->b, q, h, g_stream); }
         catch (...) { cudaStreamSynchronize(copy_stream); throw; }
+        const auto t3 = now();
         cudaStreamSynchronize(copy_stream);
         to_buf(h, q.tspace, out);
+        if (trace) fprintf(stderr, "[dn trace] align_host: A upload %.3f ms, B upload (host side) %.3f ms, align %.3f ms (device %.3f), tail %.3f ms\n",
+                           ms(t0, t1), ms(t1, t2), ms(t2, t3), h.stats.ms_total, ms(t3, now()));
         return DN_OK;
     });
 }
