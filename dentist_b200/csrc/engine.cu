@@ -117,10 +117,10 @@ void block_build_index(DevBlock &A, int k, cudaStream_t s) {
     X.tbl.zero(s);                                           // an index without entries: every range is empty
     if (!wide) {
         DN_LAUNCH(k_prefix_table, (unsigned)((nI + 255) / 256), 256, 0, s, (const u64 *)X.ta.p, nI, sh, nq, X.tbl.p);
-        DN_LAUNCH(k_kmer_bitmap, (unsigned)((nI + 255) / 256), 256, 0, s, (const u64 *)X.ta.p, nI, kshift, X.kbits.p);
+        DN_LAUNCH(k_kmer_bitmap, (unsigned)((nI + 255) / 256), 256, 0, s, (const u64 *)X.ta.p, nI, k, kshift, X.kbits.p);
     } else if (nI > 0) {
         DN_LAUNCH(k_prefix_table_w, (unsigned)((nI + 255) / 256), 256, 0, s, (const ulonglong2 *)X.tw.p, nI, sh, nq, X.tbl.p);
-        DN_LAUNCH(k_kmer_bitmap_w, (unsigned)((nI + 255) / 256), 256, 0, s, (const ulonglong2 *)X.tw.p, nI, kshift, X.kbits.p);
+        DN_LAUNCH(k_kmer_bitmap_w, (unsigned)((nI + 255) / 256), 256, 0, s, (const ulonglong2 *)X.tw.p, nI, k, kshift, X.kbits.p);
     }
     DN_CUDA(cudaStreamSynchronize(s));
     X.k = k; X.valid = true;
@@ -218,8 +218,8 @@ void align_blocks(const DevBlock &A, const DevBlock &B, const AlignParams &P, Ho
         const int kblog = cached ? cached->kbits_log2 : kbits_log2_for(nI), kshift = 32 - (kblog - 5);
         if (!cached) {
             kbits_own.alloc((size_t)1 << (kblog - 5)); kbits_own.zero(s); kbits.p = kbits_own.p;
-            if (!wide) DN_LAUNCH(k_kmer_bitmap, (unsigned)((nA + 255) / 256), 256, 0, s, (const u64 *)sa, nA, kshift, kbits_own.p);
-            else if (nI > 0) DN_LAUNCH(k_kmer_bitmap_w, (unsigned)((nI + 255) / 256), 256, 0, s, (const ulonglong2 *)sw, nI, kshift, kbits_own.p);
+            if (!wide) DN_LAUNCH(k_kmer_bitmap, (unsigned)((nA + 255) / 256), 256, 0, s, (const u64 *)sa, nA, k, kshift, kbits_own.p);
+            else if (nI > 0) DN_LAUNCH(k_kmer_bitmap_w, (unsigned)((nI + 255) / 256), 256, 0, s, (const ulonglong2 *)sw, nI, k, kshift, kbits_own.p);
         }
         // pin the k-mer filter in the persisting part of L2 while the streaming lookups run
         {
@@ -237,16 +237,18 @@ void align_blocks(const DevBlock &A, const DevBlock &B, const AlignParams &P, Ho
         {
             DBuf<u32> wcnt(2 * nwB), wlist(2 * nwB), nlist(2); DBuf<int64_t> woff(2 * nwB);
             nlist.zero(s); DBuf<unsigned short> hitmask(2 * nwB);
-            for (int st = 0; st < 2; st++) {
-                const u32 *mb = B.has_mask ? (st ? B.mask_rc.p : B.mask.p) : nullptr;
+            {   // one sweep over the forward words counts both strands; the complement strand's words collect by atomics
+                DN_CUDA(cudaMemsetAsync(wcnt.p + nwB, 0, sizeof(u32) * nwB, s));
+                DN_CUDA(cudaMemsetAsync(hitmask.p + nwB, 0, sizeof(unsigned short) * nwB, s));
+                const u32 *mb = B.has_mask ? B.mask.p : nullptr;
                 if (!wide)
-                    DN_LAUNCH(k_lookup_count, (unsigned)((nwB + 255) / 256), 256, 0, s, (const u32 *)(st ? B.rc.p : B.fwd.p), mb,
+                    DN_LAUNCH(k_lookup_count, (unsigned)((nwB + 255) / 256), 256, 0, s, (const u32 *)B.fwd.p, mb,
                               (const int64_t *)B.off.p, (const int32_t *)B.len.p, (const int32_t *)B.chunk2read.p, nwB, k,
-                              (const u64 *)sa, (const u32 *)tbl.p, sh, P.t, (const u32 *)kbits.p, kshift, JG, wcnt.p + st * nwB, hitmask.p + st * nwB, wlist.p + st * nwB, nlist.p + st);
+                              (const u64 *)sa, (const u32 *)tbl.p, sh, P.t, (const u32 *)kbits.p, kshift, JG, wcnt.p, hitmask.p, wlist.p, nlist.p);
                 else
-                    DN_LAUNCH(k_lookup_count_w, (unsigned)((nwB + 255) / 256), 256, 0, s, (const u32 *)(st ? B.rc.p : B.fwd.p), mb,
+                    DN_LAUNCH(k_lookup_count_w, (unsigned)((nwB + 255) / 256), 256, 0, s, (const u32 *)B.fwd.p, mb,
                               (const int64_t *)B.off.p, (const int32_t *)B.len.p, (const int32_t *)B.chunk2read.p, nwB, k,
-                              (const ulonglong2 *)sw, (const u32 *)tbl.p, sh, P.t, (const u32 *)kbits.p, kshift, JG, wcnt.p + st * nwB, hitmask.p + st * nwB, wlist.p + st * nwB, nlist.p + st);
+                              (const ulonglong2 *)sw, (const u32 *)tbl.p, sh, P.t, (const u32 *)kbits.p, kshift, JG, wcnt.p, hitmask.p, wlist.p, nlist.p);
             }
             exclusive_scan_u32_to_i64(wcnt.p, woff.p, 2 * nwB, dtotal.p, s);
             H = d2h_scalar(dtotal.p, s);

@@ -430,21 +430,40 @@ __device__ __forceinline__ void kbit_slot(u32 km, int kshift, u32 &word, u32 &ma
     mask = (1u << (h >> 27)) | (1u << ((h >> 22) & 31u)) | (1u << ((h >> 17) & 31u));
 }
 
+// reverse complement of a k-mer value (bases LSB first, 2 bits each, complement = 3 - base = ~base)
+__device__ __forceinline__ u32 rc_kmer(u32 x, int k) {
+    u32 r = __brev(x);
+    r = ((r >> 1) & 0x55555555u) | ((r & 0x55555555u) << 1);
+    return (~r) >> (32 - 2 * k);
+}
+__device__ __forceinline__ u64 rc_kmer(u64 x, int k) {
+    u64 r = __brevll(x);
+    r = ((r >> 1) & 0x5555555555555555ull) | ((r & 0x5555555555555555ull) << 1);
+    return (~r) >> (64 - 2 * k);
+}
+// One filter word serves both strands: the WORD is chosen by the canonical k-mer min(x, rc(x)), the three bits inside it
+// by the k-mer as it stands.  A probe of B position p then answers "is x in A?" (forward strand) and "is rc(x) in A?"
+// (complement strand, position L-k-p) with a single 32-byte sector instead of two.
+__device__ __forceinline__ u32 kbit_mask(u32 f) {
+    const u32 h = f * 0x85EBCA6Bu;
+    return (1u << (h >> 27)) | (1u << ((h >> 22) & 31u)) | (1u << ((h >> 17) & 31u));
+}
+
 template <class IDX>
-__device__ __forceinline__ void kmer_bitmap_body(IDX ta, int64_t na, int kshift, u32 *__restrict__ bits) {
+__device__ __forceinline__ void kmer_bitmap_body(IDX ta, int64_t na, int k, int kshift, u32 *__restrict__ bits) {
     int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= na) return;
     const typename IDX::key_t km = ta.key(i);
     if (IDX::invalid(km)) return;
     if (i > 0 && ta.key(i - 1) == km) return;                    // one atomic per distinct k-mer
-    u32 word, mask; kbit_slot(IDX::fold(km), kshift, word, mask);
-    atomicOr(&bits[word], mask);
+    const typename IDX::key_t y = rc_kmer(km, k), c = km < y ? km : y;
+    atomicOr(&bits[(IDX::fold(c) * 0x9E3779B1u) >> kshift], kbit_mask(IDX::fold(km)));
 }
-__global__ void __launch_bounds__(256) k_kmer_bitmap(const u64 *__restrict__ ta, int64_t na, int kshift, u32 *__restrict__ bits) {
-    kmer_bitmap_body(Idx32{ta}, na, kshift, bits);
+__global__ void __launch_bounds__(256) k_kmer_bitmap(const u64 *__restrict__ ta, int64_t na, int k, int kshift, u32 *__restrict__ bits) {
+    kmer_bitmap_body(Idx32{ta}, na, k, kshift, bits);
 }
-__global__ void __launch_bounds__(256) k_kmer_bitmap_w(const ulonglong2 *__restrict__ ta, int64_t na, int kshift, u32 *__restrict__ bits) {
-    kmer_bitmap_body(Idx64{ta}, na, kshift, bits);
+__global__ void __launch_bounds__(256) k_kmer_bitmap_w(const ulonglong2 *__restrict__ ta, int64_t na, int k, int kshift, u32 *__restrict__ bits) {
+    kmer_bitmap_body(Idx64{ta}, na, k, kshift, bits);
 }
 __device__ __forceinline__ bool kmer_present(const u32 *__restrict__ bits, int kshift, u32 km) {
     u32 word, mask; kbit_slot(km, kshift, word, mask);
@@ -484,10 +503,13 @@ __device__ __forceinline__ void a_range_fwd(IDX ta, const u32 *__restrict__ tbl,
     while (a < hi && ta.key(a) == km) { a++; if (++c > (u32)tcap) { c = 0; break; } }
 }
 
-// Count pass.  Phase 1: every thread probes the k-mer filter for the 16 positions of its word (dense, 16 loads in flight).
-// Phase 2: the positions that passed (about 1 in 15) are dealt out evenly over the lanes of the warp, so the index walks
-// -- dependent, mostly DRAM-missing loads -- run with all lanes busy instead of whichever threads happen to own a
-// candidate (ncu before: 17.7 live threads per warp, 595 M warp instructions per launch).
+// Count pass, BOTH strands in one sweep over the forward words.  Phase 1: every thread probes the k-mer filter once per
+// position (16 loads in flight); the word answers for the k-mer x (forward strand, position p) and for rc(x) (complement
+// strand, position L-k-p).  Phase 2: the candidates (about 1 in 8 probes) are dealt out evenly over the lanes of the warp,
+// so the index walks -- dependent, mostly DRAM-missing loads -- run with all lanes busy.  Forward-strand counts collect in
+// shared memory (the word belongs to this warp), complement-strand counts go to their word of the mirrored numbering with
+// global atomics (wcnt / hitmask of strand 1 start zeroed).  ncu before: one launch per strand, 340 M L2 sectors each,
+// L2-sector bound.
 template <class IDX>
 __device__ __forceinline__ void lookup_count_body(const u32 *__restrict__ seq, const u32 *__restrict__ maskbits,
                                                   const int64_t *__restrict__ off, const int32_t *__restrict__ len,
@@ -496,6 +518,7 @@ __device__ __forceinline__ void lookup_count_body(const u32 *__restrict__ seq, c
                                                   const u32 *__restrict__ kbits, int kshift, const JoinGeom &G, u32 *__restrict__ wcnt,
                                                   unsigned short *__restrict__ hitmask,
                                                   u32 *__restrict__ wlist, u32 *__restrict__ nlist) {
+    typedef typename IDX::key_t key_t;
     __shared__ u32 s_total[8][32], s_hm[8][32];
     const u32 FULL = 0xffffffffu;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -504,13 +527,18 @@ __device__ __forceinline__ void lookup_count_body(const u32 *__restrict__ seq, c
     const u64 kmask = (1ull << (2 * k)) - 1ull, mk = (1ull << k) - 1ull;
     const bool restricted = G.self || G.a_group;
     WordKmers w; w.v = 0; w.mwin = 0; w.w2 = 0; w.p0 = 0; w.L = 0; w.r = 0;
-    u32 present = 0;
+    u32 present = 0;                                  // bit jj: forward strand, bit 16 + jj: complement strand
     if (inrange) {
         w = load_word<IDX::wide>(seq, maskbits, off, len, c2r, wi);
 #pragma unroll
         for (int jj = 0; jj < 16; jj++)
-            if ((w.p0 + jj + k <= w.L) && (((w.mwin >> jj) & mk) == 0) && kmer_present(kbits, kshift, IDX::fold(kmer_at<IDX>(w, jj, kmask))))
-                present |= 1u << jj;
+            if ((w.p0 + jj + k <= w.L) && (((w.mwin >> jj) & mk) == 0)) {
+                const key_t x = kmer_at<IDX>(w, jj, kmask), y = rc_kmer(x, k), c = x < y ? x : y;
+                const u32 W = kbits[(IDX::fold(c) * 0x9E3779B1u) >> kshift];
+                const u32 mx = kbit_mask(IDX::fold(x)), my = kbit_mask(IDX::fold(y));
+                if ((W & mx) == mx) present |= 1u << jj;
+                if ((W & my) == my) present |= 1u << (16 + jj);
+            }
     }
     s_total[warp][lane] = 0; s_hm[warp][lane] = 0;
     const int cnt = __popc(present);
@@ -519,6 +547,7 @@ __device__ __forceinline__ void lookup_count_body(const u32 *__restrict__ seq, c
     for (int o = 1; o < 32; o <<= 1) { const int t = __shfl_up_sync(FULL, inc, o); if (lane >= o) inc += t; }
     const int E = inc - cnt, T = __shfl_sync(FULL, inc, 31);
     __syncwarp();
+    u32 *wcnt1 = wcnt + nwords; u32 *hm1 = reinterpret_cast<u32 *>(hitmask + nwords);       // strand 1 arrays (nwords is even)
     for (int base = 0; base < T; base += 32) {
         const int q = base + lane;
         int owner = 0;                                   // last lane whose exclusive prefix is <= q
@@ -534,9 +563,12 @@ __device__ __forceinline__ void lookup_count_body(const u32 *__restrict__ seq, c
         o.v = ((u64)__shfl_sync(FULL, (u32)(w.v >> 32), owner) << 32) | __shfl_sync(FULL, (u32)w.v, owner);
         o.w2 = __shfl_sync(FULL, w.w2, owner);
         o.r = __shfl_sync(FULL, w.r, owner);
+        o.p0 = __shfl_sync(FULL, w.p0, owner);
+        o.L = __shfl_sync(FULL, w.L, owner);
         if (q < T) {
-            const int jj = __fns(pm, 0, q - Eo + 1);
-            const typename IDX::key_t km = kmer_at<IDX>(o, jj, kmask);
+            const int b = __fns(pm, 0, q - Eo + 1), jj = b & 15, strand = b >> 4;
+            key_t km = kmer_at<IDX>(o, jj, kmask);
+            if (strand) km = rc_kmer(km, k);
             u32 s, c; a_range_fwd(ta, tbl, sh, km, tcap, s, c);
             u32 add = c;
             if (restricted) {                     // self pairs / pairs across pile-ups are never emitted
@@ -546,7 +578,17 @@ __device__ __forceinline__ void lookup_count_body(const u32 *__restrict__ seq, c
                     add += pair_ok(G, ar, o.r) ? 1u : 0u;
                 }
             }
-            if (add) { atomicAdd(&s_total[warp][owner], add); atomicOr(&s_hm[warp][owner], 1u << jj); }
+            if (add) {
+                if (!strand) { atomicAdd(&s_total[warp][owner], add); atomicOr(&s_hm[warp][owner], 1u << jj); }
+                else {
+                    // the same k-mer seen from the complement strand: position L - k - p of the mirrored read
+                    const int64_t g1 = off[o.r] + (o.L - k - (o.p0 + jj));
+                    const int64_t w1 = g1 >> 4;
+                    const u32 old = atomicAdd(&wcnt1[w1], add);
+                    atomicOr(&hm1[w1 >> 1], (1u << (int)(g1 & 15)) << ((w1 & 1) ? 16 : 0));
+                    if (old == 0) wlist[nwords + atomicAdd(nlist + 1, 1u)] = (u32)w1;
+                }
+            }
         }
     }
     __syncwarp();
