@@ -400,7 +400,7 @@ def main():
                "e2e": {"value": e2e, "unit": "Gbp/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h)},
                "gpu_launches": int(launches),
                "clocks": summarize_clocks(clk),
-               "roofline": {"kernel": "k_extend32 (O(ND) wave extension, 45% of device time)", "bound": "hbm", "achieved": ext_gbs, "peak": peak,
+               "roofline": {"kernel": "k_extend32 (O(ND) wave extension, 48% of device time)", "bound": "hbm", "achieved": ext_gbs, "peak": peak,
                             "unit": "GB/s", "frac": ext_gbs / peak,
                             "traffic": 98.5e6 / 3, "traffic_source": "ncu dram__bytes_read+write of the round-0 launch (72.1 + 26.5 MB, profiles/r01_prof_extend32_r1i_details.txt) averaged over the 3 launches of a step",
                             "peak_source": peak_src,
