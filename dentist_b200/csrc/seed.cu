@@ -419,16 +419,9 @@ __global__ void __launch_bounds__(256) k_join_emit(const u64 *__restrict__ ta, c
 // in the A index and (pass 1) counts / (pass 2) emits the hits.  Output-identical to the
 // sorted-merge join because the hit list is totally ordered by the sort that follows.
 
-// Presence bitmap over k-mers (bit = kmer mod 2^28; exact for k <= 14): 32 MB, L2-resident.  Four out of
-// five read k-mers carry a sequencing error and occur nowhere in A; the bitmap rejects them with ONE
-// sector read instead of the table + list walk.
-// blocked Bloom filter: one 32-bit word per k-mer (multiplicative hash), three bits inside it (second hash):
-// a probe touches ONE sector; 2^27 bits = 16 MB for ~1 % false positives at 10 M distinct k-mers
-__device__ __forceinline__ void kbit_slot(u32 km, int kshift, u32 &word, u32 &mask) {      // kshift = 32 - (log2(filter bits) - 5)
-    word = (km * 0x9E3779B1u) >> kshift;
-    const u32 h = km * 0x85EBCA6Bu;
-    mask = (1u << (h >> 27)) | (1u << ((h >> 22) & 31u)) | (1u << ((h >> 17) & 31u));
-}
+// k-mer presence filter (blocked Bloom: one 32-bit word per k-mer, three bits inside it; >= 12 bits per indexed position,
+// 16 MB and pinned in L2 for a 10 Mbp block).  Most read k-mers carry a sequencing error and occur nowhere in A; the filter
+// rejects them with ONE sector read instead of the table + list walk.
 
 // reverse complement of a k-mer value (bases LSB first, 2 bits each, complement = 3 - base = ~base)
 __device__ __forceinline__ u32 rc_kmer(u32 x, int k) {
@@ -464,10 +457,6 @@ __global__ void __launch_bounds__(256) k_kmer_bitmap(const u64 *__restrict__ ta,
 }
 __global__ void __launch_bounds__(256) k_kmer_bitmap_w(const ulonglong2 *__restrict__ ta, int64_t na, int k, int kshift, u32 *__restrict__ bits) {
     kmer_bitmap_body(Idx64{ta}, na, k, kshift, bits);
-}
-__device__ __forceinline__ bool kmer_present(const u32 *__restrict__ bits, int kshift, u32 km) {
-    u32 word, mask; kbit_slot(km, kshift, word, mask);
-    return (bits[word] & mask) == mask;
 }
 
 struct WordKmers { u64 v; u64 mwin; u32 w2; int p0, L, r; };
