@@ -168,7 +168,7 @@ int dn_align_host(const dn_block_desc *a, const dn_block_desc *b, const dn_align
         auto ms = [](std::chrono::steady_clock::time_point a, std::chrono::steady_clock::time_point b) { return std::chrono::duration<double, std::milli>(b - a).count(); };
         // A first: both uploads share the host->device copy engine, and A's small copy must not queue behind B's
         const auto t0 = now();
-        block_upload(*a, ba->b, g_stream);
+        block_upload(*a, ba->b, g_stream, true);             // no host sync: the alignment follows on the same stream
         const auto t1 = now();
         if (!same) block_upload(*b, bb->b, copy_stream, true);
         const auto t2 = now();
