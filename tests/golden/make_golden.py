@@ -102,11 +102,25 @@ def main():
                    changes=[[int(x) for x in m] for m in re.findall(r"CoverageChange\((\d+),\s*(\d+),\s*(\d+),\s*(\d+)\)", txt)])
     with open(os.path.join(HERE, "maskcov_kat.json"), "w") as f:
         json.dump(maskcov, f)
+    # AlignmentChain.opCmp KAT  common/alignments/base.d:780-857: two lists that must come out strictly ascending
+    bd2 = "\n".join(lines(os.path.join(REF, "common/alignments/base.d"), 780, 857))
+    order_kat = []
+    for blk in bd2.split("auto acs = [")[1:]:
+        blk = blk[:blk.index("];")]
+        la_default = [[0, 1], [0, 1]]
+        chains_ = []
+        for m in re.finditer(r"AlignmentChain\((\d+), Contig\((\d+), \d+\), Contig\((\d+), \d+\), Flags\(\), \[(.*?)\]\)", blk, re.S):
+            las_ = re.findall(r"LocalAlignment\(Locus\((\d+), (\d+)\), Locus\((\d+), (\d+)\), \d+\)", m.group(4))
+            las_ = [[int(x) for x in t] for t in las_] or [[0, 1, 0, 1]]
+            chains_.append(dict(id=int(m.group(1)), contigA=int(m.group(2)), contigB=int(m.group(3)), las=las_))
+        order_kat.append(chains_)
+    with open(os.path.join(HERE, "chain_order_kat.json"), "w") as f:
+        json.dump(order_kat, f)
     out = dict(source="a-ludi/dentist @ 1aa60e04", tspace=100, ladump=dump, flat=flat, chains=chains, trace_kat=kat)
     with open(os.path.join(HERE, "las_golden.json"), "w") as f:
         json.dump(out, f, indent=1)
     print("flat", len(flat), "chains", len(chains), "dump lines", len(dump), "kat tiles", len(kat["trace"]), "asserts", len(kat["asserts"]),
-          "cropper cases", len(cases), "consensus reads", len(cons["reads"]), "maskcov", len(maskcov["alignments"]), len(maskcov["contigs"]), len(maskcov["mask"]), len(maskcov["changes"]))
+          "cropper cases", len(cases), "consensus reads", len(cons["reads"]), "chain order lists", [len(x) for x in order_kat], "maskcov", len(maskcov["alignments"]), len(maskcov["contigs"]), len(maskcov["mask"]), len(maskcov["changes"]))
 
 
 if __name__ == "__main__":

@@ -109,3 +109,23 @@ def test_insertion_alignment_on_reference_insertions():
             process.insertion_alignment([shifted] + [dict(c) for c in chains[1:]], ref_read, positions, 100)
         n += 1
     assert n >= 10
+
+
+def test_chain_order_follows_the_reference_kat():
+    """AlignmentChain.opCmp (base.d:766-777) on the reference's two ordered lists (base.d:780-857): the key used for
+    splitAlignmentsByContigA / filterContainedAlignmentChains here and for the accepted chains in oracle/chaining.py."""
+    import itertools
+    from oracle import chaining
+    lists = json.load(open(os.path.join(HERE, "golden", "chain_order_kat.json")))
+    assert [len(x) for x in lists] == [4, 7]
+    for chains in lists:
+        sas = [dict(contigA=(c["contigA"], 10), contigB=(c["contigB"], 10),
+                    las=[dict(ab=l[0], ae=l[1], bb=l[2], be=l[3]) for l in c["las"]]) for c in chains]
+        keys = [process._chain_key(sa) for sa in sas]
+        assert keys == sorted(keys) and len(set(keys)) == len(keys)                     # strictly ascending as listed
+        for perm in itertools.islice(itertools.permutations(range(len(sas))), 50):
+            assert [i for i in sorted(perm, key=lambda i: keys[i])] == list(range(len(sas)))
+        # the chaining oracle orders accepted chains of one (A, B) group by the same coordinates
+        if len({(c["contigA"], c["contigB"]) for c in chains}) == 1:
+            ck = [(s["las"][0]["ab"], s["las"][0]["bb"], s["las"][-1]["ae"], s["las"][-1]["be"]) for s in sas]
+            assert ck == sorted(ck)
