@@ -106,6 +106,35 @@ def adjust_repeat_mask(mask, contigs, ref_positions, seeds, min_anchor_length):
     return out
 
 
+def seeds_from(chain):
+    """SeededAlignment.from (base.d:2002-2014): a chain seeds the contig's FRONT when the read sticks out beyond the
+    contig begin (first.contigB.begin > first.contigA.begin, isFrontExtension :2030-2036), its BACK when the read sticks
+    out beyond the contig end (:2042-2048); both are possible.  Returns the seeded alignment dicts in (front, back) order."""
+    first, last = chain["las"][0], chain["las"][-1]
+    out = []
+    if first["bb"] > first["ab"]:
+        out.append(dict(chain, seed="front"))
+    if chain["contigB"][1] - last["be"] > chain["contigA"][1] - last["ae"]:
+        out.append(dict(chain, seed="back"))
+    return out
+
+
+def is_extension(ra):                                                                # base.d:2226-2230
+    return len(ra) == 1
+
+
+def is_in_order(ra):                                                                 # base.d:2170-2173
+    return not _is_gap(ra) or ra[0]["contigA"][0] < ra[1]["contigA"][0]
+
+
+def is_valid(ra):                                                                    # base.d:2190-2193
+    return is_extension(ra) != _is_gap(ra)
+
+
+def is_anti_parallel(ra):                                                            # base.d:2314-2322
+    return _is_gap(ra) and ra[0]["seed"] == ra[1]["seed"] and (ra[0]["flags"] & 1) != (ra[1]["flags"] & 1)
+
+
 def _is_gap(ra):
     return len(ra) == 2 and ra[0]["contigA"][0] != ra[1]["contigA"][0] and ra[0]["contigB"][0] == ra[1]["contigB"][0]
 

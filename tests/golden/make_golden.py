@@ -116,11 +116,27 @@ def main():
         order_kat.append(chains_)
     with open(os.path.join(HERE, "chain_order_kat.json"), "w") as f:
         json.dump(order_kat, f)
+    # ReadAlignment typing KAT  common/alignments/base.d:2324-2676: chains (seeds derived by SeededAlignment.from in the test)
+    # and the expectation string per case: isInOrder isValid type isExtension isFront isBack isGap isParallel isAntiParallel
+    src = lines(os.path.join(REF, "common/alignments/base.d"), 2329, 2604)
+    body = "\n".join(ln for ln in src if not ln.strip().startswith("//"))
+    body = body[body.index("["):].replace("SeededAlignment.from(", "SAfrom(")
+    body = "{" + body[1:body.rindex("]")] + "}"
+    class _Front(dict):
+        front = property(lambda self: dict(self))
+    ns = dict(__builtins__={}, complement=1, Contig=lambda a, b: [a, b], Locus=lambda a, b: [a, b], Flags=lambda *f: sum(f),
+              LocalAlignment=lambda a, b, d: dict(ab=a[0], ae=a[1], bb=b[0], be=b[1], diffs=d),
+              AlignmentChain=lambda i, a, b, f, l: _Front(id=i, contigA=a, contigB=b, flags=f, las=l),
+              SAfrom=lambda c: c, ReadAlignment=lambda *s: list(s))
+    typing_data = eval(body, ns)
+    exp = dict(re.findall(r'"(\w+)":\s+"([+.FBG]{9})"', "\n".join(lines(os.path.join(REF, "common/alignments/base.d"), 2616, 2627))))
+    with open(os.path.join(HERE, "read_alignment_kat.json"), "w") as f:
+        json.dump(dict(cases=typing_data, expect=exp), f)
     out = dict(source="a-ludi/dentist @ 1aa60e04", tspace=100, ladump=dump, flat=flat, chains=chains, trace_kat=kat)
     with open(os.path.join(HERE, "las_golden.json"), "w") as f:
         json.dump(out, f, indent=1)
     print("flat", len(flat), "chains", len(chains), "dump lines", len(dump), "kat tiles", len(kat["trace"]), "asserts", len(kat["asserts"]),
-          "cropper cases", len(cases), "consensus reads", len(cons["reads"]), "chain order lists", [len(x) for x in order_kat], "maskcov", len(maskcov["alignments"]), len(maskcov["contigs"]), len(maskcov["mask"]), len(maskcov["changes"]))
+          "cropper cases", len(cases), "consensus reads", len(cons["reads"]), "typing cases", len(typing_data), len(exp), "chain order lists", [len(x) for x in order_kat], "maskcov", len(maskcov["alignments"]), len(maskcov["contigs"]), len(maskcov["mask"]), len(maskcov["changes"]))
 
 
 if __name__ == "__main__":

@@ -129,3 +129,30 @@ def test_chain_order_follows_the_reference_kat():
         if len({(c["contigA"], c["contigB"]) for c in chains}) == 1:
             ck = [(s["las"][0]["ab"], s["las"][0]["bb"], s["las"][-1]["ae"], s["las"][-1]["be"]) for s in sas]
             assert ck == sorted(ck)
+
+
+def test_read_alignment_typing_follows_the_reference_kat():
+    """SeededAlignment.from + ReadAlignment.{isInOrder, isValid, type, isExtension, isFrontExtension, isBackExtension, isGap,
+    isParallel, isAntiParallel} on the reference's eight cases (base.d:2324-2676)."""
+    kat = json.load(open(os.path.join(HERE, "golden", "read_alignment_kat.json")))
+    assert len(kat["cases"]) == 8
+    for name, chains in kat["cases"].items():
+        ra = []
+        for c in chains:
+            chain = dict(id=c["id"], contigA=tuple(c["contigA"]), contigB=tuple(c["contigB"]), flags=c["flags"], tpd=100, las=c["las"])
+            ra.append(process.seeds_from(chain)[0])                                   # `.front` of the filtered range
+        e = kat["expect"][name]
+        got = [process.is_in_order(ra), process.is_valid(ra), None, process.is_extension(ra),
+               len(ra) == 1 and ra[0]["seed"] == "front", len(ra) == 1 and ra[0]["seed"] == "back",
+               process._is_gap(ra), process._is_parallel(ra), process.is_anti_parallel(ra)]
+        for i, ch in enumerate(e):
+            if i == 2:
+                assert {"F": "front", "B": "back", "G": "gap"}[ch] == process._type(ra), name
+            else:
+                assert got[i] == (ch == "+"), (name, i)
+        start, end = process.make_join(ra)                                            # makeJoin, base.d:2680-2721
+        if process._is_gap(ra):
+            part = lambda s: "begin" if s == "front" else "end"
+            assert (start, end) == ((ra[0]["contigA"][0], part(ra[0]["seed"])), (ra[1]["contigA"][0], part(ra[1]["seed"])))
+        else:
+            assert start[0] == end[0] == ra[0]["contigA"][0]
