@@ -33,13 +33,10 @@ def _build_pileups(las, alen, blen, kept, n_gaps, allowance=100):
             j += 1
         sub = slice(int(i), j)
         a, b = int(rec[i]["aread"]), int(rec[i]["bread"])
-        at_end = int(rec[j - 1]["aepos"]) + allowance >= alen[a]
-        at_begin = int(rec[i]["abpos"]) <= allowance
-        for seed, ok in (("back", at_end), ("front", at_begin)):
-            if ok:
-                sa = binio.seeded_alignments_from_las(rec[sub], toff[sub], trace, alen, blen, 100, lambda f, l, s=seed: s)[0]
-                sa["id"] = int(i)
-                chains.setdefault((a, seed), {})[b] = sa
+        chain = binio.seeded_alignments_from_las(rec[sub], toff[sub], trace, alen, blen, 100, lambda f, l: "front")[0]
+        chain["id"] = int(i)
+        for sa in process.seeds_from(chain):                       # SeededAlignment.from, base.d:2002-2014
+            chains.setdefault((a, sa["seed"]), {})[b] = sa
     piles = []
     for g in range(n_gaps):
         back, front = chains.get((g, "back"), {}), chains.get((g + 1, "front"), {})
