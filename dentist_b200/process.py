@@ -119,6 +119,37 @@ def seeds_from(chain):
     return out
 
 
+def collect_read_alignments(chains):
+    """collectReadAlignments (commands/collectPileUps/pileups.d:821-888): all alignment chains of ONE read -> its read
+    alignments.  Every chain is seeded (seeds_from), the seeded alignments are ordered along the read (forward read
+    coordinates, then seed), no region of the read may be used by two different chains, and consecutive seeded
+    alignments pair up into gaps -- starting with a lone extension when the first one does not begin at the read's begin.
+    Returns (read alignments, reason): an empty list comes with the reference's reason string."""
+    def begin_b(sa):
+        return sa["contigB"][1] - sa["las"][-1]["be"] if sa["flags"] & FLAG_COMPLEMENT else sa["las"][0]["bb"]
+
+    def end_b(sa):
+        return sa["contigB"][1] - sa["las"][0]["bb"] if sa["flags"] & FLAG_COMPLEMENT else sa["las"][-1]["be"]
+
+    def seed_b(sa):
+        v = 0 if sa["seed"] == "front" else 1
+        return -v if sa["flags"] & FLAG_COMPLEMENT else v
+
+    seeded = [sa for c in chains for sa in seeds_from(c)]
+    seeded.sort(key=lambda sa: (begin_b(sa), end_b(sa), seed_b(sa)))
+    if not seeded:
+        return [], "empty input"
+    for x, y in zip(seeded, seeded[1:]):
+        same_chain = x["id"] == y["id"] and x["contigA"] == y["contigA"] and x["seed"] != y["seed"]
+        if end_b(x) > begin_b(y) and not same_chain:
+            return [], "alignments overlap on read"
+    start = 1 if begin_b(seeded[0]) > 0 else 0
+    ras = ([seeded[0:1]] if start else []) + [seeded[i:i + 2] for i in range(start, len(seeded), 2)]
+    if any(not is_valid(ra) for ra in ras):
+        return [], "invalid read alignment"
+    return ras, None
+
+
 def is_extension(ra):                                                                # base.d:2226-2230
     return len(ra) == 1
 

@@ -132,11 +132,27 @@ def main():
     exp = dict(re.findall(r'"(\w+)":\s+"([+.FBG]{9})"', "\n".join(lines(os.path.join(REF, "common/alignments/base.d"), 2616, 2627))))
     with open(os.path.join(HERE, "read_alignment_kat.json"), "w") as f:
         json.dump(dict(cases=typing_data, expect=exp), f)
+    # collectReadAlignments KAT  commands/collectPileUps/pileups.d:890-1098: five cases (chains of one read -> read alignments)
+    pu = "\n".join(lines(os.path.join(REF, "commands/collectPileUps/pileups.d"), 890, 1098))
+    cra = []
+    for blk in pu.split("auto alignmentChains = [")[1:]:
+        head, tail = blk.split("];", 1)
+        chains_ = []
+        for m in re.finditer(r"AlignmentChain\(\s*(\d+),\s*Contig\((\d+), (\d+)\),\s*Contig\((\d+), (\d+)\),\s*AlignmentFlags\((\w*)\),\s*"
+                             r"\[LocalAlignment\(\s*Locus\((\d+), (\d+)\),\s*Locus\((\d+), (\d+)\),\s*\)\]", head, re.S):
+            g = m.groups()
+            chains_.append(dict(id=int(g[0]), contigA=[int(g[1]), int(g[2])], contigB=[int(g[3]), int(g[4])], flags=1 if g[5] == "complement" else 0,
+                                las=[dict(ab=int(g[6]), ae=int(g[7]), bb=int(g[8]), be=int(g[9]), diffs=0)]))
+        expect_ = [[[int(i), sd] for i, sd in re.findall(r"SeededAlignment\(alignmentChains\[(\d+)\], Seed\.(\w+)\)", ra)]
+                   for ra in re.findall(r"ReadAlignment\(\[(.*?)\]\)", tail, re.S)]
+        cra.append(dict(chains=chains_, expect=expect_))
+    with open(os.path.join(HERE, "collect_read_alignments_kat.json"), "w") as f:
+        json.dump(cra, f)
     out = dict(source="a-ludi/dentist @ 1aa60e04", tspace=100, ladump=dump, flat=flat, chains=chains, trace_kat=kat)
     with open(os.path.join(HERE, "las_golden.json"), "w") as f:
         json.dump(out, f, indent=1)
     print("flat", len(flat), "chains", len(chains), "dump lines", len(dump), "kat tiles", len(kat["trace"]), "asserts", len(kat["asserts"]),
-          "cropper cases", len(cases), "consensus reads", len(cons["reads"]), "typing cases", len(typing_data), len(exp), "chain order lists", [len(x) for x in order_kat], "maskcov", len(maskcov["alignments"]), len(maskcov["contigs"]), len(maskcov["mask"]), len(maskcov["changes"]))
+          "cropper cases", len(cases), "consensus reads", len(cons["reads"]), "collectReadAlignments cases", [(len(c["chains"]), len(c["expect"])) for c in cra], "typing cases", len(typing_data), len(exp), "chain order lists", [len(x) for x in order_kat], "maskcov", len(maskcov["alignments"]), len(maskcov["contigs"]), len(maskcov["mask"]), len(maskcov["changes"]))
 
 
 if __name__ == "__main__":

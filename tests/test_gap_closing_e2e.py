@@ -22,32 +22,35 @@ def _identity(a, b):
     return 1.0 - prev[-1] / max(len(a), len(b))
 
 
-def _build_pileups(las, alen, blen, kept, n_gaps, allowance=100):
-    """Pile-up membership for the synthetic layout (contig g | gap g | contig g+1): reads whose kept chain ends at the
-    end of contig g and/or starts at the begin of contig g+1."""
+def _build_pileups(las, alen, blen, kept, n_gaps):
+    """`dentist collect` in miniature: the kept chains of every read become read alignments (collectReadAlignments,
+    collectPileUps/pileups.d:821-888, with SeededAlignment.from seeds); read alignments with the same join -- gap
+    (contig g end, contig g+1 begin) or an extension into that gap from either side -- form one pile-up (what bundling
+    the scaffold graph's edges does, pileups.d:650-666)."""
     rec, toff, trace = las.rec, las.toff, las.trace
-    chains = {}
+    by_read = {}
     for i in kept:
         j = i + 1
         while j < len(rec) and (int(rec[j]["flags"]) & 0x8):
             j += 1
         sub = slice(int(i), j)
-        a, b = int(rec[i]["aread"]), int(rec[i]["bread"])
         chain = binio.seeded_alignments_from_las(rec[sub], toff[sub], trace, alen, blen, 100, lambda f, l: "front")[0]
-        chain["id"] = int(i)
-        for sa in process.seeds_from(chain):                       # SeededAlignment.from, base.d:2002-2014
-            chains.setdefault((a, sa["seed"]), {})[b] = sa
-    piles = []
-    for g in range(n_gaps):
-        back, front = chains.get((g, "back"), {}), chains.get((g + 1, "front"), {})
-        pile = []
-        for b in sorted(set(back) | set(front)):
-            if b in back and b in front:
-                if (back[b]["flags"] & 1) == (front[b]["flags"] & 1):
-                    pile.append([back[b], front[b]])
-            elif b in back:
-                pile.append([back[b]])
-        piles.append(pile)
+        chain.pop("seed"); chain["id"] = int(i)
+        by_read.setdefault(int(rec[i]["bread"]), []).append(chain)
+    piles = [[] for _ in range(n_gaps)]
+    for b in sorted(by_read):
+        ras, reason = process.collect_read_alignments(by_read[b])
+        for ra in ras:
+            if process._is_gap(ra) and not process.is_in_order(ra):
+                ra = [ra[1], ra[0]]                                   # ReadAlignment.getInOrder, base.d:2177-2183
+            start, end = process.make_join(ra)
+            if process._is_gap(ra):
+                if start[1] == "end" and end[1] == "begin" and end[0] == start[0] + 1 and process._is_parallel(ra):
+                    piles[start[0] - 1].append(ra)
+            elif ra[0]["seed"] == "back" and ra[0]["contigA"][0] <= n_gaps:
+                piles[ra[0]["contigA"][0] - 1].append(ra)             # extends contig g beyond its end, into gap g
+            elif ra[0]["seed"] == "front" and ra[0]["contigA"][0] >= 2:
+                piles[ra[0]["contigA"][0] - 2].append(ra)             # extends contig g+1 beyond its begin, into gap g
     return piles
 
 
@@ -63,6 +66,7 @@ def test_collect_process_output_round_trip(tmp_path):
     las.chainMapper(reads.nreads)
     first, st, used = dazzler.collectFilter(las, alen, blen, max_alignment_error=0.3, proper_alignment_allowance=100, min_anchor_length=500)
     piles = _build_pileups(las, alen, blen, first[st == 0], len(gaps[0]))
+    assert sum(len(ra) == 2 for p in piles for ra in p) >= 6 * len(piles)
     assert all(len(p) >= 6 for p in piles) and any(len(ra) == 1 for p in piles for ra in p)
     db = str(tmp_path / "pileups.db")
     binio.write_pileup_db(db, piles)

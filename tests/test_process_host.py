@@ -156,3 +156,21 @@ def test_read_alignment_typing_follows_the_reference_kat():
             assert (start, end) == ((ra[0]["contigA"][0], part(ra[0]["seed"])), (ra[1]["contigA"][0], part(ra[1]["seed"])))
         else:
             assert start[0] == end[0] == ra[0]["contigA"][0]
+
+
+def test_collect_read_alignments_follows_the_reference_kat():
+    """collectReadAlignments (collectPileUps/pileups.d:821-888) on the reference's five cases (:890-1098)."""
+    cases = json.load(open(os.path.join(HERE, "golden", "collect_read_alignments_kat.json")))
+    assert len(cases) == 5
+    for c in cases:
+        chains = [dict(id=x["id"], contigA=tuple(x["contigA"]), contigB=tuple(x["contigB"]), flags=x["flags"], tpd=100, las=x["las"])
+                  for x in c["chains"]]
+        ras, reason = process.collect_read_alignments(chains)
+        assert reason is None
+        got = [[[chains.index({k: v for k, v in sa.items() if k != "seed"}), sa["seed"]] for sa in ra] for ra in ras]
+        assert got == c["expect"]
+    # two chains that use the same stretch of the read: the read is not touched at all
+    a = dict(id=0, contigA=(1, 20), contigB=(1, 60), flags=0, tpd=100, las=[dict(ab=10, ae=20, bb=0, be=10, diffs=0)])
+    b = dict(id=1, contigA=(2, 20), contigB=(1, 60), flags=0, tpd=100, las=[dict(ab=0, ae=20, bb=5, be=25, diffs=0)])
+    assert process.collect_read_alignments([a, b]) == ([], "alignments overlap on read")
+    assert process.collect_read_alignments([]) == ([], "empty input")
