@@ -437,7 +437,7 @@ void align_blocks(const DevBlock &A, const DevBlock &B, const AlignParams &P, Ho
         exclusive_scan_u32_to_i64(ntl.p, toff.p, nseeds, dtotal.p, s);
         const int32_t nvalid = d2h_scalar(dtot32.p, s);              // both scans are queued: one drain serves the two reads
         const int64_t ntr = d2h_scalar(dtotal.p, s);
-        if (nvalid == 0) {                                            // a round that keeps nothing ends the loop (spec item 7)
+        if (nvalid == 0) {                                            // no group kept anything: every group is finished (spec item 7)
             if (getenv("DN_TRACE")) fprintf(stderr, "[dn trace] round %d: %lld hits, %d bands, %d seeds, no candidate >= minlen: stop\n", round, (long long)n, nbands, nseeds);
             break;
         }

@@ -438,7 +438,7 @@ __global__ void __launch_bounds__(256) k_retire(const ulonglong2 *__restrict__ h
     // a hit in a cold band can never become part of a hot band later (scores only shrink): drop it for good.
     // Pure optimisation -- the later rounds see exactly the clusters they would have seen anyway.
     if (kp && !hot[bflag[i] ? bidx[i] : bidx[i] - 1]) kp = 0;
-    if (kp && nrc > 0) {
+    if (kp) {
         ulonglong2 h = hits[i];
         u64 gd = h.x & ((1ull << G.gdbits) - 1ull);
         int bs = (int)(h.x >> G.gdbits);
@@ -446,7 +446,11 @@ __global__ void __launch_bounds__(256) k_retire(const ulonglong2 *__restrict__ h
         while (hi - lo > 1) { int mid = (lo + hi) >> 1; if ((u64)G.a_dbase[mid] <= gd) lo = mid; else hi = mid; }
         const int a = lo, apos = (int)(u32)h.y, bpos = (int)(h.y >> 32), diag = apos - bpos;
         const u64 key = gkey(bs, a);
-        for (int x = group_lower(rc, 0, nrc, key); x < nrc && gkey(rc[x].bs, rc[x].a) == key; x++) {
+        int x = group_lower(rc, 0, nrc, key);
+        // the rounds are counted per (bread, strand, aread) group (spec item 7): a group that kept no alignment in this
+        // round is finished, whatever the other groups of the block do -- all its hits go
+        if (x >= nrc || gkey(rc[x].bs, rc[x].a) != key) kp = 0;
+        for (; kp && x < nrc && gkey(rc[x].bs, rc[x].a) == key; x++) {
             const Cand c = rc[x];
             if (apos >= c.ab && apos <= c.ae && diag >= c.dmin - (1 << w) && diag <= c.dmax + (1 << w)) { kp = 0; break; }
         }

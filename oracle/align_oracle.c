@@ -40,8 +40,11 @@
  *      coordinate) it records (B offset, diffs so far); tiles are differences of records.
  *   7. an alignment is kept when (aepos-abpos)+(bepos-bbpos) >= 2*minlen; contained
  *      duplicates are dropped; hits covered by a kept alignment are retired and the whole
- *      select/extend step repeats on the remaining hits for up to `rounds` rounds; a round that
- *      keeps no alignment ends the loop (its clusters would only be retried one hit poorer).
+ *      select/extend step repeats on the remaining hits for up to `rounds` rounds.  The rounds are
+ *      counted per (bread, strand, aread) group: a group whose round selects no seed or keeps no
+ *      alignment is finished (its clusters would only be retried one hit poorer), whatever the other
+ *      groups of the block do -- so the output for a read never depends on the reads it shares a
+ *      block with (shard invariance, tests/test_gpu_parity.py::test_shard_invariance).
  *   8. output order = LAsort order (aread, bread, comp, abpos, aepos, bbpos, bepos, diffs)
  *      = FlatLocalAlignment.opCmp, base.d:1787-1809.
  */
@@ -49,6 +52,7 @@
 #include <stdlib.h>
 #include <string.h>
 #include <stdio.h>
+#include <pthread.h>
 
 typedef struct {
     int32_t k;        /* k-mer length (<= 31)                       */
@@ -91,22 +95,6 @@ typedef struct {
 /* ---------------------------------------------------------------- helpers */
 
 typedef struct { uint64_t kmer; int32_t read; int32_t pos; int32_t strand; } tup_t;
-typedef struct { int32_t bs; int32_t a; int32_t diag; int32_t apos; int32_t bpos; int32_t free_; } hit_t;
-
-static int cmp_tup(const void *x, const void *y) {
-    const tup_t *a = x, *b = y;
-    if (a->kmer != b->kmer) return a->kmer < b->kmer ? -1 : 1;
-    if (a->read != b->read) return a->read < b->read ? -1 : 1;
-    if (a->strand != b->strand) return a->strand < b->strand ? -1 : 1;
-    return (a->pos > b->pos) - (a->pos < b->pos);
-}
-static int cmp_hit(const void *x, const void *y) {
-    const hit_t *a = x, *b = y;
-    if (a->bs != b->bs) return a->bs < b->bs ? -1 : 1;
-    if (a->a != b->a) return a->a < b->a ? -1 : 1;
-    if (a->diag != b->diag) return a->diag < b->diag ? -1 : 1;
-    return (a->apos > b->apos) - (a->apos < b->apos);
-}
 static int cmp_la(const void *x, const void *y) {
     const orc_la *a = x, *b = y;
 #define C_(f) if (a->f != b->f) return a->f < b->f ? -1 : 1;
@@ -129,20 +117,17 @@ static uint8_t *revcomp_block(const orc_block *B) {
 
 static int64_t emit_tuples(const orc_block *B, const uint8_t *seq, int strand, int k, tup_t *out) {
     int64_t n = 0;
+    const uint64_t kmask = k < 32 ? (((uint64_t)1 << (2 * k)) - 1) : ~(uint64_t)0;
     for (int r = 0; r < B->nreads; r++) {
         int64_t o = B->off[r]; int len = (int)(B->off[r + 1] - o);
-        for (int p = 0; p + k <= len; p++) {
-            uint64_t km = 0; int ok = 1;
-            for (int i = 0; i < k; i++) {
-                km = (km << 2) | seq[o + p + i];
-                if (B->mask) {
-                    /* mask is given in forward coordinates */
-                    int64_t f = strand ? (o + len - 1 - (p + i)) : (o + p + i);
-                    if (B->mask[f]) ok = 0;
-                }
-            }
-            if (!ok) continue;
-            if (out) { out[n].kmer = km; out[n].read = r; out[n].pos = p; out[n].strand = strand; }
+        uint64_t km = 0; int valid = 0;                  /* valid = consecutive unmasked bases ending at q */
+        for (int q = 0; q < len; q++) {
+            km = ((km << 2) | seq[o + q]) & kmask;
+            int masked = 0;
+            if (B->mask) { int64_t f = strand ? (o + len - 1 - q) : (o + q); masked = B->mask[f]; }   /* mask is given in forward coordinates */
+            valid = masked ? 0 : valid + 1;
+            if (valid < k) continue;                     /* also covers q + 1 < k */
+            if (out) { out[n].kmer = km; out[n].read = r; out[n].pos = q + 1 - k; out[n].strand = strand; }
             n++;
         }
     }
@@ -288,133 +273,172 @@ typedef struct {
     orc_la la; int32_t dmin, dmax; int32_t *bb; int32_t *df;
 } cand_t;
 
-int orc_align(const orc_block *A, const orc_block *B, const orc_params *P, orc_result *R)
+typedef struct { cand_t *c; int64_t n, cap; } candvec_t;
+
+static void cv_push(candvec_t *v, const cand_t *c) {
+    if (v->n == v->cap) { v->cap = v->cap ? 2 * v->cap : 256; v->c = realloc(v->c, sizeof(cand_t) * v->cap); }
+    v->c[v->n++] = *c;
+}
+
+/* The sorted A index: tuples ordered by (kmer, read, pos) -- emitted in (read, pos) order and radix sorted
+ * stably by k-mer -- plus a direct-address table over the top `tb` k-mer bits.  Built once per call and shared,
+ * read-only, by the threads that each map their own B reads. */
+typedef struct { tup_t *t; int64_t n; int64_t *tbl; int tb, sh; } aindex_t;
+
+/* stable LSD byte radix sort of t[0..n) on k-mer bits [0, bits); tmp holds n tuples */
+static void radix_sort_tuples(tup_t *t, tup_t *tmp, int64_t n, int bits) {
+    tup_t *src = t, *dst = tmp;
+    for (int lo = 0; lo < bits; lo += 8) {
+        int64_t cnt[257]; memset(cnt, 0, sizeof cnt);
+        for (int64_t i = 0; i < n; i++) cnt[((src[i].kmer >> lo) & 255) + 1]++;
+        for (int d = 0; d < 256; d++) cnt[d + 1] += cnt[d];
+        for (int64_t i = 0; i < n; i++) dst[cnt[(src[i].kmer >> lo) & 255]++] = src[i];
+        tup_t *x = src; src = dst; dst = x;
+    }
+    if (src != t) memcpy(t, src, sizeof(tup_t) * n);
+}
+
+typedef struct { tup_t *t, *tmp; const int64_t *beg; int nb, bits; volatile int next; } sortjob_t;
+static void *sort_worker(void *arg) {
+    sortjob_t *J = arg;
+    for (;;) {
+        const int b = __sync_fetch_and_add(&J->next, 1);
+        if (b >= J->nb) break;
+        radix_sort_tuples(J->t + J->beg[b], J->tmp + J->beg[b], J->beg[b + 1] - J->beg[b], J->bits);
+    }
+    return NULL;
+}
+
+/* One stable MSD split on the top k-mer bits (sequential: keeps the (read, pos) emission order inside every
+ * bucket), then the buckets are LSD-sorted independently by the host threads. */
+static void build_index(const orc_block *A, int k, aindex_t *X, int nthreads) {
+    X->n = emit_tuples(A, A->bases, 0, k, NULL);
+    tup_t *raw = malloc(sizeof(tup_t) * (X->n + 1));
+    X->t = malloc(sizeof(tup_t) * (X->n + 1));
+    emit_tuples(A, A->bases, 0, k, raw);
+    const int top = 2 * k < 8 ? 2 * k : 8, low = 2 * k - top, nb = 1 << top;
+    int64_t beg[257]; memset(beg, 0, sizeof beg);
+    for (int64_t i = 0; i < X->n; i++) beg[(raw[i].kmer >> low) + 1]++;
+    for (int d = 0; d < nb; d++) beg[d + 1] += beg[d];
+    { int64_t at[256]; memcpy(at, beg, sizeof(int64_t) * nb);
+      for (int64_t i = 0; i < X->n; i++) X->t[at[raw[i].kmer >> low]++] = raw[i]; }
+    sortjob_t J; J.t = X->t; J.tmp = raw; J.beg = beg; J.nb = nb; J.bits = low; J.next = 0;
+    pthread_t th[256]; if (nthreads > 256) nthreads = 256;
+    for (int t = 1; t < nthreads; t++) pthread_create(&th[t], NULL, sort_worker, &J);
+    sort_worker(&J);
+    for (int t = 1; t < nthreads; t++) pthread_join(th[t], NULL);
+    free(raw);
+    X->tb = 2 * k < 24 ? 2 * k : 24; X->sh = 2 * k - X->tb;
+    int64_t nq = (int64_t)1 << X->tb;
+    X->tbl = malloc(sizeof(int64_t) * (nq + 1));
+    int64_t i = 0;
+    for (int64_t q = 0; q <= nq; q++) {
+        while (i < X->n && (int64_t)(X->t[i].kmer >> X->sh) < q) i++;
+        X->tbl[q] = i;
+    }
+}
+
+/* [s, e) = entries of the index with this k-mer */
+static void index_range(const aindex_t *X, uint64_t km, int64_t *s, int64_t *e) {
+    int64_t lo = X->tbl[km >> X->sh], hi = X->tbl[(km >> X->sh) + 1], a = lo, b = hi;
+    while (a < b) { int64_t m = (a + b) >> 1; if (X->t[m].kmer < km) a = m + 1; else b = m; }
+    *s = a;
+    while (a < hi && X->t[a].kmer == km) a++;
+    *e = a;
+}
+
+typedef struct { int32_t a, diag, apos, bpos; } ghit_t;      /* hit inside one (bread, strand) segment */
+static int cmp_ghit(const void *x, const void *y) {
+    const ghit_t *a = x, *b = y;
+    if (a->a != b->a) return a->a < b->a ? -1 : 1;
+    if (a->diag != b->diag) return a->diag < b->diag ? -1 : 1;
+    return (a->apos > b->apos) - (a->apos < b->apos);
+}
+
+/* per-thread work buffers of the extension */
+typedef struct {
+    int *Vb, *Tb; int span; int32_t *fbb, *fdf, *rbb, *rdf; rec_t *pool;
+    ghit_t *hits; int64_t caph; seed_t *S; int64_t capS;
+    int64_t *bfirst; int32_t *bkey, *bsc; uint8_t *hot; int64_t capb;
+    int64_t nhits, nseeds, next;
+} work_t;
+
+/* Steps 4-7 for ONE (bread, strand, aread) group: its hits H[0..nh) sorted by (diag, apos).  The rounds of a
+ * group end when a round selects no seed or keeps no alignment -- the rule is evaluated per group, so a read's
+ * output never depends on which other reads share its block (shard invariance). */
+static void process_group(const orc_block *A, const orc_block *B, const uint8_t *Arc, const uint8_t *Brc, const orc_params *P,
+                          work_t *W, ghit_t *H, int64_t nh, int a, int br, int st, candvec_t *out)
 {
     const int k = P->k, ts = P->tspace;
-    memset(R, 0, sizeof *R);
-    uint8_t *Arc = revcomp_block(A), *Brc = revcomp_block(B);
-
-    /* 1. tuples */
-    int64_t nta = emit_tuples(A, A->bases, 0, k, NULL);
-    int64_t ntb = emit_tuples(B, B->bases, 0, k, NULL) + emit_tuples(B, Brc, 1, k, NULL);
-    tup_t *TA = malloc(sizeof(tup_t) * (nta + 1)), *TB = malloc(sizeof(tup_t) * (ntb + 1));
-    emit_tuples(A, A->bases, 0, k, TA);
-    { int64_t n0 = emit_tuples(B, B->bases, 0, k, TB); emit_tuples(B, Brc, 1, k, TB + n0); }
-    qsort(TA, nta, sizeof(tup_t), cmp_tup);
-    qsort(TB, ntb, sizeof(tup_t), cmp_tup);
-
-    /* 2+3. merge -> hits */
-    int64_t nh = 0, caph = 1 << 16;
-    hit_t *H = malloc(sizeof(hit_t) * caph);
-    for (int64_t ia = 0, ib = 0; ia < nta && ib < ntb;) {
-        if (TA[ia].kmer < TB[ib].kmer) { ia++; continue; }
-        if (TA[ia].kmer > TB[ib].kmer) { ib++; continue; }
-        int64_t ea = ia, eb = ib; uint64_t km = TA[ia].kmer;
-        while (ea < nta && TA[ea].kmer == km) ea++;
-        while (eb < ntb && TB[eb].kmer == km) eb++;
-        if (ea - ia <= P->t) {
-            for (int64_t x = ia; x < ea; x++) for (int64_t y = ib; y < eb; y++) {
-                if (P->self && TA[x].read == TB[y].read) continue;
-                if (A->group && B->group && A->group[TA[x].read] != B->group[TB[y].read]) continue;
-                if (nh == caph) { caph *= 2; H = realloc(H, sizeof(hit_t) * caph); }
-                hit_t *q = &H[nh++];
-                q->a = TA[x].read; q->bs = TB[y].read * 2 + TB[y].strand;
-                q->apos = TA[x].pos; q->bpos = TB[y].pos; q->diag = TA[x].pos - TB[y].pos; q->free_ = 1;
-            }
-        }
-        ia = ea; ib = eb;
+    const int la = (int)(A->off[a + 1] - A->off[a]), lb = (int)(B->off[br + 1] - B->off[br]);
+    const uint8_t *af = A->bases + A->off[a], *ar = Arc + A->off[a];
+    const uint8_t *bf = (st ? Brc : B->bases) + B->off[br], *brv = (st ? B->bases : Brc) + B->off[br];
+    const int64_t first_cand = out->n;
+    if (nh + 1 > W->capb) {
+        W->capb = 2 * (nh + 1);
+        W->bfirst = realloc(W->bfirst, sizeof(int64_t) * (W->capb + 1)); W->bkey = realloc(W->bkey, sizeof(int32_t) * W->capb);
+        W->bsc = realloc(W->bsc, sizeof(int32_t) * W->capb); W->hot = realloc(W->hot, W->capb + 1);
     }
-    free(TA); free(TB);
-    qsort(H, nh, sizeof(hit_t), cmp_hit);
-    R->nhits = nh;
-
-    /* work buffers for the extension */
-    int maxlenA = 1, maxlenB = 1;
-    for (int r = 0; r < A->nreads; r++) { int l = (int)(A->off[r + 1] - A->off[r]); if (l > maxlenA) maxlenA = l; }
-    for (int r = 0; r < B->nreads; r++) { int l = (int)(B->off[r + 1] - B->off[r]); if (l > maxlenB) maxlenB = l; }
-    int span = maxlenA + maxlenB + 4;
-    int *Vb = malloc(sizeof(int) * 2 * (2 * span + 3)), *Tb = malloc(sizeof(int) * 2 * (2 * span + 3));
-    int maxtiles = maxlenA / ts + 3;
-    int32_t *fbb = malloc(sizeof(int32_t) * maxtiles * 4);
-    int32_t *fdf = fbb + maxtiles, *rbb = fdf + maxtiles, *rdf = rbb + maxtiles;
-    rec_t *pool = malloc(sizeof(rec_t) * (size_t)P->poolmul * (maxtiles + 6));
-
-    int64_t ncand = 0, capc = 1024;
-    cand_t *Cn = malloc(sizeof(cand_t) * capc);       /* kept alignments (all rounds) */
-
-    for (int round = 0; round < P->rounds; round++) {
-        /* 4. band filter over the free hits (H stays sorted; retired hits are removed) */
-        int64_t nseeds = 0; seed_t *S = malloc(sizeof(seed_t) * (nh + 1));
-        int64_t g0 = 0;
-        while (g0 < nh) {
-            int64_t g1 = g0;
-            while (g1 < nh && H[g1].bs == H[g0].bs && H[g1].a == H[g0].a) g1++;
-            /* bands inside the group */
-            int64_t nb = 0; int64_t *bfirst = malloc(sizeof(int64_t) * (g1 - g0 + 1));
-            int32_t *bkey = malloc(sizeof(int32_t) * (g1 - g0)), *bsc = malloc(sizeof(int32_t) * (g1 - g0));
-            for (int64_t x = g0; x < g1; x++) {
-                /* shift diagonal to be non-negative before banding */
-                int32_t band = (H[x].diag + (1 << 30)) >> P->w;
-                int c = k;
-                if (x > g0 && H[x - 1].diag == H[x].diag && H[x].apos - H[x - 1].apos < k) c = H[x].apos - H[x - 1].apos;
-                if (nb == 0 || bkey[nb - 1] != band) { bkey[nb] = band; bsc[nb] = 0; bfirst[nb] = x; nb++; }
-                bsc[nb - 1] += c;
-            }
-            bfirst[nb] = g1;
-            uint8_t *hot = calloc(nb + 1, 1);
-            for (int64_t q = 0; q < nb; q++) {
-                int p = bsc[q]; int adj = (q + 1 < nb && bkey[q + 1] == bkey[q] + 1);
-                if (adj) p += bsc[q + 1];
-                if (p >= P->h) { hot[q] = 1; if (adj) hot[q + 1] = 1; }
-            }
-            for (int64_t q = 0; q < nb;) {
-                if (!hot[q]) { q++; continue; }
-                int64_t e = q;
-                while (e + 1 < nb && hot[e + 1] && bkey[e + 1] == bkey[e] + 1) e++;
-                int64_t f = bfirst[q], l = bfirst[e + 1];       /* hits [f,l) */
-                int64_t m = f + (l - f - 1) / 2;
-                S[nseeds].a = H[m].a; S[nseeds].bs = H[m].bs; S[nseeds].apos = H[m].apos; S[nseeds].bpos = H[m].bpos;
-                nseeds++;
-                H[m].free_ = 0;                                  /* a seed is consumed */
-                q = e + 1;
-            }
-            free(hot); free(bfirst); free(bkey); free(bsc);
-            g0 = g1;
+    if (nh + 1 > W->capS) { W->capS = 2 * (nh + 1); W->S = realloc(W->S, sizeof(seed_t) * W->capS); }
+    uint8_t *consumed = calloc(nh + 1, 1);
+    for (int round = 0; round < P->rounds && nh > 0; round++) {
+        /* 4. band filter */
+        int64_t nb = 0, nseeds = 0;
+        for (int64_t x = 0; x < nh; x++) {
+            int32_t band = (H[x].diag + (1 << 30)) >> P->w;           /* shift the diagonal to be non-negative before banding */
+            int c = k;
+            if (x > 0 && H[x - 1].diag == H[x].diag && H[x].apos - H[x - 1].apos < k) c = H[x].apos - H[x - 1].apos;
+            if (nb == 0 || W->bkey[nb - 1] != band) { W->bkey[nb] = band; W->bsc[nb] = 0; W->bfirst[nb] = x; nb++; }
+            W->bsc[nb - 1] += c;
         }
-        R->nseeds += nseeds;
-        if (nseeds == 0) { free(S); break; }
+        W->bfirst[nb] = nh;
+        memset(W->hot, 0, nb + 1);
+        for (int64_t q = 0; q < nb; q++) {
+            int p = W->bsc[q]; int adj = (q + 1 < nb && W->bkey[q + 1] == W->bkey[q] + 1);
+            if (adj) p += W->bsc[q + 1];
+            if (p >= P->h) { W->hot[q] = 1; if (adj) W->hot[q + 1] = 1; }
+        }
+        memset(consumed, 0, nh);
+        for (int64_t q = 0; q < nb;) {
+            if (!W->hot[q]) { q++; continue; }
+            int64_t e = q;
+            while (e + 1 < nb && W->hot[e + 1] && W->bkey[e + 1] == W->bkey[e] + 1) e++;
+            int64_t f = W->bfirst[q], l = W->bfirst[e + 1];            /* hits [f,l) */
+            int64_t m = f + (l - f - 1) / 2;
+            W->S[nseeds].a = a; W->S[nseeds].bs = 2 * br + st; W->S[nseeds].apos = H[m].apos; W->S[nseeds].bpos = H[m].bpos;
+            nseeds++;
+            consumed[m] = 1;                                           /* a seed is consumed */
+            q = e + 1;
+        }
+        W->nseeds += nseeds;
+        if (nseeds == 0) break;
 
         /* 5. extend every seed */
-        int64_t nnew0 = ncand;
+        const int64_t nnew0 = out->n;
         for (int64_t s = 0; s < nseeds; s++) {
-            int a = S[s].a, bs = S[s].bs, br = bs >> 1, st = bs & 1;
-            int la = (int)(A->off[a + 1] - A->off[a]), lb = (int)(B->off[br + 1] - B->off[br]);
-            const uint8_t *af = A->bases + A->off[a], *ar = Arc + A->off[a];
-            const uint8_t *bf = (st ? Brc : B->bases) + B->off[br], *brv = (st ? B->bases : Brc) + B->off[br];
-            int ap = S[s].apos, bp = S[s].bpos;
+            int ap = W->S[s].apos, bp = W->S[s].bpos;
             ext_out fo, ro;
             int firstT = (ap / ts + 1) * ts - ap;
             int poolcap = P->poolmul * (ext_span(la - ap, lb - bp) / ts + 4);
-            extend(af + ap, la - ap, bf + bp, lb - bp, firstT, P, poolcap, pool, Vb, Tb, span, &fo, fbb, fdf);
-            R->next++;
+            extend(af + ap, la - ap, bf + bp, lb - bp, firstT, P, poolcap, W->pool, W->Vb, W->Tb, W->span, &fo, W->fbb, W->fdf);
+            W->next++;
             if (ap > 0 && bp > 0) {
                 int firstTr = ap - ((ap - 1) / ts) * ts;          /* distance down to the boundary below ap */
                 poolcap = P->poolmul * (ext_span(ap, bp) / ts + 4);
-                extend(ar + (la - ap), ap, brv + (lb - bp), bp, firstTr, P, poolcap, pool, Vb, Tb, span, &ro, rbb, rdf);
-                R->next++;
+                extend(ar + (la - ap), ap, brv + (lb - bp), bp, firstTr, P, poolcap, W->pool, W->Vb, W->Tb, W->span, &ro, W->rbb, W->rdf);
+                W->next++;
             } else { ro.i_end = ro.j_end = ro.d_end = ro.ntiles = 0; }
             int ab = ap - ro.i_end, bb = bp - ro.j_end, ae = ap + fo.i_end, be = bp + fo.j_end;
             if ((ae - ab) + (be - bb) < 2 * P->minlen) continue;
             /* join tiles: reverse part (outermost first) then forward part */
             int merge = (ap % ts != 0) && ro.ntiles > 0 && fo.ntiles > 0;
             int nt = ro.ntiles + fo.ntiles - (merge ? 1 : 0);
-            if (ncand == capc) { capc *= 2; Cn = realloc(Cn, sizeof(cand_t) * capc); }
-            cand_t *c = &Cn[ncand];
+            cand_t cn; cand_t *c = &cn;
             c->bb = malloc(sizeof(int32_t) * (nt + 1) * 2); c->df = c->bb + nt + 1;
             int o = 0;
-            for (int q = ro.ntiles - 1; q >= (merge ? 1 : 0); q--) { c->bb[o] = rbb[q]; c->df[o] = rdf[q]; o++; }
-            if (merge) { c->bb[o] = rbb[0] + fbb[0]; c->df[o] = rdf[0] + fdf[0]; o++; }
-            for (int q = merge ? 1 : 0; q < fo.ntiles; q++) { c->bb[o] = fbb[q]; c->df[o] = fdf[q]; o++; }
+            for (int q = ro.ntiles - 1; q >= (merge ? 1 : 0); q--) { c->bb[o] = W->rbb[q]; c->df[o] = W->rdf[q]; o++; }
+            if (merge) { c->bb[o] = W->rbb[0] + W->fbb[0]; c->df[o] = W->rdf[0] + W->fdf[0]; o++; }
+            for (int q = merge ? 1 : 0; q < fo.ntiles; q++) { c->bb[o] = W->fbb[q]; c->df[o] = W->fdf[q]; o++; }
             c->la.tlen = 2 * nt; c->la.diffs = fo.d_end + ro.d_end;
             c->la.abpos = ab; c->la.bbpos = bb; c->la.aepos = ae; c->la.bepos = be;
             c->la.flags = st ? 1u : 0u; c->la.aread = a; c->la.bread = br; c->la.toff = 0;
@@ -427,68 +451,161 @@ int orc_align(const orc_block *A, const orc_block *B, const orc_params *P, orc_r
                   if (dg > mx) mx = dg;
               }
               c->dmin = mn; c->dmax = mx; }
-            ncand++;
+            cv_push(out, c);
         }
-        free(S);
+        if (out->n == nnew0) break;                    /* 7. nothing kept this round: the group is finished */
 
-        /* 7b. retire hits covered by any alignment found this round (kept or dropped --
-         * a dropped one is contained in a kept one anyway) */
-        {
-            int64_t o = 0;
-            for (int64_t x = 0; x < nh; x++) {
-                int keep = H[x].free_;
-                for (int64_t j = nnew0; j < ncand && keep; j++) {
-                    orc_la *y = &Cn[j].la;
-                    if (y->aread != H[x].a || y->bread * 2 + (int)(y->flags & 1) != H[x].bs) continue;
-                    if (H[x].apos >= y->abpos && H[x].apos <= y->aepos &&
-                        H[x].diag >= Cn[j].dmin - (1 << P->w) && H[x].diag <= Cn[j].dmax + (1 << P->w)) keep = 0;
-                }
-                if (keep) H[o++] = H[x];
+        /* 7b. retire the seeds and the hits covered by an alignment kept this round */
+        int64_t o = 0;
+        for (int64_t x = 0; x < nh; x++) {
+            int keep = !consumed[x];
+            for (int64_t j = nnew0; j < out->n && keep; j++) {
+                const cand_t *y = &out->c[j];
+                if (H[x].apos >= y->la.abpos && H[x].apos <= y->la.aepos &&
+                    H[x].diag >= y->dmin - (1 << P->w) && H[x].diag <= y->dmax + (1 << P->w)) keep = 0;
             }
-            nh = o;
+            if (keep) H[o++] = H[x];
         }
-        if (ncand == nnew0) break;                     /* nothing kept this round: stop */
+        nh = o;
     }
+    free(consumed);
 
-    /* 7a. drop contained duplicates among ALL candidates of the same (a, b, strand):
-     * candidate j is dropped when any other candidate i (dropped or not -- containment is
-     * transitive, so the result does not depend on evaluation order) contains it in both
-     * coordinates; for identical intervals the lower candidate index wins. */
-    {
-        uint8_t *dropf = calloc(ncand + 1, 1);
-        for (int64_t j = 0; j < ncand; j++) {
-            orc_la *x = &Cn[j].la;
-            for (int64_t i = 0; i < ncand && !dropf[j]; i++) {
-                if (i == j) continue;
-                orc_la *y = &Cn[i].la;
-                if (y->aread != x->aread || y->bread != x->bread || (y->flags & 1) != (x->flags & 1)) continue;
-                if (y->abpos <= x->abpos && x->aepos <= y->aepos && y->bbpos <= x->bbpos && x->bepos <= y->bepos) {
-                    int same = (y->abpos == x->abpos && x->aepos == y->aepos && y->bbpos == x->bbpos && x->bepos == y->bepos);
-                    if (!same || i < j) dropf[j] = 1;
-                }
+    /* 7a. drop contained duplicates among the candidates of the group: candidate j is dropped when any other
+     * candidate i (dropped or not -- containment is transitive, so the result does not depend on evaluation
+     * order) contains it in both coordinates; for identical intervals the lower candidate index (earlier
+     * round, then earlier cluster) wins. */
+    for (int64_t j = first_cand; j < out->n; j++) {
+        orc_la *x = &out->c[j].la;
+        int drop = 0;
+        for (int64_t i = first_cand; i < out->n && !drop; i++) {
+            if (i == j) continue;
+            const orc_la *y = &out->c[i].la;
+            if (y->abpos <= x->abpos && x->aepos <= y->aepos && y->bbpos <= x->bbpos && x->bepos <= y->bepos) {
+                int same = (y->abpos == x->abpos && x->aepos == y->aepos && y->bbpos == x->bbpos && x->bepos == y->bepos);
+                if (!same || i < j) drop = 1;
             }
         }
-        for (int64_t j = 0; j < ncand; j++) if (dropf[j]) Cn[j].la.tlen = -1;
-        free(dropf);
+        if (drop) x->toff = -1;                         /* tlen stays intact for the containment tests of the others */
     }
+}
 
-    /* 8. output */
+/* all groups of one B read (both strands) */
+static void process_bread(const orc_block *A, const orc_block *B, const uint8_t *Arc, const uint8_t *Brc, const orc_params *P,
+                          const aindex_t *X, work_t *W, int br, candvec_t *out)
+{
+    const int k = P->k;
+    const int64_t o = B->off[br]; const int len = (int)(B->off[br + 1] - o);
+    const uint64_t kmask = k < 32 ? (((uint64_t)1 << (2 * k)) - 1) : ~(uint64_t)0;
+    for (int st = 0; st < 2; st++) {
+        const uint8_t *seq = (st ? Brc : B->bases) + o;
+        int64_t nh = 0;
+        /* 1-3. this read's k-mers against the A index */
+        uint64_t km = 0; int valid = 0;                  /* valid = consecutive unmasked bases ending at p+k-1 */
+        for (int q = 0; q < len; q++) {
+            km = ((km << 2) | seq[q]) & kmask;
+            int masked = 0;
+            if (B->mask) { int64_t f = st ? (o + len - 1 - q) : (o + q); masked = B->mask[f]; }   /* mask is in forward coordinates */
+            valid = masked ? 0 : valid + 1;
+            if (q + 1 < k || valid < k) continue;
+            const int p = q + 1 - k;
+            int64_t s, e; index_range(X, km, &s, &e);
+            if (e - s == 0 || e - s > P->t) continue;
+            for (int64_t x = s; x < e; x++) {
+                const int a = X->t[x].read;
+                if (P->self && a == br) continue;
+                if (A->group && B->group && A->group[a] != B->group[br]) continue;
+                if (nh == W->caph) { W->caph = W->caph ? 2 * W->caph : 4096; W->hits = realloc(W->hits, sizeof(ghit_t) * W->caph); }
+                ghit_t *h = &W->hits[nh++];
+                h->a = a; h->apos = X->t[x].pos; h->bpos = p; h->diag = h->apos - p;
+            }
+        }
+        W->nhits += nh;
+        /* 4. per (bread, strand, aread) group, hits ordered by (diagonal, apos) */
+        qsort(W->hits, nh, sizeof(ghit_t), cmp_ghit);
+        for (int64_t g0 = 0; g0 < nh;) {
+            int64_t g1 = g0;
+            while (g1 < nh && W->hits[g1].a == W->hits[g0].a) g1++;
+            process_group(A, B, Arc, Brc, P, W, W->hits + g0, g1 - g0, W->hits[g0].a, br, st, out);
+            g0 = g1;
+        }
+    }
+}
+
+typedef struct {
+    const orc_block *A, *B; const uint8_t *Arc, *Brc; const orc_params *P; const aindex_t *X; int span, maxtiles;
+    volatile int next;                  /* next chunk of B reads to hand out */
+} job_t;
+typedef struct { job_t *job; candvec_t *out; pthread_t th; int64_t nhits, nseeds, next; } worker_t;
+
+static void *worker_main(void *arg) {
+    worker_t *me = arg; job_t *J = me->job; const orc_params *P = J->P;
+    work_t W; memset(&W, 0, sizeof W);
+    W.span = J->span;
+    W.Vb = malloc(sizeof(int) * 2 * (2 * J->span + 3)); W.Tb = malloc(sizeof(int) * 2 * (2 * J->span + 3));
+    W.fbb = malloc(sizeof(int32_t) * J->maxtiles * 4);
+    W.fdf = W.fbb + J->maxtiles; W.rbb = W.fdf + J->maxtiles; W.rdf = W.rbb + J->maxtiles;
+    W.pool = malloc(sizeof(rec_t) * (size_t)P->poolmul * (J->maxtiles + 6));
+    for (;;) {
+        const int b0 = __sync_fetch_and_add(&J->next, 4);
+        if (b0 >= J->B->nreads) break;
+        for (int br = b0; br < b0 + 4 && br < J->B->nreads; br++) process_bread(J->A, J->B, J->Arc, J->Brc, P, J->X, &W, br, me->out);
+    }
+    me->nhits = W.nhits; me->nseeds = W.nseeds; me->next = W.next;
+    free(W.Vb); free(W.Tb); free(W.fbb); free(W.pool); free(W.hits); free(W.S); free(W.bfirst); free(W.bkey); free(W.bsc); free(W.hot);
+    return NULL;
+}
+
+/* `nthreads` host threads share the A index; B reads are dealt out dynamically; the result is independent of
+ * the thread count (every group is processed by exactly one thread, the output is sorted at the end). */
+int orc_align_mt(const orc_block *A, const orc_block *B, const orc_params *P, orc_result *R, int nthreads)
+{
+    const int ts = P->tspace;
+    memset(R, 0, sizeof *R);
+    if (nthreads < 1) nthreads = 1;
+    uint8_t *Arc = revcomp_block(A), *Brc = revcomp_block(B);
+    aindex_t X; build_index(A, P->k, &X, nthreads);
+
+    int maxlenA = 1, maxlenB = 1;
+    for (int r = 0; r < A->nreads; r++) { int l = (int)(A->off[r + 1] - A->off[r]); if (l > maxlenA) maxlenA = l; }
+    for (int r = 0; r < B->nreads; r++) { int l = (int)(B->off[r + 1] - B->off[r]); if (l > maxlenB) maxlenB = l; }
+    const int span = maxlenA + maxlenB + 4;
+    const int maxtiles = maxlenA / ts + 3;
+
+    candvec_t *CV = calloc(nthreads, sizeof(candvec_t));
+    int64_t st_hits = 0, st_seeds = 0, st_ext = 0;
+    job_t J; J.A = A; J.B = B; J.Arc = Arc; J.Brc = Brc; J.P = P; J.X = &X; J.span = span; J.maxtiles = maxtiles; J.next = 0;
+    worker_t *wk = calloc(nthreads, sizeof(worker_t));
+    for (int t = 0; t < nthreads; t++) { wk[t].job = &J; wk[t].out = &CV[t]; }
+    for (int t = 1; t < nthreads; t++) pthread_create(&wk[t].th, NULL, worker_main, &wk[t]);
+    worker_main(&wk[0]);
+    for (int t = 1; t < nthreads; t++) pthread_join(wk[t].th, NULL);
+    for (int t = 0; t < nthreads; t++) { st_hits += wk[t].nhits; st_seeds += wk[t].nseeds; st_ext += wk[t].next; }
+    free(wk);
+    R->nhits = st_hits; R->nseeds = st_seeds; R->next = st_ext;
+
+    /* 8. output in LAsort order */
     int64_t nla = 0, ntr = 0;
-    for (int64_t j = 0; j < ncand; j++) if (Cn[j].la.tlen >= 0) { nla++; ntr += Cn[j].la.tlen; }
+    for (int t = 0; t < nthreads; t++)
+        for (int64_t j = 0; j < CV[t].n; j++) if (CV[t].c[j].la.toff >= 0) { nla++; ntr += CV[t].c[j].la.tlen; }
     R->la = malloc(sizeof(orc_la) * (nla + 1)); R->trace = malloc(sizeof(uint16_t) * (ntr + 1));
+    cand_t **src = malloc(sizeof(cand_t *) * (nla + 1));
+    orc_la *tmp = malloc(sizeof(orc_la) * (nla + 1));
     { int64_t o = 0;
-      for (int64_t j = 0; j < ncand; j++) if (Cn[j].la.tlen >= 0) { R->la[o] = Cn[j].la; R->la[o].toff = (int32_t)j; o++; } }
-    qsort(R->la, nla, sizeof(orc_la), cmp_la);
+      for (int t = 0; t < nthreads; t++)
+          for (int64_t j = 0; j < CV[t].n; j++) if (CV[t].c[j].la.toff >= 0) { src[o] = &CV[t].c[j]; tmp[o] = CV[t].c[j].la; tmp[o].toff = (int32_t)o; o++; } }
+    qsort(tmp, nla, sizeof(orc_la), cmp_la);
     { int64_t to = 0;
       for (int64_t o = 0; o < nla; o++) {
-          cand_t *c = &Cn[R->la[o].toff]; int nt = c->la.tlen / 2;
-          R->la[o].toff = (int32_t)to;
+          const cand_t *c = src[tmp[o].toff]; const int nt = c->la.tlen / 2;
+          R->la[o] = tmp[o]; R->la[o].toff = (int32_t)to;
           for (int q = 0; q < nt; q++) { R->trace[to++] = (uint16_t)c->df[q]; R->trace[to++] = (uint16_t)c->bb[q]; }
       } }
     R->nla = nla; R->ntrace = ntr;
-    for (int64_t j = 0; j < ncand; j++) free(Cn[j].bb);
-    free(Cn); free(H); free(Vb); free(Tb); free(fbb); free(pool); free(Arc); free(Brc);
+    for (int t = 0; t < nthreads; t++) { for (int64_t j = 0; j < CV[t].n; j++) free(CV[t].c[j].bb); free(CV[t].c); }
+    free(CV); free(src); free(tmp); free(X.t); free(X.tbl); free(Arc); free(Brc);
     return 0;
 }
+
+int orc_align(const orc_block *A, const orc_block *B, const orc_params *P, orc_result *R) { return orc_align_mt(A, B, P, R, 1); }
 
 void orc_free(orc_result *R) { free(R->la); free(R->trace); memset(R, 0, sizeof *R); }

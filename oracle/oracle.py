@@ -48,9 +48,9 @@ def lib():
     global _LIB
     if _LIB is None:
         _LIB = C.CDLL(build())
-        _LIB.orc_align.restype = C.c_int
-        _LIB.orc_align.argtypes = [C.POINTER(OrcBlock), C.POINTER(OrcBlock), C.POINTER(OrcParams),
-                                   C.POINTER(OrcResult)]
+        _LIB.orc_align_mt.restype = C.c_int
+        _LIB.orc_align_mt.argtypes = [C.POINTER(OrcBlock), C.POINTER(OrcBlock), C.POINTER(OrcParams),
+                                      C.POINTER(OrcResult), C.c_int]
         _LIB.orc_free.argtypes = [C.POINTER(OrcResult)]
     return _LIB
 
@@ -71,8 +71,9 @@ def _block(off, bases, mask, group=None):
     return b, keep
 
 
-def align(a_off, a_bases, b_off, b_bases, a_mask=None, b_mask=None, a_group=None, b_group=None, **params):
+def align(a_off, a_bases, b_off, b_bases, a_mask=None, b_mask=None, a_group=None, b_group=None, threads=1, **params):
     """Run the oracle.  Blocks are (offsets[nreads+1], bases uint8 0..3 concatenated).
+    `threads` host threads share the A index and map their own B reads (same result for any count).
     Returns (la structured array, trace uint16 array, stats dict)."""
     p = dict(DEFAULTS)
     if "self" in params:
@@ -82,7 +83,7 @@ def align(a_off, a_bases, b_off, b_bases, a_mask=None, b_mask=None, a_group=None
     A, ka = _block(a_off, a_bases, a_mask, a_group)
     B, kb = _block(b_off, b_bases, b_mask, b_group)
     R = OrcResult()
-    rc = lib().orc_align(C.byref(A), C.byref(B), C.byref(P), C.byref(R))
+    rc = lib().orc_align_mt(C.byref(A), C.byref(B), C.byref(P), C.byref(R), int(threads))
     if rc != 0:
         raise RuntimeError("oracle failed: %d" % rc)
     la = np.ctypeslib.as_array(C.cast(R.la, C.POINTER(C.c_uint8)), shape=(R.nla * LA_DTYPE.itemsize,)) \

@@ -106,7 +106,7 @@ static void vote_tile(const uint8_t *a, int n, const uint8_t *b, int m, int p0,
                       int32_t *cnt, int32_t *ins, int32_t *insn, int32_t *cov)
 {
     if (m > 250) return;
-    static uint8_t D[128 + 1][256];
+    uint8_t D[128 + 1][256];                    /* on the stack: the oracle is called from several host threads */
     for (int j = 0; j <= m; j++) D[0][j] = (uint8_t)j;
     for (int i = 1; i <= n; i++) {
         D[i][0] = (uint8_t)i;

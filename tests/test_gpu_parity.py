@@ -342,3 +342,44 @@ def test_concurrent_callers_get_the_serial_results():
         th = [threading.Thread(target=lambda i=i: out.__setitem__(i, work(cases[i]))) for i in range(4)]
         [t.start() for t in th]; [t.join() for t in th]
         assert out == serial
+
+
+def _shards(reads, cuts):
+    for lo, hi in zip(cuts[:-1], cuts[1:]):
+        yield lo, synth.Block(reads.off[lo:hi + 1] - reads.off[lo], reads.bases[reads.off[lo]:reads.off[hi]])
+
+
+def test_shard_invariance():
+    """align(ref, reads) == merge(align(ref, shard_i)): the rounds are counted per (bread, strand, aread) group, so
+    what a read aligns to never depends on the reads it shares a block with.  4 shards and one-read shards."""
+    from dentist_b200 import dazzler, sharding
+    sc = synth.make_scaffolds(2, 150000, 81, n_repeats=2, repeat_copies=6)          # repeats: groups that go several rounds
+    ref, _ = synth.contigs_from(sc, synth.make_gaps(sc, 2, 82))
+    reads, _ = synth.simulate_reads(sc, 1.5, 7000, 2500, 0.13, 83)
+    ga = dazzler.Block(ref.off, ref.bases)
+    whole = dazzler.align(ga, dazzler.Block(reads.off, reads.bases), tspace=100, minlen=500)
+    assert len(whole) > 150
+    for cuts in (np.linspace(0, reads.nreads, 5).astype(int), np.arange(reads.nreads + 1)):
+        recs, trs = [], []
+        for lo, sh in _shards(reads, cuts):
+            las = dazzler.align(ga, dazzler.Block(sh.off, sh.bases), tspace=100, minlen=500)
+            r = las.rec.copy(); r["bread"] += lo
+            recs.append(r); trs.append(las.trace.copy())
+        mrec, mtoff, mtr = sharding.merge_las(recs, trs)
+        assert mrec.tobytes() == whole.rec.tobytes() and np.array_equal(mtr, whole.trace) and np.array_equal(mtoff, whole.toff)
+
+
+def test_config1_at_scale_matches_oracle():
+    """BASELINE configs[1] (the bench workload, k = 20, -s100 -l1000) at scale 0.2: 2 Mbp assembly x 43 Mbp of reads,
+    every record and trace point against the oracle (all host threads share the oracle's A index)."""
+    import os
+    import bench
+    from dentist_b200 import dazzler
+    from oracle import oracle
+    ref, reads = bench.make_workload(0.2, 0)
+    assert reads.total > 40e6
+    la, tr, st = oracle.align(ref.off, ref.bases, reads.off, reads.bases, threads=os.cpu_count() or 1,
+                              tspace=bench.PARAMS["tspace"], minlen=bench.PARAMS["minlen"], **bench.ORC)
+    rec, toff, gtr, gst = dazzler.align_blocks(dazzler.Block(ref.off, ref.bases), dazzler.Block(reads.off, reads.bases), **bench.PARAMS)
+    assert len(la) > 8000
+    assert_same((la, tr, st), (rec, toff, gtr, gst))

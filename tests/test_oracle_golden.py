@@ -118,3 +118,31 @@ def test_oracle_alignment_satisfies_trace_invariants():
             assert int(t[:, 1].sum()) == r["bepos"] - r["bbpos"]
         key = np.stack([la["aread"], la["bread"], la["flags"] & 1, la["abpos"]], 1).tolist()
         assert key == sorted(key)                                   # LAsort order, base.d:1787-1809
+
+
+def test_oracle_is_shard_and_thread_invariant():
+    """Spec item 7: the rounds are counted per (bread, strand, aread) group, so the oracle's output for a read does
+    not depend on the other reads of its block (one-read shards merge to the whole-block result), nor on the number
+    of host threads sharing the A index."""
+    from dentist_b200 import sharding, synth
+    from oracle import oracle
+    from dentist_b200._lib import REC_DTYPE
+    sc = synth.make_scaffolds(2, 100000, 81, n_repeats=2, repeat_copies=6)
+    ref, _ = synth.contigs_from(sc, synth.make_gaps(sc, 2, 82))
+    reads, _ = synth.simulate_reads(sc, 1.5, 6000, 2000, 0.13, 83)
+    la, tr, st = oracle.align(ref.off, ref.bases, reads.off, reads.bases, tspace=100, minlen=500)
+    la4, tr4, st4 = oracle.align(ref.off, ref.bases, reads.off, reads.bases, tspace=100, minlen=500, threads=4)
+    assert len(la) > 100 and la.tobytes() == la4.tobytes() and np.array_equal(tr, tr4) and st == st4
+    recs, trs = [], []
+    for r in range(reads.nreads):
+        o = reads.off[r:r + 2] - reads.off[r]
+        l1, t1, _ = oracle.align(ref.off, ref.bases, o, reads.bases[reads.off[r]:reads.off[r + 1]], tspace=100, minlen=500)
+        rec = np.zeros(len(l1), REC_DTYPE)
+        for f in ("tlen", "diffs", "abpos", "bbpos", "aepos", "bepos", "flags", "aread", "bread"):
+            rec[f] = l1[f]
+        rec["bread"] += r
+        recs.append(rec); trs.append(t1)
+    mrec, mtoff, mtr = sharding.merge_las(recs, trs)
+    for f in ("tlen", "diffs", "abpos", "bbpos", "aepos", "bepos", "flags", "aread", "bread"):
+        assert np.array_equal(mrec[f], la[f]), f
+    assert np.array_equal(mtr, tr) and np.array_equal(mtoff, la["toff"])
