@@ -16,6 +16,7 @@ EXPORTS = [
     "dn_align_params_default", "dn_las_free", "dn_block_upload", "dn_block_free", "dn_block_bases",
     "dn_align_blocks", "dn_align_host", "dn_las_write", "dn_las_read", "dn_dalign", "dn_damap",
     "dn_las_filter_error", "dn_las_filter_pileup", "dn_compute_qvs", "dn_compute_qvs_v", "dn_dust_block", "dn_block_mask_dust", "dn_block_index", "dn_mask_coverage", "dn_propagate_mask", "dn_dbdust", "dn_las_chain_mapper", "dn_las_chain", "dn_las_merge_device", "dn_block_crop", "dn_consensus_db", "dn_collect_filter", "dn_las_force_flat", "dn_reference_read_candidates", "dn_free", "dn_consensus", "dn_seq_free",
+    "dn_process_pileups", "dn_pileup_params_default", "dn_insertion_free", "dn_pile_status_string", "dn_block_add_mask",
 ]
 
 
@@ -55,6 +56,23 @@ class AlignStats(C.Structure):
 class LasBuf(C.Structure):
     _fields_ = [("nrec", C.c_int64), ("rec", C.POINTER(LasRecord)), ("toff", C.POINTER(C.c_int64)),
                 ("ntrace", C.c_int64), ("trace", C.POINTER(C.c_uint16)), ("tspace", C.c_int32), ("stats", AlignStats)]
+
+
+class PileupDesc(C.Structure):
+    _fields_ = [("nreads", C.c_int32), ("rlen", C.c_void_p), ("bases", C.c_void_p), ("allowed", C.c_void_p),
+                ("nflanks", C.c_int32), ("flank_read", C.c_void_p), ("mask_anno", C.c_void_p), ("mask_data", C.c_void_p)]
+
+
+class PileupParams(C.Structure):
+    _fields_ = [("max_alignment_error", C.c_double), ("min_anchor_length", C.c_int32), ("tspace", C.c_int32),
+                ("proper_alignment_allowance", C.c_int32), ("bad_fraction", C.c_double), ("min_qv_coverage", C.c_int32),
+                ("dust", C.c_int32), ("max_indel", C.c_int32), ("max_chain_gap", C.c_int32), ("max_rel_overlap", C.c_double),
+                ("min_rel_score", C.c_double), ("min_score", C.c_int32), ("k", C.c_int32), ("flank_k", C.c_int32)]
+
+
+class InsertionOut(C.Structure):
+    _fields_ = [("status", C.c_int32), ("reference_read", C.c_int32), ("ntries", C.c_int32), ("cons_len", C.c_int64),
+                ("consensus", C.POINTER(C.c_uint8)), ("flank_las", LasBuf)]
 
 
 _lib = None
@@ -106,6 +124,12 @@ def lib():
         L.dn_free.argtypes = [C.c_void_p]
         L.dn_consensus.argtypes = [C.c_void_p, C.POINTER(LasBuf), C.c_void_p, C.c_int32, C.c_void_p]
         L.dn_seq_free.argtypes = [C.c_void_p]
+        L.dn_pileup_params_default.argtypes = [C.POINTER(PileupParams)]
+        L.dn_process_pileups.argtypes = [C.c_void_p, C.POINTER(PileupDesc), C.c_int32, C.POINTER(PileupParams), C.POINTER(InsertionOut)]
+        L.dn_insertion_free.argtypes = [C.POINTER(InsertionOut), C.c_int32]
+        L.dn_pile_status_string.argtypes = [C.c_int32]
+        L.dn_pile_status_string.restype = C.c_char_p
+        L.dn_block_add_mask.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
         _lib = L
     return _lib
 

@@ -31,6 +31,26 @@ template <typename T> T *to_device(DBuf<T> &d, const T *h, size_t n, cudaStream_
     return d.p;
 }
 
+// Records of a caller-supplied LAS are checked on the host before a kernel indexes reads, traces or vote columns by
+// them: ids, coordinates against the read lengths, tile count against the span, trace extent against the buffer.
+const char *validate_las(const dn_las_buf *l, const int32_t *alen, int64_t na, const int32_t *blen, int64_t nb, bool with_trace) {
+    const int ts = l->tspace;
+    for (int64_t i = 0; i < l->nrec; i++) {
+        const dn_las_record &r = l->rec[i];
+        if (r.aread < 0 || r.aread >= na || r.bread < 0 || r.bread >= nb) return "contig id out of bounds";
+        if (r.abpos < 0 || r.abpos > r.aepos || r.aepos > alen[r.aread]) return "A coordinates outside the read";
+        if (r.bbpos < 0 || r.bbpos > r.bepos || r.bepos > blen[r.bread]) return "B coordinates outside the read";
+        if (!with_trace) continue;
+        const int nt = r.aepos > r.abpos ? (r.aepos + ts - 1) / ts - r.abpos / ts : 0;
+        if (r.tlen != 2 * nt) return "tlen does not match the number of trace tiles";
+        if (l->toff[i] < 0 || l->toff[i] + r.tlen > l->ntrace) return "trace outside the trace buffer";
+        int64_t sb = 0; const uint16_t *t = l->trace + l->toff[i];
+        for (int q = 0; q < nt; q++) sb += t[2 * q + 1];
+        if (sb != r.bepos - r.bbpos) return "trace B bases do not add up to the B span";
+    }
+    return nullptr;
+}
+
 int filter_common(dn_las_buf *las, int mode, double max_err, const int32_t *alen, int32_t na, const int32_t *blen, int32_t nb, int allowance) {
     if (!las) return fail(DN_ERR_INVALID, "null argument");
     if (mode == 1) {
@@ -78,10 +98,9 @@ int dn_compute_qvs_v(const int32_t *rlen, int32_t nreads, const dn_las_buf *las,
                      uint8_t **qv, int64_t **qoff) {
     if (!rlen || !las || !qv || !qoff || nreads < 0) return fail(DN_ERR_INVALID, "null argument");
     if (las->tspace < 1) return fail(DN_ERR_INVALID, "bad trace spacing");
-    for (int64_t i = 0; i < las->nrec; i++) {
-        if (las->rec[i].aread < 0 || las->rec[i].aread >= nreads) return fail(DN_ERR_INVALID, "contig id out of bounds");
-        if (i && las->rec[i].aread < las->rec[i - 1].aread) return fail(DN_ERR_INVALID, "LAS not sorted by A read");
-    }
+    if (const char *bad = validate_las(las, rlen, nreads, rlen, nreads, true)) return fail(DN_ERR_INVALID, bad);
+    for (int64_t i = 1; i < las->nrec; i++)
+        if (las->rec[i].aread < las->rec[i - 1].aread) return fail(DN_ERR_INVALID, "LAS not sorted by A read");
     std::lock_guard<std::mutex> lk(g_mu);
     if (int rc = ensure_device()) return rc;
     return guarded([&] {
@@ -174,9 +193,7 @@ int dn_consensus(const dn_block *db, const dn_las_buf *las, const int32_t *reads
     const DevBlock &B = db->b;
     if (las->tspace < 1 || las->tspace > 128) return fail(DN_ERR_INVALID, "consensus needs trace spacing <= 128");
     for (int i = 0; i < nreads; i++) if (reads[i] < 0 || reads[i] >= B.nreads) return fail(DN_ERR_INVALID, "read id out of bounds");
-    for (int64_t i = 0; i < las->nrec; i++)
-        if (las->rec[i].aread < 0 || las->rec[i].aread >= B.nreads || las->rec[i].bread < 0 || las->rec[i].bread >= B.nreads)
-            return fail(DN_ERR_INVALID, "contig id out of bounds");
+    if (const char *bad = validate_las(las, B.h_len.data(), B.nreads, B.h_len.data(), B.nreads, true)) return fail(DN_ERR_INVALID, bad);
     std::lock_guard<std::mutex> lk(g_mu);
     if (int rc = ensure_device()) return rc;
     return guarded([&] {
@@ -190,11 +207,13 @@ int dn_consensus(const dn_block *db, const dn_las_buf *las, const int32_t *reads
         for (int i = 0; i < nreads; i++) vote_off[i + 1] = vote_off[i] + B.h_len[reads[i]] + 1;
         const int64_t ncols = vote_off[nreads];
         std::vector<int32_t> vla, la_target(las->nrec + 1, -1); std::vector<int64_t> task_off;
+        std::vector<int32_t> voters(nreads, 0);
         int64_t ntasks = 0;
         for (int64_t x = 0; x < las->nrec; x++) {
             int tg = target_of[las->rec[x].aread];
             if (tg < 0 || reads[tg] != las->rec[x].aread) continue;
             la_target[x] = tg; vla.push_back((int32_t)x); task_off.push_back(ntasks); ntasks += las->rec[x].tlen / 2;
+            voters[tg]++;
         }
         DevLasIn d; d.upload(las, true, s);
         DBuf<int32_t> d_vla, d_lat, d_targets; DBuf<int64_t> d_toff, d_voff;
@@ -229,7 +248,15 @@ int dn_consensus(const dn_block *db, const dn_las_buf *las, const int32_t *reads
         out->bases = (uint8_t *)hcache_alloc(total + 1);
         if (total) DN_CUDA(cudaMemcpyAsync(out->bases, dout.p, total, cudaMemcpyDeviceToHost, s));
         DN_CUDA(cudaStreamSynchronize(s));
-        for (int i = 0; i <= nreads; i++) out->off[i] = heoff[i];
+        // a read nothing aligns to has no consensus (daccord prints nothing -> "consensus could not be computed" and the
+        // next reference read candidate, package.d:600-619, 307-329): its columns are squeezed out of the result
+        int64_t w = 0;
+        for (int i = 0; i < nreads; i++) {
+            const int64_t b = heoff[i], e = heoff[i + 1];
+            out->off[i] = w;
+            if (voters[i] > 0) { if (w != b) memmove(out->bases + w, out->bases + b, (size_t)(e - b)); w += e - b; }
+        }
+        out->off[nreads] = w;
         return DN_OK;
     });
 }

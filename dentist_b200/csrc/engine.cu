@@ -11,6 +11,7 @@
 namespace dn {
 
 int ext_warps_per_cta();
+int ext_ctas_per_sm();
 
 namespace {
 
@@ -77,6 +78,14 @@ void hcache_free(void *p) {
     if (h->pinned) cudaFreeHost(h); else free(h);
 }
 
+// k > 15: the index entry packs into 8 bytes (kmer << pb | position) when the k-mer and the block's positions fit 64 bits
+// together -- e.g. k = 20 against an assembly block of up to 16 M padded bases; larger blocks take 16-byte entries
+static int packed_pos_bits(int64_t nA, int k) {
+    if (k <= 15 || getenv("DN_NO_PACKED")) return 0;
+    const int pb = bits_for((uint64_t)nA);
+    return 2 * k + pb <= 64 ? pb : 0;
+}
+
 static int index_tbits(int64_t nA, int k, bool lookup) {
     int tbits = bits_for((uint64_t)nA) + (lookup ? -1 : 1);
     if (tbits < 16) tbits = 16;
@@ -92,6 +101,7 @@ void block_build_index(DevBlock &A, int k, cudaStream_t s) {
     const int64_t nA = A.total;
     if (nA == 0) return;
     const bool wide = k > 15;
+    const int pb = packed_pos_bits(nA, k);
     DevBlock::Index &X = A.index;
     int64_t nI = nA;
     if (!wide) {
@@ -100,14 +110,20 @@ void block_build_index(DevBlock &A, int k, cudaStream_t s) {
         u64 *sa = radix_sort_u64(ta.p, ta2.p, nA, 32, 32 + 2 * k + 1, s);
         X.ta.persistent(nA);
         DN_CUDA(cudaMemcpyAsync(X.ta.p, sa, sizeof(u64) * nA, cudaMemcpyDeviceToDevice, s));
+    } else if (pb) {
+        DBuf<u64> tp(nA), tp2(nA);
+        nI = emit_tuples_wide(A, k, tp.p, pb, s);
+        u64 *sp = radix_sort_u64(tp.p, tp2.p, nI, pb, pb + 2 * k, s);
+        X.ta.persistent(nI + 1);
+        if (nI) DN_CUDA(cudaMemcpyAsync(X.ta.p, sp, sizeof(u64) * nI, cudaMemcpyDeviceToDevice, s));
     } else {
         DBuf<ulonglong2> tw(nA), tw2(nA);
-        nI = emit_tuples_wide(A, k, tw.p, s);
+        nI = emit_tuples_wide(A, k, tw.p, 0, s);
         ulonglong2 *sw = radix_sort_rec16(tw.p, tw2.p, nI, 0, 0, 2 * k, s);
         X.tw.persistent(nI + 1);
         if (nI) DN_CUDA(cudaMemcpyAsync(X.tw.p, sw, sizeof(ulonglong2) * nI, cudaMemcpyDeviceToDevice, s));
     }
-    X.n = nI;
+    X.n = nI; X.pb = pb;
     X.tbits = index_tbits(nI, k, true);
     const int sh = 2 * k - X.tbits; const u32 nq = 1u << X.tbits;
     X.tbl.persistent((size_t)nq + 2);
@@ -118,6 +134,9 @@ void block_build_index(DevBlock &A, int k, cudaStream_t s) {
     if (!wide) {
         DN_LAUNCH(k_prefix_table, (unsigned)((nI + 255) / 256), 256, 0, s, (const u64 *)X.ta.p, nI, sh, nq, X.tbl.p);
         DN_LAUNCH(k_kmer_bitmap, (unsigned)((nI + 255) / 256), 256, 0, s, (const u64 *)X.ta.p, nI, k, kshift, X.kbits.p);
+    } else if (nI > 0 && pb) {
+        DN_LAUNCH(k_prefix_table_p, (unsigned)((nI + 255) / 256), 256, 0, s, (const u64 *)X.ta.p, pb, nI, sh, nq, X.tbl.p);
+        DN_LAUNCH(k_kmer_bitmap_p, (unsigned)((nI + 255) / 256), 256, 0, s, (const u64 *)X.ta.p, pb, nI, k, kshift, X.kbits.p);
     } else if (nI > 0) {
         DN_LAUNCH(k_prefix_table_w, (unsigned)((nI + 255) / 256), 256, 0, s, (const ulonglong2 *)X.tw.p, nI, sh, nq, X.tbl.p);
         DN_LAUNCH(k_kmer_bitmap_w, (unsigned)((nI + 255) / 256), 256, 0, s, (const ulonglong2 *)X.tw.p, nI, k, kshift, X.kbits.p);
@@ -154,23 +173,30 @@ void align_blocks(const DevBlock &A, const DevBlock &B, const AlignParams &P, Ho
     u64 *sa = nullptr; ulonglong2 *sw = nullptr;
     const DevBlock::Index *cached = (A.index.valid && A.index.k == k && P.join_mode != 1) ? &A.index : nullptr;
     int64_t nI = nA;                                       // index entries: k > 15 keeps the valid positions only
+    int pb = cached ? cached->pb : packed_pos_bits(nA, k);  // > 0: 8-byte packed entries kmer << pb | position (in `sa`)
     if (cached) { sa = cached->ta.p; sw = cached->tw.p; nI = cached->n; }
     else if (!wide) {
         ta.alloc(nA); ta2.alloc(nA);
         emit_tuples(A, false, k, 0u, ta.p, s);
         sa = radix_sort_u64(ta.p, ta2.p, nA, 32, 32 + 2 * k + 1, s);
         if (sa == ta.p) ta2.release(); else ta.release();
+    } else if (pb) {
+        ta.alloc(nA); ta2.alloc(nA);
+        nI = emit_tuples_wide(A, k, ta.p, pb, s);
+        sa = radix_sort_u64(ta.p, ta2.p, nI, pb, pb + 2 * k, s);
+        if (sa == ta.p) ta2.release(); else ta.release();
     } else {
         tw.alloc(nA); tw2.alloc(nA);
-        nI = emit_tuples_wide(A, k, tw.p, s);
+        nI = emit_tuples_wide(A, k, tw.p, 0, s);
         sw = radix_sort_rec16(tw.p, tw2.p, nI, 0, 0, 2 * k, s);
         if (sw == tw.p) tw2.release(); else tw.release();
     }
+    const bool wide16 = wide && !pb;
     tr.mark("A tuples + sort");
     const bool lookup = cached || wide || P.join_mode == 2 || (P.join_mode == 0 && nA * 8 <= (2ll << 30));   // auto: index lookup unless the A index is huge
     const int npass_t = (2 * k + (wide ? 0 : 1) + 7) / 8;
     out.stats.tuples_a = A.total_real; out.stats.tuples_b = 2 * B.total_real;
-    int64_t abytes = nA / 4 + (wide ? 16 : 8) * nA + (int64_t)npass_t * (wide ? 48 : 24) * nA;      // A: read packed, write tuples, sort passes (2R+1W)
+    int64_t abytes = nA / 4 + (wide16 ? 16 : 8) * nA + (int64_t)npass_t * (wide16 ? 48 : 24) * nA;      // A: read packed, write tuples, sort passes (2R+1W)
 
     // hit-key geometry
     const int64_t bandw = 1ll << P.w;
@@ -201,6 +227,7 @@ void align_blocks(const DevBlock &A, const DevBlock &B, const AlignParams &P, Ho
     else {
         tbl_own.alloc((size_t)nq + 2); tblp = tbl_own.p;
         if (!wide) DN_LAUNCH(k_prefix_table, (unsigned)((nA + 255) / 256), 256, 0, s, (const u64 *)sa, nA, sh, nq, tbl_own.p);
+        else if (nI > 0 && pb) DN_LAUNCH(k_prefix_table_p, (unsigned)((nI + 255) / 256), 256, 0, s, (const u64 *)sa, pb, nI, sh, nq, tbl_own.p);
         else if (nI > 0) DN_LAUNCH(k_prefix_table_w, (unsigned)((nI + 255) / 256), 256, 0, s, (const ulonglong2 *)sw, nI, sh, nq, tbl_own.p);
         else tbl_own.zero(s);                                // no valid k-mer in A: every range is empty
     }
@@ -219,6 +246,7 @@ void align_blocks(const DevBlock &A, const DevBlock &B, const AlignParams &P, Ho
         if (!cached) {
             kbits_own.alloc((size_t)1 << (kblog - 5)); kbits_own.zero(s); kbits.p = kbits_own.p;
             if (!wide) DN_LAUNCH(k_kmer_bitmap, (unsigned)((nA + 255) / 256), 256, 0, s, (const u64 *)sa, nA, k, kshift, kbits_own.p);
+            else if (nI > 0 && pb) DN_LAUNCH(k_kmer_bitmap_p, (unsigned)((nI + 255) / 256), 256, 0, s, (const u64 *)sa, pb, nI, k, kshift, kbits_own.p);
             else if (nI > 0) DN_LAUNCH(k_kmer_bitmap_w, (unsigned)((nI + 255) / 256), 256, 0, s, (const ulonglong2 *)sw, nI, k, kshift, kbits_own.p);
         }
         // pin the k-mer filter in the persisting part of L2 while the streaming lookups run
@@ -245,6 +273,10 @@ void align_blocks(const DevBlock &A, const DevBlock &B, const AlignParams &P, Ho
                     DN_LAUNCH(k_lookup_count, (unsigned)((nwB + 255) / 256), 256, 0, s, (const u32 *)B.fwd.p, mb,
                               (const int64_t *)B.off.p, (const int32_t *)B.len.p, (const int32_t *)B.chunk2read.p, nwB, k,
                               (const u64 *)sa, (const u32 *)tbl.p, sh, P.t, (const u32 *)kbits.p, kshift, JG, wcnt.p, hitmask.p, wlist.p, nlist.p);
+                else if (pb)
+                    DN_LAUNCH(k_lookup_count_p, (unsigned)((nwB + 255) / 256), 256, 0, s, (const u32 *)B.fwd.p, mb,
+                              (const int64_t *)B.off.p, (const int32_t *)B.len.p, (const int32_t *)B.chunk2read.p, nwB, k,
+                              (const u64 *)sa, pb, (const u32 *)tbl.p, sh, P.t, (const u32 *)kbits.p, kshift, JG, wcnt.p, hitmask.p, wlist.p, nlist.p);
                 else
                     DN_LAUNCH(k_lookup_count_w, (unsigned)((nwB + 255) / 256), 256, 0, s, (const u32 *)B.fwd.p, mb,
                               (const int64_t *)B.off.p, (const int32_t *)B.len.p, (const int32_t *)B.chunk2read.p, nwB, k,
@@ -264,6 +296,11 @@ void align_blocks(const DevBlock &A, const DevBlock &B, const AlignParams &P, Ho
                         DN_LAUNCH(k_lookup_emit, (unsigned)((nl[st] + 255) / 256), 256, 0, s, (const u32 *)(st ? B.rc.p : B.fwd.p), mb,
                                   (const int64_t *)B.off.p, (const int32_t *)B.len.p, (const int32_t *)B.chunk2read.p, (int64_t)nl[st], k,
                                   (const u64 *)sa, (const u32 *)tbl.p, sh, P.t, (const unsigned short *)(hitmask.p + st * nwB), (const u32 *)(wcnt.p + st * nwB),
+                                  (const int64_t *)(woff.p + st * nwB), st, JG, hits.p, (const u32 *)(wlist.p + st * nwB));
+                    else if (pb)
+                        DN_LAUNCH(k_lookup_emit_p, (unsigned)((nl[st] + 255) / 256), 256, 0, s, (const u32 *)(st ? B.rc.p : B.fwd.p), mb,
+                                  (const int64_t *)B.off.p, (const int32_t *)B.len.p, (const int32_t *)B.chunk2read.p, (int64_t)nl[st], k,
+                                  (const u64 *)sa, pb, (const u32 *)tbl.p, sh, P.t, (const unsigned short *)(hitmask.p + st * nwB), (const u32 *)(wcnt.p + st * nwB),
                                   (const int64_t *)(woff.p + st * nwB), st, JG, hits.p, (const u32 *)(wlist.p + st * nwB));
                     else
                         DN_LAUNCH(k_lookup_emit_w, (unsigned)((nl[st] + 255) / 256), 256, 0, s, (const u32 *)(st ? B.rc.p : B.fwd.p), mb,
@@ -412,8 +449,7 @@ void align_blocks(const DevBlock &A, const DevBlock &B, const AlignParams &P, Ho
         const int64_t ntile_cap = d2h_scalar(dtotal.p, s);
         DBuf<int2> tiles((size_t)ntile_cap + 1); DBuf<ExtOut> outs(2 * (size_t)nseeds);
         const int wpc = ext_warps_per_cta();
-        static const int ext_ctas_per_sm = getenv("DN_EXT_CTAS") ? atoi(getenv("DN_EXT_CTAS")) : 5;
-        int ctas = sm_count() * ext_ctas_per_sm;      // 47 registers: up to 5 CTAs x 8 warps per SM
+        int ctas = sm_count() * ext_ctas_per_sm();    // 48 registers: 5 CTAs x 8 warps per SM (DN_EXT_CTAS=6: the 40-register build)
         { int64_t need = (2ll * nseeds + wpc - 1) / wpc; if (ctas > need) ctas = (int)need;
           const int64_t budget = 24ll << 30;   // bytes of HBM for trace-record pools
           int64_t maxc = budget / (pool_stride * 16 * wpc); if (maxc < 1) maxc = 1;

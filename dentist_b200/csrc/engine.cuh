@@ -40,10 +40,11 @@ struct DevBlock {
     // align_blocks otherwise rebuilds for the A block on every call.  Invalidated when the seed mask changes.
     struct Index {
         int k = 0, tbits = 0, kbits_log2 = 27;
+        int pb = 0;                    // > 0: k > 15 with 8-byte packed entries kmer << pb | position in `ta`
         int64_t n = 0;                 // index entries (k > 15: valid positions only)
         DBuf<u64> ta; DBuf<ulonglong2> tw; DBuf<u32> tbl, kbits;
         bool valid = false;
-        void drop() { ta.release(); tw.release(); tbl.release(); kbits.release(); valid = false; k = 0; }
+        void drop() { ta.release(); tw.release(); tbl.release(); kbits.release(); valid = false; k = 0; pb = 0; }
     } index;
 };
 void block_build_index(DevBlock &A, int k, cudaStream_t s);

@@ -10,8 +10,11 @@
 // from the 2-bit packed block with 32-bit funnel-shifted windows (16 bases per compare); the whole
 // packed block is L2-resident on B200 (126 MB L2), so slides are L1/L2 hits.
 #include "seed.cuh"
+#include <stdlib.h>
 
 namespace dn {
+
+int ext_ctas_per_sm();
 
 namespace {
 
@@ -231,7 +234,8 @@ __global__ void __launch_bounds__(EXT_WARPS * 32) k_extend(const Seed *__restric
 // Register-resident variant for wmax <= 30 (the default): the window never exceeds 32 diagonals, lane l
 // owns the diagonal congruent to l mod 32, and V / T / R live in registers; neighbours are one shuffle
 // away.  No shared memory, no modular addressing, one slot per lane.  Same specification, same results.
-__global__ void __launch_bounds__(EXT_WARPS * 32) k_extend32(const Seed *__restrict__ seeds, int ntasks, ExtGeom G,
+template <int MINB>
+__global__ void __launch_bounds__(EXT_WARPS * 32, MINB) k_extend32(const Seed *__restrict__ seeds, int ntasks, ExtGeom G,
                                                              const int64_t *__restrict__ tile_off, int2 *__restrict__ tiles,
                                                              ExtOut *__restrict__ outs, int4 *__restrict__ pool_all,
                                                              int64_t pool_stride, int *__restrict__ counter) {
@@ -240,6 +244,7 @@ __global__ void __launch_bounds__(EXT_WARPS * 32) k_extend32(const Seed *__restr
     int4 *pool = pool_all + (int64_t)(blockIdx.x * EXT_WARPS + warp) * pool_stride;
     const int ts = G.ts, C = G.cdiff, X = G.xdrop, WM = G.wmax;
     const int lane_l = (lane + 31) & 31, lane_r = (lane + 1) & 31;
+    const u32 lt_mask = (1u << lane) - 1u;
 
     for (;;) {
         int task = 0;
@@ -274,48 +279,60 @@ __global__ void __launch_bounds__(EXT_WARPS * 32) k_extend32(const Seed *__restr
             if (i == la || i == lb) { lo = 1; hi = 0; }
             __syncwarp();
         }
+        int Cd = 0;                                           // C * d, carried instead of multiplied
         while (lo <= hi) {
-            d++;
-            const int nlo = lo - 1, nhi = hi + 1;
+            d++; Cd += C;
+            const int nlo = lo - 1;
             const int k = nlo + ((lane - nlo) & 31);            // the diagonal = lane (mod 32) inside the new window
             // invariant: V == NEGV in every lane whose diagonal is outside [lo, hi] (kept at the end of each wave), so the
-            // three predecessors need no range checks and lanes beyond nhi fall out by themselves
+            // three predecessors need no range checks and lanes beyond hi + 1 fall out by themselves
             const int Vl = __shfl_sync(FULL, V, lane_l), Vr = __shfl_sync(FULL, V, lane_r);
             int i = V + 1, src = lane;
             if (Vl + 1 > i) { i = Vl + 1; src = lane_l; }
             if (Vr > i) { i = Vr; src = lane_r; }
-            if (i <= NEGV + 1) i = NEGV;
             int cT = __shfl_sync(FULL, T, src), cR = __shfl_sync(FULL, R, src);
             int cn = 0;
-            if (i > NEGV) {
+            {
                 const int j = i - k;
-                if (i > la || j > lb || j < 0) i = NEGV;
+                if (i <= NEGV + 1 || i > la || j > lb || j < 0) i = NEGV;
                 else {
                     i += slide(tk.A, tk.ga + i, tk.B, tk.gb + j, min(la - i, lb - j));
-                    while (i >= cR) { cn++; cR += ts; }
+                    // tile boundaries crossed: almost always 0 or 1 (a second one needs a slide of >= ts bases); written
+                    // this way the common case costs one compare instead of the division the counted loop compiles to
+                    // (ts_magic: exact floor(x / ts) for every x the length check in align_blocks admits)
+                    if (i >= cR) {
+                        cn = 1; cR += ts;
+                        if (i >= cR) { const int more = (int)__umulhi((u32)(i - cR), G.ts_magic) + 1; cn += more; cR += more * ts; }
+                    }
                 }
             }
             const u32 cm = __ballot_sync(FULL, cn != 0);
             if (cm) {
-                int need, at;
                 if (!__any_sync(FULL, cn > 1)) {                // the usual case: at most one tile boundary per cell
-                    need = __popc(cm); at = npool + __popc(cm & ((1u << lane) - 1u));
+                    const int need = __popc(cm);
+                    if (npool + need > poolcap) break;          // pool exhausted: stop before this wave
+                    if (cn) {
+                        const int at = npool + __popc(cm & lt_mask);
+                        pool[at] = make_int4(cT, cR - ts - k, d, 0); cT = at;
+                    }
+                    npool += need;
                 } else {
-                    need = __reduce_add_sync(FULL, cn);
+                    const int need = __reduce_add_sync(FULL, cn);
                     int pre = cn;
 #pragma unroll
                     for (int o = 1; o < 32; o <<= 1) { int t = __shfl_up_sync(FULL, pre, o); if (lane >= o) pre += t; }
-                    at = npool + pre - cn;
+                    int at = npool + pre - cn;
+                    if (npool + need > poolcap) break;
+#pragma unroll 1
+                    for (int q = cn; q >= 1; q--) { pool[at] = make_int4(cT, cR - q * ts - k, d, 0); cT = at++; }
+                    npool += need;
                 }
-                if (npool + need > poolcap) break;              // pool exhausted: stop before this wave
-                for (int q = cn; q >= 1; q--) { pool[at] = make_int4(cT, cR - q * ts - k, d, 0); cT = at++; }
-                npool += need;
             }
-            const int S = i > NEGV ? 3 * (2 * i - k) - C * d : NEGS;
+            const int S = i > NEGV ? 3 * (2 * i - k) - Cd : NEGS;
             if (S > bS) { bS = S; bi = i; bk = k; bd = d; bT = cT; }
             const int waveS = __reduce_max_sync(FULL, S);
             gbest = max(gbest, waveS);
-            const bool alive = i > NEGV && !(S < gbest - X || i == la || i - k == lb);
+            const bool alive = S >= gbest - X && i != la && i - k != lb;      // S = NEGS (dead cell) fails the first test
             V = alive ? i : NEGV; T = cT; R = cR;
             const u32 m = __ballot_sync(FULL, alive);
             if (m == 0u) break;
@@ -557,7 +574,9 @@ void launch_task_caps(const Seed *seeds, int nseeds, ExtGeom G, u32 *caps, cudaS
 void launch_extend(const Seed *seeds, int nseeds, ExtGeom G, const int64_t *tile_off, int2 *tiles, ExtOut *outs,
                    int4 *pool, int64_t pool_stride, int nwarps_total, int *counter, cudaStream_t s) {
     int ctas = nwarps_total / EXT_WARPS;
-    if (G.wmax <= 30) DN_LAUNCH(k_extend32, ctas, EXT_WARPS * 32, 0, s, seeds, 2 * nseeds, G, tile_off, tiles, outs, pool, pool_stride, counter);
+    // two register budgets of the same kernel: 5 resident CTAs per SM (48 registers) or 6 (40 registers, a few spilled words)
+    if (G.wmax <= 30 && ext_ctas_per_sm() >= 6) DN_LAUNCH(k_extend32<6>, ctas, EXT_WARPS * 32, 0, s, seeds, 2 * nseeds, G, tile_off, tiles, outs, pool, pool_stride, counter);
+    else if (G.wmax <= 30) DN_LAUNCH(k_extend32<5>, ctas, EXT_WARPS * 32, 0, s, seeds, 2 * nseeds, G, tile_off, tiles, outs, pool, pool_stride, counter);
     else DN_LAUNCH(k_extend, ctas, EXT_WARPS * 32, 0, s, seeds, 2 * nseeds, G, tile_off, tiles, outs, pool, pool_stride, counter);
 }
 void launch_combine(const Seed *seeds, int nseeds, ExtGeom G, int minlen, const int64_t *tile_off, const int2 *tiles,
@@ -582,6 +601,7 @@ void launch_dedupe(const Cand *cands, int ncand, const int32_t *round_beg, int n
 }
 
 int ext_warps_per_cta() { return EXT_WARPS; }
+int ext_ctas_per_sm() { static const int v = getenv("DN_EXT_CTAS") ? atoi(getenv("DN_EXT_CTAS")) : 5; return v < 1 ? 1 : v; }
 
 }  // namespace dn
 

@@ -269,10 +269,12 @@ __global__ void __launch_bounds__(256) k_tuples_wide_count(const u32 *__restrict
     cnt[wi] = (u32)__popc(wide_valid_mask(maskbits, off, len, c2r, wi, k));
 }
 
+// PB = 0: 16-byte {kmer, position} tuples; PB > 0 (2k + PB <= 64): 8-byte tuples kmer << PB | position
+template <bool PACKED>
 __global__ void __launch_bounds__(256) k_tuples_wide(const u32 *__restrict__ seq, const u32 *__restrict__ maskbits,
                                                      const int64_t *__restrict__ off, const int32_t *__restrict__ len,
                                                      const int32_t *__restrict__ c2r, int64_t nwords, int k,
-                                                     const int64_t *__restrict__ woff, ulonglong2 *__restrict__ out) {
+                                                     const int64_t *__restrict__ woff, void *__restrict__ out_, int pb) {
     int64_t wi = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (wi >= nwords) return;
     u32 valid = wide_valid_mask(maskbits, off, len, c2r, wi, k);
@@ -284,12 +286,13 @@ __global__ void __launch_bounds__(256) k_tuples_wide(const u32 *__restrict__ seq
     int64_t o = woff[wi];
     while (valid) {
         const int jj = __ffs(valid) - 1; valid &= valid - 1;
-        out[o++] = make_ulonglong2(wide_kmer(v, w2, jj, kmask), (u64)(u32)(g0 + jj));
+        if (PACKED) reinterpret_cast<u64 *>(out_)[o++] = (wide_kmer(v, w2, jj, kmask) << pb) | (u64)(u32)(g0 + jj);
+        else reinterpret_cast<ulonglong2 *>(out_)[o++] = make_ulonglong2(wide_kmer(v, w2, jj, kmask), (u64)(u32)(g0 + jj));
     }
 }
 
 // returns the number of tuples written (a host sync: the caller sizes the sort and the index with it)
-int64_t emit_tuples_wide(const DevBlock &B, int k, ulonglong2 *out, cudaStream_t s) {
+int64_t emit_tuples_wide(const DevBlock &B, int k, void *out, int pb, cudaStream_t s) {
     int64_t nwords = B.total >> 4;
     if (nwords == 0) return 0;
     const u32 *mb = B.has_mask ? (const u32 *)B.mask.p : nullptr;
@@ -297,8 +300,12 @@ int64_t emit_tuples_wide(const DevBlock &B, int k, ulonglong2 *out, cudaStream_t
     DN_LAUNCH(k_tuples_wide_count, (unsigned)((nwords + 255) / 256), 256, 0, s, mb, (const int64_t *)B.off.p, (const int32_t *)B.len.p,
               (const int32_t *)B.chunk2read.p, nwords, k, cnt.p);
     exclusive_scan_u32_to_i64(cnt.p, woff.p, nwords, tot.p, s);
-    DN_LAUNCH(k_tuples_wide, (unsigned)((nwords + 255) / 256), 256, 0, s, (const u32 *)B.fwd.p, mb,
-              (const int64_t *)B.off.p, (const int32_t *)B.len.p, (const int32_t *)B.chunk2read.p, nwords, k, (const int64_t *)woff.p, out);
+    if (pb > 0)
+        DN_LAUNCH(k_tuples_wide<true>, (unsigned)((nwords + 255) / 256), 256, 0, s, (const u32 *)B.fwd.p, mb,
+                  (const int64_t *)B.off.p, (const int32_t *)B.len.p, (const int32_t *)B.chunk2read.p, nwords, k, (const int64_t *)woff.p, out, pb);
+    else
+        DN_LAUNCH(k_tuples_wide<false>, (unsigned)((nwords + 255) / 256), 256, 0, s, (const u32 *)B.fwd.p, mb,
+                  (const int64_t *)B.off.p, (const int32_t *)B.len.p, (const int32_t *)B.chunk2read.p, nwords, k, (const int64_t *)woff.p, out, 0);
     int64_t n = 0;
     DN_CUDA(cudaMemcpyAsync(&n, tot.p, sizeof n, cudaMemcpyDeviceToHost, s)); DN_CUDA(cudaStreamSynchronize(s));
     return n;
@@ -327,6 +334,18 @@ struct Idx64 {
     __device__ __forceinline__ static u32 fold(u64 km) { return (u32)(km ^ (km >> 31)); }
 };
 
+// k = 16..31 in 8 bytes when 2k + pb <= 64 (pb = bits of the block's padded size): kmer << pb | position.  Half the
+// bytes of Idx64 in the sort, the table build and every index walk of the lookup join.
+struct IdxP {
+    const u64 *t; int pb;
+    typedef u64 key_t;
+    static constexpr bool wide = true;
+    __device__ __forceinline__ u64 key(int64_t i) const { return t[i] >> pb; }
+    __device__ __forceinline__ u32 pos(int64_t i) const { return (u32)(t[i] & ((1ull << pb) - 1ull)); }
+    __device__ __forceinline__ static bool invalid(u64) { return false; }
+    __device__ __forceinline__ static u32 fold(u64 km) { return (u32)(km ^ (km >> 31)); }
+};
+
 // tbl[q] = first index i in the sorted A list with min(kmer_i >> sh, nq) >= q, q in [0, nq]
 template <class IDX>
 __device__ __forceinline__ void prefix_table_body(IDX ta, int64_t na, int sh, u32 nq, u32 *__restrict__ tbl) {
@@ -344,6 +363,10 @@ __global__ void __launch_bounds__(256) k_prefix_table(const u64 *__restrict__ ta
 }
 __global__ void __launch_bounds__(256) k_prefix_table_w(const ulonglong2 *__restrict__ ta, int64_t na, int sh, u32 nq, u32 *__restrict__ tbl) {
     prefix_table_body(Idx64{ta}, na, sh, nq, tbl);
+}
+
+__global__ void __launch_bounds__(256) k_prefix_table_p(const u64 *__restrict__ ta, int pb, int64_t na, int sh, u32 nq, u32 *__restrict__ tbl) {
+    prefix_table_body(IdxP{ta, pb}, na, sh, nq, tbl);
 }
 
 __device__ __forceinline__ void a_range(const u64 *__restrict__ ta, const u32 *__restrict__ tbl, int sh, u32 km, u32 &s, u32 &e) {
@@ -457,6 +480,10 @@ __global__ void __launch_bounds__(256) k_kmer_bitmap(const u64 *__restrict__ ta,
 }
 __global__ void __launch_bounds__(256) k_kmer_bitmap_w(const ulonglong2 *__restrict__ ta, int64_t na, int k, int kshift, u32 *__restrict__ bits) {
     kmer_bitmap_body(Idx64{ta}, na, k, kshift, bits);
+}
+
+__global__ void __launch_bounds__(256) k_kmer_bitmap_p(const u64 *__restrict__ ta, int pb, int64_t na, int k, int kshift, u32 *__restrict__ bits) {
+    kmer_bitmap_body(IdxP{ta, pb}, na, k, kshift, bits);
 }
 
 struct WordKmers { u64 v; u64 mwin; u32 w2; int p0, L, r; };
@@ -614,6 +641,16 @@ __global__ void __launch_bounds__(256) k_lookup_count_w(const u32 *__restrict__ 
     lookup_count_body(seq, maskbits, off, len, c2r, nwords, k, Idx64{ta}, tbl, sh, tcap, kbits, kshift, G, wcnt, hitmask, wlist, nlist);
 }
 
+__global__ void __launch_bounds__(256) k_lookup_count_p(const u32 *__restrict__ seq, const u32 *__restrict__ maskbits,
+                                                        const int64_t *__restrict__ off, const int32_t *__restrict__ len,
+                                                        const int32_t *__restrict__ c2r, int64_t nwords, int k,
+                                                        const u64 *__restrict__ ta, int pb, const u32 *__restrict__ tbl, int sh, int tcap,
+                                                        const u32 *__restrict__ kbits, int kshift, JoinGeom G, u32 *__restrict__ wcnt,
+                                                        unsigned short *__restrict__ hitmask,
+                                                        u32 *__restrict__ wlist, u32 *__restrict__ nlist) {
+    lookup_count_body(seq, maskbits, off, len, c2r, nwords, k, IdxP{ta, pb}, tbl, sh, tcap, kbits, kshift, G, wcnt, hitmask, wlist, nlist);
+}
+
 template <class IDX>
 __device__ __forceinline__ void lookup_emit_body(const u32 *__restrict__ seq, const u32 *__restrict__ maskbits,
                                                  const int64_t *__restrict__ off, const int32_t *__restrict__ len,
@@ -664,6 +701,16 @@ __global__ void __launch_bounds__(256) k_lookup_emit_w(const u32 *__restrict__ s
                                                        const int64_t *__restrict__ woff, int strand,
                                                        JoinGeom G, ulonglong2 *__restrict__ hits, const u32 *__restrict__ wlist) {
     lookup_emit_body(seq, maskbits, off, len, c2r, nwords, k, Idx64{ta}, tbl, sh, tcap, hitmask, wcnt, woff, strand, G, hits, wlist);
+}
+
+__global__ void __launch_bounds__(256) k_lookup_emit_p(const u32 *__restrict__ seq, const u32 *__restrict__ maskbits,
+                                                       const int64_t *__restrict__ off, const int32_t *__restrict__ len,
+                                                       const int32_t *__restrict__ c2r, int64_t nwords, int k,
+                                                       const u64 *__restrict__ ta, int pb, const u32 *__restrict__ tbl, int sh, int tcap,
+                                                       const unsigned short *__restrict__ hitmask, const u32 *__restrict__ wcnt,
+                                                       const int64_t *__restrict__ woff, int strand,
+                                                       JoinGeom G, ulonglong2 *__restrict__ hits, const u32 *__restrict__ wlist) {
+    lookup_emit_body(seq, maskbits, off, len, c2r, nwords, k, IdxP{ta, pb}, tbl, sh, tcap, hitmask, wcnt, woff, strand, G, hits, wlist);
 }
 
 // ------------------------------------------------------------------------- K4: band filter

@@ -31,7 +31,7 @@ struct Cand {
 struct ExtOut { int32_t i_end, j_end, d_end, ntiles; };
 
 void emit_tuples(const DevBlock &B, bool rc, int k, u32 payload_base, u64 *out, cudaStream_t s);
-int64_t emit_tuples_wide(const DevBlock &B, int k, ulonglong2 *out, cudaStream_t s);   // k = 16..31: {kmer, position} tuples of the valid forward positions; returns their number
+int64_t emit_tuples_wide(const DevBlock &B, int k, void *out, int pb, cudaStream_t s);   // k = 16..31: tuples of the valid forward positions (pb = 0: 16-byte {kmer, position}; pb > 0: 8-byte kmer << pb | position); returns their number
 
 // kernels defined in seed.cu
 __global__ void k_prefix_table(const u64 *ta, int64_t na, int sh, u32 nq, u32 *tbl);
@@ -62,6 +62,16 @@ __global__ void k_band_pass(const int32_t *bfirst, const u64 *bkey, const int32_
 __global__ void k_band_hot(const u64 *bkey, const uint8_t *pass, int32_t nbands, uint8_t *hot, int32_t *cstart);
 __global__ void k_seeds(const ulonglong2 *hits, const int32_t *bfirst, const u64 *bkey, const uint8_t *hot,
                         const int32_t *cstart, const int32_t *cidx, int32_t nbands, SeedGeom G, Seed *seeds, uint8_t *consumed);
+
+// k = 16..31 with 2k + pb <= 64: 8-byte packed index entries (kmer << pb | position)
+__global__ void k_prefix_table_p(const u64 *ta, int pb, int64_t na, int sh, u32 nq, u32 *tbl);
+__global__ void k_kmer_bitmap_p(const u64 *ta, int pb, int64_t na, int k, int kshift, u32 *bits);
+__global__ void k_lookup_count_p(const u32 *seq, const u32 *maskbits, const int64_t *off, const int32_t *len, const int32_t *c2r,
+                                 int64_t nwords, int k, const u64 *ta, int pb, const u32 *tbl, int sh, int tcap, const u32 *kbits, int kshift, JoinGeom G,
+                                 u32 *wcnt, unsigned short *hitmask, u32 *wlist, u32 *nlist);
+__global__ void k_lookup_emit_p(const u32 *seq, const u32 *maskbits, const int64_t *off, const int32_t *len, const int32_t *c2r,
+                                int64_t nwords, int k, const u64 *ta, int pb, const u32 *tbl, int sh, int tcap, const unsigned short *hitmask,
+                                const u32 *wcnt, const int64_t *woff, int strand, JoinGeom G, ulonglong2 *hits, const u32 *wlist);
 
 // segmented hit sort (segsort.cu)
 void launch_seg_offsets(const int64_t *woff, const int64_t *b_off, int nr, int64_t nwB, int64_t H, int64_t *seg_beg, int32_t *seg_len,

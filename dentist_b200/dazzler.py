@@ -473,3 +473,72 @@ def findReferenceReadCandidates(qv, qoff, group, npiles, bad_fraction=0.08):
                                                        group.ctypes.data_as(C.c_void_p), len(group), int(npiles), C.c_double(bad_fraction),
                                                        rank.ctypes.data_as(C.c_void_p), poff.ctypes.data_as(C.c_void_p)))
     return [rank[poff[p]:poff[p + 1]] for p in range(npiles)]
+
+
+def block_add_mask(block, mask):
+    """`-m<track>` for a resident block (dazzler.d:5842-5848): per-read interval lists join the seed-exclusion mask."""
+    anno, data = _track_arrays(mask, block.nreads)
+    _lib.check(_lib.lib().dn_block_add_mask(block._h, anno.ctypes.data_as(C.c_void_p), data.ctypes.data_as(C.c_void_p)))
+
+
+class _HostLas:
+    """Copied-out LAS of one pile-up's consensus-vs-flanks alignment (rec / toff / trace like `Las`)."""
+
+    def __init__(self, buf):
+        n = int(buf.nrec)
+        self.rec = np.frombuffer(C.string_at(buf.rec, n * 40), _lib.REC_DTYPE).copy() if n else np.zeros(0, _lib.REC_DTYPE)
+        self.toff = np.ctypeslib.as_array(buf.toff, shape=(n,)).copy() if n else np.zeros(0, np.int64)
+        nt = int(buf.ntrace)
+        self.trace = np.ctypeslib.as_array(buf.trace, shape=(nt,)).copy() if nt else np.zeros(0, np.uint16)
+        self.tspace = int(buf.tspace)
+
+    def __len__(self):
+        return len(self.rec)
+
+    def traces(self):
+        return [self.trace[o:o + t].reshape(-1, 2) for o, t in zip(self.toff, self.rec["tlen"])]
+
+
+def processPileUps(ref, piles, **params):
+    """dn_process_pileups: the device part of PileUpProcessor.processPileUp (package.d:303-341) for a batch.
+    ref: resident Block holding the flanking contigs (or None); piles: list of dicts with
+      reads   = list of base-code arrays (the cropped reads, pile-up order)
+      allowed = optional bool per read (allowedReferenceReadIds)
+      flanks  = list of 0-based read ids in `ref` (croppingPositions order)
+      mask    = optional per-flank list of (begin, end) intervals (repeat mask)
+    params: fields of dn_pileup_params.  Returns one dict per pile-up: status, reason, reference_read (index in the
+    pile-up or -1), ntries, consensus (base codes), flank_las (_HostLas: aread = index into `flanks`)."""
+    L = _lib.lib()
+    P = _lib.PileupParams()
+    L.dn_pileup_params_default(C.byref(P))
+    for k, v in params.items():
+        if not hasattr(P, k):
+            raise TypeError("unknown pile-up parameter %r" % k)
+        setattr(P, k, v)
+    n = len(piles)
+    descs = (_lib.PileupDesc * max(n, 1))()
+    keep = []
+    for i, p in enumerate(piles):
+        rl = np.ascontiguousarray([len(r) for r in p["reads"]], np.int32)
+        bs = np.ascontiguousarray(np.concatenate([np.asarray(r, np.uint8) for r in p["reads"]]) if len(rl) else np.zeros(0, np.uint8))
+        fl = np.ascontiguousarray(p.get("flanks", ()), np.int32)
+        keep += [rl, bs, fl]
+        d = descs[i]
+        d.nreads = len(rl); d.rlen = rl.ctypes.data; d.bases = bs.ctypes.data
+        if p.get("allowed") is not None:
+            al = np.ascontiguousarray(p["allowed"], np.uint8); keep.append(al); d.allowed = al.ctypes.data
+        d.nflanks = len(fl); d.flank_read = fl.ctypes.data
+        if p.get("mask") is not None:
+            anno, data = _track_arrays(p["mask"], len(fl)); keep += [anno, data]
+            d.mask_anno = anno.ctypes.data; d.mask_data = data.ctypes.data
+    outs = (_lib.InsertionOut * max(n, 1))()
+    _lib.check(L.dn_process_pileups(ref._h if ref is not None else None, descs, n, C.byref(P), outs))
+    res = []
+    for i in range(n):
+        o = outs[i]
+        cons = np.ctypeslib.as_array(o.consensus, shape=(int(o.cons_len),)).copy() if o.cons_len else np.zeros(0, np.uint8)
+        res.append(dict(status=int(o.status), reason=L.dn_pile_status_string(o.status).decode(), reference_read=int(o.reference_read),
+                        ntries=int(o.ntries), consensus=cons, flank_las=_HostLas(o.flank_las)))
+    L.dn_insertion_free(outs, n)
+    del keep
+    return res

@@ -64,8 +64,16 @@ def find_reference_read_candidates(qv, qoff, reads):
     return [r for _, _, r in scored]
 
 
-def process_pileups(reads, group, max_alignment_error=0.3, flanks=None, allowed=None, dust=False, candidates=False):
-    """reads: synth.Block-like (off, bases) of all cropped reads; group: pile id per read.
+def process_pileups_batch(piles, ref=None, **params):
+    """The batch path of `dentist process` through the C ABI (dn_process_pileups): see dazzler.processPileUps."""
+    return dazzler.processPileUps(ref, piles, **params)
+
+
+def process_pileups(reads, group, max_alignment_error=0.3, flanks=None, allowed=None, dust=False, candidates=False,
+                    min_anchor_length=MIN_ANCHOR, proper_alignment_allowance=TSPACE):
+    """The same path STEP BY STEP through the per-stage entry points (what a D host that keeps processPileUp's
+    structure would call; tests assert it equals dn_process_pileups byte for byte).
+    reads: synth.Block-like (off, bases) of all cropped reads; group: pile id per read.
     allowed: bool per read = member of allowedReferenceReadIds (package.d:456-468; default all); dust: DUST-mask the
     cropped reads first (package.d:476); candidates: also return the ranked reference read candidates of every pile.
     Returns dict(consensus=[codes per pile], reference_read=[read id per pile], las=Las, flank_las=Las|None)."""
@@ -76,39 +84,41 @@ def process_pileups(reads, group, max_alignment_error=0.3, flanks=None, allowed=
     if dust:
         g.maskDust()                                                     # dbdust(croppedDb) + -mdust, package.d:476-481
     # daligner -T<n> -B -s126 -l500 -e0.7 -mdust X X   (pileUpAlignmentOptions, commandline.d:2886-2902)
-    las = dazzler.align(g, g, tspace=TSPACE, minlen=MIN_ANCHOR, e=0.7, self_block=1)
+    las = dazzler.align(g, g, tspace=TSPACE, minlen=min_anchor_length, e=1.0 - max_alignment_error, self_block=1)
     las.filterLocalAlignments(max_alignment_error)                      # package.d:483-485
-    if len(las) == 0:
-        raise dazzler.DnError("empty pileup alignment")                  # package.d:487-490
-    las.chainLocalAlignments(min_score=TSPACE)                           # package.d:492-496, chainingOptions commandline.d:2820-2830
+    status = np.zeros(npiles, np.int32)
+    status[np.bincount(group[las.rec["aread"]], minlength=npiles) == 0] = 1     # "empty pileup alignment", package.d:487-490 (per pile-up)
+    if len(las):
+        las.chainLocalAlignments(min_score=TSPACE)                       # package.d:492-496, chainingOptions commandline.d:2820-2830
     # coverage = |allowedReferenceReadIds|, raised to minQVCoverage for piles of >= 4 reads (package.d:498-501)
     psize = np.bincount(group, minlength=npiles)
     ok = np.ones(len(group), bool) if allowed is None else np.ascontiguousarray(allowed, bool)
     nallowed = np.bincount(group[ok], minlength=npiles)
     cov_pile = np.where((nallowed < MIN_QV_COVERAGE) & (psize >= MIN_QV_COVERAGE), MIN_QV_COVERAGE, nallowed)
     qv, qoff = dazzler.computeQVs(lens, las, cov_pile[group])            # package.d:498-503
-    las.filterPileUpAlignments(lens, lens, TSPACE)                       # package.d:505-510 (Yes.forceFlat)
+    las.filterPileUpAlignments(lens, lens, proper_alignment_allowance)   # package.d:505-510 (Yes.forceFlat)
     las.forceFlat()
-    if len(las) == 0:
-        raise dazzler.DnError("empty pileup alignment after filtering")
-    ranked = dazzler.findReferenceReadCandidates(qv, qoff, np.where(ok, group, -1), npiles, BAD_FRACTION)   # package.d:518-568
+    status[(status == 0) & (np.bincount(group[las.rec["aread"]], minlength=npiles) == 0)] = 2   # "... after filtering", :512-515
+    ranked = dazzler.findReferenceReadCandidates(qv, qoff, np.where(ok & (status[group] == 0), group, -1), npiles, BAD_FRACTION)   # package.d:518-568
     # selectReferenceRead / computeConsensus with retry on the next candidate (package.d:307-329)
-    ref_reads = [int(c[0]) if len(c) else -1 for c in ranked]
+    ref_reads = [-1] * npiles
     cons = [np.zeros(0, np.uint8)] * npiles
-    pending = [p for p in range(npiles) if ref_reads[p] >= 0]
+    pending = [p for p in range(npiles) if status[p] == 0]
     attempt = 0
     while pending:
-        got = dazzler.getConsensus(g, las, [ref_reads[p] for p in pending])   # package.d:600-619
+        todo = [p for p in pending if attempt < len(ranked[p])]
+        for p in pending:
+            if attempt >= len(ranked[p]):
+                status[p] = 3                                                # "no valid reference read found"
+        got = dazzler.getConsensus(g, las, [int(ranked[p][attempt]) for p in todo]) if todo else []   # package.d:600-619
         nxt = []
-        for p, c in zip(pending, got):
+        for p, c in zip(todo, got):
             if len(c):
-                cons[p] = c
-            elif attempt + 1 < len(ranked[p]):
-                ref_reads[p] = int(ranked[p][attempt + 1]); nxt.append(p)
+                cons[p] = c; ref_reads[p] = int(ranked[p][attempt])
             else:
-                ref_reads[p] = -1                                            # "no valid reference read found"
+                nxt.append(p)                                                # "consensus could not be computed": next candidate
         pending = nxt; attempt += 1
-    out = dict(consensus=cons, reference_read=ref_reads, las=las, qv=qv, qoff=qoff, flank_las=None)
+    out = dict(consensus=cons, reference_read=ref_reads, las=las, qv=qv, qoff=qoff, flank_las=None, status=status)
     if candidates:
         out["candidates"] = ranked
     if flanks is not None:

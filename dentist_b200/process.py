@@ -241,7 +241,11 @@ def process_pileup_db(pile_ups, reads, ref, repeat_mask=None, min_reads_per_pile
     """PileUpsProcessor.run (package.d:100-160) for all pile-ups at once.
     pile_ups: binio.read_pileup_db() nesting; reads / ref: host blocks with .read(i) (0-based) -> base codes;
     repeat_mask: {contig id: [(begin, end), ...]}.  Returns (insertions sorted like `insertions.sort()`, skipped =
-    {pile-up index: reason})."""
+    {pile-up index: reason}).
+    Singular pile-ups (`--allow-single-reads`, package.d:297-305) are not built: the reference reaches
+    getInsertionAlignment with empty croppingPositions there (crop() is skipped), so its insertion alignment is a
+    default-initialised SeededAlignment -- gaps fail its own isValid check (package.d:747-751), extensions pass with an
+    empty overlap; nothing on the device path is involved."""
     repeat_mask = dict(repeat_mask or {})
     skipped, crops, live = {}, {}, []
     for p, pile in enumerate(pile_ups):
@@ -258,34 +262,31 @@ def process_pileup_db(pile_ups, reads, ref, repeat_mask=None, min_reads_per_pile
         live.append(p)
     if not live:
         return [], skipped
-    seqs, group, allowed = [], [], []
-    for g, p in enumerate(live):
-        seqs += crops[p]["sequences"]; group += [g] * len(pile_ups[p]); allowed += crops[p]["allowed"]
-    first_read = np.concatenate([[0], np.cumsum([len(pile_ups[p]) for p in live])])
-    # flanking contigs of every pile-up as one grouped block, repeat mask + DUST as seed mask (-mdust -mrep, package.d:621-665)
-    fl_seq, fl_group, fl_mask, fl_cid = [], [], [], []
-    for g, p in enumerate(live):
-        for cid, _ in crops[p]["ref_positions"]:
-            fl_seq.append(ref.read(cid - 1)); fl_group.append(g); fl_mask.append(pileups._normalise(crops[p]["mask"].get(cid, ()))); fl_cid.append(cid)
-    fb_host = _HostBlock(fl_seq)
-    fb = dazzler.Block(fb_host.off, fb_host.bases, mask=fl_mask, group=np.array(fl_group, np.int32))
-    fb.maskDust()
-    res = pileups.process_pileups(_HostBlock(seqs), np.array(group, np.int32), max_alignment_error, flanks=fb, allowed=allowed, dust=True)
-    fb.free()
-    fl = res["flank_las"]
-    rec, traces = fl.rec, fl.traces()
+    # ONE call for all pile-ups: pile alignment, filters, chaining, QVs, reference read, consensus (with retry) and the
+    # consensus-vs-flanks alignment (-mdust -mrep) run grouped on the device (dn_process_pileups, package.d:303-341)
+    piles_in = []
+    for p in live:
+        cids = [cid for cid, _ in crops[p]["ref_positions"]]
+        piles_in.append(dict(reads=crops[p]["sequences"], allowed=crops[p]["allowed"], flanks=[cid - 1 for cid in cids],
+                             mask=[pileups._normalise(crops[p]["mask"].get(cid, ())) for cid in cids]))
+    ref_block = ref if isinstance(ref, dazzler.Block) else dazzler.Block(ref.off, ref.bases)
+    res = dazzler.processPileUps(ref_block, piles_in, max_alignment_error=max_alignment_error, min_anchor_length=min_anchor_length,
+                                 proper_alignment_allowance=proper_alignment_allowance)
+    if ref_block is not ref:
+        ref_block.free()
     insertions = []
     for g, p in enumerate(live):
-        pile, crop = pile_ups[p], crops[p]
+        pile, crop, out = pile_ups[p], crops[p], res[g]
         try:
-            r = res["reference_read"][g]
-            if r < 0 or len(res["consensus"][g]) == 0:
-                raise PileUpSkipped("no valid reference read found")
-            ref_read = pile[r - int(first_read[g])]
-            cons = res["consensus"][g]
+            if out["status"] != 0:
+                raise PileUpSkipped(out["reason"])
+            ref_read = pile[out["reference_read"]]
+            cons = out["consensus"]
+            fl = out["flank_las"]
+            rec, traces = fl.rec, fl.traces()
             chains = []
-            for i in np.flatnonzero(rec["bread"] == g):
-                cid = fl_cid[int(rec[i]["aread"])]
+            for i in range(len(rec)):
+                cid = crop["ref_positions"][int(rec[i]["aread"])][0]
                 chains.append(dict(id=len(chains), contigA=(cid, crop["contigs"][cid]), contigB=(1, len(cons)), flags=int(rec[i]["flags"]) & 1,
                                    tpd=pileups.TSPACE, seed="front",
                                    las=[dict(ab=int(rec[i]["abpos"]), ae=int(rec[i]["aepos"]), bb=int(rec[i]["bbpos"]), be=int(rec[i]["bepos"]),

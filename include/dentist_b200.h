@@ -198,6 +198,70 @@ int dn_las_force_flat(dn_las_buf *las);
 int dn_reference_read_candidates(const uint8_t *qv, const int64_t *qoff, const int32_t *group, int32_t nreads, int32_t npiles,
                                  double bad_fraction, int32_t *rank, int64_t *pile_off);
 
+/* ---- the whole per-pile-up device path in ONE call (SURVEY §8b "fused fast path") ------------------- */
+
+/* One pile-up of a batch as PileUpProcessor holds it after crop() (processPileUps/package.d:411-426):
+ * its cropped reads (cropper.d:97-380; read i <-> pileUp[i]), which of them are in allowedReferenceReadIds
+ * (package.d:456-468), and its flanking contigs (croppingPositions order) with their part of the repeat mask
+ * (reduceRepeatMaskToFlankingContigs / adjustRepeatMaskToMakeMappingPossible, package.d:399-454). */
+typedef struct dn_pileup_desc {
+    int32_t nreads;
+    const int32_t *rlen;        /* [nreads] cropped read lengths */
+    const uint8_t *bases;       /* base codes 0..3 of the cropped reads, concatenated in read order */
+    const uint8_t *allowed;     /* [nreads] != 0: member of allowedReferenceReadIds; NULL = all */
+    int32_t nflanks;            /* flanking contigs, 1 (extension) or 2 (gap); 0 = no post-consensus alignment */
+    const int32_t *flank_read;  /* [nflanks] 0-based read index of each flanking contig in the `ref` block */
+    const int64_t *mask_anno;   /* optional repeat mask of the flanking contigs, track layout (dazzler.d:4943-5052): */
+    const int32_t *mask_data;   /*   nflanks+1 int64 byte offsets into int32 (begin, end) pairs; NULL = none */
+} dn_pileup_desc;
+
+/* The options of `dentist process` that reach the tools (commandline.d: maxAlignmentError :1808, minAnchorLength :2036,
+ * properAlignmentAllowance :2317-2332, badFraction :1101, chainingOptions :2820-2830; minQVCoverage dazzler.d:3771,
+ * forceLargeTracePointType dazzler.d:154). */
+typedef struct dn_pileup_params {
+    double max_alignment_error;          /* 0.3: filterLocalAlignments, and -e(1 - err) of the pile alignment */
+    int32_t min_anchor_length;           /* 500: -l of the pile alignment */
+    int32_t tspace;                      /* 126: -s of the pile and flank alignments (<= 128) */
+    int32_t proper_alignment_allowance;  /* 126: filterPileUpAlignments */
+    double bad_fraction;                 /* 0.08 */
+    int32_t min_qv_coverage;             /* 4 */
+    int32_t dust;                        /* != 0: dbdust(croppedDb) + -mdust (package.d:476-481) */
+    int32_t max_indel, max_chain_gap;    /* 1000, 10000 */
+    double max_rel_overlap, min_rel_score; /* 0.3, 1.0 */
+    int32_t min_score;                   /* 0 = tspace */
+    int32_t k, flank_k;                  /* 14, 14: daligner's -k for the pile / flank alignments */
+} dn_pileup_params;
+void dn_pileup_params_default(dn_pileup_params *p);
+
+#define DN_PILE_OK 0
+#define DN_PILE_EMPTY_ALIGNMENT 1        /* "empty pileup alignment"                    package.d:487-490 */
+#define DN_PILE_EMPTY_AFTER_FILTER 2     /* "empty pileup alignment after filtering"    package.d:512-515 */
+#define DN_PILE_NO_REFERENCE_READ 3      /* "no valid reference read found"             package.d:331-339 */
+const char *dn_pile_status_string(int32_t status);   /* the reference's message for a status */
+
+/* Per pile-up result: what processPileUp holds when it reaches getInsertionAlignment() (package.d:341-345). */
+typedef struct dn_insertion_out {
+    int32_t status;             /* DN_PILE_*: != 0 => the D host logs `pileUpSkipped` with dn_pile_status_string() */
+    int32_t reference_read;     /* referenceReadIdx: index in the pile-up of the read that was corrected, -1 if none */
+    int32_t ntries;             /* reference read candidates tried (consensus failures retry the next one, :307-329) */
+    int64_t cons_len;
+    uint8_t *consensus;         /* base codes 0..3 of the consensus (read 1 of consensusDb, package.d:783) */
+    dn_las_buf flank_las;       /* postConsensusAlignment before filterContainedAlignmentChains: aread = index into the
+                                   pile-up's flank list, bread = 0 (the consensus), LAsort order, traces included */
+} dn_insertion_out;
+void dn_insertion_free(dn_insertion_out *out, int32_t n);
+
+/* computeQVs + findReferenceReadCandidates + selectReferenceRead/computeConsensus (with retry) +
+ * alignConsensusToFlankingContigs (package.d:303-341) for n pile-ups at once: every alignment / QV / consensus step is
+ * ONE grouped launch sequence over all pile-ups instead of >= 12 forked tools per pile-up.  `ref` = the resident
+ * reference block the flank ids refer to (may be NULL when no pile-up has flanks).  `out` = caller array of n results;
+ * a pile-up that fails is reported in out[i].status, it does not fail the call.  Free with dn_insertion_free. */
+int dn_process_pileups(const dn_block *ref, const dn_pileup_desc *piles, int32_t n, const dn_pileup_params *p, dn_insertion_out *out);
+
+/* OR a mask track (track layout, dazzler.d:4943-5052: nreads+1 int64 byte offsets, int32 (begin, end) pairs) into a
+ * resident block's seed-exclusion mask -- what `-m<track>` does for daligner / damapper (dazzler.d:5842-5848). */
+int dn_block_add_mask(dn_block *blk, const int64_t *mask_anno, const int32_t *mask_data);
+
 /* damapper-style chain flags: START on the first record of a chain, NEXT on continuations, BEST on the
  * top-scoring chain of every B read -- the flags DENTIST decodes at dazzler.d:1738-1755 and packs into
  * AlignmentChains at :708-743.  `las` must be in LAsort order (as dn_align_blocks returns it). */

@@ -31,7 +31,8 @@
  *      insertion in front of p.  Tiles with more than 250 B bases do not vote.  Read r itself votes its own
  *      base once.  Position p emits the winning symbol (ties: r's own base first, then lowest code;
  *      a winning "deleted" emits nothing); an insertion in front of p is emitted when more than half of
- *      (covering LAs + 1) vote for one.  Uncovered positions keep r's base (daccord -f).
+ *      (covering LAs + 1) vote for one.  Uncovered positions keep r's base (daccord -f).  A read without a single
+ *      voting LA has no consensus at all (empty output).
  */
 #include <stdint.h>
 #include <stdlib.h>
@@ -143,8 +144,10 @@ int orc_consensus(const int64_t *off, const uint8_t *bases, const las_rec *la, i
     int32_t *cnt = calloc((size_t)(L + 1) * 5, 4), *ins = calloc((size_t)(L + 2) * 4, 4);
     int32_t *insn = calloc(L + 2, 4), *cov = calloc(L + 2, 4);
     uint8_t *brc = NULL; int brc_cap = 0;
+    int64_t voters = 0;
     for (int64_t x = 0; x < nla; x++) {
         if (la[x].aread != r) continue;
+        voters++;
         const int b = la[x].bread, LB = (int)(off[b + 1] - off[b]);
         const uint8_t *B = bases + off[b];
         if (la[x].flags & 1u) {
@@ -161,7 +164,9 @@ int orc_consensus(const int64_t *off, const uint8_t *bases, const las_rec *la, i
         }
     }
     int o = 0;
-    for (int p = 0; p <= L; p++) {
+    /* a read nothing aligns to has no consensus (daccord prints nothing; DENTIST then reports "consensus could not be
+     * computed" and tries the next reference read candidate, package.d:600-619, 307-329) */
+    for (int p = 0; voters > 0 && p <= L; p++) {
         /* insertion in front of p (p == L: after the last base) */
         int total = (p < L ? cov[p] : (L > 0 ? cov[L - 1] : 0)) + 1;
         if (2 * insn[p] > total) {

@@ -80,9 +80,14 @@ def test_consensus_matches_oracle_on_noisy_piles():
         oc = oracle.consensus(blk.off, blk.bases, las.rec, las.toff, las.trace, 126, r)
         assert np.array_equal(c, oc), r
         assert abs(len(c) - lens[r]) < 0.1 * lens[r]
-    # a read without any alignment keeps its own sequence (daccord -f)
-    empty = dazzler.getConsensus(g, dazzler.align(g, g, tspace=126, minlen=10 ** 6, self_block=1), [2])
-    assert np.array_equal(empty[0], blk.read(2))
+    # a read nothing aligns to has no consensus ("empty consensus", dazzler.d:4232-4235 -> the next candidate, package.d:307-329)
+    none = dazzler.align(g, g, tspace=126, minlen=10 ** 6, self_block=1)
+    empty = dazzler.getConsensus(g, none, [2, 0])
+    assert len(empty[0]) == 0 and len(empty[1]) == 0
+    assert len(oracle.consensus(blk.off, blk.bases, none.rec, none.toff, none.trace, 126, 2)) == 0
+    # several targets in one call give what single calls give
+    multi = dazzler.getConsensus(g, las, [0, 3, 5])
+    assert np.array_equal(multi[0], cons[0]) and np.array_equal(multi[1], cons[1]) and np.array_equal(multi[2], cons[3])
 
 
 def test_batched_pileups_equal_per_pile_processing():
@@ -244,3 +249,71 @@ def test_chain_local_alignments_matches_oracle():
     las.rec[:] = las.rec[::-1].copy()
     with pytest.raises(dazzler.DnError, match="not ordered properly"):
         las.chainLocalAlignments()
+
+
+def _batch_case():
+    """4 gap pile-ups + one pile-up of unrelated reads (no alignments) + one whose reads are all outside
+    allowedReferenceReadIds; flanking contigs with a repeat mask on one of them."""
+    sc = synth.make_scaffolds(1, 120000, 501, n_repeats=0)
+    gaps = synth.make_gaps(sc, 4, 502, min_len=200, max_len=1500)
+    reads, group, regions = synth.make_pile_batch(sc, gaps, 503, depth=9, anchor=1200)
+    ref, _ = synth.contigs_from(sc, gaps)
+    rng = np.random.default_rng(9)
+    piles = []
+    for p in range(4):
+        members = np.flatnonzero(group == p)
+        piles.append(dict(reads=[reads.read(int(r)) for r in members], flanks=[p, p + 1],
+                          mask=[[(100, 400)], []] if p == 1 else None,
+                          allowed=[i % 5 != 0 for i in range(len(members))] if p == 2 else None))
+    piles.append(dict(reads=[rng.integers(0, 4, 2500, dtype=np.uint8) for _ in range(4)], flanks=[0, 1], mask=None, allowed=None))
+    members = np.flatnonzero(group == 0)
+    piles.append(dict(reads=[reads.read(int(r)) for r in members], flanks=[0, 1], mask=None, allowed=[False] * len(members)))
+    return ref, piles
+
+
+def test_batch_entry_point_equals_stepwise_path():
+    """dn_process_pileups (one C call for the batch) == the same stages called one by one through the per-stage entry
+    points (pileups.process_pileups), pile-up by pile-up: status, reference read, consensus bytes, flank alignments and
+    their traces.  Failing pile-ups are reported with the reference's reasons and do not disturb the others."""
+    from dentist_b200 import dazzler, pileups
+    ref, piles = _batch_case()
+    ref_block = dazzler.Block(ref.off, ref.bases)
+    got = dazzler.processPileUps(ref_block, piles)
+    assert [o["status"] for o in got] == [0, 0, 0, 0, 1, 3]
+    assert got[4]["reason"] == "empty pileup alignment" and got[5]["reason"] == "no valid reference read found"
+    # the stepwise mirror over the same batch
+    seqs = [r for p in piles for r in p["reads"]]
+    group = np.concatenate([[i] * len(p["reads"]) for i, p in enumerate(piles)]).astype(np.int32)
+    allowed = np.concatenate([p["allowed"] if p["allowed"] is not None else [True] * len(p["reads"]) for p in piles]).astype(bool)
+    off = np.zeros(len(seqs) + 1, np.int64); off[1:] = np.cumsum([len(x) for x in seqs])
+    first = np.concatenate([[0], np.cumsum([len(p["reads"]) for p in piles])])
+    fl_seq, fl_group, fl_mask = [], [], []
+    for i, p in enumerate(piles):
+        for j, c in enumerate(p["flanks"]):
+            fl_seq.append(ref.read(c)); fl_group.append(i); fl_mask.append(p["mask"][j] if p["mask"] is not None else [])
+    foff = np.zeros(len(fl_seq) + 1, np.int64); foff[1:] = np.cumsum([len(x) for x in fl_seq])
+    ffirst = np.concatenate([[0], np.cumsum([len(p["flanks"]) for p in piles])])
+    fb = dazzler.Block(foff, np.concatenate(fl_seq), mask=fl_mask, group=np.array(fl_group, np.int32))
+    fb.maskDust()
+    step = pileups.process_pileups(synth.Block(off, np.concatenate(seqs)), group, flanks=fb, allowed=allowed, dust=True)
+    assert step["status"].tolist() == [o["status"] for o in got]
+    frec, ftr = step["flank_las"].rec, step["flank_las"].traces()
+    for i, o in enumerate(got):
+        if o["status"]:
+            assert o["reference_read"] == -1 and len(o["consensus"]) == 0 and len(o["flank_las"]) == 0
+            continue
+        assert o["reference_read"] + first[i] == step["reference_read"][i]
+        assert np.array_equal(o["consensus"], step["consensus"][i]) and len(o["consensus"]) > 2000
+        sel = np.flatnonzero(frec["bread"] == i)
+        r = o["flank_las"].rec
+        assert len(r) == len(sel) >= 2 and (r["bread"] == 0).all()
+        assert np.array_equal(r["aread"] + ffirst[i], frec["aread"][sel])
+        for f in ("abpos", "aepos", "bbpos", "bepos", "diffs", "tlen", "flags"):
+            assert np.array_equal(r[f], frec[f][sel]), f
+        for a, b in zip(o["flank_las"].traces(), [ftr[j] for j in sel]):
+            assert np.array_equal(a, b)
+    assert got[2]["reference_read"] % 5 != 0                       # the reference read honours allowedReferenceReadIds
+    # non-default options reach the aligner and the filters (ADVICE r1): a stricter error bound changes the result
+    strict = dazzler.processPileUps(ref_block, piles[:2], max_alignment_error=0.22, min_anchor_length=800, proper_alignment_allowance=50)
+    assert [o["status"] for o in strict] == [0, 0]
+    assert any(not np.array_equal(a["consensus"], b["consensus"]) for a, b in zip(strict, got[:2]))
