@@ -7,6 +7,7 @@
 #include "api_internal.hpp"
 #include "pile.cuh"
 #include <string.h>
+#include <algorithm>
 #include <vector>
 
 namespace dn {
@@ -146,6 +147,8 @@ __global__ void __launch_bounds__(64) k_chain_groups(const dn_las_record *__rest
     int cnt = 0;
     for (int x = 0; x < nacc; x++) {
         const int q = acc[x];
+        // alternate chains repeat shared prefixes (chaining.d:252-275): the group's 4 * n output slots can run out
+        if (cnt + (sel_off[q + 1] - sel_off[q]) > 4 * n) { out_cnt[g] = 0; status[g] = 2; return; }
         const u32 base = la[sel_path[sel_off[q]]].flags & (DN_LAS_COMP | DN_LAS_ELIM);
         for (int t = sel_off[q]; t < sel_off[q + 1]; t++) {
             out_src[4 * s + cnt] = s + sel_path[t];
@@ -154,6 +157,109 @@ __global__ void __launch_bounds__(64) k_chain_groups(const dn_las_record *__rest
         }
     }
     out_cnt[g] = cnt;
+}
+
+// The same algorithm on the host, without size limits, for the rare groups the kernel declines (more than 63 local
+// alignments between one pair of reads, or more output than the group's 4 * n slots): chaining.d:152-334 restated with
+// vectors instead of 64-bit set masks.  DENTIST runs this logic on the host too; the reference has no limit.
+struct HostChainOpts { int max_indel, max_chain_gap, min_score; double max_rel_overlap, min_rel_score; };
+
+bool h_chainable(const dn_las_record &x, const dn_las_record &y, const HostChainOpts &o) {
+    if ((x.flags ^ y.flags) & DN_LAS_COMP) return false;
+    const int ga = y.abpos - x.aepos, gb = y.bbpos - x.bepos;
+    const int indel = ga > gb ? ga - gb : gb - ga;
+    const int mg = std::max(ga < 0 ? -ga : ga, gb < 0 ? -gb : gb);
+    const int la = std::min(x.aepos - x.abpos, y.aepos - y.abpos), lb = std::min(x.bepos - x.bbpos, y.bepos - y.bbpos);
+    return x.abpos < y.abpos && x.bbpos < y.bbpos && indel <= o.max_indel && mg <= o.max_chain_gap &&
+           (double)std::max(0, -ga) <= o.max_rel_overlap * (double)la && (double)std::max(0, -gb) <= o.max_rel_overlap * (double)lb;
+}
+int h_ascore(const dn_las_record &x) { return ((x.aepos - x.abpos) + (x.bepos - x.bbpos)) / 2; }
+int h_cscore(const dn_las_record &x, const dn_las_record &y) {
+    const int ga = y.abpos - x.aepos, gb = y.bbpos - x.bepos;
+    const int indel = ga > gb ? ga - gb : gb - ga;
+    const int mg = std::max(ga < 0 ? -ga : ga, gb < 0 ? -gb : gb);
+    return indel + mg / 10 - h_ascore(y);
+}
+int h_min_score(const HostChainOpts &o, int best) {
+    const double a = (double)o.min_score, b = o.min_rel_score * (double)best;
+    return (int)(a > b ? a : b);
+}
+
+void chain_group_host(const dn_las_record *la, int n, const HostChainOpts &o, std::vector<int32_t> &out_src, std::vector<u32> &out_flags) {
+    std::vector<std::vector<char>> ch(n, std::vector<char>(n, 0));
+    for (int x = 0; x < n; x++) for (int y = 0; y < n; y++) ch[x][y] = x != y && h_chainable(la[x], la[y], o);
+    struct Sel { std::vector<int> path; bool alt; int score; };
+    std::vector<Sel> selected;
+    std::vector<char> visited(n, 0);
+    for (int root = 0; root < n; root++) {
+        if (visited[root]) continue;
+        std::vector<int> comp{root}; visited[root] = 1;                 // connected component of the smallest unvisited node
+        for (size_t q = 0; q < comp.size(); q++)
+            for (int y = 0; y < n; y++) if (!visited[y] && (ch[comp[q]][y] || ch[y][comp[q]])) { visited[y] = 1; comp.push_back(y); }
+        std::sort(comp.begin(), comp.end());
+        const int M = (int)comp.size() + 1;                               // local nodes 0..m, 0 = source
+        auto edge = [&](int x, int y) { return y > 0 && (x == 0 || ch[comp[x - 1]][comp[y - 1]]); };
+        // DFS topological sort with the live ascending iteration over the unvisited set (graphalgo.d:1011-1052)
+        std::vector<int> order(M); int head = M;
+        {
+            std::vector<char> U(M, 1), onstack(M, 0);
+            auto next_member = [&](int after) { for (int e = after + 1; e < M; e++) if (U[e]) return e; return -1; };
+            std::vector<int> st_node, st_cur;
+            for (int oc = next_member(-1); oc >= 0; oc = next_member(oc)) {
+                st_node.assign(1, oc); st_cur.assign(1, -1); onstack[oc] = 1;
+                while (!st_node.empty()) {
+                    const int v = st_node.back();
+                    const int nx = next_member(st_cur.back());
+                    if (nx >= 0) {
+                        st_cur.back() = nx;
+                        if (edge(v, nx) && !onstack[nx]) { st_node.push_back(nx); st_cur.push_back(-1); onstack[nx] = 1; }
+                    } else { st_node.pop_back(); st_cur.pop_back(); onstack[v] = 0; U[v] = 0; order[--head] = v; }
+                }
+            }
+        }
+        std::vector<int> dist(M, 0x7fffffff), pred(M, -1);
+        dist[0] = 0;
+        int u0 = 0; while (order[u0] != 0) u0++;
+        for (int u = u0; u < M; u++) for (int v = u + 1; v < M; v++) {
+            const int nu = order[u], nv = order[v];
+            if (!edge(nu, nv) || dist[nu] == 0x7fffffff) continue;
+            const int w = nu == 0 ? -h_ascore(la[comp[nv - 1]]) : h_cscore(la[comp[nu - 1]], la[comp[nv - 1]]);
+            if (dist[nv] > dist[nu] + w) { dist[nv] = dist[nu] + w; pred[nv] = nu; }
+        }
+        std::vector<int> srt(M);
+        for (int x = 0; x < M; x++) srt[x] = x;
+        std::stable_sort(srt.begin(), srt.end(), [&](int a, int b) { return dist[a] < dist[b]; });
+        const int max_distance = -h_min_score(o, -dist[srt[0]]);
+        std::vector<char> forbidden(M, 0); forbidden[0] = 1;
+        for (int q = 0; q < M; q++) {
+            const int end = srt[q];
+            if (forbidden[end] || dist[end] > max_distance) continue;
+            Sel sl; sl.alt = false; sl.score = -dist[end];
+            for (int p = end; p >= 0; p = pred[p]) if (p > 0) { if (forbidden[p]) sl.alt = true; forbidden[p] = 1; sl.path.push_back(comp[p - 1]); }
+            std::reverse(sl.path.begin(), sl.path.end());
+            selected.push_back(std::move(sl));
+        }
+    }
+    if (selected.empty()) return;
+    int best = selected[0].score;
+    for (const Sel &c : selected) if (c.score > best) best = c.score;
+    const int min_score = h_min_score(o, best);
+    std::vector<const Sel *> acc;
+    for (const Sel &c : selected) if (min_score <= c.score) acc.push_back(&c);
+    std::stable_sort(acc.begin(), acc.end(), [&](const Sel *p, const Sel *q) {
+        const dn_las_record &pf = la[p->path.front()], &pl = la[p->path.back()], &qf = la[q->path.front()], &ql = la[q->path.back()];
+        if (pf.abpos != qf.abpos) return pf.abpos < qf.abpos;
+        if (pf.bbpos != qf.bbpos) return pf.bbpos < qf.bbpos;
+        if (pl.aepos != ql.aepos) return pl.aepos < ql.aepos;
+        return pl.bepos < ql.bepos;
+    });
+    for (const Sel *c : acc) {
+        const u32 base = la[c->path.front()].flags & (DN_LAS_COMP | DN_LAS_ELIM);
+        for (size_t t = 0; t < c->path.size(); t++) {
+            out_src.push_back(c->path[t]);
+            out_flags.push_back(base | (t == 0 ? (DN_LAS_START | (c->alt ? 0u : DN_LAS_BEST)) : DN_LAS_NEXT));
+        }
+    }
 }
 
 }  // namespace
@@ -199,10 +305,16 @@ extern "C" int dn_las_chain(dn_las_buf *las, int32_t max_indel, int32_t max_chai
         DN_CUDA(cudaMemcpyAsync(hcnt.data(), ocnt.p, sizeof(int32_t) * ngroups, cudaMemcpyDeviceToHost, s));
         DN_CUDA(cudaMemcpyAsync(hst.data(), ost.p, sizeof(int32_t) * ngroups, cudaMemcpyDeviceToHost, s));
         DN_CUDA(cudaStreamSynchronize(s));
+        // groups the kernel declined (> 63 records, or more output than 4 * n slots) go through the host restatement
+        std::vector<std::vector<int32_t>> xsrc(ngroups); std::vector<std::vector<u32>> xfl(ngroups);
+        const HostChainOpts ho{max_indel, max_chain_gap, min_score, max_rel_overlap, min_rel_score};
         int64_t total = 0;
         for (int g = 0; g < ngroups; g++) {
-            if (hst[g] == 1) return fail(DN_ERR_INVALID, "chaining: more than 63 local alignments between one pair of reads");
-            if (hst[g]) return fail(DN_ERR_INVALID, "chaining: too many alternate chains in one group");
+            if (hst[g]) {
+                chain_group_host(in.data() + gstart[g], gstart[g + 1] - gstart[g], ho, xsrc[g], xfl[g]);
+                for (auto &v : xsrc[g]) v += gstart[g];
+                hcnt[g] = (int32_t)xsrc[g].size();
+            }
             total += hcnt[g];
         }
         // gather: records keep their trace (toff), flags are rewritten; a record may appear in two chains
@@ -211,8 +323,8 @@ extern "C" int dn_las_chain(dn_las_buf *las, int32_t max_indel, int32_t max_chai
         int64_t w = 0;
         for (int g = 0; g < ngroups; g++)
             for (int t = 0; t < hcnt[g]; t++) {
-                const int64_t src = idx[hsrc[4 * (int64_t)gstart[g] + t]];
-                nrec[w] = las->rec[src]; nrec[w].flags = hfl[4 * (int64_t)gstart[g] + t]; ntoff[w] = las->toff[src]; w++;
+                const int64_t src = idx[hst[g] ? xsrc[g][t] : hsrc[4 * (int64_t)gstart[g] + t]];
+                nrec[w] = las->rec[src]; nrec[w].flags = hst[g] ? xfl[g][t] : hfl[4 * (int64_t)gstart[g] + t]; ntoff[w] = las->toff[src]; w++;
             }
         hcache_free(las->rec); hcache_free(las->toff);
         las->rec = nrec; las->toff = ntoff; las->nrec = total;

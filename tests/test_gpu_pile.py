@@ -317,3 +317,54 @@ def test_batch_entry_point_equals_stepwise_path():
     strict = dazzler.processPileUps(ref_block, piles[:2], max_alignment_error=0.22, min_anchor_length=800, proper_alignment_allowance=50)
     assert [o["status"] for o in strict] == [0, 0]
     assert any(not np.array_equal(a["consensus"], b["consensus"]) for a, b in zip(strict, got[:2]))
+
+
+def _synthetic_las(tmp_path, rec, tspace=126):
+    """A Las object over hand-made records (written and read back through the LAS codec; traces are dummies)."""
+    import ctypes as C
+    from dentist_b200 import _lib, dazzler
+    nt = -(-rec["aepos"] // tspace) - rec["abpos"] // tspace
+    rec["tlen"] = 2 * nt
+    toff = np.cumsum(rec["tlen"]) - rec["tlen"]
+    path = str(tmp_path / "synthetic.las")
+    dazzler.write_las(path, tspace, rec, toff, np.zeros(int(rec["tlen"].sum()), np.uint16))
+    buf = _lib.LasBuf()
+    _lib.check(_lib.lib().dn_las_read(path.encode(), C.byref(buf)))
+    return dazzler.Las(buf)
+
+
+def test_chaining_of_oversized_groups_goes_through_the_host_restatement(tmp_path):
+    """one (A,B) pair with more than 63 local alignments, and a group whose alternate chains need more than
+    4 * n output records, used to fail the whole call / overrun the group's slots; both now equal the oracle."""
+    from dentist_b200._lib import REC_DTYPE
+    from oracle import chaining
+    rng = np.random.default_rng(77)
+
+    def colinear(n, a, b, step, ln, jitter):
+        r = np.zeros(n, REC_DTYPE)
+        r["aread"], r["bread"] = a, b
+        r["abpos"] = 1000 + step * np.arange(n) + rng.integers(0, jitter, n)
+        r["bbpos"] = 500 + step * np.arange(n) + rng.integers(0, jitter, n)
+        r["aepos"] = r["abpos"] + ln; r["bepos"] = r["bbpos"] + ln + rng.integers(-20, 20, n)
+        r["diffs"] = ln // 10
+        return r
+    big = colinear(90, 0, 1, 700, 600, 60)                       # 90 > 63 records between one pair of reads
+    # many overlapping alternatives: every record chains with many later ones -> alternate chains repeat prefixes
+    alt = colinear(16, 0, 2, 300, 900, 5)
+    alt["abpos"][8:] = alt["abpos"][:8] + 40; alt["bbpos"][8:] = alt["bbpos"][:8] + 55
+    alt["aepos"][8:] = alt["aepos"][:8] + 40; alt["bepos"][8:] = alt["bepos"][:8] + 55
+    small = colinear(5, 1, 2, 2000, 1500, 30)
+    rec = np.concatenate([big, alt, small])
+    order = np.lexsort((rec["abpos"], rec["bread"], rec["aread"]))
+    rec = rec[order]
+    for opts in (dict(), dict(min_rel_score=0.05, max_rel_overlap=0.9), dict(min_rel_score=0.3, max_indel=200)):
+        las = _synthetic_las(tmp_path, rec.copy())
+        before = las.rec.copy()
+        las.chainLocalAlignments(**opts)
+        o = chaining.ChainingOptions(max_indel=opts.get("max_indel", 1000), max_rel_overlap=opts.get("max_rel_overlap", 0.3),
+                                     min_rel_score=opts.get("min_rel_score", 1.0), min_score=126)
+        src, fl = chaining.chain_local_alignments(before, o)
+        assert len(las) == len(src) and np.array_equal(las.rec["flags"], fl)
+        for f in ("aread", "bread", "abpos", "aepos", "bbpos", "bepos"):
+            assert np.array_equal(las.rec[f], before[src][f]), f
+    assert len(src) > 0
