@@ -254,6 +254,7 @@ def main():
     dazzler.init(local_rank)
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+        dazzler.comm_init(rank, world)                  # the library's own NCCL communicator (id handed over by torch.distributed)
     dev = torch.device("cuda", local_rank)
 
     ref, reads = make_workload(args.scale, rank)
@@ -340,14 +341,12 @@ def main():
         # dn_align_host: pinned host .bps in, host LAS out, one call (the reads' upload overlaps the assembly's indexing)
         a2 = dazzler.HostBlock(ref.off, bps=ref_bps, boff=ref_boff)
         b2 = dazzler.HostBlock(reads.off, bps=reads_bps, boff=reads_boff)
-        rec, toff, tr, st = dazzler.align_host(a2, b2, **PARAMS)
         if world > 1:
-            tg = time.perf_counter()
-            merged = sharding.gather_las(rec, tr, bread_offset, device=dev, tspace=PARAMS["tspace"], bounds=gather_bounds, root=0)
-            if merged is not None:
-                rec, toff, tr = merged
-            if os.environ.get("BENCH_DEBUG"):
-                print("[bench] rank %d gather+merge %.2f ms" % (rank, (time.perf_counter() - tg) * 1e3), file=sys.stderr)
+            # one call: upload + align + gather of the per-rank LAS segments HBM to HBM (NCCL inside the library) + placement
+            # merge + download on the root -- what the per-block damapper jobs + LAmerge do (Snakefile:1143-1200)
+            rec, toff, tr, st = dazzler.align_host_gather(a2, b2, bread_offset, root=0, **PARAMS)
+        else:
+            rec, toff, tr, st = dazzler.align_host(a2, b2, **PARAMS)
         barrier()
         dt = time.perf_counter() - t1
         if os.environ.get("BENCH_DEBUG"):
@@ -432,7 +431,7 @@ def main():
             out["resident_reference_index"] = resident
         emit(out)
     if world > 1:
-        dist.barrier(); dist.destroy_process_group()
+        dist.barrier(); dazzler.comm_shutdown(); dist.destroy_process_group()
 
 
 if __name__ == "__main__":

@@ -145,8 +145,9 @@ void block_build_index(DevBlock &A, int k, cudaStream_t s) {
     X.k = k; X.valid = true;
 }
 
-void align_blocks(const DevBlock &A, const DevBlock &B, const AlignParams &P, HostLas &out, cudaStream_t s) {
+void align_blocks(const DevBlock &A, const DevBlock &B, const AlignParams &P, HostLas &out, cudaStream_t s, DevLas *keep) {
     out = HostLas();
+    if (keep) *keep = DevLas();
     arena().reset();
     if (P.k < 4 || P.k > 31) throw Error("k must be in [4,31]");
     if (P.wmax < 4 || P.wmax > 62) throw Error("wmax must be in [4,62]");
@@ -523,8 +524,10 @@ void align_blocks(const DevBlock &A, const DevBlock &B, const AlignParams &P, Ho
         if (getenv("DN_TRACE")) fprintf(stderr, "[dn trace] candidates %d, kept after duplicate removal %d\n", ncand, nkeep);
         tr.mark("dedupe + final sort");
         out.nrec = nkeep;
-        out.rec = (dn_las_record *)hcache_alloc(sizeof(dn_las_record) * ((size_t)nkeep + 1));
-        out.toff = (int64_t *)hcache_alloc(sizeof(int64_t) * ((size_t)nkeep + 1));
+        if (!keep) {
+            out.rec = (dn_las_record *)hcache_alloc(sizeof(dn_las_record) * ((size_t)nkeep + 1));
+            out.toff = (int64_t *)hcache_alloc(sizeof(int64_t) * ((size_t)nkeep + 1));
+        }
         if (nkeep > 0) {
             DBuf<dn_las_record> drec(nkeep); DBuf<u32> tl(nkeep); DBuf<int64_t> dtoff(nkeep);
             launch_final_records(all.p, cur, nkeep, B.nreads, drec.p, tl.p, ctr.p + 1, s);
@@ -536,22 +539,26 @@ void align_blocks(const DevBlock &A, const DevBlock &B, const AlignParams &P, Ho
             DBuf<uint16_t> dtr((size_t)tot + 1);
             launch_final_traces(all.p, cur, nkeep, dtoff.p, FG, dtr.p, s);
             tr.mark("final records + traces");
-            out.trace = (uint16_t *)hcache_alloc(sizeof(uint16_t) * ((size_t)tot + 1));
-            tr.mark("host buffer alloc");
-            DN_CUDA(cudaMemcpyAsync(out.rec, drec.p, sizeof(dn_las_record) * nkeep, cudaMemcpyDeviceToHost, s));
-            DN_CUDA(cudaMemcpyAsync(out.toff, dtoff.p, sizeof(int64_t) * nkeep, cudaMemcpyDeviceToHost, s));
-            if (tot) DN_CUDA(cudaMemcpyAsync(out.trace, dtr.p, sizeof(uint16_t) * tot, cudaMemcpyDeviceToHost, s));
+            if (keep) { keep->rec = drec.p; keep->toff = dtoff.p; keep->trace = dtr.p; keep->nrec = nkeep; keep->ntrace = tot; }
+            else {
+                out.trace = (uint16_t *)hcache_alloc(sizeof(uint16_t) * ((size_t)tot + 1));
+                tr.mark("host buffer alloc");
+                DN_CUDA(cudaMemcpyAsync(out.rec, drec.p, sizeof(dn_las_record) * nkeep, cudaMemcpyDeviceToHost, s));
+                DN_CUDA(cudaMemcpyAsync(out.toff, dtoff.p, sizeof(int64_t) * nkeep, cudaMemcpyDeviceToHost, s));
+                if (tot) DN_CUDA(cudaMemcpyAsync(out.trace, dtr.p, sizeof(uint16_t) * tot, cudaMemcpyDeviceToHost, s));
+            }
             DN_CUDA(cudaMemcpyAsync(hctr, ctr.p, sizeof hctr, cudaMemcpyDeviceToHost, s));
             DN_CUDA(cudaStreamSynchronize(s));
             aligned = (int64_t)hctr[1]; ext_bytes = (int64_t)hctr[2];
         }
     }
+    if (keep) { out.nrec = 0; tot = keep->ntrace; }          // the records stay in HBM: the host result holds the statistics only
     if (!out.rec) out.rec = (dn_las_record *)hcache_alloc(64);
     if (!out.toff) out.toff = (int64_t *)hcache_alloc(64);
     if (!out.trace) out.trace = (uint16_t *)hcache_alloc(64);
-    out.ntrace = tot;
+    out.ntrace = keep ? 0 : tot;
     tr.mark("dedupe + order + download");
-    out.stats.las = out.nrec; out.stats.aligned_bases = aligned; out.stats.trace_points = tot / 2;
+    out.stats.las = keep ? keep->nrec : out.nrec; out.stats.aligned_bases = aligned; out.stats.trace_points = tot / 2;
     out.stats.algo_bytes_seed = abytes; out.stats.algo_bytes_extend = ext_bytes;
     out.stats.ms_total = tt.stop();                          // syncs the stream: the extension brackets are complete
     for (auto &e : ext_ev) { float ms = 0; cudaEventElapsedTime(&ms, e.first, e.second); ms_ext += ms; cudaEventDestroy(e.first); cudaEventDestroy(e.second); }

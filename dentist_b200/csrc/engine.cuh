@@ -74,6 +74,14 @@ void block_crop(const DevBlock &src, int n, const int32_t *read, const int32_t *
 void force_flat_device(dn_las_record *h_rec, int64_t *h_toff, int64_t n, cudaStream_t s);
 void merge_las_device(const dn_las_record *d_rec, int64_t n, const uint16_t *d_trace, int64_t ntrace, int64_t max_alen, int64_t max_blen,
                       int64_t na_reads, int64_t nb_reads, HostLas &out, cudaStream_t s);
-void align_blocks(const DevBlock &A, const DevBlock &B, const AlignParams &P, HostLas &out, cudaStream_t s);
+// The same result left in HBM (arena memory: valid until the next call resets the arena) -- the input of the multi-GPU
+// gather, which must not bounce through the host.
+struct DevLas { dn_las_record *rec = nullptr; int64_t *toff = nullptr; uint16_t *trace = nullptr; int64_t nrec = 0, ntrace = 0; };
+// keep != nullptr: records / traces stay on the device (out gets the statistics only)
+void align_blocks(const DevBlock &A, const DevBlock &B, const AlignParams &P, HostLas &out, cudaStream_t s, DevLas *keep = nullptr);
+// LAmerge for the all-gathered segments of `world` ranks (segment r = records [seg_beg[r], seg_beg[r+1]) in LAsort order,
+// B reads of rank r all below those of rank r+1): one pass of run offsets + placement instead of a full re-sort
+void merge_segments_device(const dn_las_record *d_rec, const int64_t *h_seg_beg, int world, const uint16_t *d_trace, int64_t ntrace,
+                           int64_t na_reads, HostLas &out, cudaStream_t s);
 
 }  // namespace dn

@@ -542,3 +542,64 @@ def processPileUps(ref, piles, **params):
     L.dn_insertion_free(outs, n)
     del keep
     return res
+
+
+# ---------------------------------------------------------------------------------------------
+# multi-GPU (one process per GPU; the collective lives in the library: csrc/comm.cu)
+
+
+def comm_init(rank, world, exchange=None):
+    """Joins the library's NCCL communicator.  `exchange(id_bytes or None) -> id_bytes` moves the 128-byte id from
+    rank 0 to the other ranks; the default uses torch.distributed's already initialised process group (plumbing)."""
+    L = _lib.lib()
+    idb = (C.c_uint8 * 128)()
+    if rank == 0:
+        _lib.check(L.dn_comm_get_id(idb))
+    if exchange is None:
+        import torch
+        import torch.distributed as dist
+        dev = torch.device("cuda", torch.cuda.current_device()) if dist.get_backend() == "nccl" else torch.device("cpu")
+        t = torch.tensor(list(bytes(idb)), dtype=torch.uint8, device=dev)
+        dist.broadcast(t, src=0)
+        raw = bytes(t.cpu().tolist())
+    else:
+        raw = exchange(bytes(idb) if rank == 0 else None)
+    idb = (C.c_uint8 * 128).from_buffer_copy(raw)
+    _lib.check(L.dn_comm_init(int(rank), int(world), idb))
+
+
+def comm_shutdown():
+    _lib.check(_lib.lib().dn_comm_shutdown())
+
+
+def align_blocks_gather(a, b, bread_offset, root=0, **params):
+    """dn_align_blocks_gather: every rank aligns its own resident read block `b` against `a`; the merged LAS arrives on
+    `root` (every rank if root < 0).  Returns (records, trace offsets, trace, this rank's stats)."""
+    p = make_params(**params)
+    buf = _lib.LasBuf()
+    _lib.check(_lib.lib().dn_align_blocks_gather(a._h, b._h, C.byref(p), int(bread_offset), int(root), C.byref(buf)))
+    rec, toff, tr, _, st = _take(buf)
+    return rec, toff, tr, st
+
+
+def align_host_gather(a, b, bread_offset, root=0, **params):
+    """dn_align_host_gather: host blocks in, merged host LAS out on `root` (upload + align + gather + merge + download)."""
+    p = make_params(**params)
+    buf = _lib.LasBuf()
+    _lib.check(_lib.lib().dn_align_host_gather(C.byref(a._desc), C.byref(b._desc), C.byref(p), int(bread_offset), int(root), C.byref(buf)))
+    rec, toff, tr, _, st = _take(buf)
+    return rec, toff, tr, st
+
+
+def comm_allgatherv(data):
+    """dn_comm_allgatherv: bytes-like in, list of every rank's bytes out."""
+    L = _lib.lib()
+    buf = np.frombuffer(bytes(data), np.uint8) if not isinstance(data, np.ndarray) else np.ascontiguousarray(data, np.uint8)
+    world = int(L.dn_comm_size())
+    counts = np.zeros(world, np.int64); out = C.c_void_p()
+    _lib.check(L.dn_comm_allgatherv(buf.ctypes.data_as(C.c_void_p), int(buf.nbytes), C.byref(out), counts.ctypes.data_as(C.c_void_p)))
+    tot = int(counts.sum())
+    allb = np.ctypeslib.as_array(C.cast(out, C.POINTER(C.c_uint8)), shape=(max(tot, 1),))[:tot].copy()
+    L.dn_free(out)
+    cuts = np.concatenate([[0], np.cumsum(counts)])
+    return [allb[cuts[r]:cuts[r + 1]].tobytes() for r in range(world)]

@@ -150,6 +150,29 @@ int dn_align_host(const dn_block_desc *a, const dn_block_desc *b, const dn_align
 int dn_las_merge_device(const void *d_rec, int64_t nrec, const void *d_trace, int64_t ntrace, int32_t tspace, int64_t max_alen,
                         int64_t max_blen, int64_t na_reads, int64_t nb_reads, dn_las_buf *out);
 
+/* ---- multi-GPU: one process per GPU, NCCL inside the library ---------------------------------
+ * Read blocks shard across the ranks with no data-path collective (the Snakemake fan-out, Snakefile:1143-1170);
+ * the per-rank LAS segments are exchanged HBM to HBM in ONE variable-size gather and merged by placement
+ * (what LAmerge does through files, Snakefile:1173-1200).  NCCL is bound at run time (libnccl.so.2 / DN_NCCL_LIB). */
+#define DN_COMM_ID_BYTES 128
+/* Rank 0 creates the communicator id (ncclGetUniqueId) and hands its 128 bytes to the other ranks by whatever the host
+ * has (a file in tmpdir, MPI, torch.distributed ...); every rank then joins with dn_comm_init on its own device. */
+int dn_comm_get_id(uint8_t *id);
+int dn_comm_init(int32_t rank, int32_t world, const uint8_t *id);
+int dn_comm_shutdown(void);
+int32_t dn_comm_rank(void);
+int32_t dn_comm_size(void);
+/* dn_align_blocks on every rank's own read block `b` (B read numbers local to the block) + gather + merge:
+ * `bread_offset` = global number of the block's first read (blocks must be dealt out in rank order: a rank's reads
+ * all come before the next rank's).  root >= 0: that rank receives the merged A.B.las, the others get an empty LAS with
+ * their own statistics; root < 0: every rank receives it. */
+int dn_align_blocks_gather(const dn_block *a, const dn_block *b, const dn_align_params *p, int64_t bread_offset, int32_t root, dn_las_buf *out);
+/* the same from host descriptors (upload + align + gather + merge + download on the receiving ranks) */
+int dn_align_host_gather(const dn_block_desc *a, const dn_block_desc *b, const dn_align_params *p, int64_t bread_offset, int32_t root, dn_las_buf *out);
+/* Variable-size all-gather of host byte buffers (e.g. every rank's InsertionDb bytes, commands/mergeInsertions.d):
+ * *recv = the ranks' buffers back to back (free with dn_free), counts[r] = size of rank r's. */
+int dn_comm_allgatherv(const void *send, int64_t nbytes, void **recv, int64_t *counts /* [world] */);
+
 /* Serialise to the LAS wire format (dazzler.d:1913-2170: int64 novl, int32 tspace, 40-byte records,
  * uint8 traces iff tspace <= 125). */
 int dn_las_write(const char *path, const dn_las_buf *buf);
