@@ -402,7 +402,8 @@ void align_blocks(const DevBlock &A, const DevBlock &B, const AlignParams &P, Ho
 
     // ---- rounds of band filter -> seeds -> extension -> retirement ----------------------------
     ExtGeom EG{A.fwd.p, A.rc.p, B.fwd.p, B.rc.p, A.off.p, B.off.p, A.len.p, B.len.p,
-               P.tspace, P.cdiff, P.xdrop, P.wmax, P.poolmul, (u32)((1ull << 32) / (u32)P.tspace + 1), B.nreads};
+               P.tspace, P.cdiff, P.xdrop, P.wmax, P.poolmul, (u32)((1ull << 32) / (u32)P.tspace + 1), B.nreads,
+               (u32)A.fwd.n, (u32)B.fwd.n};
     {
         long long span = (long long)B.maxlen + B.maxlen / 2 + 64; if (A.maxlen < span) span = A.maxlen;
         if ((unsigned long long)span >= (1ull << 32) / (unsigned)P.tspace) throw Error("reads too long for the tile arithmetic");

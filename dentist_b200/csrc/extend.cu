@@ -39,6 +39,49 @@ __device__ __forceinline__ int slide(const u32 *__restrict__ A, u32 ga, const u3
     return s < lim ? s : lim;
 }
 
+// ---- experiment (DN_EXT_TMA=1): the first STAGE_BASES bases of a task's A and B windows staged in shared memory by one
+// bulk copy each (cp.async.bulk -> SASS UBLKCP, completion on an mbarrier); slides read the staged words with LDS and fall
+// back to the global path beyond them.  Same results; measured against the __ldg path in DESIGN.md.
+constexpr int STAGE_WORDS = 512;                     // 2 KB = 8192 bases per stream and warp
+constexpr int STAGE_BASES = STAGE_WORDS * 16;
+
+__device__ __forceinline__ u32 smem_u32(const void *p) { return (u32)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t *bar, int count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, u32 bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(void *dst, const void *src, u32 bytes, uint64_t *bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, u32 parity) {
+    asm volatile("{\n .reg .pred p;\n WAIT_%=:\n mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n @p bra DONE_%=;\n bra WAIT_%=;\n DONE_%=:\n}"
+                 ::"r"(smem_u32(bar)), "r"(parity) : "memory");
+}
+
+struct Staged { const u32 *sa, *sb; u32 a_base, b_base; int a_n, b_n; };     // staged bases [x_base, x_base + x_n)
+
+__device__ __forceinline__ u32 fetch16s(const u32 *__restrict__ w, u32 g, const u32 *__restrict__ sw, u32 base, int n) {
+    const u32 rel = g - base;
+    if ((int)rel + 32 <= n && g >= base) {
+        const u32 wi = rel >> 4; const int sh = (int)(rel & 15u) << 1;
+        return __funnelshift_r(sw[wi], sw[wi + 1], sh);
+    }
+    return fetch16(w, g);
+}
+__device__ __forceinline__ int slide_s(const u32 *__restrict__ A, u32 ga, const u32 *__restrict__ B, u32 gb, int lim, const Staged &S) {
+    int s = 0;
+    while (s < lim) {
+        u32 x = fetch16s(A, ga + s, S.sa, S.a_base, S.a_n) ^ fetch16s(B, gb + s, S.sb, S.b_base, S.b_n);
+        if (x) { s += (__ffs(x) - 1) >> 1; break; }
+        s += 16;
+    }
+    return s < lim ? s : lim;
+}
+
 __host__ __device__ inline int ext_span(int la, int lb) { long long s = (long long)lb + lb / 2 + 64; return la < s ? la : (int)s; }
 
 struct Task {
@@ -234,7 +277,7 @@ __global__ void __launch_bounds__(EXT_WARPS * 32) k_extend(const Seed *__restric
 // Register-resident variant for wmax <= 30 (the default): the window never exceeds 32 diagonals, lane l
 // owns the diagonal congruent to l mod 32, and V / T / R live in registers; neighbours are one shuffle
 // away.  No shared memory, no modular addressing, one slot per lane.  Same specification, same results.
-template <int MINB>
+template <int MINB, bool STAGE>
 __global__ void __launch_bounds__(EXT_WARPS * 32, MINB) k_extend32(const Seed *__restrict__ seeds, int ntasks, ExtGeom G,
                                                              const int64_t *__restrict__ tile_off, int2 *__restrict__ tiles,
                                                              ExtOut *__restrict__ outs, int4 *__restrict__ pool_all,
@@ -245,6 +288,10 @@ __global__ void __launch_bounds__(EXT_WARPS * 32, MINB) k_extend32(const Seed *_
     const int ts = G.ts, C = G.cdiff, X = G.xdrop, WM = G.wmax;
     const int lane_l = (lane + 31) & 31, lane_r = (lane + 1) & 31;
     const u32 lt_mask = (1u << lane) - 1u;
+    __shared__ __align__(16) u32 s_seq[STAGE ? EXT_WARPS : 1][2][STAGE ? STAGE_WORDS : 4];
+    __shared__ uint64_t s_bar[STAGE ? EXT_WARPS : 1];
+    u32 parity = 0;
+    if (STAGE) { if (lane == 0) mbar_init(&s_bar[warp], 1); __syncwarp(); }
 
     for (;;) {
         int task = 0;
@@ -254,6 +301,23 @@ __global__ void __launch_bounds__(EXT_WARPS * 32, MINB) k_extend32(const Seed *_
         const Seed sd = seeds[task >> 1];
         const Task tk = make_task(sd, task & 1, G);
         const int la = tk.la, lb = tk.lb, firstT = tk.firstT;
+        Staged SG; SG.sa = s_seq[STAGE ? warp : 0][0]; SG.sb = s_seq[STAGE ? warp : 0][1]; SG.a_base = SG.b_base = 0; SG.a_n = SG.b_n = 0;
+        if (STAGE) {
+            // 16-byte aligned windows starting at the 64-base boundary below the task's first base, clipped to the arrays
+            SG.a_base = tk.ga & ~63u; SG.b_base = tk.gb & ~63u;
+            const u32 wa = SG.a_base >> 4, wb = SG.b_base >> 4;
+            const u32 na = min((u32)STAGE_WORDS, (tk.A == G.a_fwd || tk.A == G.a_rc ? G.a_words : G.b_words) - wa) & ~3u;
+            const u32 nb = min((u32)STAGE_WORDS, (tk.B == G.b_fwd || tk.B == G.b_rc ? G.b_words : G.a_words) - wb) & ~3u;
+            SG.a_n = (int)na * 16; SG.b_n = (int)nb * 16;
+            __syncwarp();                                       // the previous task's LDS reads are done
+            if (lane == 0) {
+                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                mbar_expect_tx(&s_bar[warp], (na + nb) * 4u);
+                if (na) bulk_g2s(s_seq[warp][0], tk.A + wa, na * 4u, &s_bar[warp]);
+                if (nb) bulk_g2s(s_seq[warp][1], tk.B + wb, nb * 4u, &s_bar[warp]);
+            }
+            mbar_wait(&s_bar[warp], parity); parity ^= 1u;
+        }
         const int poolcap = G.poolmul * (ext_span(la, lb) / ts + 4);
         auto NB = [&](int i) -> int { return i >= firstT ? (int)__umulhi((u32)(i - firstT), G.ts_magic) + 1 : 0; };
 
@@ -262,7 +326,7 @@ __global__ void __launch_bounds__(EXT_WARPS * 32, MINB) k_extend32(const Seed *_
         int bS = NEGS, bi = 0, bk = 0, bd = 0, bT = -1;     // lane-local best
         int gbest;
         {   // wave 0 (uniform): diagonal 0 lives in lane 0
-            const int i = slide(tk.A, tk.ga, tk.B, tk.gb, la < lb ? la : lb);
+            const int i = STAGE ? slide_s(tk.A, tk.ga, tk.B, tk.gb, la < lb ? la : lb, SG) : slide(tk.A, tk.ga, tk.B, tk.gb, la < lb ? la : lb);
             const int n = NB(i);
             if (n > poolcap) {
                 if (lane == 0) outs[task] = ExtOut{0, 0, 0, 0};
@@ -296,7 +360,8 @@ __global__ void __launch_bounds__(EXT_WARPS * 32, MINB) k_extend32(const Seed *_
                 const int j = i - k;
                 if (i <= NEGV + 1 || i > la || j > lb || j < 0) i = NEGV;
                 else {
-                    i += slide(tk.A, tk.ga + i, tk.B, tk.gb + j, min(la - i, lb - j));
+                    i += STAGE ? slide_s(tk.A, tk.ga + i, tk.B, tk.gb + j, min(la - i, lb - j), SG)
+                               : slide(tk.A, tk.ga + i, tk.B, tk.gb + j, min(la - i, lb - j));
                     // tile boundaries crossed: almost always 0 or 1 (a second one needs a slide of >= ts bases); written
                     // this way the common case costs one compare instead of the division the counted loop compiles to
                     // (ts_magic: exact floor(x / ts) for every x the length check in align_blocks admits)
@@ -575,8 +640,10 @@ void launch_extend(const Seed *seeds, int nseeds, ExtGeom G, const int64_t *tile
                    int4 *pool, int64_t pool_stride, int nwarps_total, int *counter, cudaStream_t s) {
     int ctas = nwarps_total / EXT_WARPS;
     // two register budgets of the same kernel: 5 resident CTAs per SM (48 registers) or 6 (40 registers, a few spilled words)
-    if (G.wmax <= 30 && ext_ctas_per_sm() >= 6) DN_LAUNCH(k_extend32<6>, ctas, EXT_WARPS * 32, 0, s, seeds, 2 * nseeds, G, tile_off, tiles, outs, pool, pool_stride, counter);
-    else if (G.wmax <= 30) DN_LAUNCH(k_extend32<5>, ctas, EXT_WARPS * 32, 0, s, seeds, 2 * nseeds, G, tile_off, tiles, outs, pool, pool_stride, counter);
+    static const bool stage = getenv("DN_EXT_TMA") != nullptr;
+    if (G.wmax <= 30 && stage) DN_LAUNCH((k_extend32<5, true>), ctas, EXT_WARPS * 32, 0, s, seeds, 2 * nseeds, G, tile_off, tiles, outs, pool, pool_stride, counter);
+    else if (G.wmax <= 30 && ext_ctas_per_sm() >= 6) DN_LAUNCH((k_extend32<6, false>), ctas, EXT_WARPS * 32, 0, s, seeds, 2 * nseeds, G, tile_off, tiles, outs, pool, pool_stride, counter);
+    else if (G.wmax <= 30) DN_LAUNCH((k_extend32<5, false>), ctas, EXT_WARPS * 32, 0, s, seeds, 2 * nseeds, G, tile_off, tiles, outs, pool, pool_stride, counter);
     else DN_LAUNCH(k_extend, ctas, EXT_WARPS * 32, 0, s, seeds, 2 * nseeds, G, tile_off, tiles, outs, pool, pool_stride, counter);
 }
 void launch_combine(const Seed *seeds, int nseeds, ExtGeom G, int minlen, const int64_t *tile_off, const int2 *tiles,

@@ -88,6 +88,7 @@ struct ExtGeom {
     const int64_t *a_off, *b_off; const int32_t *a_len, *b_len;
     int ts, cdiff, xdrop, wmax, poolmul; u32 ts_magic;
     int nb_reads;
+    u32 a_words, b_words;           // packed words allocated per strand array (bounds of the staged bulk copies)
 };
 void launch_task_caps(const Seed *seeds, int nseeds, ExtGeom G, u32 *caps, cudaStream_t s);
 void launch_extend(const Seed *seeds, int nseeds, ExtGeom G, const int64_t *tile_off, int2 *tiles, ExtOut *outs,
