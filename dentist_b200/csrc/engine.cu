@@ -261,6 +261,12 @@ void align_blocks(const DevBlock &A, const DevBlock &B, const AlignParams &P, Ho
             cudaStreamSetAttribute(s, cudaStreamAttributeAccessPolicyWindow, &av); cudaGetLastError();
         }
         DBuf<int64_t> seg_beg((size_t)nseg + 1); DBuf<int32_t> seg_len((size_t)nseg + 1);
+        // segments by size class, dealt out on the device right after the scan (ccnt[3] = segments beyond every class)
+        const int scaps[3] = {2048, 8192, 16384};
+        const bool seg_ok = gdbits + aposbits <= 63 && !getenv("DN_NO_SEGSORT");
+        const bool radix = gdbits <= 32 && !getenv("DN_BITONIC");     // stable radix by gd: hits -> hits2
+        DBuf<int32_t> clists((size_t)4 * nseg + 1); DBuf<u32> ccnt(4); ccnt.zero(s);
+        u32 hcc[4] = {0, 0, 0, 0};
         // (a fused one-CTA-per-read count+reserve+emit kernel was measured at 2x the time of these two passes:
         //  the lookups are latency-bound and want full occupancy, which the per-read shared-memory state prevents)
         {
@@ -284,9 +290,13 @@ void align_blocks(const DevBlock &A, const DevBlock &B, const AlignParams &P, Ho
                               (const ulonglong2 *)sw, (const u32 *)tbl.p, sh, P.t, (const u32 *)kbits.p, kshift, JG, wcnt.p, hitmask.p, wlist.p, nlist.p);
             }
             exclusive_scan_u32_to_i64(wcnt.p, woff.p, 2 * nwB, dtotal.p, s);
-            H = d2h_scalar(dtotal.p, s);
+            // radix variant writes to the other buffer: singletons are copied too (minimum length 1)
+            launch_seg_offsets(woff.p, B.off.p, B.nreads, nwB, dtotal.p, seg_beg.p, seg_len.p, radix ? 1 : 2, scaps, clists.p, ccnt.p, s);
             u32 nl[2] = {0, 0};
-            DN_CUDA(cudaMemcpyAsync(nl, nlist.p, 8, cudaMemcpyDeviceToHost, s)); DN_CUDA(cudaStreamSynchronize(s));
+            DN_CUDA(cudaMemcpyAsync(&H, dtotal.p, 8, cudaMemcpyDeviceToHost, s));            // ONE drain: hit total, word lists, class counts
+            DN_CUDA(cudaMemcpyAsync(nl, nlist.p, 8, cudaMemcpyDeviceToHost, s));
+            DN_CUDA(cudaMemcpyAsync(hcc, ccnt.p, 16, cudaMemcpyDeviceToHost, s));
+            DN_CUDA(cudaStreamSynchronize(s));
             if (H >= (1ll << 31) - 4096) throw Error("too many seed hits for one block pair (>= 2^31); use smaller blocks or lower -t");
             hits.alloc((size_t)H + 1); hits2.alloc((size_t)H + 1);
             if (H > 0)
@@ -309,7 +319,6 @@ void align_blocks(const DevBlock &A, const DevBlock &B, const AlignParams &P, Ho
                                   (const ulonglong2 *)sw, (const u32 *)tbl.p, sh, P.t, (const unsigned short *)(hitmask.p + st * nwB), (const u32 *)(wcnt.p + st * nwB),
                                   (const int64_t *)(woff.p + st * nwB), st, JG, hits.p, (const u32 *)(wlist.p + st * nwB));
                 }
-            launch_seg_offsets(woff.p, B.off.p, B.nreads, nwB, H, seg_beg.p, seg_len.p, s);
             abytes += 2 * (nB / 4) * 2 + 2 * nwB * (4 + 4 + 8 + 8 + 4) + 16 * H;   // packed B read twice per strand, word counts/offsets, hits
         }
         if (H >= (1ll << 31) - 4096) throw Error("too many seed hits for one block pair (>= 2^31); use smaller blocks or lower -t");
@@ -319,50 +328,35 @@ void align_blocks(const DevBlock &A, const DevBlock &B, const AlignParams &P, Ho
             cudaCtxResetPersistingL2Cache(); cudaGetLastError();
         }
         // every (strand, read) segment is contiguous and, per diagonal, already in apos order: sort inside the segments only
-        if (H > 0 && gdbits + aposbits <= 63 && !getenv("DN_NO_SEGSORT")) {
-            std::vector<int64_t> hbeg(nseg); std::vector<int32_t> hlen(nseg);
-            DN_CUDA(cudaMemcpyAsync(hbeg.data(), seg_beg.p, sizeof(int64_t) * nseg, cudaMemcpyDeviceToHost, s));
-            DN_CUDA(cudaMemcpyAsync(hlen.data(), seg_len.p, sizeof(int32_t) * nseg, cudaMemcpyDeviceToHost, s));
-            DN_CUDA(cudaStreamSynchronize(s));
-            std::vector<int32_t> cls[3]; const int caps[3] = {2048, 8192, 16384};
-            const bool radix = gdbits <= 32 && !getenv("DN_BITONIC");     // stable radix by gd: hits -> hits2
-            std::vector<int> big;                       // segments too large for shared memory
-            int64_t nbig = 0;
-            for (int i = 0; i < nseg; i++) {
-                const int64_t len = hlen[i];
-                if (len < (radix ? 1 : 2)) continue;              // the radix variant writes to the other buffer: copy singletons too
-                int c = 0; while (c < 3 && len > caps[c]) c++;
-                if (c == 3) { big.push_back(i); nbig += len; } else cls[c].push_back(i);
+        if (H > 0 && seg_ok && hcc[3] <= 256) {
+            if (getenv("DN_TRACE"))
+                fprintf(stderr, "[dn trace] two-pass join, segments %d, classes %u/%u/%u, oversized %u\n", nseg, hcc[0], hcc[1], hcc[2], hcc[3]);
+            for (int c = 0; c < 3; c++) {
+                if (hcc[c] == 0) continue;
+                const int32_t *lst = clists.p + (size_t)c * nseg;
+                if (radix) launch_segsort_radix(hits.p, hits2.p, seg_beg.p, seg_len.p, lst, (int)hcc[c], scaps[c], gdbits, s);
+                else launch_segsort(hits.p, seg_beg.p, seg_len.p, lst, (int)hcc[c], scaps[c], gdbits, aposbits, s);
             }
-            const bool fits = big.size() <= 256;
-            if (getenv("DN_TRACE")) {
-                int64_t mx = 0; for (int i = 0; i < nseg; i++) mx = std::max<int64_t>(mx, hlen[i]);
-                fprintf(stderr, "[dn trace] %s join, segments %d, largest %lld hits, classes %zu/%zu/%zu, oversized %zu (%lld hits), fits %d\n",
-                        "two-pass", nseg, (long long)mx, cls[0].size(), cls[1].size(), cls[2].size(), big.size(), (long long)nbig, (int)fits);
+            ulonglong2 *sorted = radix ? hits2.p : hits.p;
+            if (hcc[3] > 0) {
+                // the few oversized segments: gather, radix sort by (bs, gd, apos), copy back segment by segment (ascending bs)
+                std::vector<int32_t> big(hcc[3]); std::vector<int64_t> hbeg(nseg); std::vector<int32_t> hlen(nseg);
+                DN_CUDA(cudaMemcpyAsync(big.data(), clists.p + (size_t)3 * nseg, sizeof(int32_t) * hcc[3], cudaMemcpyDeviceToHost, s));
+                DN_CUDA(cudaMemcpyAsync(hbeg.data(), seg_beg.p, sizeof(int64_t) * nseg, cudaMemcpyDeviceToHost, s));
+                DN_CUDA(cudaMemcpyAsync(hlen.data(), seg_len.p, sizeof(int32_t) * nseg, cudaMemcpyDeviceToHost, s));
+                DN_CUDA(cudaStreamSynchronize(s));
+                std::sort(big.begin(), big.end());
+                int64_t nbig = 0; for (int i : big) nbig += hlen[i];
+                DBuf<ulonglong2> t1(nbig), t2(nbig);
+                int64_t o = 0;
+                for (int i : big) { DN_CUDA(cudaMemcpyAsync(t1.p + o, hits.p + hbeg[i], 16 * (int64_t)hlen[i], cudaMemcpyDeviceToDevice, s)); o += hlen[i]; }
+                ulonglong2 *r = radix_sort_rec16(t1.p, t2.p, nbig, 1, 0, aposbits, s);
+                r = radix_sort_rec16(r, r == t1.p ? t2.p : t1.p, nbig, 0, 0, keybits, s);
+                o = 0;
+                for (int i : big) { DN_CUDA(cudaMemcpyAsync(sorted + hbeg[i], r + o, 16 * (int64_t)hlen[i], cudaMemcpyDeviceToDevice, s)); o += hlen[i]; }
             }
-            if (fits) {
-                for (int c = 0; c < 3; c++) {
-                    if (cls[c].empty()) continue;
-                    DBuf<int32_t> lst(cls[c].size());
-                    DN_CUDA(cudaMemcpyAsync(lst.p, cls[c].data(), sizeof(int32_t) * cls[c].size(), cudaMemcpyHostToDevice, s));
-                    if (radix) launch_segsort_radix(hits.p, hits2.p, seg_beg.p, seg_len.p, lst.p, (int)cls[c].size(), caps[c], gdbits, s);
-                    else launch_segsort(hits.p, seg_beg.p, seg_len.p, lst.p, (int)cls[c].size(), caps[c], gdbits, aposbits, s);
-                }
-                ulonglong2 *sorted = radix ? hits2.p : hits.p;
-                if (!big.empty()) {
-                    // the few oversized segments: gather, radix sort by (bs, gd, apos), copy back segment by segment (ascending bs)
-                    DBuf<ulonglong2> t1(nbig), t2(nbig);
-                    int64_t o = 0;
-                    for (int i : big) { DN_CUDA(cudaMemcpyAsync(t1.p + o, hits.p + hbeg[i], 16 * (int64_t)hlen[i], cudaMemcpyDeviceToDevice, s)); o += hlen[i]; }
-                    ulonglong2 *r = radix_sort_rec16(t1.p, t2.p, nbig, 1, 0, aposbits, s);
-                    r = radix_sort_rec16(r, r == t1.p ? t2.p : t1.p, nbig, 0, 0, keybits, s);
-                    o = 0;
-                    for (int i : big) { DN_CUDA(cudaMemcpyAsync(sorted + hbeg[i], r + o, 16 * (int64_t)hlen[i], cudaMemcpyDeviceToDevice, s)); o += hlen[i]; }
-                }
-                DN_CUDA(cudaStreamSynchronize(s));      // cls[] vectors are read by the async copies above
-                segsorted = true; seg_in_hits2 = radix;
-                abytes += 32 * H + 12ll * nseg;
-            }
+            segsorted = true; seg_in_hits2 = radix;
+            abytes += 32 * H + 12ll * nseg;
         }
     } else {
         DBuf<u64> tb(2 * nB), tb2(2 * nB);
@@ -382,7 +376,7 @@ void align_blocks(const DevBlock &A, const DevBlock &B, const AlignParams &P, Ho
                       (const u32 *)cnt.p, (const u32 *)start.p, (const int64_t *)hoff.p, JG, hits.p, ninv.p);
         abytes += 2 * (nB / 4) + 8 * 2 * nB + (int64_t)npass_t * 24 * 2 * nB + 2 * 8 * 2 * nB + 16 * 2 * nB + 16 * H;
     }
-    const int64_t ninvalid = (int64_t)d2h_scalar(ninv.p, s);
+    const int64_t ninvalid = lookup ? 0 : (int64_t)d2h_scalar(ninv.p, s);      // the lookup join never emits a self / cross-pile pair
     tr.mark("join");
     ta.release(); ta2.release(); tw.release(); tw2.release(); tbl_own.release();
 
@@ -445,10 +439,21 @@ void align_blocks(const DevBlock &A, const DevBlock &B, const AlignParams &P, Ho
         out.stats.seeds += nseeds; out.stats.extensions += 2ll * nseeds;
 
         // ---- K5: extension
-        DBuf<u32> caps(2 * (size_t)nseeds); DBuf<int64_t> tile_off(2 * (size_t)nseeds);
-        launch_task_caps(seeds.p, nseeds, EG, caps.p, s);
-        exclusive_scan_u32_to_i64(caps.p, tile_off.p, 2 * (size_t)nseeds, dtotal.p, s);
-        const int64_t ntile_cap = d2h_scalar(dtotal.p, s);
+        DBuf<int64_t> tile_off(2 * (size_t)nseeds);
+        int64_t ntile_cap;
+        {   // one tile capacity for every task when that stays affordable: no per-task caps, no scan, no host round trip
+            long long sp = (long long)B.maxlen + B.maxlen / 2 + 64; if (A.maxlen < sp) sp = A.maxlen;
+            const int64_t capmax = sp / P.tspace + 3;
+            if (2ll * nseeds * capmax * (int64_t)sizeof(int2) <= (1ll << 30)) {
+                launch_task_strides(nseeds, capmax, tile_off.p, s);
+                ntile_cap = 2ll * nseeds * capmax;
+            } else {
+                DBuf<u32> caps(2 * (size_t)nseeds);
+                launch_task_caps(seeds.p, nseeds, EG, caps.p, s);
+                exclusive_scan_u32_to_i64(caps.p, tile_off.p, 2 * (size_t)nseeds, dtotal.p, s);
+                ntile_cap = d2h_scalar(dtotal.p, s);
+            }
+        }
         DBuf<int2> tiles((size_t)ntile_cap + 1); DBuf<ExtOut> outs(2 * (size_t)nseeds);
         const int wpc = ext_warps_per_cta();
         int ctas = sm_count() * ext_ctas_per_sm();    // 48 registers: 5 CTAs x 8 warps per SM (DN_EXT_CTAS=6: the 40-register build)
@@ -468,23 +473,27 @@ void align_blocks(const DevBlock &A, const DevBlock &B, const AlignParams &P, Ho
         }
         tr.mark("k_extend");
 
-        // ---- K6: candidates, traces, retirement
+        // ---- K6: candidates, traces, retirement.  The kept alignments are counted on the device; their buffers are sized by
+        // upper bounds (every seed kept; every tile slot used), so combine -> traces -> retire -> compaction offsets run without
+        // the host, which reads the three totals in ONE drain at the end of the round.
         DBuf<Cand> cand_all(nseeds); DBuf<int32_t> valid(nseeds), vidx(nseeds); DBuf<u32> ntl(nseeds); DBuf<int64_t> toff(nseeds);
         launch_combine(seeds.p, nseeds, EG, P.minlen, tile_off.p, tiles.p, outs.p, cand_all.p, valid.p, ntl.p, s);
         exclusive_scan_i32(valid.p, vidx.p, nseeds, dtot32.p, s);
         exclusive_scan_u32_to_i64(ntl.p, toff.p, nseeds, dtotal.p, s);
-        const int32_t nvalid = d2h_scalar(dtot32.p, s);              // both scans are queued: one drain serves the two reads
-        const int64_t ntr = d2h_scalar(dtotal.p, s);
+        DBuf<Cand> rc((size_t)nseeds + 1); DBuf<uint16_t> rtr((size_t)2 * ntile_cap + 2);
+        launch_write_traces(seeds.p, nseeds, EG, tile_off.p, tiles.p, outs.p, cand_all.p, valid.p, vidx.p, toff.p, rc.p, rtr.p, s);
+        DBuf<int32_t> keep(n), kidx(n);
+        launch_retire((const ulonglong2 *)hs, n, consumed.p, rc.p, dtot32.p, SG, P.w, bflag.p, bidx.p, hot.p, keep.p, s);
+        exclusive_scan_i32(keep.p, kidx.p, n, dtot32.p + 1, s);
+        int32_t two2[2]; int64_t ntr = 0;
+        DN_CUDA(cudaMemcpyAsync(two2, dtot32.p, 8, cudaMemcpyDeviceToHost, s));
+        DN_CUDA(cudaMemcpyAsync(&ntr, dtotal.p, 8, cudaMemcpyDeviceToHost, s));
+        DN_CUDA(cudaStreamSynchronize(s));
+        const int32_t nvalid = two2[0]; const int64_t n_new = two2[1];
         if (nvalid == 0) {                                            // no group kept anything: every group is finished (spec item 7)
             if (getenv("DN_TRACE")) fprintf(stderr, "[dn trace] round %d: %lld hits, %d bands, %d seeds, no candidate >= minlen: stop\n", round, (long long)n, nbands, nseeds);
             break;
         }
-        DBuf<Cand> rc((size_t)nvalid + 1); DBuf<uint16_t> rtr((size_t)2 * ntr + 2);
-        launch_write_traces(seeds.p, nseeds, EG, tile_off.p, tiles.p, outs.p, cand_all.p, valid.p, vidx.p, toff.p, rc.p, rtr.p, s);
-        DBuf<int32_t> keep(n), kidx(n);
-        launch_retire((const ulonglong2 *)hs, n, consumed.p, rc.p, nvalid, SG, P.w, bflag.p, bidx.p, hot.p, keep.p, s);
-        exclusive_scan_i32(keep.p, kidx.p, n, dtot32.p, s);
-        const int64_t n_new = d2h_scalar(dtot32.p, s);
         launch_compact_hits((const ulonglong2 *)hs, n, keep.p, kidx.p, ho, s);      // same stream: the next round is ordered behind it
         std::swap(hs, ho);
         abytes += 24 * n + 16 * n_new;
@@ -519,39 +528,36 @@ void align_blocks(const DevBlock &A, const DevBlock &B, const AlignParams &P, Ho
             ulonglong2 *res = radix_sort_rec16(cur, oth, ncand, 0, 0, fbits[f], s);
             if (res != cur) { oth = cur; cur = res; }
         }
+        // records and traces are laid out for all ncand items (the dropped duplicates sort to the end and get no record);
+        // the buffers are sized by the bounds the host already knows, so the counters travel with the result: ONE drain
+        int64_t trbound = 0; for (int64_t v : round_ntr) trbound += v;
+        DBuf<dn_las_record> drec(ncand); DBuf<u32> tl(ncand); DBuf<int64_t> dtoff(ncand);
+        launch_final_records(all.p, cur, ncand, B.nreads, drec.p, tl.p, ctr.p, s);
+        exclusive_scan_u32_to_i64(tl.p, dtoff.p, ncand, dtotal.p, s);
+        FinalGeom FG; memset(&FG, 0, sizeof FG); FG.nrounds = nrounds;
+        for (int r = 0; r < nrounds; r++) { FG.round_trace[r] = round_traces[r].p; FG.round_beg[r] = round_beg[r]; }
+        FG.round_beg[nrounds] = round_beg[nrounds];
+        DBuf<uint16_t> dtr((size_t)trbound + 1);
+        launch_final_traces(all.p, cur, ncand, ctr.p, dtoff.p, FG, dtr.p, s);
+        tr.mark("final records + traces");
         unsigned long long hctr[3];
-        DN_CUDA(cudaMemcpyAsync(hctr, ctr.p, sizeof hctr, cudaMemcpyDeviceToHost, s)); DN_CUDA(cudaStreamSynchronize(s));
+        if (!keep) {
+            out.rec = (dn_las_record *)hcache_alloc(sizeof(dn_las_record) * ((size_t)ncand + 1));
+            out.toff = (int64_t *)hcache_alloc(sizeof(int64_t) * ((size_t)ncand + 1));
+            out.trace = (uint16_t *)hcache_alloc(sizeof(uint16_t) * ((size_t)trbound + 1));
+            tr.mark("host buffer alloc");
+            DN_CUDA(cudaMemcpyAsync(out.rec, drec.p, sizeof(dn_las_record) * ncand, cudaMemcpyDeviceToHost, s));
+            DN_CUDA(cudaMemcpyAsync(out.toff, dtoff.p, sizeof(int64_t) * ncand, cudaMemcpyDeviceToHost, s));
+            if (trbound) DN_CUDA(cudaMemcpyAsync(out.trace, dtr.p, sizeof(uint16_t) * trbound, cudaMemcpyDeviceToHost, s));
+        }
+        DN_CUDA(cudaMemcpyAsync(hctr, ctr.p, sizeof hctr, cudaMemcpyDeviceToHost, s));
+        DN_CUDA(cudaMemcpyAsync(&tot, dtotal.p, 8, cudaMemcpyDeviceToHost, s));
+        DN_CUDA(cudaStreamSynchronize(s));
         const int nkeep = ncand - (int)hctr[0];
         if (getenv("DN_TRACE")) fprintf(stderr, "[dn trace] candidates %d, kept after duplicate removal %d\n", ncand, nkeep);
-        tr.mark("dedupe + final sort");
         out.nrec = nkeep;
-        if (!keep) {
-            out.rec = (dn_las_record *)hcache_alloc(sizeof(dn_las_record) * ((size_t)nkeep + 1));
-            out.toff = (int64_t *)hcache_alloc(sizeof(int64_t) * ((size_t)nkeep + 1));
-        }
-        if (nkeep > 0) {
-            DBuf<dn_las_record> drec(nkeep); DBuf<u32> tl(nkeep); DBuf<int64_t> dtoff(nkeep);
-            launch_final_records(all.p, cur, nkeep, B.nreads, drec.p, tl.p, ctr.p + 1, s);
-            exclusive_scan_u32_to_i64(tl.p, dtoff.p, nkeep, dtotal.p, s);
-            tot = d2h_scalar(dtotal.p, s);
-            FinalGeom FG; memset(&FG, 0, sizeof FG); FG.nrounds = nrounds;
-            for (int r = 0; r < nrounds; r++) { FG.round_trace[r] = round_traces[r].p; FG.round_beg[r] = round_beg[r]; }
-            FG.round_beg[nrounds] = round_beg[nrounds];
-            DBuf<uint16_t> dtr((size_t)tot + 1);
-            launch_final_traces(all.p, cur, nkeep, dtoff.p, FG, dtr.p, s);
-            tr.mark("final records + traces");
-            if (keep) { keep->rec = drec.p; keep->toff = dtoff.p; keep->trace = dtr.p; keep->nrec = nkeep; keep->ntrace = tot; }
-            else {
-                out.trace = (uint16_t *)hcache_alloc(sizeof(uint16_t) * ((size_t)tot + 1));
-                tr.mark("host buffer alloc");
-                DN_CUDA(cudaMemcpyAsync(out.rec, drec.p, sizeof(dn_las_record) * nkeep, cudaMemcpyDeviceToHost, s));
-                DN_CUDA(cudaMemcpyAsync(out.toff, dtoff.p, sizeof(int64_t) * nkeep, cudaMemcpyDeviceToHost, s));
-                if (tot) DN_CUDA(cudaMemcpyAsync(out.trace, dtr.p, sizeof(uint16_t) * tot, cudaMemcpyDeviceToHost, s));
-            }
-            DN_CUDA(cudaMemcpyAsync(hctr, ctr.p, sizeof hctr, cudaMemcpyDeviceToHost, s));
-            DN_CUDA(cudaStreamSynchronize(s));
-            aligned = (int64_t)hctr[1]; ext_bytes = (int64_t)hctr[2];
-        }
+        aligned = (int64_t)hctr[1]; ext_bytes = (int64_t)hctr[2];
+        if (keep) { keep->rec = drec.p; keep->toff = dtoff.p; keep->trace = dtr.p; keep->nrec = nkeep; keep->ntrace = tot; }
     }
     if (keep) { out.nrec = 0; tot = keep->ntrace; }          // the records stay in HBM: the host result holds the statistics only
     if (!out.rec) out.rec = (dn_las_record *)hcache_alloc(64);

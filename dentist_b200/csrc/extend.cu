@@ -511,11 +511,12 @@ __device__ __forceinline__ int group_lower(const Cand *__restrict__ c, int lo, i
 }
 
 __global__ void __launch_bounds__(256) k_retire(const ulonglong2 *__restrict__ hits, int64_t n, const uint8_t *__restrict__ consumed,
-                                                const Cand *__restrict__ rc, int nrc, SeedGeom G, int w,
+                                                const Cand *__restrict__ rc, const int32_t *__restrict__ d_nrc, SeedGeom G, int w,
                                                 const int32_t *__restrict__ bflag, const int32_t *__restrict__ bidx,
                                                 const uint8_t *__restrict__ hot, int32_t *__restrict__ keep) {
     int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
+    const int nrc = *d_nrc;                              // alignments kept this round: counted on the device, never seen by the host before
     int kp = consumed[i] ? 0 : 1;
     // a hit in a cold band can never become part of a hot band later (scores only shrink): drop it for good.
     // Pure optimisation -- the later rounds see exactly the clusters they would have seen anyway.
@@ -591,11 +592,13 @@ __global__ void __launch_bounds__(256) k_final_setkey(const Cand *__restrict__ c
     items[i] = make_ulonglong2(key, idx);
 }
 
-__global__ void __launch_bounds__(256) k_final_records(const Cand *__restrict__ c, const ulonglong2 *__restrict__ items, int nkeep,
+__global__ void __launch_bounds__(256) k_final_records(const Cand *__restrict__ c, const ulonglong2 *__restrict__ items, int ncand,
                                                        int nb_reads, dn_las_record *__restrict__ rec, u32 *__restrict__ tl,
-                                                       unsigned long long *__restrict__ acc /* [0] aligned bases, [1] ext bytes */) {
+                                                       unsigned long long *__restrict__ ctr /* [0] dropped, [1] aligned bases, [2] ext bytes */) {
     int o = blockIdx.x * blockDim.x + threadIdx.x;
-    if (o >= nkeep) return;
+    if (o >= ncand) return;
+    if (o >= ncand - (int)ctr[0]) { tl[o] = 0u; return; }          // dropped duplicates sort to the end: no record, no trace
+    unsigned long long *acc = ctr + 1;
     const Cand x = c[items[o].y];
     dn_las_record q;
     q.tlen = 2 * x.nt; q.diffs = x.diffs; q.abpos = x.ab; q.bbpos = x.bb; q.aepos = x.ae; q.bepos = x.be;
@@ -607,10 +610,11 @@ __global__ void __launch_bounds__(256) k_final_records(const Cand *__restrict__ 
 }
 
 // one warp per record: copy its (diffs, bbases) pairs from the round buffer to the output position
-__global__ void __launch_bounds__(256) k_final_traces(const Cand *__restrict__ c, const ulonglong2 *__restrict__ items, int nkeep,
+__global__ void __launch_bounds__(256) k_final_traces(const Cand *__restrict__ c, const ulonglong2 *__restrict__ items, int ncand,
+                                                      const unsigned long long *__restrict__ ctr,
                                                       const int64_t *__restrict__ toff, FinalGeom G, uint16_t *__restrict__ out) {
     const int o = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
-    if (o >= nkeep) return;
+    if (o >= ncand - (int)ctr[0]) return;
     const int j = (int)items[o].y;
     const Cand x = c[j];
     int r = 0;
@@ -626,11 +630,19 @@ void launch_final_setkey(const Cand *c, const uint8_t *drop, ulonglong2 *items, 
                          unsigned long long *ndrop, cudaStream_t s) {
     DN_LAUNCH(k_final_setkey, (n + 255) / 256, 256, 0, s, c, drop, items, n, field, fb, ndrop);
 }
-void launch_final_records(const Cand *c, const ulonglong2 *items, int nkeep, int nb_reads, dn_las_record *rec, u32 *tl, unsigned long long *acc, cudaStream_t s) {
-    DN_LAUNCH(k_final_records, (nkeep + 255) / 256, 256, 0, s, c, items, nkeep, nb_reads, rec, tl, acc);
+void launch_final_records(const Cand *c, const ulonglong2 *items, int ncand, int nb_reads, dn_las_record *rec, u32 *tl, unsigned long long *ctr, cudaStream_t s) {
+    DN_LAUNCH(k_final_records, (ncand + 255) / 256, 256, 0, s, c, items, ncand, nb_reads, rec, tl, ctr);
 }
-void launch_final_traces(const Cand *c, const ulonglong2 *items, int nkeep, const int64_t *toff, FinalGeom G, uint16_t *out, cudaStream_t s) {
-    DN_LAUNCH(k_final_traces, (nkeep * 32 + 255) / 256, 256, 0, s, c, items, nkeep, toff, G, out);
+void launch_final_traces(const Cand *c, const ulonglong2 *items, int ncand, const unsigned long long *ctr, const int64_t *toff, FinalGeom G, uint16_t *out, cudaStream_t s) {
+    DN_LAUNCH(k_final_traces, (unsigned)(((int64_t)ncand * 32 + 255) / 256), 256, 0, s, c, items, ncand, ctr, toff, G, out);
+}
+namespace { __global__ void __launch_bounds__(256) k_task_strides(int ntasks, int64_t stride, int64_t *__restrict__ tile_off) {
+    int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t < ntasks) tile_off[t] = (int64_t)t * stride;
+} }
+// every task gets the same tile capacity: no per-task caps, no scan, no host round trip for their sum
+void launch_task_strides(int nseeds, int64_t stride, int64_t *tile_off, cudaStream_t s) {
+    DN_LAUNCH(k_task_strides, (2 * nseeds + 255) / 256, 256, 0, s, 2 * nseeds, stride, tile_off);
 }
 
 void launch_task_caps(const Seed *seeds, int nseeds, ExtGeom G, u32 *caps, cudaStream_t s) {
@@ -656,9 +668,9 @@ void launch_write_traces(const Seed *seeds, int nseeds, ExtGeom G, const int64_t
     DN_LAUNCH(k_write_traces, (nseeds + 255) / 256, 256, 0, s, seeds, nseeds, G, tile_off, tiles, outs, cand_all, valid, vidx,
               toff, cand_out, trace);
 }
-void launch_retire(const ulonglong2 *hits, int64_t n, const uint8_t *consumed, const Cand *rc, int nrc, SeedGeom G, int w,
+void launch_retire(const ulonglong2 *hits, int64_t n, const uint8_t *consumed, const Cand *rc, const int32_t *d_nrc, SeedGeom G, int w,
                    const int32_t *bflag, const int32_t *bidx, const uint8_t *hot, int32_t *keep, cudaStream_t s) {
-    DN_LAUNCH(k_retire, (unsigned)((n + 255) / 256), 256, 0, s, hits, n, consumed, rc, nrc, G, w, bflag, bidx, hot, keep);
+    DN_LAUNCH(k_retire, (unsigned)((n + 255) / 256), 256, 0, s, hits, n, consumed, rc, d_nrc, G, w, bflag, bidx, hot, keep);
 }
 void launch_compact_hits(const ulonglong2 *hits, int64_t n, const int32_t *keep, const int32_t *kidx, ulonglong2 *out, cudaStream_t s) {
     DN_LAUNCH(k_compact_hits, (unsigned)((n + 255) / 256), 256, 0, s, hits, n, keep, kidx, out);

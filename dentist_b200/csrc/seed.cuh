@@ -74,8 +74,8 @@ __global__ void k_lookup_emit_p(const u32 *seq, const u32 *maskbits, const int64
                                 const u32 *wcnt, const int64_t *woff, int strand, JoinGeom G, ulonglong2 *hits, const u32 *wlist);
 
 // segmented hit sort (segsort.cu)
-void launch_seg_offsets(const int64_t *woff, const int64_t *b_off, int nr, int64_t nwB, int64_t H, int64_t *seg_beg, int32_t *seg_len,
-                        cudaStream_t s);
+void launch_seg_offsets(const int64_t *woff, const int64_t *b_off, int nr, int64_t nwB, const int64_t *dH, int64_t *seg_beg, int32_t *seg_len,
+                        int minlen, const int *caps, int32_t *lists, u32 *counts, cudaStream_t s);
 void launch_segsort(ulonglong2 *hits, const int64_t *seg_beg, const int32_t *seg_len, const int32_t *seglist, int nseg, int cap, int gdbits,
                     int aposbits, cudaStream_t s);
 
@@ -98,15 +98,17 @@ void launch_combine(const Seed *seeds, int nseeds, ExtGeom G, int minlen, const 
 void launch_write_traces(const Seed *seeds, int nseeds, ExtGeom G, const int64_t *tile_off, const int2 *tiles,
                          const ExtOut *outs, const Cand *cand_all, const int32_t *valid, const int32_t *vidx,
                          const int64_t *toff, Cand *cand_out, uint16_t *trace, cudaStream_t s);
-void launch_retire(const ulonglong2 *hits, int64_t n, const uint8_t *consumed, const Cand *rc, int nrc, SeedGeom G, int w,
+void launch_retire(const ulonglong2 *hits, int64_t n, const uint8_t *consumed, const Cand *rc, const int32_t *d_nrc, SeedGeom G, int w,
                    const int32_t *bflag, const int32_t *bidx, const uint8_t *hot, int32_t *keep, cudaStream_t s);
 void launch_compact_hits(const ulonglong2 *hits, int64_t n, const int32_t *keep, const int32_t *kidx, ulonglong2 *out, cudaStream_t s);
 struct FinalBits { int na, nb, nra, nrb, nb_reads; };       // bits of: A coordinate, B coordinate, A read id, B read id
 struct FinalGeom { const uint16_t *round_trace[16]; int32_t round_beg[17]; int nrounds; };
 void launch_final_setkey(const Cand *c, const uint8_t *drop, ulonglong2 *items, int n, int field, FinalBits fb,
                          unsigned long long *ndrop, cudaStream_t s);
-void launch_final_records(const Cand *c, const ulonglong2 *items, int nkeep, int nb_reads, dn_las_record *rec, u32 *tl, unsigned long long *acc, cudaStream_t s);
-void launch_final_traces(const Cand *c, const ulonglong2 *items, int nkeep, const int64_t *toff, FinalGeom G, uint16_t *out, cudaStream_t s);
+// ncand items, of which the first ncand - ctr[0] are kept (ctr[0] = dropped duplicates, still on the device)
+void launch_final_records(const Cand *c, const ulonglong2 *items, int ncand, int nb_reads, dn_las_record *rec, u32 *tl, unsigned long long *ctr, cudaStream_t s);
+void launch_final_traces(const Cand *c, const ulonglong2 *items, int ncand, const unsigned long long *ctr, const int64_t *toff, FinalGeom G, uint16_t *out, cudaStream_t s);
+void launch_task_strides(int nseeds, int64_t stride, int64_t *tile_off, cudaStream_t s);
 void launch_dedupe(const Cand *cands, int ncand, const int32_t *round_beg, int nrounds, uint8_t *drop, cudaStream_t s);
 
 }  // namespace dn

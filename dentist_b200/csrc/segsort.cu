@@ -8,13 +8,23 @@
 namespace dn {
 namespace {
 
+// Segment extents from the scanned word offsets (H = total hits, still on the device), and -- in the same pass -- the
+// segments dealt out by size class: lists[c] collects the segments of class c (caps[0..2]; class 3 = larger than any
+// shared-memory class), counts[c] their number.  The host reads the four counts together with H: no second round trip.
 __global__ void __launch_bounds__(256) k_seg_offsets(const int64_t *__restrict__ woff, const int64_t *__restrict__ b_off, int nr,
-                                                     int64_t nwB, int64_t H, int64_t *__restrict__ seg_beg, int32_t *__restrict__ seg_len) {
+                                                     int64_t nwB, const int64_t *__restrict__ dH, int64_t *__restrict__ seg_beg,
+                                                     int32_t *__restrict__ seg_len, int minlen, int cap0, int cap1, int cap2,
+                                                     int32_t *__restrict__ lists /* [4][2 * nr] */, u32 *__restrict__ counts /* [4] */) {
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= 2 * nr) return;
+    const int64_t H = *dH;
     auto at = [&](int q) -> int64_t { if (q == 2 * nr) return H; const int st = q >= nr, r = q - st * nr; return woff[st * nwB + (b_off[r] >> 4)]; };
     const int64_t b = at(i);
-    seg_beg[i] = b; seg_len[i] = (int32_t)(at(i + 1) - b);
+    const int64_t len = at(i + 1) - b;
+    seg_beg[i] = b; seg_len[i] = (int32_t)len;
+    if (len < minlen) return;
+    const int c = len <= cap0 ? 0 : len <= cap1 ? 1 : len <= cap2 ? 2 : 3;
+    lists[(int64_t)c * 2 * nr + atomicAdd(&counts[c], 1u)] = i;
 }
 
 __global__ void __launch_bounds__(1024) k_segsort(ulonglong2 *__restrict__ hits, const int64_t *__restrict__ seg_beg,
@@ -146,9 +156,10 @@ __global__ void __launch_bounds__(WARPS * 32) k_segsort_radix(const ulonglong2 *
 
 }  // namespace
 
-void launch_seg_offsets(const int64_t *woff, const int64_t *b_off, int nr, int64_t nwB, int64_t H, int64_t *seg_beg, int32_t *seg_len,
-                        cudaStream_t s) {
-    DN_LAUNCH(k_seg_offsets, (2 * nr + 255) / 256, 256, 0, s, woff, b_off, nr, nwB, H, seg_beg, seg_len);
+void launch_seg_offsets(const int64_t *woff, const int64_t *b_off, int nr, int64_t nwB, const int64_t *dH, int64_t *seg_beg, int32_t *seg_len,
+                        int minlen, const int *caps, int32_t *lists, u32 *counts, cudaStream_t s) {
+    DN_LAUNCH(k_seg_offsets, (2 * nr + 255) / 256, 256, 0, s, woff, b_off, nr, nwB, dH, seg_beg, seg_len, minlen, caps[0], caps[1], caps[2],
+              lists, counts);
 }
 
 // cap = per-segment capacity class (power of two); segments in `seglist` have at most cap hits
