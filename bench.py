@@ -42,6 +42,89 @@ def make_workload(scale, rank):
     return ref, reads
 
 
+C3_WORKLOAD = "synthetic 100 Mbp assembly, 1000 gaps, 30x ONT-like 20 kb reads 12% error, 15 read blocks block-sharded (BASELINE.json configs[2])"
+C3_BLOCKS = 15
+
+
+def c3_blocks_of(rank, world, nblocks):
+    """Contiguous deal of the read blocks over the ranks (a rank's reads all precede the next rank's: the gather's
+    placement merge relies on it); the reference's fan-out is one damapper job per block (Snakefile:1143-1170)."""
+    base, rem = divmod(nblocks, world)
+    lo = rank * base + min(rank, rem)
+    return list(range(lo, lo + base + (1 if rank < rem else 0)))
+
+
+def make_c3(blocks):
+    """configs[2]: 100 scaffolds x 1 Mbp (seed 2001), 1000 gaps (seed 2002); read block b = 2x coverage (30x / 15 blocks) of
+    20 kb +- 10 kb reads, 12 % ONT-like error ins:del:sub .25:.45:.30 (seed 2003 + b)."""
+    sc = synth.make_scaffolds(100, 1000000, 2001)
+    gaps = synth.make_gaps(sc, 10, 2002)
+    ref, _ = synth.contigs_from(sc, gaps)
+    out = []
+    for b in blocks:
+        reads, _ = synth.simulate_reads(sc, 2.0, 20000, 10000, 0.12, 2003 + b, mix=(0.25, 0.45, 0.30))
+        out.append(reads)
+    return ref, out
+
+
+def run_c3(args, rank, world, dev, barrier, dist, torch, nblocks):
+    """One step = every read block of configs[2] against the assembly whose k-mer index is resident (dn_block_index), blocks
+    dealt contiguously over the ranks, each block's LAS gathered HBM to HBM onto rank 0 and merged there (csrc/comm.cu).
+    Returns the fields of the c3 line (rank 0) -- device-timed value, end-to-end value, per-stage times."""
+    from dentist_b200 import dazzler
+    mine = c3_blocks_of(rank, world, nblocks)
+    per_rank = -(-nblocks // world)
+    t0 = time.perf_counter()
+    ref, blocks = make_c3(mine)
+    gen_s = time.perf_counter() - t0
+    ga = dazzler.Block(ref.off, ref.bases)
+    ga.index(PARAMS["k"])
+    gbs = [dazzler.Block(b.off, b.bases) for b in blocks]
+    empty = dazzler.Block(np.array([0]), np.zeros(0, np.uint8))
+    counts = torch.zeros(nblocks, dtype=torch.int64, device=dev)
+    for b, blk in zip(mine, blocks):
+        counts[b] = blk.nreads
+    if world > 1:
+        dist.all_reduce(counts)
+    first_read = np.concatenate([[0], np.cumsum(counts.cpu().numpy())])
+    def step(gather):
+        ms = ext = 0.0; al = 0; nla = 0; eb = sb = 0
+        for j in range(per_rank):
+            gb = gbs[j] if j < len(gbs) else empty
+            off = int(first_read[mine[j]]) if j < len(mine) else 0
+            if gather and world > 1:
+                rec, _, _, st = dazzler.align_blocks_gather(ga, gb, off, root=0, **PARAMS)
+            else:
+                rec, _, _, st = dazzler.align_blocks(ga, gb, **PARAMS)
+            ms += st["ms_total"]; ext += st["ms_extend"]; al += st["aligned_bases"]; nla += st["las"]
+            eb += st["algo_bytes_extend"]; sb += st["algo_bytes_seed"]
+        return ms, ext, al, nla, eb, sb
+    for _ in range(max(2, args.warmup // 2)):
+        step(False); step(True)
+    res = {}
+    for name, gather in (("device", False), ("gathered", True)):
+        barrier(); tw = time.perf_counter()
+        tot = np.zeros(6)
+        for _ in range(args.steps):
+            tot += np.array(step(gather), dtype=np.float64)
+        barrier(); wall = time.perf_counter() - tw
+        t = torch.tensor([tot[0], tot[1], wall * 1e3], dtype=torch.float64, device=dev)
+        u = torch.tensor([tot[2], tot[3], tot[4], tot[5]], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX); dist.all_reduce(u, op=dist.ReduceOp.SUM)
+        res[name] = dict(dev_ms=float(t[0]), ext_ms=float(t[1]), wall_ms=float(t[2]), aligned=float(u[0]), las=float(u[1]) / args.steps,
+                         ext_bytes=float(u[2]), seed_bytes=float(u[3]))
+    d, g = res["device"], res["gathered"]
+    return {"workload": C3_WORKLOAD, "read_blocks": nblocks, "blocks_per_rank": per_rank, "assembly_bp": int(ref.total),
+            "read_bp_total": None, "value": d["aligned"] / 1e9 / (d["dev_ms"] / 1e3), "unit": "Gbp/s",
+            "ms_per_step": d["dev_ms"] / args.steps, "extend_ms_per_step": d["ext_ms"] / args.steps,
+            "gathered": {"value": g["aligned"] / 1e9 / (g["wall_ms"] / 1e3), "unit": "Gbp/s", "wall_ms_per_step": g["wall_ms"] / args.steps,
+                         "note": "same steps with every block's LAS gathered onto rank 0 and merged (dn_align_blocks_gather), wall clock between barriers"},
+            "local_alignments_per_step": d["las"], "aligned_bp_per_step": d["aligned"] / args.steps,
+            "algo_bytes_per_step": {"extend": d["ext_bytes"] / args.steps, "seed": d["seed_bytes"] / args.steps},
+            "resident_index": True, "generation_s": gen_s, "params": PARAMS}
+
+
 def clocks_sampler(stop, out, gpu_index):
     """Samples SM clock / throttle reasons every 50 ms DURING the timed region (the default run times about 0.3 s).  Uses NVML in-process
     (same counters as the recipe's `nvidia-smi --query-gpu=clocks.sm,...,clocks_event_reasons.* -lms 200`
@@ -209,6 +292,8 @@ def main():
     ap.add_argument("--scale", type=float, default=1.0, help="shrink the workload (tests only; 1.0 = configs[1])")
     ap.add_argument("--cpu-sample-mbp", type=float, default=0.0, help="CPU leg on the first N Mbp of reads only (0 = the whole block)")
     ap.add_argument("--profile", action="store_true", help="device-resident arm only (for ncu runs)")
+    ap.add_argument("--config", default="c1", choices=["c1", "c3"], help="c1 = BASELINE configs[1] (default, the headline); c3 = configs[2], 15 read blocks block-sharded")
+    ap.add_argument("--c3-blocks", type=int, default=C3_BLOCKS, help="read blocks of the c3 workload (15 = configs[2]; fewer for a quick run)")
     args = ap.parse_args()
     # the contract is ONE JSON line on stdout: anything a library prints there (e.g. NCCL's version banner) goes to stderr
     sys.stdout.flush(); real_stdout = os.dup(1); os.dup2(2, 1)
@@ -257,6 +342,33 @@ def main():
         dazzler.comm_init(rank, world)                  # the library's own NCCL communicator (id handed over by torch.distributed)
     dev = torch.device("cuda", local_rank)
 
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    if args.config == "c3":
+        c3 = run_c3(args, rank, world, dev, barrier, dist, torch, args.c3_blocks)
+        if rank == 0:
+            peaks = {}
+            try:
+                peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+            except Exception:
+                pass
+            peak = float(peaks.get("hbm_gbs", 6650.0))
+            ext_gbs = c3["algo_bytes_per_step"]["extend"] / 1e9 / (c3["extend_ms_per_step"] / 1e3) if c3["extend_ms_per_step"] else 0.0
+            emit({"metric": "Gbp aligned/sec", "value": c3["value"], "unit": "Gbp/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+                  "ms_per_step": c3["ms_per_step"], "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "u8/int32",
+                  "data": "synthetic", "config": {k: v for k, v in c3.items() if k not in ("value", "unit", "ms_per_step", "gathered")},
+                  "e2e": {"value": c3["gathered"]["value"], "unit": "Gbp/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": None,
+                          "note": c3["gathered"]["note"] + "; read blocks resident (uploaded once), merged LAS downloaded on rank 0"},
+                  "roofline": {"kernel": "k_extend32", "bound": "hbm", "achieved": ext_gbs, "peak": peak, "unit": "GB/s", "frac": ext_gbs / peak,
+                               "traffic": None, "note": "issue-bound kernel; see the c1 line and DESIGN.md"},
+                  "gpu_launches": None})
+        if world > 1:
+            dist.barrier(); dazzler.comm_shutdown(); dist.destroy_process_group()
+        return
+
     ref, reads = make_workload(args.scale, rank)
     # pinned host copies of the step's inputs (DAZZ_DB .bps 2-bit form: what the reference keeps on disk)
     def pinned(a):
@@ -277,11 +389,6 @@ def main():
         mx = torch.tensor([int(np.diff(reads.off).max())], dtype=torch.int64, device=dev)
         dist.all_reduce(mx, op=dist.ReduceOp.MAX)
         gather_bounds = (int(np.diff(ref.off).max()), int(mx.item()), ref.nreads, int(sum(int(c.item()) for c in cnts)))
-
-    def barrier():
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
 
     # ---- device-resident arm (`value`): blocks uploaded before the timed region ------------------
     ga = dazzler.Block(ref.off, bps=ref_bps, boff=ref_boff)
@@ -359,34 +466,52 @@ def main():
         dist.all_reduce(t2, op=dist.ReduceOp.MAX); dist.all_reduce(u2, op=dist.ReduceOp.SUM)
     e2e = float(u2[0]) / 1e9 / float(t2[0]) if float(t2[0]) > 0 else None
 
-    # ---- second headline: consensus bases/s over the workload's 100 gap pile-ups (batched) --------
+    # ---- second headline: consensus bases/s over the workload's 100 gap pile-ups, ONE dn_process_pileups call per step ----
     cons = None
     if not args.profile:
-        from dentist_b200 import pileups
         n_sc = max(1, int(round(10 * args.scale)))
         sc = synth.make_scaffolds(n_sc, 1000000, 1001)
         gaps = synth.make_gaps(sc, 10, 1002)
         preads, pgroup, _ = synth.make_pile_batch(sc, gaps, 1004 + rank, depth=20, anchor=1500)
-        ct = 0.0; cb = 0
+        npiles = int(pgroup.max()) + 1
+        # pile-up p closes gap p: its flanking contigs are the contigs either side of it (contigs_from order)
+        flank_of, c = [], 0
+        for gl in gaps:
+            for _g in gl:
+                flank_of.append([c, c + 1]); c += 1
+            c += 1
+        order = np.argsort(pgroup, kind="stable"); bounds = np.searchsorted(pgroup[order], np.arange(npiles + 1))
+        piles_in = [dict(reads=[preads.read(int(r)) for r in order[bounds[p]:bounds[p + 1]]], flanks=flank_of[p]) for p in range(npiles)]
+        batch = dazzler.PileupBatch(ga, piles_in)                          # host buffers + descriptors, built once
+        ct = 0.0; cb = 0; nok = 0
         for it in range(1 + max(1, args.steps // 2)):
             barrier(); t1 = time.perf_counter()
-            res = pileups.process_pileups(preads, pgroup, flanks=ga)
+            res = batch.run()                                              # the C call a D host makes: host reads in, insertions' inputs out
             barrier(); dt = time.perf_counter() - t1
             if os.environ.get("BENCH_DEBUG"):
                 print("[bench] consensus iter %d %.2f ms" % (it, dt * 1e3), file=sys.stderr)
             if it >= 1:
-                ct += dt; cb += sum(len(c) for c in res["consensus"])
+                ct += dt; cb += res.consensus_bases()
+        outs = res.to_list(); nok = sum(1 for o in outs if o["status"] == 0 and len(o["flank_las"]) >= 2)
         t3 = torch.tensor([ct], dtype=torch.float64, device=dev); u3 = torch.tensor([float(cb)], dtype=torch.float64, device=dev)
         if world > 1:
             dist.all_reduce(t3, op=dist.ReduceOp.MAX); dist.all_reduce(u3, op=dist.ReduceOp.SUM)
-        cons = {"value": float(u3[0]) / float(t3[0]), "unit": "consensus bases/s", "pile_ups_per_gpu": int(pgroup.max()) + 1,
-                "cropped_reads_per_gpu": int(preads.nreads), "cropped_bp_per_gpu": int(preads.total),
-                "stages": "pile alignment (daligner -s126 -l500) + error filter + chaining + QVs + pile filter + reference read + consensus + flank alignment"}
-        if rank == 0:
-            piles = list(range(min(int(pgroup.max()) + 1, 2 * cores)))
+        nsteps_c = max(1, args.steps // 2)
+        # algorithmic bytes of the leg (B_pack + B_cons + B_qv): packed cropped reads read by the pile alignment, the
+        # QV pass and the vote; LAS records + traces; consensus out
+        cons_algo = 3 * preads.total / 4 + sum(len(o["consensus"]) for o in outs) / 4
+        cons = {"value": float(u3[0]) / float(t3[0]), "unit": "consensus bases/s", "pile_ups_per_gpu": npiles, "pile_ups_with_both_flanks_aligned": nok,
+                "cropped_reads_per_gpu": int(preads.nreads), "cropped_bp_per_gpu": int(preads.total), "ms_per_batch": 1e3 * float(t3[0]) / nsteps_c,
+                "h2d_bytes_per_batch": int(batch.bases_bytes), "entry_point": "dn_process_pileups (one C call per batch, host buffers in)",
+                "stages": "dust + pile alignment (daligner -s126 -l500) + error filter + chaining + QVs + pile filter + reference read + consensus (with retry) + flank alignment (-mdust -mrep)",
+                "roofline": {"bound": "hbm", "achieved": cons_algo / 1e9 / (float(t3[0]) / nsteps_c), "unit": "GB/s",
+                             "note": "whole leg, algorithmic bytes / wall time: the leg is ~60 short launches on 28 Mbp, launch- and latency-bound; k_cons_vote "
+                                     "(2.3 ms of it) runs at IPC 2.0 with 4.8 % DRAM throughput (profiles/r02_a_prof_consensus_kernels_start_of_round.txt)"}}
+        if rank == 0 and world == 1:
+            piles = list(range(min(npiles, 4 * cores)))
             nb, dt = oracle_piles_threads(preads, pgroup, piles, cores)
             cons["cpu_baseline"] = {"value": nb / dt, "unit": "consensus bases/s", "cores": cores, "kind": "port",
-                                    "sample": "%d of the pile-ups, without flank alignment" % len(piles)}
+                                    "sample": "%d of the %d pile-ups, pile alignment + filters + chaining + QVs + consensus on the oracle port, without flank alignment" % (len(piles), npiles)}
 
     if rank == 0:
         peaks = {}
@@ -409,9 +534,12 @@ def main():
                "clocks": summarize_clocks(clk),
                "roofline": {"kernel": "k_extend32 (O(ND) wave extension, 48% of device time)", "bound": "hbm", "achieved": ext_gbs, "peak": peak,
                             "unit": "GB/s", "frac": ext_gbs / peak,
-                            "traffic": 98.5e6 / 3, "traffic_source": "ncu dram__bytes_read+write of the round-0 launch (72.1 + 26.5 MB, profiles/r01_prof_extend32_r1i_details.txt) averaged over the 3 launches of a step",
+                            "launches_per_step": 2,
+                            "traffic": (72.46e6 + 30.29e6 + 0.83e6 + 5.89e6) / 2,
+                            "traffic_source": "ncu dram__bytes_read+write per launch, averaged over the step's 2 launches: round 0 72.5 + 30.3 MB (profiles/r02_d_prof_extend32_ldg.txt), round 1 0.8 + 5.9 MB (profiles/r02_a_prof_hot_kernels_start_of_round.txt)",
                             "peak_source": peak_src,
-                            "note": "instruction-issue-bound kernel (79% issue slots busy, IPC 3.1, DRAM 0.2%): algorithmic bytes = packed sequence under each alignment + records + traces"},
+                            "note": "instruction-issue-bound kernel (81% issue slots busy, IPC 3.25, DRAM 0.2%, L1 hit rate 97%): the HBM fraction says nothing about its quality; "
+                                    "algorithmic bytes = packed sequence under each alignment + records + traces; measured DRAM traffic is BELOW them because the packed blocks stay in L2"},
                "roofline_seed": {"kernels": "A tuples+radix, lookup join, segment sort, band filter, retire, final ordering", "bound": "hbm", "achieved": seed_gbs, "peak": peak,
                                  "unit": "GB/s", "frac": seed_gbs / peak},
                "stage_ms_per_step": {"seed": seed_ms / args.steps, "extend": ext_ms / args.steps}}

@@ -499,6 +499,69 @@ class _HostLas:
         return [self.trace[o:o + t].reshape(-1, 2) for o, t in zip(self.toff, self.rec["tlen"])]
 
 
+class PileupBatch:
+    """The dn_pileup_desc array of a batch, built once over host buffers: `run()` is then exactly the C call a D host
+    makes (no Python work between the host buffers and dn_process_pileups)."""
+
+    def __init__(self, ref, piles):
+        self.ref, self.n = ref, len(piles)
+        self.descs = (_lib.PileupDesc * max(self.n, 1))()
+        self._keep = []
+        self.bases_bytes = 0
+        for i, p in enumerate(piles):
+            rl = np.ascontiguousarray([len(r) for r in p["reads"]], np.int32)
+            bs = np.ascontiguousarray(np.concatenate([np.asarray(r, np.uint8) for r in p["reads"]]) if len(rl) else np.zeros(0, np.uint8))
+            fl = np.ascontiguousarray(p.get("flanks", ()), np.int32)
+            self._keep += [rl, bs, fl]
+            self.bases_bytes += int(bs.nbytes)
+            d = self.descs[i]
+            d.nreads = len(rl); d.rlen = rl.ctypes.data; d.bases = bs.ctypes.data
+            if p.get("allowed") is not None:
+                al = np.ascontiguousarray(p["allowed"], np.uint8); self._keep.append(al); d.allowed = al.ctypes.data
+            d.nflanks = len(fl); d.flank_read = fl.ctypes.data
+            if p.get("mask") is not None:
+                anno, data = _track_arrays(p["mask"], len(fl)); self._keep += [anno, data]
+                d.mask_anno = anno.ctypes.data; d.mask_data = data.ctypes.data
+
+    def run(self, **params):
+        L = _lib.lib()
+        P = _lib.PileupParams()
+        L.dn_pileup_params_default(C.byref(P))
+        for k, v in params.items():
+            if not hasattr(P, k):
+                raise TypeError("unknown pile-up parameter %r" % k)
+            setattr(P, k, v)
+        outs = (_lib.InsertionOut * max(self.n, 1))()
+        _lib.check(L.dn_process_pileups(self.ref._h if self.ref is not None else None, self.descs, self.n, C.byref(P), outs))
+        return _Insertions(outs, self.n)
+
+
+class _Insertions:
+    """Owner of the dn_insertion_out array of one dn_process_pileups call."""
+
+    def __init__(self, outs, n):
+        self.outs, self.n = outs, n
+
+    def consensus_bases(self):
+        return sum(int(self.outs[i].cons_len) for i in range(self.n))
+
+    def to_list(self):
+        L = _lib.lib()
+        res = []
+        for i in range(self.n):
+            o = self.outs[i]
+            cons = np.ctypeslib.as_array(o.consensus, shape=(int(o.cons_len),)).copy() if o.cons_len else np.zeros(0, np.uint8)
+            res.append(dict(status=int(o.status), reason=L.dn_pile_status_string(o.status).decode(), reference_read=int(o.reference_read),
+                            ntries=int(o.ntries), consensus=cons, flank_las=_HostLas(o.flank_las)))
+        return res
+
+    def __del__(self):
+        try:
+            _lib.lib().dn_insertion_free(self.outs, self.n)
+        except Exception:
+            pass
+
+
 def processPileUps(ref, piles, **params):
     """dn_process_pileups: the device part of PileUpProcessor.processPileUp (package.d:303-341) for a batch.
     ref: resident Block holding the flanking contigs (or None); piles: list of dicts with
@@ -508,40 +571,7 @@ def processPileUps(ref, piles, **params):
       mask    = optional per-flank list of (begin, end) intervals (repeat mask)
     params: fields of dn_pileup_params.  Returns one dict per pile-up: status, reason, reference_read (index in the
     pile-up or -1), ntries, consensus (base codes), flank_las (_HostLas: aread = index into `flanks`)."""
-    L = _lib.lib()
-    P = _lib.PileupParams()
-    L.dn_pileup_params_default(C.byref(P))
-    for k, v in params.items():
-        if not hasattr(P, k):
-            raise TypeError("unknown pile-up parameter %r" % k)
-        setattr(P, k, v)
-    n = len(piles)
-    descs = (_lib.PileupDesc * max(n, 1))()
-    keep = []
-    for i, p in enumerate(piles):
-        rl = np.ascontiguousarray([len(r) for r in p["reads"]], np.int32)
-        bs = np.ascontiguousarray(np.concatenate([np.asarray(r, np.uint8) for r in p["reads"]]) if len(rl) else np.zeros(0, np.uint8))
-        fl = np.ascontiguousarray(p.get("flanks", ()), np.int32)
-        keep += [rl, bs, fl]
-        d = descs[i]
-        d.nreads = len(rl); d.rlen = rl.ctypes.data; d.bases = bs.ctypes.data
-        if p.get("allowed") is not None:
-            al = np.ascontiguousarray(p["allowed"], np.uint8); keep.append(al); d.allowed = al.ctypes.data
-        d.nflanks = len(fl); d.flank_read = fl.ctypes.data
-        if p.get("mask") is not None:
-            anno, data = _track_arrays(p["mask"], len(fl)); keep += [anno, data]
-            d.mask_anno = anno.ctypes.data; d.mask_data = data.ctypes.data
-    outs = (_lib.InsertionOut * max(n, 1))()
-    _lib.check(L.dn_process_pileups(ref._h if ref is not None else None, descs, n, C.byref(P), outs))
-    res = []
-    for i in range(n):
-        o = outs[i]
-        cons = np.ctypeslib.as_array(o.consensus, shape=(int(o.cons_len),)).copy() if o.cons_len else np.zeros(0, np.uint8)
-        res.append(dict(status=int(o.status), reason=L.dn_pile_status_string(o.status).decode(), reference_read=int(o.reference_read),
-                        ntries=int(o.ntries), consensus=cons, flank_las=_HostLas(o.flank_las)))
-    L.dn_insertion_free(outs, n)
-    del keep
-    return res
+    return PileupBatch(ref, piles).run(**params).to_list()
 
 
 # ---------------------------------------------------------------------------------------------
