@@ -206,16 +206,24 @@ int dn_las_write(const char *path, const dn_las_buf *buf) {
         FILE *f = fopen(path, "wb");
         if (!f) return fail(DN_ERR_IO, std::string("cannot open for writing: ") + path);
         int64_t novl = buf->nrec; int32_t ts = buf->tspace;
-        fwrite(&novl, 8, 1, f); fwrite(&ts, 4, 1, f);
+        bool ok = fwrite(&novl, 8, 1, f) == 1 && fwrite(&ts, 4, 1, f) == 1;
         const bool large = ts > 125;                     // TRACE_XOVR, dazzler.d:2019-2025
         std::vector<uint8_t> small;
-        for (int64_t i = 0; i < buf->nrec; i++) {
-            fwrite(&buf->rec[i], 40, 1, f);
+        for (int64_t i = 0; ok && i < buf->nrec; i++) {
+            ok = fwrite(&buf->rec[i], 40, 1, f) == 1;
             const uint16_t *t = buf->trace + buf->toff[i]; const int tl = buf->rec[i].tlen;
-            if (large) fwrite(t, 2, tl, f);
-            else { small.resize(tl); for (int x = 0; x < tl; x++) small[x] = (uint8_t)(t[x] > 255 ? 255 : t[x]); fwrite(small.data(), 1, tl, f); }
+            if (large) ok = ok && fwrite(t, 2, tl, f) == (size_t)tl;
+            else {
+                small.resize(tl);
+                for (int x = 0; x < tl; x++) {
+                    // a value that does not fit the 1-byte trace of tspace <= 125 would silently break sum(bbases) == bepos - bbpos
+                    if (t[x] > 255) { fclose(f); remove(path); return fail(DN_ERR_INVALID, "trace value > 255 cannot be written with trace spacing <= 125 (use -s126 or larger)"); }
+                    small[x] = (uint8_t)t[x];
+                }
+                ok = ok && fwrite(small.data(), 1, tl, f) == (size_t)tl;
+            }
         }
-        if (fclose(f) != 0) return fail(DN_ERR_IO, std::string("write failed: ") + path);
+        if (fclose(f) != 0 || !ok) return fail(DN_ERR_IO, std::string("write failed: ") + path);
         return DN_OK;
     });
 }
@@ -255,7 +263,7 @@ int dn_las_read(const char *path, dn_las_buf *out) {
 
 // ---- file-level drop-ins ------------------------------------------------------------------
 
-static int parse_opts(const char *const *opts, int nopts, dn_align_params *p, bool *asym, std::vector<std::string> *masks) {
+static int parse_opts(const char *const *opts, int nopts, dn_align_params *p, bool *asym, std::vector<std::string> *masks, double *best_frac = nullptr) {
     for (int i = 0; i < nopts; i++) {
         const char *o = opts[i];
         if (!o || o[0] != '-' || !o[1]) return fail(DN_ERR_INVALID, std::string("bad option: ") + (o ? o : "(null)"));
@@ -271,7 +279,8 @@ static int parse_opts(const char *const *opts, int nopts, dn_align_params *p, bo
             case 'I': p->identity = 1; break;
             case 'A': *asym = true; break;
             case 'm': masks->push_back(v); break;
-            case 'T': case 'M': case 'B': case 'v': case 'b': case 'a': case 'C': case 'N': case 'z': case 'n': case 'P': case 'p': break;   // accepted, no effect on a GPU
+            case 'n': if (best_frac) *best_frac = atof(v); break;                 // damapper: also report chains within this fraction of the best (dazzler.d:5920-5923)
+            case 'T': case 'M': case 'B': case 'v': case 'b': case 'a': case 'C': case 'N': case 'z': case 'P': case 'p': break;   // accepted, no effect on a GPU
             default: return fail(DN_ERR_INVALID, std::string("unknown option: ") + o);
         }
     }
@@ -284,8 +293,8 @@ static int align_files(const char *dbA, const char *dbB, const char *const *opts
     return guarded([&]() -> int {
         dn_align_params p; dn_align_params_default(&p);
         if (mapper) { p.minlen = 1000; p.k = 20; }       /* damapper's own defaults (DENTIST passes neither -k nor -l, commandline.d:2943-2955) */
-        bool asym = false; std::vector<std::string> masks;
-        if (int rc = parse_opts(opts, nopts, &p, &asym, &masks)) return rc;
+        bool asym = false; std::vector<std::string> masks; double best_frac = 0.0;     // no -n: the best chain of every read only
+        if (int rc = parse_opts(opts, nopts, &p, &asym, &masks, &best_frac)) return rc;
         const bool self = (dbB == nullptr) || std::string(dbA) == std::string(dbB);
         HostDb A, B;
         std::string err;
@@ -297,7 +306,11 @@ static int align_files(const char *dbA, const char *dbB, const char *const *opts
         dn_las_buf ab; memset(&ab, 0, sizeof ab);
         int rc = dn_align_host(&da, self ? &da : &db, &p, &ab);
         if (rc) return rc;
-        if (mapper) { rc = dn_las_chain_mapper(&ab, (int32_t)Bx.rlen.size(), 1000, 10000); if (rc) { dn_las_free(&ab); return rc; } }
+        if (mapper) {
+            rc = dn_las_chain_mapper(&ab, (int32_t)Bx.rlen.size(), 1000, 10000);
+            if (!rc) rc = dn_las_keep_best_chains(&ab, (int32_t)Bx.rlen.size(), best_frac);
+            if (rc) { dn_las_free(&ab); return rc; }
+        }
         std::string pa = std::string(outdir) + "/" + A.name + "." + Bx.name + ".las";
         rc = dn_las_write(pa.c_str(), &ab);
         dn_las_free(&ab);
@@ -306,7 +319,10 @@ static int align_files(const char *dbA, const char *dbB, const char *const *opts
             dn_las_buf ba; memset(&ba, 0, sizeof ba);
             rc = dn_align_host(&db, &da, &p, &ba);
             if (rc) return rc;
-            if (mapper) { rc = dn_las_chain_mapper(&ba, (int32_t)A.rlen.size(), 1000, 10000); if (rc) { dn_las_free(&ba); return rc; } }
+            if (mapper) {
+                rc = dn_las_chain_mapper(&ba, (int32_t)A.rlen.size(), 1000, 10000);
+                if (rc) { dn_las_free(&ba); return rc; }
+            }
             std::string pb = std::string(outdir) + "/" + Bx.name + "." + A.name + ".las";
             rc = dn_las_write(pb.c_str(), &ba);
             dn_las_free(&ba);

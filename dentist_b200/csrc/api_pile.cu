@@ -141,6 +141,36 @@ int dn_las_chain_mapper(dn_las_buf *las, int32_t nb_reads, int32_t max_indel, in
     });
 }
 
+// damapper reports, per mapped read, the best chain and -- with -n<f> -- every chain whose score reaches the fraction f of
+// the best (dazzler.d:5920-5923); DENTIST passes no -n (commandline.d:2943-2955).  Host logic over the START/NEXT/BEST
+// flags dn_las_chain_mapper wrote: chain score = sum of the A spans of its records (the score BEST was chosen by).
+int dn_las_keep_best_chains(dn_las_buf *las, int32_t nb_reads, double n_frac) {
+    if (!las || nb_reads < 0) return fail(DN_ERR_INVALID, "null argument");
+    return guarded([&]() -> int {
+        std::vector<long long> best(nb_reads, -1);
+        std::vector<long long> score(las->nrec, 0);
+        for (int64_t i = 0; i < las->nrec;) {
+            if (las->rec[i].bread < 0 || las->rec[i].bread >= nb_reads) return fail(DN_ERR_INVALID, "contig id out of bounds");
+            if (!(las->rec[i].flags & DN_LAS_START)) return fail(DN_ERR_INVALID, "chain flags missing: call dn_las_chain_mapper first");
+            int64_t j = i; long long sc = 0;
+            do { sc += las->rec[j].aepos - las->rec[j].abpos; j++; } while (j < las->nrec && (las->rec[j].flags & DN_LAS_NEXT));
+            for (int64_t x = i; x < j; x++) score[x] = sc;
+            if (las->rec[i].flags & DN_LAS_BEST) best[las->rec[i].bread] = sc;
+            i = j;
+        }
+        int64_t w = 0; bool keep = false;
+        for (int64_t i = 0; i < las->nrec; i++) {
+            if (las->rec[i].flags & DN_LAS_START) {
+                const bool is_best = (las->rec[i].flags & DN_LAS_BEST) != 0;
+                keep = is_best || (n_frac > 0.0 && (double)score[i] >= n_frac * (double)best[las->rec[i].bread]);
+            }
+            if (keep) { las->rec[w] = las->rec[i]; las->toff[w] = las->toff[i]; w++; }
+        }
+        las->nrec = w;
+        return DN_OK;
+    });
+}
+
 int dn_las_force_flat(dn_las_buf *las) {
     if (!las) return fail(DN_ERR_INVALID, "null argument");
     std::lock_guard<std::mutex> lk(g_mu);

@@ -307,6 +307,12 @@ class Las:
         self._refresh()
         return self
 
+    def keepBestChains(self, nb_reads, n_frac=0.0):
+        """What damapper reports (dazzler.d:5920-5923): the best chain per read, plus chains within `n_frac` of it (-n)."""
+        _lib.check(_lib.lib().dn_las_keep_best_chains(C.byref(self._buf), int(nb_reads), C.c_double(n_frac)))
+        self._refresh()
+        return self
+
     def write(self, path):
         _lib.check(_lib.lib().dn_las_write(path.encode(), C.byref(self._buf)))
 

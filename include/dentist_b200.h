@@ -290,6 +290,11 @@ int dn_block_add_mask(dn_block *blk, const int64_t *mask_anno, const int32_t *ma
  * AlignmentChains at :708-743.  `las` must be in LAsort order (as dn_align_blocks returns it). */
 int dn_las_chain_mapper(dn_las_buf *las, int32_t nb_reads, int32_t max_indel, int32_t max_gap);
 
+/* What damapper reports: per mapped read its best chain and, with -n<f>, every chain scoring at least the fraction f of
+ * the best (dazzler.d:5920-5923).  n_frac <= 0: the BEST chains only (DENTIST passes no -n, commandline.d:2943-2955).
+ * `las` must carry the flags of dn_las_chain_mapper.  In place, order preserving. */
+int dn_las_keep_best_chains(dn_las_buf *las, int32_t nb_reads, double n_frac);
+
 /* The alignment filters of collectPileUps (commands/collectPileUps/filter.d:122-356, order of package.d:129-141:
  * LQ, Improper, WeaklyAnchored, Contained, Ambiguous, Redundant) over the AlignmentChains of a chained
  * ref-vs-reads LAS (`las` in LAsort order with START/NEXT flags).  mask_* = repeat mask on the A contigs in

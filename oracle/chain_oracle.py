@@ -47,3 +47,22 @@ def mapper_chain_flags(rec, max_indel=1000, max_gap=10000):
                 f |= BEST
         out[i] = f
     return out
+
+
+def keep_best_chains(rec, flags, n_frac=0.0):
+    """damapper's reporting rule (dazzler.d:5920-5923): indices of the records of every read's BEST chain and of the
+    chains whose score (sum of A spans) reaches n_frac of the best; n_frac <= 0: best chains only."""
+    n = len(rec)
+    chains, i = [], 0
+    while i < n:
+        j = i + 1
+        while j < n and (int(flags[j]) & NEXT):
+            j += 1
+        chains.append((i, j, sum(int(rec[x]["aepos"]) - int(rec[x]["abpos"]) for x in range(i, j))))
+        i = j
+    best = {int(rec[i]["bread"]): sc for i, j, sc in chains if int(flags[i]) & BEST}
+    keep = []
+    for i, j, sc in chains:
+        if (int(flags[i]) & BEST) or (n_frac > 0 and sc >= n_frac * best[int(rec[i]["bread"])]):
+            keep += list(range(i, j))
+    return np.array(keep, np.int64)

@@ -99,6 +99,38 @@ def test_reference_read_candidates_matches_python_mirror():
         assert got[p].tolist() == pileups.find_reference_read_candidates(qv, qoff, members)
 
 
+def test_reference_read_candidates_hand_derived_vectors():
+    """findReferenceReadCandidates worked out BY HAND from the D source (processPileUps/package.d:518-568), independent of
+    both implementations in this repo:
+      hist over qv < maxQV(50) of the allowed reads (:525-532); badThres = cast(size_t)(badFraction * histTotal) (:534);
+      badQV = 49 - (first index of the cumulative sum over the reversed histogram that reaches badThres) (:535-538);
+      reads ordered by the tuple (count(qv >= badQV), mean(qv), readNumber) (:546-557)."""
+    from dentist_b200 import dazzler
+
+    def run(per_read, group, npiles, bad_fraction):
+        qoff = np.zeros(len(per_read) + 1, np.int64); qoff[1:] = np.cumsum([len(q) for q in per_read])
+        qv = np.concatenate([np.array(q, np.uint8) for q in per_read])
+        return [r.tolist() for r in dazzler.findReferenceReadCandidates(qv, qoff, np.array(group, np.int32), npiles, bad_fraction)]
+
+    # Case 1, badFraction 0.2.  hist: 10 -> 4, 12 -> 4, 30 -> 1, 40 -> 1 (the two 50s are >= maxQV: not counted), total 10,
+    # badThres = 2.  Reversed cumulative sum: QV 49..41 -> 0, QV 40 -> 1, QV 39..31 -> 1, QV 30 -> 2 >= 2 at index 19
+    # => badQV = 49 - 19 = 30.  (numBad, mean): read 0 -> (1, 17.5), read 1 -> (0, 12.0), read 2 -> (3, 35.0)  => 1, 0, 2.
+    r0, r1, r2 = [10, 10, 10, 40], [12, 12, 12, 12], [10, 30, 50, 50]
+    assert run([r0, r1, r2], [0, 0, 0], 1, 0.2) == [[1, 0, 2]]
+    # Case 2, badFraction 0.08 (the default) on the same reads: badThres = cast(size_t)(0.8) = 0; the cumulative sum is
+    # >= 0 already at index 0 => badQV = 49; only the 50s count as bad: (0, 17.5), (0, 12.0), (2, 35.0) => 1, 0, 2.
+    assert run([r0, r1, r2], [0, 0, 0], 1, 0.08) == [[1, 0, 2]]
+    # Case 3: equal numBad and equal mean -> the read number decides; equal numBad, different mean -> lower mean first.
+    # badFraction 0.5: hist 20 -> 6, 30 -> 2, total 8, badThres 4; reversed cumulative: QV 30 -> 2, QV 20 -> 8 >= 4 at index 29
+    # => badQV = 20: every value is bad.  (3, 23.33), (3, 20.0), (2, 25.0), (3, 20.0) => read 2, then 1 and 3 (tie: id), then 0.
+    assert run([[20, 20, 30], [20, 20, 20], [20, 30], [20, 20, 20]], [0, 0, 0, 0], 1, 0.5) == [[2, 1, 3, 0]]
+    # Case 4: reads outside allowedReferenceReadIds (group -1) enter neither the histogram nor the ranking (:520-523); piles
+    # are independent.  Pile 0 = reads 0, 2 (read 1 not allowed): hist 10 -> 3, 40 -> 1, 30 -> 1 (50s dropped), total 6,
+    # badFraction 0.2 -> badThres 1; reversed cumulative reaches 1 at QV 40 (index 9) => badQV 40: (1, 17.5), (2, 35.0) => 0, 2.
+    # Pile 1 = read 3 alone.
+    assert run([r0, r1, r2, [5, 5]], [0, -1, 0, 1], 2, 0.2) == [[0, 2], [3]]
+
+
 def test_cli_stand_ins_exist_and_print_usage():
     """dn-damapper / dn-daligner / dn-dbdust keep the argv contract of the tools the workflow calls (Snakefile:1143-1169)."""
     import subprocess

@@ -27,10 +27,24 @@ def test_getDamapping_writes_both_las_files(tmp_path):
     ts, rec, traces = las.decode(open(out, "rb").read())
     assert ts == 100 and len(rec) > 20
     ga, gb = dazzler.Block(ref.off, ref.bases), dazzler.Block(reads.off, reads.bases)
-    mrec, mtoff, mtr, _ = dazzler.align_blocks(ga, gb, tspace=100, minlen=500, k=20)     # damapper's default k
+    mem = dazzler.align(ga, gb, tspace=100, minlen=500, k=20)                            # damapper's default k
+    allrec, alltr = mem.rec.copy(), [t.copy() for t in mem.traces()]
+    # damapper reports the best chain of every read only (no -n, commandline.d:2943-2955; dazzler.d:5920-5923)
+    from oracle import chain_oracle
+    keep = chain_oracle.keep_best_chains(allrec, chain_oracle.mapper_chain_flags(allrec))
+    assert 20 < len(keep) <= len(allrec)
+    mrec = allrec[keep]
     for f in ("aread", "bread", "abpos", "aepos", "bbpos", "bepos", "diffs", "tlen"):
         assert np.array_equal(rec[f], mrec[f]), f
-    assert np.concatenate([t.reshape(-1) for t in traces]).tolist() == np.minimum(mtr, 255).tolist()
+    assert np.concatenate([t.reshape(-1) for t in traces]).tolist() == np.concatenate([alltr[i].reshape(-1) for i in keep]).tolist()
+    assert sorted(set(rec["bread"].tolist())) == sorted(set(allrec["bread"].tolist()))     # every mapped read keeps exactly its best chain
+    assert all(int(f) & las.BEST for f in rec["flags"] if int(f) & las.START)
+    # -n<f>: chains within the fraction f of the best come back too; -n0.01 ~ everything
+    (tmp_path / "n").mkdir()
+    outn = dazzler.getDamapping(str(tmp_path / "ref.dam"), str(tmp_path / "reads.db"), ["-C", "-e0.7", "-l500", "-n0.01"], str(tmp_path / "n"))
+    _, recn, _ = las.decode(open(outn, "rb").read())
+    keepn = chain_oracle.keep_best_chains(allrec, chain_oracle.mapper_chain_flags(allrec), 0.01)
+    assert len(recn) == len(keepn) >= len(rec) and np.array_equal(recn["abpos"], allrec[keepn]["abpos"])
     assert all(int(f) & (las.START | las.NEXT) for f in rec["flags"])              # chain flags set -> AlignmentChainPacker accepts it
     assert len(las.chains(rec)) == len(rec)
     # transposed file exists, is sorted by read and has uint8 traces
