@@ -110,14 +110,22 @@ bool read_dazz_db(const std::string &path, const std::vector<std::string> &mask_
         bool any = false;
         for (const std::string &t : mask_tracks) {
             std::vector<uint8_t> anno, data;
+            // a block DB takes its block-level track .<root>.<block>.<track> (what DBdust X.<block> writes, before Catrack
+            // merges the blocks; getMaskFiles dazzler.d:4870-4912) when there is one, else the whole-DB track
             std::string base = pp.dir + "/." + pp.root + "." + t;
+            bool block_track = false;
+            if (pp.block > 0) {
+                const std::string bb = pp.dir + "/." + pp.root + "." + std::to_string(pp.block) + "." + t;
+                if (exists(bb + ".anno")) { base = bb; block_track = true; }
+            }
             if (!slurp(base + ".anno", anno) || anno.size() < 8) continue;        // a missing track masks nothing
             slurp(base + ".data", data);
             int32_t tn, tsz; memcpy(&tn, anno.data(), 4); memcpy(&tsz, anno.data() + 4, 4);
             if (tsz != 0 || anno.size() < 8 + (size_t)(tn + 1) * 8) continue;
             const int64_t *o = (const int64_t *)(anno.data() + 8);
             for (size_t r = 0; r < uid.size(); r++) {
-                int64_t id = (tn == h.ureads) ? uid[r] : (int64_t)tcount_before + (int64_t)r;
+                int64_t id = block_track ? (tn == u1 - u0 ? (int64_t)uid[r] - u0 : (int64_t)r)
+                                         : (tn == h.ureads) ? uid[r] : (int64_t)tcount_before + (int64_t)r;
                 if (id < 0 || id >= tn) continue;
                 for (int64_t b = o[id]; b + 8 <= o[id + 1] && b + 8 <= (int64_t)data.size(); b += 8) {
                     int32_t be[2]; memcpy(be, data.data() + b, 8);
@@ -177,16 +185,20 @@ bool write_dazz_db(const std::string &path, const std::vector<std::vector<uint8_
 bool write_mask_track(const std::string &dbpath, const std::string &track, const std::vector<std::vector<int32_t>> &iv, std::string &err) {
     PathParts pp;
     if (!split_path(dbpath, pp, err)) return false;
-    std::string base = pp.dir + "/." + pp.root + "." + track;
+    // a block DB (X.<n>) gets the block-level track .<root>.<n>.<track>, like DBdust X.<n>; the whole-DB track is not touched
+    std::string base = pp.dir + "/." + pp.root + (pp.block > 0 ? "." + std::to_string(pp.block) : "") + "." + track;
     FILE *fa = fopen((base + ".anno").c_str(), "wb"), *fd = fopen((base + ".data").c_str(), "wb");
     if (!fa || !fd) { if (fa) fclose(fa); if (fd) fclose(fd); err = "cannot write track " + base; return false; }
-    int32_t n = (int32_t)iv.size(), sz = 0; fwrite(&n, 4, 1, fa); fwrite(&sz, 4, 1, fa);
+    int32_t n = (int32_t)iv.size(), sz = 0;
+    bool ok = fwrite(&n, 4, 1, fa) == 1 && fwrite(&sz, 4, 1, fa) == 1;
     int64_t off = 0;
-    for (size_t r = 0; r <= iv.size(); r++) {
-        fwrite(&off, 8, 1, fa);
-        if (r < iv.size()) { if (!iv[r].empty()) fwrite(iv[r].data(), 4, iv[r].size(), fd); off += 4 * (int64_t)iv[r].size(); }
+    for (size_t r = 0; ok && r <= iv.size(); r++) {
+        ok = fwrite(&off, 8, 1, fa) == 1;
+        if (r < iv.size()) { if (!iv[r].empty()) ok = ok && fwrite(iv[r].data(), 4, iv[r].size(), fd) == iv[r].size(); off += 4 * (int64_t)iv[r].size(); }
     }
-    fclose(fa); fclose(fd);
+    if (fclose(fa) != 0) ok = false;
+    if (fclose(fd) != 0) ok = false;
+    if (!ok) { err = "write failed for track " + base; return false; }
     return true;
 }
 

@@ -187,5 +187,46 @@ inline std::vector<uint8_t> getConsensus(const Block &db, const Las &las, size_t
     return out;
 }
 
+/// One pile-up after crop() and the result PileUpProcessor needs to go on with getInsertionAlignment()
+/// (commands/processPileUps/package.d:283-374).
+struct PileUp {
+    std::vector<std::vector<uint8_t>> croppedReads;       // base codes 0..3
+    std::vector<uint8_t> allowedReferenceRead;            // empty = all
+    std::vector<int32_t> flankingContigs;                 // 0-based read ids in the reference block
+};
+struct PileUpResult {
+    int32_t status = 0; std::string reason; int32_t referenceReadIdx = -1;
+    std::vector<uint8_t> consensus;
+    std::vector<dn_las_record> postConsensusAlignment; std::vector<std::vector<uint16_t>> traces;
+};
+
+/// processPileUps' device path for a whole batch in ONE call (dn_process_pileups).  A failing pile-up comes back with
+/// the reference's reason (`pileUpSkipped`), it does not throw.
+inline std::vector<PileUpResult> processPileUps(const Block &refDb, const std::vector<PileUp> &pileUps, const dn_pileup_params *params = nullptr) {
+    const size_t n = pileUps.size();
+    std::vector<dn_pileup_desc> d(n); std::vector<std::vector<int32_t>> rlen(n); std::vector<std::vector<uint8_t>> bases(n);
+    for (size_t i = 0; i < n; i++) {
+        for (const auto &r : pileUps[i].croppedReads) { rlen[i].push_back((int32_t)r.size()); bases[i].insert(bases[i].end(), r.begin(), r.end()); }
+        d[i] = dn_pileup_desc{};
+        d[i].nreads = (int32_t)rlen[i].size(); d[i].rlen = rlen[i].data(); d[i].bases = bases[i].data();
+        d[i].allowed = pileUps[i].allowedReferenceRead.empty() ? nullptr : pileUps[i].allowedReferenceRead.data();
+        d[i].nflanks = (int32_t)pileUps[i].flankingContigs.size(); d[i].flank_read = pileUps[i].flankingContigs.data();
+    }
+    std::vector<dn_insertion_out> o(n);
+    enforce(dn_process_pileups(refDb.raw(), d.data(), (int32_t)n, params, o.data()));
+    std::vector<PileUpResult> out(n);
+    for (size_t i = 0; i < n; i++) {
+        out[i].status = o[i].status; out[i].reason = dn_pile_status_string(o[i].status); out[i].referenceReadIdx = o[i].reference_read;
+        if (o[i].cons_len) out[i].consensus.assign(o[i].consensus, o[i].consensus + o[i].cons_len);
+        const dn_las_buf &l = o[i].flank_las;
+        for (int64_t x = 0; x < l.nrec; x++) {
+            out[i].postConsensusAlignment.push_back(l.rec[x]);
+            out[i].traces.emplace_back(l.trace + l.toff[x], l.trace + l.toff[x] + l.rec[x].tlen);
+        }
+    }
+    dn_insertion_free(o.data(), (int32_t)n);
+    return out;
+}
+
 }  // namespace dazzler
 }  // namespace dentist

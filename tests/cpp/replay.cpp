@@ -56,6 +56,28 @@ int main(int argc, char **argv) {
         for (size_t i = 0; i < cons.size(); i++) { h = (h ^ cons[i]) * 1099511628211ull; }
         for (size_t i = 0; i < cons.size() && i < truth.size(); i++) same += cons[i] == truth[i];
         printf("consensus %zu %llu\n", cons.size(), h);
+        // the same pile-up (and a copy with another reference-read restriction) through the ONE batch entry point: the first
+        // and the last 1200 truth bases are its flanking contigs
+        std::vector<uint8_t> fl(truth.begin(), truth.begin() + 1200), fr(truth.end() - 1200, truth.end());
+        std::vector<uint8_t> fbases(fl); fbases.insert(fbases.end(), fr.begin(), fr.end());
+        std::vector<int32_t> flen{1200, 1200}; std::vector<int64_t> foff{0, 1200};
+        dn_block_desc fd{}; fd.nreads = 2; fd.format = DN_SEQ_BYTES; fd.rlen = flen.data(); fd.boff = foff.data(); fd.data = fbases.data(); fd.data_bytes = 2400;
+        Block ref(fd);
+        PileUp pu; pu.flankingContigs = {0, 1};
+        for (int r = 0; r < N; r++) pu.croppedReads.emplace_back(bases.begin() + boff[r], bases.begin() + boff[r] + rlen[r]);
+        PileUp pv = pu; pv.allowedReferenceRead.assign(N, 0); pv.allowedReferenceRead[3] = 1;
+        auto res = processPileUps(ref, {pu, pv});
+        for (auto &o : res) {
+            unsigned long long hc = 1469598103934665603ull, hf = 1469598103934665603ull;
+            for (auto b : o.consensus) hc = (hc ^ b) * 1099511628211ull;
+            for (size_t x = 0; x < o.postConsensusAlignment.size(); x++) {
+                const dn_las_record &q = o.postConsensusAlignment[x];
+                const int32_t f[8] = {q.aread, q.abpos, q.aepos, q.bbpos, q.bepos, q.diffs, (int32_t)q.flags, q.tlen};
+                for (int32_t v : f) hf = (hf ^ (unsigned long long)(uint32_t)v) * 1099511628211ull;
+                for (auto t : o.traces[x]) hf = (hf ^ t) * 1099511628211ull;
+            }
+            printf("batch %d|%d|%zu|%llu|%zu|%llu\n", o.status, o.referenceReadIdx, o.consensus.size(), hc, o.postConsensusAlignment.size(), hf);
+        }
         return 0;
     } catch (const DazzlerCommandException &e) {
         printf("DazzlerCommandException: %s\n", e.what());

@@ -11,7 +11,8 @@ from dentist_b200 import synth
 DB_BEST = 0x800
 
 
-def write_db(path, block, cutoff=0, all_=1, flags=None):
+def write_db(path, block, cutoff=0, all_=1, flags=None, block_first=None):
+    """block_first: first read of every DB block after the first (DBsplit); default one block."""
     d, base = os.path.split(path)
     dam = base.endswith(".dam")
     root = base[:-4] if dam else base[:-3]
@@ -34,9 +35,12 @@ def write_db(path, block, cutoff=0, all_=1, flags=None):
         f.write(np.concatenate(bps).tobytes() if bps else b"")
     if dam:
         open(os.path.join(d, "." + root + ".hdr"), "w").write(">%s\n" % root)
+    firsts = [0] + list(block_first or []) + [n]
     with open(path, "w") as f:
-        f.write("files = %9d\n  %9d %s %s\nblocks = %9d\nsize = %11d cutoff = %9d all = %1d\n %9d %9d\n %9d %9d\n"
-                % (1, n, root, root, 1, 200000000, cutoff, all_, 0, 0, n, n))
+        f.write("files = %9d\n  %9d %s %s\nblocks = %9d\nsize = %11d cutoff = %9d all = %1d\n"
+                % (1, n, root, root, len(firsts) - 1, 200000000, cutoff, all_))
+        for x in firsts:
+            f.write(" %9d %9d\n" % (x, x))
 
 
 def write_track(dbpath, name, intervals):

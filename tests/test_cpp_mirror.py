@@ -27,6 +27,15 @@ def test_cpp_mirror_builds_and_fails_loudly_without_gpu(tmp_path):
     assert r.returncode == 3 and "DazzlerCommandException" in r.stdout and "no CUDA device" in r.stdout
 
 
+def _truth(seed, L):
+    s = seed
+    out = []
+    for _ in range(L):
+        s = (s * 6364136223846793005 + 1442695040888963407) & M
+        out.append((s >> 33) & 3)
+    return np.array(out, np.uint8)
+
+
 def _pile(seed):
     s = seed
     def lcg():
@@ -79,3 +88,23 @@ def test_cpp_mirror_equals_python_path(tmp_path):
     for b in cons.tolist():
         h = ((h ^ b) * 1099511628211) & M
     assert got["consensus"] == "%d %d" % (len(cons), h)
+    # the batch entry point from C++ == the Python path (same C call), byte for byte
+    L = 3000
+    truth = _truth(7, L)
+    ref = dazzler.Block(np.array([0, 1200, 2400]), np.concatenate([truth[:1200], truth[-1200:]]))
+    allowed = [i == 3 for i in range(len(reads))]
+    py = dazzler.processPileUps(ref, [dict(reads=reads, flanks=[0, 1]), dict(reads=reads, flanks=[0, 1], allowed=allowed)])
+    lines = [ln.split(" ", 1)[1] for ln in r.stdout.strip().split("\n") if ln.startswith("batch ")]
+    assert len(lines) == 2
+    for o, ln in zip(py, lines):
+        hc = hf = 1469598103934665603
+        for b in o["consensus"].tolist():
+            hc = ((hc ^ b) * 1099511628211) & M
+        fl = o["flank_las"]
+        for q, t in zip(fl.rec, fl.traces()):
+            for v in (q["aread"], q["abpos"], q["aepos"], q["bbpos"], q["bepos"], q["diffs"], q["flags"], q["tlen"]):
+                hf = ((hf ^ (int(v) & 0xffffffff)) * 1099511628211) & M
+            for v in t.reshape(-1).tolist():
+                hf = ((hf ^ v) * 1099511628211) & M
+        assert ln == "%d|%d|%d|%d|%d|%d" % (o["status"], o["reference_read"], len(o["consensus"]), hc, len(fl), hf)
+    assert py[0]["status"] == 0 and len(py[0]["flank_las"]) >= 2 and py[1]["reference_read"] in (3, -1)

@@ -11,47 +11,7 @@ from dentist_b200 import binio, process, synth
 pytestmark = pytest.mark.gpu
 
 
-def _identity(a, b):
-    """1 - edit distance / len via numpy row DP (sequences of a few kb)."""
-    prev = np.arange(len(b) + 1)
-    for i in range(1, len(a) + 1):
-        cur = np.minimum(prev[:-1] + (a[i - 1] != b), prev[1:] + 1)
-        cur = np.concatenate([[i], cur])
-        cur = np.minimum.accumulate(cur - np.arange(len(cur))) + np.arange(len(cur))     # insertion chain
-        prev = cur
-    return 1.0 - prev[-1] / max(len(a), len(b))
-
-
-def _build_pileups(las, alen, blen, kept, n_gaps):
-    """`dentist collect` in miniature: the kept chains of every read become read alignments (collectReadAlignments,
-    collectPileUps/pileups.d:821-888, with SeededAlignment.from seeds); read alignments with the same join -- gap
-    (contig g end, contig g+1 begin) or an extension into that gap from either side -- form one pile-up (what bundling
-    the scaffold graph's edges does, pileups.d:650-666)."""
-    rec, toff, trace = las.rec, las.toff, las.trace
-    by_read = {}
-    for i in kept:
-        j = i + 1
-        while j < len(rec) and (int(rec[j]["flags"]) & 0x8):
-            j += 1
-        sub = slice(int(i), j)
-        chain = binio.seeded_alignments_from_las(rec[sub], toff[sub], trace, alen, blen, 100, lambda f, l: "front")[0]
-        chain.pop("seed"); chain["id"] = int(i)
-        by_read.setdefault(int(rec[i]["bread"]), []).append(chain)
-    piles = [[] for _ in range(n_gaps)]
-    for b in sorted(by_read):
-        ras, reason = process.collect_read_alignments(by_read[b])
-        for ra in ras:
-            if process._is_gap(ra) and not process.is_in_order(ra):
-                ra = [ra[1], ra[0]]                                   # ReadAlignment.getInOrder, base.d:2177-2183
-            start, end = process.make_join(ra)
-            if process._is_gap(ra):
-                if start[1] == "end" and end[1] == "begin" and end[0] == start[0] + 1 and process._is_parallel(ra):
-                    piles[start[0] - 1].append(ra)
-            elif ra[0]["seed"] == "back" and ra[0]["contigA"][0] <= n_gaps:
-                piles[ra[0]["contigA"][0] - 1].append(ra)             # extends contig g beyond its end, into gap g
-            elif ra[0]["seed"] == "front" and ra[0]["contigA"][0] >= 2:
-                piles[ra[0]["contigA"][0] - 2].append(ra)             # extends contig g+1 beyond its begin, into gap g
-    return piles
+from tests.pipeline_util import build_pileups as _build_pileups, identity as _identity  # noqa: E402
 
 
 def test_collect_process_output_round_trip(tmp_path):
@@ -89,3 +49,27 @@ def test_collect_process_output_round_trip(tmp_path):
         t = sc[0][lbeg + left["las"][0]["ab"]:rbeg + right["las"][-1]["ae"]]
         ident = _identity(cons, t)
         assert ident >= 0.97, (g, ident, len(cons), len(t))
+
+
+def test_example_dataset_excerpt_gaps_are_closed(tmp_path):
+    """BASELINE configs[0] in miniature: 1.5 Mbp of the reference's own example assembly with the four gaps its gaps.bed
+    places there (tests/golden/example_excerpt.npz, cut by tests/golden/make_example_excerpt.py), reads from our generator
+    with the example's simulator settings (-m25000 -s12500 -e.13 -c20, example/Makefile:13; the DAZZ_DB simulator itself is
+    absent).  map -> collect filters -> PileUpDb -> dn_process_pileups -> InsertionDb closes all four gaps."""
+    import os
+    from tests import pipeline_util
+    z = np.load(os.path.join(os.path.dirname(__file__), "golden", "example_excerpt.npz"))
+    n = int(z["length"])
+    p = z["packed"]
+    scaffold = np.stack([(p >> 6) & 3, (p >> 4) & 3, (p >> 2) & 3, p & 3], 1).reshape(-1)[:n].astype(np.uint8)
+    gaps = [tuple(int(x) for x in g) for g in z["gaps"]]
+    assert n == 1500000 and len(gaps) == 4
+    ref, meta = synth.contigs_from([scaffold], [gaps])
+    reads, _ = synth.simulate_reads([scaffold], 20, 25000, 12500, 0.13, 19339)
+    ins, skipped, piles, st = pipeline_util.close_gaps(ref, reads, len(gaps), tmp_path, k=20, minlen=1000)
+    assert all(len(pl) >= 6 for pl in piles), [len(pl) for pl in piles]
+    assert not skipped and len(ins) == 4
+    for g, i in enumerate(ins):
+        assert i["start"] == (g + 1, "end") and i["end"] == (g + 2, "begin") and len(i["overlaps"]) == 2
+        ident, lc, lt = pipeline_util.gap_identity(i, scaffold, meta, g)
+        assert ident >= 0.97, (g, ident, lc, lt)

@@ -117,6 +117,40 @@ def test_dbdust_writes_a_track_that_mdust_reads(tmp_path):
     assert out.endswith("x.x.las")
 
 
+def test_dbdust_on_a_db_block_writes_the_block_level_track(tmp_path):
+    """ADVICE r1: the workflow dusts DB blocks one by one (`DBdust X.<n>` writes .X.<n>.dust.*, merged later by Catrack;
+    getMaskFiles dazzler.d:4870-4912).  dbdust on a block path must not overwrite the whole-DB track, and an alignment of
+    that block with -mdust must find the block-level track."""
+    from dentist_b200 import dazzler
+    from oracle import dust
+    import os
+    import struct
+    rng = np.random.default_rng(4)
+    seqs = [rng.integers(0, 4, 2500, dtype=np.uint8) for _ in range(6)]
+    seqs[4][300:460] = 2
+    off = np.zeros(7, np.int64); off[1:] = np.cumsum([len(s) for s in seqs])
+    blk = synth.Block(off, np.concatenate(seqs))
+    db = str(tmp_path / "y.db")
+    dbutil.write_db(db, blk, block_first=[3])                      # blocks: reads 0-2 and 3-5
+    dbutil.write_track(db, "dust", [[] for _ in range(6)])         # a whole-DB track that must survive
+    whole_before = open(str(tmp_path / ".y.dust.anno"), "rb").read()
+    dazzler.dbdustFile(str(tmp_path / "y.2.db"))
+    assert open(str(tmp_path / ".y.dust.anno"), "rb").read() == whole_before
+    anno = open(str(tmp_path / ".y.2.dust.anno"), "rb").read(); data = open(str(tmp_path / ".y.2.dust.data"), "rb").read()
+    n, size = struct.unpack_from("<ii", anno, 0)
+    assert (n, size) == (3, 0)
+    offs = struct.unpack_from("<4q", anno, 8)
+    got = [[struct.unpack_from("<ii", data, o) for o in range(offs[r], offs[r + 1], 8)] for r in range(3)]
+    assert got == dust.dust_block(blk.off, blk.bases)[3:] and got[1] and not got[0]
+    # the block alignment with -mdust reads .y.2.dust (the whole-DB track is empty): fewer seed hits than without a mask
+    sub = synth.Block(off[3:] - off[3], blk.bases[off[3]:])
+    masked = dazzler.align_blocks(dazzler.Block(sub.off, sub.bases, mask=got), dazzler.Block(sub.off, sub.bases, mask=got), tspace=126, minlen=500, self_block=1, identity=1)
+    out = dazzler.getDalignment(str(tmp_path / "y.2.db"), None, ["-s126", "-l500", "-mdust", "-I"], str(tmp_path))
+    assert os.path.basename(out) == "y.2.y.2.las"
+    _, rec, _, _ = dazzler.read_las(out)
+    assert rec.tobytes() == masked[0].tobytes() and len(rec) >= 3
+
+
 def test_getConsensus_file_form_on_the_reference_kat(tmp_path):
     """dazzler.d:4257-4299 through files: buildDamFile -> daligner -l15 -> filterPileUpAlignments -> getConsensus
     -> the consensus .dam holds exactly one read, equal to read 3."""
