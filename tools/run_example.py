@@ -39,6 +39,6 @@ for i in ins:
 print(json.dumps({"dataset": str(z["source"]), "assembly_bp": n, "gaps": len(gaps), "contigs": int(ref.nreads), "reads": int(reads.nreads),
                   "read_bp": int(reads.total), "pile_ups": len(piles), "pile_ups_with_>=3_reads": sum(len(pl) >= 3 for pl in piles),
                   "insertions": len(ins), "gaps_closed_as_gap_insertions": len(closed), "skipped": {str(k): v for k, v in skipped.items()},
-                  "identity_min": min(idents) if idents else None, "identity_median": float(np.median(idents)) if idents else None,
-                  "gaps_closed_at_>=0.97_identity": sum(v >= 0.97 for v in idents), "mapping": st,
+                  "identity_min": float(min(idents)) if idents else None, "identity_median": float(np.median(idents)) if idents else None,
+                  "gaps_closed_at_>=0.97_identity": int(sum(v >= 0.97 for v in idents)), "mapping": {k: int(v) for k, v in st.items()},
                   "seconds": {"generate_reads": t1 - t0, "map_collect_process": t2 - t1}, "gpu_launches": launches}))
