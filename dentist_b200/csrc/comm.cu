@@ -10,6 +10,12 @@
 // the system one), so the library has no link-time dependency on it and single-GPU users never touch it.
 #include "api_internal.hpp"
 #include <dlfcn.h>
+#include <fcntl.h>
+#include <sys/mman.h>
+#include <sys/stat.h>
+#include <unistd.h>
+#include <atomic>
+#include <new>
 #include <string.h>
 #include <stdlib.h>
 #include <algorithm>
@@ -108,14 +114,13 @@ __global__ void __launch_bounds__(256) k_seg_traces(const int32_t *__restrict__ 
 
 namespace dn {
 
-void merge_segments_device(const dn_las_record *d_rec, const int64_t *h_seg_beg, int world, const uint16_t *d_trace, int64_t ntrace,
-                           int64_t na, HostLas &out, cudaStream_t s) {
+// the merged LAS of the gathered segments, still in HBM (arena memory)
+struct MergedDev { dn_las_record *rec = nullptr; int64_t *toff = nullptr; uint16_t *trace = nullptr; int64_t n = 0, ntrace = 0; };
+
+static void merge_segments_on_device(const dn_las_record *d_rec, const int64_t *h_seg_beg, int world, const uint16_t *d_trace, int64_t ntrace,
+                                     int64_t na, MergedDev &M, cudaStream_t s) {
     const int64_t n = h_seg_beg[world];
-    out = HostLas();
-    out.rec = (dn_las_record *)hcache_alloc(sizeof(dn_las_record) * (size_t)(n + 1));
-    out.toff = (int64_t *)hcache_alloc(sizeof(int64_t) * (size_t)(n + 1));
-    out.trace = (uint16_t *)hcache_alloc(sizeof(uint16_t) * (size_t)(ntrace + 1));
-    out.nrec = n; out.ntrace = ntrace;
+    M = MergedDev(); M.n = n; M.ntrace = ntrace;
     if (n == 0) return;
     if (n >= (1ll << 31)) throw Error("too many records to merge");
     DBuf<int64_t> dseg(world + 1);
@@ -131,19 +136,27 @@ void merge_segments_device(const dn_las_record *d_rec, const int64_t *h_seg_beg,
     DN_LAUNCH(k_seg_place, (unsigned)((n + 255) / 256), 256, 0, s, d_rec, (const int64_t *)dseg.p, world, na, (const int32_t *)run.p,
               (const int32_t *)base.p, n, orec.p, tl.p, src.p);
     exclusive_scan_u32_to_i64(tl.p, dtoff.p, n, tot.p, s);
-    // the records leave for the host while the traces are still being gathered
-    static cudaStream_t copy_stream = nullptr; static cudaEvent_t ev = nullptr;
-    if (!copy_stream) { DN_CUDA(cudaStreamCreateWithFlags(&copy_stream, cudaStreamNonBlocking)); DN_CUDA(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming)); }
-    DN_CUDA(cudaEventRecord(ev, s));
-    DN_CUDA(cudaStreamWaitEvent(copy_stream, ev, 0));
-    DN_CUDA(cudaMemcpyAsync(out.rec, orec.p, sizeof(dn_las_record) * n, cudaMemcpyDeviceToHost, copy_stream));
-    DN_CUDA(cudaMemcpyAsync(out.toff, dtoff.p, sizeof(int64_t) * n, cudaMemcpyDeviceToHost, copy_stream));
     DBuf<uint16_t> otr((size_t)ntrace + 1);
     DN_LAUNCH(k_seg_traces, (unsigned)((n * 32 + 255) / 256), 256, 0, s, (const int32_t *)src.p, n, (const int64_t *)stoff.p,
               (const int64_t *)dtoff.p, (const dn_las_record *)orec.p, d_trace, otr.p);
-    if (ntrace) DN_CUDA(cudaMemcpyAsync(out.trace, otr.p, sizeof(uint16_t) * ntrace, cudaMemcpyDeviceToHost, s));
+    M.rec = orec.p; M.toff = dtoff.p; M.trace = otr.p;            // arena memory: stays valid until the next reset
+}
+
+void merge_segments_device(const dn_las_record *d_rec, const int64_t *h_seg_beg, int world, const uint16_t *d_trace, int64_t ntrace,
+                           int64_t na, HostLas &out, cudaStream_t s) {
+    const int64_t n = h_seg_beg[world];
+    out = HostLas();
+    out.rec = (dn_las_record *)hcache_alloc(sizeof(dn_las_record) * (size_t)(n + 1));
+    out.toff = (int64_t *)hcache_alloc(sizeof(int64_t) * (size_t)(n + 1));
+    out.trace = (uint16_t *)hcache_alloc(sizeof(uint16_t) * (size_t)(ntrace + 1));
+    out.nrec = n; out.ntrace = ntrace;
+    if (n == 0) return;
+    MergedDev M;
+    merge_segments_on_device(d_rec, h_seg_beg, world, d_trace, ntrace, na, M, s);
+    DN_CUDA(cudaMemcpyAsync(out.rec, M.rec, sizeof(dn_las_record) * n, cudaMemcpyDeviceToHost, s));
+    DN_CUDA(cudaMemcpyAsync(out.toff, M.toff, sizeof(int64_t) * n, cudaMemcpyDeviceToHost, s));
+    if (ntrace) DN_CUDA(cudaMemcpyAsync(out.trace, M.trace, sizeof(uint16_t) * ntrace, cudaMemcpyDeviceToHost, s));
     DN_CUDA(cudaStreamSynchronize(s));
-    DN_CUDA(cudaStreamSynchronize(copy_stream));
 }
 
 }  // namespace dn
@@ -205,21 +218,98 @@ AlignParams params_of(const dn_align_params *p) {
     return q;
 }
 
+// ---- sharded download (root >= 0, world > 1) ------------------------------------------------------------------
+// The root would have to pull the whole merged LAS (world x one rank's result) through its ONE PCIe link.  Instead every
+// rank receives all segments over NVLink (cheap), runs the same placement merge, and downloads only ITS 1/world slice of
+// the merged arrays -- through its OWN PCIe link -- into a host segment shared by the ranks of the node (POSIX shared
+// memory, page-locked by every rank).  The root's result points into that segment; two halves alternate, so a result
+// stays valid until the second following gather call.  Any failure to set the segment up (no /dev/shm space, ...) is
+// agreed on by all ranks at dn_comm_init and falls back to the root-only download.
+struct ShmHeader { std::atomic<unsigned long long> arrivals[2]; };
+struct Shm {
+    bool ok = false; int fd = -1; uint8_t *base = nullptr; size_t size = 0, half = 0; std::string name; unsigned long long calls[2] = {0, 0};
+    unsigned long long seq = 0;
+} g_shm;
+constexpr size_t SHM_HEADER = 4096;
+
+void shm_close() {
+    if (g_shm.base) { cudaHostUnregister(g_shm.base); munmap(g_shm.base, g_shm.size); }
+    if (g_shm.fd >= 0) close(g_shm.fd);
+    if (!g_shm.name.empty() && g_rank == 0) shm_unlink(g_shm.name.c_str());
+    g_shm = Shm();
+}
+
+// rank 0 creates the segment BEFORE it enters ncclCommInitRank; the others open it AFTER they left it
+bool shm_create_or_open(const uint8_t *id, int rank, bool create) {
+    unsigned long long h = 1469598103934665603ull;
+    for (int i = 0; i < DN_COMM_ID_BYTES; i++) h = (h ^ id[i]) * 1099511628211ull;
+    char nm[64]; snprintf(nm, sizeof nm, "/dn_b200_%016llx", h);
+    g_shm.name = nm;
+    const char *mb = getenv("DN_SHM_MB");
+    const size_t half = (size_t)(mb ? atoll(mb) : 384) << 20;
+    if (half == 0) return false;
+    g_shm.half = half; g_shm.size = SHM_HEADER + 2 * half;
+    g_shm.fd = shm_open(nm, create ? (O_CREAT | O_RDWR | O_TRUNC) : O_RDWR, 0600);
+    if (g_shm.fd < 0) return false;
+    if (create && (ftruncate(g_shm.fd, (off_t)g_shm.size) != 0 || posix_fallocate(g_shm.fd, 0, (off_t)g_shm.size) != 0)) return false;
+    void *p = mmap(nullptr, g_shm.size, PROT_READ | PROT_WRITE, MAP_SHARED, g_shm.fd, 0);
+    if (p == MAP_FAILED) return false;
+    g_shm.base = (uint8_t *)p;
+    if (create) { ShmHeader *H = new (g_shm.base) ShmHeader; H->arrivals[0].store(0); H->arrivals[1].store(0); }
+    if (cudaHostRegister(g_shm.base, g_shm.size, cudaHostRegisterPortable) != cudaSuccess) { cudaGetLastError(); return false; }
+    (void)rank;
+    return true;
+}
+
+bool shm_contains(const void *p) { return g_shm.base && (const uint8_t *)p >= g_shm.base && (const uint8_t *)p < g_shm.base + g_shm.size; }
+
 // after the local alignment: shift bread to the global numbering, gather, merge on the receiving ranks
 void gather_and_merge(DevLas &mine, HostLas &h, int64_t bread_offset, int root, int64_t na_reads, cudaStream_t s) {
     if (mine.nrec && bread_offset)
         DN_LAUNCH(k_shift_bread, (unsigned)((mine.nrec + 255) / 256), 256, 0, s, mine.rec, mine.nrec, (int32_t)bread_offset);
+    const bool want_shard = root >= 0 && g_world > 1 && g_shm.ok;
     std::vector<int64_t> seg_beg, tr_beg; DBuf<dn_las_record> allrec; DBuf<uint16_t> alltr;
-    gather_segments(mine, root, seg_beg, tr_beg, allrec, alltr, s);
+    gather_segments(mine, want_shard ? -1 : root, seg_beg, tr_beg, allrec, alltr, s);
     const dn_align_stats st = h.stats;
-    if (root < 0 || root == g_rank) {
-        hcache_free(h.rec); hcache_free(h.toff); hcache_free(h.trace); h.rec = nullptr; h.toff = nullptr; h.trace = nullptr;
-        merge_segments_device(allrec.p, seg_beg.data(), g_world, alltr.p, tr_beg[g_world], na_reads, h, s);
+    const int W = g_world;
+    const int64_t n = seg_beg[W], nt = tr_beg[W];
+    const size_t o_toff = ((size_t)n * sizeof(dn_las_record) + 255) & ~(size_t)255, o_tr = (o_toff + (size_t)n * 8 + 255) & ~(size_t)255;
+    const bool shard = want_shard && o_tr + (size_t)nt * 2 + 256 <= g_shm.half;       // every rank knows the sizes: same decision everywhere
+    if (shard) {
+        const unsigned long long seq = g_shm.seq++; const int hf = (int)(seq & 1);
+        uint8_t *dst = g_shm.base + SHM_HEADER + (size_t)hf * g_shm.half;
+        MergedDev M;
+        merge_segments_on_device(allrec.p, seg_beg.data(), W, alltr.p, nt, na_reads, M, s);
+        const int64_t r0 = n * g_rank / W, r1 = n * (g_rank + 1) / W, t0 = nt * g_rank / W, t1 = nt * (g_rank + 1) / W;
+        if (r1 > r0) {
+            DN_CUDA(cudaMemcpyAsync(dst + (size_t)r0 * sizeof(dn_las_record), M.rec + r0, sizeof(dn_las_record) * (size_t)(r1 - r0), cudaMemcpyDeviceToHost, s));
+            DN_CUDA(cudaMemcpyAsync(dst + o_toff + (size_t)r0 * 8, M.toff + r0, 8 * (size_t)(r1 - r0), cudaMemcpyDeviceToHost, s));
+        }
+        if (t1 > t0) DN_CUDA(cudaMemcpyAsync(dst + o_tr + (size_t)t0 * 2, M.trace + t0, 2 * (size_t)(t1 - t0), cudaMemcpyDeviceToHost, s));
+        DN_CUDA(cudaStreamSynchronize(s));
+        ShmHeader *H = (ShmHeader *)g_shm.base;
+        H->arrivals[hf].fetch_add(1, std::memory_order_release);
+        g_shm.calls[hf]++;
+        if (g_rank == root) {
+            const unsigned long long want = g_shm.calls[hf] * (unsigned long long)W;
+            while (H->arrivals[hf].load(std::memory_order_acquire) < want) { /* the other ranks' slices land within microseconds of ours */ }
+            hcache_free(h.rec); hcache_free(h.toff); hcache_free(h.trace);
+            h.rec = (dn_las_record *)dst; h.toff = (int64_t *)(dst + o_toff); h.trace = (uint16_t *)(dst + o_tr);
+            h.nrec = n; h.ntrace = nt;
+        }
+    } else if (root < 0 || root == g_rank || want_shard) {
+        // (want_shard but too large for the shared segment: every rank holds all segments; only the root merges and downloads)
+        if (root < 0 || root == g_rank) {
+            hcache_free(h.rec); hcache_free(h.toff); hcache_free(h.trace); h.rec = nullptr; h.toff = nullptr; h.trace = nullptr;
+            merge_segments_device(allrec.p, seg_beg.data(), W, alltr.p, nt, na_reads, h, s);
+        } else DN_CUDA(cudaStreamSynchronize(s));
     } else DN_CUDA(cudaStreamSynchronize(s));
     h.stats = st;                                 // the statistics stay this rank's own
 }
 
 }  // namespace
+
+namespace dn { bool comm_owns_host_pointer(const void *p) { return shm_contains(p); } }
 
 extern "C" {
 
@@ -242,9 +332,33 @@ int dn_comm_init(int32_t rank, int32_t world, const uint8_t *id) {
         if (!load_nccl(err)) return fail(DN_ERR_INVALID, err);
         cudaSetDevice(g_device);
         if (g_comm) { N.CommDestroy(g_comm); g_comm = nullptr; }
+        shm_close();
+        g_rank = rank; g_world = world;
+        const bool use_shm = world > 1 && !getenv("DN_NO_SHM");
+        bool mine_ok = false;
+        if (use_shm && rank == 0) mine_ok = shm_create_or_open(id, rank, true);       // before the collective init: the others open it after
         NcclId u; memcpy(&u, id, DN_COMM_ID_BYTES);
         DN_NCCL(N.CommInitRank(&g_comm, world, u, rank));
-        g_rank = rank; g_world = world;
+        if (use_shm && rank != 0) mine_ok = shm_create_or_open(id, rank, false);
+        if (world > 1) {
+            // all ranks must agree: one rank without the segment switches everybody to the root-only download
+            arena().reset();
+            DBuf<int64_t> f(1), all(world);
+            const int64_t v = mine_ok ? 1 : 0;
+            DN_CUDA(cudaMemcpyAsync(f.p, &v, 8, cudaMemcpyHostToDevice, g_stream));
+            DN_NCCL(N.AllGather(f.p, all.p, 1, 4, g_comm, g_stream));
+            std::vector<int64_t> hv(world);
+            DN_CUDA(cudaMemcpyAsync(hv.data(), all.p, 8 * (size_t)world, cudaMemcpyDeviceToHost, g_stream));
+            DN_CUDA(cudaStreamSynchronize(g_stream));
+            bool all_ok = use_shm;
+            for (int64_t x : hv) all_ok = all_ok && x == 1;
+            g_shm.ok = all_ok;
+            // every rank holds its mapping now: the name can go, so that a crashed job leaves nothing behind in /dev/shm
+            if (rank == 0 && !g_shm.name.empty()) { shm_unlink(g_shm.name.c_str()); }
+            g_shm.name.clear();
+            if (!all_ok) shm_close();
+            if (!all_ok && use_shm && getenv("DN_TRACE")) fprintf(stderr, "[dn trace] shared host segment unavailable: root-only download\n");
+        }
         return DN_OK;
     });
 }
@@ -252,6 +366,7 @@ int dn_comm_init(int32_t rank, int32_t world, const uint8_t *id) {
 int dn_comm_shutdown(void) {
     std::lock_guard<std::mutex> lk(g_mu);
     if (g_comm) { if (g_stream) cudaStreamSynchronize(g_stream); N.CommDestroy(g_comm); g_comm = nullptr; }
+    shm_close();
     g_rank = 0; g_world = 1;
     return DN_OK;
 }

@@ -70,8 +70,9 @@ void *hcache_alloc(size_t bytes) {
     h->cap = cap; h->pinned = pinned;
     return (void *)(h + 1);
 }
+bool comm_owns_host_pointer(const void *p);           // comm.cu: results of the sharded multi-GPU download live in a shared segment
 void hcache_free(void *p) {
-    if (!p) return;
+    if (!p || comm_owns_host_pointer(p)) return;
     HBlock *h = (HBlock *)p - 1;
     std::lock_guard<std::mutex> lk(g_hmu);
     if (g_hfree.size() < 16) { g_hfree.push_back(h); return; }

@@ -15,12 +15,15 @@ def main():
     ap.add_argument("--lens", default="1000,2000,5000,10000,20000,50000,100000"); ap.add_argument("--errors", default="0.05,0.10,0.15")
     ap.add_argument("--k", type=int, default=20, help="k-mer length (damapper default 20)")
     ap.add_argument("--ont", action="store_true", help="ONT-like error mix and a log-normal length spread (configs[2] reads)")
+    ap.add_argument("--resident-index", action="store_true", help="build the reference block's k-mer index once (dn_block_index), as a multi-block job does")
     a = ap.parse_args()
     dazzler.init(0)
     n_sc = max(1, int(a.ref_mbp))
     sc = synth.make_scaffolds(n_sc, 1000000, 4001, n_repeats=0)
     ref, _ = synth.contigs_from(sc, [[] for _ in sc])
     ga = dazzler.Block(ref.off, ref.bases)
+    if a.resident_index:
+        ga.index(a.k)
     out = open(a.out, "w")
     for L in [int(x) for x in a.lens.split(",")]:
         for ei, e in enumerate([float(x) for x in a.errors.split(",")]):
@@ -38,7 +41,7 @@ def main():
                 ms += st["ms_total"]; al += st["aligned_bases"]
             row = dict(k=a.k, read_len=L, error=e, ref_bp=int(ref.total), reads_bp=int(reads.total), reads=int(reads.nreads), las=int(len(rec)),
                        ms_per_step=ms / 3, gbp_aligned_per_s=al / 1e9 / (ms / 1e3), input_gbp_per_s=3 * reads.total / 1e9 / (ms / 1e3),
-                       hits=int(st["hits"]), seeds=int(st["seeds"]))
+                       hits=int(st["hits"]), seeds=int(st["seeds"]), ms_extend=float(st["ms_extend"]), resident_index=bool(a.resident_index))
             if a.cpu:
                 from oracle import oracle
                 nr = max(1, int(np.searchsorted(reads.off, 300000)))
