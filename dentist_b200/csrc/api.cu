@@ -303,30 +303,25 @@ static int align_files(const char *dbA, const char *dbB, const char *const *opts
         HostDb &Bx = self ? A : B;
         p.self_block = self ? 1 : 0;
         dn_block_desc da = A.desc(), db = Bx.desc();
-        dn_las_buf ab; memset(&ab, 0, sizeof ab);
-        int rc = dn_align_host(&da, self ? &da : &db, &p, &ab);
-        if (rc) return rc;
+        struct Blk { dn_block *b = nullptr; ~Blk() { if (b) dn_block_free(b); } } ga, gb;
+        struct LasG { dn_las_buf l; LasG() { memset(&l, 0, sizeof l); } ~LasG() { dn_las_free(&l); } } ab, ba;
+        if (int rc = dn_block_upload(&da, &ga.b)) return rc;
+        if (!self) { if (int rc = dn_block_upload(&db, &gb.b)) return rc; }
+        const dn_block *pb = self ? ga.b : gb.b;
+        if (int rc = dn_align_blocks(ga.b, pb, &p, &ab.l)) return rc;
         if (mapper) {
-            rc = dn_las_chain_mapper(&ab, (int32_t)Bx.rlen.size(), 1000, 10000);
-            if (!rc) rc = dn_las_keep_best_chains(&ab, (int32_t)Bx.rlen.size(), best_frac);
-            if (rc) { dn_las_free(&ab); return rc; }
+            if (int rc = dn_las_chain_mapper(&ab.l, (int32_t)Bx.rlen.size(), 1000, 10000)) return rc;
+            if (int rc = dn_las_keep_best_chains(&ab.l, (int32_t)Bx.rlen.size(), best_frac)) return rc;
         }
         std::string pa = std::string(outdir) + "/" + A.name + "." + Bx.name + ".las";
-        rc = dn_las_write(pa.c_str(), &ab);
-        dn_las_free(&ab);
-        if (rc) return rc;
+        if (int rc = dn_las_write(pa.c_str(), &ab.l)) return rc;
         if (!self && (!asym || mapper)) {
-            dn_las_buf ba; memset(&ba, 0, sizeof ba);
-            rc = dn_align_host(&db, &da, &p, &ba);
-            if (rc) return rc;
-            if (mapper) {
-                rc = dn_las_chain_mapper(&ba, (int32_t)A.rlen.size(), 1000, 10000);
-                if (rc) { dn_las_free(&ba); return rc; }
-            }
-            std::string pb = std::string(outdir) + "/" + Bx.name + "." + A.name + ".las";
-            rc = dn_las_write(pb.c_str(), &ba);
-            dn_las_free(&ba);
-            if (rc) return rc;
+            // the second file holds "all the same matches" with the reads' roles swapped (damapper -C, dazzler.d:5931-5936;
+            // daligner without -A, :5797-5801): the transposition of the first, not a second alignment
+            if (int rc = dn_las_transpose(ga.b, gb.b, &ab.l, &ba.l)) return rc;
+            if (mapper) { if (int rc = dn_las_chain_mapper(&ba.l, (int32_t)A.rlen.size(), 1000, 10000)) return rc; }
+            std::string pbn = std::string(outdir) + "/" + Bx.name + "." + A.name + ".las";
+            if (int rc = dn_las_write(pbn.c_str(), &ba.l)) return rc;
         }
         return DN_OK;
     });

@@ -216,6 +216,65 @@ int dn_reference_read_candidates(const uint8_t *qv, const int64_t *qoff, const i
     });
 }
 
+// damapper -C (dazzler.d:5931-5936): the records of B.A.las from those of A.B.las -- roles swapped, coordinates mirrored for
+// complemented alignments, trace points re-laid on the new A read by per-tile realignment (spec: oracle/pile_oracle.c,
+// orc_transpose), result in LAsort order.  Chain flags are cleared (chain the result again: the criteria are symmetric).
+int dn_las_transpose(const dn_block *a, const dn_block *b, const dn_las_buf *las, dn_las_buf *out) {
+    if (!a || !b || !las || !out) return fail(DN_ERR_INVALID, "null argument");
+    const DevBlock &A = a->b, &B = b->b;
+    const int ts = las->tspace;
+    if (ts < 1) return fail(DN_ERR_INVALID, "bad trace spacing");
+    if (const char *bad = validate_las(las, A.h_len.data(), A.nreads, B.h_len.data(), B.nreads, true)) return fail(DN_ERR_INVALID, bad);
+    std::lock_guard<std::mutex> lk(g_mu);
+    if (int rc = ensure_device()) return rc;
+    return guarded([&]() -> int {
+        cudaSetDevice(g_device); arena().reset();
+        cudaStream_t s = g_stream;
+        const int64_t n = las->nrec;
+        std::vector<int32_t> vla(n); std::vector<int64_t> task0(n + 1, 0), otoff(n + 1, 0);
+        int maxm = 0;
+        for (int64_t i = 0; i < n; i++) {
+            const dn_las_record &r = las->rec[i];
+            vla[i] = (int32_t)i; task0[i + 1] = task0[i] + r.tlen / 2;
+            for (int q = 0; q < r.tlen / 2; q++) maxm = std::max<int>(maxm, las->trace[las->toff[i] + 2 * q + 1]);
+            const bool comp = (r.flags & DN_LAS_COMP) != 0;
+            const int lb = B.h_len[r.bread];
+            const int ab2 = comp ? lb - r.bepos : r.bbpos, ae2 = comp ? lb - r.bbpos : r.bepos;
+            otoff[i + 1] = otoff[i] + (ae2 > ab2 ? 2 * ((ae2 + ts - 1) / ts - ab2 / ts) : 0);
+        }
+        const int64_t ntasks = task0[n], ntr = otoff[n];
+        const int kmax = maxm / ts + 2;
+        HostLas h;
+        if (n == 0) {
+            h.rec = (dn_las_record *)hcache_alloc(64); h.toff = (int64_t *)hcache_alloc(64); h.trace = (uint16_t *)hcache_alloc(64);
+        } else {
+            DevLasIn d; d.upload(las, true, s);
+            DBuf<int32_t> d_vla; DBuf<int64_t> d_task0, d_otoff;
+            to_device(d_vla, vla.data(), (size_t)n, s); to_device(d_task0, task0.data(), (size_t)n + 1, s); to_device(d_otoff, otoff.data(), (size_t)n + 1, s);
+            DBuf<ConsTask> tasks((size_t)ntasks + 1);
+            launch_cons_tasks(d.rec.p, d.toff.p, d.trace.p, d_vla.p, (int)n, d_task0.p, ts, tasks.p, s);
+            TrGeom G{A.fwd.p, B.fwd.p, B.rc.p, A.off.p, B.off.p, A.len.p, B.len.p};
+            DBuf<u32> scratch((size_t)cons_vote_threads() * 2048);
+            DBuf<int4> cross((size_t)ntasks * kmax + 1); DBuf<int32_t> ncross((size_t)ntasks + 1), tcost((size_t)ntasks + 1), status(1);
+            status.zero(s);
+            launch_tr_tiles(tasks.p, ntasks, d.rec.p, d.toff.p, d.trace.p, d_task0.p, G, ts, kmax, scratch.p, cross.p, ncross.p, tcost.p, s);
+            DBuf<dn_las_record> orec((size_t)n); DBuf<uint16_t> otr((size_t)ntr + 2);
+            launch_tr_assemble(d.rec.p, n, d_task0.p, G, kmax, cross.p, ncross.p, tcost.p, d_otoff.p, orec.p, otr.p, status.p, s);
+            int32_t st = 0;
+            DN_CUDA(cudaMemcpyAsync(&st, status.p, 4, cudaMemcpyDeviceToHost, s)); DN_CUDA(cudaStreamSynchronize(s));
+            if (st) return fail(DN_ERR_INVALID, "transpose: more trace-point crossings in one tile than its B bases allow");
+            // LAsort order of the transposed records (aread' = B read ...), traces gathered, one download
+            merge_las_device(orec.p, n, otr.p, ntr, B.maxlen, A.maxlen, B.nreads, A.nreads, h, s, false);
+            for (int64_t i = 0; i < h.nrec; i++) h.rec[i].flags &= (DN_LAS_COMP | DN_LAS_ELIM);
+        }
+        memset(out, 0, sizeof *out);
+        out->nrec = h.nrec; out->ntrace = h.ntrace; out->tspace = ts;
+        out->rec = h.rec; out->toff = h.toff; out->trace = h.trace;
+        h.rec = nullptr; h.toff = nullptr; h.trace = nullptr;
+        return DN_OK;
+    });
+}
+
 void dn_seq_free(dn_seq_buf *b) { if (!b) return; hcache_free(b->off); hcache_free(b->bases); memset(b, 0, sizeof *b); }
 
 int dn_consensus(const dn_block *db, const dn_las_buf *las, const int32_t *reads, int32_t nreads, dn_seq_buf *out) {

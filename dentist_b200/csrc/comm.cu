@@ -232,8 +232,11 @@ struct Shm {
 } g_shm;
 constexpr size_t SHM_HEADER = 4096;
 
+// Results handed to the caller point into the segment and may be released (dn_las_free) long after dn_comm_shutdown: the
+// mapping is therefore never unmapped before the process ends -- only the descriptor and the name go -- and every range
+// ever mapped stays known to comm_owns_host_pointer.
+std::vector<std::pair<const uint8_t *, size_t>> g_shm_ranges;
 void shm_close() {
-    if (g_shm.base) { cudaHostUnregister(g_shm.base); munmap(g_shm.base, g_shm.size); }
     if (g_shm.fd >= 0) close(g_shm.fd);
     if (!g_shm.name.empty() && g_rank == 0) shm_unlink(g_shm.name.c_str());
     g_shm = Shm();
@@ -255,13 +258,17 @@ bool shm_create_or_open(const uint8_t *id, int rank, bool create) {
     void *p = mmap(nullptr, g_shm.size, PROT_READ | PROT_WRITE, MAP_SHARED, g_shm.fd, 0);
     if (p == MAP_FAILED) return false;
     g_shm.base = (uint8_t *)p;
+    g_shm_ranges.emplace_back(g_shm.base, g_shm.size);
     if (create) { ShmHeader *H = new (g_shm.base) ShmHeader; H->arrivals[0].store(0); H->arrivals[1].store(0); }
     if (cudaHostRegister(g_shm.base, g_shm.size, cudaHostRegisterPortable) != cudaSuccess) { cudaGetLastError(); return false; }
     (void)rank;
     return true;
 }
 
-bool shm_contains(const void *p) { return g_shm.base && (const uint8_t *)p >= g_shm.base && (const uint8_t *)p < g_shm.base + g_shm.size; }
+bool shm_contains(const void *p) {
+    for (const auto &r : g_shm_ranges) if ((const uint8_t *)p >= r.first && (const uint8_t *)p < r.first + r.second) return true;
+    return false;
+}
 
 // after the local alignment: shift bread to the global numbering, gather, merge on the receiving ranks
 void gather_and_merge(DevLas &mine, HostLas &h, int64_t bread_offset, int root, int64_t na_reads, cudaStream_t s) {

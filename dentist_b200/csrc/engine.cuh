@@ -73,7 +73,7 @@ void block_crop(const DevBlock &src, int n, const int32_t *read, const int32_t *
                 DevBlock &out, cudaStream_t s);
 void force_flat_device(dn_las_record *h_rec, int64_t *h_toff, int64_t n, cudaStream_t s);
 void merge_las_device(const dn_las_record *d_rec, int64_t n, const uint16_t *d_trace, int64_t ntrace, int64_t max_alen, int64_t max_blen,
-                      int64_t na_reads, int64_t nb_reads, HostLas &out, cudaStream_t s);
+                      int64_t na_reads, int64_t nb_reads, HostLas &out, cudaStream_t s, bool reset_arena = true);
 // The same result left in HBM (arena memory: valid until the next call resets the arena) -- the input of the multi-GPU
 // gather, which must not bounce through the host.
 struct DevLas { dn_las_record *rec = nullptr; int64_t *toff = nullptr; uint16_t *trace = nullptr; int64_t nrec = 0, ntrace = 0; };

@@ -768,9 +768,9 @@ void force_flat_device(dn_las_record *h_rec, int64_t *h_toff, int64_t n, cudaStr
 }
 
 void merge_las_device(const dn_las_record *d_rec, int64_t n, const uint16_t *d_trace, int64_t ntrace, int64_t max_alen, int64_t max_blen,
-                      int64_t na_reads, int64_t nb_reads, HostLas &out, cudaStream_t s) {
+                      int64_t na_reads, int64_t nb_reads, HostLas &out, cudaStream_t s, bool reset_arena) {
     out = HostLas();
-    arena().reset();
+    if (reset_arena) arena().reset();                  // false: the inputs themselves live in the arena (dn_las_transpose)
     out.rec = (dn_las_record *)hcache_alloc(sizeof(dn_las_record) * (size_t)(n + 1));
     out.toff = (int64_t *)hcache_alloc(sizeof(int64_t) * (size_t)(n + 1));
     out.trace = (uint16_t *)hcache_alloc(sizeof(uint16_t) * (size_t)(ntrace + 1));

@@ -195,7 +195,146 @@ __global__ void __launch_bounds__(256) k_cons_write(int64_t ncols, const int32_t
     for (int e = 0; e < nemit[c]; e++) out[eoff[c] + e] = sym[2 * c + e];
 }
 
+// ---- transposition (damapper -C, dazzler.d:5931-5936): specification in oracle/pile_oracle.c (orc_transpose) -----------
+// thread per A tile: the same unit-cost DP and traceback as the consensus vote; instead of votes it records where the
+// path crosses the trace-point columns of the NEW A read (= B): {x, a, c} = column, the other read's coordinate there,
+// and the diffs from the tile's start (not complemented) or from its end (complemented: the new read runs backwards).
+__global__ void __launch_bounds__(128) k_tr_tiles(const ConsTask *__restrict__ tasks, int64_t ntasks, const dn_las_record *__restrict__ rec,
+                                                  const int64_t *__restrict__ toff, const uint16_t *__restrict__ trace,
+                                                  const int64_t *__restrict__ la_task0, TrGeom G, int ts, int kmax,
+                                                  u32 *__restrict__ scratch, int4 *__restrict__ cross, int32_t *__restrict__ ncross,
+                                                  int32_t *__restrict__ tcost) {
+    const int64_t nthreads = (int64_t)gridDim.x * blockDim.x;
+    const int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    u32 *dirs = scratch + tid;
+    for (int64_t task = tid; task < ntasks; task += nthreads) {
+        const ConsTask T = tasks[task];
+        const int n = T.alen, m = T.bb;
+        const dn_las_record la = rec[T.la];
+        const bool comp = (la.flags & DN_LAS_COMP) != 0;
+        const int lb = G.b_len[la.bread], lo = la.bbpos, hi = la.bepos, bp = T.bp;
+        int4 *cr = cross + task * kmax; int nc = 0;
+        if (m > 250 || n > 128) {                             // diagonal-first path, the tile's recorded diffs spread along it
+            const int dt = trace[toff[T.la] + 2 * (task - la_task0[T.la])];
+            const int q = n < m ? n : m;
+            for (int j = m; j >= 0; j--) {
+                const int x = bp + j;
+                if (x <= lo || x >= hi) continue;
+                int i;
+                if (!comp) { if (j == 0 || x % ts) continue; i = j <= q ? j : n; if (j == m && n > m) i = m; }
+                else { if (j == m || (lb - x) % ts) continue; i = j <= q ? j : n; }
+                const int from_start = (n + m) ? (int)((long long)dt * (i + j) / (n + m)) : 0;
+                if (nc < kmax) cr[nc] = make_int4(x, T.ap + i, comp ? dt - from_start : from_start, 0);
+                nc++;
+            }
+            ncross[task] = nc; tcost[task] = dt;
+            continue;
+        }
+        const u32 *Aw = G.a_fwd, *Bw = comp ? G.b_rc : G.b_fwd;
+        const int64_t ga = G.a_off[la.aread] + T.ap, gb = G.b_off[la.bread] + T.bp;
+        unsigned char bq[256], row[256];
+        for (int j = 0; j < m; j++) bq[j] = (unsigned char)base_at(Bw, gb + j);
+        for (int j = 0; j <= m; j++) row[j] = (unsigned char)j;
+        const int wpr = (m + 16) >> 4;
+        for (int i = 1; i <= n; i++) {
+            const int ai = base_at(Aw, ga + i - 1);
+            int diag = row[0]; row[0] = (unsigned char)i;
+            int left = i;
+            u32 word = 0;
+            for (int j = 1; j <= m; j++) {
+                const int up = row[j];
+                const int d = diag + (ai != bq[j - 1]), u = up + 1, l = left + 1;
+                int v = d; if (u < v) v = u; if (l < v) v = l;
+                const u32 dir = (v == d) ? 0u : ((v == u) ? 1u : 2u);
+                word |= dir << ((j & 15) << 1);
+                if ((j & 15) == 15 || j == m) { dirs[(int64_t)((i - 1) * wpr + (j >> 4)) * nthreads] = word; word = 0; }
+                row[j] = (unsigned char)v; diag = up; left = v;
+            }
+        }
+        const int total = n == 0 ? m : row[m];
+        int i = n, j = m, cend = 0;
+        for (;;) {
+            u32 dir;
+            if (i == 0 && j == 0) dir = 3u; else if (i == 0) dir = 2u; else if (j == 0) dir = 1u;
+            else dir = (dirs[(int64_t)((i - 1) * wpr + (j >> 4)) * nthreads] >> ((j & 15) << 1)) & 3u;
+            const int x = bp + j;
+            if (!comp && (dir == 0u || dir == 2u) && j > 0 && x % ts == 0 && x > lo && x < hi) {      // leaving column j: its last (lowest) cell
+                if (nc < kmax) cr[nc] = make_int4(x, T.ap + i, total - cend, 0);
+                nc++;
+            }
+            if (dir == 3u) break;
+            if (dir == 0u) { cend += (base_at(Aw, ga + i - 1) != (int)bq[j - 1]); i--; j--; }
+            else if (dir == 1u) { cend += 1; i--; }
+            else { cend += 1; j--; }
+            if (comp && (dir == 0u || dir == 2u)) {                                                      // entering column j: its first (highest) cell
+                const int xn = bp + j;
+                if ((lb - xn) % ts == 0 && xn > lo && xn < hi) { if (nc < kmax) cr[nc] = make_int4(xn, T.ap + i, cend, 0); nc++; }
+            }
+        }
+        ncross[task] = nc; tcost[task] = total;
+    }
+}
+
+// thread per record: strings the tiles' crossings together into the trace of the transposed record
+__global__ void __launch_bounds__(128) k_tr_assemble(const dn_las_record *__restrict__ rec, int64_t nla, const int64_t *__restrict__ la_task0,
+                                                     TrGeom G, int kmax, const int4 *__restrict__ cross, const int32_t *__restrict__ ncross,
+                                                     const int32_t *__restrict__ tcost, const int64_t *__restrict__ out_toff,
+                                                     dn_las_record *__restrict__ out, uint16_t *__restrict__ out_trace, int32_t *__restrict__ status) {
+    const int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= nla) return;
+    const dn_las_record x = rec[r];
+    const int nt = x.tlen / 2;
+    const int64_t t0 = la_task0[r];
+    const bool comp = (x.flags & DN_LAS_COMP) != 0;
+    const int LA = G.a_len[x.aread], LB = G.b_len[x.bread];
+    dn_las_record o = x;
+    o.aread = x.bread; o.bread = x.aread;
+    uint16_t *tr = out_trace + out_toff[r];
+    int total = 0, ntp = 0, w = 0;
+    for (int t = 0; t < nt; t++) { total += tcost[t0 + t]; if (ncross[t0 + t] > kmax) atomicExch(status, 1); }
+    if (!comp) {
+        o.abpos = x.bbpos; o.aepos = x.bepos; o.bbpos = x.abpos; o.bepos = x.aepos;
+        int pa = x.abpos, pd = 0, base = 0;
+        for (int t = 0; t < nt; t++) {
+            const int4 *cr = cross + (t0 + t) * kmax;
+            for (int q = min(ncross[t0 + t], kmax) - 1; q >= 0; q--) {
+                const int d = base + cr[q].z;
+                tr[w++] = (uint16_t)(d - pd); tr[w++] = (uint16_t)(cr[q].y - pa); ntp++;
+                pd = d; pa = cr[q].y;
+            }
+            base += tcost[t0 + t];
+        }
+        if (x.bepos > x.bbpos) { tr[w++] = (uint16_t)(total - pd); tr[w++] = (uint16_t)(x.aepos - pa); ntp++; }
+    } else {
+        o.abpos = LB - x.bepos; o.aepos = LB - x.bbpos; o.bbpos = LA - x.aepos; o.bepos = LA - x.abpos;
+        int pa = x.aepos, pd = 0, base = 0;
+        for (int t = nt - 1; t >= 0; t--) {
+            const int4 *cr = cross + (t0 + t) * kmax;
+            const int k = min(ncross[t0 + t], kmax);
+            for (int q = 0; q < k; q++) {
+                const int d = base + cr[q].z;
+                tr[w++] = (uint16_t)(d - pd); tr[w++] = (uint16_t)(pa - cr[q].y); ntp++;
+                pd = d; pa = cr[q].y;
+            }
+            base += tcost[t0 + t];
+        }
+        if (x.bepos > x.bbpos) { tr[w++] = (uint16_t)(total - pd); tr[w++] = (uint16_t)(pa - x.abpos); ntp++; }
+    }
+    o.diffs = total; o.tlen = 2 * ntp;
+    out[r] = o;
+}
+
 }  // namespace
+
+void launch_tr_tiles(const ConsTask *tasks, int64_t ntasks, const dn_las_record *rec, const int64_t *toff, const uint16_t *trace,
+                     const int64_t *la_task0, TrGeom G, int ts, int kmax, u32 *scratch, int4 *cross, int32_t *ncross, int32_t *tcost, cudaStream_t s) {
+    DN_LAUNCH(k_tr_tiles, sm_count() * 4, 128, 0, s, tasks, ntasks, rec, toff, trace, la_task0, G, ts, kmax, scratch, cross, ncross, tcost);
+}
+void launch_tr_assemble(const dn_las_record *rec, int64_t nla, const int64_t *la_task0, TrGeom G, int kmax, const int4 *cross,
+                        const int32_t *ncross, const int32_t *tcost, const int64_t *out_toff, dn_las_record *out, uint16_t *out_trace,
+                        int32_t *status, cudaStream_t s) {
+    DN_LAUNCH(k_tr_assemble, (unsigned)((nla + 127) / 128), 128, 0, s, rec, nla, la_task0, G, kmax, cross, ncross, tcost, out_toff, out, out_trace, status);
+}
 
 void las_filter_device(const dn_las_record *rec, const int64_t *toff, int64_t n, int mode, double max_err, const int32_t *alen,
                        const int32_t *blen, int allowance, dn_las_record *orec, int64_t *otoff, int64_t *n_out, cudaStream_t s) {

@@ -10,6 +10,14 @@ struct ConsGeom {
     const int64_t *vote_off;      // [ntargets+1] first vote column of each target read (L+1 columns each)
 };
 
+// transposition (damapper -C): A and B blocks of the alignment
+struct TrGeom { const u32 *a_fwd, *b_fwd, *b_rc; const int64_t *a_off, *b_off; const int32_t *a_len, *b_len; };
+void launch_tr_tiles(const ConsTask *tasks, int64_t ntasks, const dn_las_record *rec, const int64_t *toff, const uint16_t *trace,
+                     const int64_t *la_task0, TrGeom G, int ts, int kmax, u32 *scratch, int4 *cross, int32_t *ncross, int32_t *tcost, cudaStream_t s);
+void launch_tr_assemble(const dn_las_record *rec, int64_t nla, const int64_t *la_task0, TrGeom G, int kmax, const int4 *cross,
+                        const int32_t *ncross, const int32_t *tcost, const int64_t *out_toff, dn_las_record *out, uint16_t *out_trace,
+                        int32_t *status, cudaStream_t s);
+
 // mode 0: keep diffs/(aepos-abpos) <= max_err; mode 1: isValidPileUpAlignment(allowance). Order preserving.
 void las_filter_device(const dn_las_record *rec, const int64_t *toff, int64_t n, int mode, double max_err, const int32_t *alen,
                        const int32_t *blen, int allowance, dn_las_record *orec, int64_t *otoff, int64_t *n_out, cudaStream_t s);

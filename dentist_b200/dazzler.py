@@ -313,6 +313,12 @@ class Las:
         self._refresh()
         return self
 
+    def transpose(self, a, b):
+        """`damapper -C`'s second file (dazzler.d:5931-5936): the records of B.A.las for these records of A.B.las."""
+        buf = _lib.LasBuf()
+        _lib.check(_lib.lib().dn_las_transpose(a._h, b._h, C.byref(self._buf), C.byref(buf)))
+        return Las(buf)
+
     def write(self, path):
         _lib.check(_lib.lib().dn_las_write(path.encode(), C.byref(self._buf)))
 

@@ -290,6 +290,12 @@ int dn_block_add_mask(dn_block *blk, const int64_t *mask_anno, const int32_t *ma
  * AlignmentChains at :708-743.  `las` must be in LAsort order (as dn_align_blocks returns it). */
 int dn_las_chain_mapper(dn_las_buf *las, int32_t nb_reads, int32_t max_indel, int32_t max_gap);
 
+/* `damapper -C` (dazzler.d:5931-5936): "Y.X.las ... contains all the same matches as in X.Y.las" with the reads' roles
+ * swapped.  `las` = records of A.B.las (traces required), a / b = the resident blocks they refer to; out = the records of
+ * B.A.las in LAsort order: coordinates mirrored (complemented alignments: each read in its own frame), trace points
+ * re-laid every tspace bases of the new A read along the per-tile alignment path, chain flags cleared. */
+int dn_las_transpose(const dn_block *a, const dn_block *b, const dn_las_buf *las, dn_las_buf *out);
+
 /* What damapper reports: per mapped read its best chain and, with -n<f>, every chain scoring at least the fraction f of
  * the best (dazzler.d:5920-5923).  n_frac <= 0: the BEST chains only (DENTIST passes no -n, commandline.d:2943-2955).
  * `las` must carry the flags of dn_las_chain_mapper.  In place, order preserving. */

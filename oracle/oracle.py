@@ -151,3 +151,21 @@ def consensus(off, bases, rec, toff, trace, tspace, read):
     f.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_void_p, C.POINTER(C.c_int32)]
     f(_p(off), _p(bases), _p(r), len(r), _p(toff), _p(trace), int(tspace), int(read), _p(out), C.byref(n))
     return out[:n.value].copy()
+
+
+def transpose(a_off, a_bases, b_off, b_bases, rec, toff, trace, tspace):
+    """orc_transpose: the records of B.A.las for the records of A.B.las (input order; the caller sorts).
+    Returns (records LAS40, toff, trace)."""
+    a_off = np.ascontiguousarray(a_off, np.int64); a_bases = np.ascontiguousarray(a_bases, np.uint8)
+    b_off = np.ascontiguousarray(b_off, np.int64); b_bases = np.ascontiguousarray(b_bases, np.uint8)
+    r = _las40(rec); toff = np.ascontiguousarray(toff, np.int64); trace = np.ascontiguousarray(trace, np.uint16)
+    blen = np.diff(b_off)
+    comp = (r["flags"] & 1).astype(bool)
+    ab2 = np.where(comp, blen[r["bread"]] - r["bepos"], r["bbpos"]); ae2 = np.where(comp, blen[r["bread"]] - r["bbpos"], r["bepos"])
+    nt2 = np.where(ae2 > ab2, -(-ae2 // tspace) - ab2 // tspace, 0)
+    out = np.zeros(len(r), LAS40); otoff = np.zeros(len(r), np.int64); otr = np.zeros(int(2 * nt2.sum()) + 2, np.uint16)
+    f = lib().orc_transpose
+    f.argtypes = [C.c_void_p] * 5 + [C.c_int64, C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p]
+    f(_p(a_off), _p(a_bases), _p(b_off), _p(b_bases), _p(r), len(r), _p(toff), _p(trace), int(tspace), _p(out), _p(otoff), _p(otr))
+    assert np.array_equal(out["tlen"], 2 * nt2)
+    return out, otoff, otr[:int(2 * nt2.sum())]

@@ -187,3 +187,141 @@ int orc_consensus(const int64_t *off, const uint8_t *bases, const las_rec *la, i
     free(cnt); free(ins); free(insn); free(cov); free(brc);
     return 0;
 }
+
+/* ------------------------------------------------------------------------------------------------------------
+ * orc_transpose -- what `damapper -C` adds (dazzler.d:5931-5936): the file Y.X.las "that contains all the same matches
+ * as in X.Y.las" with the roles of the reads swapped.  PARITY UNPINNED (DAMAPPER absent); specification:
+ *   record: aread' = bread, bread' = aread, COMP kept; not complemented: (ab', ae', bb', be') = (bb, be, ab, ae);
+ *           complemented: ab' = lb - be, ae' = lb - bb, bb' = la - ae, be' = la - ab (each read in its own frame).
+ *   path:   every A tile (its A bases against its B bases) is aligned globally with unit costs, traceback from the end
+ *           preferring diagonal, then "A base unmatched", then "B base inserted" -- the rule of the consensus vote.
+ *           Tiles with more than 250 B bases or more than 128 A bases take the diagonal-first path with the tile's
+ *           recorded diffs spread evenly along it.
+ *   trace': a trace point at every multiple of ts of the NEW A read (= B) strictly inside the alignment: the other read's
+ *           coordinate and the diffs at the moment the path first reaches that column, walking in the new A read's
+ *           direction (for complemented alignments that is the old path walked backwards).  diffs' = sum of the tiles'.
+ * Records come back in input order (the caller sorts them into LAsort order); out_trace needs sum(tlen') elements. */
+typedef struct { int x, a, c; } orc_cross;
+
+static int tile_path(const uint8_t *a, int n, const uint8_t *b, int m, int dt, int comp, int bp, int ts, int lb, int lo, int hi,
+                     orc_cross *cr, int *total)
+{
+    /* fills cr[] with the crossings of this tile in DECREASING x; returns their number */
+    int nc = 0;
+    if (m > 250 || n > 128) {
+        *total = dt;
+        const int q = n < m ? n : m;
+        for (int j = m; j >= 0; j--) {
+            const int x = bp + j;
+            if (x <= lo || x >= hi) continue;
+            int i;
+            if (!comp) { if (j == 0 || x % ts) continue; i = j <= q ? j : n; if (j == m && n > m) i = m; }
+            else { if (j == m || (lb - x) % ts) continue; i = j <= q ? j : n; if (j == m && n > m) i = n; }
+            const int from_start = (n + m) ? (int)((long long)dt * (i + j) / (n + m)) : 0;
+            cr[nc].x = x; cr[nc].a = i; cr[nc].c = comp ? dt - from_start : from_start; nc++;
+        }
+        return nc;
+    }
+    static __thread uint8_t D[128 + 1][256];
+    for (int j = 0; j <= m; j++) D[0][j] = (uint8_t)j;
+    for (int i = 1; i <= n; i++) {
+        D[i][0] = (uint8_t)i;
+        for (int j = 1; j <= m; j++) {
+            int d = D[i - 1][j - 1] + (a[i - 1] != b[j - 1]);
+            int u = D[i - 1][j] + 1, l = D[i][j - 1] + 1;
+            int v = d; if (u < v) v = u; if (l < v) v = l;
+            D[i][j] = (uint8_t)v;
+        }
+    }
+    *total = D[n][m];
+    int i = n, j = m, cend = 0;
+    /* comp: the first cell visited in a column; not comp: the last one (recorded when the walk leaves the column) */
+    for (;;) {
+        const int x = bp + j;
+        int dir;                                     /* 0 diagonal, 1 up (A base unmatched), 2 left (B base inserted), 3 done */
+        if (i == 0 && j == 0) dir = 3;
+        else if (i > 0 && j > 0 && D[i][j] == D[i - 1][j - 1] + (a[i - 1] != b[j - 1])) dir = 0;
+        else if (i > 0 && D[i][j] == D[i - 1][j] + 1) dir = 1;
+        else dir = 2;
+        if (!comp) {
+            if ((dir == 0 || dir == 2) && j > 0 && x % ts == 0 && x > lo && x < hi) { cr[nc].x = x; cr[nc].a = i; cr[nc].c = *total - cend; nc++; }
+        }
+        if (dir == 3) break;
+        if (dir == 0) { cend += (a[i - 1] != b[j - 1]); i--; j--; }
+        else if (dir == 1) { cend += 1; i--; }
+        else { cend += 1; j--; }
+        if (comp && (dir == 0 || dir == 2)) {        /* just entered column j (< m) */
+            const int xn = bp + j;
+            if ((lb - xn) % ts == 0 && xn > lo && xn < hi) { cr[nc].x = xn; cr[nc].a = i; cr[nc].c = cend; nc++; }
+        }
+    }
+    return nc;
+}
+
+void orc_transpose(const int64_t *aoff, const uint8_t *abases, const int64_t *boff, const uint8_t *bbases,
+                   const las_rec *la, int64_t nla, const int64_t *toff, const uint16_t *trace, int32_t ts,
+                   las_rec *out, int64_t *out_toff, uint16_t *out_trace)
+{
+    int64_t to = 0;
+    uint8_t *brc = NULL; int brc_cap = 0;
+    for (int64_t r = 0; r < nla; r++) {
+        const las_rec *x = &la[r];
+        const int LA = (int)(aoff[x->aread + 1] - aoff[x->aread]), LB = (int)(boff[x->bread + 1] - boff[x->bread]);
+        const uint8_t *A = abases + aoff[x->aread], *B = bbases + boff[x->bread];
+        const int comp = (int)(x->flags & 1u);
+        if (comp) {
+            if (LB > brc_cap) { brc = realloc(brc, LB + 1); brc_cap = LB; }
+            for (int i = 0; i < LB; i++) brc[i] = 3 - B[LB - 1 - i];
+            B = brc;
+        }
+        const int nt = x->tlen / 2;
+        /* all crossings of the record, tile after tile */
+        int cap = (x->bepos - x->bbpos) / ts + 4 + nt, ncr = 0;
+        orc_cross *cr = malloc(sizeof(orc_cross) * cap), *tmp = malloc(sizeof(orc_cross) * cap);
+        int *tcost = malloc(sizeof(int) * (nt + 1)), *tfirst = malloc(sizeof(int) * (nt + 2));
+        int ap = x->abpos, bp = x->bbpos;
+        for (int t = 0; t < nt; t++) {
+            const int aend = (t == nt - 1) ? x->aepos : (ap / ts + 1) * ts;
+            const int m = trace[toff[r] + 2 * t + 1], dt = trace[toff[r] + 2 * t];
+            tfirst[t] = ncr;
+            const int k = tile_path(A + ap, aend - ap, B + bp, m, dt, comp, bp, ts, LB, x->bbpos, x->bepos, tmp, &tcost[t]);
+            for (int q = 0; q < k; q++) { cr[ncr] = tmp[q]; cr[ncr].a += ap; ncr++; }     /* a: global A coordinate */
+            ap = aend; bp += m;
+        }
+        tfirst[nt] = ncr;
+        las_rec o = *x;
+        o.aread = x->bread; o.bread = x->aread;
+        out_toff[r] = to;
+        int total = 0; for (int t = 0; t < nt; t++) total += tcost[t];
+        int ntp = 0;
+        if (!comp) {
+            o.abpos = x->bbpos; o.aepos = x->bepos; o.bbpos = x->abpos; o.bepos = x->aepos;
+            int pa = x->abpos, pd = 0, base = 0;
+            for (int t = 0; t < nt; t++) {
+                for (int q = tfirst[t + 1] - 1; q >= tfirst[t]; q--) {           /* increasing x inside the tile */
+                    const int d = base + cr[q].c;
+                    out_trace[to++] = (uint16_t)(d - pd); out_trace[to++] = (uint16_t)(cr[q].a - pa); ntp++;
+                    pd = d; pa = cr[q].a;
+                }
+                base += tcost[t];
+            }
+            if (x->bepos > x->bbpos) { out_trace[to++] = (uint16_t)(total - pd); out_trace[to++] = (uint16_t)(x->aepos - pa); ntp++; }
+        } else {
+            o.abpos = LB - x->bepos; o.aepos = LB - x->bbpos; o.bbpos = LA - x->aepos; o.bepos = LA - x->abpos;
+            int pa = x->aepos, pd = 0, base = 0;
+            for (int t = nt - 1; t >= 0; t--) {
+                for (int q = tfirst[t]; q < tfirst[t + 1]; q++) {                /* decreasing x inside the tile */
+                    const int d = base + cr[q].c;
+                    out_trace[to++] = (uint16_t)(d - pd); out_trace[to++] = (uint16_t)(pa - cr[q].a); ntp++;
+                    pd = d; pa = cr[q].a;
+                }
+                base += tcost[t];
+            }
+            if (x->bepos > x->bbpos) { out_trace[to++] = (uint16_t)(total - pd); out_trace[to++] = (uint16_t)(pa - x->abpos); ntp++; }
+        }
+        o.diffs = total; o.tlen = 2 * ntp;
+        out[r] = o;
+        free(cr); free(tmp); free(tcost); free(tfirst);
+    }
+    free(brc);
+}

@@ -371,3 +371,32 @@ def test_chaining_of_oversized_groups_goes_through_the_host_restatement(tmp_path
         for f in ("aread", "bread", "abpos", "aepos", "bbpos", "bepos"):
             assert np.array_equal(las.rec[f], before[src][f]), f
     assert len(src) > 0
+
+
+def test_transposed_las_matches_oracle():
+    """dn_las_transpose (damapper -C's second file, dazzler.d:5931-5936) == oracle/pile_oracle.c orc_transpose: records,
+    mirrored coordinates, re-laid trace points; LAsort order of the new (read, contig) numbering; and the double
+    transposition returns to the original coordinates."""
+    from dentist_b200 import dazzler
+    from oracle import oracle
+    sc = synth.make_scaffolds(1, 150000, 171, n_repeats=1, repeat_copies=3)
+    ref, _ = synth.contigs_from(sc, synth.make_gaps(sc, 2, 172))
+    reads, _ = synth.simulate_reads(sc, 4, 8000, 2500, 0.13, 173)
+    ga, gb = dazzler.Block(ref.off, ref.bases), dazzler.Block(reads.off, reads.bases)
+    for ts in (100, 126):
+        las = dazzler.align(ga, gb, tspace=ts, minlen=500)
+        assert len(las) > 60 and (las.rec["flags"] & 1).any()
+        t = las.transpose(ga, gb)
+        orec, otoff, otr = oracle.transpose(ref.off, ref.bases, reads.off, reads.bases, las.rec, las.toff, las.trace, ts)
+        order = np.lexsort((orec["diffs"], orec["bepos"], orec["bbpos"], orec["aepos"], orec["abpos"], orec["flags"] & 1, orec["bread"], orec["aread"]))
+        assert len(t) == len(orec)
+        for f in ("aread", "bread", "abpos", "aepos", "bbpos", "bepos", "diffs", "tlen"):
+            assert np.array_equal(t.rec[f], orec[f][order]), f
+        assert np.array_equal(t.rec["flags"], orec["flags"][order] & 1)
+        for i, tr in zip(order, t.traces()):
+            assert np.array_equal(tr.reshape(-1), otr[otoff[i]:otoff[i] + orec["tlen"][i]])
+        back = t.transpose(gb, ga)
+        for f in ("aread", "bread", "abpos", "aepos", "bbpos", "bepos"):
+            assert np.array_equal(back.rec[f], las.rec[f]), f
+    empty = dazzler.align(ga, gb, tspace=100, minlen=10 ** 6).transpose(ga, gb)
+    assert len(empty) == 0

@@ -103,3 +103,33 @@ def test_qv_rule_on_hand_made_pile():
     assert q[qoff[1]:].tolist() == [50] * 12          # uncovered reads
     q2, _ = oracle.qv(rlen, rec, toff, np.array(traces, np.uint16), 100, 20)
     assert q2[:3].tolist() == [50, 50, 50]            # 4 LAs * 4 < cov 20 -> uncovered
+
+
+def test_transposed_las_keeps_the_data_model_invariants():
+    """orc_transpose (what damapper -C writes as Y.X.las, dazzler.d:5931-5936): every transposed record satisfies the LAS /
+    trace contract pinned from the reference (tile count from the span, sum of tile B bases == B span, sum of tile diffs ==
+    diffs: base.d:434-458, 196-219), coordinates mirror exactly, and transposing twice returns the original coordinates."""
+    from dentist_b200 import synth
+    sc = synth.make_scaffolds(1, 120000, 71, n_repeats=0)
+    ref, _ = synth.contigs_from(sc, synth.make_gaps(sc, 1, 72))
+    reads, _ = synth.simulate_reads(sc, 3, 7000, 2000, 0.13, 73)
+    la, tr, _ = oracle.align(ref.off, ref.bases, reads.off, reads.bases, tspace=100, minlen=500)
+    assert len(la) > 30 and (la["flags"] & 1).any() and not (la["flags"] & 1).all()
+    t, ttoff, ttr = oracle.transpose(ref.off, ref.bases, reads.off, reads.bases, la, la["toff"].astype(np.int64), tr, 100)
+    alen, blen = np.diff(ref.off), np.diff(reads.off)
+    for i in range(len(la)):
+        x, y = la[i], t[i]
+        assert (y["aread"], y["bread"], y["flags"] & 1) == (x["bread"], x["aread"], x["flags"] & 1)
+        if x["flags"] & 1:
+            assert (y["abpos"], y["aepos"]) == (blen[x["bread"]] - x["bepos"], blen[x["bread"]] - x["bbpos"])
+            assert (y["bbpos"], y["bepos"]) == (alen[x["aread"]] - x["aepos"], alen[x["aread"]] - x["abpos"])
+        else:
+            assert (y["abpos"], y["aepos"], y["bbpos"], y["bepos"]) == (x["bbpos"], x["bepos"], x["abpos"], x["aepos"])
+        tiles = ttr[ttoff[i]:ttoff[i] + y["tlen"]].reshape(-1, 2).astype(np.int64)
+        assert len(tiles) == -(-int(y["aepos"]) // 100) - int(y["abpos"]) // 100
+        assert tiles[:, 1].sum() == y["bepos"] - y["bbpos"] and tiles[:, 0].sum() == y["diffs"]
+        assert y["diffs"] <= x["diffs"]                              # per-tile optimal paths never cost more than the extension's path
+        assert (tiles[:, 1] >= 0).all() and (tiles[:, 0] >= 0).all() and tiles[:, 1].max() < 250
+    back, btoff, btr = oracle.transpose(reads.off, reads.bases, ref.off, ref.bases, t, ttoff, ttr, 100)
+    for f in ("aread", "bread", "abpos", "aepos", "bbpos", "bepos"):
+        assert np.array_equal(back[f], la[f]), f
