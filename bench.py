@@ -332,7 +332,7 @@ def main():
 
     import torch
     import torch.distributed as dist
-    from dentist_b200 import dazzler, sharding
+    from dentist_b200 import dazzler, sharding, _lib
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a CUDA device (no CPU fallback); use --impl reference for the CPU arm")
     torch.cuda.set_device(local_rank)
@@ -529,7 +529,11 @@ def main():
                           "read_block_bp_per_gpu": int(reads.total), "reads_per_gpu": int(reads.nreads), "params": PARAMS,
                           "l2": "per-step working set (tuple + hit arrays, >5 GB) far exceeds the 126 MB L2; no explicit flush",
                           "local_alignments_per_step": nla, "wall_ms_per_step": wall_ms_max / args.steps},
-               "e2e": {"value": e2e, "unit": "Gbp/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h)},
+               "e2e": {"value": e2e, "unit": "Gbp/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
+                       "path": "dn_align_host (pinned host .bps in, host LAS out)" if world == 1 else
+                               "dn_align_host_gather: per-rank segments gathered HBM to HBM (NCCL inside the library), placement merge, " +
+                               ("merged LAS downloaded in %d slices, one per rank / PCIe link, into a shared page-locked host segment" % world
+                                if _lib.lib().dn_comm_shared_segment_bytes() > 0 else "merged LAS downloaded by rank 0")},
                "gpu_launches": int(launches),
                "clocks": summarize_clocks(clk),
                "roofline": {"kernel": "k_extend32 (O(ND) wave extension, 48% of device time)", "bound": "hbm", "achieved": ext_gbs, "peak": peak,

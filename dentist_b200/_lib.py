@@ -18,7 +18,7 @@ EXPORTS = [
     "dn_las_filter_error", "dn_las_filter_pileup", "dn_compute_qvs", "dn_compute_qvs_v", "dn_dust_block", "dn_block_mask_dust", "dn_block_index", "dn_mask_coverage", "dn_propagate_mask", "dn_dbdust", "dn_las_chain_mapper", "dn_las_chain", "dn_las_merge_device", "dn_block_crop", "dn_consensus_db", "dn_collect_filter", "dn_las_force_flat", "dn_reference_read_candidates", "dn_free", "dn_consensus", "dn_seq_free",
     "dn_process_pileups", "dn_pileup_params_default", "dn_insertion_free", "dn_pile_status_string", "dn_block_add_mask",
     "dn_comm_get_id", "dn_comm_init", "dn_comm_shutdown", "dn_comm_rank", "dn_comm_size", "dn_align_blocks_gather", "dn_align_host_gather",
-    "dn_comm_allgatherv", "dn_las_keep_best_chains", "dn_las_transpose",
+    "dn_comm_allgatherv", "dn_las_keep_best_chains", "dn_las_transpose", "dn_comm_shared_segment_bytes",
 ]
 
 
@@ -135,6 +135,7 @@ def lib():
         L.dn_pile_status_string.restype = C.c_char_p
         L.dn_block_add_mask.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
         L.dn_comm_get_id.argtypes = [C.c_void_p]
+        L.dn_comm_shared_segment_bytes.restype = C.c_int64
         L.dn_comm_init.argtypes = [C.c_int32, C.c_int32, C.c_void_p]
         L.dn_align_blocks_gather.argtypes = [C.c_void_p, C.c_void_p, C.POINTER(AlignParams), C.c_int64, C.c_int32, C.POINTER(LasBuf)]
         L.dn_align_host_gather.argtypes = [C.POINTER(BlockDesc), C.POINTER(BlockDesc), C.POINTER(AlignParams), C.c_int64, C.c_int32, C.POINTER(LasBuf)]

@@ -377,6 +377,7 @@ int dn_comm_shutdown(void) {
     g_rank = 0; g_world = 1;
     return DN_OK;
 }
+int64_t dn_comm_shared_segment_bytes(void) { return g_shm.ok ? (int64_t)g_shm.size : 0; }
 int32_t dn_comm_rank(void) { return g_rank; }
 int32_t dn_comm_size(void) { return g_world; }
 

@@ -160,6 +160,11 @@ int dn_las_merge_device(const void *d_rec, int64_t nrec, const void *d_trace, in
 int dn_comm_get_id(uint8_t *id);
 int dn_comm_init(int32_t rank, int32_t world, const uint8_t *id);
 int dn_comm_shutdown(void);
+/* > 0: the ranks of this node share a page-locked host segment of that many bytes and a gather with root >= 0 downloads
+ * the merged LAS in slices, one per rank and PCIe link (the root's result then points into the segment and stays valid
+ * until the second following gather call); 0: the root downloads everything itself.  DN_SHM_MB sizes one half (default 384),
+ * DN_NO_SHM=1 disables it. */
+int64_t dn_comm_shared_segment_bytes(void);
 int32_t dn_comm_rank(void);
 int32_t dn_comm_size(void);
 /* dn_align_blocks on every rank's own read block `b` (B read numbers local to the block) + gather + merge:
