@@ -15,6 +15,7 @@
 #include <sys/stat.h>
 #include <unistd.h>
 #include <atomic>
+#include <chrono>
 #include <new>
 #include <string.h>
 #include <stdlib.h>
@@ -276,7 +277,14 @@ void gather_and_merge(DevLas &mine, HostLas &h, int64_t bread_offset, int root, 
         DN_LAUNCH(k_shift_bread, (unsigned)((mine.nrec + 255) / 256), 256, 0, s, mine.rec, mine.nrec, (int32_t)bread_offset);
     const bool want_shard = root >= 0 && g_world > 1 && g_shm.ok;
     std::vector<int64_t> seg_beg, tr_beg; DBuf<dn_las_record> allrec; DBuf<uint16_t> alltr;
+    const bool trace = getenv("DN_TRACE") != nullptr && g_rank == 0;      // diagnostics only (adds stream syncs)
+    auto now = [] { return std::chrono::steady_clock::now(); };
+    auto ms = [](std::chrono::steady_clock::time_point a, std::chrono::steady_clock::time_point b) { return std::chrono::duration<double, std::milli>(b - a).count(); };
+    if (trace) cudaStreamSynchronize(s);
+    const auto ts0 = now();
     gather_segments(mine, want_shard ? -1 : root, seg_beg, tr_beg, allrec, alltr, s);
+    if (trace) cudaStreamSynchronize(s);
+    const auto ts1 = now();
     const dn_align_stats st = h.stats;
     const int W = g_world;
     const int64_t n = seg_beg[W], nt = tr_beg[W];
@@ -287,6 +295,8 @@ void gather_and_merge(DevLas &mine, HostLas &h, int64_t bread_offset, int root, 
         uint8_t *dst = g_shm.base + SHM_HEADER + (size_t)hf * g_shm.half;
         MergedDev M;
         merge_segments_on_device(allrec.p, seg_beg.data(), W, alltr.p, nt, na_reads, M, s);
+        if (trace) cudaStreamSynchronize(s);
+        const auto ts2 = now();
         const int64_t r0 = n * g_rank / W, r1 = n * (g_rank + 1) / W, t0 = nt * g_rank / W, t1 = nt * (g_rank + 1) / W;
         if (r1 > r0) {
             DN_CUDA(cudaMemcpyAsync(dst + (size_t)r0 * sizeof(dn_las_record), M.rec + r0, sizeof(dn_las_record) * (size_t)(r1 - r0), cudaMemcpyDeviceToHost, s));
@@ -294,12 +304,15 @@ void gather_and_merge(DevLas &mine, HostLas &h, int64_t bread_offset, int root, 
         }
         if (t1 > t0) DN_CUDA(cudaMemcpyAsync(dst + o_tr + (size_t)t0 * 2, M.trace + t0, 2 * (size_t)(t1 - t0), cudaMemcpyDeviceToHost, s));
         DN_CUDA(cudaStreamSynchronize(s));
+        const auto ts3 = now();
         ShmHeader *H = (ShmHeader *)g_shm.base;
         H->arrivals[hf].fetch_add(1, std::memory_order_release);
         g_shm.calls[hf]++;
         if (g_rank == root) {
             const unsigned long long want = g_shm.calls[hf] * (unsigned long long)W;
             while (H->arrivals[hf].load(std::memory_order_acquire) < want) { /* the other ranks' slices land within microseconds of ours */ }
+            if (trace) fprintf(stderr, "[dn trace] gather: exchange %.3f ms (%lld records, %lld trace values from %d ranks), placement merge %.3f ms, "
+                               "slice download %.3f ms, wait for the other slices %.3f ms\n", ms(ts0, ts1), (long long)n, (long long)nt, W, ms(ts1, ts2), ms(ts2, ts3), ms(ts3, now()));
             hcache_free(h.rec); hcache_free(h.toff); hcache_free(h.trace);
             h.rec = (dn_las_record *)dst; h.toff = (int64_t *)(dst + o_toff); h.trace = (uint16_t *)(dst + o_tr);
             h.nrec = n; h.ntrace = nt;

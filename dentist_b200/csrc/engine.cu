@@ -523,11 +523,20 @@ void align_blocks(const DevBlock &A, const DevBlock &B, const AlignParams &P, Ho
         FinalBits fb{bits_for((uint64_t)A.maxlen), bits_for((uint64_t)B.maxlen), bits_for((uint64_t)A.nreads), bits_for((uint64_t)B.nreads), B.nreads};
         DBuf<ulonglong2> it1(ncand), it2(ncand); DBuf<unsigned long long> ctr(3); ctr.zero(s);
         ulonglong2 *cur = it1.p, *oth = it2.p;
-        const int fbits[4] = {bits_for((uint64_t)A.maxlen + B.maxlen), 2 * fb.nb, 2 * fb.na + 1, fb.nra + fb.nrb + 1};
-        for (int f = 0; f < 4; f++) {
-            launch_final_setkey(all.p, drop.p, cur, ncand, f, fb, ctr.p, s);
-            ulonglong2 *res = radix_sort_rec16(cur, oth, ncand, 0, 0, fbits[f], s);
+        const int pbits = 1 + fb.nra + fb.nrb + 1 + fb.na;            // (dropped, aread, bread, comp, abpos) in one key
+        if (pbits <= 64 && !getenv("DN_FINAL_4SORTS")) {
+            // one stable sort on the packed leading fields + a fix-up of the rare ties on the remaining ones: 6 passes instead of 16
+            launch_final_setkey(all.p, drop.p, cur, ncand, 4, fb, ctr.p, s);
+            ulonglong2 *res = radix_sort_rec16(cur, oth, ncand, 0, 0, pbits, s);
             if (res != cur) { oth = cur; cur = res; }
+            launch_final_fixup(all.p, cur, ncand, s);
+        } else {
+            const int fbits[4] = {bits_for((uint64_t)A.maxlen + B.maxlen), 2 * fb.nb, 2 * fb.na + 1, fb.nra + fb.nrb + 1};
+            for (int f = 0; f < 4; f++) {
+                launch_final_setkey(all.p, drop.p, cur, ncand, f, fb, ctr.p, s);
+                ulonglong2 *res = radix_sort_rec16(cur, oth, ncand, 0, 0, fbits[f], s);
+                if (res != cur) { oth = cur; cur = res; }
+            }
         }
         // records and traces are laid out for all ncand items (the dropped duplicates sort to the end and get no record);
         // the buffers are sized by the bounds the host already knows, so the counters travel with the result: ONE drain

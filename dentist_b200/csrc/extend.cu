@@ -578,18 +578,49 @@ __global__ void __launch_bounds__(256) k_final_setkey(const Cand *__restrict__ c
                                                       unsigned long long *__restrict__ ndrop) {
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
-    const u64 idx = field == 0 ? (u64)i : items[i].y;
+    const u64 idx = (field == 0 || field == 4) ? (u64)i : items[i].y;      // fields 0 and 4 start a sort: items are not set yet
     const Cand x = c[idx];
     u64 key;
     if (field == 0) key = (u64)(u32)x.diffs;
     else if (field == 1) key = ((u64)(u32)x.bb << fb.nb) | (u32)x.be;
     else if (field == 2) key = ((u64)(x.bs >= fb.nb_reads ? 1 : 0) << (2 * fb.na)) | ((u64)(u32)x.ab << fb.na) | (u32)x.ae;
-    else {
+    else if (field == 3) {
         const u64 d = drop[idx] ? 1ull : 0ull;
         key = (d << (fb.nra + fb.nrb)) | ((u64)(u32)x.a << fb.nrb) | (u32)(x.bs >= fb.nb_reads ? x.bs - fb.nb_reads : x.bs);
         if (d) atomicAdd(ndrop, 1ull);
+    } else {
+        // field 4: the leading fields of the LAsort order in ONE key -- (dropped, aread, bread, comp, abpos); the few records
+        // that tie on it are put in order by k_final_fixup
+        const u64 d = drop[idx] ? 1ull : 0ull;
+        const u64 comp = x.bs >= fb.nb_reads ? 1ull : 0ull;
+        key = (d << (fb.nra + fb.nrb + 1 + fb.na)) | ((u64)(u32)x.a << (fb.nrb + 1 + fb.na)) |
+              ((u64)(u32)(comp ? x.bs - fb.nb_reads : x.bs) << (1 + fb.na)) | (comp << fb.na) | (u64)(u32)x.ab;
+        if (d) atomicAdd(ndrop, 1ull);
     }
     items[i] = make_ulonglong2(key, idx);
+}
+
+// runs of items with equal primary key (same aread, bread, comp, abpos: rare and tiny) ordered by the remaining LAsort
+// fields (aepos, bbpos, bepos, diffs) and the candidate index: one thread per run start, insertion sort in place
+__global__ void __launch_bounds__(256) k_final_fixup(const Cand *__restrict__ c, ulonglong2 *__restrict__ items, int n) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n || (i > 0 && items[i - 1].x == items[i].x)) return;
+    int j = i + 1;
+    while (j < n && items[j].x == items[i].x) j++;
+    if (j - i < 2) return;
+    auto less = [&](u64 p, u64 q) {
+        const Cand &x = c[p], &y = c[q];
+        if (x.ae != y.ae) return x.ae < y.ae;
+        if (x.bb != y.bb) return x.bb < y.bb;
+        if (x.be != y.be) return x.be < y.be;
+        if (x.diffs != y.diffs) return x.diffs < y.diffs;
+        return p < q;
+    };
+    for (int a = i + 1; a < j; a++) {
+        const ulonglong2 t = items[a]; int b = a;
+        while (b > i && less(t.y, items[b - 1].y)) { items[b] = items[b - 1]; b--; }
+        items[b] = t;
+    }
 }
 
 __global__ void __launch_bounds__(256) k_final_records(const Cand *__restrict__ c, const ulonglong2 *__restrict__ items, int ncand,
@@ -629,6 +660,9 @@ __global__ void __launch_bounds__(256) k_final_traces(const Cand *__restrict__ c
 void launch_final_setkey(const Cand *c, const uint8_t *drop, ulonglong2 *items, int n, int field, FinalBits fb,
                          unsigned long long *ndrop, cudaStream_t s) {
     DN_LAUNCH(k_final_setkey, (n + 255) / 256, 256, 0, s, c, drop, items, n, field, fb, ndrop);
+}
+void launch_final_fixup(const Cand *c, ulonglong2 *items, int n, cudaStream_t s) {
+    DN_LAUNCH(k_final_fixup, (n + 255) / 256, 256, 0, s, c, items, n);
 }
 void launch_final_records(const Cand *c, const ulonglong2 *items, int ncand, int nb_reads, dn_las_record *rec, u32 *tl, unsigned long long *ctr, cudaStream_t s) {
     DN_LAUNCH(k_final_records, (ncand + 255) / 256, 256, 0, s, c, items, ncand, nb_reads, rec, tl, ctr);

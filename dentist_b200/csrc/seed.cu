@@ -651,6 +651,10 @@ __global__ void __launch_bounds__(256) k_lookup_count_p(const u32 *__restrict__ 
     lookup_count_body(seq, maskbits, off, len, c2r, nwords, k, IdxP{ta, pb}, tbl, sh, tcap, kbits, kshift, G, wcnt, hitmask, wlist, nlist);
 }
 
+// Emit pass over the compact list of words with hits.  Like the count pass it deals the (word, position) units of a warp's 32
+// words out evenly over the lanes (ncu before: 8 live threads per warp -- one thread walked all hit positions of its word while
+// the lanes of hit-free positions idled), walks the index once per unit, and places the unit's hits behind those of the earlier
+// positions of the same word by a segmented warp scan (units of a word are consecutive), so a word's hits stay ordered by bpos.
 template <class IDX>
 __device__ __forceinline__ void lookup_emit_body(const u32 *__restrict__ seq, const u32 *__restrict__ maskbits,
                                                  const int64_t *__restrict__ off, const int32_t *__restrict__ len,
@@ -659,28 +663,82 @@ __device__ __forceinline__ void lookup_emit_body(const u32 *__restrict__ seq, co
                                                  const unsigned short *__restrict__ hitmask, const u32 *__restrict__ wcnt,
                                                  const int64_t *__restrict__ woff, int strand,
                                                  const JoinGeom &G, ulonglong2 *__restrict__ hits, const u32 *__restrict__ wlist) {
+    __shared__ u32 s_done[8][32];                         // hits of each lane's word already placed by earlier batches
+    const u32 FULL = 0xffffffffu;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int64_t li = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (li >= nwords) return;                             // nwords = length of the list of words with hits
-    const int64_t wi = wlist[li];
-    const WordKmers w = load_word<IDX::wide>(seq, maskbits, off, len, c2r, wi);
+    const bool inrange = li < nwords;                     // nwords = length of the list of words with hits
     const u64 kmask = (1ull << (2 * k)) - 1ull;
-    const u64 bs = (u64)strand * G.nb_reads + w.r;
-    int64_t o = __ldcs((const long long *)woff + wi);
-    u32 present = hitmask[wi];                        // from the count pass: no filter probes, no fruitless lookups
-    while (present) {                                 // ascending jj: hits of a word stay ordered by bpos
-        const int jj = __ffs(present) - 1; present &= present - 1;
-        const typename IDX::key_t km = kmer_at<IDX>(w, jj, kmask);
-        u32 s, c; a_range_fwd(ta, tbl, sh, km, tcap, s, c);
-        const int bpos = w.p0 + jj;
-        for (u32 x = 0; x < c; x++) {
-            int64_t ga = (int64_t)ta.pos(s + x);
-            int ar = read_of(G.a_c2r, G.a_off, ga);
-            int apos = (int)(ga - G.a_off[ar]);
-            if (!pair_ok(G, ar, w.r)) continue;
-            const u64 gd = (u64)(G.a_dbase[ar] + apos - bpos + G.maxlb);
-            __stcs(reinterpret_cast<ulonglong2 *>(hits + o), make_ulonglong2((bs << G.gdbits) | gd, (u64)(u32)apos | ((u64)(u32)bpos << 32)));
-            o++;
+    const bool restricted = G.self || G.a_group;
+    WordKmers w; w.v = 0; w.mwin = 0; w.w2 = 0; w.p0 = 0; w.L = 0; w.r = 0;
+    u32 present = 0; long long wo = 0;
+    if (inrange) {
+        const int64_t wi = wlist[li];
+        w = load_word<IDX::wide>(seq, maskbits, off, len, c2r, wi);
+        present = hitmask[wi];                            // from the count pass: no filter probes, no fruitless lookups
+        wo = __ldcs((const long long *)woff + wi);
+    }
+    s_done[warp][lane] = 0;
+    const int cnt = __popc(present);
+    int inc = cnt;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) { const int t = __shfl_up_sync(FULL, inc, o); if (lane >= o) inc += t; }
+    const int E = inc - cnt, T = __shfl_sync(FULL, inc, 31);
+    __syncwarp();
+    for (int base = 0; base < T; base += 32) {
+        const int q = base + lane;
+        int owner = 0;                                    // last lane whose exclusive prefix is <= q
+#pragma unroll
+        for (int step = 16; step >= 1; step >>= 1) {
+            const int mid = owner + step;
+            const int Em = __shfl_sync(FULL, E, mid & 31);
+            if (mid < 32 && Em <= q) owner = mid;
         }
+        const u32 pm = __shfl_sync(FULL, present, owner);
+        const int Eo = __shfl_sync(FULL, E, owner);
+        WordKmers o;
+        o.v = ((u64)__shfl_sync(FULL, (u32)(w.v >> 32), owner) << 32) | __shfl_sync(FULL, (u32)w.v, owner);
+        o.w2 = __shfl_sync(FULL, w.w2, owner);
+        o.r = __shfl_sync(FULL, w.r, owner);
+        o.p0 = __shfl_sync(FULL, w.p0, owner);
+        const long long owo = ((long long)__shfl_sync(FULL, (int)(wo >> 32), owner) << 32) | (u32)__shfl_sync(FULL, (int)(u32)wo, owner);
+        u32 s = 0, c = 0, add = 0; int jj = 0;
+        if (q < T) {
+            jj = __fns(pm, 0, q - Eo + 1);
+            const typename IDX::key_t km = kmer_at<IDX>(o, jj, kmask);
+            a_range_fwd(ta, tbl, sh, km, tcap, s, c);
+            add = c;
+            if (restricted) {
+                add = 0;
+                for (u32 x = 0; x < c; x++) add += pair_ok(G, read_of(G.a_c2r, G.a_off, (int64_t)ta.pos(s + x)), o.r) ? 1u : 0u;
+            }
+        }
+        // segmented exclusive scan of `add` over the units of one word
+        u32 sc = add;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) { const u32 t = __shfl_up_sync(FULL, sc, d); if (lane >= d) sc += t; }
+        const u32 excl = sc - add;
+        const int head_lane = Eo > base ? Eo - base : 0;  // first unit of this word inside the batch
+        const u32 head = __shfl_sync(FULL, excl, head_lane);
+        if (q < T) {
+            int64_t at = owo + s_done[warp][owner] + (excl - head);
+            const u64 bs = (u64)strand * G.nb_reads + o.r;
+            const int bpos = o.p0 + jj;
+            for (u32 x = 0; x < c; x++) {
+                const int64_t ga = (int64_t)ta.pos(s + x);
+                const int ar = read_of(G.a_c2r, G.a_off, ga);
+                if (!pair_ok(G, ar, o.r)) continue;
+                const int apos = (int)(ga - G.a_off[ar]);
+                const u64 gd = (u64)(G.a_dbase[ar] + apos - bpos + G.maxlb);
+                __stcs(reinterpret_cast<ulonglong2 *>(hits + at), make_ulonglong2((bs << G.gdbits) | gd, (u64)(u32)apos | ((u64)(u32)bpos << 32)));
+                at++;
+            }
+        }
+        __syncwarp();
+        // the last unit of a word inside this batch books the word's progress for the next batch
+        const int cnt_o = __popc(pm);
+        if (q < T && (lane == 31 || q == T - 1 || q == Eo + cnt_o - 1)) s_done[warp][owner] += sc - head;
+        __syncwarp();
     }
 }
 

@@ -108,6 +108,7 @@ void launch_final_setkey(const Cand *c, const uint8_t *drop, ulonglong2 *items, 
 // ncand items, of which the first ncand - ctr[0] are kept (ctr[0] = dropped duplicates, still on the device)
 void launch_final_records(const Cand *c, const ulonglong2 *items, int ncand, int nb_reads, dn_las_record *rec, u32 *tl, unsigned long long *ctr, cudaStream_t s);
 void launch_final_traces(const Cand *c, const ulonglong2 *items, int ncand, const unsigned long long *ctr, const int64_t *toff, FinalGeom G, uint16_t *out, cudaStream_t s);
+void launch_final_fixup(const Cand *c, ulonglong2 *items, int n, cudaStream_t s);
 void launch_task_strides(int nseeds, int64_t stride, int64_t *tile_off, cudaStream_t s);
 void launch_dedupe(const Cand *cands, int ncand, const int32_t *round_beg, int nrounds, uint8_t *drop, cudaStream_t s);
 

@@ -18,7 +18,13 @@ __global__ void __launch_bounds__(256) k_seg_offsets(const int64_t *__restrict__
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= 2 * nr) return;
     const int64_t H = *dH;
-    auto at = [&](int q) -> int64_t { if (q == 2 * nr) return H; const int st = q >= nr, r = q - st * nr; return woff[st * nwB + (b_off[r] >> 4)]; };
+    // a block that ends with empty reads has b_off[r] == padded total for them: their strand-1 segment starts at H, not past the array
+    auto at = [&](int q) -> int64_t {
+        if (q == 2 * nr) return H;
+        const int st = q >= nr, r = q - st * nr;
+        const int64_t x = (int64_t)st * nwB + (b_off[r] >> 4);
+        return x >= 2 * nwB ? H : woff[x];
+    };
     const int64_t b = at(i);
     const int64_t len = at(i + 1) - b;
     seg_beg[i] = b; seg_len[i] = (int32_t)len;
