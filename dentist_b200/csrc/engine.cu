@@ -483,8 +483,8 @@ void align_blocks(const DevBlock &A, const DevBlock &B, const AlignParams &P, Ho
         exclusive_scan_u32_to_i64(ntl.p, toff.p, nseeds, dtotal.p, s);
         DBuf<Cand> rc((size_t)nseeds + 1); DBuf<uint16_t> rtr((size_t)2 * ntile_cap + 2);
         launch_write_traces(seeds.p, nseeds, EG, tile_off.p, tiles.p, outs.p, cand_all.p, valid.p, vidx.p, toff.p, rc.p, rtr.p, s);
-        DBuf<int32_t> keep(n), kidx(n);
-        launch_retire((const ulonglong2 *)hs, n, consumed.p, rc.p, dtot32.p, SG, P.w, bflag.p, bidx.p, hot.p, keep.p, s);
+        DBuf<int32_t> keep(n), kidx(n); DBuf<int2> crange((size_t)nbands + 1);
+        launch_retire((const ulonglong2 *)hs, n, consumed.p, rc.p, dtot32.p, SG, P.w, bflag.p, bidx.p, hot.p, bfirst.p, nbands, crange.p, keep.p, s);
         exclusive_scan_i32(keep.p, kidx.p, n, dtot32.p + 1, s);
         int32_t two2[2]; int64_t ntr = 0;
         DN_CUDA(cudaMemcpyAsync(two2, dtot32.p, 8, cudaMemcpyDeviceToHost, s));

@@ -510,32 +510,49 @@ __device__ __forceinline__ int group_lower(const Cand *__restrict__ c, int lo, i
     return lo;
 }
 
+// The kept alignments of a hit's (bread, strand, aread) group, looked up ONCE per hot band (all hits of a band share the group)
+// instead of once per hit: crange[band] = [first, last) candidate of the group in rc (empty: the group kept nothing this round).
+__global__ void __launch_bounds__(256) k_band_candidates(const ulonglong2 *__restrict__ hits, const int32_t *__restrict__ bfirst,
+                                                         const uint8_t *__restrict__ hot, int32_t nbands, const Cand *__restrict__ rc,
+                                                         const int32_t *__restrict__ d_nrc, SeedGeom G, int2 *__restrict__ crange) {
+    const int q = blockIdx.x * blockDim.x + threadIdx.x;
+    if (q >= nbands) return;
+    if (!hot[q]) { crange[q] = make_int2(0, 0); return; }
+    const int nrc = *d_nrc;
+    const ulonglong2 h = hits[bfirst[q]];
+    const u64 gd = h.x & ((1ull << G.gdbits) - 1ull);
+    const int bs = (int)(h.x >> G.gdbits);
+    int lo = 0, hi = G.na;
+    while (hi - lo > 1) { int mid = (lo + hi) >> 1; if ((u64)G.a_dbase[mid] <= gd) lo = mid; else hi = mid; }
+    const u64 key = gkey(bs, lo);
+    int x = group_lower(rc, 0, nrc, key), e = x;
+    while (e < nrc && gkey(rc[e].bs, rc[e].a) == key) e++;
+    crange[q] = make_int2(x, e);
+}
+
 __global__ void __launch_bounds__(256) k_retire(const ulonglong2 *__restrict__ hits, int64_t n, const uint8_t *__restrict__ consumed,
-                                                const Cand *__restrict__ rc, const int32_t *__restrict__ d_nrc, SeedGeom G, int w,
+                                                const Cand *__restrict__ rc, const int2 *__restrict__ crange, int w,
                                                 const int32_t *__restrict__ bflag, const int32_t *__restrict__ bidx,
                                                 const uint8_t *__restrict__ hot, int32_t *__restrict__ keep) {
     int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
-    const int nrc = *d_nrc;                              // alignments kept this round: counted on the device, never seen by the host before
     int kp = consumed[i] ? 0 : 1;
     // a hit in a cold band can never become part of a hot band later (scores only shrink): drop it for good.
     // Pure optimisation -- the later rounds see exactly the clusters they would have seen anyway.
-    if (kp && !hot[bflag[i] ? bidx[i] : bidx[i] - 1]) kp = 0;
+    const int band = bflag[i] ? bidx[i] : bidx[i] - 1;
+    if (kp && !hot[band]) kp = 0;
     if (kp) {
-        ulonglong2 h = hits[i];
-        u64 gd = h.x & ((1ull << G.gdbits) - 1ull);
-        int bs = (int)(h.x >> G.gdbits);
-        int lo = 0, hi = G.na;
-        while (hi - lo > 1) { int mid = (lo + hi) >> 1; if ((u64)G.a_dbase[mid] <= gd) lo = mid; else hi = mid; }
-        const int a = lo, apos = (int)(u32)h.y, bpos = (int)(h.y >> 32), diag = apos - bpos;
-        const u64 key = gkey(bs, a);
-        int x = group_lower(rc, 0, nrc, key);
+        const int2 cr = crange[band];
         // the rounds are counted per (bread, strand, aread) group (spec item 7): a group that kept no alignment in this
         // round is finished, whatever the other groups of the block do -- all its hits go
-        if (x >= nrc || gkey(rc[x].bs, rc[x].a) != key) kp = 0;
-        for (; kp && x < nrc && gkey(rc[x].bs, rc[x].a) == key; x++) {
-            const Cand c = rc[x];
-            if (apos >= c.ab && apos <= c.ae && diag >= c.dmin - (1 << w) && diag <= c.dmax + (1 << w)) { kp = 0; break; }
+        if (cr.x >= cr.y) kp = 0;
+        else {
+            const ulonglong2 h = hits[i];
+            const int apos = (int)(u32)h.y, bpos = (int)(h.y >> 32), diag = apos - bpos;
+            for (int x = cr.x; x < cr.y; x++) {
+                const Cand c = rc[x];
+                if (apos >= c.ab && apos <= c.ae && diag >= c.dmin - (1 << w) && diag <= c.dmax + (1 << w)) { kp = 0; break; }
+            }
         }
     }
     keep[i] = kp;
@@ -703,8 +720,10 @@ void launch_write_traces(const Seed *seeds, int nseeds, ExtGeom G, const int64_t
               toff, cand_out, trace);
 }
 void launch_retire(const ulonglong2 *hits, int64_t n, const uint8_t *consumed, const Cand *rc, const int32_t *d_nrc, SeedGeom G, int w,
-                   const int32_t *bflag, const int32_t *bidx, const uint8_t *hot, int32_t *keep, cudaStream_t s) {
-    DN_LAUNCH(k_retire, (unsigned)((n + 255) / 256), 256, 0, s, hits, n, consumed, rc, d_nrc, G, w, bflag, bidx, hot, keep);
+                   const int32_t *bflag, const int32_t *bidx, const uint8_t *hot, const int32_t *bfirst, int32_t nbands, int2 *crange,
+                   int32_t *keep, cudaStream_t s) {
+    DN_LAUNCH(k_band_candidates, (unsigned)((nbands + 255) / 256), 256, 0, s, hits, bfirst, hot, nbands, rc, d_nrc, G, crange);
+    DN_LAUNCH(k_retire, (unsigned)((n + 255) / 256), 256, 0, s, hits, n, consumed, rc, (const int2 *)crange, w, bflag, bidx, hot, keep);
 }
 void launch_compact_hits(const ulonglong2 *hits, int64_t n, const int32_t *keep, const int32_t *kidx, ulonglong2 *out, cudaStream_t s) {
     DN_LAUNCH(k_compact_hits, (unsigned)((n + 255) / 256), 256, 0, s, hits, n, keep, kidx, out);

@@ -6,6 +6,7 @@
 // [digit][cta] table, (3) stable scatter.  Grid = 4 CTAs per SM, each CTA walks its range in tiles.
 // Algorithmic HBM traffic per pass: 2 reads + 1 write of the array.
 #include "common.cuh"
+#include <stdlib.h>
 
 namespace dn {
 namespace {
@@ -154,7 +155,8 @@ template <typename Item, int FIELD>
 Item *radix_sort_impl(Item *a, Item *b, size_t n, int bit_lo, int bit_hi, cudaStream_t s) {
     if (n == 0 || bit_hi <= bit_lo) return a;
     if (n >= (1ull << 32)) throw Error("radix sort: more than 2^32 items");
-    int G = sm_count() * 4;
+    static const int per_sm = getenv("DN_RADIX_CTAS") ? atoi(getenv("DN_RADIX_CTAS")) : 4;
+    int G = sm_count() * (per_sm > 0 ? per_sm : 4);
     size_t need = (n + RS_TILE - 1) / RS_TILE;
     if ((size_t)G > need) G = (int)need;
     DBuf<u32> hist((size_t)256 * G);

@@ -99,7 +99,8 @@ void launch_write_traces(const Seed *seeds, int nseeds, ExtGeom G, const int64_t
                          const ExtOut *outs, const Cand *cand_all, const int32_t *valid, const int32_t *vidx,
                          const int64_t *toff, Cand *cand_out, uint16_t *trace, cudaStream_t s);
 void launch_retire(const ulonglong2 *hits, int64_t n, const uint8_t *consumed, const Cand *rc, const int32_t *d_nrc, SeedGeom G, int w,
-                   const int32_t *bflag, const int32_t *bidx, const uint8_t *hot, int32_t *keep, cudaStream_t s);
+                   const int32_t *bflag, const int32_t *bidx, const uint8_t *hot, const int32_t *bfirst, int32_t nbands, int2 *crange,
+                   int32_t *keep, cudaStream_t s);
 void launch_compact_hits(const ulonglong2 *hits, int64_t n, const int32_t *keep, const int32_t *kidx, ulonglong2 *out, cudaStream_t s);
 struct FinalBits { int na, nb, nra, nrb, nb_reads; };       // bits of: A coordinate, B coordinate, A read id, B read id
 struct FinalGeom { const uint16_t *round_trace[16]; int32_t round_beg[17]; int nrounds; };
