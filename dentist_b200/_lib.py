@@ -19,6 +19,7 @@ EXPORTS = [
     "dn_process_pileups", "dn_pileup_params_default", "dn_insertion_free", "dn_pile_status_string", "dn_block_add_mask",
     "dn_comm_get_id", "dn_comm_init", "dn_comm_shutdown", "dn_comm_rank", "dn_comm_size", "dn_align_blocks_gather", "dn_align_host_gather",
     "dn_comm_allgatherv", "dn_las_keep_best_chains", "dn_las_transpose", "dn_comm_shared_segment_bytes",
+    "dn_compute_qvs_db", "dn_read_qvs_db",
 ]
 
 
@@ -120,6 +121,8 @@ def lib():
         L.dn_las_force_flat.argtypes = [C.POINTER(LasBuf)]
         L.dn_reference_read_candidates.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_double, C.c_void_p, C.c_void_p]
         L.dn_dbdust.argtypes = [C.c_char_p, C.POINTER(C.c_char_p), C.c_int]
+        L.dn_compute_qvs_db.argtypes = [C.c_char_p, C.c_char_p, C.c_uint32]
+        L.dn_read_qvs_db.argtypes = [C.c_char_p, C.c_void_p, C.c_void_p, C.c_void_p]
         L.dn_dust_block.argtypes = [C.c_void_p, C.c_int32, C.c_double, C.c_int32, C.c_void_p, C.c_void_p]
         L.dn_mask_coverage.argtypes = [C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p, C.c_int32, C.c_double, C.c_double, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p]
         L.dn_propagate_mask.argtypes = [C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p]

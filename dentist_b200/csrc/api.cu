@@ -389,6 +389,49 @@ int dn_consensus_db(const char *db, const char *las, uint32_t read_id_1based, co
     });
 }
 
+// computeQVs(dbFile, lasFile, coverage)  dazzler.d:3782-3792: `DAScover` + `DASqv -c<coverage>` on files.  Writes the `qual`
+// track of `db`; DENTIST reads it back per read through `DBdump -r -i` (package.d:520-523) -- dn_read_qvs_db is that read.
+int dn_compute_qvs_db(const char *db, const char *las, uint32_t coverage) {
+    if (!db || !las) return fail(DN_ERR_INVALID, "null argument");
+    return guarded([&]() -> int {
+        HostDb D; std::string err;
+        if (!read_dazz_db(db, {}, D, err)) return fail(DN_ERR_IO, err);
+        dn_las_buf L; memset(&L, 0, sizeof L);
+        if (int rc = dn_las_read(las, &L)) return rc;
+        int64_t cov = coverage;
+        if (cov == 0) {
+            // no coverage given: DAScover's estimate stands in as the mean depth of the alignments over the DB (>= 1);
+            // DENTIST always passes a positive coverage (package.d:498-503)
+            int64_t span = 0, tot = 0;
+            for (int64_t i = 0; i < L.nrec; i++) span += L.rec[i].aepos - L.rec[i].abpos;
+            for (int32_t l : D.rlen) tot += l;
+            cov = tot > 0 ? span / tot : 0; if (cov < 1) cov = 1;
+        }
+        uint8_t *qv = nullptr; int64_t *qoff = nullptr;
+        int rc = dn_compute_qvs(D.rlen.data(), (int32_t)D.rlen.size(), &L, (int32_t)cov, &qv, &qoff);
+        dn_las_free(&L);
+        if (rc) return rc;
+        const bool ok = write_byte_track(db, "qual", qv, qoff, (int32_t)D.rlen.size(), err);
+        hcache_free(qv); hcache_free(qoff);
+        return ok ? DN_OK : fail(DN_ERR_IO, err);
+    });
+}
+
+int dn_read_qvs_db(const char *db, uint8_t **qv, int64_t **qoff, int32_t *nreads) {
+    if (!db || !qv || !qoff || !nreads) return fail(DN_ERR_INVALID, "null argument");
+    return guarded([&]() -> int {
+        std::vector<int64_t> off; std::vector<uint8_t> data; std::string err;
+        if (!read_byte_track(db, "qual", off, data, err)) return fail(DN_ERR_IO, err);
+        const int32_t n = (int32_t)off.size() - 1;
+        int64_t *ho = (int64_t *)hcache_alloc(sizeof(int64_t) * ((size_t)n + 1));
+        uint8_t *hq = (uint8_t *)hcache_alloc((size_t)off[n] + 1);
+        memcpy(ho, off.data(), sizeof(int64_t) * ((size_t)n + 1));
+        if (off[n]) memcpy(hq, data.data(), (size_t)off[n]);
+        *qv = hq; *qoff = ho; *nreads = n;
+        return DN_OK;
+    });
+}
+
 int dn_dalign(const char *dbA, const char *dbB, const char *const *opts, int nopts, const char *outdir) {
     return align_files(dbA, dbB, opts, nopts, outdir, false);
 }

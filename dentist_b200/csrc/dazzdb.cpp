@@ -202,4 +202,38 @@ bool write_mask_track(const std::string &dbpath, const std::string &track, const
     return true;
 }
 
+// Byte-valued per-read track (DASqv's `qual`, computeintrinsicqv's `inqual`): the same .anno/.data pair as an interval
+// track -- int32 nreads, int32 size (= 0: variable length), nreads + 1 int64 byte offsets -- with one QV byte per
+// trace-spacing tile in .data (what `DBdump -i` prints as letters, dazzler.d:2877-2898).
+bool write_byte_track(const std::string &dbpath, const std::string &track, const uint8_t *data, const int64_t *off, int32_t n, std::string &err) {
+    PathParts pp;
+    if (!split_path(dbpath, pp, err)) return false;
+    std::string base = pp.dir + "/." + pp.root + (pp.block > 0 ? "." + std::to_string(pp.block) : "") + "." + track;
+    FILE *fa = fopen((base + ".anno").c_str(), "wb"), *fd = fopen((base + ".data").c_str(), "wb");
+    if (!fa || !fd) { if (fa) fclose(fa); if (fd) fclose(fd); err = "cannot write track " + base; return false; }
+    int32_t sz = 0;
+    bool ok = fwrite(&n, 4, 1, fa) == 1 && fwrite(&sz, 4, 1, fa) == 1;
+    ok = ok && fwrite(off, 8, (size_t)n + 1, fa) == (size_t)n + 1;
+    if (ok && off[n] > 0) ok = fwrite(data, 1, (size_t)off[n], fd) == (size_t)off[n];
+    if (fclose(fa) != 0) ok = false;
+    if (fclose(fd) != 0) ok = false;
+    if (!ok) { err = "write failed for track " + base; return false; }
+    return true;
+}
+
+bool read_byte_track(const std::string &dbpath, const std::string &track, std::vector<int64_t> &off, std::vector<uint8_t> &data, std::string &err) {
+    PathParts pp;
+    if (!split_path(dbpath, pp, err)) return false;
+    std::string base = pp.dir + "/." + pp.root + (pp.block > 0 ? "." + std::to_string(pp.block) : "") + "." + track;
+    std::vector<uint8_t> anno;
+    if (!slurp(base + ".anno", anno) || anno.size() < 8) { err = "cannot read track " + base; return false; }
+    int32_t n, sz; memcpy(&n, anno.data(), 4); memcpy(&sz, anno.data() + 4, 4);
+    if (n < 0 || sz != 0 || anno.size() < 8 + ((size_t)n + 1) * 8) { err = "malformed track " + base; return false; }
+    off.resize((size_t)n + 1); memcpy(off.data(), anno.data() + 8, ((size_t)n + 1) * 8);
+    data.clear(); slurp(base + ".data", data);
+    for (int32_t r = 0; r < n; r++) if (off[r] < 0 || off[r] > off[r + 1]) { err = "malformed track " + base; return false; }
+    if ((int64_t)data.size() < off[n]) { err = "track data shorter than its index: " + base; return false; }
+    return true;
+}
+
 }  // namespace dn

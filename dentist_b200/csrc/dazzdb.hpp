@@ -32,5 +32,8 @@ bool read_dazz_db(const std::string &path, const std::vector<std::string> &mask_
 // writes <dir>/<name>.db|.dam + .<name>.idx + .<name>.bps (+ .hdr for .dam) with one block, all reads kept
 bool write_dazz_db(const std::string &path, const std::vector<std::vector<uint8_t>> &reads, std::string &err);
 bool write_mask_track(const std::string &dbpath, const std::string &track, const std::vector<std::vector<int32_t>> &intervals, std::string &err);
+// per-read byte tracks (`qual` of DASqv, `inqual` of computeintrinsicqv): one QV byte per trace-spacing tile
+bool write_byte_track(const std::string &dbpath, const std::string &track, const uint8_t *data, const int64_t *off, int32_t nreads, std::string &err);
+bool read_byte_track(const std::string &dbpath, const std::string &track, std::vector<int64_t> &off, std::vector<uint8_t> &data, std::string &err);
 
 }  // namespace dn

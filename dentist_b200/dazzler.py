@@ -384,6 +384,23 @@ def dbdustFile(dbFile, opts=()):
     _lib.check(_lib.lib().dn_dbdust(dbFile.encode(), arr, n))
 
 
+def computeQVsDb(dbFile, lasFile, coverage=0):
+    """dazzler.d:3782-3792 on files (`DAScover`, `DASqv -c`): writes the `qual` track of dbFile."""
+    _lib.check(_lib.lib().dn_compute_qvs_db(dbFile.encode(), lasFile.encode(), int(coverage)))
+
+
+def getIntrinsicQVs(dbFile):
+    """What getDbRecords(db, [readNumber, intrinsicQualityVector]) takes from `DBdump -r -i` (package.d:520-523,
+    dazzler.d:2877-2898): the `qual` track of dbFile as one QV array per read."""
+    L = _lib.lib()
+    qv = C.POINTER(C.c_uint8)(); qoff = C.POINTER(C.c_int64)(); n = C.c_int32(0)
+    _lib.check(L.dn_read_qvs_db(dbFile.encode(), C.byref(qv), C.byref(qoff), C.byref(n)))
+    o = np.ctypeslib.as_array(qoff, shape=(n.value + 1,)).copy()
+    q = np.ctypeslib.as_array(qv, shape=(max(int(o[-1]), 1),))[:int(o[-1])].copy()
+    L.dn_free(qv); L.dn_free(qoff)
+    return [q[int(o[r]):int(o[r + 1])] for r in range(n.value)]
+
+
 def getConsensusDb(dbFile, filteredLasFile, readId, opts=()):
     """dazzler.d:4213-4238 (file form): returns the path of the consensus .dam; raises "empty consensus"."""
     arr, n = _opts(list(opts))

@@ -237,18 +237,22 @@ class _HostBlock:
 
 
 def process_pileup_db(pile_ups, reads, ref, repeat_mask=None, min_reads_per_pileup=3, min_anchor_length=500,
-                      proper_alignment_allowance=100, max_alignment_error=0.3):
+                      proper_alignment_allowance=100, max_alignment_error=0.3, allow_single_reads=False):
     """PileUpsProcessor.run (package.d:100-160) for all pile-ups at once.
     pile_ups: binio.read_pileup_db() nesting; reads / ref: host blocks with .read(i) (0-based) -> base codes;
     repeat_mask: {contig id: [(begin, end), ...]}.  Returns (insertions sorted like `insertions.sort()`, skipped =
     {pile-up index: reason}).
-    Singular pile-ups (`--allow-single-reads`, package.d:297-305) are not built: the reference reaches
-    getInsertionAlignment with empty croppingPositions there (crop() is skipped), so its insertion alignment is a
-    default-initialised SeededAlignment -- gaps fail its own isValid check (package.d:747-751), extensions pass with an
-    empty overlap; nothing on the device path is involved."""
+    Singular pile-ups (`--allow-single-reads`, shouldProcessSingularPileUp package.d:376-379): the single read stands in for
+    the pile-up -- postConsensusAlignment = its own alignments (:294), insertion sequence = the read as stored
+    (getInsertionSequence :764-772), referenceRead = pileUp[0] (referenceReadIdx keeps its initial 0, :231, :587-590).  The
+    reference then builds the insertion alignment from croppingPositions, which crop() never filled on this path
+    (:704-747), i.e. from default-initialised SeededAlignments; what is returned here is the evidently intended value, the
+    read's own seeded alignments, checked with the same validity / type rule (:749-760).  No device work is involved."""
     repeat_mask = dict(repeat_mask or {})
-    skipped, crops, live = {}, {}, []
+    skipped, crops, live, singular = {}, {}, [], []
     for p, pile in enumerate(pile_ups):
+        if allow_single_reads and len(pile) == 1:                                   # shouldProcessSingularPileUp, package.d:292-305
+            singular.append(p); continue
         if len(pile) < min_reads_per_pileup:                                        # shouldSkipSmallPileUp, package.d:381-397
             skipped[p] = "minReadsPerPileUp"; continue
         contigs = {sa["contigA"][0]: sa["contigA"][1] for ra in pile for sa in ra}
@@ -260,8 +264,17 @@ def process_pileup_db(pile_ups, reads, ref, repeat_mask=None, min_reads_per_pile
         crops[p]["mask"] = adjust_repeat_mask(local_mask, contigs, crops[p]["ref_positions"], crops[p]["seeds"], min_anchor_length)
         crops[p]["contigs"] = contigs
         live.append(p)
+    insertions = []
+    for p in singular:
+        ra = pile_ups[p][0]
+        if not is_valid(ra):                                                         # insertionAlignment.isValid, package.d:749-753
+            skipped[p] = "consensus alignment is invalid"; continue
+        start, end = make_join(ra)
+        rid = ra[0]["contigB"][0]
+        insertions.append(dict(start=start, end=end, sequence=np.asarray(reads.read(rid - 1), np.uint8), contig_length=0,
+                               overlaps=[dict(sa) for sa in ra], read_ids=[rid], pile_up=p))
     if not live:
-        return [], skipped
+        return _sorted_insertions(insertions), skipped
     # ONE call for all pile-ups: pile alignment, filters, chaining, QVs, reference read, consensus (with retry) and the
     # consensus-vs-flanks alignment (-mdust -mrep) run grouped on the device (dn_process_pileups, package.d:303-341)
     piles_in = []
@@ -274,7 +287,6 @@ def process_pileup_db(pile_ups, reads, ref, repeat_mask=None, min_reads_per_pile
                                  proper_alignment_allowance=proper_alignment_allowance)
     if ref_block is not ref:
         ref_block.free()
-    insertions = []
     for g, p in enumerate(live):
         pile, crop, out = pile_ups[p], crops[p], res[g]
         try:
@@ -299,6 +311,11 @@ def process_pileup_db(pile_ups, reads, ref, repeat_mask=None, min_reads_per_pile
                                    read_ids=sorted(ra[0]["contigB"][0] for ra in pile), pile_up=p))      # makeInsertion :787-803
         except PileUpSkipped as e:
             skipped[p] = str(e)
+    return _sorted_insertions(insertions), skipped
+
+
+def _sorted_insertions(insertions):
+    """`insertions.sort()` (package.d:156): by start node, then end node."""
     part = {"pre": 0, "begin": 1, "end": 2, "post": 3}
     insertions.sort(key=lambda i: (i["start"][0], part[i["start"][1]], i["end"][0], part[i["end"][1]]))
-    return insertions, skipped
+    return insertions

@@ -354,6 +354,15 @@ int dn_dbdust(const char *db, const char *const *opts, int nopts);
  * <dir>/<db>-daccord-I<i>-<i>.dam (+ hidden .idx/.bps/.hdr) holding exactly one read and returns its path in
  * out_db.  DN_ERR_EMPTY ("empty consensus", :4232-4235) when nothing comes back. */
 int dn_consensus_db(const char *db, const char *las, uint32_t read_id_1based, const char *const *opts, int nopts, char *out_db, size_t cap);
+/* computeQVs(dbFile, lasFile, coverage)  dazzler.d:3782-3792 (`DAScover -v`, `DASqv -v -c<coverage>`, :6142-6156) on
+ * files: writes the `qual` track of `db` (.<db>.qual.anno/.data: int32 nreads, int32 0, nreads+1 int64 byte offsets; one QV
+ * byte in [0,50] per trace-spacing tile).  coverage == 0 stands for DAScover's own estimate (DENTIST never passes it,
+ * package.d:498-503). */
+int dn_compute_qvs_db(const char *db, const char *las, uint32_t coverage);
+/* the read DENTIST does afterwards -- getDbRecords(db, [readNumber, intrinsicQualityVector]) = `DBdump -r -i`,
+ * package.d:520-523, decoded by DbRecord.fromQVChar dazzler.d:2877-2898 -- without the text round trip: read r owns
+ * qv[qoff[r] .. qoff[r+1]).  Free both with dn_free. */
+int dn_read_qvs_db(const char *db, uint8_t **qv, int64_t **qoff, int32_t *nreads);
 /* getDamapping(refDb, queryDb, opts, outdir)  dazzler.d:3855-3866 / damapper() :6163-6170. */
 int dn_damap(const char *refDb, const char *queryDb, const char *const *opts, int nopts, const char *outdir);
 

@@ -138,6 +138,20 @@ inline std::vector<std::vector<uint8_t>> computeQVs(const std::vector<int32_t> &
     return out;
 }
 
+/// computeQVs(dbFile, lasFile, coverage)  dazzler.d:3782-3792, file form: writes the `qual` track of dbFile.
+inline void computeQVs(const std::string &dbFile, const std::string &lasFile, uint32_t coverage = 0) {
+    enforce(dn_compute_qvs_db(dbFile.c_str(), lasFile.c_str(), coverage));
+}
+/// the intrinsicQualityVector column of getDbRecords (`DBdump -r -i`, package.d:520-523) read from the `qual` track
+inline std::vector<std::vector<uint8_t>> getIntrinsicQVs(const std::string &dbFile) {
+    uint8_t *qv = nullptr; int64_t *off = nullptr; int32_t n = 0;
+    enforce(dn_read_qvs_db(dbFile.c_str(), &qv, &off, &n));
+    std::vector<std::vector<uint8_t>> out((size_t)n);
+    for (size_t r = 0; r < out.size(); r++) out[r].assign(qv + off[r], qv + off[r + 1]);
+    dn_free(qv); dn_free(off);
+    return out;
+}
+
 /// A mask as DENTIST's ReferenceRegion restricted to one DB: per contig a sorted list of disjoint [begin, end).
 using Mask = std::vector<std::vector<std::pair<int32_t, int32_t>>>;
 

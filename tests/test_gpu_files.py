@@ -196,3 +196,39 @@ def test_cli_damapper_equals_the_library_call(tmp_path):
     r = subprocess.run([os.path.join(root, "bin", "dn-damapper"), "-C", str(tmp_path / "missing.dam"), str(tmp_path / "reads.db")],
                        cwd=str(tmp_path / "cli"), capture_output=True, text=True)
     assert r.returncode == 1 and "missing" in r.stderr
+
+
+def test_computeQVs_file_form_writes_the_qual_track(tmp_path):
+    """computeQVs(db, las, coverage) dazzler.d:3782-3792 on files; the track is what package.d:520-523 reads back."""
+    import struct
+    from dentist_b200 import dazzler
+    from oracle import las, oracle
+    sc = synth.make_scaffolds(1, 20000, 71, n_repeats=0)
+    pile, _ = synth.simulate_reads(sc, 10, 6000, 1500, 0.13, 72)
+    db = str(tmp_path / "pile.db")
+    dbutil.write_db(db, pile)
+    out = dazzler.getDalignment(db, None, ["-T8", "-s126", "-l500", "-e0.7"], str(tmp_path))
+    ts, rec, traces = las.decode(open(out, "rb").read())
+    assert ts == 126 and len(rec) > 50
+    lens = np.diff(pile.off)
+    toff = np.concatenate([[0], np.cumsum([2 * len(t) for t in traces])]).astype(np.int64)
+    tr = np.concatenate([t.reshape(-1) for t in traces]).astype(np.uint16)
+    for cov in (4, pile.nreads):
+        dazzler.computeQVsDb(db, out, cov)
+        qvs = dazzler.getIntrinsicQVs(db)
+        oq, ooff = oracle.qv(lens, rec, toff[:-1], tr, 126, cov)
+        assert len(qvs) == pile.nreads
+        for r in range(pile.nreads):
+            assert len(qvs[r]) == -(-int(lens[r]) // 126)
+            assert np.array_equal(qvs[r], oq[ooff[r]:ooff[r + 1]]), r
+    # the files themselves: int32 nreads, int32 0, nreads + 1 int64 offsets | one byte per tile
+    anno = open(str(tmp_path / ".pile.qual.anno"), "rb").read()
+    data = open(str(tmp_path / ".pile.qual.data"), "rb").read()
+    n, sz = struct.unpack("<ii", anno[:8])
+    offs = struct.unpack("<%dq" % (n + 1), anno[8:])
+    assert n == pile.nreads and sz == 0 and offs[0] == 0 and offs[-1] == len(data) == sum(-(-int(l) // 126) for l in lens)
+    assert max(data) <= 50
+    # a missing track is an error, not an empty answer
+    dbutil.write_db(str(tmp_path / "other.db"), pile)
+    with pytest.raises(dazzler.DnError):
+        dazzler.getIntrinsicQVs(str(tmp_path / "other.db"))

@@ -174,3 +174,35 @@ def test_collect_read_alignments_follows_the_reference_kat():
     b = dict(id=1, contigA=(2, 20), contigB=(1, 60), flags=0, tpd=100, las=[dict(ab=0, ae=20, bb=5, be=25, diffs=0)])
     assert process.collect_read_alignments([a, b]) == ([], "alignments overlap on read")
     assert process.collect_read_alignments([]) == ([], "empty input")
+
+
+def test_singular_pile_ups_use_the_single_read():
+    """--allow-single-reads (shouldProcessSingularPileUp, package.d:292-305, 376-379): the read itself is the insertion."""
+    kat = json.load(open(os.path.join(HERE, "golden", "read_alignment_kat.json")))
+    piles, names = [], []
+    for name, chains in kat["cases"].items():
+        ra = [process.seeds_from(dict(id=c["id"], contigA=tuple(c["contigA"]), contigB=tuple(c["contigB"]), flags=c["flags"], tpd=100, las=c["las"]))[0]
+              for c in chains]
+        piles.append([ra]); names.append(name)
+    # an invalid read alignment (two alignments to ONE contig: neither extension nor gap, base.d:2190-2193)
+    bad = [dict(sa) for sa in next(ra for (ra,) in piles if len(ra) == 2)]
+    bad[1]["contigA"] = bad[0]["contigA"]
+    assert not process.is_valid(bad)
+    piles.append([bad])
+    reads = _Seqs({ra[0]["contigB"][0]: ra[0]["contigB"][1] for (ra,) in piles}, 5)
+    # without the flag every one-read pile-up falls to minReadsPerPileUp (shouldSkipSmallPileUp, :381-397)
+    ins, skipped = process.process_pileup_db(piles, reads, None, min_reads_per_pileup=3)
+    assert ins == [] and all(skipped[p] == "minReadsPerPileUp" for p in range(len(piles)))
+    ins, skipped = process.process_pileup_db(piles, reads, None, min_reads_per_pileup=3, allow_single_reads=True)
+    valid = [p for p, (ra,) in enumerate(piles) if process.is_valid(ra)]
+    assert 0 < len(valid) < len(piles)
+    assert sorted(i["pile_up"] for i in ins) == valid
+    assert all(skipped[p] == "consensus alignment is invalid" for p in range(len(piles)) if p not in valid)
+    for i in ins:
+        (ra,) = piles[i["pile_up"]]
+        assert (i["start"], i["end"]) == process.make_join(ra)
+        assert i["read_ids"] == [ra[0]["contigB"][0]] and len(i["overlaps"]) == len(ra)
+        assert np.array_equal(i["sequence"], reads.read(ra[0]["contigB"][0] - 1)) and len(i["sequence"]) == i["overlaps"][0]["contigB"][1]
+    part = {"pre": 0, "begin": 1, "end": 2, "post": 3}
+    keys = [(i["start"][0], part[i["start"][1]], i["end"][0], part[i["end"][1]]) for i in ins]
+    assert keys == sorted(keys)                                                       # insertions.sort(), package.d:156
