@@ -398,7 +398,7 @@ void align_blocks(const DevBlock &A, const DevBlock &B, const AlignParams &P, Ho
     // ---- rounds of band filter -> seeds -> extension -> retirement ----------------------------
     ExtGeom EG{A.fwd.p, A.rc.p, B.fwd.p, B.rc.p, A.off.p, B.off.p, A.len.p, B.len.p,
                P.tspace, P.cdiff, P.xdrop, P.wmax, P.poolmul, (u32)((1ull << 32) / (u32)P.tspace + 1), B.nreads,
-               (u32)A.fwd.n, (u32)B.fwd.n};
+               (u32)A.fwd.n, (u32)B.fwd.n, 0};
     {
         long long span = (long long)B.maxlen + B.maxlen / 2 + 64; if (A.maxlen < span) span = A.maxlen;
         if ((unsigned long long)span >= (1ull << 32) / (unsigned)P.tspace) throw Error("reads too long for the tile arithmetic");
@@ -411,26 +411,31 @@ void align_blocks(const DevBlock &A, const DevBlock &B, const AlignParams &P, Ho
     float ms_ext = 0;
     std::vector<std::pair<cudaEvent_t, cudaEvent_t>> ext_ev;      // brackets of the k_extend launches, read after the last sync
     int64_t ext_bytes = 0;
-    DBuf<int32_t> dtot32(2);
+    DBuf<int32_t> dtot32(2);          // 8-byte aligned (arena allocations are 512-byte aligned)
 
     for (int round = 0; round < P.rounds && n > 0; round++) {
-        DBuf<int32_t> cov(n), bflag(n), bidx(n), covsum(n);
-        DN_LAUNCH(k_hit_cover, (unsigned)((n + 255) / 256), 256, 0, s, (const ulonglong2 *)hs, n, k, P.w, cov.p, bflag.p);
-        exclusive_scan_i32(bflag.p, bidx.p, n, dtot32.p, s);
-        exclusive_scan_i32(cov.p, covsum.p, n, dtot32.p + 1, s);
+        DBuf<int32_t> bflag(n), bidx(n), covsum(n);
+        // the packed totals land as {total cover, bands} in dtot32[0..1] (little endian: low word first)
+        if (n < (1ll << 30)) launch_cover_scan((const ulonglong2 *)hs, n, k, P.w, bflag.p, bidx.p, covsum.p, (unsigned long long *)dtot32.p, s);
+        else {
+            DBuf<int32_t> cov(n);
+            DN_LAUNCH(k_hit_cover, (unsigned)((n + 255) / 256), 256, 0, s, (const ulonglong2 *)hs, n, k, P.w, cov.p, bflag.p);
+            exclusive_scan_i32(bflag.p, bidx.p, n, dtot32.p + 1, s);
+            exclusive_scan_i32(cov.p, covsum.p, n, dtot32.p, s);
+        }
         int32_t two[2];
         DN_CUDA(cudaMemcpyAsync(two, dtot32.p, 8, cudaMemcpyDeviceToHost, s)); DN_CUDA(cudaStreamSynchronize(s));
-        const int32_t nbands = two[0], total_cov = two[1];
+        const int32_t nbands = two[1];
         DBuf<int32_t> bfirst((size_t)nbands + 2), cstart(nbands), cidx(nbands);
         DBuf<u64> bkey((size_t)nbands + 1);
-        DBuf<uint8_t> pass(nbands), hot(nbands);
+        DBuf<uint8_t> hot(nbands);
         DN_LAUNCH(k_band_table, (unsigned)((n + 255) / 256), 256, 0, s, (const ulonglong2 *)hs, n, P.w, (const int32_t *)bflag.p,
                   (const int32_t *)bidx.p, bfirst.p, bkey.p, nbands);
-        DN_LAUNCH(k_band_pass, (nbands + 255) / 256, 256, 0, s, (const int32_t *)bfirst.p, (const u64 *)bkey.p,
-                  (const int32_t *)covsum.p, total_cov, n, nbands, P.h, pass.p);
-        DN_LAUNCH(k_band_hot, (nbands + 255) / 256, 256, 0, s, (const u64 *)bkey.p, (const uint8_t *)pass.p, nbands, hot.p, cstart.p);
-        exclusive_scan_i32(cstart.p, cidx.p, nbands, dtot32.p, s);
-        const int32_t nseeds = d2h_scalar(dtot32.p, s);
+        DN_LAUNCH(k_band_hot, (nbands + 255) / 256, 256, 0, s, (const int32_t *)bfirst.p, (const u64 *)bkey.p,
+                  (const int32_t *)covsum.p, (const int32_t *)dtot32.p, n, nbands, P.h, hot.p, cstart.p);
+        DBuf<int32_t> dseeds(1);
+        exclusive_scan_i32(cstart.p, cidx.p, nbands, dseeds.p, s);
+        const int32_t nseeds = d2h_scalar(dseeds.p, s);
         abytes += 16 * n + 8 * n + 3 * 12 * n + 16ll * nbands;
         tr.mark("band filter");
         if (nseeds == 0) break;
@@ -440,15 +445,17 @@ void align_blocks(const DevBlock &A, const DevBlock &B, const AlignParams &P, Ho
         out.stats.seeds += nseeds; out.stats.extensions += 2ll * nseeds;
 
         // ---- K5: extension
-        DBuf<int64_t> tile_off(2 * (size_t)nseeds);
+        DBuf<int64_t> tile_off;
         int64_t ntile_cap;
         {   // one tile capacity for every task when that stays affordable: no per-task caps, no scan, no host round trip
             long long sp = (long long)B.maxlen + B.maxlen / 2 + 64; if (A.maxlen < sp) sp = A.maxlen;
             const int64_t capmax = sp / P.tspace + 3;
             if (2ll * nseeds * capmax * (int64_t)sizeof(int2) <= (1ll << 30)) {
-                launch_task_strides(nseeds, capmax, tile_off.p, s);
+                EG.tile_stride = capmax;                              // task t owns tiles [t * capmax, (t + 1) * capmax)
                 ntile_cap = 2ll * nseeds * capmax;
             } else {
+                EG.tile_stride = 0;
+                tile_off.alloc(2 * (size_t)nseeds);
                 DBuf<u32> caps(2 * (size_t)nseeds);
                 launch_task_caps(seeds.p, nseeds, EG, caps.p, s);
                 exclusive_scan_u32_to_i64(caps.p, tile_off.p, 2 * (size_t)nseeds, dtotal.p, s);
@@ -464,11 +471,16 @@ void align_blocks(const DevBlock &A, const DevBlock &B, const AlignParams &P, Ho
           if (ctas > maxc) ctas = (int)maxc; }
         DBuf<int4> pool((size_t)ctas * wpc * pool_stride);
         DBuf<int> counter(1); counter.zero(s);
+        DBuf<int> order; 
+        if (!getenv("DN_EXT_NO_ORDER")) {              // tasks handed out longest-expected-first (no effect on any result)
+            DBuf<int> oscr(128); order.alloc(2 * (size_t)nseeds);
+            launch_task_order(seeds.p, nseeds, EG, oscr.p, order.p, s);
+        }
         tr.mark("seeds + ext setup");
         {   // events bracket exactly the k_extend launch; no host sync here
             cudaEvent_t ea, eb; cudaEventCreate(&ea); cudaEventCreate(&eb);
             cudaEventRecord(ea, s);
-            launch_extend(seeds.p, nseeds, EG, tile_off.p, tiles.p, outs.p, pool.p, pool_stride, ctas * wpc, counter.p, s);
+            launch_extend(seeds.p, nseeds, EG, tile_off.p, tiles.p, outs.p, pool.p, pool_stride, ctas * wpc, counter.p, order.p, s);
             cudaEventRecord(eb, s);
             ext_ev.emplace_back(ea, eb);
         }

@@ -120,7 +120,7 @@ __global__ void __launch_bounds__(256) k_task_caps(const Seed *__restrict__ seed
 __global__ void __launch_bounds__(EXT_WARPS * 32) k_extend(const Seed *__restrict__ seeds, int ntasks, ExtGeom G,
                                                            const int64_t *__restrict__ tile_off, int2 *__restrict__ tiles,
                                                            ExtOut *__restrict__ outs, int4 *__restrict__ pool_all,
-                                                           int64_t pool_stride, int *__restrict__ counter) {
+                                                           int64_t pool_stride, int *__restrict__ counter, const int *__restrict__ order) {
     __shared__ int sV[EXT_WARPS][2][64];      // furthest A offset per diagonal (two wave buffers)
     __shared__ int sT[EXT_WARPS][2][64];      // trace record index per diagonal
     __shared__ int sR[EXT_WARPS][2][64];      // next tile boundary (relative A offset) above the cell
@@ -131,7 +131,7 @@ __global__ void __launch_bounds__(EXT_WARPS * 32) k_extend(const Seed *__restric
 
     for (;;) {
         int task = 0;
-        if (lane == 0) task = atomicAdd(counter, 1);
+        if (lane == 0) { task = atomicAdd(counter, 1); if (task < ntasks && order) task = order[task]; }   // longest expected tasks first
         task = __shfl_sync(FULL, task, 0);
         if (task >= ntasks) break;
         const Seed sd = seeds[task >> 1];
@@ -255,7 +255,7 @@ __global__ void __launch_bounds__(EXT_WARPS * 32) k_extend(const Seed *__restric
         const int bestd = __shfl_sync(FULL, bd, wl), bestT = __shfl_sync(FULL, bT, wl);
         __syncwarp();
         if (lane == 0) {
-            int2 *tl = tiles + tile_off[task];
+            int2 *tl = tiles + (tile_off ? tile_off[task] : (int64_t)task * G.tile_stride);
             int n = NB(besti);
             int T = bestT, lastj = 0, lastd = 0;
             if (T >= 0) { int4 r = pool[T]; lastj = r.y; lastd = r.z; }
@@ -281,7 +281,7 @@ template <int MINB, bool STAGE>
 __global__ void __launch_bounds__(EXT_WARPS * 32, MINB) k_extend32(const Seed *__restrict__ seeds, int ntasks, ExtGeom G,
                                                              const int64_t *__restrict__ tile_off, int2 *__restrict__ tiles,
                                                              ExtOut *__restrict__ outs, int4 *__restrict__ pool_all,
-                                                             int64_t pool_stride, int *__restrict__ counter) {
+                                                             int64_t pool_stride, int *__restrict__ counter, const int *__restrict__ order) {
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const u32 FULL = 0xffffffffu;
     int4 *pool = pool_all + (int64_t)(blockIdx.x * EXT_WARPS + warp) * pool_stride;
@@ -295,7 +295,7 @@ __global__ void __launch_bounds__(EXT_WARPS * 32, MINB) k_extend32(const Seed *_
 
     for (;;) {
         int task = 0;
-        if (lane == 0) task = atomicAdd(counter, 1);
+        if (lane == 0) { task = atomicAdd(counter, 1); if (task < ntasks && order) task = order[task]; }   // longest expected tasks first
         task = __shfl_sync(FULL, task, 0);
         if (task >= ntasks) break;
         const Seed sd = seeds[task >> 1];
@@ -371,7 +371,14 @@ __global__ void __launch_bounds__(EXT_WARPS * 32, MINB) k_extend32(const Seed *_
                     }
                 }
             }
+            // the wave's collectives sit together in one convergent stretch (one divergence check instead of three); nothing is
+            // committed before the pool check below, so an exhausted pool still stops BEFORE this wave
+            const int S = i > NEGV ? 3 * (2 * i - k) - Cd : NEGS;
             const u32 cm = __ballot_sync(FULL, cn != 0);
+            const int waveS = __reduce_max_sync(FULL, S);
+            const int nbest = max(gbest, waveS);
+            const bool alive = S >= nbest - X && i != la && i - k != lb;      // S = NEGS (dead cell) fails the first test
+            const u32 m = __ballot_sync(FULL, alive);
             if (cm) {
                 if (!__any_sync(FULL, cn > 1)) {                // the usual case: at most one tile boundary per cell
                     const int need = __popc(cm);
@@ -393,13 +400,9 @@ __global__ void __launch_bounds__(EXT_WARPS * 32, MINB) k_extend32(const Seed *_
                     npool += need;
                 }
             }
-            const int S = i > NEGV ? 3 * (2 * i - k) - Cd : NEGS;
             if (S > bS) { bS = S; bi = i; bk = k; bd = d; bT = cT; }
-            const int waveS = __reduce_max_sync(FULL, S);
-            gbest = max(gbest, waveS);
-            const bool alive = S >= gbest - X && i != la && i - k != lb;      // S = NEGS (dead cell) fails the first test
+            gbest = nbest;
             V = alive ? i : NEGV; T = cT; R = cR;
-            const u32 m = __ballot_sync(FULL, alive);
             if (m == 0u) break;
             const u32 rot = __funnelshift_r(m, m, nlo & 31);    // bit j <-> diagonal nlo + j
             int alo = nlo + __ffs(rot) - 1, ahi = nlo + 31 - __clz(rot);
@@ -425,7 +428,7 @@ __global__ void __launch_bounds__(EXT_WARPS * 32, MINB) k_extend32(const Seed *_
         const int bestd = __shfl_sync(FULL, bd, wl), bestT = __shfl_sync(FULL, bT, wl);
         __syncwarp();
         if (lane == 0) {
-            int2 *tl = tiles + tile_off[task];
+            int2 *tl = tiles + (tile_off ? tile_off[task] : (int64_t)task * G.tile_stride);
             int n = NB(besti);
             int lastj = 0, lastd = 0;
             int4 curr = bestT >= 0 ? pool[bestT] : make_int4(-1, 0, 0, 0);
@@ -442,6 +445,48 @@ __global__ void __launch_bounds__(EXT_WARPS * 32, MINB) k_extend32(const Seed *_
         }
         __syncwarp();
     }
+}
+
+// ---------------------------------------------------------------- task order
+// The warps fetch tasks from one counter; a task is a chain of dependent waves that no second warp can help with, so the
+// kernel ends when the LAST-started long task ends.  Handing the tasks out longest-expected-first (counting sort into
+// half-octave classes of min(la, lb), largest class first) leaves only short tasks for the tail.  The order of the tasks
+// has no influence on any result: every task writes its own output slots.
+constexpr int ORD_CLASSES = 64;
+__device__ __forceinline__ int order_class(const Seed &sd, int dir, const ExtGeom &G) {
+    const Task t = make_task(sd, dir, G);
+    const u32 span = (u32)min(t.la, t.lb) | 1u;
+    const int msb = 31 - __clz(span);
+    const int c = 2 * msb + (msb > 0 ? (int)((span >> (msb - 1)) & 1u) : 0);
+    return ORD_CLASSES - 1 - c;                      // class 0 = longest
+}
+__global__ void __launch_bounds__(256) k_task_classes(const Seed *__restrict__ seeds, int ntasks, ExtGeom G, int *__restrict__ counts) {
+    __shared__ int h[ORD_CLASSES];
+    if (threadIdx.x < ORD_CLASSES) h[threadIdx.x] = 0;
+    __syncthreads();
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t < ntasks) atomicAdd(&h[order_class(seeds[t >> 1], t & 1, G)], 1);
+    __syncthreads();
+    if (threadIdx.x < ORD_CLASSES && h[threadIdx.x]) atomicAdd(&counts[threadIdx.x], h[threadIdx.x]);
+}
+__global__ void __launch_bounds__(256) k_task_order(const Seed *__restrict__ seeds, int ntasks, ExtGeom G, const int *__restrict__ counts,
+                                                    int *__restrict__ cursors, int *__restrict__ order) {
+    // a few classes hold almost every task: ranks are taken inside the CTA (shared-memory atomics), one global atomic per
+    // (CTA, class) reserves the CTA's slots
+    __shared__ int h[ORD_CLASSES], gbase[ORD_CLASSES];
+    if (threadIdx.x < ORD_CLASSES) h[threadIdx.x] = 0;
+    __syncthreads();
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    int c = 0, r = 0;
+    if (t < ntasks) { c = order_class(seeds[t >> 1], t & 1, G); r = atomicAdd(&h[c], 1); }
+    __syncthreads();
+    if (threadIdx.x < ORD_CLASSES && h[threadIdx.x]) {
+        int a = 0;
+        for (int q = 0; q < (int)threadIdx.x; q++) a += counts[q];
+        gbase[threadIdx.x] = a + atomicAdd(&cursors[threadIdx.x], h[threadIdx.x]);
+    }
+    __syncthreads();
+    if (t < ntasks) order[gbase[c] + r] = t;
 }
 
 // ---------------------------------------------------------------- candidate assembly
@@ -463,7 +508,7 @@ __global__ void __launch_bounds__(256) k_combine(const Seed *__restrict__ seeds,
     c.a = sd.a; c.bs = sd.bs; c.ab = ab; c.ae = ae; c.bb = bb; c.be = be; c.diffs = fo.d_end + ro.d_end; c.nt = nt; c.toff = 0;
     int dmin = ab - bb, dmax = dmin;
     if (ok) {
-        const int2 *ft = tiles + tile_off[2 * s], *rt = tiles + tile_off[2 * s + 1];
+        const int2 *ft = tiles + (tile_off ? tile_off[2 * s] : (int64_t)(2 * s) * G.tile_stride), *rt = tiles + (tile_off ? tile_off[2 * s + 1] : (int64_t)(2 * s + 1) * G.tile_stride);
         int apos = ab, bpos = bb, q = 0;
         auto step = [&](int bbases) {
             int aend = (q == nt - 1) ? ae : (apos / ts + 1) * ts;
@@ -491,7 +536,7 @@ __global__ void __launch_bounds__(256) k_write_traces(const Seed *__restrict__ s
     const Seed sd = seeds[s];
     const ExtOut fo = outs[2 * s], ro = outs[2 * s + 1];
     const bool merge = (sd.apos % G.ts != 0) && ro.ntiles > 0 && fo.ntiles > 0;
-    const int2 *ft = tiles + tile_off[2 * s], *rt = tiles + tile_off[2 * s + 1];
+    const int2 *ft = tiles + (tile_off ? tile_off[2 * s] : (int64_t)(2 * s) * G.tile_stride), *rt = tiles + (tile_off ? tile_off[2 * s + 1] : (int64_t)(2 * s + 1) * G.tile_stride);
     Cand c = cand[s];
     c.toff = 2 * toff[s];
     uint16_t *o = trace + c.toff;
@@ -687,27 +732,24 @@ void launch_final_records(const Cand *c, const ulonglong2 *items, int ncand, int
 void launch_final_traces(const Cand *c, const ulonglong2 *items, int ncand, const unsigned long long *ctr, const int64_t *toff, FinalGeom G, uint16_t *out, cudaStream_t s) {
     DN_LAUNCH(k_final_traces, (unsigned)(((int64_t)ncand * 32 + 255) / 256), 256, 0, s, c, items, ncand, ctr, toff, G, out);
 }
-namespace { __global__ void __launch_bounds__(256) k_task_strides(int ntasks, int64_t stride, int64_t *__restrict__ tile_off) {
-    int t = blockIdx.x * blockDim.x + threadIdx.x;
-    if (t < ntasks) tile_off[t] = (int64_t)t * stride;
-} }
-// every task gets the same tile capacity: no per-task caps, no scan, no host round trip for their sum
-void launch_task_strides(int nseeds, int64_t stride, int64_t *tile_off, cudaStream_t s) {
-    DN_LAUNCH(k_task_strides, (2 * nseeds + 255) / 256, 256, 0, s, 2 * nseeds, stride, tile_off);
-}
-
 void launch_task_caps(const Seed *seeds, int nseeds, ExtGeom G, u32 *caps, cudaStream_t s) {
     DN_LAUNCH(k_task_caps, (nseeds + 255) / 256, 256, 0, s, seeds, nseeds, G, caps);
 }
+// order: 2 * nseeds ints; scratch: 2 * 64 ints, zeroed here
+void launch_task_order(const Seed *seeds, int nseeds, ExtGeom G, int *scratch, int *order, cudaStream_t s) {
+    DN_CUDA(cudaMemsetAsync(scratch, 0, sizeof(int) * 2 * ORD_CLASSES, s));
+    DN_LAUNCH(k_task_classes, (2 * nseeds + 255) / 256, 256, 0, s, seeds, 2 * nseeds, G, scratch);
+    DN_LAUNCH(k_task_order, (2 * nseeds + 255) / 256, 256, 0, s, seeds, 2 * nseeds, G, (const int *)scratch, scratch + ORD_CLASSES, order);
+}
 void launch_extend(const Seed *seeds, int nseeds, ExtGeom G, const int64_t *tile_off, int2 *tiles, ExtOut *outs,
-                   int4 *pool, int64_t pool_stride, int nwarps_total, int *counter, cudaStream_t s) {
+                   int4 *pool, int64_t pool_stride, int nwarps_total, int *counter, const int *order, cudaStream_t s) {
     int ctas = nwarps_total / EXT_WARPS;
     // two register budgets of the same kernel: 5 resident CTAs per SM (48 registers) or 6 (40 registers, a few spilled words)
     static const bool stage = getenv("DN_EXT_TMA") != nullptr;
-    if (G.wmax <= 30 && stage) DN_LAUNCH((k_extend32<5, true>), ctas, EXT_WARPS * 32, 0, s, seeds, 2 * nseeds, G, tile_off, tiles, outs, pool, pool_stride, counter);
-    else if (G.wmax <= 30 && ext_ctas_per_sm() >= 6) DN_LAUNCH((k_extend32<6, false>), ctas, EXT_WARPS * 32, 0, s, seeds, 2 * nseeds, G, tile_off, tiles, outs, pool, pool_stride, counter);
-    else if (G.wmax <= 30) DN_LAUNCH((k_extend32<5, false>), ctas, EXT_WARPS * 32, 0, s, seeds, 2 * nseeds, G, tile_off, tiles, outs, pool, pool_stride, counter);
-    else DN_LAUNCH(k_extend, ctas, EXT_WARPS * 32, 0, s, seeds, 2 * nseeds, G, tile_off, tiles, outs, pool, pool_stride, counter);
+    if (G.wmax <= 30 && stage) DN_LAUNCH((k_extend32<5, true>), ctas, EXT_WARPS * 32, 0, s, seeds, 2 * nseeds, G, tile_off, tiles, outs, pool, pool_stride, counter, order);
+    else if (G.wmax <= 30 && ext_ctas_per_sm() >= 6) DN_LAUNCH((k_extend32<6, false>), ctas, EXT_WARPS * 32, 0, s, seeds, 2 * nseeds, G, tile_off, tiles, outs, pool, pool_stride, counter, order);
+    else if (G.wmax <= 30) DN_LAUNCH((k_extend32<5, false>), ctas, EXT_WARPS * 32, 0, s, seeds, 2 * nseeds, G, tile_off, tiles, outs, pool, pool_stride, counter, order);
+    else DN_LAUNCH(k_extend, ctas, EXT_WARPS * 32, 0, s, seeds, 2 * nseeds, G, tile_off, tiles, outs, pool, pool_stride, counter, order);
 }
 void launch_combine(const Seed *seeds, int nseeds, ExtGeom G, int minlen, const int64_t *tile_off, const int2 *tiles,
                     const ExtOut *outs, Cand *cand_all, int32_t *valid, u32 *ntl, cudaStream_t s) {

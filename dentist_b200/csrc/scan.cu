@@ -1,6 +1,7 @@
 // scan.cu -- hand-written exclusive prefix sums (three-phase: tile reduce, recursive scan of the
 // tile sums, tile scan + offset).  HBM-bound: reads the input twice, writes the output once.
 #include "common.cuh"
+#include "scan.cuh"
 #include <mutex>
 #include <stdlib.h>
 
@@ -92,34 +93,6 @@ int sm_count() {
 }
 
 namespace {
-constexpr int SCAN_THREADS = 256;
-constexpr int SCAN_ITEMS = 16;
-constexpr int SCAN_TILE = SCAN_THREADS * SCAN_ITEMS;
-
-template <typename Tout>
-__device__ __forceinline__ Tout block_exclusive(Tout v, Tout *total, Tout *smem /* 32 */) {
-    // exclusive scan of one value per thread across the block
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    Tout inc = v;
-#pragma unroll
-    for (int o = 1; o < 32; o <<= 1) { Tout t = __shfl_up_sync(0xffffffffu, inc, o); if (lane >= o) inc += t; }
-    if (lane == 31) smem[warp] = inc;
-    __syncthreads();
-    if (warp == 0) {
-        Tout w = lane < (SCAN_THREADS / 32) ? smem[lane] : Tout(0);
-        Tout winc = w;
-#pragma unroll
-        for (int o = 1; o < 32; o <<= 1) { Tout t = __shfl_up_sync(0xffffffffu, winc, o); if (lane >= o) winc += t; }
-        smem[lane] = winc - w;               // exclusive warp offsets
-        if (lane == 31) smem[32] = winc;     // block total
-    }
-    __syncthreads();
-    Tout res = smem[warp] + inc - v;
-    if (total) *total = smem[32];
-    __syncthreads();
-    return res;
-}
-
 template <typename Tin, typename Tout>
 __global__ void __launch_bounds__(SCAN_THREADS) k_scan_reduce(const Tin *__restrict__ in, Tout *__restrict__ sums, size_t n) {
     __shared__ Tout sm[33];
@@ -170,6 +143,8 @@ __global__ void __launch_bounds__(SCAN_THREADS) k_scan_apply(const Tin *__restri
 template <typename Tin, typename Tout>
 void scan_rec(const Tin *in, Tout *out, size_t n, Tout *d_total, cudaStream_t s) {
     if (n == 0) { if (d_total) DN_CUDA(cudaMemsetAsync(d_total, 0, sizeof(Tout), s)); return; }
+    static const bool three_phase = getenv("DN_SCAN3") != nullptr;
+    if (!three_phase) { scan_chained<Tout>(ScanPlain<Tin, Tout>{in, out}, n, d_total, s); return; }
     size_t nb = (n + SCAN_TILE - 1) / SCAN_TILE;
     if (nb == 1) {
         DN_LAUNCH((k_scan_apply<Tin, Tout>), 1, SCAN_THREADS, 0, s, in, out, (const Tout *)nullptr, n, d_total);

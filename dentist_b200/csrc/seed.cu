@@ -4,6 +4,7 @@
 // through dazzler.d:6131-6170.
 #include "engine.cuh"
 #include "seed.cuh"
+#include "scan.cuh"
 
 namespace dn {
 
@@ -799,32 +800,55 @@ __global__ void __launch_bounds__(256) k_band_table(const ulonglong2 *__restrict
     if (i == n - 1) bfirst[nbands] = (int32_t)n;
 }
 
-// per band: pass flag of the pair (q, q+1)
-__global__ void __launch_bounds__(256) k_band_pass(const int32_t *__restrict__ bfirst, const u64 *__restrict__ bkey,
-                                                   const int32_t *__restrict__ covsum, int32_t total_cov, int64_t nhits,
-                                                   int32_t nbands, int h, uint8_t *__restrict__ pass) {
+// pass(q) = covered bases of the band pair (q, q+1) >= h.
+// hot[q] = pass(q) || (adjacent(q-1,q) && pass(q-1)); cstart[q] = hot[q] && !(hot[q-1] && adjacent(q-1,q))
+__global__ void __launch_bounds__(256) k_band_hot(const int32_t *__restrict__ bfirst, const u64 *__restrict__ bkey,
+                                                  const int32_t *__restrict__ covsum, const int32_t *__restrict__ d_total_cov,
+                                                  int64_t nhits, int32_t nbands, int h, uint8_t *__restrict__ hot, int32_t *__restrict__ cstart) {
     int q = blockIdx.x * blockDim.x + threadIdx.x;
     if (q >= nbands) return;
+    const int32_t total_cov = *d_total_cov;
     auto cs = [&](int32_t i) { return i >= nhits ? total_cov : covsum[i]; };
-    int sc = cs(bfirst[q + 1]) - cs(bfirst[q]);
-    bool adj = (q + 1 < nbands) && (bkey[q + 1] == bkey[q] + 1);
-    if (adj) sc += cs(bfirst[q + 2]) - cs(bfirst[q + 1]);
-    pass[q] = sc >= h;
-}
-
-// hot[q] = pass[q] || (adjacent(q-1,q) && pass[q-1]); cstart[q] = hot[q] && !(hot[q-1] && adjacent(q-1,q))
-__global__ void __launch_bounds__(256) k_band_hot(const u64 *__restrict__ bkey, const uint8_t *__restrict__ pass, int32_t nbands,
-                                                  uint8_t *__restrict__ hot, int32_t *__restrict__ cstart) {
-    int q = blockIdx.x * blockDim.x + threadIdx.x;
-    if (q >= nbands) return;
+    auto pass = [&](int x) -> bool {
+        int sc = cs(bfirst[x + 1]) - cs(bfirst[x]);
+        const bool adj = (x + 1 < nbands) && (bkey[x + 1] == bkey[x] + 1);
+        if (adj) sc += cs(bfirst[x + 2]) - cs(bfirst[x + 1]);
+        return sc >= h;
+    };
     auto is_hot = [&](int x) -> bool {
-        if (pass[x]) return true;
-        return x > 0 && bkey[x - 1] + 1 == bkey[x] && pass[x - 1];
+        if (pass(x)) return true;
+        return x > 0 && bkey[x - 1] + 1 == bkey[x] && pass(x - 1);
     };
     bool hq = is_hot(q);
     hot[q] = hq;
     bool cont = hq && q > 0 && bkey[q - 1] + 1 == bkey[q] && is_hot(q - 1);
     cstart[q] = hq && !cont;
+}
+
+// k_hit_cover fused into the scan that consumes it: the load computes (band flag, covered bases) of hit i from hits i - 1
+// and i, the scan runs over the packed pair (flag << 32 | cover), the store splits the prefix into bidx / covsum.  The
+// per-hit cover never exists in memory.  Totals: packed (bands << 32 | cover) through *d_total.
+namespace {
+struct CoverScan {
+    const ulonglong2 *hits; int k, w; int32_t *bflag, *bidx, *covsum;
+    __device__ __forceinline__ unsigned long long load(size_t i) const {
+        const ulonglong2 h = hits[i];
+        int c = k, f = 1;
+        if (i > 0) {
+            const ulonglong2 p = hits[i - 1];
+            const int da = (int)(u32)h.y - (int)(u32)p.y;
+            if (p.x == h.x && da < k) c = da;
+            f = (p.x >> w) != (h.x >> w);
+        }
+        bflag[i] = f;
+        return ((unsigned long long)f << 32) | (unsigned long long)(u32)c;
+    }
+    __device__ __forceinline__ void store(size_t i, unsigned long long v) const { bidx[i] = (int32_t)(v >> 32); covsum[i] = (int32_t)(u32)v; }
+};
+}
+void launch_cover_scan(const ulonglong2 *hits, int64_t n, int k, int w, int32_t *bflag, int32_t *bidx, int32_t *covsum,
+                       unsigned long long *d_total, cudaStream_t s) {
+    scan_chained<unsigned long long>(CoverScan{hits, k, w, bflag, bidx, covsum}, (size_t)n, d_total, s);
 }
 
 // one thread per cluster start: walk to the end of the run, pick the median hit as seed

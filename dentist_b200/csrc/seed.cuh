@@ -57,9 +57,11 @@ __global__ void k_lookup_emit_w(const u32 *seq, const u32 *maskbits, const int64
 __global__ void k_hit_cover(const ulonglong2 *hits, int64_t n, int k, int w, int32_t *cov, int32_t *bflag);
 __global__ void k_band_table(const ulonglong2 *hits, int64_t n, int w, const int32_t *bflag, const int32_t *bidx,
                              int32_t *bfirst, u64 *bkey, int32_t nbands);
-__global__ void k_band_pass(const int32_t *bfirst, const u64 *bkey, const int32_t *covsum, int32_t total_cov, int64_t nhits,
-                            int32_t nbands, int h, uint8_t *pass);
-__global__ void k_band_hot(const u64 *bkey, const uint8_t *pass, int32_t nbands, uint8_t *hot, int32_t *cstart);
+__global__ void k_band_hot(const int32_t *bfirst, const u64 *bkey, const int32_t *covsum, const int32_t *d_total_cov, int64_t nhits,
+                           int32_t nbands, int h, uint8_t *hot, int32_t *cstart);
+// hit cover + band flags fused into their prefix sums (one launch); *d_total = bands << 32 | total cover
+void launch_cover_scan(const ulonglong2 *hits, int64_t n, int k, int w, int32_t *bflag, int32_t *bidx, int32_t *covsum,
+                       unsigned long long *d_total, cudaStream_t s);
 __global__ void k_seeds(const ulonglong2 *hits, const int32_t *bfirst, const u64 *bkey, const uint8_t *hot,
                         const int32_t *cstart, const int32_t *cidx, int32_t nbands, SeedGeom G, Seed *seeds, uint8_t *consumed);
 
@@ -89,10 +91,12 @@ struct ExtGeom {
     int ts, cdiff, xdrop, wmax, poolmul; u32 ts_magic;
     int nb_reads;
     u32 a_words, b_words;           // packed words allocated per strand array (bounds of the staged bulk copies)
+    int64_t tile_stride;            // > 0: task t owns tiles [t * tile_stride, (t + 1) * tile_stride) and no offset array exists
 };
 void launch_task_caps(const Seed *seeds, int nseeds, ExtGeom G, u32 *caps, cudaStream_t s);
 void launch_extend(const Seed *seeds, int nseeds, ExtGeom G, const int64_t *tile_off, int2 *tiles, ExtOut *outs,
-                   int4 *pool, int64_t pool_stride, int nwarps_total, int *counter, cudaStream_t s);
+                   int4 *pool, int64_t pool_stride, int nwarps_total, int *counter, const int *order, cudaStream_t s);
+void launch_task_order(const Seed *seeds, int nseeds, ExtGeom G, int *scratch /* 128 ints */, int *order /* 2 * nseeds */, cudaStream_t s);
 void launch_combine(const Seed *seeds, int nseeds, ExtGeom G, int minlen, const int64_t *tile_off, const int2 *tiles,
                     const ExtOut *outs, Cand *cand_all, int32_t *valid, u32 *ntl, cudaStream_t s);
 void launch_write_traces(const Seed *seeds, int nseeds, ExtGeom G, const int64_t *tile_off, const int2 *tiles,
@@ -110,7 +114,6 @@ void launch_final_setkey(const Cand *c, const uint8_t *drop, ulonglong2 *items, 
 void launch_final_records(const Cand *c, const ulonglong2 *items, int ncand, int nb_reads, dn_las_record *rec, u32 *tl, unsigned long long *ctr, cudaStream_t s);
 void launch_final_traces(const Cand *c, const ulonglong2 *items, int ncand, const unsigned long long *ctr, const int64_t *toff, FinalGeom G, uint16_t *out, cudaStream_t s);
 void launch_final_fixup(const Cand *c, ulonglong2 *items, int n, cudaStream_t s);
-void launch_task_strides(int nseeds, int64_t stride, int64_t *tile_off, cudaStream_t s);
 void launch_dedupe(const Cand *cands, int ncand, const int32_t *round_beg, int nrounds, uint8_t *drop, cudaStream_t s);
 
 }  // namespace dn
