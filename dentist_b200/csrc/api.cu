@@ -12,6 +12,7 @@ using namespace dnapi;
 
 namespace dnapi {
 thread_local std::string t_err;
+thread_local bool g_trusted_las = false;
 std::mutex g_mu;
 int g_device = -1;
 cudaStream_t g_stream = nullptr;

@@ -11,6 +11,7 @@
 #include <stdlib.h>
 #include <memory>
 #include <vector>
+#include <chrono>
 
 using namespace dn;
 using namespace dnapi;
@@ -32,6 +33,17 @@ void drop_piles(dn_las_buf &las, const std::vector<int32_t> &group, const dn_ins
         if (out[group[las.rec[i].aread]].status == DN_PILE_OK) { las.rec[w] = las.rec[i]; las.toff[w] = las.toff[i]; w++; }
     las.nrec = w;
 }
+
+// DN_TRACE=1: wall clock per stage of the batch (every stage entry point returns synchronised)
+struct StageClock {
+    bool on = getenv("DN_TRACE") != nullptr; std::chrono::steady_clock::time_point t0 = std::chrono::steady_clock::now();
+    void mark(const char *what) {
+        if (!on) return;
+        auto t1 = std::chrono::steady_clock::now();
+        fprintf(stderr, "[dn batch] %-34s %8.3f ms\n", what, std::chrono::duration<double, std::milli>(t1 - t0).count());
+        t0 = t1;
+    }
+};
 
 }  // namespace
 
@@ -106,9 +118,13 @@ int dn_process_pileups(const dn_block *ref, const dn_pileup_desc *piles, int32_t
         dn_block_desc d; memset(&d, 0, sizeof d);
         d.nreads = (int32_t)nr; d.format = DN_SEQ_BYTES; d.rlen = rlen.data(); d.boff = boff.data(); d.data = bases.data();
         d.data_bytes = boff[nr]; d.group = group.data();
+        StageClock sc; sc.mark("gather reads (host)");
+        TrustedLas trusted;            // every LAS below is produced by this call itself
         BlockGuard g;
         if (int rc = dn_block_upload(&d, &g.b)) return rc;
+        sc.mark("upload");
         if (P.dust) { if (int rc = dn_block_mask_dust(g.b, 64, 2.0, 10, nullptr)) return rc; }          // package.d:476
+        sc.mark("dust");
 
         // ---- computeQVs (package.d:474-516) ---------------------------------------------------------------------
         // daligner -B -s126 -l<minAnchorLength> -e<1 - maxAlignmentError> -mdust X X   (pileUpAlignmentOptions, commandline.d:2886-2902)
@@ -116,13 +132,16 @@ int dn_process_pileups(const dn_block *ref, const dn_pileup_desc *piles, int32_t
         ap.k = P.k; ap.tspace = P.tspace; ap.minlen = P.min_anchor_length; ap.e = 1.0 - P.max_alignment_error; ap.self_block = 1;
         LasGuard las;
         if (int rc = dn_align_blocks(g.b, g.b, &ap, &las.l)) return rc;
+        sc.mark("pile alignment");
         if (int rc = dn_las_filter_error(&las.l, P.max_alignment_error)) return rc;                      // :483-485
+        sc.mark("filter error");
         std::vector<int64_t> cnt(n > 0 ? n : 1);
         count_per_pile(las.l, group, cnt);
         for (int p = 0; p < n; p++) if (out[p].status == DN_PILE_OK && cnt[p] == 0) out[p].status = DN_PILE_EMPTY_ALIGNMENT;   // :487-490
         if (las.l.nrec > 0)
             if (int rc = dn_las_chain(&las.l, P.max_indel, P.max_chain_gap, P.max_rel_overlap, P.min_rel_score,
                                       P.min_score > 0 ? P.min_score : P.tspace)) return rc;              // :492-496
+        sc.mark("chain");
         // coverage = |allowedReferenceReadIds|, raised to minQVCoverage for pile-ups of >= minQVCoverage reads (:498-501)
         std::vector<int32_t> cov(nr);
         for (int p = 0; p < n; p++) {
@@ -133,9 +152,12 @@ int dn_process_pileups(const dn_block *ref, const dn_pileup_desc *piles, int32_t
         }
         uint8_t *qv = nullptr; int64_t *qoff = nullptr;
         if (int rc = dn_compute_qvs_v(rlen.data(), (int32_t)nr, &las.l, 0, cov.data(), &qv, &qoff)) return rc;       // :503
+        sc.mark("qvs");
         struct QvGuard { uint8_t *q; int64_t *o; ~QvGuard() { dn_free(q); dn_free(o); } } qg{qv, qoff};
         if (int rc = dn_las_filter_pileup(&las.l, rlen.data(), (int32_t)nr, rlen.data(), (int32_t)nr, P.proper_alignment_allowance)) return rc;   // :505-510
+        sc.mark("filter pile-up");
         if (int rc = dn_las_force_flat(&las.l)) return rc;
+        sc.mark("force flat");
         count_per_pile(las.l, group, cnt);
         for (int p = 0; p < n; p++) if (out[p].status == DN_PILE_OK && cnt[p] == 0) out[p].status = DN_PILE_EMPTY_AFTER_FILTER;   // :512-515
         drop_piles(las.l, group, out);
@@ -144,6 +166,7 @@ int dn_process_pileups(const dn_block *ref, const dn_pileup_desc *piles, int32_t
         std::vector<int32_t> cgroup(nr), rank(nr > 0 ? nr : 1); std::vector<int64_t> poff(n + 1, 0);
         for (int64_t r = 0; r < nr; r++) cgroup[r] = (allowed[r] && out[group[r]].status == DN_PILE_OK) ? group[r] : -1;
         if (int rc = dn_reference_read_candidates(qv, qoff, cgroup.data(), (int32_t)nr, n, P.bad_fraction, rank.data(), poff.data())) return rc;
+        sc.mark("reference read candidates");
         std::vector<std::vector<uint8_t>> cons(n);
         std::vector<int32_t> pending;
         for (int p = 0; p < n; p++) if (out[p].status == DN_PILE_OK) pending.push_back(p);
@@ -173,6 +196,7 @@ int dn_process_pileups(const dn_block *ref, const dn_pileup_desc *piles, int32_t
             if (!cons[p].empty()) memcpy(out[p].consensus, cons[p].data(), cons[p].size());
         }
 
+        sc.mark("consensus");
         // ---- alignConsensusToFlankingContigs (:621-667) ---------------------------------------------------------------
         // daligner -A -B -s126 -l126 -e0.7 -mdust -mrep F C   (postConsensusAlignmentOptions, commandline.d:2918-2935)
         const int64_t nf = ffirst[n];
@@ -201,10 +225,12 @@ int dn_process_pileups(const dn_block *ref, const dn_pileup_desc *piles, int32_t
             cd.nreads = n; cd.format = DN_SEQ_BYTES; cd.rlen = clen.data(); cd.boff = coff.data(); cd.data = cbases.data();
             cd.data_bytes = coff[n]; cd.group = cgrp.data();
             if (int rc = dn_block_upload(&cd, &cb.b)) return rc;
+            sc.mark("flank crop + masks + upload");
             dn_align_params fp; dn_align_params_default(&fp);
             fp.k = P.flank_k; fp.tspace = P.tspace; fp.minlen = P.tspace; fp.e = 0.7;
             LasGuard fl;
             if (int rc = dn_align_blocks(fb.b, cb.b, &fp, &fl.l)) return rc;
+            sc.mark("flank alignment");
             // split by pile-up (bread = pile-up id): records keep their LAsort order, aread becomes the index into the
             // pile-up's own flank list (1-based contig id of the reference's flankingContigsDb minus one), bread = 0
             std::vector<int64_t> pn(n, 0), pt(n, 0);
@@ -227,6 +253,7 @@ int dn_process_pileups(const dn_block *ref, const dn_pileup_desc *piles, int32_t
                 memcpy(o.trace + o.ntrace, fl.l.trace + fl.l.toff[i], sizeof(uint16_t) * (size_t)r.tlen);
                 o.ntrace += r.tlen; o.nrec++;
             }
+            sc.mark("split by pile-up");
         }
         return DN_OK;
     });

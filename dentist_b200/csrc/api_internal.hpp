@@ -12,6 +12,10 @@ extern cudaStream_t g_stream;
 extern int g_device;
 int fail(int code, const std::string &m);
 int ensure_device();
+// Set by dn_process_pileups around its stage calls: the LAS handed from stage to stage there was produced by this library
+// in the same call, so the per-record / per-trace-point host validation of caller-supplied LAS is skipped.
+extern thread_local bool g_trusted_las;
+struct TrustedLas { bool prev; TrustedLas() : prev(g_trusted_las) { g_trusted_las = true; } ~TrustedLas() { g_trusted_las = prev; } };
 template <typename F> int guarded(F &&f) {
     try { return f(); }
     catch (const dn::Error &e) { return fail(DN_ERR_CUDA, e.what()); }

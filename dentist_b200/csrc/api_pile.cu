@@ -34,6 +34,7 @@ template <typename T> T *to_device(DBuf<T> &d, const T *h, size_t n, cudaStream_
 // Records of a caller-supplied LAS are checked on the host before a kernel indexes reads, traces or vote columns by
 // them: ids, coordinates against the read lengths, tile count against the span, trace extent against the buffer.
 const char *validate_las(const dn_las_buf *l, const int32_t *alen, int64_t na, const int32_t *blen, int64_t nb, bool with_trace) {
+    if (dnapi::g_trusted_las) return nullptr;
     const int ts = l->tspace;
     for (int64_t i = 0; i < l->nrec; i++) {
         const dn_las_record &r = l->rec[i];
@@ -173,6 +174,21 @@ int dn_las_keep_best_chains(dn_las_buf *las, int32_t nb_reads, double n_frac) {
 
 int dn_las_force_flat(dn_las_buf *las) {
     if (!las) return fail(DN_ERR_INVALID, "null argument");
+    {   // already in FlatLocalAlignment order (base.d:1787-1809), e.g. straight from the aligner and order-preserving
+        // filters: only the chain flags go (dazzler.d:4084-4093), no sort
+        bool sorted = true;
+        for (int64_t i = 1; i < las->nrec && sorted; i++) {
+            const dn_las_record &p = las->rec[i - 1], &q = las->rec[i];
+            const int pc = p.flags & DN_LAS_COMP ? 1 : 0, qc = q.flags & DN_LAS_COMP ? 1 : 0;
+            const int32_t a[8] = {p.aread, p.bread, pc, p.abpos, p.aepos, p.bbpos, p.bepos, p.diffs};
+            const int32_t b[8] = {q.aread, q.bread, qc, q.abpos, q.aepos, q.bbpos, q.bepos, q.diffs};
+            for (int f = 0; f < 8; f++) { if (a[f] < b[f]) break; if (a[f] > b[f]) { sorted = false; break; } }
+        }
+        if (sorted) {
+            for (int64_t i = 0; i < las->nrec; i++) las->rec[i].flags &= (DN_LAS_COMP | DN_LAS_ELIM);
+            return DN_OK;
+        }
+    }
     std::lock_guard<std::mutex> lk(g_mu);
     if (int rc = ensure_device()) return rc;
     return guarded([&] { cudaSetDevice(g_device); force_flat_device(las->rec, las->toff, las->nrec, g_stream); return DN_OK; });
@@ -329,14 +345,16 @@ int dn_consensus(const dn_block *db, const dn_las_buf *las, const int32_t *reads
         if (ncols > 0) launch_cons_write(ncols, nemit.p, eoff.p, sym.p, dout.p, s);
         // sequence offsets = eoff at each target's first column
         std::vector<int32_t> heoff(nreads + 1, total);
-        for (int i = 0; i < nreads; i++)
-            DN_CUDA(cudaMemcpyAsync(&heoff[i], eoff.p + vote_off[i], 4, cudaMemcpyDeviceToHost, s));
+        int32_t *h_eoff = (int32_t *)hcache_alloc(sizeof(int32_t) * (size_t)(ncols + 1));      // pinned: one copy instead of one per target
+        if (ncols > 0) DN_CUDA(cudaMemcpyAsync(h_eoff, eoff.p, sizeof(int32_t) * (size_t)ncols, cudaMemcpyDeviceToHost, s));
         memset(out, 0, sizeof *out);
         out->nseq = nreads;
         out->off = (int64_t *)hcache_alloc(sizeof(int64_t) * (nreads + 1));
         out->bases = (uint8_t *)hcache_alloc(total + 1);
         if (total) DN_CUDA(cudaMemcpyAsync(out->bases, dout.p, total, cudaMemcpyDeviceToHost, s));
         DN_CUDA(cudaStreamSynchronize(s));
+        for (int i = 0; i < nreads; i++) heoff[i] = h_eoff[vote_off[i]];
+        hcache_free(h_eoff);
         // a read nothing aligns to has no consensus (daccord prints nothing -> "consensus could not be computed" and the
         // next reference read candidate, package.d:600-619, 307-329): its columns are squeezed out of the result
         int64_t w = 0;

@@ -291,41 +291,50 @@ extern "C" int dn_las_chain(dn_las_buf *las, int32_t max_indel, int32_t max_chai
     return guarded([&]() -> int {
         cudaSetDevice(g_device); arena().reset();
         cudaStream_t s = g_stream;
-        std::vector<dn_las_record> in(n);
+        // page-locked staging for both directions (hcache blocks >= 256 KB are pinned and recycled)
+        dn_las_record *in = (dn_las_record *)hcache_alloc(sizeof(dn_las_record) * (size_t)(n + 1));
         for (int64_t i = 0; i < n; i++) in[i] = las->rec[idx[i]];
         DBuf<dn_las_record> drec(n); DBuf<int32_t> dg(ngroups + 1), osrc(4 * n), ocnt(ngroups), ost(ngroups); DBuf<u32> ofl(4 * n);
-        DN_CUDA(cudaMemcpyAsync(drec.p, in.data(), sizeof(dn_las_record) * n, cudaMemcpyHostToDevice, s));
+        DN_CUDA(cudaMemcpyAsync(drec.p, in, sizeof(dn_las_record) * n, cudaMemcpyHostToDevice, s));
         DN_CUDA(cudaMemcpyAsync(dg.p, gstart.data(), sizeof(int32_t) * (ngroups + 1), cudaMemcpyHostToDevice, s));
         ChainOpts o{max_indel, max_chain_gap, min_score, max_rel_overlap, min_rel_score};
         DN_LAUNCH(k_chain_groups, (ngroups + 63) / 64, 64, 0, s, (const dn_las_record *)drec.p, (const int32_t *)dg.p, ngroups, o,
                   osrc.p, ofl.p, ocnt.p, ost.p);
-        std::vector<int32_t> hsrc(4 * n), hcnt(ngroups), hst(ngroups); std::vector<u32> hfl(4 * n);
-        DN_CUDA(cudaMemcpyAsync(hsrc.data(), osrc.p, sizeof(int32_t) * 4 * n, cudaMemcpyDeviceToHost, s));
-        DN_CUDA(cudaMemcpyAsync(hfl.data(), ofl.p, sizeof(u32) * 4 * n, cudaMemcpyDeviceToHost, s));
-        DN_CUDA(cudaMemcpyAsync(hcnt.data(), ocnt.p, sizeof(int32_t) * ngroups, cudaMemcpyDeviceToHost, s));
-        DN_CUDA(cudaMemcpyAsync(hst.data(), ost.p, sizeof(int32_t) * ngroups, cudaMemcpyDeviceToHost, s));
+        int32_t *hsrc = (int32_t *)hcache_alloc(sizeof(int32_t) * (size_t)(4 * n + 1));
+        u32 *hfl = (u32 *)hcache_alloc(sizeof(u32) * (size_t)(4 * n + 1));
+        int32_t *hcnt = (int32_t *)hcache_alloc(sizeof(int32_t) * (size_t)(2 * ngroups + 1)), *hst = hcnt + ngroups;
+        struct Stage { void *a, *b, *c, *d; ~Stage() { hcache_free(a); hcache_free(b); hcache_free(c); hcache_free(d); } } stage{in, hsrc, hfl, hcnt};
+        DN_CUDA(cudaMemcpyAsync(hsrc, osrc.p, sizeof(int32_t) * 4 * n, cudaMemcpyDeviceToHost, s));
+        DN_CUDA(cudaMemcpyAsync(hfl, ofl.p, sizeof(u32) * 4 * n, cudaMemcpyDeviceToHost, s));
+        DN_CUDA(cudaMemcpyAsync(hcnt, ocnt.p, sizeof(int32_t) * ngroups, cudaMemcpyDeviceToHost, s));
+        DN_CUDA(cudaMemcpyAsync(hst, ost.p, sizeof(int32_t) * ngroups, cudaMemcpyDeviceToHost, s));
         DN_CUDA(cudaStreamSynchronize(s));
         // groups the kernel declined (> 63 records, or more output than 4 * n slots) go through the host restatement
-        std::vector<std::vector<int32_t>> xsrc(ngroups); std::vector<std::vector<u32>> xfl(ngroups);
+        std::vector<int32_t> xgroup;                                   // declined groups, ascending
+        std::vector<std::vector<int32_t>> xsrc; std::vector<std::vector<u32>> xfl;
         const HostChainOpts ho{max_indel, max_chain_gap, min_score, max_rel_overlap, min_rel_score};
         int64_t total = 0;
         for (int g = 0; g < ngroups; g++) {
             if (hst[g]) {
-                chain_group_host(in.data() + gstart[g], gstart[g + 1] - gstart[g], ho, xsrc[g], xfl[g]);
-                for (auto &v : xsrc[g]) v += gstart[g];
-                hcnt[g] = (int32_t)xsrc[g].size();
+                xgroup.push_back(g); xsrc.emplace_back(); xfl.emplace_back();
+                chain_group_host(in + gstart[g], gstart[g + 1] - gstart[g], ho, xsrc.back(), xfl.back());
+                for (auto &v : xsrc.back()) v += gstart[g];
+                hcnt[g] = (int32_t)xsrc.back().size();
             }
             total += hcnt[g];
         }
         // gather: records keep their trace (toff), flags are rewritten; a record may appear in two chains
         dn_las_record *nrec = (dn_las_record *)hcache_alloc(sizeof(dn_las_record) * (total + 1));
         int64_t *ntoff = (int64_t *)hcache_alloc(sizeof(int64_t) * (total + 1));
-        int64_t w = 0;
-        for (int g = 0; g < ngroups; g++)
+        int64_t w = 0; size_t xi = 0;
+        for (int g = 0; g < ngroups; g++) {
+            const bool host = hst[g] != 0;
             for (int t = 0; t < hcnt[g]; t++) {
-                const int64_t src = idx[hst[g] ? xsrc[g][t] : hsrc[4 * (int64_t)gstart[g] + t]];
-                nrec[w] = las->rec[src]; nrec[w].flags = hst[g] ? xfl[g][t] : hfl[4 * (int64_t)gstart[g] + t]; ntoff[w] = las->toff[src]; w++;
+                const int64_t src = idx[host ? xsrc[xi][t] : hsrc[4 * (int64_t)gstart[g] + t]];
+                nrec[w] = las->rec[src]; nrec[w].flags = host ? xfl[xi][t] : hfl[4 * (int64_t)gstart[g] + t]; ntoff[w] = las->toff[src]; w++;
             }
+            if (host) xi++;
+        }
         hcache_free(las->rec); hcache_free(las->toff);
         las->rec = nrec; las->toff = ntoff; las->nrec = total;
         return DN_OK;

@@ -75,7 +75,7 @@ void hcache_free(void *p) {
     if (!p || comm_owns_host_pointer(p)) return;
     HBlock *h = (HBlock *)p - 1;
     std::lock_guard<std::mutex> lk(g_hmu);
-    if (g_hfree.size() < 16) { g_hfree.push_back(h); return; }
+    if (g_hfree.size() < 96) { g_hfree.push_back(h); return; }           // a pile-up batch cycles through ~40 result / staging blocks
     if (h->pinned) cudaFreeHost(h); else free(h);
 }
 
