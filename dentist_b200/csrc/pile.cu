@@ -10,6 +10,7 @@
 // of the error-rate filter, which is evaluated with the same IEEE operations as the D source.
 #include "engine.cuh"
 #include "pile.cuh"
+#include <stdlib.h>
 
 namespace dn {
 namespace {
@@ -154,6 +155,94 @@ __global__ void __launch_bounds__(128) k_cons_vote(const ConsTask *__restrict__ 
             if (dir == 0u) { atomicAdd(&cnt[(vbase + T.ap + i - 1) * 5 + bq[j - 1]], 1); i--; j--; }
             else if (dir == 1u) { atomicAdd(&cnt[(vbase + T.ap + i - 1) * 5 + 4], 1); i--; }
             else { pend = bq[j - 1]; j--; }
+        }
+        if (pend >= 0) { atomicAdd(&ins[(vbase + T.ap + i) * 4 + pend], 1); atomicAdd(&insn[vbase + T.ap + i], 1); }
+        for (int x = 0; x < n; x++) atomicAdd(&cov[vbase + T.ap + x], 1);
+    }
+}
+
+// The same votes from a bit-parallel DP (Myers 1999 in Hyyro's edit-distance form): the A tile (<= 128 bases) is the
+// pattern, one 128-bit pair (VP, VN) of vertical +1 / -1 deltas per B column replaces the column of cells, so a column
+// costs ~60 instructions instead of 126 cells x ~15, and nothing lives in local memory.  The traceback needs exact cell
+// values to repeat the cell DP's choice (diagonal > deletion > insertion among the minima): D[i][j] = j + popc(VP_j & low i
+// bits) - popc(VN_j & low i bits), so the directions -- hence every vote -- are identical to k_cons_vote's.
+struct U128 { unsigned long long lo, hi; };
+__device__ __forceinline__ U128 u_and(U128 a, U128 b) { return U128{a.lo & b.lo, a.hi & b.hi}; }
+__device__ __forceinline__ U128 u_or(U128 a, U128 b) { return U128{a.lo | b.lo, a.hi | b.hi}; }
+__device__ __forceinline__ U128 u_xor(U128 a, U128 b) { return U128{a.lo ^ b.lo, a.hi ^ b.hi}; }
+__device__ __forceinline__ U128 u_not(U128 a) { return U128{~a.lo, ~a.hi}; }
+__device__ __forceinline__ U128 u_add(U128 a, U128 b) { U128 r; r.lo = a.lo + b.lo; r.hi = a.hi + b.hi + (r.lo < a.lo ? 1ull : 0ull); return r; }
+__device__ __forceinline__ U128 u_shl1(U128 a) { return U128{a.lo << 1, (a.hi << 1) | (a.lo >> 63)}; }
+__device__ __forceinline__ int u_bit(U128 a, int i) { return (int)(((i < 64 ? a.lo >> i : a.hi >> (i - 64))) & 1ull); }
+// number of set bits among the lowest i bits (0 <= i <= 128)
+__device__ __forceinline__ int u_popc_low(U128 a, int i) {
+    if (i >= 64) return __popcll(a.lo) + (i >= 128 ? __popcll(a.hi) : __popcll(a.hi & ((1ull << (i - 64)) - 1ull)));
+    return __popcll(a.lo & ((1ull << i) - 1ull));
+}
+
+__global__ void __launch_bounds__(128) k_cons_vote_bv(const ConsTask *__restrict__ tasks, int64_t ntasks,
+                                                      const dn_las_record *__restrict__ rec, const int32_t *__restrict__ la_target,
+                                                      ConsGeom G, u32 *__restrict__ scratch, int32_t *__restrict__ cnt,
+                                                      int32_t *__restrict__ ins, int32_t *__restrict__ insn, int32_t *__restrict__ cov) {
+    const int64_t nthreads = (int64_t)gridDim.x * blockDim.x;
+    const int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    unsigned long long *cols = (unsigned long long *)scratch + tid;      // word w of column j (1-based) at cols[((j - 1) * 4 + w) * nthreads]
+    for (int64_t task = tid; task < ntasks; task += nthreads) {
+        const ConsTask T = tasks[task];
+        const int n = T.alen, m = T.bb;
+        if (m > 250 || n > 128) continue;
+        const dn_las_record la = rec[T.la];
+        const int tg = la_target[T.la];
+        const int64_t vbase = G.vote_off[tg];
+        const u32 *Aw = G.fwd, *Bw = (la.flags & DN_LAS_COMP) ? G.rc : G.fwd;
+        const int64_t ga = G.off[la.aread] + T.ap, gb = G.off[la.bread] + T.bp;
+        U128 P0{0, 0}, P1{0, 0}, P2{0, 0}, P3{0, 0};                  // positions of each base in the A tile
+        for (int i = 0; i < n; i++) {
+            const int a = base_at(Aw, ga + i);
+            const unsigned long long bl = i < 64 ? 1ull << i : 0ull, bh = i < 64 ? 0ull : 1ull << (i - 64);
+            if (a == 0) { P0.lo |= bl; P0.hi |= bh; } else if (a == 1) { P1.lo |= bl; P1.hi |= bh; }
+            else if (a == 2) { P2.lo |= bl; P2.hi |= bh; } else { P3.lo |= bl; P3.hi |= bh; }
+        }
+        U128 VP{~0ull, ~0ull}, VN{0, 0};
+        for (int j = 1; j <= m; j++) {
+            const int b = base_at(Bw, gb + j - 1);
+            const U128 Eq = b == 0 ? P0 : (b == 1 ? P1 : (b == 2 ? P2 : P3));
+            const U128 D0 = u_or(u_or(u_xor(u_add(u_and(Eq, VP), VP), VP), Eq), VN);
+            const U128 HP = u_or(VN, u_not(u_or(D0, VP))), HN = u_and(D0, VP);
+            U128 X = u_shl1(HP); X.lo |= 1ull;                        // row 0 grows by one per column (global alignment)
+            VP = u_or(u_shl1(HN), u_not(u_or(D0, X))); VN = u_and(D0, X);
+            unsigned long long *c = cols + (int64_t)((j - 1) * 4) * nthreads;
+            c[0] = VP.lo; c[nthreads] = VP.hi; c[2 * nthreads] = VN.lo; c[3 * nthreads] = VN.hi;
+        }
+        auto column = [&](int j, U128 &vp, U128 &vn) {
+            if (j == 0) { vp = U128{~0ull, ~0ull}; vn = U128{0, 0}; return; }
+            const unsigned long long *c = cols + (int64_t)((j - 1) * 4) * nthreads;
+            vp = U128{c[0], c[nthreads]}; vn = U128{c[2 * nthreads], c[3 * nthreads]};
+        };
+        int i = n, j = m, pend = -1;
+        U128 vpj, vnj; column(m, vpj, vnj);
+        int c0 = m + u_popc_low(vpj, n) - u_popc_low(vnj, n);          // D[n][m]
+        while (i > 0 || j > 0) {
+            u32 dir; int bj = 0, nc0 = 0;
+            U128 vpl, vnl;
+            if (i == 0) { dir = 2u; bj = base_at(Bw, gb + j - 1); nc0 = j - 1; column(j - 1, vpl, vnl); }
+            else if (j == 0) { dir = 1u; nc0 = i - 1; }
+            else {
+                column(j - 1, vpl, vnl);
+                bj = base_at(Bw, gb + j - 1);
+                const int up = c0 - (u_bit(vpj, i - 1) - u_bit(vnj, i - 1));
+                const int left = (j - 1) + u_popc_low(vpl, i) - u_popc_low(vnl, i);
+                const int dg = left - (u_bit(vpl, i - 1) - u_bit(vnl, i - 1));
+                const int d = dg + (base_at(Aw, ga + i - 1) != bj), u = up + 1, l = left + 1;
+                int v = d; if (u < v) v = u; if (l < v) v = l;
+                dir = (v == d) ? 0u : ((v == u) ? 1u : 2u);
+                nc0 = dir == 0u ? dg : (dir == 1u ? up : left);
+            }
+            if (dir != 2u && pend >= 0) { atomicAdd(&ins[(vbase + T.ap + i) * 4 + pend], 1); atomicAdd(&insn[vbase + T.ap + i], 1); pend = -1; }
+            if (dir == 0u) { atomicAdd(&cnt[(vbase + T.ap + i - 1) * 5 + bj], 1); i--; j--; vpj = vpl; vnj = vnl; }
+            else if (dir == 1u) { atomicAdd(&cnt[(vbase + T.ap + i - 1) * 5 + 4], 1); i--; }
+            else { pend = bj; j--; vpj = vpl; vnj = vnl; }
+            c0 = nc0;
         }
         if (pend >= 0) { atomicAdd(&ins[(vbase + T.ap + i) * 4 + pend], 1); atomicAdd(&insn[vbase + T.ap + i], 1); }
         for (int x = 0; x < n; x++) atomicAdd(&cov[vbase + T.ap + x], 1);
@@ -361,7 +450,9 @@ void launch_cons_tasks(const dn_las_record *rec, const int64_t *toff, const uint
 int cons_vote_threads() { return sm_count() * 4 * 128; }
 void launch_cons_vote(const ConsTask *tasks, int64_t ntasks, const dn_las_record *rec, const int32_t *la_target, ConsGeom G,
                       u32 *scratch, int32_t *cnt, int32_t *ins, int32_t *insn, int32_t *cov, cudaStream_t s) {
-    DN_LAUNCH(k_cons_vote, sm_count() * 4, 128, 0, s, tasks, ntasks, rec, la_target, G, scratch, cnt, ins, insn, cov);
+    static const bool cell_dp = getenv("DN_CONS_CELL_DP") != nullptr;         // the thread-per-cell-row DP the bit-parallel kernel replaced
+    if (cell_dp) DN_LAUNCH(k_cons_vote, sm_count() * 4, 128, 0, s, tasks, ntasks, rec, la_target, G, scratch, cnt, ins, insn, cov);
+    else DN_LAUNCH(k_cons_vote_bv, sm_count() * 4, 128, 0, s, tasks, ntasks, rec, la_target, G, scratch, cnt, ins, insn, cov);
 }
 void launch_cons_count(ConsGeom G, const int32_t *targets, int ntargets, int64_t ncols, const int32_t *cnt, const int32_t *ins,
                        const int32_t *insn, const int32_t *cov, int32_t *nemit, uint8_t *sym, cudaStream_t s) {
