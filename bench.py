@@ -262,6 +262,7 @@ def oracle_pile(reads, group, p):
     lens = np.diff(off)
     la, tr, _ = oracle.align(off, bases, off, bases, tspace=126, minlen=500, self=1, **ORC)
     toff = la["toff"].astype(np.int64)
+    la, toff, tr, _ = oracle.bridge(off, bases, off, bases, la, toff, tr, 126)          # daligner -B
     keep = oracle.filter_error(la, 0.3); la, toff = la[keep], toff[keep]
     from oracle import chaining
     src, fl = chaining.chain_local_alignments(la, chaining.ChainingOptions(min_score=126))

@@ -19,7 +19,7 @@ EXPORTS = [
     "dn_process_pileups", "dn_pileup_params_default", "dn_insertion_free", "dn_pile_status_string", "dn_block_add_mask",
     "dn_comm_get_id", "dn_comm_init", "dn_comm_shutdown", "dn_comm_rank", "dn_comm_size", "dn_align_blocks_gather", "dn_align_host_gather",
     "dn_comm_allgatherv", "dn_las_keep_best_chains", "dn_las_transpose", "dn_comm_shared_segment_bytes",
-    "dn_compute_qvs_db", "dn_read_qvs_db",
+    "dn_compute_qvs_db", "dn_read_qvs_db", "dn_las_bridge",
 ]
 
 
@@ -70,7 +70,7 @@ class PileupParams(C.Structure):
     _fields_ = [("max_alignment_error", C.c_double), ("min_anchor_length", C.c_int32), ("tspace", C.c_int32),
                 ("proper_alignment_allowance", C.c_int32), ("bad_fraction", C.c_double), ("min_qv_coverage", C.c_int32),
                 ("dust", C.c_int32), ("max_indel", C.c_int32), ("max_chain_gap", C.c_int32), ("max_rel_overlap", C.c_double),
-                ("min_rel_score", C.c_double), ("min_score", C.c_int32), ("k", C.c_int32), ("flank_k", C.c_int32)]
+                ("min_rel_score", C.c_double), ("min_score", C.c_int32), ("k", C.c_int32), ("flank_k", C.c_int32), ("bridge", C.c_int32)]
 
 
 class InsertionOut(C.Structure):
@@ -121,6 +121,7 @@ def lib():
         L.dn_las_force_flat.argtypes = [C.POINTER(LasBuf)]
         L.dn_reference_read_candidates.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_double, C.c_void_p, C.c_void_p]
         L.dn_dbdust.argtypes = [C.c_char_p, C.POINTER(C.c_char_p), C.c_int]
+        L.dn_las_bridge.argtypes = [C.c_void_p, C.c_void_p, C.POINTER(LasBuf), C.c_int32, C.c_void_p]
         L.dn_compute_qvs_db.argtypes = [C.c_char_p, C.c_char_p, C.c_uint32]
         L.dn_read_qvs_db.argtypes = [C.c_char_p, C.c_void_p, C.c_void_p, C.c_void_p]
         L.dn_dust_block.argtypes = [C.c_void_p, C.c_int32, C.c_double, C.c_int32, C.c_void_p, C.c_void_p]

@@ -264,7 +264,8 @@ int dn_las_read(const char *path, dn_las_buf *out) {
 
 // ---- file-level drop-ins ------------------------------------------------------------------
 
-static int parse_opts(const char *const *opts, int nopts, dn_align_params *p, bool *asym, std::vector<std::string> *masks, double *best_frac = nullptr) {
+static int parse_opts(const char *const *opts, int nopts, dn_align_params *p, bool *asym, std::vector<std::string> *masks, double *best_frac = nullptr,
+                      bool *bridge = nullptr) {
     for (int i = 0; i < nopts; i++) {
         const char *o = opts[i];
         if (!o || o[0] != '-' || !o[1]) return fail(DN_ERR_INVALID, std::string("bad option: ") + (o ? o : "(null)"));
@@ -281,7 +282,8 @@ static int parse_opts(const char *const *opts, int nopts, dn_align_params *p, bo
             case 'A': *asym = true; break;
             case 'm': masks->push_back(v); break;
             case 'n': if (best_frac) *best_frac = atof(v); break;                 // damapper: also report chains within this fraction of the best (dazzler.d:5920-5923)
-            case 'T': case 'M': case 'B': case 'v': case 'b': case 'a': case 'C': case 'N': case 'z': case 'P': case 'p': break;   // accepted, no effect on a GPU
+            case 'B': if (bridge) *bridge = true; break;                               // bridge consecutive aligned segments (dazzler.d:5823-5824)
+            case 'T': case 'M': case 'v': case 'b': case 'a': case 'C': case 'N': case 'z': case 'P': case 'p': break;   // accepted, no effect on a GPU
             default: return fail(DN_ERR_INVALID, std::string("unknown option: ") + o);
         }
     }
@@ -294,8 +296,8 @@ static int align_files(const char *dbA, const char *dbB, const char *const *opts
     return guarded([&]() -> int {
         dn_align_params p; dn_align_params_default(&p);
         if (mapper) { p.minlen = 1000; p.k = 20; }       /* damapper's own defaults (DENTIST passes neither -k nor -l, commandline.d:2943-2955) */
-        bool asym = false; std::vector<std::string> masks; double best_frac = 0.0;     // no -n: the best chain of every read only
-        if (int rc = parse_opts(opts, nopts, &p, &asym, &masks, &best_frac)) return rc;
+        bool asym = false, bridge = false; std::vector<std::string> masks; double best_frac = 0.0;     // no -n: the best chain of every read only
+        if (int rc = parse_opts(opts, nopts, &p, &asym, &masks, &best_frac, &bridge)) return rc;
         const bool self = (dbB == nullptr) || std::string(dbA) == std::string(dbB);
         HostDb A, B;
         std::string err;
@@ -310,6 +312,7 @@ static int align_files(const char *dbA, const char *dbB, const char *const *opts
         if (!self) { if (int rc = dn_block_upload(&db, &gb.b)) return rc; }
         const dn_block *pb = self ? ga.b : gb.b;
         if (int rc = dn_align_blocks(ga.b, pb, &p, &ab.l)) return rc;
+        if (bridge && !mapper) { if (int rc = dn_las_bridge(ga.b, pb, &ab.l, (int32_t)(6.0 / (1.0 - p.e) + 0.5), nullptr)) return rc; }   // daligner -B
         if (mapper) {
             if (int rc = dn_las_chain_mapper(&ab.l, (int32_t)Bx.rlen.size(), 1000, 10000)) return rc;
             if (int rc = dn_las_keep_best_chains(&ab.l, (int32_t)Bx.rlen.size(), best_frac)) return rc;

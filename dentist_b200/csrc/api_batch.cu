@@ -60,6 +60,7 @@ void dn_pileup_params_default(dn_pileup_params *p) {
     p->dust = 1;                              // dbdust(croppedDb) + -mdust, package.d:476-481
     p->max_indel = 1000; p->max_chain_gap = 10000; p->max_rel_overlap = 0.3; p->min_rel_score = 1.0; p->min_score = 0;   // commandline.d:2820-2830 (0: tspace)
     p->k = 14; p->flank_k = 14;
+    p->bridge = 1;                            // daligner -B in pileUpAlignmentOptions and postConsensusAlignmentOptions
 }
 
 void dn_insertion_free(dn_insertion_out *out, int32_t n) {
@@ -132,6 +133,7 @@ int dn_process_pileups(const dn_block *ref, const dn_pileup_desc *piles, int32_t
         ap.k = P.k; ap.tspace = P.tspace; ap.minlen = P.min_anchor_length; ap.e = 1.0 - P.max_alignment_error; ap.self_block = 1;
         LasGuard las;
         if (int rc = dn_align_blocks(g.b, g.b, &ap, &las.l)) return rc;
+        if (P.bridge) { if (int rc = dn_las_bridge(g.b, g.b, &las.l, (int32_t)(6.0 / (1.0 - ap.e) + 0.5), nullptr)) return rc; }
         sc.mark("pile alignment");
         if (int rc = dn_las_filter_error(&las.l, P.max_alignment_error)) return rc;                      // :483-485
         sc.mark("filter error");
@@ -230,6 +232,7 @@ int dn_process_pileups(const dn_block *ref, const dn_pileup_desc *piles, int32_t
             fp.k = P.flank_k; fp.tspace = P.tspace; fp.minlen = P.tspace; fp.e = 0.7;
             LasGuard fl;
             if (int rc = dn_align_blocks(fb.b, cb.b, &fp, &fl.l)) return rc;
+            if (P.bridge) { if (int rc = dn_las_bridge(fb.b, cb.b, &fl.l, (int32_t)(6.0 / (1.0 - fp.e) + 0.5), nullptr)) return rc; }
             sc.mark("flank alignment");
             // split by pile-up (bread = pile-up id): records keep their LAsort order, aread becomes the index into the
             // pile-up's own flank list (1-based contig id of the reference's flankingContigsDb minus one), bread = 0

@@ -235,6 +235,96 @@ int dn_reference_read_candidates(const uint8_t *qv, const int64_t *qoff, const i
 // damapper -C (dazzler.d:5931-5936): the records of B.A.las from those of A.B.las -- roles swapped, coordinates mirrored for
 // complemented alignments, trace points re-laid on the new A read by per-tile realignment (spec: oracle/pile_oracle.c,
 // orc_transpose), result in LAsort order.  Chain flags are cleared (chain the result again: the criteria are symmetric).
+// `daligner -B` (dazzler.d:5823-5824): neighbouring records of one (aread, bread, comp) separated by a short gap become
+// one record; specification in oracle/pile_oracle.c (orc_bridge).  The bridges' DPs run on the device (one thread each),
+// the records and traces are re-assembled on the host (bridges are few).
+int dn_las_bridge(const dn_block *a, const dn_block *b, dn_las_buf *las, int32_t cdiff, int64_t *nbridged) {
+    if (!a || !b || !las) return fail(DN_ERR_INVALID, "null argument");
+    const DevBlock &A = a->b, &B = b->b;
+    const int ts = las->tspace;
+    if (ts < 1) return fail(DN_ERR_INVALID, "bad trace spacing");
+    if (cdiff < 1) return fail(DN_ERR_INVALID, "bad cdiff");
+    if (const char *bad = validate_las(las, A.h_len.data(), A.nreads, B.h_len.data(), B.nreads, true)) return fail(DN_ERR_INVALID, bad);
+    if (nbridged) *nbridged = 0;
+    const int64_t n = las->nrec;
+    std::vector<uint8_t> br(n > 0 ? n : 1, 0);
+    std::vector<BridgeTask> tasks; int64_t nrows = 0;
+    for (int64_t r = 1; r < n; r++) {
+        const dn_las_record &p = las->rec[r - 1], &q = las->rec[r];
+        const int gA = q.abpos - p.aepos, gB = q.bbpos - p.bepos;
+        const int dg = gA > gB ? gA - gB : gB - gA, mx = gA > gB ? gA : gB;
+        const long long lim = std::max<long long>(16ll * cdiff, 6ll * mx);
+        if (p.aread != q.aread || p.bread != q.bread || ((p.flags ^ q.flags) & DN_LAS_COMP) || gA < 0 || gA > 128 || gB < 0 || gB > 250 ||
+            (long long)dg * cdiff > lim) continue;
+        br[r] = 1;
+        BridgeTask t; t.ga = A.h_off[q.aread] + p.aepos; t.gb = B.h_off[q.bread] + p.bepos; t.n = gA; t.m = gB; t.a0 = p.aepos;
+        t.comp = (q.flags & DN_LAS_COMP) ? 1 : 0;
+        t.nrow = (p.aepos + gA) / ts - p.aepos / ts;                       // multiples of ts in (aepos, aepos + gA]
+        t.row_off = nrows; nrows += t.nrow;
+        tasks.push_back(t);
+    }
+    if (tasks.empty()) return DN_OK;
+    std::vector<int32_t> total(tasks.size()); std::vector<int2> rows((size_t)nrows + 1);
+    {
+        std::lock_guard<std::mutex> lk(g_mu);
+        if (int rc = ensure_device()) return rc;
+        int rc = guarded([&]() -> int {
+            cudaSetDevice(g_device); arena().reset();
+            cudaStream_t s = g_stream;
+            DBuf<BridgeTask> dt; to_device(dt, tasks.data(), tasks.size(), s);
+            DBuf<int32_t> dtot(tasks.size()); DBuf<int2> drows((size_t)nrows + 1);
+            DBuf<u32> scratch((size_t)cons_vote_threads() * 2048);
+            launch_bridge(dt.p, (int64_t)tasks.size(), A.fwd.p, B.fwd.p, B.rc.p, ts, scratch.p, dtot.p, drows.p, s);
+            DN_CUDA(cudaMemcpyAsync(total.data(), dtot.p, sizeof(int32_t) * tasks.size(), cudaMemcpyDeviceToHost, s));
+            if (nrows) DN_CUDA(cudaMemcpyAsync(rows.data(), drows.p, sizeof(int2) * (size_t)nrows, cudaMemcpyDeviceToHost, s));
+            DN_CUDA(cudaStreamSynchronize(s));
+            return DN_OK;
+        });
+        if (rc) return rc;
+    }
+    return guarded([&]() -> int {
+        // host: records and traces re-assembled (orc_bridge's fold)
+        dn_las_record *orec = (dn_las_record *)hcache_alloc(sizeof(dn_las_record) * (size_t)(n + 1));
+        int64_t *otoff = (int64_t *)hcache_alloc(sizeof(int64_t) * (size_t)(n + 1));
+        uint16_t *otr = (uint16_t *)hcache_alloc(sizeof(uint16_t) * (size_t)(las->ntrace + 2 * (nrows + (int64_t)tasks.size()) + 2));
+        int64_t no = 0, to = 0; size_t ti = 0; bool open = false;
+        for (int64_t r = 0; r < n; r++) {
+            const dn_las_record &q = las->rec[r];
+            const uint16_t *tq = las->trace + las->toff[r];
+            const int ntq = q.tlen / 2;
+            if (!br[r]) {
+                orec[no] = q; otoff[no] = to;
+                for (int t = 0; t < 2 * ntq; t++) otr[to++] = tq[t];
+                open = q.aepos % ts != 0; no++;
+                continue;
+            }
+            const BridgeTask &T = tasks[ti]; const int tot = total[ti]; ti++;
+            int pj = 0, pd = 0;
+            for (int k = 0; k <= T.nrow; k++) {
+                const int ej = k < T.nrow ? rows[T.row_off + k].x : T.m, ed = k < T.nrow ? rows[T.row_off + k].y : tot;
+                const int dd = ed - pd, bb = ej - pj;
+                if (k < T.nrow || dd > 0 || bb > 0) {
+                    if (open) { otr[to - 2] = (uint16_t)(otr[to - 2] + dd); otr[to - 1] = (uint16_t)(otr[to - 1] + bb); }
+                    else { otr[to++] = (uint16_t)dd; otr[to++] = (uint16_t)bb; open = true; }
+                    if (k < T.nrow) open = false;
+                }
+                pj = ej; pd = ed;
+            }
+            for (int t = 0; t < ntq; t++) {
+                if (t == 0 && open) { otr[to - 2] = (uint16_t)(otr[to - 2] + tq[0]); otr[to - 1] = (uint16_t)(otr[to - 1] + tq[1]); }
+                else { otr[to++] = tq[2 * t]; otr[to++] = tq[2 * t + 1]; }
+            }
+            open = q.aepos % ts != 0;
+            dn_las_record &o = orec[no - 1];
+            o.aepos = q.aepos; o.bepos = q.bepos; o.diffs += tot + q.diffs; o.tlen = (int32_t)(to - otoff[no - 1]);
+        }
+        hcache_free(las->rec); hcache_free(las->toff); hcache_free(las->trace);
+        las->rec = orec; las->toff = otoff; las->trace = otr; las->nrec = no; las->ntrace = to;
+        if (nbridged) *nbridged = (int64_t)tasks.size();
+        return DN_OK;
+    });
+}
+
 int dn_las_transpose(const dn_block *a, const dn_block *b, const dn_las_buf *las, dn_las_buf *out) {
     if (!a || !b || !las || !out) return fail(DN_ERR_INVALID, "null argument");
     const DevBlock &A = a->b, &B = b->b;

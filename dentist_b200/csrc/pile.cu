@@ -249,6 +249,71 @@ __global__ void __launch_bounds__(128) k_cons_vote_bv(const ConsTask *__restrict
     }
 }
 
+// `daligner -B` bridges (specification: oracle/pile_oracle.c, orc_bridge): thread per bridge, the same bit-parallel DP over
+// A[P.aepos, Q.abpos) x B[P.bepos, Q.bbpos); the traceback records, for every multiple of ts of A inside the bridge, the
+// B column and the cost at the path's FIRST cell on that row (the cell it leaves the row from, walking backwards).
+__global__ void __launch_bounds__(128) k_bridge(const BridgeTask *__restrict__ tasks, int64_t ntasks, const u32 *__restrict__ a_fwd,
+                                                const u32 *__restrict__ b_fwd, const u32 *__restrict__ b_rc, int ts,
+                                                u32 *__restrict__ scratch, int32_t *__restrict__ total, int2 *__restrict__ rows) {
+    const int64_t nthreads = (int64_t)gridDim.x * blockDim.x;
+    const int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    unsigned long long *cols = (unsigned long long *)scratch + tid;
+    for (int64_t task = tid; task < ntasks; task += nthreads) {
+        const BridgeTask T = tasks[task];
+        const int n = T.n, m = T.m;
+        const u32 *Aw = a_fwd, *Bw = T.comp ? b_rc : b_fwd;
+        const int64_t ga = T.ga, gb = T.gb;
+        U128 P0{0, 0}, P1{0, 0}, P2{0, 0}, P3{0, 0};
+        for (int i = 0; i < n; i++) {
+            const int a = base_at(Aw, ga + i);
+            const unsigned long long bl = i < 64 ? 1ull << i : 0ull, bh = i < 64 ? 0ull : 1ull << (i - 64);
+            if (a == 0) { P0.lo |= bl; P0.hi |= bh; } else if (a == 1) { P1.lo |= bl; P1.hi |= bh; }
+            else if (a == 2) { P2.lo |= bl; P2.hi |= bh; } else { P3.lo |= bl; P3.hi |= bh; }
+        }
+        U128 VP{~0ull, ~0ull}, VN{0, 0};
+        for (int j = 1; j <= m; j++) {
+            const int b = base_at(Bw, gb + j - 1);
+            const U128 Eq = b == 0 ? P0 : (b == 1 ? P1 : (b == 2 ? P2 : P3));
+            const U128 D0 = u_or(u_or(u_xor(u_add(u_and(Eq, VP), VP), VP), Eq), VN);
+            const U128 HP = u_or(VN, u_not(u_or(D0, VP))), HN = u_and(D0, VP);
+            U128 X = u_shl1(HP); X.lo |= 1ull;
+            VP = u_or(u_shl1(HN), u_not(u_or(D0, X))); VN = u_and(D0, X);
+            unsigned long long *c = cols + (int64_t)((j - 1) * 4) * nthreads;
+            c[0] = VP.lo; c[nthreads] = VP.hi; c[2 * nthreads] = VN.lo; c[3 * nthreads] = VN.hi;
+        }
+        auto column = [&](int j, U128 &vp, U128 &vn) {
+            if (j == 0) { vp = U128{~0ull, ~0ull}; vn = U128{0, 0}; return; }
+            const unsigned long long *c = cols + (int64_t)((j - 1) * 4) * nthreads;
+            vp = U128{c[0], c[nthreads]}; vn = U128{c[2 * nthreads], c[3 * nthreads]};
+        };
+        int i = n, j = m, k = T.nrow;
+        U128 vpj, vnj; column(m, vpj, vnj);
+        int c0 = m + u_popc_low(vpj, n) - u_popc_low(vnj, n);
+        total[task] = c0;
+        while (i > 0 || j > 0) {
+            u32 dir; int nc0 = 0;
+            U128 vpl, vnl;
+            if (i == 0) { dir = 2u; nc0 = j - 1; column(j - 1, vpl, vnl); }
+            else if (j == 0) { dir = 1u; nc0 = i - 1; }
+            else {
+                column(j - 1, vpl, vnl);
+                const int up = c0 - (u_bit(vpj, i - 1) - u_bit(vnj, i - 1));
+                const int left = (j - 1) + u_popc_low(vpl, i) - u_popc_low(vnl, i);
+                const int dg = left - (u_bit(vpl, i - 1) - u_bit(vnl, i - 1));
+                const int d = dg + (base_at(Aw, ga + i - 1) != base_at(Bw, gb + j - 1)), u = up + 1, l = left + 1;
+                int v = d; if (u < v) v = u; if (l < v) v = l;
+                dir = (v == d) ? 0u : ((v == u) ? 1u : 2u);
+                nc0 = dir == 0u ? dg : (dir == 1u ? up : left);
+            }
+            if (dir != 2u && (T.a0 + i) % ts == 0) { k--; rows[T.row_off + k] = make_int2(j, c0); }
+            if (dir == 0u) { i--; j--; vpj = vpl; vnj = vnl; }
+            else if (dir == 1u) i--;
+            else { j--; vpj = vpl; vnj = vnl; }
+            c0 = nc0;
+        }
+    }
+}
+
 // thread per vote column (targets concatenated, L+1 columns each): how many symbols does it emit?
 __global__ void __launch_bounds__(256) k_cons_count(ConsGeom G, const int32_t *__restrict__ targets, int ntargets, int64_t ncols,
                                                     const int32_t *__restrict__ cnt, const int32_t *__restrict__ ins,
@@ -448,6 +513,10 @@ void launch_cons_tasks(const dn_las_record *rec, const int64_t *toff, const uint
     DN_LAUNCH(k_cons_tasks, (nvla + 255) / 256, 256, 0, s, rec, toff, trace, vla, nvla, task_off, ts, tasks);
 }
 int cons_vote_threads() { return sm_count() * 4 * 128; }
+void launch_bridge(const BridgeTask *tasks, int64_t ntasks, const u32 *a_fwd, const u32 *b_fwd, const u32 *b_rc, int ts, u32 *scratch,
+                   int32_t *total, int2 *rows, cudaStream_t s) {
+    DN_LAUNCH(k_bridge, sm_count() * 4, 128, 0, s, tasks, ntasks, a_fwd, b_fwd, b_rc, ts, scratch, total, rows);
+}
 void launch_cons_vote(const ConsTask *tasks, int64_t ntasks, const dn_las_record *rec, const int32_t *la_target, ConsGeom G,
                       u32 *scratch, int32_t *cnt, int32_t *ins, int32_t *insn, int32_t *cov, cudaStream_t s) {
     static const bool cell_dp = getenv("DN_CONS_CELL_DP") != nullptr;         // the thread-per-cell-row DP the bit-parallel kernel replaced

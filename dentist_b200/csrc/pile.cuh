@@ -10,6 +10,12 @@ struct ConsGeom {
     const int64_t *vote_off;      // [ntargets+1] first vote column of each target read (L+1 columns each)
 };
 
+// `daligner -B` bridge between two neighbouring records: rows = A[ga, ga + n), columns = B[gb, gb + m) of the strand array,
+// a0 = A coordinate of row 0 (for the trace-point grid), nrow grid rows in (0, n] whose crossings go to rows[row_off ...]
+struct BridgeTask { int64_t ga, gb; int32_t n, m, a0, comp, nrow; int64_t row_off; };
+void launch_bridge(const BridgeTask *tasks, int64_t ntasks, const u32 *a_fwd, const u32 *b_fwd, const u32 *b_rc, int ts, u32 *scratch /* cons_vote_threads() * 2048 */,
+                   int32_t *total, int2 *rows, cudaStream_t s);
+
 // transposition (damapper -C): A and B blocks of the alignment
 struct TrGeom { const u32 *a_fwd, *b_fwd, *b_rc; const int64_t *a_off, *b_off; const int32_t *a_len, *b_len; };
 void launch_tr_tiles(const ConsTask *tasks, int64_t ntasks, const dn_las_record *rec, const int64_t *toff, const uint16_t *trace,

@@ -313,6 +313,14 @@ class Las:
         self._refresh()
         return self
 
+    def bridge(self, a, b, e=0.7):
+        """`daligner -B` (dazzler.d:5823-5824): neighbouring records separated by a short gap become one.  Returns the
+        number of bridges made."""
+        nb = C.c_int64(0)
+        _lib.check(_lib.lib().dn_las_bridge(a._h, b._h, C.byref(self._buf), int(round(6.0 / (1.0 - e))), C.byref(nb)))
+        self._refresh()
+        return int(nb.value)
+
     def transpose(self, a, b):
         """`damapper -C`'s second file (dazzler.d:5931-5936): the records of B.A.las for these records of A.B.las."""
         buf = _lib.LasBuf()

@@ -70,7 +70,7 @@ def process_pileups_batch(piles, ref=None, **params):
 
 
 def process_pileups(reads, group, max_alignment_error=0.3, flanks=None, allowed=None, dust=False, candidates=False,
-                    min_anchor_length=MIN_ANCHOR, proper_alignment_allowance=TSPACE):
+                    min_anchor_length=MIN_ANCHOR, proper_alignment_allowance=TSPACE, bridge=True):
     """The same path STEP BY STEP through the per-stage entry points (what a D host that keeps processPileUp's
     structure would call; tests assert it equals dn_process_pileups byte for byte).
     reads: synth.Block-like (off, bases) of all cropped reads; group: pile id per read.
@@ -85,6 +85,8 @@ def process_pileups(reads, group, max_alignment_error=0.3, flanks=None, allowed=
         g.maskDust()                                                     # dbdust(croppedDb) + -mdust, package.d:476-481
     # daligner -T<n> -B -s126 -l500 -e0.7 -mdust X X   (pileUpAlignmentOptions, commandline.d:2886-2902)
     las = dazzler.align(g, g, tspace=TSPACE, minlen=min_anchor_length, e=1.0 - max_alignment_error, self_block=1)
+    if bridge:
+        las.bridge(g, g, e=1.0 - max_alignment_error)                    # -B
     las.filterLocalAlignments(max_alignment_error)                      # package.d:483-485
     status = np.zeros(npiles, np.int32)
     status[np.bincount(group[las.rec["aread"]], minlength=npiles) == 0] = 1     # "empty pileup alignment", package.d:487-490 (per pile-up)
@@ -128,6 +130,8 @@ def process_pileups(reads, group, max_alignment_error=0.3, flanks=None, allowed=
                            group=None if not getattr(flanks, "has_group", False) else np.arange(npiles, dtype=np.int32))
         fb = flanks if isinstance(flanks, dazzler.Block) else dazzler.Block(flanks.off, flanks.bases)
         out["flank_las"] = dazzler.align(fb, cb, tspace=TSPACE, minlen=TSPACE, e=0.7)
+        if bridge:
+            out["flank_las"].bridge(fb, cb, e=0.7)                       # -B
     g.free()
     return out
 

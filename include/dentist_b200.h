@@ -258,6 +258,7 @@ typedef struct dn_pileup_params {
     double max_rel_overlap, min_rel_score; /* 0.3, 1.0 */
     int32_t min_score;                   /* 0 = tspace */
     int32_t k, flank_k;                  /* 14, 14: daligner's -k for the pile / flank alignments */
+    int32_t bridge;                      /* 1: -B of both alignments (commandline.d:2886-2902, 2918-2935), see dn_las_bridge */
 } dn_pileup_params;
 void dn_pileup_params_default(dn_pileup_params *p);
 
@@ -300,6 +301,14 @@ int dn_las_chain_mapper(dn_las_buf *las, int32_t nb_reads, int32_t max_indel, in
  * B.A.las in LAsort order: coordinates mirrored (complemented alignments: each read in its own frame), trace points
  * re-laid every tspace bases of the new A read along the per-tile alignment path, chain flags cleared. */
 int dn_las_transpose(const dn_block *a, const dn_block *b, const dn_las_buf *las, dn_las_buf *out);
+
+/* What `daligner -B` adds (dazzler.d:5823-5824, "bridge consecutive aligned segments into one if possible"; DENTIST passes
+ * it for the pile and the flank alignments, commandline.d:2886-2902, 2918-2935): neighbouring records of one (aread, bread,
+ * comp) whose gap is short (<= 128 A bases, <= 250 B bases, diagonal drift within the error budget) become one record; the
+ * bridge is a unit-cost global alignment of the gap, the trace points of the merged record follow the concatenated path.
+ * `las` in LAsort order with traces, a / b = the resident blocks; cdiff = round(6 / (1 - e)) (20 at -e0.7).  In place;
+ * *nbridged (may be NULL) = bridges made.  DALIGNER's own rule is not in the reference: specification in oracle/. */
+int dn_las_bridge(const dn_block *a, const dn_block *b, dn_las_buf *las, int32_t cdiff, int64_t *nbridged);
 
 /* What damapper reports: per mapped read its best chain and, with -n<f>, every chain scoring at least the fraction f of
  * the best (dazzler.d:5920-5923).  n_frac <= 0: the BEST chains only (DENTIST passes no -n, commandline.d:2943-2955).

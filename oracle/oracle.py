@@ -169,3 +169,21 @@ def transpose(a_off, a_bases, b_off, b_bases, rec, toff, trace, tspace):
     f(_p(a_off), _p(a_bases), _p(b_off), _p(b_bases), _p(r), len(r), _p(toff), _p(trace), int(tspace), _p(out), _p(otoff), _p(otr))
     assert np.array_equal(out["tlen"], 2 * nt2)
     return out, otoff, otr[:int(2 * nt2.sum())]
+
+
+def bridge(a_off, a_bases, b_off, b_bases, rec, toff, trace, tspace, cdiff=20):
+    """orc_bridge (`daligner -B`): neighbouring records of one (aread, bread, comp) separated by a short gap become one.
+    rec in LAsort order.  Returns (records LAS40, toff, trace, number of bridges)."""
+    a_off = np.ascontiguousarray(a_off, np.int64); a_bases = np.ascontiguousarray(a_bases, np.uint8)
+    b_off = np.ascontiguousarray(b_off, np.int64); b_bases = np.ascontiguousarray(b_bases, np.uint8)
+    r = _las40(rec); toff = np.ascontiguousarray(toff, np.int64); trace = np.ascontiguousarray(trace, np.uint16)
+    out = np.zeros(len(r) + 1, LAS40); otoff = np.zeros(len(r) + 1, np.int64)
+    otr = np.zeros(int(r["tlen"].sum()) + 2 * len(r) * (128 // int(tspace) + 2) + 2, np.uint16)
+    nb = C.c_int64(0)
+    f = lib().orc_bridge
+    f.restype = C.c_int64
+    f.argtypes = [C.c_void_p] * 5 + [C.c_int64, C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+    n = f(_p(a_off), _p(a_bases), _p(b_off), _p(b_bases), _p(r), len(r), _p(toff), _p(trace), int(tspace), int(cdiff),
+          _p(out), _p(otoff), _p(otr), C.byref(nb))
+    out = out[:n]; otoff = otoff[:n]
+    return out, otoff, otr[:int(out["tlen"].sum())], int(nb.value)

@@ -325,3 +325,114 @@ void orc_transpose(const int64_t *aoff, const uint8_t *abases, const int64_t *bo
     }
     free(brc);
 }
+
+/* ---- bridging: what `daligner -B` adds (dazzler.d:5823-5824; DENTIST passes it for pile and flank alignments,
+ * commandline.d:2886-2902, 2918-2935).  PARITY UNPINNED: DALIGNER's bridging rule is neither in the reference nor
+ * documented there; this is an own deterministic specification of "bridge consecutive aligned segments into one if
+ * possible".
+ *   Records are in LAsort order.  Inside a run of records of one (aread, bread, comp), neighbours P, Q (in file order)
+ *   bridge iff  gA = Q.abpos - P.aepos and gB = Q.bbpos - P.bepos satisfy 0 <= gA <= 128, 0 <= gB <= 250 and
+ *   |gA - gB| * cdiff <= max(16 * cdiff, 6 * max(gA, gB))      (cdiff = round(6 / (1 - e)): the diagonal may drift by
+ *   the alignment's own error budget, at least 16).  The test uses the ORIGINAL neighbours, so a run of bridges folds
+ *   into one record.  The bridge is the unit-cost global alignment of A[P.aepos, Q.abpos) with B[P.bepos, Q.bbpos),
+ *   traceback from the end preferring diagonal, then "A base unmatched", then "B base inserted" (as in the consensus).
+ *   Merged record: P's begin, Q's end, diffs = sum of both + the bridge's cost, P's flags.  Trace: the concatenated path
+ *   cut at the multiples of ts of A where it FIRST reaches them -- P's tiles, the bridge's pieces, Q's tiles, pieces
+ *   that share a tile added up.
+ * out / out_toff need nla entries, out_trace the input's trace length + 2 * (number of bridges) * (128 / ts + 2).
+ * Returns the number of output records; *nbridged = bridges made. */
+static void bridge_path(const uint8_t *a, int n, const uint8_t *b, int m, int a0 /* A coordinate of row 0 */, int ts,
+                        int *nrow, int *row_j, int *row_d, int *total)
+{
+    /* rows r in (0, n] with (a0 + r) % ts == 0, increasing: column and cost at the first arrival on the row */
+    static __thread uint8_t D[128 + 1][256];
+    for (int j = 0; j <= m; j++) D[0][j] = (uint8_t)j;
+    for (int i = 1; i <= n; i++) {
+        D[i][0] = (uint8_t)i;
+        for (int j = 1; j <= m; j++) {
+            int d = D[i - 1][j - 1] + (a[i - 1] != b[j - 1]);
+            int u = D[i - 1][j] + 1, l = D[i][j - 1] + 1;
+            int v = d; if (u < v) v = u; if (l < v) v = l;
+            D[i][j] = (uint8_t)v;
+        }
+    }
+    *total = D[n][m];
+    int cnt = 0;
+    for (int r = 1; r <= n; r++) if ((a0 + r) % ts == 0) cnt++;
+    *nrow = cnt;
+    int i = n, j = m, k = cnt;
+    while (i > 0 || j > 0) {
+        int dir;
+        if (i > 0 && j > 0 && D[i][j] == D[i - 1][j - 1] + (a[i - 1] != b[j - 1])) dir = 0;
+        else if (i > 0 && D[i][j] == D[i - 1][j] + 1) dir = 1;
+        else dir = 2;
+        if (dir != 2 && (a0 + i) % ts == 0) { k--; row_j[k] = j; row_d[k] = D[i][j]; }   /* leaving row i upwards: its first cell */
+        if (dir == 0) { i--; j--; } else if (dir == 1) i--; else j--;
+    }
+}
+
+int64_t orc_bridge(const int64_t *aoff, const uint8_t *abases, const int64_t *boff, const uint8_t *bbases,
+                   const las_rec *la, int64_t nla, const int64_t *toff, const uint16_t *trace, int32_t ts, int32_t cdiff,
+                   las_rec *out, int64_t *out_toff, uint16_t *out_trace, int64_t *nbridged)
+{
+    int64_t no = 0, to = 0, nb = 0;
+    uint8_t *brc = NULL; int brc_cap = 0;
+    int open = 0;                                   /* the last tile written still takes pieces (does not end on the grid) */
+    for (int64_t r = 0; r < nla; r++) {
+        const las_rec *q = &la[r];
+        int bridged = 0;
+        if (r > 0) {
+            const las_rec *p = &la[r - 1];
+            const int gA = q->abpos - p->aepos, gB = q->bbpos - p->bepos;
+            const int dg = gA > gB ? gA - gB : gB - gA, mx = gA > gB ? gA : gB;
+            const int lim = 16 * cdiff > 6 * mx ? 16 * cdiff : 6 * mx;
+            if (p->aread == q->aread && p->bread == q->bread && ((p->flags ^ q->flags) & 1u) == 0 &&
+                gA >= 0 && gA <= 128 && gB >= 0 && gB <= 250 && dg * cdiff <= lim) bridged = 1;
+        }
+        const uint16_t *tq = trace + toff[r];
+        const int ntq = q->tlen / 2;
+        if (!bridged) {
+            out[no] = *q; out_toff[no] = to;
+            for (int t = 0; t < 2 * ntq; t++) out_trace[to++] = tq[t];
+            open = q->aepos % ts != 0;
+            no++;
+            continue;
+        }
+        nb++;
+        las_rec *o = &out[no - 1];
+        const las_rec *p = &la[r - 1];
+        const int LB = (int)(boff[q->bread + 1] - boff[q->bread]);
+        const uint8_t *A = abases + aoff[q->aread], *B = bbases + boff[q->bread];
+        if (q->flags & 1u) {
+            if (LB > brc_cap) { brc = realloc(brc, LB + 1); brc_cap = LB; }
+            for (int i = 0; i < LB; i++) brc[i] = 3 - B[LB - 1 - i];
+            B = brc;
+        }
+        const int gA = q->abpos - p->aepos, gB = q->bbpos - p->bepos;
+        int nrow = 0, row_j[130], row_d[130], total = 0;
+        bridge_path(A + p->aepos, gA, B + p->bepos, gB, p->aepos, ts, &nrow, row_j, row_d, &total);
+        /* pieces of the bridge: up to each grid row, then the rest up to (gA, gB) */
+        int pj = 0, pd = 0;
+        for (int k = 0; k <= nrow; k++) {
+            const int ej = k < nrow ? row_j[k] : gB, ed = k < nrow ? row_d[k] : total;
+            const int dd = ed - pd, bb = ej - pj;
+            if (k < nrow || dd > 0 || bb > 0) {     /* the last piece is empty when the path ends with its arrival on a grid row */
+                if (open) { out_trace[to - 2] += (uint16_t)dd; out_trace[to - 1] += (uint16_t)bb; }
+                else { out_trace[to++] = (uint16_t)dd; out_trace[to++] = (uint16_t)bb; open = 1; }
+                if (k < nrow) open = 0;             /* the piece ends on the grid: the tile is complete */
+            }
+            pj = ej; pd = ed;
+        }
+        /* Q's tiles: the first joins an open tile */
+        for (int t = 0; t < ntq; t++) {
+            if (t == 0 && open) { out_trace[to - 2] += tq[0]; out_trace[to - 1] += tq[1]; }
+            else { out_trace[to++] = tq[2 * t]; out_trace[to++] = tq[2 * t + 1]; }
+        }
+        open = q->aepos % ts != 0;
+        o->aepos = q->aepos; o->bepos = q->bepos; o->diffs += total + q->diffs;
+        o->tlen = (int32_t)(to - out_toff[no - 1]);
+    }
+    free(brc);
+    if (nbridged) *nbridged = nb;
+    return no;
+}

@@ -76,6 +76,7 @@ def test_getDalignment_pile_with_dust_mask(tmp_path):
         for b, e in mask[r]:
             m[pile.off[r] + b:pile.off[r] + e] = 1
     la, tr, _ = oracle.align(pile.off, pile.bases, pile.off, pile.bases, a_mask=m, b_mask=m, tspace=126, minlen=500, self=1)
+    la, _, tr, _ = oracle.bridge(pile.off, pile.bases, pile.off, pile.bases, la, la["toff"].astype(np.int64), tr, 126)      # -B
     assert len(la) == len(rec) > 50
     for f in ("aread", "bread", "abpos", "aepos", "bbpos", "bepos", "diffs", "flags"):
         assert np.array_equal(rec[f], la[f]), f

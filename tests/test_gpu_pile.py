@@ -400,3 +400,39 @@ def test_transposed_las_matches_oracle():
             assert np.array_equal(back.rec[f], las.rec[f]), f
     empty = dazzler.align(ga, gb, tspace=100, minlen=10 ** 6).transpose(ga, gb)
     assert len(empty) == 0
+
+
+def test_bridging_matches_oracle():
+    """`daligner -B` (dazzler.d:5823-5824) as dn_las_bridge: reads with a stretch of junk break their alignments in two; the
+    bridged LAS equals the oracle's (records, diffs, every trace point) and keeps the trace invariants."""
+    from dentist_b200 import dazzler
+    from oracle import las as olas, oracle
+    for ts, seed in ((126, 301), (100, 302), (40, 303)):
+        blk = _pile(seed, cov=8)
+        rng = np.random.default_rng(seed)
+        bases = blk.bases.copy()
+        for r in range(0, blk.nreads, 2):                              # junk in the middle of every second read
+            L = int(blk.off[r + 1] - blk.off[r])
+            if L > 3000:
+                s = int(blk.off[r]) + L // 2
+                n = int(rng.integers(20, 110))
+                bases[s:s + n] = rng.integers(0, 4, n)
+        blk = synth.Block(blk.off, bases)
+        g, las = _gpu_las(blk, ts, 500)
+        rec0, toff0, tr0 = las.rec.copy(), las.toff.copy(), las.trace.copy()
+        exp, etoff, etr, enb = oracle.bridge(blk.off, blk.bases, blk.off, blk.bases, rec0, toff0, tr0, ts)
+        nb = las.bridge(g, g)
+        assert nb == enb > 10 and len(las) == len(exp) == len(rec0) - nb
+        for f in ("aread", "bread", "abpos", "aepos", "bbpos", "bepos", "diffs", "tlen", "flags"):
+            assert np.array_equal(las.rec[f], exp[f]), f
+        got_tr = np.concatenate([las.trace[int(o):int(o) + int(t)] for o, t in zip(las.toff, las.rec["tlen"])])
+        assert np.array_equal(got_tr, etr)
+        for x, o in zip(las.rec, las.toff):
+            t = las.trace[int(o):int(o) + int(x["tlen"])].reshape(-1, 2)
+            assert len(t) == olas.num_tiles(int(x["abpos"]), int(x["aepos"]), ts)
+            assert int(t[:, 1].sum()) == x["bepos"] - x["bbpos"] and int(t[:, 0].sum()) == x["diffs"]
+        # bridging an LAS without bridgeable neighbours changes nothing
+        again = las.bridge(g, g)
+        rest = oracle.bridge(blk.off, blk.bases, blk.off, blk.bases, las.rec.copy(), las.toff.copy(), las.trace.copy(), ts)[3]
+        assert again == rest
+        g.free()

@@ -133,3 +133,82 @@ def test_transposed_las_keeps_the_data_model_invariants():
     back, btoff, btr = oracle.transpose(reads.off, reads.bases, ref.off, ref.bases, t, ttoff, ttr, 100)
     for f in ("aread", "bread", "abpos", "aepos", "bbpos", "bepos"):
         assert np.array_equal(back[f], la[f]), f
+
+
+def _edit_path(a, b):
+    """unit-cost global alignment, traceback diagonal > A base unmatched > B base inserted: first column and cost on every row"""
+    n, m = len(a), len(b)
+    D = np.zeros((n + 1, m + 1), np.int32)
+    D[0, :] = np.arange(m + 1); D[:, 0] = np.arange(n + 1)
+    for i in range(1, n + 1):
+        for j in range(1, m + 1):
+            D[i, j] = min(D[i - 1, j - 1] + (a[i - 1] != b[j - 1]), D[i - 1, j] + 1, D[i, j - 1] + 1)
+    first = {}
+    i, j = n, m
+    while i > 0 or j > 0:
+        if i > 0 and j > 0 and D[i, j] == D[i - 1, j - 1] + (a[i - 1] != b[j - 1]):
+            first[i] = (j, int(D[i, j])); i -= 1; j -= 1
+        elif i > 0 and D[i, j] == D[i - 1, j] + 1:
+            first[i] = (j, int(D[i, j])); i -= 1
+        else:
+            j -= 1
+    return int(D[n, m]), first
+
+
+def test_bridging_by_hand():
+    """orc_bridge (`daligner -B`): two exact alignments either side of a junk stretch become one record whose tiles are the
+    pieces of the concatenated path; checked against an independent DP for three positions of the gap on the tile grid."""
+    rng = np.random.default_rng(11)
+    ts = 100
+    for p_end, gap_a, gap_b, q_len in ((300, 50, 45, 350), (270, 60, 71, 330), (250, 128, 120, 222), (300, 0, 7, 200), (233, 0, 0, 167)):
+        A = rng.integers(0, 4, p_end + gap_a + q_len).astype(np.uint8)
+        junk = rng.integers(0, 4, gap_b).astype(np.uint8)
+        B = np.concatenate([A[:p_end], junk, A[p_end + gap_a:]])
+        aoff = np.array([0, len(A)], np.int64); boff = np.array([0, len(B)], np.int64)
+
+        def exact(ab, ae, bb):
+            tiles, p = [], ab
+            while p < ae:
+                e = min((p // ts + 1) * ts, ae); tiles.append((0, e - p)); p = e
+            return dict(abpos=ab, aepos=ae, bbpos=bb, bepos=bb + (ae - ab), diffs=0, tlen=2 * len(tiles)), tiles
+        P, tp = exact(0, p_end, 0)
+        Q, tq = exact(p_end + gap_a, len(A), p_end + gap_b)
+        rec = np.zeros(2, oracle.LAS40)
+        for i, r in enumerate((P, Q)):
+            for f, v in r.items():
+                rec[i][f] = v
+        trace = np.array([x for t in tp + tq for x in t], np.uint16)
+        toff = np.array([0, 2 * len(tp)], np.int64)
+        out, otoff, otr, nb = oracle.bridge(aoff, A, boff, B, rec, toff, trace, ts)
+        assert nb == 1 and len(out) == 1
+        ed, first = _edit_path(A[p_end:p_end + gap_a], B[p_end:p_end + gap_b])
+        o = out[0]
+        assert (o["abpos"], o["aepos"], o["bbpos"], o["bepos"], o["diffs"]) == (0, len(A), 0, len(B), ed)
+        # expected tiles: cumulative (B offset, cost) of the whole path at every multiple of ts of A, first arrival
+        cum = []
+        for g in range(ts, len(A), ts):
+            if g <= p_end:
+                cum.append((g, 0))
+            elif g <= p_end + gap_a:
+                j, d = first[g - p_end]; cum.append((p_end + j, d))
+            else:
+                cum.append((g - gap_a + gap_b, ed))
+        cum.append((len(B), ed))
+        exp, pb, pd = [], 0, 0
+        for b, d in cum:
+            exp += [d - pd, b - pb]; pb, pd = b, d
+        assert otr.tolist() == exp and o["tlen"] == len(exp)
+    # no bridge: other strand, other read, overlapping or far-apart neighbours, too much diagonal drift
+    rec = np.zeros(2, oracle.LAS40)
+    base = dict(abpos=0, aepos=100, bbpos=0, bepos=100, diffs=0, tlen=2)
+    for i in range(2):
+        for f, v in base.items():
+            rec[i][f] = v
+    A = rng.integers(0, 4, 1000).astype(np.uint8); aoff = np.array([0, 1000], np.int64)
+    for ab, bb, flags in ((90, 90, 0), (100 + 129, 100 + 129, 0), (110, 100 + 251, 0), (150, 100, 0), (110, 110, 1)):
+        rec[1]["abpos"], rec[1]["aepos"], rec[1]["bbpos"], rec[1]["bepos"], rec[1]["flags"] = ab, ab + 100, bb, bb + 100, flags
+        tr = np.array([0, 100, 0, (ab // ts + 1) * ts - ab, 0, 100 - ((ab // ts + 1) * ts - ab)], np.uint16)
+        n2 = 2 if ab % ts else 1
+        rec[1]["tlen"] = 2 * n2
+        out, _, _, nb = oracle.bridge(aoff, A, aoff, A, rec, np.array([0, 2], np.int64), tr[:2 + 2 * n2], ts)
+        assert nb == 0 and len(out) == 2
