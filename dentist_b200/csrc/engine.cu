@@ -88,7 +88,8 @@ static int packed_pos_bits(int64_t nA, int k) {
 }
 
 static int index_tbits(int64_t nA, int k, bool lookup) {
-    int tbits = bits_for((uint64_t)nA) + (lookup ? -1 : 1);
+    static const int delta = getenv("DN_TBITS_DELTA") ? atoi(getenv("DN_TBITS_DELTA")) : 0;      // experiment: coarser / finer prefix table
+    int tbits = bits_for((uint64_t)nA) + (lookup ? -1 + delta : 1);
     if (tbits < 16) tbits = 16;
     if (tbits > 2 * k) tbits = 2 * k;
     return tbits;
@@ -253,8 +254,13 @@ void align_blocks(const DevBlock &A, const DevBlock &B, const AlignParams &P, Ho
         }
         // pin the k-mer filter in the persisting part of L2 while the streaming lookups run
         {
-            static bool limit_set = false;
-            if (!limit_set) { cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, 48u << 20); cudaGetLastError(); limit_set = true; }
+            // the set-aside comes out of the L2 every other access of the step shares (index walks, packed reads): it is sized
+            // by the filter itself, not by a fixed 48 MB
+            static size_t limit_set = 0;
+            static const size_t forced = getenv("DN_L2_PERSIST_MB") ? (size_t)atoi(getenv("DN_L2_PERSIST_MB")) << 20 : 0;
+            const size_t fbytes = kblog <= 28 ? ((size_t)1 << (kblog - 3)) : 0;
+            const size_t want = forced ? forced : std::min<size_t>(48u << 20, fbytes + (fbytes >> 3));
+            if (limit_set != want) { cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, want); cudaGetLastError(); limit_set = want; }
             cudaStreamAttrValue av; memset(&av, 0, sizeof av);
             av.accessPolicyWindow.base_ptr = (void *)kbits.p; av.accessPolicyWindow.num_bytes = kblog <= 28 ? ((size_t)1 << (kblog - 3)) : 0;   // only an L2-sized filter is pinned
             av.accessPolicyWindow.hitRatio = 1.0f; av.accessPolicyWindow.hitProp = cudaAccessPropertyPersisting;

@@ -762,7 +762,7 @@ __global__ void __launch_bounds__(256) k_lookup_emit_w(const u32 *__restrict__ s
     lookup_emit_body(seq, maskbits, off, len, c2r, nwords, k, Idx64{ta}, tbl, sh, tcap, hitmask, wcnt, woff, strand, G, hits, wlist);
 }
 
-__global__ void __launch_bounds__(256) k_lookup_emit_p(const u32 *__restrict__ seq, const u32 *__restrict__ maskbits,
+__global__ void __launch_bounds__(256, 6) k_lookup_emit_p(const u32 *__restrict__ seq, const u32 *__restrict__ maskbits,
                                                        const int64_t *__restrict__ off, const int32_t *__restrict__ len,
                                                        const int32_t *__restrict__ c2r, int64_t nwords, int k,
                                                        const u64 *__restrict__ ta, int pb, const u32 *__restrict__ tbl, int sh, int tcap,

@@ -1,12 +1,16 @@
 // seed.cuh -- shared structs between the seeding and extension stages.
 #pragma once
+#include <stdlib.h>
 #include "engine.cuh"
 
 namespace dn {
 
 // k-mer presence filter (blocked Bloom, 3 bits per k-mer): >= 12 bits per indexed position, 2^27 bits (16 MB, pinned in
 // L2) at least, 2^32 at most (a 100 Mbp reference block gets 2^31 bits = 256 MB; a 16 MB filter would be ~90 % full there)
-inline int kbits_log2_for(int64_t n_index) { int b = 27; while (b < 32 && (1ll << b) < 12 * n_index) b++; return b; }
+inline int kbits_log2_for(int64_t n_index) {
+    static const int per = getenv("DN_KBITS_PER") ? atoi(getenv("DN_KBITS_PER")) : 12;      // filter bits per indexed position (at least)
+    int b = 27; while (b < 32 && (1ll << b) < (long long)per * n_index) b++; return b;
+}
 
 struct Seed { int32_t a, bs, apos, bpos; };
 
