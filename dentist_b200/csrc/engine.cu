@@ -106,38 +106,53 @@ void block_build_index(DevBlock &A, int k, cudaStream_t s) {
     const int pb = packed_pos_bits(nA, k);
     DevBlock::Index &X = A.index;
     int64_t nI = nA;
+    bool bucketed = false;                                   // index built by bucket counting (bucket.cu): the table comes with it
+    auto table_geom = [&](int64_t n_index) {
+        X.tbits = index_tbits(n_index, k, true);
+        X.tbl.persistent(((size_t)1 << X.tbits) + 3);
+    };
     if (!wide) {
-        DBuf<u64> ta(nA), ta2(nA);
+        DBuf<u64> ta(nA), ta2;
         emit_tuples(A, false, k, 0u, ta.p, s);
-        u64 *sa = radix_sort_u64(ta.p, ta2.p, nA, 32, 32 + 2 * k + 1, s);
+        table_geom(nA);
         X.ta.persistent(nA);
-        DN_CUDA(cudaMemcpyAsync(X.ta.p, sa, sizeof(u64) * nA, cudaMemcpyDeviceToDevice, s));
+        bucketed = build_index_u64(ta.p, X.ta.p, nA, 32, 2 * k - X.tbits, 1u << X.tbits, X.tbl.p, s);
+        if (!bucketed) {
+            ta2.alloc(nA);
+            u64 *sa = radix_sort_u64(ta.p, ta2.p, nA, 32, 32 + 2 * k + 1, s);
+            DN_CUDA(cudaMemcpyAsync(X.ta.p, sa, sizeof(u64) * nA, cudaMemcpyDeviceToDevice, s));
+        }
     } else if (pb) {
-        DBuf<u64> tp(nA), tp2(nA);
+        DBuf<u64> tp(nA), tp2;
         nI = emit_tuples_wide(A, k, tp.p, pb, s);
-        u64 *sp = radix_sort_u64(tp.p, tp2.p, nI, pb, pb + 2 * k, s);
+        table_geom(nI);
         X.ta.persistent(nI + 1);
-        if (nI) DN_CUDA(cudaMemcpyAsync(X.ta.p, sp, sizeof(u64) * nI, cudaMemcpyDeviceToDevice, s));
+        bucketed = build_index_u64(tp.p, X.ta.p, nI, pb, 2 * k - X.tbits, 1u << X.tbits, X.tbl.p, s);
+        if (!bucketed) {
+            tp2.alloc(nA);
+            u64 *sp = radix_sort_u64(tp.p, tp2.p, nI, pb, pb + 2 * k, s);
+            if (nI) DN_CUDA(cudaMemcpyAsync(X.ta.p, sp, sizeof(u64) * nI, cudaMemcpyDeviceToDevice, s));
+        }
     } else {
         DBuf<ulonglong2> tw(nA), tw2(nA);
         nI = emit_tuples_wide(A, k, tw.p, 0, s);
+        table_geom(nI);
         ulonglong2 *sw = radix_sort_rec16(tw.p, tw2.p, nI, 0, 0, 2 * k, s);
         X.tw.persistent(nI + 1);
         if (nI) DN_CUDA(cudaMemcpyAsync(X.tw.p, sw, sizeof(ulonglong2) * nI, cudaMemcpyDeviceToDevice, s));
     }
     X.n = nI; X.pb = pb;
-    X.tbits = index_tbits(nI, k, true);
+    X.tbl_shift = bucketed ? 1 : 0;
     const int sh = 2 * k - X.tbits; const u32 nq = 1u << X.tbits;
-    X.tbl.persistent((size_t)nq + 2);
     X.kbits_log2 = kbits_log2_for(nI);
     const int kshift = 32 - (X.kbits_log2 - 5);
     X.kbits.persistent((size_t)1 << (X.kbits_log2 - 5)); X.kbits.zero(s);
-    X.tbl.zero(s);                                           // an index without entries: every range is empty
+    if (!bucketed) X.tbl.zero(s);                            // an index without entries: every range is empty
     if (!wide) {
-        DN_LAUNCH(k_prefix_table, (unsigned)((nI + 255) / 256), 256, 0, s, (const u64 *)X.ta.p, nI, sh, nq, X.tbl.p);
+        if (!bucketed) DN_LAUNCH(k_prefix_table, (unsigned)((nI + 255) / 256), 256, 0, s, (const u64 *)X.ta.p, nI, sh, nq, X.tbl.p);
         DN_LAUNCH(k_kmer_bitmap, (unsigned)((nI + 255) / 256), 256, 0, s, (const u64 *)X.ta.p, nI, k, kshift, X.kbits.p);
     } else if (nI > 0 && pb) {
-        DN_LAUNCH(k_prefix_table_p, (unsigned)((nI + 255) / 256), 256, 0, s, (const u64 *)X.ta.p, pb, nI, sh, nq, X.tbl.p);
+        if (!bucketed) DN_LAUNCH(k_prefix_table_p, (unsigned)((nI + 255) / 256), 256, 0, s, (const u64 *)X.ta.p, pb, nI, sh, nq, X.tbl.p);
         DN_LAUNCH(k_kmer_bitmap_p, (unsigned)((nI + 255) / 256), 256, 0, s, (const u64 *)X.ta.p, pb, nI, k, kshift, X.kbits.p);
     } else if (nI > 0) {
         DN_LAUNCH(k_prefix_table_w, (unsigned)((nI + 255) / 256), 256, 0, s, (const ulonglong2 *)X.tw.p, nI, sh, nq, X.tbl.p);
@@ -177,29 +192,49 @@ void align_blocks(const DevBlock &A, const DevBlock &B, const AlignParams &P, Ho
     const DevBlock::Index *cached = (A.index.valid && A.index.k == k && P.join_mode != 1) ? &A.index : nullptr;
     int64_t nI = nA;                                       // index entries: k > 15 keeps the valid positions only
     int pb = cached ? cached->pb : packed_pos_bits(nA, k);  // > 0: 8-byte packed entries kmer << pb | position (in `sa`)
-    if (cached) { sa = cached->ta.p; sw = cached->tw.p; nI = cached->n; }
+    const bool lookup = cached || wide || P.join_mode == 2 || (P.join_mode == 0 && nA * 8 <= (2ll << 30));   // auto: index lookup unless the A index is huge
+    DBuf<u32> tbl_own; const u32 *tblp = nullptr;
+    bool bucketed = false;                                 // index built by bucket counting (bucket.cu): the prefix table comes with it
+    int tbits = 0;
+    if (cached) { sa = cached->ta.p; sw = cached->tw.p; nI = cached->n; tbits = cached->tbits; tblp = cached->tbl.p + cached->tbl_shift; }
     else if (!wide) {
-        ta.alloc(nA); ta2.alloc(nA);
+        ta.alloc(nA);
         emit_tuples(A, false, k, 0u, ta.p, s);
-        sa = radix_sort_u64(ta.p, ta2.p, nA, 32, 32 + 2 * k + 1, s);
-        if (sa == ta.p) ta2.release(); else ta.release();
+        tbits = index_tbits(nA, k, lookup);
+        tbl_own.alloc(((size_t)1 << tbits) + 3);
+        if (lookup) { ta2.alloc(nA); bucketed = build_index_u64(ta.p, ta2.p, nA, 32, 2 * k - tbits, 1u << tbits, tbl_own.p, s); }
+        if (bucketed) { sa = ta2.p; ta.release(); }
+        else {
+            if (!ta2.p) ta2.alloc(nA);
+            sa = radix_sort_u64(ta.p, ta2.p, nA, 32, 32 + 2 * k + 1, s);
+            if (sa == ta.p) ta2.release(); else ta.release();
+        }
     } else if (pb) {
         ta.alloc(nA); ta2.alloc(nA);
         nI = emit_tuples_wide(A, k, ta.p, pb, s);
-        sa = radix_sort_u64(ta.p, ta2.p, nI, pb, pb + 2 * k, s);
-        if (sa == ta.p) ta2.release(); else ta.release();
+        tbits = index_tbits(nI, k, lookup);
+        tbl_own.alloc(((size_t)1 << tbits) + 3);
+        bucketed = build_index_u64(ta.p, ta2.p, nI, pb, 2 * k - tbits, 1u << tbits, tbl_own.p, s);
+        if (bucketed) { sa = ta2.p; ta.release(); }
+        else {
+            sa = radix_sort_u64(ta.p, ta2.p, nI, pb, pb + 2 * k, s);
+            if (sa == ta.p) ta2.release(); else ta.release();
+        }
     } else {
         tw.alloc(nA); tw2.alloc(nA);
         nI = emit_tuples_wide(A, k, tw.p, 0, s);
+        tbits = index_tbits(nI, k, lookup);
+        tbl_own.alloc(((size_t)1 << tbits) + 3);
         sw = radix_sort_rec16(tw.p, tw2.p, nI, 0, 0, 2 * k, s);
         if (sw == tw.p) tw2.release(); else tw.release();
     }
     const bool wide16 = wide && !pb;
     tr.mark("A tuples + sort");
-    const bool lookup = cached || wide || P.join_mode == 2 || (P.join_mode == 0 && nA * 8 <= (2ll << 30));   // auto: index lookup unless the A index is huge
     const int npass_t = (2 * k + (wide ? 0 : 1) + 7) / 8;
     out.stats.tuples_a = A.total_real; out.stats.tuples_b = 2 * B.total_real;
-    int64_t abytes = nA / 4 + (wide16 ? 16 : 8) * nA + (int64_t)npass_t * (wide16 ? 48 : 24) * nA;      // A: read packed, write tuples, sort passes (2R+1W)
+    int64_t abytes = nA / 4 + (wide16 ? 16 : 8) * nA;                                                   // A: read packed, write tuples
+    if (bucketed) abytes += 24 * nI + 12ll * ((int64_t)1 << tbits);                                       // count (1R), scatter (1R + 1W), table (zero, scan R + W)
+    else if (!cached) abytes += (int64_t)npass_t * (wide16 ? 32 : 16) * nI + (wide16 ? 16 : 8) * nI;      // one-sweep radix: histograms (1R) + passes (1R + 1W)
 
     // hit-key geometry
     const int64_t bandw = 1ll << P.w;
@@ -222,17 +257,15 @@ void align_blocks(const DevBlock &A, const DevBlock &B, const AlignParams &P, Ho
     bool segsorted = false, seg_in_hits2 = false;
     if (B.ready) DN_CUDA(cudaStreamWaitEvent(s, B.ready, 0));       // B may still be uploading on the copy stream (dn_align_host)
     // ---- K3: join ------------------------------------------------------------------------------
-    int tbits = index_tbits(nI, k, lookup);
-    if (cached) tbits = cached->tbits;
     const int sh = 2 * k - tbits; const u32 nq = 1u << tbits;
-    DBuf<u32> tbl_own; const u32 *tblp;
-    if (cached) tblp = cached->tbl.p;
-    else {
-        tbl_own.alloc((size_t)nq + 2); tblp = tbl_own.p;
-        if (!wide) DN_LAUNCH(k_prefix_table, (unsigned)((nA + 255) / 256), 256, 0, s, (const u64 *)sa, nA, sh, nq, tbl_own.p);
-        else if (nI > 0 && pb) DN_LAUNCH(k_prefix_table_p, (unsigned)((nI + 255) / 256), 256, 0, s, (const u64 *)sa, pb, nI, sh, nq, tbl_own.p);
-        else if (nI > 0) DN_LAUNCH(k_prefix_table_w, (unsigned)((nI + 255) / 256), 256, 0, s, (const ulonglong2 *)sw, nI, sh, nq, tbl_own.p);
-        else tbl_own.zero(s);                                // no valid k-mer in A: every range is empty
+    if (!cached) {
+        tblp = tbl_own.p + (bucketed ? 1 : 0);
+        if (!bucketed) {
+            if (!wide) DN_LAUNCH(k_prefix_table, (unsigned)((nA + 255) / 256), 256, 0, s, (const u64 *)sa, nA, sh, nq, tbl_own.p);
+            else if (nI > 0 && pb) DN_LAUNCH(k_prefix_table_p, (unsigned)((nI + 255) / 256), 256, 0, s, (const u64 *)sa, pb, nI, sh, nq, tbl_own.p);
+            else if (nI > 0) DN_LAUNCH(k_prefix_table_w, (unsigned)((nI + 255) / 256), 256, 0, s, (const ulonglong2 *)sw, nI, sh, nq, tbl_own.p);
+            else tbl_own.zero(s);                                // no valid k-mer in A: every range is empty
+        }
     }
     struct { const u32 *p; } tbl{tblp};
     DBuf<int64_t> dtotal(1);

@@ -40,6 +40,7 @@ struct DevBlock {
     // align_blocks otherwise rebuilds for the A block on every call.  Invalidated when the seed mask changes.
     struct Index {
         int k = 0, tbits = 0, kbits_log2 = 27;
+        int tbl_shift = 0;             // the prefix table starts at tbl.p + tbl_shift (1: built by bucket counting, bucket.cu)
         int pb = 0;                    // > 0: k > 15 with 8-byte packed entries kmer << pb | position in `ta`
         int64_t n = 0;                 // index entries (k > 15: valid positions only)
         DBuf<u64> ta; DBuf<ulonglong2> tw; DBuf<u32> tbl, kbits;

@@ -35,6 +35,8 @@ struct Cand {
 struct ExtOut { int32_t i_end, j_end, d_end, ntiles; };
 
 void emit_tuples(const DevBlock &B, bool rc, int k, u32 payload_base, u64 *out, cudaStream_t s);
+// bucket.cu: the ordered 8-byte index + its prefix table (C + 1, C = nq + 3 words) without a full sort; false = take the radix path
+bool build_index_u64(const u64 *tuples, u64 *out, int64_t n, int key_shift, int sh, u32 nq, u32 *C, cudaStream_t s);
 int64_t emit_tuples_wide(const DevBlock &B, int k, void *out, int pb, cudaStream_t s);   // k = 16..31: tuples of the valid forward positions (pb = 0: 16-byte {kmer, position}; pb > 0: 8-byte kmer << pb | position); returns their number
 
 // kernels defined in seed.cu
