@@ -39,10 +39,15 @@ struct BucketScan {
 // after the scan C[q + 2] = first slot of bucket q; every tuple takes the next slot of its bucket, which leaves
 // C[q + 2] = first slot of bucket q + 1, i.e. T = C + 1 is the prefix table: T[q] = begin, T[q + 1] = end of bucket q
 __global__ void __launch_bounds__(256) k_bucket_scatter(const u64 *__restrict__ t, int64_t n, BucketOf bk, u32 *__restrict__ C, u64 *__restrict__ out) {
-    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n) return;
-    const u64 v = __ldcs(t + i);
-    out[atomicAdd(&C[bk(v) + 2], 1u)] = v;
+    // four tuples per thread: the slot comes back from L2 (an atomic with a return value), so the four round trips overlap
+    const int64_t base = (int64_t)blockIdx.x * (blockDim.x * 4) + threadIdx.x;
+    u64 v[4]; u32 p[4];
+#pragma unroll
+    for (int x = 0; x < 4; x++) { const int64_t i = base + x * (int64_t)blockDim.x; if (i < n) v[x] = __ldcs(t + i); }
+#pragma unroll
+    for (int x = 0; x < 4; x++) { const int64_t i = base + x * (int64_t)blockDim.x; if (i < n) p[x] = atomicAdd(&C[bk(v[x]) + 2], 1u); }
+#pragma unroll
+    for (int x = 0; x < 4; x++) { const int64_t i = base + x * (int64_t)blockDim.x; if (i < n) out[p[x]] = v[x]; }
 }
 
 __global__ void __launch_bounds__(256) k_bucket_order(u64 *__restrict__ a, const u32 *__restrict__ T, u32 nq, u32 *__restrict__ biglist, u32 *__restrict__ nbig) {
@@ -100,7 +105,7 @@ bool build_index_u64(const u64 *t, u64 *out, int64_t n, int key_shift, int sh, u
     DN_CUDA(cudaMemcpyAsync(hs, stat.p, sizeof hs, cudaMemcpyDeviceToHost, s));
     DN_CUDA(cudaStreamSynchronize(s));
     if (hs[0] > 4096u) return false;
-    DN_LAUNCH(k_bucket_scatter, (unsigned)((n + 255) / 256), 256, 0, s, t, n, bk, C, out);
+    DN_LAUNCH(k_bucket_scatter, (unsigned)((n + 1023) / 1024), 256, 0, s, t, n, bk, C, out);
     DBuf<u32> biglist((size_t)hs[1] + 1), nbig(1); nbig.zero(s);
     DN_LAUNCH(k_bucket_order, (nq + 255) / 256, 256, 0, s, out, (const u32 *)(C + 1), nq, biglist.p, nbig.p);
     if (hs[1] > 0) DN_LAUNCH(k_bucket_order_big, hs[1], 256, 0, s, out, (const u32 *)(C + 1), (const u32 *)biglist.p);
