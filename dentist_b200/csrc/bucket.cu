@@ -58,11 +58,16 @@ __global__ void __launch_bounds__(256) k_bucket_order(u64 *__restrict__ a, const
     u64 *b = a + s;
     if (n == 2) { const u64 x = b[0], y = b[1]; if (y < x) { b[0] = y; b[1] = x; } return; }
     if (n > 32) { biglist[atomicAdd(nbig, 1u)] = q; return; }
+    // the bucket is read once (independent loads), ordered in thread-local storage (L1) and written back: an insertion sort
+    // on the global array itself is a chain of dependent L2 round trips
+    u64 v[32];
+    for (u32 i = 0; i < n; i++) v[i] = b[i];
     for (u32 i = 1; i < n; i++) {
-        const u64 x = b[i]; u32 j = i;
-        while (j > 0 && b[j - 1] > x) { b[j] = b[j - 1]; j--; }
-        b[j] = x;
+        const u64 x = v[i]; u32 j = i;
+        while (j > 0 && v[j - 1] > x) { v[j] = v[j - 1]; j--; }
+        v[j] = x;
     }
+    for (u32 i = 0; i < n; i++) b[i] = v[i];
 }
 
 // buckets of 33 .. 4096 tuples: one CTA each, bitonic sort in shared memory

@@ -10,31 +10,35 @@
 namespace dn {
 namespace {
 
+// thread per window over ALL windows of the block (woff = first window of each read): a block of few long reads (flanking
+// contigs) fills the GPU like one of many short reads
 __global__ void __launch_bounds__(256) k_dust_windows(const u32 *__restrict__ seq, const int64_t *__restrict__ off,
                                                       const int32_t *__restrict__ len, const int64_t *__restrict__ woff,
-                                                      int nreads, int w, int t10, uint8_t *__restrict__ flags) {
-    const int r = blockIdx.x;
+                                                      int nreads, int64_t nwin_total, int w, int t10, uint8_t *__restrict__ flags) {
+    const int64_t gw = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (gw >= nwin_total) return;
+    int lo = 0, hi = nreads;                                   // last read r with woff[r] <= gw (reads without windows share their successor's offset)
+    while (hi - lo > 1) { const int mid = (lo + hi) >> 1; if (woff[mid] <= gw) lo = mid; else hi = mid; }
+    const int r = lo;
     const int L = len[r], stride = w >> 1;
-    const int nwin = L > 0 ? (L + stride - 1) / stride : 0;
-    for (int q = threadIdx.x; q < nwin; q += blockDim.x) {
-        const int start = q * stride, n = min(w, L - start), l = n - 2;
-        uint8_t f = 0;
-        if (l >= 14) {
-            unsigned char c[64];
+    const int q = (int)(gw - woff[r]);
+    const int start = q * stride, n = min(w, L - start), l = n - 2;
+    uint8_t f = 0;
+    if (l >= 14) {
+        unsigned char c[64];
 #pragma unroll
-            for (int i = 0; i < 64; i++) c[i] = 0;
-            const int64_t g = off[r] + start;
-            int sum = 0, t = 0;
-            for (int i = 0; i < n; i++) {
-                const int64_t p = g + i;
-                const int b = (int)((seq[p >> 4] >> ((p & 15) << 1)) & 3u);
-                t = ((t << 2) | b) & 63;
-                if (i >= 2) { sum += c[t]; c[t]++; }           // sum_t c_t*(c_t-1)/2 accumulated incrementally
-            }
-            f = (10 * sum > t10 * (l - 1)) ? 1 : 0;
+        for (int i = 0; i < 64; i++) c[i] = 0;
+        const int64_t g = off[r] + start;
+        int sum = 0, t = 0;
+        for (int i = 0; i < n; i++) {
+            const int64_t p = g + i;
+            const int b = (int)((seq[p >> 4] >> ((p & 15) << 1)) & 3u);
+            t = ((t << 2) | b) & 63;
+            if (i >= 2) { sum += c[t]; c[t]++; }           // sum_t c_t*(c_t-1)/2 accumulated incrementally
         }
-        flags[woff[r] + q] = f;
+        f = (10 * sum > t10 * (l - 1)) ? 1 : 0;
     }
+    flags[gw] = f;
 }
 
 }  // namespace
@@ -54,8 +58,8 @@ static void dust_intervals(const DevBlock &B, int window, double threshold, int 
     if (nw > 0) {
         DBuf<int64_t> dw(B.nreads + 1); DBuf<uint8_t> df(nw);
         DN_CUDA(cudaMemcpyAsync(dw.p, woff.data(), sizeof(int64_t) * (B.nreads + 1), cudaMemcpyHostToDevice, g_stream));
-        DN_LAUNCH(k_dust_windows, B.nreads, 256, 0, g_stream, (const u32 *)B.fwd.p, (const int64_t *)B.off.p, (const int32_t *)B.len.p,
-                  (const int64_t *)dw.p, B.nreads, window, t10, df.p);
+        DN_LAUNCH(k_dust_windows, (unsigned)((nw + 255) / 256), 256, 0, g_stream, (const u32 *)B.fwd.p, (const int64_t *)B.off.p, (const int32_t *)B.len.p,
+                  (const int64_t *)dw.p, B.nreads, nw, window, t10, df.p);
         DN_CUDA(cudaMemcpyAsync(flags.data(), df.p, nw, cudaMemcpyDeviceToHost, g_stream));
         DN_CUDA(cudaStreamSynchronize(g_stream));
     }
