@@ -70,6 +70,7 @@ struct PinnedBuf {
 };
 
 int sm_count();
+size_t l2_persisting_bytes(size_t want);     // scan.cu: sizes the device's persisting-L2 set-aside for a window of `want` bytes; returns the bytes it can count on
 
 // ---- device primitives implemented in scan.cu / radix.cu ---------------------------------
 // exclusive prefix sum: out[i] = sum_{j<i} in[j]; returns total through *d_total (device, 1 elem) if non-null

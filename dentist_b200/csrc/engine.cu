@@ -287,15 +287,10 @@ void align_blocks(const DevBlock &A, const DevBlock &B, const AlignParams &P, Ho
         }
         // pin the k-mer filter in the persisting part of L2 while the streaming lookups run
         {
-            // the set-aside comes out of the L2 every other access of the step shares (index walks, packed reads): it is sized
-            // by the filter itself, not by a fixed 48 MB
-            static size_t limit_set = 0;
-            static const size_t forced = getenv("DN_L2_PERSIST_MB") ? (size_t)atoi(getenv("DN_L2_PERSIST_MB")) << 20 : 0;
-            const size_t fbytes = kblog <= 28 ? ((size_t)1 << (kblog - 3)) : 0;
-            const size_t want = forced ? forced : std::min<size_t>(48u << 20, fbytes + (fbytes >> 3));
-            if (limit_set != want) { cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, want); cudaGetLastError(); limit_set = want; }
+            const size_t fbytes = kblog <= 28 ? ((size_t)1 << (kblog - 3)) : 0;       // only an L2-sized filter is pinned
+            const size_t fset = l2_persisting_bytes(fbytes);
             cudaStreamAttrValue av; memset(&av, 0, sizeof av);
-            av.accessPolicyWindow.base_ptr = (void *)kbits.p; av.accessPolicyWindow.num_bytes = kblog <= 28 ? ((size_t)1 << (kblog - 3)) : 0;   // only an L2-sized filter is pinned
+            av.accessPolicyWindow.base_ptr = (void *)kbits.p; av.accessPolicyWindow.num_bytes = fset >= fbytes ? fbytes : 0;
             av.accessPolicyWindow.hitRatio = 1.0f; av.accessPolicyWindow.hitProp = cudaAccessPropertyPersisting;
             av.accessPolicyWindow.missProp = cudaAccessPropertyStreaming;
             cudaStreamSetAttribute(s, cudaStreamAttributeAccessPolicyWindow, &av); cudaGetLastError();

@@ -86,6 +86,24 @@ void *PinnedBuf::get(size_t bytes) {
     return p;
 }
 
+// The L2 set-aside for persisting accesses comes OUT of the L2 every other access shares (measured: the device maximum as a
+// standing limit costs the lookup join 1.5 ms per step), so it is sized by the window that is about to use it and changed
+// only when that size changes.  Returns the bytes a window of `want` bytes can count on.
+size_t l2_persisting_bytes(size_t want) {
+    static size_t maxb = [] {
+        int dev = 0, mx = 0; cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&mx, cudaDevAttrMaxPersistingL2CacheSize, dev);
+        return (size_t)(mx > 0 ? mx : 0);
+    }();
+    static size_t cur = (size_t)-1;
+    size_t lim = want + (want >> 3); if (lim > maxb) lim = maxb;
+    if (lim != cur) {
+        if (cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, lim) != cudaSuccess) { cudaGetLastError(); return 0; }
+        cur = lim;
+    }
+    return want < lim ? want : lim;
+}
+
 int sm_count() {
     static int n = 0;
     if (!n) { int dev; DN_CUDA(cudaGetDevice(&dev)); DN_CUDA(cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev)); }
