@@ -518,10 +518,11 @@ def main():
         cons = {"value": float(u3[0]) / float(t3[0]), "unit": "consensus bases/s", "pile_ups_per_gpu": npiles, "pile_ups_with_both_flanks_aligned": nok,
                 "cropped_reads_per_gpu": int(preads.nreads), "cropped_bp_per_gpu": int(preads.total), "ms_per_batch": 1e3 * float(t3[0]) / nsteps_c,
                 "h2d_bytes_per_batch": int(batch.bases_bytes), "entry_point": "dn_process_pileups (one C call per batch, host buffers in)",
-                "stages": "dust + pile alignment (daligner -s126 -l500) + error filter + chaining + QVs + pile filter + reference read + consensus (with retry) + flank alignment (-mdust -mrep)",
+                "stages": "dust + pile alignment (daligner -B -s126 -l500) + error filter + chaining + QVs + pile filter + reference read + consensus (with retry) + flank alignment (-B -mdust -mrep)",
                 "roofline": {"bound": "hbm", "achieved": cons_algo / 1e9 / (float(t3[0]) / nsteps_c), "unit": "GB/s",
-                             "note": "whole leg, algorithmic bytes / wall time: the leg is ~60 short launches on 28 Mbp, launch- and latency-bound; k_cons_vote "
-                                     "(2.3 ms of it) runs at IPC 2.0 with 4.8 % DRAM throughput (profiles/r02_a_prof_consensus_kernels_start_of_round.txt)"}}
+                             "note": "whole leg, algorithmic bytes / wall time: the leg is ~108 short launches on 28 Mbp, half of its time the pile alignment's "
+                                     "issue-bound extension kernel; the consensus vote itself (k_cons_vote_bv, bit-parallel DP) takes 0.38 ms at 1.56 TB/s of "
+                                     "memory throughput (profiles/r02_f_prof_consensus_batch_kernels_final.txt)"}}
         if rank == 0 and world == 1:
             piles = list(range(min(npiles, 4 * cores)))
             nb, dt = oracle_piles_threads(preads, pgroup, piles, cores)
@@ -551,13 +552,13 @@ def main():
                                 if _lib.lib().dn_comm_shared_segment_bytes() > 0 else "merged LAS downloaded by rank 0")},
                "gpu_launches": int(launches),
                "clocks": summarize_clocks(clk),
-               "roofline": {"kernel": "k_extend32 (O(ND) wave extension, 48% of device time)", "bound": "hbm", "achieved": ext_gbs, "peak": peak,
+               "roofline": {"kernel": "k_extend32 (O(ND) wave extension, 49% of device time)", "bound": "hbm", "achieved": ext_gbs, "peak": peak,
                             "unit": "GB/s", "frac": ext_gbs / peak,
                             "launches_per_step": 2,
-                            "traffic": (72.46e6 + 30.29e6 + 0.83e6 + 5.89e6) / 2,
-                            "traffic_source": "ncu dram__bytes_read+write per launch, averaged over the step's 2 launches: round 0 72.5 + 30.3 MB (profiles/r02_d_prof_extend32_ldg.txt), round 1 0.8 + 5.9 MB (profiles/r02_a_prof_hot_kernels_start_of_round.txt)",
+                            "traffic": (70.15e6 + 18.78e6 + 0.12e6 + 0.0) / 2,
+                            "traffic_source": "ncu dram__bytes_read+write per launch, averaged over the step's 2 launches: round 0 70.2 + 18.8 MB (profiles/r02_g_prof_extend32_final.txt), round 1 0.1 + 0.0 MB (profiles/r02_f_prof_extend32_lookup_final.txt, launch 0)",
                             "peak_source": peak_src,
-                            "note": "instruction-issue-bound kernel (81% issue slots busy, IPC 3.25, DRAM 0.2%, L1 hit rate 97%): the HBM fraction says nothing about its quality; "
+                            "note": "instruction-issue-bound kernel (83% issue slots busy, IPC 3.33, occupancy 61.7% of a theoretical 62.5%, DRAM 0.2%, L1 hit rate 97%): the HBM fraction says nothing about its quality; "
                                     "algorithmic bytes = packed sequence under each alignment + records + traces; measured DRAM traffic is BELOW them because the packed blocks stay in L2"},
                "roofline_seed": {"kernels": "A tuples+radix, lookup join, segment sort, band filter, retire, final ordering", "bound": "hbm", "achieved": seed_gbs, "peak": peak,
                                  "unit": "GB/s", "frac": seed_gbs / peak},
