@@ -498,7 +498,7 @@ void align_blocks(const DevBlock &A, const DevBlock &B, const AlignParams &P, Ho
         }
         DBuf<int2> tiles((size_t)ntile_cap + 1); DBuf<ExtOut> outs(2 * (size_t)nseeds);
         const int wpc = ext_warps_per_cta();
-        int ctas = sm_count() * ext_ctas_per_sm();    // 48 registers: 5 CTAs x 8 warps per SM (DN_EXT_CTAS=6: the 40-register build)
+        int ctas = sm_count() * ext_ctas_per_sm();    // 48 registers: 4 CTAs x 9 warps per SM (measured optimum; DN_EXT_CTAS overrides)
         { int64_t need = (2ll * nseeds + wpc - 1) / wpc; if (ctas > need) ctas = (int)need;
           const int64_t budget = 24ll << 30;   // bytes of HBM for trace-record pools
           int64_t maxc = budget / (pool_stride * 16 * wpc); if (maxc < 1) maxc = 1;

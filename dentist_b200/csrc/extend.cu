@@ -18,7 +18,7 @@ int ext_ctas_per_sm();
 
 namespace {
 
-constexpr int EXT_WARPS = 8;                 // warps per CTA
+constexpr int EXT_WARPS = 9;                 // warps per CTA: 4 resident CTAs x 9 warps = 36 warps per SM measured best (32: +1.6 %, 40: +6.5 %, 27: +7 %)
 constexpr int NEGV = -(1 << 29);
 constexpr int NEGS = -(1 << 30);
 
@@ -286,7 +286,9 @@ __global__ void __launch_bounds__(EXT_WARPS * 32, MINB) k_extend32(const Seed *_
     const u32 FULL = 0xffffffffu;
     int4 *pool = pool_all + (int64_t)(blockIdx.x * EXT_WARPS + warp) * pool_stride;
     const int ts = G.ts, C = G.cdiff, X = G.xdrop, WM = G.wmax;
-    const int lane_l = (lane + 31) & 31, lane_r = (lane + 1) & 31;
+    // lane constants held in registers: left to itself the compiler re-derives them from SR_TID in every wave (S2R + 4 ALU)
+    int lane_l = (lane + 31) & 31, lane_r = (lane + 1) & 31, lane_k = lane;
+    asm volatile("" : "+r"(lane_l), "+r"(lane_r), "+r"(lane_k));
     const u32 lt_mask = (1u << lane) - 1u;
     __shared__ __align__(16) u32 s_seq[STAGE ? EXT_WARPS : 1][2][STAGE ? STAGE_WORDS : 4];
     __shared__ uint64_t s_bar[STAGE ? EXT_WARPS : 1];
@@ -347,11 +349,11 @@ __global__ void __launch_bounds__(EXT_WARPS * 32, MINB) k_extend32(const Seed *_
         while (lo <= hi) {
             d++; Cd += C;
             const int nlo = lo - 1;
-            const int k = nlo + ((lane - nlo) & 31);            // the diagonal = lane (mod 32) inside the new window
+            const int k = nlo + ((lane_k - nlo) & 31);          // the diagonal = lane (mod 32) inside the new window
             // invariant: V == NEGV in every lane whose diagonal is outside [lo, hi] (kept at the end of each wave), so the
             // three predecessors need no range checks and lanes beyond hi + 1 fall out by themselves
             const int Vl = __shfl_sync(FULL, V, lane_l), Vr = __shfl_sync(FULL, V, lane_r);
-            int i = V + 1, src = lane;
+            int i = V + 1, src = lane_k;
             if (Vl + 1 > i) { i = Vl + 1; src = lane_l; }
             if (Vr > i) { i = Vr; src = lane_r; }
             int cT = __shfl_sync(FULL, T, src), cR = __shfl_sync(FULL, R, src);
@@ -744,9 +746,12 @@ void launch_task_order(const Seed *seeds, int nseeds, ExtGeom G, int *scratch, i
 void launch_extend(const Seed *seeds, int nseeds, ExtGeom G, const int64_t *tile_off, int2 *tiles, ExtOut *outs,
                    int4 *pool, int64_t pool_stride, int nwarps_total, int *counter, const int *order, cudaStream_t s) {
     int ctas = nwarps_total / EXT_WARPS;
-    // two register budgets of the same kernel: 5 resident CTAs per SM (48 registers) or 6 (40 registers, a few spilled words)
+    // resident CTAs per SM: 4 by default (DN_EXT_CTAS = 2..6 for the sweep recorded in DESIGN.md; 6 = the 40-register build, a few spilled words)
     static const bool stage = getenv("DN_EXT_TMA") != nullptr;
     if (G.wmax <= 30 && stage) DN_LAUNCH((k_extend32<5, true>), ctas, EXT_WARPS * 32, 0, s, seeds, 2 * nseeds, G, tile_off, tiles, outs, pool, pool_stride, counter, order);
+    else if (G.wmax <= 30 && ext_ctas_per_sm() == 2) DN_LAUNCH((k_extend32<2, false>), ctas, EXT_WARPS * 32, 0, s, seeds, 2 * nseeds, G, tile_off, tiles, outs, pool, pool_stride, counter, order);
+    else if (G.wmax <= 30 && ext_ctas_per_sm() == 3) DN_LAUNCH((k_extend32<3, false>), ctas, EXT_WARPS * 32, 0, s, seeds, 2 * nseeds, G, tile_off, tiles, outs, pool, pool_stride, counter, order);
+    else if (G.wmax <= 30 && ext_ctas_per_sm() == 4) DN_LAUNCH((k_extend32<4, false>), ctas, EXT_WARPS * 32, 0, s, seeds, 2 * nseeds, G, tile_off, tiles, outs, pool, pool_stride, counter, order);
     else if (G.wmax <= 30 && ext_ctas_per_sm() >= 6) DN_LAUNCH((k_extend32<6, false>), ctas, EXT_WARPS * 32, 0, s, seeds, 2 * nseeds, G, tile_off, tiles, outs, pool, pool_stride, counter, order);
     else if (G.wmax <= 30) DN_LAUNCH((k_extend32<5, false>), ctas, EXT_WARPS * 32, 0, s, seeds, 2 * nseeds, G, tile_off, tiles, outs, pool, pool_stride, counter, order);
     else DN_LAUNCH(k_extend, ctas, EXT_WARPS * 32, 0, s, seeds, 2 * nseeds, G, tile_off, tiles, outs, pool, pool_stride, counter, order);
@@ -775,7 +780,7 @@ void launch_dedupe(const Cand *cands, int ncand, const int32_t *round_beg, int n
 }
 
 int ext_warps_per_cta() { return EXT_WARPS; }
-int ext_ctas_per_sm() { static const int v = getenv("DN_EXT_CTAS") ? atoi(getenv("DN_EXT_CTAS")) : 5; return v < 1 ? 1 : v; }
+int ext_ctas_per_sm() { static const int v = getenv("DN_EXT_CTAS") ? atoi(getenv("DN_EXT_CTAS")) : 4; return v < 1 ? 1 : v; }
 
 }  // namespace dn
 
