@@ -160,6 +160,8 @@ int dn_align_host(const dn_block_desc *a, const dn_block_desc *b, const dn_align
         cudaSetDevice(g_device);
         static cudaStream_t copy_stream = nullptr;
         if (!copy_stream) DN_CUDA(cudaStreamCreateWithFlags(&copy_stream, cudaStreamNonBlocking));
+        static cudaStream_t pack_stream = nullptr;           // B's chunks are packed here as they arrive on the copy stream
+        if (!pack_stream) DN_CUDA(cudaStreamCreateWithFlags(&pack_stream, cudaStreamNonBlocking));
         const bool same = (a == b);
         std::unique_ptr<dn_block> ba(new dn_block()), bb(same ? nullptr : new dn_block());
         // B's (large) host->device copy and packing run on the copy stream while A is indexed on the engine's stream;
@@ -171,14 +173,14 @@ int dn_align_host(const dn_block_desc *a, const dn_block_desc *b, const dn_align
         const auto t0 = now();
         block_upload(*a, ba->b, g_stream, true);             // no host sync: the alignment follows on the same stream
         const auto t1 = now();
-        if (!same) block_upload(*b, bb->b, copy_stream, true);
+        if (!same) block_upload(*b, bb->b, copy_stream, true, pack_stream);
         const auto t2 = now();
         AlignParams q = to_internal(p);
         HostLas h;
         try { align_blocks(ba->b, same ? ba->b : bb->b, q, h, g_stream); }
-        catch (...) { cudaStreamSynchronize(copy_stream); throw; }
+        catch (...) { cudaStreamSynchronize(copy_stream); cudaStreamSynchronize(pack_stream); throw; }
         const auto t3 = now();
-        cudaStreamSynchronize(copy_stream);
+        cudaStreamSynchronize(copy_stream); cudaStreamSynchronize(pack_stream);
         to_buf(h, q.tspace, out);
         if (trace) fprintf(stderr, "[dn trace] align_host: A upload %.3f ms, B upload (host side) %.3f ms, align %.3f ms (device %.3f), tail %.3f ms\n",
                            ms(t0, t1), ms(t1, t2), ms(t2, t3), h.stats.ms_total, ms(t3, now()));

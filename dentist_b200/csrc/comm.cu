@@ -421,14 +421,16 @@ int dn_align_host_gather(const dn_block_desc *a, const dn_block_desc *b, const d
         cudaSetDevice(g_device);
         static cudaStream_t copy_stream = nullptr;
         if (!copy_stream) DN_CUDA(cudaStreamCreateWithFlags(&copy_stream, cudaStreamNonBlocking));
+        static cudaStream_t pack_stream = nullptr;           // B's chunks are packed here as they arrive on the copy stream
+        if (!pack_stream) DN_CUDA(cudaStreamCreateWithFlags(&pack_stream, cudaStreamNonBlocking));
         dn_block ba, bb;
         block_upload(*a, ba.b, g_stream, true);              // A first: its small copy must not queue behind B's
-        block_upload(*b, bb.b, copy_stream, true);           // B's upload overlaps A's indexing
+        block_upload(*b, bb.b, copy_stream, true, pack_stream);   // B's upload overlaps A's indexing; the count pass follows its chunks
         const AlignParams q = params_of(p);
         HostLas h; DevLas mine;
         try { align_blocks(ba.b, bb.b, q, h, g_stream, &mine); }
-        catch (...) { cudaStreamSynchronize(copy_stream); throw; }
-        cudaStreamSynchronize(copy_stream);
+        catch (...) { cudaStreamSynchronize(copy_stream); cudaStreamSynchronize(pack_stream); throw; }
+        cudaStreamSynchronize(copy_stream); cudaStreamSynchronize(pack_stream);
         gather_and_merge(mine, h, bread_offset, root, ba.b.nreads, g_stream);
         to_out(h, q.tspace, out);
         return DN_OK;

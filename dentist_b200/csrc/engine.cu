@@ -255,7 +255,10 @@ void align_blocks(const DevBlock &A, const DevBlock &B, const AlignParams &P, Ho
 
     const int aposbits = bits_for((uint64_t)A.maxlen);
     bool segsorted = false, seg_in_hits2 = false;
-    if (B.ready) DN_CUDA(cudaStreamWaitEvent(s, B.ready, 0));       // B may still be uploading on the copy stream (dn_align_host)
+    // B may still be uploading on the copy stream (dn_align_host): a chunked upload lets the count pass start behind the
+    // metadata and follow the chunks; otherwise wait for the whole block
+    if (!B.chunk_ready.empty() && lookup) { if (B.meta_ready) DN_CUDA(cudaStreamWaitEvent(s, B.meta_ready, 0)); }
+    else if (B.ready) DN_CUDA(cudaStreamWaitEvent(s, B.ready, 0));
     // ---- K3: join ------------------------------------------------------------------------------
     const int sh = 2 * k - tbits; const u32 nq = 1u << tbits;
     if (!cached) {
@@ -311,18 +314,31 @@ void align_blocks(const DevBlock &A, const DevBlock &B, const AlignParams &P, Ho
                 DN_CUDA(cudaMemsetAsync(wcnt.p + nwB, 0, sizeof(u32) * nwB, s));
                 DN_CUDA(cudaMemsetAsync(hitmask.p + nwB, 0, sizeof(unsigned short) * nwB, s));
                 const u32 *mb = B.has_mask ? B.mask.p : nullptr;
-                if (!wide)
-                    DN_LAUNCH(k_lookup_count, (unsigned)((nwB + 255) / 256), 256, 0, s, (const u32 *)B.fwd.p, mb,
-                              (const int64_t *)B.off.p, (const int32_t *)B.len.p, (const int32_t *)B.chunk2read.p, nwB, k,
-                              (const u64 *)sa, (const u32 *)tbl.p, sh, P.t, (const u32 *)kbits.p, kshift, JG, wcnt.p, hitmask.p, wlist.p, nlist.p);
-                else if (pb)
-                    DN_LAUNCH(k_lookup_count_p, (unsigned)((nwB + 255) / 256), 256, 0, s, (const u32 *)B.fwd.p, mb,
-                              (const int64_t *)B.off.p, (const int32_t *)B.len.p, (const int32_t *)B.chunk2read.p, nwB, k,
-                              (const u64 *)sa, pb, (const u32 *)tbl.p, sh, P.t, (const u32 *)kbits.p, kshift, JG, wcnt.p, hitmask.p, wlist.p, nlist.p);
-                else
-                    DN_LAUNCH(k_lookup_count_w, (unsigned)((nwB + 255) / 256), 256, 0, s, (const u32 *)B.fwd.p, mb,
-                              (const int64_t *)B.off.p, (const int32_t *)B.len.p, (const int32_t *)B.chunk2read.p, nwB, k,
-                              (const ulonglong2 *)sw, (const u32 *)tbl.p, sh, P.t, (const u32 *)kbits.p, kshift, JG, wcnt.p, hitmask.p, wlist.p, nlist.p);
+                // a block that is still arriving (dn_align_host: chunked upload on the copy stream) is swept chunk by chunk, each
+                // sweep behind its chunk's event; a resident block is one chunk
+                const size_t nchunks = B.chunk_ready.empty() ? 1 : B.chunk_ready.size();
+                for (size_t c = 0; c < nchunks; c++) {
+                    int64_t w0 = 0, w1 = nwB;
+                    if (!B.chunk_ready.empty()) {
+                        DN_CUDA(cudaStreamWaitEvent(s, B.chunk_ready[c], 0));
+                        w0 = B.chunk_word[c]; w1 = B.chunk_word[c + 1];
+                    }
+                    if (w1 <= w0) continue;
+                    const unsigned grid = (unsigned)((w1 - w0 + 255) / 256);
+                    if (!wide)
+                        DN_LAUNCH(k_lookup_count, grid, 256, 0, s, (const u32 *)B.fwd.p, mb,
+                                  (const int64_t *)B.off.p, (const int32_t *)B.len.p, (const int32_t *)B.chunk2read.p, nwB, k,
+                                  (const u64 *)sa, (const u32 *)tbl.p, sh, P.t, (const u32 *)kbits.p, kshift, JG, wcnt.p, hitmask.p, wlist.p, nlist.p, w0, w1);
+                    else if (pb)
+                        DN_LAUNCH(k_lookup_count_p, grid, 256, 0, s, (const u32 *)B.fwd.p, mb,
+                                  (const int64_t *)B.off.p, (const int32_t *)B.len.p, (const int32_t *)B.chunk2read.p, nwB, k,
+                                  (const u64 *)sa, pb, (const u32 *)tbl.p, sh, P.t, (const u32 *)kbits.p, kshift, JG, wcnt.p, hitmask.p, wlist.p, nlist.p, w0, w1);
+                    else
+                        DN_LAUNCH(k_lookup_count_w, grid, 256, 0, s, (const u32 *)B.fwd.p, mb,
+                                  (const int64_t *)B.off.p, (const int32_t *)B.len.p, (const int32_t *)B.chunk2read.p, nwB, k,
+                                  (const ulonglong2 *)sw, (const u32 *)tbl.p, sh, P.t, (const u32 *)kbits.p, kshift, JG, wcnt.p, hitmask.p, wlist.p, nlist.p, w0, w1);
+                }
+                if (B.ready) DN_CUDA(cudaStreamWaitEvent(s, B.ready, 0));       // everything of B from here on
             }
             exclusive_scan_u32_to_i64(wcnt.p, woff.p, 2 * nwB, dtotal.p, s);
             // radix variant writes to the other buffer: singletons are copied too (minimum length 1)

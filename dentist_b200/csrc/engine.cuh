@@ -32,10 +32,14 @@ struct DevBlock {
     // asynchronous upload (dn_align_host): the copy stream records `ready`, the first consumer's stream waits on it;
     // the staging buffers live until the block dies
     cudaEvent_t ready = nullptr;
+    // chunked upload: chunk c = words [chunk_word[c], chunk_word[c + 1]) of fwd / rc, packed when chunk_ready[c] fires;
+    // meta_ready = offsets, lengths, chunk2read are on the device
+    cudaEvent_t meta_ready = nullptr;
+    std::vector<cudaEvent_t> chunk_ready; std::vector<int64_t> chunk_word;
     DBuf<uint8_t> up_raw; DBuf<int64_t> up_boff;
     DevBlock() {}
     DevBlock(const DevBlock &) = delete; DevBlock &operator=(const DevBlock &) = delete;
-    ~DevBlock() { if (ready) cudaEventDestroy(ready); }
+    ~DevBlock() { if (ready) cudaEventDestroy(ready); if (meta_ready) cudaEventDestroy(meta_ready); for (cudaEvent_t e : chunk_ready) cudaEventDestroy(e); }
     // optional resident k-mer index (dn_block_index): the sorted tuple list, prefix table and k-mer filter that
     // align_blocks otherwise rebuilds for the A block on every call.  Invalidated when the seed mask changes.
     struct Index {
@@ -68,7 +72,7 @@ struct HostLas {
 void *hcache_alloc(size_t bytes);
 void hcache_free(void *p);
 
-void block_upload(const dn_block_desc &d, DevBlock &out, cudaStream_t s, bool async = false);
+void block_upload(const dn_block_desc &d, DevBlock &out, cudaStream_t s, bool async = false, cudaStream_t pack_stream = nullptr);
 void block_add_mask(DevBlock &B, const int64_t *anno_h, const int32_t *data_h, cudaStream_t s);
 void block_crop(const DevBlock &src, int n, const int32_t *read, const int32_t *begin, const int32_t *end, const int32_t *group,
                 DevBlock &out, cudaStream_t s);

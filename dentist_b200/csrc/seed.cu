@@ -12,8 +12,8 @@ namespace dn {
 
 __global__ void __launch_bounds__(128) k_pack(const uint8_t *__restrict__ data, const int64_t *__restrict__ boff,
                                               const int32_t *__restrict__ len, const int64_t *__restrict__ off,
-                                              int format, u32 *__restrict__ fwd, u32 *__restrict__ rc) {
-    const int r = blockIdx.x;
+                                              int format, u32 *__restrict__ fwd, u32 *__restrict__ rc, int r0) {
+    const int r = r0 + blockIdx.x;
     const int L = len[r];
     const uint8_t *src = data + boff[r];
     const int64_t w0 = off[r] >> 4;
@@ -83,14 +83,18 @@ void block_add_mask(DevBlock &B, const int64_t *anno_h, const int32_t *data_h, c
     DN_CUDA(cudaStreamSynchronize(s));
 }
 
-// async = true: no host sync at the end; `B.ready` is recorded on `s` and the staging buffers stay with the block
-// (the caller keeps the host arrays alive and untouched until the block was consumed -- dn_align_host does)
-void block_upload(const dn_block_desc &d, DevBlock &B, cudaStream_t s, bool async) {
+// async = true: no host sync at the end; `B.ready` is recorded and the staging buffers stay with the block
+// (the caller keeps the host arrays alive and untouched until the block was consumed -- dn_align_host does).
+// pack_stream != nullptr (async only): the raw bytes travel in chunks on `s`, every chunk is packed on `pack_stream` as soon as it
+// has arrived and announces itself through B.chunk_ready[c] -- the consumer's first pass over the block (the lookup join's count
+// pass) follows the chunks instead of waiting for the whole upload.
+void block_upload(const dn_block_desc &d, DevBlock &B, cudaStream_t s, bool async, cudaStream_t pack_stream) {
     if (d.nreads < 0 || (d.nreads > 0 && (!d.rlen || !d.boff || !d.data))) throw Error("dn_block_desc: null field");
     B.nreads = d.nreads;
     B.h_len.assign(d.rlen, d.rlen + d.nreads);
     B.h_off.resize(d.nreads + 1);
     int64_t g = 0; B.maxlen = 0; B.total_real = 0;
+    bool monotonic = true;
     for (int r = 0; r < d.nreads; r++) {
         if (d.rlen[r] < 0) throw Error("negative read length");
         B.h_off[r] = g; g += ((int64_t)d.rlen[r] + 63) / 64 * 64;
@@ -98,35 +102,67 @@ void block_upload(const dn_block_desc &d, DevBlock &B, cudaStream_t s, bool asyn
         B.total_real += d.rlen[r];
         int64_t need = d.format == DN_SEQ_BPS ? ((int64_t)d.rlen[r] + 3) / 4 : d.rlen[r];
         if (d.boff[r] < 0 || d.boff[r] + need > d.data_bytes) throw Error("dn_block_desc: read outside data");
+        if (r > 0 && d.boff[r] < d.boff[r - 1]) monotonic = false;
     }
     B.h_off[d.nreads] = g; B.total = g;
     if (2 * g >= (1ll << 32) - 1024) throw Error("block too large: 2*padded bases must be < 2^32");
     size_t nwords = (size_t)(g >> 4) + 8;
+    static const int want_chunks = getenv("DN_UPLOAD_CHUNKS") ? atoi(getenv("DN_UPLOAD_CHUNKS")) : 4;
+    const bool chunked = async && pack_stream && want_chunks > 1 && monotonic && d.nreads >= 16 * want_chunks &&
+                         !(d.mask_anno && d.mask_data) && d.data_bytes >= (8 << 20);
+    cudaStream_t ps = chunked ? pack_stream : s;              // the stream the device-side work of the upload runs on
     B.fwd.persistent(nwords); B.rc.persistent(nwords);
-    B.fwd.zero(s); B.rc.zero(s);
+    B.fwd.zero(ps); B.rc.zero(ps);
     B.off.persistent(d.nreads + 1); B.len.persistent(d.nreads > 0 ? d.nreads : 1);
     B.chunk2read.persistent((size_t)(g >> 10) + 2);
-    B.chunk2read.zero(s);
+    B.chunk2read.zero(ps);
     DN_CUDA(cudaMemcpyAsync(B.off.p, B.h_off.data(), sizeof(int64_t) * (d.nreads + 1), cudaMemcpyHostToDevice, s));
     if (d.nreads == 0) { DN_CUDA(cudaStreamSynchronize(s)); return; }
     DN_CUDA(cudaMemcpyAsync(B.len.p, B.h_len.data(), sizeof(int32_t) * d.nreads, cudaMemcpyHostToDevice, s));
     DBuf<uint8_t> &raw = B.up_raw; raw.persistent((size_t)d.data_bytes + 16);
     DBuf<int64_t> &boff = B.up_boff; boff.persistent(d.nreads);
-    DN_CUDA(cudaMemcpyAsync(raw.p, d.data, d.data_bytes, cudaMemcpyHostToDevice, s));
     DN_CUDA(cudaMemcpyAsync(boff.p, d.boff, sizeof(int64_t) * d.nreads, cudaMemcpyHostToDevice, s));
-    DN_LAUNCH(k_pack, d.nreads, 128, 0, s, (const uint8_t *)raw.p, (const int64_t *)boff.p, (const int32_t *)B.len.p,
-              (const int64_t *)B.off.p, d.format, B.fwd.p, B.rc.p);
-    DN_LAUNCH(k_chunk2read, (d.nreads + 255) / 256, 256, 0, s, (const int64_t *)B.off.p, d.nreads, B.chunk2read.p);
     B.has_group = d.group != nullptr;
     if (d.group) {
         B.group.persistent(d.nreads);
         DN_CUDA(cudaMemcpyAsync(B.group.p, d.group, sizeof(int32_t) * d.nreads, cudaMemcpyHostToDevice, s));
     }
     B.has_mask = false;
+    auto event = [](cudaEvent_t &e) { if (!e) DN_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming)); return e; };
+    if (chunked) {
+        cudaEvent_t meta_copied = nullptr; event(meta_copied);
+        DN_CUDA(cudaEventRecord(meta_copied, s));
+        DN_CUDA(cudaStreamWaitEvent(ps, meta_copied, 0));
+        DN_LAUNCH(k_chunk2read, (d.nreads + 255) / 256, 256, 0, ps, (const int64_t *)B.off.p, d.nreads, B.chunk2read.p);
+        DN_CUDA(cudaEventRecord(event(B.meta_ready), ps));
+        const int C = want_chunks;
+        for (cudaEvent_t e : B.chunk_ready) cudaEventDestroy(e);
+        B.chunk_ready.assign(C, nullptr); B.chunk_word.assign(C + 1, 0);
+        std::vector<cudaEvent_t> copied(C, nullptr);
+        for (int c = 0; c < C; c++) {
+            const int r0 = (int)((int64_t)d.nreads * c / C), r1 = (int)((int64_t)d.nreads * (c + 1) / C);
+            const int64_t b0 = c == 0 ? 0 : d.boff[r0], b1 = c == C - 1 ? d.data_bytes : d.boff[r1];
+            if (b1 > b0) DN_CUDA(cudaMemcpyAsync(raw.p + b0, (const uint8_t *)d.data + b0, (size_t)(b1 - b0), cudaMemcpyHostToDevice, s));
+            DN_CUDA(cudaEventRecord(event(copied[c]), s));
+            DN_CUDA(cudaStreamWaitEvent(ps, copied[c], 0));
+            if (r1 > r0)
+                DN_LAUNCH(k_pack, r1 - r0, 128, 0, ps, (const uint8_t *)raw.p, (const int64_t *)boff.p, (const int32_t *)B.len.p,
+                          (const int64_t *)B.off.p, d.format, B.fwd.p, B.rc.p, r0);
+            DN_CUDA(cudaEventRecord(event(B.chunk_ready[c]), ps));
+            B.chunk_word[c] = B.h_off[r0] >> 4; B.chunk_word[c + 1] = B.h_off[r1] >> 4;
+        }
+        DN_CUDA(cudaEventRecord(event(B.ready), ps));
+        // the helper events may be destroyed once recorded and waited on: the driver keeps what the streams still need
+        cudaEventDestroy(meta_copied); for (cudaEvent_t e : copied) cudaEventDestroy(e);
+        return;
+    }
+    DN_CUDA(cudaMemcpyAsync(raw.p, d.data, d.data_bytes, cudaMemcpyHostToDevice, s));
+    DN_LAUNCH(k_pack, d.nreads, 128, 0, s, (const uint8_t *)raw.p, (const int64_t *)boff.p, (const int32_t *)B.len.p,
+              (const int64_t *)B.off.p, d.format, B.fwd.p, B.rc.p, 0);
+    DN_LAUNCH(k_chunk2read, (d.nreads + 255) / 256, 256, 0, s, (const int64_t *)B.off.p, d.nreads, B.chunk2read.p);
     if (d.mask_anno && d.mask_data) block_add_mask(B, d.mask_anno, d.mask_data, s);
     if (async) {
-        if (!B.ready) DN_CUDA(cudaEventCreateWithFlags(&B.ready, cudaEventDisableTiming));
-        DN_CUDA(cudaEventRecord(B.ready, s));
+        DN_CUDA(cudaEventRecord(event(B.ready), s));
         return;
     }
     DN_CUDA(cudaStreamSynchronize(s));
@@ -534,13 +570,14 @@ __device__ __forceinline__ void lookup_count_body(const u32 *__restrict__ seq, c
                                                   IDX ta, const u32 *__restrict__ tbl, int sh, int tcap,
                                                   const u32 *__restrict__ kbits, int kshift, const JoinGeom &G, u32 *__restrict__ wcnt,
                                                   unsigned short *__restrict__ hitmask,
-                                                  u32 *__restrict__ wlist, u32 *__restrict__ nlist) {
+                                                  u32 *__restrict__ wlist, u32 *__restrict__ nlist, int64_t w0, int64_t w1) {
+    // words [w0, w1) of the block's nwords: the pass can follow a read block that is still arriving chunk by chunk
     typedef typename IDX::key_t key_t;
     __shared__ u32 s_total[8][32], s_hm[8][32];
     const u32 FULL = 0xffffffffu;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int64_t wi = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    const bool inrange = wi < nwords;
+    const int64_t wi = w0 + (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const bool inrange = wi < w1;
     const u64 kmask = (1ull << (2 * k)) - 1ull, mk = (1ull << k) - 1ull;
     const bool restricted = G.self || G.a_group;
     WordKmers w; w.v = 0; w.mwin = 0; w.w2 = 0; w.p0 = 0; w.L = 0; w.r = 0;
@@ -629,8 +666,8 @@ __global__ void __launch_bounds__(256) k_lookup_count(const u32 *__restrict__ se
                                                       const u64 *__restrict__ ta, const u32 *__restrict__ tbl, int sh, int tcap,
                                                       const u32 *__restrict__ kbits, int kshift, JoinGeom G, u32 *__restrict__ wcnt,
                                                       unsigned short *__restrict__ hitmask,
-                                                      u32 *__restrict__ wlist, u32 *__restrict__ nlist) {
-    lookup_count_body(seq, maskbits, off, len, c2r, nwords, k, Idx32{ta}, tbl, sh, tcap, kbits, kshift, G, wcnt, hitmask, wlist, nlist);
+                                                      u32 *__restrict__ wlist, u32 *__restrict__ nlist, int64_t w0, int64_t w1) {
+    lookup_count_body(seq, maskbits, off, len, c2r, nwords, k, Idx32{ta}, tbl, sh, tcap, kbits, kshift, G, wcnt, hitmask, wlist, nlist, w0, w1);
 }
 __global__ void __launch_bounds__(256) k_lookup_count_w(const u32 *__restrict__ seq, const u32 *__restrict__ maskbits,
                                                         const int64_t *__restrict__ off, const int32_t *__restrict__ len,
@@ -638,8 +675,8 @@ __global__ void __launch_bounds__(256) k_lookup_count_w(const u32 *__restrict__ 
                                                         const ulonglong2 *__restrict__ ta, const u32 *__restrict__ tbl, int sh, int tcap,
                                                         const u32 *__restrict__ kbits, int kshift, JoinGeom G, u32 *__restrict__ wcnt,
                                                         unsigned short *__restrict__ hitmask,
-                                                        u32 *__restrict__ wlist, u32 *__restrict__ nlist) {
-    lookup_count_body(seq, maskbits, off, len, c2r, nwords, k, Idx64{ta}, tbl, sh, tcap, kbits, kshift, G, wcnt, hitmask, wlist, nlist);
+                                                        u32 *__restrict__ wlist, u32 *__restrict__ nlist, int64_t w0, int64_t w1) {
+    lookup_count_body(seq, maskbits, off, len, c2r, nwords, k, Idx64{ta}, tbl, sh, tcap, kbits, kshift, G, wcnt, hitmask, wlist, nlist, w0, w1);
 }
 
 __global__ void __launch_bounds__(256) k_lookup_count_p(const u32 *__restrict__ seq, const u32 *__restrict__ maskbits,
@@ -648,8 +685,8 @@ __global__ void __launch_bounds__(256) k_lookup_count_p(const u32 *__restrict__ 
                                                         const u64 *__restrict__ ta, int pb, const u32 *__restrict__ tbl, int sh, int tcap,
                                                         const u32 *__restrict__ kbits, int kshift, JoinGeom G, u32 *__restrict__ wcnt,
                                                         unsigned short *__restrict__ hitmask,
-                                                        u32 *__restrict__ wlist, u32 *__restrict__ nlist) {
-    lookup_count_body(seq, maskbits, off, len, c2r, nwords, k, IdxP{ta, pb}, tbl, sh, tcap, kbits, kshift, G, wcnt, hitmask, wlist, nlist);
+                                                        u32 *__restrict__ wlist, u32 *__restrict__ nlist, int64_t w0, int64_t w1) {
+    lookup_count_body(seq, maskbits, off, len, c2r, nwords, k, IdxP{ta, pb}, tbl, sh, tcap, kbits, kshift, G, wcnt, hitmask, wlist, nlist, w0, w1);
 }
 
 // Emit pass over the compact list of words with hits.  Like the count pass it deals the (word, position) units of a warp's 32

@@ -46,7 +46,7 @@ __global__ void k_join_emit(const u64 *ta, const u64 *tb, int64_t nb, const u32 
                             JoinGeom G, ulonglong2 *hits, unsigned long long *ninvalid);
 __global__ void k_lookup_count(const u32 *seq, const u32 *maskbits, const int64_t *off, const int32_t *len, const int32_t *c2r,
                                int64_t nwords, int k, const u64 *ta, const u32 *tbl, int sh, int tcap, const u32 *kbits, int kshift, JoinGeom G,
-                               u32 *wcnt, unsigned short *hitmask, u32 *wlist, u32 *nlist);
+                               u32 *wcnt, unsigned short *hitmask, u32 *wlist, u32 *nlist, int64_t w0, int64_t w1);
 __global__ void k_kmer_bitmap(const u64 *ta, int64_t na, int k, int kshift, u32 *bits);
 __global__ void k_lookup_emit(const u32 *seq, const u32 *maskbits, const int64_t *off, const int32_t *len, const int32_t *c2r,
                               int64_t nwords, int k, const u64 *ta, const u32 *tbl, int sh, int tcap, const unsigned short *hitmask,
@@ -56,7 +56,7 @@ __global__ void k_prefix_table_w(const ulonglong2 *ta, int64_t na, int sh, u32 n
 __global__ void k_kmer_bitmap_w(const ulonglong2 *ta, int64_t na, int k, int kshift, u32 *bits);
 __global__ void k_lookup_count_w(const u32 *seq, const u32 *maskbits, const int64_t *off, const int32_t *len, const int32_t *c2r,
                                  int64_t nwords, int k, const ulonglong2 *ta, const u32 *tbl, int sh, int tcap, const u32 *kbits, int kshift, JoinGeom G,
-                                 u32 *wcnt, unsigned short *hitmask, u32 *wlist, u32 *nlist);
+                                 u32 *wcnt, unsigned short *hitmask, u32 *wlist, u32 *nlist, int64_t w0, int64_t w1);
 __global__ void k_lookup_emit_w(const u32 *seq, const u32 *maskbits, const int64_t *off, const int32_t *len, const int32_t *c2r,
                                 int64_t nwords, int k, const ulonglong2 *ta, const u32 *tbl, int sh, int tcap, const unsigned short *hitmask,
                                 const u32 *wcnt, const int64_t *woff, int strand, JoinGeom G, ulonglong2 *hits, const u32 *wlist);
@@ -76,7 +76,7 @@ __global__ void k_prefix_table_p(const u64 *ta, int pb, int64_t na, int sh, u32 
 __global__ void k_kmer_bitmap_p(const u64 *ta, int pb, int64_t na, int k, int kshift, u32 *bits);
 __global__ void k_lookup_count_p(const u32 *seq, const u32 *maskbits, const int64_t *off, const int32_t *len, const int32_t *c2r,
                                  int64_t nwords, int k, const u64 *ta, int pb, const u32 *tbl, int sh, int tcap, const u32 *kbits, int kshift, JoinGeom G,
-                                 u32 *wcnt, unsigned short *hitmask, u32 *wlist, u32 *nlist);
+                                 u32 *wcnt, unsigned short *hitmask, u32 *wlist, u32 *nlist, int64_t w0, int64_t w1);
 __global__ void k_lookup_emit_p(const u32 *seq, const u32 *maskbits, const int64_t *off, const int32_t *len, const int32_t *c2r,
                                 int64_t nwords, int k, const u64 *ta, int pb, const u32 *tbl, int sh, int tcap, const unsigned short *hitmask,
                                 const u32 *wcnt, const int64_t *woff, int strand, JoinGeom G, ulonglong2 *hits, const u32 *wlist);
