@@ -251,6 +251,68 @@ def parity_on_config(la, otr, rec, gtr):
     return {"reads": nr, "las": int(len(la)), "gpu_las_same_reads": int(len(g)), "trace_points": int(len(otr) // 2), "identical": bool(same)}
 
 
+C4_GAPS = 2000          # configs[3] sampled: 50 000 gaps / 3 Gbp scaled to C4_GAPS gaps on C4_GAPS / 10 Mbp (same gap density as configs[1])
+C4_BATCH = 100          # pile-ups per dn_process_pileups call (the reference runs batch_size = 50 per job, Snakefile:626-673; at k = 14 the chance k-mer matches between the piles of one block grow with the square of the batch, 100 measured best)
+
+
+def run_c4(args, rank, world, dev, barrier, dist, torch, ngaps):
+    """configs[3], sampled: the pile-ups of `ngaps` gaps dealt contiguously over the ranks (by scaffold: a pile-up's flanking
+    contigs travel with it), every rank runs its pile-ups through dn_process_pileups in batches, the insertion payloads
+    (pile-up id, status, consensus bases) of all ranks are gathered with ONE dn_comm_allgatherv at the end -- what
+    `merge-insertions` collects from files (commands/mergeInsertions.d).  Strong scaling: the job is fixed, N ranks share it."""
+    from dentist_b200 import dazzler
+    n_sc = max(world, ngaps // 10)
+    mine = [s for s in range(n_sc) if s * world // n_sc == rank]                     # contiguous scaffold ranges
+    t0 = time.perf_counter()
+    scs, gaps, batches, first_gap = [], [], [], 0
+    for s in range(n_sc):
+        if s not in mine:
+            continue
+        sc = synth.make_scaffolds(1, 1000000, 3001 + s, n_repeats=1)
+        gp = synth.make_gaps(sc, 10, 3002 + 7 * s)
+        scs.append(sc[0]); gaps.append(gp[0])
+    ref, _ = synth.contigs_from(scs, gaps)
+    preads, pgroup, _ = synth.make_pile_batch(scs, gaps, 3003 + rank, depth=20, anchor=1500)
+    npiles = int(pgroup.max()) + 1 if len(pgroup) else 0
+    flank_of, c = [], 0
+    for gl in gaps:
+        for _g in gl:
+            flank_of.append([c, c + 1]); c += 1
+        c += 1
+    order = np.argsort(pgroup, kind="stable"); bounds = np.searchsorted(pgroup[order], np.arange(npiles + 1))
+    piles_in = [dict(reads=[preads.read(int(r)) for r in order[bounds[p]:bounds[p + 1]]], flanks=flank_of[p]) for p in range(npiles)]
+    gen_s = time.perf_counter() - t0
+    ga = dazzler.Block(ref.off, ref.bases)
+    pbs = [dazzler.PileupBatch(ga, piles_in[i:i + C4_BATCH]) for i in range(0, npiles, C4_BATCH)]
+    gap0 = min(mine) * 10 if mine else 0
+    def step():
+        payload = []; bases = 0; ok = 0
+        for bi, pb in enumerate(pbs):
+            res = pb.run()
+            for j, o in enumerate(res.to_list()):
+                hdr = np.array([gap0 + bi * C4_BATCH + j, o["status"], len(o["consensus"])], np.int64).tobytes()
+                payload.append(hdr); payload.append(o["consensus"].tobytes())
+                bases += len(o["consensus"]); ok += int(o["status"] == 0 and len(o["flank_las"]) >= 2)
+        mine_bytes = b"".join(payload)
+        allb = dazzler.comm_allgatherv(mine_bytes) if world > 1 else [mine_bytes]
+        return bases, ok, sum(len(x) for x in allb)
+    tt = 0.0; tb = 0; nok = 0; gathered = 0
+    for it in range(args.warmup + args.steps):
+        barrier(); t1 = time.perf_counter()
+        b, k, gathered = step()
+        barrier(); dt = time.perf_counter() - t1
+        if os.environ.get("BENCH_DEBUG"):
+            print("[bench] c4 rank %d iter %d %.1f ms, %d pile-ups, %d consensus bases" % (rank, it, dt * 1e3, npiles, b), file=sys.stderr)
+        if it >= args.warmup:
+            tt += dt; tb += b; nok = k
+    t = torch.tensor([tt], dtype=torch.float64, device=dev); u = torch.tensor([float(tb), float(nok), float(npiles), float(preads.total)], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX); dist.all_reduce(u, op=dist.ReduceOp.SUM)
+    return {"value": float(u[0]) / float(t[0]), "ms_per_step": 1e3 * float(t[0]) / args.steps, "pile_ups": int(u[2]), "pile_ups_with_both_flanks_aligned": int(u[1]),
+            "cropped_bp": int(u[3]), "consensus_bases_per_step": int(u[0]) // args.steps, "gathered_bytes": int(gathered), "batch": C4_BATCH,
+            "generation_s": gen_s}
+
+
 def oracle_pile(reads, group, p):
     """processPileUp for one pile on the CPU oracle (alignment, filters, QVs, reference read, consensus)."""
     from oracle import oracle
@@ -294,7 +356,8 @@ def main():
     ap.add_argument("--scale", type=float, default=1.0, help="shrink the workload (tests only; 1.0 = configs[1])")
     ap.add_argument("--cpu-sample-mbp", type=float, default=0.0, help="CPU leg on the first N Mbp of reads only (0 = the whole block)")
     ap.add_argument("--profile", action="store_true", help="device-resident arm only (for ncu runs)")
-    ap.add_argument("--config", default="c1", choices=["c1", "c3"], help="c1 = BASELINE configs[1] (default, the headline); c3 = configs[2], 15 read blocks block-sharded")
+    ap.add_argument("--config", default="c1", choices=["c1", "c3", "c4"], help="c1 = BASELINE configs[1] (default, the headline); c3 = configs[2], 15 read blocks block-sharded; c4 = configs[3] sampled, pile-ups sharded + all-gatherv")
+    ap.add_argument("--c4-gaps", type=int, default=C4_GAPS, help="gaps (= pile-ups) of the c4 workload, all ranks together")
     ap.add_argument("--c3-blocks", type=int, default=C3_BLOCKS, help="read blocks of the c3 workload (15 = configs[2]; fewer for a quick run)")
     args = ap.parse_args()
     # the contract is ONE JSON line on stdout: anything a library prints there (e.g. NCCL's version banner) goes to stderr
@@ -361,6 +424,21 @@ def main():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
+
+    if args.config == "c4":
+        c4 = run_c4(args, rank, world, dev, barrier, dist, torch, args.c4_gaps)
+        if rank == 0:
+            emit({"metric": "consensus bases/sec", "value": c4["value"], "unit": "consensus bases/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+                  "ms_per_step": c4["ms_per_step"], "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "u8/int32", "data": "synthetic",
+                  "config": {"workload": "synthetic human-scale assembly, 50k gaps, 30x reads, pile-ups sharded across the GPUs + NCCL gather (BASELINE.json configs[3]), "
+                                         "SAMPLED to %d gaps on %d Mbp" % (c4["pile_ups"], max(world, args.c4_gaps // 10)),
+                             **{k: v for k, v in c4.items() if k not in ("value", "ms_per_step")}},
+                  "e2e": {"value": c4["value"], "unit": "consensus bases/s", "h2d_bytes_per_step": c4["cropped_bp"], "d2h_bytes_per_step": c4["gathered_bytes"],
+                          "note": "the timed region IS end to end: host pile-ups in (dn_process_pileups per batch), insertion payloads of all ranks out through dn_comm_allgatherv"},
+                  "gpu_launches": None})
+        if world > 1:
+            dist.barrier(); dazzler.comm_shutdown(); dist.destroy_process_group()
+        return
 
     if args.config == "c3":
         c3 = run_c3(args, rank, world, dev, barrier, dist, torch, args.c3_blocks)
