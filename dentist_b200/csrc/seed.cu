@@ -107,9 +107,11 @@ void block_upload(const dn_block_desc &d, DevBlock &B, cudaStream_t s, bool asyn
     B.h_off[d.nreads] = g; B.total = g;
     if (2 * g >= (1ll << 32) - 1024) throw Error("block too large: 2*padded bases must be < 2^32");
     size_t nwords = (size_t)(g >> 4) + 8;
-    static const int want_chunks = getenv("DN_UPLOAD_CHUNKS") ? atoi(getenv("DN_UPLOAD_CHUNKS")) : 4;
-    const bool chunked = async && pack_stream && want_chunks > 1 && monotonic && d.nreads >= 16 * want_chunks &&
-                         !(d.mask_anno && d.mask_data) && d.data_bytes >= (8 << 20);
+    // (read per call: tests force the chunked path on small blocks)
+    const int want_chunks = getenv("DN_UPLOAD_CHUNKS") ? atoi(getenv("DN_UPLOAD_CHUNKS")) : 4;
+    const int64_t min_bytes = getenv("DN_UPLOAD_CHUNK_MIN_BYTES") ? atoll(getenv("DN_UPLOAD_CHUNK_MIN_BYTES")) : (8 << 20);
+    const bool chunked = async && pack_stream && want_chunks > 1 && want_chunks <= 64 && monotonic && d.nreads >= 2 * want_chunks &&
+                         !(d.mask_anno && d.mask_data) && d.data_bytes >= min_bytes;
     cudaStream_t ps = chunked ? pack_stream : s;              // the stream the device-side work of the upload runs on
     B.fwd.persistent(nwords); B.rc.persistent(nwords);
     B.fwd.zero(ps); B.rc.zero(ps);

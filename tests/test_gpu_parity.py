@@ -300,6 +300,20 @@ def test_align_host_equals_resident_blocks():
     for _ in range(3):
         got = dazzler.align_host(dazzler.HostBlock(ref.off, ref.bases), dazzler.HostBlock(reads.off, bps=bps, boff=boff), tspace=100, minlen=500, k=20)
         assert got[0].tobytes() == want[0].tobytes() and got[2].tobytes() == want[2].tobytes()
+    # the chunked upload (the count pass follows the chunks of the arriving block), forced onto this small block: 2, 5 and 13 chunks,
+    # .bps and byte input, k = 14 and k = 20 indexes
+    import os
+    os.environ["DN_UPLOAD_CHUNK_MIN_BYTES"] = "1"
+    try:
+        for chunks in ("2", "5", "13"):
+            os.environ["DN_UPLOAD_CHUNKS"] = chunks
+            got = dazzler.align_host(dazzler.HostBlock(ref.off, ref.bases), dazzler.HostBlock(reads.off, bps=bps, boff=boff), tspace=100, minlen=500, k=20)
+            assert got[0].tobytes() == want[0].tobytes() and got[2].tobytes() == want[2].tobytes(), chunks
+        want14 = dazzler.align_blocks(dazzler.Block(ref.off, ref.bases), dazzler.Block(reads.off, reads.bases), tspace=100, minlen=500, k=14)
+        got = dazzler.align_host(dazzler.HostBlock(ref.off, ref.bases), dazzler.HostBlock(reads.off, reads.bases), tspace=100, minlen=500, k=14)
+        assert got[0].tobytes() == want14[0].tobytes() and got[2].tobytes() == want14[2].tobytes()
+    finally:
+        del os.environ["DN_UPLOAD_CHUNK_MIN_BYTES"]; os.environ.pop("DN_UPLOAD_CHUNKS", None)
     amask = [[(0, 500)] for _ in range(ref.nreads)]; bmask = [[(100, 400)] for _ in range(reads.nreads)]
     want = dazzler.align_blocks(dazzler.Block(ref.off, ref.bases, mask=amask), dazzler.Block(reads.off, reads.bases, mask=bmask), tspace=100, minlen=500)
     got = dazzler.align_host(dazzler.HostBlock(ref.off, ref.bases, mask=amask), dazzler.HostBlock(reads.off, reads.bases, mask=bmask), tspace=100, minlen=500)
