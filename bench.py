@@ -252,7 +252,7 @@ def parity_on_config(la, otr, rec, gtr):
 
 
 C4_GAPS = 2000          # configs[3] sampled: 50 000 gaps / 3 Gbp scaled to C4_GAPS gaps on C4_GAPS / 10 Mbp (same gap density as configs[1])
-C4_BATCH = 100          # pile-ups per dn_process_pileups call (the reference runs batch_size = 50 per job, Snakefile:626-673; at k = 14 the chance k-mer matches between the piles of one block grow with the square of the batch, 100 measured best)
+C4_BATCH = 100          # pile-ups per dn_process_pileups call (the reference runs batch_size = 50 per job, Snakefile:626-673; larger batches cost more per pile-up: the index of the batch's flanking contigs outgrows L2)
 
 
 def run_c4(args, rank, world, dev, barrier, dist, torch, ngaps):

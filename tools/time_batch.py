@@ -4,7 +4,8 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np
 from dentist_b200 import dazzler, synth
 dazzler.init(0)
-sc = synth.make_scaffolds(10, 1000000, 1001)
+NSC = int(sys.argv[2]) if len(sys.argv) > 2 else 10          # scaffolds of 10 gaps each: the batch holds 10 * NSC pile-ups
+sc = synth.make_scaffolds(NSC, 1000000, 1001)
 gaps = synth.make_gaps(sc, 10, 1002)
 ref, _ = synth.contigs_from(sc, gaps)
 preads, pgroup, _ = synth.make_pile_batch(sc, gaps, 1004, depth=20, anchor=1500)
