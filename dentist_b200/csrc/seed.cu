@@ -536,8 +536,9 @@ __device__ __forceinline__ WordKmers load_word(const u32 *__restrict__ seq, cons
     int r = c2r[g0 >> 10];
     while (off[r + 1] <= g0) r++;
     w.r = r; w.p0 = (int)(g0 - off[r]); w.L = len[r];
-    w.v = ((u64)seq[wi + 1] << 32) | seq[wi];
-    w.w2 = WIDE ? seq[wi + 2] : 0u;
+    // streaming (evict-first) loads: the packed reads pass through once per sweep and must not push the index out of L2
+    w.v = ((u64)__ldcs(seq + wi + 1) << 32) | __ldcs(seq + wi);
+    w.w2 = WIDE ? __ldcs(seq + wi + 2) : 0u;
     w.mwin = 0;
     if (maskbits) { int64_t mw = g0 >> 5; w.mwin = (((u64)maskbits[mw + 1] << 32) | maskbits[mw]) >> (g0 & 31); }
     return w;

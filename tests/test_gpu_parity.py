@@ -397,3 +397,25 @@ def test_config1_at_scale_matches_oracle():
     rec, toff, gtr, gst = dazzler.align_blocks(dazzler.Block(ref.off, ref.bases), dazzler.Block(reads.off, reads.bases), **bench.PARAMS)
     assert len(la) > 8000
     assert_same((la, tr, st), (rec, toff, gtr, gst))
+
+
+@pytest.mark.parametrize("k", [14, 20])
+def test_low_complexity_takes_every_index_build_path(k):
+    """The bucket-counting index build (csrc/bucket.cu) orders buckets of 2, of <= 32 (thread-local insertion sort) and of
+    <= 4096 tuples (CTA bitonic sort) in place and hands blocks with a larger bucket to the radix sort.  A reference with a
+    tandem repeat (buckets of hundreds) and, in the second round, a 12 kb homopolymer run (one bucket of thousands: the
+    radix fallback) must still give the oracle's alignments; -t caps what the repeats may seed."""
+    rng = np.random.default_rng(77 + k)
+    g = rng.integers(0, 4, 60000, dtype=np.uint8)
+    unit = rng.integers(0, 4, 37, dtype=np.uint8)
+    for with_run in (False, True):
+        ref = g.copy()
+        ref[10000:10000 + 37 * 60] = np.tile(unit, 60)                       # 60 copies of a 37-mer: every k-mer of it 60 times (minus the ends)
+        if with_run:
+            ref[30000:36000] = 0                                             # 6 000 x 'a': one k-mer ~6 000 times (> 4096: radix fallback)
+        a = synth.Block(np.array([0, len(ref)]), ref)
+        reads, _ = synth.simulate_reads([ref], 5, 5000, 1500, 0.12, 78 + k)
+        for t in ((100,) if with_run else (100, 100000)):                    # the homopolymer run only under the frequency cap
+            orc, gpu = run_both(a, reads, 100, 500, k=k, t=t)
+            assert len(orc[0]) > 20
+            assert_same(orc, gpu)
