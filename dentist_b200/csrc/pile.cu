@@ -180,13 +180,74 @@ __device__ __forceinline__ int u_popc_low(U128 a, int i) {
     return __popcll(a.lo & ((1ull << i) - 1ull));
 }
 
+// The DP and its traceback, shared by the consensus vote, the `-B` bridges and the transposition.  Rows = A[ga, ga + n),
+// n <= 128; columns = B[gb, gb + m), m <= 250; `cols` = this thread's slice of the interleaved column store (word w of
+// column j at cols[((j - 1) * 4 + w) * nthreads]).  Returns D[n][m].  The visitor sees every cell of the path from (n, m)
+// down to (0, 0), the last one with dir = 3:  step(dir, i, j, d_here, d_next)  with dir 0 = diagonal, 1 = A base unmatched,
+// 2 = B base inserted -- the cell DP's choice among the minima -- and the exact cell values of this cell and the next.
+template <class Visitor>
+__device__ __forceinline__ int bv_align(const u32 *__restrict__ Aw, int64_t ga, int n, const u32 *__restrict__ Bw, int64_t gb, int m,
+                                        unsigned long long *__restrict__ cols, int64_t nthreads, Visitor &&visit) {
+    U128 P0{0, 0}, P1{0, 0}, P2{0, 0}, P3{0, 0};                      // positions of each base in the A tile
+    for (int i = 0; i < n; i++) {
+        const int a = base_at(Aw, ga + i);
+        const unsigned long long bl = i < 64 ? 1ull << i : 0ull, bh = i < 64 ? 0ull : 1ull << (i - 64);
+        if (a == 0) { P0.lo |= bl; P0.hi |= bh; } else if (a == 1) { P1.lo |= bl; P1.hi |= bh; }
+        else if (a == 2) { P2.lo |= bl; P2.hi |= bh; } else { P3.lo |= bl; P3.hi |= bh; }
+    }
+    U128 VP{~0ull, ~0ull}, VN{0, 0};
+    for (int j = 1; j <= m; j++) {
+        const int b = base_at(Bw, gb + j - 1);
+        const U128 Eq = b == 0 ? P0 : (b == 1 ? P1 : (b == 2 ? P2 : P3));
+        const U128 D0 = u_or(u_or(u_xor(u_add(u_and(Eq, VP), VP), VP), Eq), VN);
+        const U128 HP = u_or(VN, u_not(u_or(D0, VP))), HN = u_and(D0, VP);
+        U128 X = u_shl1(HP); X.lo |= 1ull;                            // row 0 grows by one per column (global alignment)
+        VP = u_or(u_shl1(HN), u_not(u_or(D0, X))); VN = u_and(D0, X);
+        unsigned long long *c = cols + (int64_t)((j - 1) * 4) * nthreads;
+        c[0] = VP.lo; c[nthreads] = VP.hi; c[2 * nthreads] = VN.lo; c[3 * nthreads] = VN.hi;
+    }
+    auto column = [&](int j, U128 &vp, U128 &vn) {
+        if (j == 0) { vp = U128{~0ull, ~0ull}; vn = U128{0, 0}; return; }
+        const unsigned long long *c = cols + (int64_t)((j - 1) * 4) * nthreads;
+        vp = U128{c[0], c[nthreads]}; vn = U128{c[2 * nthreads], c[3 * nthreads]};
+    };
+    int i = n, j = m;
+    U128 vpj, vnj; column(m, vpj, vnj);
+    int c0 = m + u_popc_low(vpj, n) - u_popc_low(vnj, n);             // D[n][m]
+    const int total = c0;
+    for (;;) {
+        u32 dir; int nc0 = 0;
+        U128 vpl{0, 0}, vnl{0, 0};
+        if (i == 0 && j == 0) dir = 3u;
+        else if (i == 0) { dir = 2u; nc0 = j - 1; column(j - 1, vpl, vnl); }
+        else if (j == 0) { dir = 1u; nc0 = i - 1; }
+        else {
+            column(j - 1, vpl, vnl);
+            const int up = c0 - (u_bit(vpj, i - 1) - u_bit(vnj, i - 1));
+            const int left = (j - 1) + u_popc_low(vpl, i) - u_popc_low(vnl, i);
+            const int dg = left - (u_bit(vpl, i - 1) - u_bit(vnl, i - 1));
+            const int d = dg + (base_at(Aw, ga + i - 1) != base_at(Bw, gb + j - 1)), u = up + 1, l = left + 1;
+            int v = d; if (u < v) v = u; if (l < v) v = l;
+            dir = (v == d) ? 0u : ((v == u) ? 1u : 2u);
+            nc0 = dir == 0u ? dg : (dir == 1u ? up : left);
+        }
+        visit(dir, i, j, c0, nc0);
+        if (dir == 3u) break;
+        if (dir == 0u) { i--; j--; vpj = vpl; vnj = vnl; }
+        else if (dir == 1u) i--;
+        else { j--; vpj = vpl; vnj = vnl; }
+        c0 = nc0;
+    }
+    return total;
+}
+
 __global__ void __launch_bounds__(128) k_cons_vote_bv(const ConsTask *__restrict__ tasks, int64_t ntasks,
                                                       const dn_las_record *__restrict__ rec, const int32_t *__restrict__ la_target,
                                                       ConsGeom G, u32 *__restrict__ scratch, int32_t *__restrict__ cnt,
                                                       int32_t *__restrict__ ins, int32_t *__restrict__ insn, int32_t *__restrict__ cov) {
     const int64_t nthreads = (int64_t)gridDim.x * blockDim.x;
     const int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    unsigned long long *cols = (unsigned long long *)scratch + tid;      // word w of column j (1-based) at cols[((j - 1) * 4 + w) * nthreads]
+    unsigned long long *cols = (unsigned long long *)scratch + tid;
     for (int64_t task = tid; task < ntasks; task += nthreads) {
         const ConsTask T = tasks[task];
         const int n = T.alen, m = T.bb;
@@ -196,60 +257,18 @@ __global__ void __launch_bounds__(128) k_cons_vote_bv(const ConsTask *__restrict
         const int64_t vbase = G.vote_off[tg];
         const u32 *Aw = G.fwd, *Bw = (la.flags & DN_LAS_COMP) ? G.rc : G.fwd;
         const int64_t ga = G.off[la.aread] + T.ap, gb = G.off[la.bread] + T.bp;
-        U128 P0{0, 0}, P1{0, 0}, P2{0, 0}, P3{0, 0};                  // positions of each base in the A tile
-        for (int i = 0; i < n; i++) {
-            const int a = base_at(Aw, ga + i);
-            const unsigned long long bl = i < 64 ? 1ull << i : 0ull, bh = i < 64 ? 0ull : 1ull << (i - 64);
-            if (a == 0) { P0.lo |= bl; P0.hi |= bh; } else if (a == 1) { P1.lo |= bl; P1.hi |= bh; }
-            else if (a == 2) { P2.lo |= bl; P2.hi |= bh; } else { P3.lo |= bl; P3.hi |= bh; }
-        }
-        U128 VP{~0ull, ~0ull}, VN{0, 0};
-        for (int j = 1; j <= m; j++) {
-            const int b = base_at(Bw, gb + j - 1);
-            const U128 Eq = b == 0 ? P0 : (b == 1 ? P1 : (b == 2 ? P2 : P3));
-            const U128 D0 = u_or(u_or(u_xor(u_add(u_and(Eq, VP), VP), VP), Eq), VN);
-            const U128 HP = u_or(VN, u_not(u_or(D0, VP))), HN = u_and(D0, VP);
-            U128 X = u_shl1(HP); X.lo |= 1ull;                        // row 0 grows by one per column (global alignment)
-            VP = u_or(u_shl1(HN), u_not(u_or(D0, X))); VN = u_and(D0, X);
-            unsigned long long *c = cols + (int64_t)((j - 1) * 4) * nthreads;
-            c[0] = VP.lo; c[nthreads] = VP.hi; c[2 * nthreads] = VN.lo; c[3 * nthreads] = VN.hi;
-        }
-        auto column = [&](int j, U128 &vp, U128 &vn) {
-            if (j == 0) { vp = U128{~0ull, ~0ull}; vn = U128{0, 0}; return; }
-            const unsigned long long *c = cols + (int64_t)((j - 1) * 4) * nthreads;
-            vp = U128{c[0], c[nthreads]}; vn = U128{c[2 * nthreads], c[3 * nthreads]};
-        };
-        int i = n, j = m, pend = -1;
-        U128 vpj, vnj; column(m, vpj, vnj);
-        int c0 = m + u_popc_low(vpj, n) - u_popc_low(vnj, n);          // D[n][m]
-        while (i > 0 || j > 0) {
-            u32 dir; int bj = 0, nc0 = 0;
-            U128 vpl, vnl;
-            if (i == 0) { dir = 2u; bj = base_at(Bw, gb + j - 1); nc0 = j - 1; column(j - 1, vpl, vnl); }
-            else if (j == 0) { dir = 1u; nc0 = i - 1; }
-            else {
-                column(j - 1, vpl, vnl);
-                bj = base_at(Bw, gb + j - 1);
-                const int up = c0 - (u_bit(vpj, i - 1) - u_bit(vnj, i - 1));
-                const int left = (j - 1) + u_popc_low(vpl, i) - u_popc_low(vnl, i);
-                const int dg = left - (u_bit(vpl, i - 1) - u_bit(vnl, i - 1));
-                const int d = dg + (base_at(Aw, ga + i - 1) != bj), u = up + 1, l = left + 1;
-                int v = d; if (u < v) v = u; if (l < v) v = l;
-                dir = (v == d) ? 0u : ((v == u) ? 1u : 2u);
-                nc0 = dir == 0u ? dg : (dir == 1u ? up : left);
-            }
+        int pend = -1;                                               // first base (lowest j) of the insertion run being walked
+        bv_align(Aw, ga, n, Bw, gb, m, cols, nthreads, [&](u32 dir, int i, int j, int, int) {
             if (dir != 2u && pend >= 0) { atomicAdd(&ins[(vbase + T.ap + i) * 4 + pend], 1); atomicAdd(&insn[vbase + T.ap + i], 1); pend = -1; }
-            if (dir == 0u) { atomicAdd(&cnt[(vbase + T.ap + i - 1) * 5 + bj], 1); i--; j--; vpj = vpl; vnj = vnl; }
-            else if (dir == 1u) { atomicAdd(&cnt[(vbase + T.ap + i - 1) * 5 + 4], 1); i--; }
-            else { pend = bj; j--; vpj = vpl; vnj = vnl; }
-            c0 = nc0;
-        }
-        if (pend >= 0) { atomicAdd(&ins[(vbase + T.ap + i) * 4 + pend], 1); atomicAdd(&insn[vbase + T.ap + i], 1); }
+            if (dir == 0u) atomicAdd(&cnt[(vbase + T.ap + i - 1) * 5 + base_at(Bw, gb + j - 1)], 1);
+            else if (dir == 1u) atomicAdd(&cnt[(vbase + T.ap + i - 1) * 5 + 4], 1);
+            else if (dir == 2u) pend = base_at(Bw, gb + j - 1);
+        });
         for (int x = 0; x < n; x++) atomicAdd(&cov[vbase + T.ap + x], 1);
     }
 }
 
-// `daligner -B` bridges (specification: oracle/pile_oracle.c, orc_bridge): thread per bridge, the same bit-parallel DP over
+// `daligner -B` bridges (specification: oracle/pile_oracle.c, orc_bridge): thread per bridge, the same DP over
 // A[P.aepos, Q.abpos) x B[P.bepos, Q.bbpos); the traceback records, for every multiple of ts of A inside the bridge, the
 // B column and the cost at the path's FIRST cell on that row (the cell it leaves the row from, walking backwards).
 __global__ void __launch_bounds__(128) k_bridge(const BridgeTask *__restrict__ tasks, int64_t ntasks, const u32 *__restrict__ a_fwd,
@@ -260,57 +279,10 @@ __global__ void __launch_bounds__(128) k_bridge(const BridgeTask *__restrict__ t
     unsigned long long *cols = (unsigned long long *)scratch + tid;
     for (int64_t task = tid; task < ntasks; task += nthreads) {
         const BridgeTask T = tasks[task];
-        const int n = T.n, m = T.m;
-        const u32 *Aw = a_fwd, *Bw = T.comp ? b_rc : b_fwd;
-        const int64_t ga = T.ga, gb = T.gb;
-        U128 P0{0, 0}, P1{0, 0}, P2{0, 0}, P3{0, 0};
-        for (int i = 0; i < n; i++) {
-            const int a = base_at(Aw, ga + i);
-            const unsigned long long bl = i < 64 ? 1ull << i : 0ull, bh = i < 64 ? 0ull : 1ull << (i - 64);
-            if (a == 0) { P0.lo |= bl; P0.hi |= bh; } else if (a == 1) { P1.lo |= bl; P1.hi |= bh; }
-            else if (a == 2) { P2.lo |= bl; P2.hi |= bh; } else { P3.lo |= bl; P3.hi |= bh; }
-        }
-        U128 VP{~0ull, ~0ull}, VN{0, 0};
-        for (int j = 1; j <= m; j++) {
-            const int b = base_at(Bw, gb + j - 1);
-            const U128 Eq = b == 0 ? P0 : (b == 1 ? P1 : (b == 2 ? P2 : P3));
-            const U128 D0 = u_or(u_or(u_xor(u_add(u_and(Eq, VP), VP), VP), Eq), VN);
-            const U128 HP = u_or(VN, u_not(u_or(D0, VP))), HN = u_and(D0, VP);
-            U128 X = u_shl1(HP); X.lo |= 1ull;
-            VP = u_or(u_shl1(HN), u_not(u_or(D0, X))); VN = u_and(D0, X);
-            unsigned long long *c = cols + (int64_t)((j - 1) * 4) * nthreads;
-            c[0] = VP.lo; c[nthreads] = VP.hi; c[2 * nthreads] = VN.lo; c[3 * nthreads] = VN.hi;
-        }
-        auto column = [&](int j, U128 &vp, U128 &vn) {
-            if (j == 0) { vp = U128{~0ull, ~0ull}; vn = U128{0, 0}; return; }
-            const unsigned long long *c = cols + (int64_t)((j - 1) * 4) * nthreads;
-            vp = U128{c[0], c[nthreads]}; vn = U128{c[2 * nthreads], c[3 * nthreads]};
-        };
-        int i = n, j = m, k = T.nrow;
-        U128 vpj, vnj; column(m, vpj, vnj);
-        int c0 = m + u_popc_low(vpj, n) - u_popc_low(vnj, n);
-        total[task] = c0;
-        while (i > 0 || j > 0) {
-            u32 dir; int nc0 = 0;
-            U128 vpl, vnl;
-            if (i == 0) { dir = 2u; nc0 = j - 1; column(j - 1, vpl, vnl); }
-            else if (j == 0) { dir = 1u; nc0 = i - 1; }
-            else {
-                column(j - 1, vpl, vnl);
-                const int up = c0 - (u_bit(vpj, i - 1) - u_bit(vnj, i - 1));
-                const int left = (j - 1) + u_popc_low(vpl, i) - u_popc_low(vnl, i);
-                const int dg = left - (u_bit(vpl, i - 1) - u_bit(vnl, i - 1));
-                const int d = dg + (base_at(Aw, ga + i - 1) != base_at(Bw, gb + j - 1)), u = up + 1, l = left + 1;
-                int v = d; if (u < v) v = u; if (l < v) v = l;
-                dir = (v == d) ? 0u : ((v == u) ? 1u : 2u);
-                nc0 = dir == 0u ? dg : (dir == 1u ? up : left);
-            }
-            if (dir != 2u && (T.a0 + i) % ts == 0) { k--; rows[T.row_off + k] = make_int2(j, c0); }
-            if (dir == 0u) { i--; j--; vpj = vpl; vnj = vnl; }
-            else if (dir == 1u) i--;
-            else { j--; vpj = vpl; vnj = vnl; }
-            c0 = nc0;
-        }
+        int k = T.nrow;
+        total[task] = bv_align(a_fwd, T.ga, T.n, T.comp ? b_rc : b_fwd, T.gb, T.m, cols, nthreads, [&](u32 dir, int i, int j, int d_here, int) {
+            if (dir < 2u && (T.a0 + i) % ts == 0) { k--; rows[T.row_off + k] = make_int2(j, d_here); }
+        });
     }
 }
 
@@ -360,7 +332,7 @@ __global__ void __launch_bounds__(128) k_tr_tiles(const ConsTask *__restrict__ t
                                                   int32_t *__restrict__ tcost) {
     const int64_t nthreads = (int64_t)gridDim.x * blockDim.x;
     const int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    u32 *dirs = scratch + tid;
+    unsigned long long *cols = (unsigned long long *)scratch + tid;
     for (int64_t task = tid; task < ntasks; task += nthreads) {
         const ConsTask T = tasks[task];
         const int n = T.alen, m = T.bb;
@@ -386,45 +358,20 @@ __global__ void __launch_bounds__(128) k_tr_tiles(const ConsTask *__restrict__ t
         }
         const u32 *Aw = G.a_fwd, *Bw = comp ? G.b_rc : G.b_fwd;
         const int64_t ga = G.a_off[la.aread] + T.ap, gb = G.b_off[la.bread] + T.bp;
-        unsigned char bq[256], row[256];
-        for (int j = 0; j < m; j++) bq[j] = (unsigned char)base_at(Bw, gb + j);
-        for (int j = 0; j <= m; j++) row[j] = (unsigned char)j;
-        const int wpr = (m + 16) >> 4;
-        for (int i = 1; i <= n; i++) {
-            const int ai = base_at(Aw, ga + i - 1);
-            int diag = row[0]; row[0] = (unsigned char)i;
-            int left = i;
-            u32 word = 0;
-            for (int j = 1; j <= m; j++) {
-                const int up = row[j];
-                const int d = diag + (ai != bq[j - 1]), u = up + 1, l = left + 1;
-                int v = d; if (u < v) v = u; if (l < v) v = l;
-                const u32 dir = (v == d) ? 0u : ((v == u) ? 1u : 2u);
-                word |= dir << ((j & 15) << 1);
-                if ((j & 15) == 15 || j == m) { dirs[(int64_t)((i - 1) * wpr + (j >> 4)) * nthreads] = word; word = 0; }
-                row[j] = (unsigned char)v; diag = up; left = v;
-            }
-        }
-        const int total = n == 0 ? m : row[m];
-        int i = n, j = m, cend = 0;
-        for (;;) {
-            u32 dir;
-            if (i == 0 && j == 0) dir = 3u; else if (i == 0) dir = 2u; else if (j == 0) dir = 1u;
-            else dir = (dirs[(int64_t)((i - 1) * wpr + (j >> 4)) * nthreads] >> ((j & 15) << 1)) & 3u;
+        // the crossings of a non-complemented tile carry costs from the tile's start (d_here); those of a complemented one
+        // costs from its end (D[n][m] - d_next): D[n][m] is added once the walk has returned it
+        const int total = bv_align(Aw, ga, n, Bw, gb, m, cols, nthreads, [&](u32 dir, int i, int j, int d_here, int d_next) {
             const int x = bp + j;
             if (!comp && (dir == 0u || dir == 2u) && j > 0 && x % ts == 0 && x > lo && x < hi) {      // leaving column j: its last (lowest) cell
-                if (nc < kmax) cr[nc] = make_int4(x, T.ap + i, total - cend, 0);
+                if (nc < kmax) cr[nc] = make_int4(x, T.ap + i, d_here, 0);
                 nc++;
             }
-            if (dir == 3u) break;
-            if (dir == 0u) { cend += (base_at(Aw, ga + i - 1) != (int)bq[j - 1]); i--; j--; }
-            else if (dir == 1u) { cend += 1; i--; }
-            else { cend += 1; j--; }
-            if (comp && (dir == 0u || dir == 2u)) {                                                      // entering column j: its first (highest) cell
-                const int xn = bp + j;
-                if ((lb - xn) % ts == 0 && xn > lo && xn < hi) { if (nc < kmax) cr[nc] = make_int4(xn, T.ap + i, cend, 0); nc++; }
+            if (comp && (dir == 0u || dir == 2u)) {                                                  // entering column j - 1: its first (highest) cell
+                const int xn = bp + j - 1, in = dir == 0u ? i - 1 : i;
+                if ((lb - xn) % ts == 0 && xn > lo && xn < hi) { if (nc < kmax) cr[nc] = make_int4(xn, T.ap + in, -d_next, 0); nc++; }
             }
-        }
+        });
+        if (comp) for (int q = 0; q < nc && q < kmax; q++) cr[q].z += total;
         ncross[task] = nc; tcost[task] = total;
     }
 }
