@@ -212,3 +212,58 @@ def test_bridging_by_hand():
         rec[1]["tlen"] = 2 * n2
         out, _, _, nb = oracle.bridge(aoff, A, aoff, A, rec, np.array([0, 2], np.int64), tr[:2 + 2 * n2], ts)
         assert nb == 0 and len(out) == 2
+
+
+def test_bridging_random_gaps_against_independent_dp():
+    """orc_bridge over seeded random gap geometries and three trace spacings: merged coordinates, diffs and every tile against
+    the path of an independent DP (first arrival on each trace-point row of A)."""
+    rng = np.random.default_rng(2024)
+    done = 0
+    for case in range(60):
+        ts = int(rng.choice([40, 100, 126]))
+        p_end = int(rng.integers(150, 400)); q_len = int(rng.integers(150, 400))
+        gap_a = int(rng.integers(0, 129)); gap_b = int(rng.integers(0, 251))
+        if abs(gap_a - gap_b) * 20 > max(320, 6 * max(gap_a, gap_b)):
+            gap_b = max(0, min(250, gap_a + int(rng.integers(-10, 11))))            # keep the pair bridgeable
+        A = rng.integers(0, 4, p_end + gap_a + q_len).astype(np.uint8)
+        # the bridged stretch of B: a noisy copy of A's (some bridges cheap, some junk)
+        core = A[p_end:p_end + gap_a]
+        junk = rng.integers(0, 4, gap_b).astype(np.uint8)
+        if gap_a and gap_b and case % 2:
+            junk[:min(gap_a, gap_b)] = core[:min(gap_a, gap_b)]
+            flip = rng.random(gap_b) < 0.15; junk[flip] = (junk[flip] + 1) % 4
+        B = np.concatenate([A[:p_end], junk, A[p_end + gap_a:]])
+        aoff = np.array([0, len(A)], np.int64); boff = np.array([0, len(B)], np.int64)
+
+        def exact(ab, ae, bb):
+            tiles, p = [], ab
+            while p < ae:
+                e = min((p // ts + 1) * ts, ae); tiles.append((0, e - p)); p = e
+            return dict(abpos=ab, aepos=ae, bbpos=bb, bepos=bb + (ae - ab), diffs=0, tlen=2 * len(tiles)), tiles
+        P, tp = exact(0, p_end, 0)
+        Q, tq = exact(p_end + gap_a, len(A), p_end + gap_b)
+        rec = np.zeros(2, oracle.LAS40)
+        for i, r in enumerate((P, Q)):
+            for f, v in r.items():
+                rec[i][f] = v
+        trace = np.array([x for t in tp + tq for x in t], np.uint16)
+        out, otoff, otr, nb = oracle.bridge(aoff, A, boff, B, rec, np.array([0, 2 * len(tp)], np.int64), trace, ts)
+        assert nb == 1 and len(out) == 1, (case, gap_a, gap_b)
+        ed, first = _edit_path(A[p_end:p_end + gap_a], B[p_end:p_end + gap_b])
+        o = out[0]
+        assert (o["abpos"], o["aepos"], o["bbpos"], o["bepos"], o["diffs"]) == (0, len(A), 0, len(B), ed)
+        cum = []
+        for g in range(ts, len(A), ts):
+            if g <= p_end:
+                cum.append((g, 0))
+            elif g <= p_end + gap_a:
+                j, d = first[g - p_end]; cum.append((p_end + j, d))
+            else:
+                cum.append((g - gap_a + gap_b, ed))
+        cum.append((len(B), ed))
+        exp, pb, pd = [], 0, 0
+        for b, d in cum:
+            exp += [d - pd, b - pb]; pb, pd = b, d
+        assert otr.tolist() == exp, (case, ts, p_end, gap_a, gap_b)
+        done += 1
+    assert done == 60
