@@ -267,3 +267,14 @@ def test_bridging_random_gaps_against_independent_dp():
         assert otr.tolist() == exp, (case, ts, p_end, gap_a, gap_b)
         done += 1
     assert done == 60
+
+
+def test_bit_parallel_dp_reproduces_the_cell_dp(tmp_path):
+    """The identity the CUDA kernels' bit-parallel DP rests on (tests/cpp/bitparallel_dp_check.c): all cell values and
+    every traceback direction of the plain unit-cost DP, from 128-bit vertical-delta columns."""
+    import subprocess
+    src = os.path.join(os.path.dirname(__file__), "cpp", "bitparallel_dp_check.c")
+    exe = str(tmp_path / "bvcheck")
+    subprocess.check_call(["gcc", "-O2", "-o", exe, src])
+    r = subprocess.run([exe, "20000"], capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0 and "all ok" in r.stdout, r.stdout
