@@ -642,8 +642,19 @@ def main():
                             "peak_source": peak_src,
                             "note": "instruction-issue-bound kernel (85% issue slots busy, IPC 3.39, 36 resident warps per SM = the measured optimum, DRAM 0.2%, L1 hit rate 97%): the HBM fraction says nothing about its quality; "
                                     "algorithmic bytes = packed sequence under each alignment + records + traces; measured DRAM traffic is BELOW them because the packed blocks stay in L2"},
-               "roofline_seed": {"kernels": "A tuples+radix, lookup join, segment sort, band filter, retire, final ordering", "bound": "hbm", "achieved": seed_gbs, "peak": peak,
-                                 "unit": "GB/s", "frac": seed_gbs / peak},
+               "roofline_seed": {"kernels": "A tuples + bucket index, lookup join, segment sort, band filter, retire, final ordering", "bound": "hbm", "achieved": seed_gbs, "peak": peak,
+                                 "unit": "GB/s", "frac": seed_gbs / peak,
+                                 # the largest kernels of the seeding half, per launch, from the committed ncu --set full captures of this workload
+                                 # (profiles/r02_f_prof_extend32_lookup_final.txt, r02_f_prof_scan_segsort_retire_final.txt, r02_g_prof_bucket_index_cover_scan_final.txt):
+                                 # algorithmic = bytes the kernel has to move once; dram = dram__bytes_read.sum + dram__bytes_write.sum
+                                 "per_kernel_ncu": [
+                                     {"kernel": "k_lookup_count_p", "ms": 1.52, "algorithmic_mb": 1500, "dram_mb": 2675, "l2_sectors_m": 450,
+                                      "note": "213 M filter probes (one random 32-byte L2 sector each, both strands per probe) + ~27 M index walks that miss L2"},
+                                     {"kernel": "k_lookup_emit_p (x2, one per strand)", "ms": 0.40, "algorithmic_mb": 620, "dram_mb": 1046, "note": "re-walks the index for the words with hits, writes 16-byte hits"},
+                                     {"kernel": "k_scan_chained<CoverScan>", "ms": 0.315, "algorithmic_mb": 637, "dram_mb": 599, "note": "22.8 M hits: 16 B in, 12 B out; streaming at 1.9 TB/s"},
+                                     {"kernel": "k_bucket_scatter", "ms": 0.274, "algorithmic_mb": 160, "dram_mb": 617, "note": "8-byte stores into random 32-byte sectors of an 80 MB array: read-modify-write in DRAM"},
+                                     {"kernel": "k_retire", "ms": 0.202, "algorithmic_mb": 660, "dram_mb": 654, "note": "streaming at 3.2 TB/s"},
+                                     {"kernel": "k_bucket_order", "ms": 0.126, "algorithmic_mb": 150, "dram_mb": 186}]},
                "stage_ms_per_step": {"seed": seed_ms / args.steps, "extend": ext_ms / args.steps}}
         # CPU baseline beside it: the oracle port on a bounded sample, all host cores
         if world == 1:
