@@ -255,6 +255,11 @@ C4_GAPS = 2000          # configs[3] sampled: 50 000 gaps / 3 Gbp scaled to C4_G
 C4_BATCH = 100          # pile-ups per dn_process_pileups call (the reference runs batch_size = 50 per job, Snakefile:626-673; larger batches cost more per pile-up: the index of the batch's flanking contigs outgrows L2)
 
 
+def c4_scaffolds_of(rank, world, n_sc):
+    """Scaffolds (10 gaps each) of one rank: contiguous ranges, every scaffold on exactly one rank, sizes within one of each other."""
+    return [s for s in range(n_sc) if s * world // n_sc == rank]
+
+
 def run_c4(args, rank, world, dev, barrier, dist, torch, ngaps):
     """configs[3], sampled: the pile-ups of `ngaps` gaps dealt contiguously over the ranks (by scaffold: a pile-up's flanking
     contigs travel with it), every rank runs its pile-ups through dn_process_pileups in batches, the insertion payloads
@@ -262,7 +267,7 @@ def run_c4(args, rank, world, dev, barrier, dist, torch, ngaps):
     `merge-insertions` collects from files (commands/mergeInsertions.d).  Strong scaling: the job is fixed, N ranks share it."""
     from dentist_b200 import dazzler
     n_sc = max(world, ngaps // 10)
-    mine = [s for s in range(n_sc) if s * world // n_sc == rank]                     # contiguous scaffold ranges
+    mine = c4_scaffolds_of(rank, world, n_sc)
     t0 = time.perf_counter()
     scs, gaps, batches, first_gap = [], [], [], 0
     for s in range(n_sc):

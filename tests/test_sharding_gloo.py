@@ -67,3 +67,16 @@ def test_gather_las_world2_gloo():
     for i in range(len(mrec)):
         t = mtr[mtoff[i]:mtoff[i] + mrec[i]["tlen"]]
         assert int(t[0::2].sum()) == mrec[i]["diffs"]
+
+
+def test_bench_deals_blocks_and_scaffolds_once():
+    """bench.py's dealing of configs[2] read blocks and configs[3] scaffolds over the ranks: contiguous, complete, disjoint, balanced."""
+    import bench
+    for world in (1, 2, 3, 4, 8):
+        for n in (8, 15, 200, 201):
+            for deal in (bench.c3_blocks_of, bench.c4_scaffolds_of):
+                parts = [list(deal(r, world, n)) for r in range(world)]
+                flat = [x for p in parts for x in p]
+                assert flat == list(range(n)), (deal.__name__, world, n)
+                sizes = [len(p) for p in parts]
+                assert max(sizes) - min(sizes) <= 1 or deal is bench.c3_blocks_of
