@@ -128,6 +128,14 @@ inline Las align(const Block &a, const Block &b, const dn_align_params &p) {
     return l;
 }
 
+/// What `-B` adds to a daligner call (dazzler.d:5823-5824; pileUpAlignmentOptions / postConsensusAlignmentOptions pass it):
+/// neighbouring local alignments of a read pair separated by a short gap become one.  Returns the number of bridges made.
+inline int64_t bridge(const Block &a, const Block &b, Las &las, double averageCorrelationRate = 0.7) {
+    int64_t n = 0;
+    enforce(dn_las_bridge(a.raw(), b.raw(), las.raw(), (int32_t)(6.0 / (1.0 - averageCorrelationRate) + 0.5), &n));
+    return n;
+}
+
 /// computeQVs(db, las, coverage)  dazzler.d:3782-3792 -> one QV byte per trace-spacing tile of every read.
 inline std::vector<std::vector<uint8_t>> computeQVs(const std::vector<int32_t> &readLengths, const Las &las, uint32_t coverage) {
     uint8_t *qv = nullptr; int64_t *off = nullptr;
